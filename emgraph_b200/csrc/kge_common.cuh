@@ -1,0 +1,140 @@
+// Shared device/host helpers for the KGE hot-path kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/kge_b200.h"
+
+#define KGE_WARP 32
+
+void kge_set_error(const char* fmt, ...);
+
+#define KGE_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            kge_set_error("%s:%d CUDA error %d (%s) in `%s`", __FILE__, __LINE__, (int)_e,    \
+                          cudaGetErrorString(_e), #expr);                                     \
+            return -2;                                                                        \
+        }                                                                                     \
+    } while (0)
+
+#define KGE_REQUIRE(cond, ...)                                                                \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            kge_set_error(__VA_ARGS__);                                                       \
+            return -1;                                                                        \
+        }                                                                                     \
+    } while (0)
+
+// grow-only device buffer owned by the ctx
+struct KgeBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) {
+            KGE_CUDA_CHECK(cudaDeviceSynchronize());
+            KGE_CUDA_CHECK(cudaFree(p));
+            p = nullptr;
+            cap = 0;
+        }
+        size_t want = bytes + bytes / 8 + 256;
+        KGE_CUDA_CHECK(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct kge_ctx {
+    int device = 0;
+    int sm_count = 148;
+    // training workspace
+    KgeBuf keys_in, keys_out, vals_in, vals_out, sort_tmp;
+    KgeBuf repl, keep, grad_rows, loss_part, neg_scores;
+    // ranking workspace
+    KgeBuf q_fold, q_hi, q_lo, e_hi, e_lo, pos_q, excl_lo, excl_hi;
+    // filter index (sorted, deduplicated composites and the entity column of each)
+    KgeBuf f_sp_comp, f_po_comp, f_sp_ent, f_po_ent, f_tmp, f_tmp2, f_count;
+    int64_t f_n_sp = 0, f_n_po = 0;  // capacity (pre-unique) sizes
+    int64_t f_E = 0, f_R = 0;
+    bool    f_valid = false;
+    // cached 3xTF32 split of the local entity shard (ranking)
+    const float* split_src = nullptr;
+    int64_t split_rows = 0;
+    int     split_K = 0;
+    uint64_t split_epoch = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// table access (row-range sharded over peers)
+// ------------------------------------------------------------------------------------------
+struct TableView {
+    float*  shard[KGE_MAX_SHARDS];
+    int64_t rows_per_shard;
+    int32_t n_shards;
+    int32_t K;
+};
+
+static inline TableView make_view(const kge_table& t) {
+    TableView v;
+    for (int i = 0; i < KGE_MAX_SHARDS; ++i) v.shard[i] = t.shard[i];
+    v.rows_per_shard = t.rows_per_shard > 0 ? t.rows_per_shard : t.rows;
+    v.n_shards = t.n_shards;
+    v.K = t.K;
+    return v;
+}
+
+__device__ __forceinline__ float* table_row(const TableView& t, int64_t row) {
+    if (t.n_shards == 1) return t.shard[0] + row * (int64_t)t.K;
+    int s = (int)(row / t.rows_per_shard);
+    return t.shard[s] + (row - (int64_t)s * t.rows_per_shard) * (int64_t)t.K;
+}
+
+// ------------------------------------------------------------------------------------------
+// warp helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// tf.cast(score * 1e5, tf.int32): fp32 multiply, truncate toward zero
+// (reference models/EmbeddingModel.py:2010-2014; utils/constants.py:87)
+__device__ __forceinline__ int quantise_score(float s) {
+    return __float2int_rz(__fmul_rn(s, 1e5f));
+}
+
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011), one call per negative.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static inline bool model_is_complex(int model) { return model == KGE_COMPLEX || model == KGE_HOLE; }
+static inline int  model_row_width(int model, int k) { return model_is_complex(model) ? 2 * k : k; }

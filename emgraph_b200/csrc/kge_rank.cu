@@ -1,0 +1,526 @@
+// Filtered ranking for sm_100a: device filter index, query folding, all-entity sweep with the
+// x1e5 int quantisation, in-kernel filter and fused rank counting.
+//
+// Replaces reference evaluation/protocol.py:726-979 (evaluate_performance), :448-528
+// (generate_corruptions_for_eval), models/EmbeddingModel.py:1845-2033 (eval graph,
+// perform_comparision), datasets/sqlite_adapter.py:449-508 (filter queries).
+//
+// The [T, 2E] score matrix is never materialised: every (query tile x entity tile) is scored in
+// registers, quantised, compared with the positive's quantised score and reduced to four counters
+// per (test triple, side): gt, eq over all candidates and gt, eq over filtered candidates.  The
+// candidate that IS the test triple (e == o on the object sweep, e == s on the subject sweep) is
+// skipped by the sweep and added analytically in kge_rank_finalize (its score equals the
+// positive's by construction in the reference, models/EmbeddingModel.py:1861-1866).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
+#include "kge_common.cuh"
+
+int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ, int64_t T, const float* ent_local,
+                      int64_t row_begin, int64_t row_end, const int32_t* test, const int32_t* pos_q,
+                      const int32_t* excl_lo, const int32_t* excl_hi, const int32_t* sp_ent, const int32_t* po_ent,
+                      int side_mask, int32_t* counts, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// filter index
+// ------------------------------------------------------------------------------------------------
+__global__ void kge_filter_comp_kernel(const int32_t* __restrict__ tri, int64_t F, int64_t E, int64_t R,
+                                       uint64_t* __restrict__ sp, uint64_t* __restrict__ po) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < F; t += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t s = (uint64_t)tri[3 * t], p = (uint64_t)tri[3 * t + 1], o = (uint64_t)tri[3 * t + 2];
+        sp[t] = (s * (uint64_t)R + p) * (uint64_t)E + o;
+        po[t] = (o * (uint64_t)R + p) * (uint64_t)E + s;
+    }
+}
+
+__global__ void kge_filter_ent_kernel(const uint64_t* __restrict__ comp, const int32_t* __restrict__ cnt, int64_t E,
+                                      int32_t* __restrict__ ent) {
+    int64_t n = *cnt;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        ent[t] = (int32_t)(comp[t] % (uint64_t)E);
+}
+
+extern "C" int kge_filter_clear(kge_ctx* ctx) {
+    KGE_REQUIRE(ctx != nullptr, "kge_filter_clear: null ctx");
+    ctx->f_valid = false;
+    return 0;
+}
+
+extern "C" int kge_filter_build(kge_ctx* ctx, const int32_t* triples, int64_t F, int64_t E, int64_t R, void* stream) {
+    KGE_REQUIRE(ctx != nullptr, "kge_filter_build: null ctx");
+    KGE_REQUIRE(F >= 0 && E > 0 && R > 0, "kge_filter_build: bad sizes");
+    KGE_REQUIRE(F < (int64_t)INT32_MAX, "kge_filter_build: too many filter triples");
+    KGE_REQUIRE((double)E * (double)R * (double)E < 9.0e18, "kge_filter_build: E*R*E overflows the 64-bit composite key");
+    cudaStream_t st = (cudaStream_t)stream;
+    ctx->f_E = E;
+    ctx->f_R = R;
+    if (ctx->f_count.reserve(4 * sizeof(int32_t))) return -2;
+    KGE_CUDA_CHECK(cudaMemsetAsync(ctx->f_count.p, 0, 4 * sizeof(int32_t), st));
+    ctx->f_valid = true;
+    ctx->f_n_sp = ctx->f_n_po = F;
+    if (F == 0) return 0;
+    KGE_REQUIRE(triples != nullptr, "kge_filter_build: null triples");
+    size_t b8 = (size_t)F * sizeof(uint64_t);
+    if (ctx->f_sp_comp.reserve(b8) || ctx->f_po_comp.reserve(b8) || ctx->f_tmp.reserve(b8) || ctx->f_tmp2.reserve(b8)) return -2;
+    if (ctx->f_sp_ent.reserve((size_t)F * 4) || ctx->f_po_ent.reserve((size_t)F * 4)) return -2;
+    int threads = 256;
+    int blocks = (int)std::min<int64_t>((F + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
+    kge_filter_comp_kernel<<<blocks, threads, 0, st>>>(triples, F, E, R, ctx->f_tmp.as<uint64_t>(), ctx->f_tmp2.as<uint64_t>());
+    KGE_CUDA_CHECK(cudaGetLastError());
+    int end_bit = 1;
+    {
+        double top = (double)E * (double)R * (double)E;
+        while (end_bit < 64 && ldexp(1.0, end_bit) < top) ++end_bit;
+    }
+    int32_t* cnt = ctx->f_count.as<int32_t>();
+    for (int which = 0; which < 2; ++which) {
+        uint64_t* raw = which == 0 ? ctx->f_tmp.as<uint64_t>() : ctx->f_tmp2.as<uint64_t>();
+        uint64_t* dst = which == 0 ? ctx->f_sp_comp.as<uint64_t>() : ctx->f_po_comp.as<uint64_t>();
+        int32_t* ent = which == 0 ? ctx->f_sp_ent.as<int32_t>() : ctx->f_po_ent.as<int32_t>();
+        // sort into dst, then unique back into raw, then copy raw->dst
+        size_t tb = 0, tb2 = 0;
+        KGE_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tb, raw, dst, (int)F, 0, end_bit, st));
+        KGE_CUDA_CHECK(cub::DeviceSelect::Unique(nullptr, tb2, dst, raw, cnt + which, (int)F, st));
+        if (ctx->sort_tmp.reserve(std::max(tb, tb2))) return -2;
+        KGE_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, tb, raw, dst, (int)F, 0, end_bit, st));
+        KGE_CUDA_CHECK(cub::DeviceSelect::Unique(ctx->sort_tmp.p, tb2, dst, raw, cnt + which, (int)F, st));
+        KGE_CUDA_CHECK(cudaMemcpyAsync(dst, raw, b8, cudaMemcpyDeviceToDevice, st));
+        kge_filter_ent_kernel<<<blocks, threads, 0, st>>>(dst, cnt + which, E, ent);
+        KGE_CUDA_CHECK(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int64_t kge_filter_size_sync(kge_ctx* ctx) {
+    if (!ctx || !ctx->f_valid || !ctx->f_count.p) return 0;
+    int32_t c[2] = {0, 0};
+    if (cudaMemcpy(c, ctx->f_count.p, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    return c[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-test-triple preparation: positive score (normal fp32 _fn), folded queries, exclusion ranges
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t lower_bound_u64(const uint64_t* __restrict__ a, int32_t n, uint64_t key) {
+    int32_t lo = 0, hi = n;
+    while (lo < hi) {
+        int32_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+struct PrepParams {
+    int model, k;
+    TableView ent;
+    const float* rel;
+    const int32_t* test;
+    int64_t T;
+    int filtered;
+    const uint64_t* sp_comp;
+    const uint64_t* po_comp;
+    const int32_t* f_cnt;
+    int64_t E, R;
+    float* q;         // [2T,K]: rows [0,T) object-sweep queries, [T,2T) subject-sweep queries
+    int32_t* pos_q;   // [T] quantised positive score
+    int32_t* excl_lo; // [2T]
+    int32_t* excl_hi; // [2T]
+};
+
+__global__ void kge_rank_prepare_kernel(PrepParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= P.T) return;
+    const int K = P.ent.K, k = P.k, model = P.model;
+    const int32_t si = P.test[3 * t], pi = P.test[3 * t + 1], oi = P.test[3 * t + 2];
+    const float* s = table_row(P.ent, si);
+    const float* p = P.rel + (size_t)pi * K;
+    const float* o = table_row(P.ent, oi);
+    float* qo = P.q + (size_t)t * K;
+    float* qs = P.q + (size_t)(P.T + t) * K;
+    float acc = 0.f;
+    const float hs = model == KGE_HOLE ? 2.0f / (float)k : 1.0f;
+    if (model == KGE_TRANSE_L1 || model == KGE_TRANSE_L2) {
+        for (int c = lane; c < K; c += 32) {
+            float sv = s[c], pv = p[c], ov = o[c];
+            qo[c] = sv + pv;   // S_o[e] = -|| (s+p) - e ||
+            qs[c] = ov - pv;   // S_s[e] = -|| e - (o-p) ||
+            float u = sv + pv - ov;
+            acc = model == KGE_TRANSE_L1 ? acc + fabsf(u) : fmaf(u, u, acc);
+        }
+        acc = warp_sum(acc);
+        acc = model == KGE_TRANSE_L1 ? -acc : -sqrtf(acc);
+    } else if (model == KGE_DISTMULT) {
+        for (int c = lane; c < K; c += 32) {
+            float sv = s[c], pv = p[c], ov = o[c];
+            qo[c] = sv * pv;
+            qs[c] = pv * ov;
+            acc = fmaf(sv * pv, ov, acc);
+        }
+        acc = warp_sum(acc);
+    } else {
+        for (int c = lane; c < k; c += 32) {
+            float sr = s[c], si2 = s[c + k], pr = p[c], pim = p[c + k], orr = o[c], oim = o[c + k];
+            float a = pr * sr - pim * si2, b = pr * si2 + pim * sr;
+            qo[c] = hs * a;
+            qo[c + k] = hs * b;
+            qs[c] = hs * (pr * orr + pim * oim);
+            qs[c + k] = hs * (pr * oim - pim * orr);
+            acc = fmaf(a, orr, acc);
+            acc = fmaf(b, oim, acc);
+        }
+        acc = hs * warp_sum(acc);
+    }
+    if (lane == 0) P.pos_q[t] = quantise_score(acc);
+    if (lane < 2) {
+        int32_t lo = 0, hi = 0;
+        if (P.filtered) {
+            const uint64_t* comp = lane == 0 ? P.sp_comp : P.po_comp;
+            int32_t n = P.f_cnt[lane];
+            uint64_t a = (uint64_t)(lane == 0 ? si : oi);
+            uint64_t prefix = a * (uint64_t)P.R + (uint64_t)pi;
+            lo = lower_bound_u64(comp, n, prefix * (uint64_t)P.E);
+            hi = lower_bound_u64(comp, n, (prefix + 1) * (uint64_t)P.E);
+        }
+        P.excl_lo[(int64_t)lane * P.T + t] = lo;
+        P.excl_hi[(int64_t)lane * P.T + t] = hi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 CUDA-core sweep (all models; the only path for TransE, whose L1/L2 distance has no MMA form)
+// ------------------------------------------------------------------------------------------------
+struct SweepParams {
+    int model;
+    int K;
+    const float* q;          // [NQ,K]
+    int64_t NQ, T;
+    const float* ent_local;  // [row_end-row_begin, K]
+    int64_t row_begin, row_end;
+    const int32_t* test;
+    const int32_t* pos_q;
+    const int32_t* excl_lo;
+    const int32_t* excl_hi;
+    const int32_t* sp_ent;
+    const int32_t* po_ent;
+    int64_t chunk;           // entities per blockIdx.y
+    int64_t q_row0;          // first query row handled (side selection)
+    int64_t q_rows;          // number of query rows handled
+    int32_t* counts;         // [T,2,4]
+};
+
+#define SW_BM 64
+#define SW_BN 64
+#define SW_BK 16
+
+template <int MODE>  // 0 dot, 1 L1, 2 L2
+__global__ void __launch_bounds__(256) kge_rank_sweep_kernel(SweepParams P) {
+    __shared__ float Qs[SW_BK][SW_BM + 4];
+    __shared__ float Es[SW_BK][SW_BN + 4];
+    __shared__ unsigned long long s_mask[SW_BM];
+    __shared__ int32_t s_cur[SW_BM], s_hi[SW_BM], s_self[SW_BM], s_posq[SW_BM];
+    __shared__ const int32_t* s_list[SW_BM];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = P.q_row0 + (int64_t)blockIdx.x * SW_BM;
+    const int64_t m_end = P.q_row0 + P.q_rows;
+    const int64_t e0 = P.row_begin + (int64_t)blockIdx.y * P.chunk;
+    const int64_t e1 = min(P.row_end, e0 + P.chunk);
+    if (e0 >= e1) return;
+    const int K = P.K;
+
+    if (tid < SW_BM) {
+        int64_t r = m0 + tid;
+        int32_t cur = 0, hi = 0, self = -1, pq = 0;
+        const int32_t* list = nullptr;
+        if (r < m_end) {
+            int side = r >= P.T ? 1 : 0;
+            int64_t t = r - (int64_t)side * P.T;
+            self = side == 0 ? P.test[3 * t + 2] : P.test[3 * t + 0];
+            pq = P.pos_q[t];
+            list = side == 0 ? P.sp_ent : P.po_ent;
+            int32_t lo = P.excl_lo[r];
+            hi = P.excl_hi[r];
+            // first list entry >= e0
+            int32_t a = lo, b = hi;
+            while (a < b) {
+                int32_t mid = (a + b) >> 1;
+                if ((int64_t)list[mid] < e0) a = mid + 1;
+                else b = mid;
+            }
+            cur = a;
+        }
+        s_cur[tid] = cur;
+        s_hi[tid] = hi;
+        s_self[tid] = self;
+        s_posq[tid] = pq;
+        s_list[tid] = list;
+    }
+    int cnt[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cnt[i][c] = 0;
+
+    // loader mapping: 256 threads x float4 = 64 rows x 16 floats
+    const int lr = tid >> 2, lc = (tid & 3) * 4;
+
+    for (int64_t n0 = e0; n0 < e1; n0 += SW_BN) {
+        __syncthreads();
+        if (tid < SW_BM) {
+            unsigned long long mk = 0ull;
+            int32_t cur = s_cur[tid], hi = s_hi[tid];
+            const int32_t* list = s_list[tid];
+            while (cur < hi) {
+                int64_t e = list[cur];
+                if (e >= n0 + SW_BN) break;
+                mk |= 1ull << (int)(e - n0);
+                ++cur;
+            }
+            s_cur[tid] = cur;
+            s_mask[tid] = mk;
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int k0 = 0; k0 < K; k0 += SW_BK) {
+            float qv[4] = {0.f, 0.f, 0.f, 0.f}, ev[4] = {0.f, 0.f, 0.f, 0.f};
+            {
+                int64_t r = m0 + lr;
+                if (r < m_end) {
+                    const float* src = P.q + (size_t)r * K + k0 + lc;
+                    if ((K & 3) == 0 && k0 + lc + 3 < K) {
+                        float4 v = *reinterpret_cast<const float4*>(src);
+                        qv[0] = v.x; qv[1] = v.y; qv[2] = v.z; qv[3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+                            if (k0 + lc + x < K) qv[x] = src[x];
+                    }
+                }
+                int64_t e = n0 + lr;
+                if (e < e1) {
+                    const float* src = P.ent_local + (size_t)(e - P.row_begin) * K + k0 + lc;
+                    if ((K & 3) == 0 && k0 + lc + 3 < K) {
+                        float4 v = *reinterpret_cast<const float4*>(src);
+                        ev[0] = v.x; ev[1] = v.y; ev[2] = v.z; ev[3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+                            if (k0 + lc + x < K) ev[x] = src[x];
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                Qs[lc + x][lr] = qv[x];
+                Es[lc + x][lr] = ev[x];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < SW_BK; ++kk) {
+                float4 a4 = *reinterpret_cast<const float4*>(&Qs[kk][ty * 4]);
+                float4 b4 = *reinterpret_cast<const float4*>(&Es[kk][tx * 4]);
+                float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (MODE == 0) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                        else if (MODE == 1) acc[i][j] += fabsf(a[i] - b[j]);
+                        else {
+                            float d = a[i] - b[j];
+                            acc[i][j] = fmaf(d, d, acc[i][j]);
+                        }
+                    }
+            }
+        }
+        // quantise, compare, count (zero-padded K tail contributes 0 in every mode)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rl = ty * 4 + i;
+            const int32_t pq = s_posq[rl];
+            const int32_t self = s_self[rl];
+            const unsigned long long mk = s_mask[rl];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int cl = tx * 4 + j;
+                const int64_t e = n0 + cl;
+                float sc = MODE == 0 ? acc[i][j] : (MODE == 1 ? -acc[i][j] : -sqrtf(acc[i][j]));
+                int qv2 = quantise_score(sc);
+                bool valid = (e < e1) && (e != (int64_t)self) && (self >= 0);
+                int gt = valid && (qv2 > pq), eq = valid && (qv2 == pq);
+                int f = (int)((mk >> cl) & 1ull);
+                cnt[i][0] += gt;
+                cnt[i][1] += eq;
+                cnt[i][2] += gt & f;
+                cnt[i][3] += eq & f;
+            }
+        }
+    }
+    // reduce over the 16 threads (tx) that share a row, then one atomic per (row, counter)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int v = cnt[i][c];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            cnt[i][c] = v;
+        }
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int64_t r = m0 + ty * 4 + i;
+            if (r < m_end) {
+                int side = r >= P.T ? 1 : 0;
+                int64_t t = r - (int64_t)side * P.T;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (cnt[i][c]) atomicAdd(&P.counts[(t * 2 + side) * 4 + c], cnt[i][c]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rank assembly (models/EmbeddingModel.py:1966-1986 with perform_comparision :1989-2033)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cmp_count(int gt, int eq, int strategy) {
+    if (strategy == KGE_STRAT_BEST) return gt;
+    if (strategy == KGE_STRAT_MIDDLE) return gt + (eq + 1) / 2;
+    return gt + eq;
+}
+
+__global__ void kge_rank_finalize_kernel(const int32_t* __restrict__ counts, int64_t T, int side, int strategy,
+                                         int filtered, int32_t* __restrict__ ranks) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    // object sweep = side 0, subject sweep = side 1; +1 on eq: the test triple's own candidate
+    const int32_t* co = counts + (t * 2 + 0) * 4;
+    const int32_t* cs = counts + (t * 2 + 1) * 4;
+    int go = co[0], eo = co[1] + 1, gfo = filtered ? co[2] : 0, efo = filtered ? co[3] + 1 : 0;
+    int gs = cs[0], es = cs[1] + 1, gfs = filtered ? cs[2] : 0, efs = filtered ? cs[3] + 1 : 0;
+    int fo = filtered ? cmp_count(gfo, efo, strategy) : 0;
+    int fs = filtered ? cmp_count(gfs, efs, strategy) : 0;
+    if (side == KGE_RANK_S_O) {
+        ranks[2 * t + 0] = cmp_count(gs, es, strategy) + 1 - fs;
+        ranks[2 * t + 1] = cmp_count(go, eo, strategy) + 1 - fo;
+    } else if (side == KGE_RANK_SPO) {
+        ranks[t] = cmp_count(go + gs, eo + es, strategy) + 1 - fs - fo;
+    } else if (side == KGE_RANK_S) {
+        ranks[t] = cmp_count(gs, es, strategy) + 1 - fs;
+    } else {
+        ranks[t] = cmp_count(go, eo, strategy) + 1 - fo;
+    }
+}
+
+extern "C" int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
+                               const float* ent_local, int64_t row_begin, int64_t row_end, const int32_t* test, int64_t T,
+                               int side, int filtered, int use_tensor_cores, int32_t* counts, void* stream) {
+    KGE_REQUIRE(ctx != nullptr, "kge_rank_counts: null ctx");
+    KGE_REQUIRE(model >= KGE_TRANSE_L1 && model <= KGE_HOLE, "kge_rank_counts: unknown model %d", model);
+    KGE_REQUIRE(side >= KGE_RANK_S_O && side <= KGE_RANK_O, "Invalid value for corrupt_side.");
+    KGE_REQUIRE(ent && rel && ent_local && counts, "kge_rank_counts: null tensor");
+    KGE_REQUIRE(ent->K == model_row_width(model, k), "kge_rank_counts: table width %d != internal_k %d", ent->K,
+                model_row_width(model, k));
+    KGE_REQUIRE(row_begin >= 0 && row_end <= ent->rows && row_begin <= row_end, "kge_rank_counts: bad row range");
+    KGE_REQUIRE(T < (int64_t)(1 << 30), "kge_rank_counts: too many test triples");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (T == 0) return 0;
+    KGE_REQUIRE(test != nullptr, "kge_rank_counts: null test triples");
+    if (filtered) {
+        KGE_REQUIRE(ctx->f_valid, "kge_rank_counts: filtered ranking requested but no filter was built");
+        KGE_REQUIRE(ctx->f_E == ent->rows && ctx->f_R == R, "kge_rank_counts: filter built for E=%lld R=%lld, model has E=%lld R=%lld",
+                    (long long)ctx->f_E, (long long)ctx->f_R, (long long)ent->rows, (long long)R);
+    }
+    const int K = ent->K;
+    KGE_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)T * 8 * sizeof(int32_t), st));
+    if (ctx->q_fold.reserve((size_t)2 * T * K * sizeof(float))) return -2;
+    if (ctx->pos_q.reserve((size_t)T * 4) || ctx->excl_lo.reserve((size_t)2 * T * 4) || ctx->excl_hi.reserve((size_t)2 * T * 4)) return -2;
+    PrepParams pp;
+    pp.model = model;
+    pp.k = k;
+    pp.ent = make_view(*ent);
+    pp.rel = rel;
+    pp.test = test;
+    pp.T = T;
+    pp.filtered = filtered && ctx->f_n_sp > 0;
+    pp.sp_comp = ctx->f_sp_comp.as<uint64_t>();
+    pp.po_comp = ctx->f_po_comp.as<uint64_t>();
+    pp.f_cnt = ctx->f_count.as<int32_t>();
+    pp.E = ent->rows;
+    pp.R = R;
+    pp.q = ctx->q_fold.as<float>();
+    pp.pos_q = ctx->pos_q.as<int32_t>();
+    pp.excl_lo = ctx->excl_lo.as<int32_t>();
+    pp.excl_hi = ctx->excl_hi.as<int32_t>();
+    {
+        const int warps = 8;
+        kge_rank_prepare_kernel<<<(unsigned)((T + warps - 1) / warps), warps * 32, 0, st>>>(pp);
+        KGE_CUDA_CHECK(cudaGetLastError());
+    }
+    if (row_end == row_begin) return 0;
+    // which query rows: [0,T) object sweep, [T,2T) subject sweep
+    int64_t q_row0 = 0, q_rows = 2 * T;
+    if (side == KGE_RANK_O) q_rows = T;
+    if (side == KGE_RANK_S) { q_row0 = T; q_rows = T; }
+    const bool trilinear = !(model == KGE_TRANSE_L1 || model == KGE_TRANSE_L2);
+    if (use_tensor_cores) {
+        KGE_REQUIRE(trilinear, "kge_rank_counts: the tensor-core sweep covers DistMult/ComplEx/HolE; TransE uses the fp32 sweep");
+        int side_mask = side == KGE_RANK_O ? 1 : (side == KGE_RANK_S ? 2 : 3);
+        return kge_rank_sweep_tc(ctx, model, K, pp.q, 2 * T, T, ent_local, row_begin, row_end, test, pp.pos_q, pp.excl_lo,
+                                 pp.excl_hi, ctx->f_sp_ent.as<int32_t>(), ctx->f_po_ent.as<int32_t>(), side_mask, counts, st);
+    }
+    SweepParams sp;
+    sp.model = model;
+    sp.K = K;
+    sp.q = pp.q;
+    sp.NQ = 2 * T;
+    sp.T = T;
+    sp.ent_local = ent_local;
+    sp.row_begin = row_begin;
+    sp.row_end = row_end;
+    sp.test = test;
+    sp.pos_q = pp.pos_q;
+    sp.excl_lo = pp.excl_lo;
+    sp.excl_hi = pp.excl_hi;
+    sp.sp_ent = ctx->f_sp_ent.as<int32_t>();
+    sp.po_ent = ctx->f_po_ent.as<int32_t>();
+    sp.q_row0 = q_row0;
+    sp.q_rows = q_rows;
+    sp.counts = counts;
+    int64_t row_tiles = (q_rows + SW_BM - 1) / SW_BM;
+    int64_t n_ent = row_end - row_begin;
+    // enough CTAs for >= 4 waves, entity chunks a multiple of the tile
+    int64_t want_chunks = std::max<int64_t>(1, ((int64_t)ctx->sm_count * 8 + row_tiles - 1) / row_tiles);
+    int64_t chunk = (n_ent + want_chunks - 1) / want_chunks;
+    chunk = std::max<int64_t>(SW_BN * 4, ((chunk + SW_BN - 1) / SW_BN) * SW_BN);
+    int64_t n_chunks = (n_ent + chunk - 1) / chunk;
+    KGE_REQUIRE(n_chunks <= 65535, "kge_rank_counts: too many entity chunks");
+    sp.chunk = chunk;
+    dim3 grid((unsigned)row_tiles, (unsigned)n_chunks), block(256);
+    if (trilinear) kge_rank_sweep_kernel<0><<<grid, block, 0, st>>>(sp);
+    else if (model == KGE_TRANSE_L1) kge_rank_sweep_kernel<1><<<grid, block, 0, st>>>(sp);
+    else kge_rank_sweep_kernel<2><<<grid, block, 0, st>>>(sp);
+    KGE_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int kge_rank_finalize(kge_ctx* ctx, const int32_t* counts, int64_t T, int side, int strategy, int filtered,
+                                 int32_t* ranks_out, void* stream) {
+    KGE_REQUIRE(ctx != nullptr, "kge_rank_finalize: null ctx");
+    KGE_REQUIRE(side >= KGE_RANK_S_O && side <= KGE_RANK_O, "Invalid value for corrupt_side.");
+    KGE_REQUIRE(strategy >= KGE_STRAT_WORST && strategy <= KGE_STRAT_MIDDLE, "Invalid ranking_strategy!");
+    if (T == 0) return 0;
+    KGE_REQUIRE(counts && ranks_out, "kge_rank_finalize: null tensor");
+    kge_rank_finalize_kernel<<<(unsigned)((T + 255) / 256), 256, 0, (cudaStream_t)stream>>>(counts, T, side, strategy, filtered,
+                                                                                        ranks_out);
+    KGE_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

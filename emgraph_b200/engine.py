@@ -1,0 +1,264 @@
+"""Thin host driver over the C ABI: owns the kge_ctx, turns torch CUDA tensors into the plain
+pointers/sizes of include/kge_b200.h, and enqueues on torch's current stream.  No arithmetic
+happens here; without the CUDA library every entry point raises (no CPU fallback)."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import KgeTable, KgeTrainArgs, check
+
+
+def model_id(name: str, norm: int = 1) -> int:
+    if name == "TransE":
+        if norm not in (1, 2):
+            raise ValueError("TransE norm must be 1 or 2 on the CUDA path, got %r" % (norm,))
+        return _lib.MODEL_IDS["TransE"] if norm == 1 else _lib.MODEL_IDS["TransE_L2"]
+    return _lib.MODEL_IDS[name]
+
+
+def internal_k(name: str, k: int) -> int:
+    return 2 * k if name in ("ComplEx", "HolE") else k
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk_f32(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise ValueError("%s must be a contiguous float32 CUDA tensor" % name)
+
+
+def _chk_i32(t, name):
+    if not (t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
+        raise ValueError("%s must be a contiguous int32 CUDA tensor" % name)
+
+
+def make_table(shards, rows=None, rows_per_shard=None, K=None) -> KgeTable:
+    """shards: one [rows,K] fp32 CUDA tensor, or a list of raw device pointers / tensors (one per
+    rank, peer-mapped) for a row-range-sharded table."""
+    tb = KgeTable()
+    if isinstance(shards, torch.Tensor):
+        _chk_f32(shards, "table")
+        tb.shard[0] = shards.data_ptr()
+        tb.rows = shards.shape[0]
+        tb.rows_per_shard = shards.shape[0]
+        tb.n_shards = 1
+        tb.K = shards.shape[1]
+        return tb
+    if shards is None:
+        tb.n_shards = 1
+        tb.rows = rows or 0
+        tb.rows_per_shard = rows_per_shard or (rows or 0)
+        tb.K = K or 0
+        return tb
+    assert len(shards) <= _lib.KGE_MAX_SHARDS
+    for i, s in enumerate(shards):
+        tb.shard[i] = s.data_ptr() if isinstance(s, torch.Tensor) else int(s)
+    tb.rows = rows
+    tb.rows_per_shard = rows_per_shard
+    tb.n_shards = len(shards)
+    tb.K = K
+    return tb
+
+
+class Engine:
+    """One per process/GPU.  Wraps kge_ctx."""
+
+    def __init__(self, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise _lib.KgeError("emgraph_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        check(self.lib.kge_ctx_create(self.device, C.byref(h)))
+        self._h = h
+        self.launches = 0  # kernels of ours launched through this engine (bench bookkeeping)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.kge_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def tdev(self):
+        return torch.device("cuda", self.device)
+
+    def workspace_bytes(self) -> int:
+        return int(self.lib.kge_ctx_workspace_bytes(self._h))
+
+    # ---------------------------------------------------------------- scoring
+    def score(self, model: int, k: int, ent, rel, triples):
+        """ent: tensor [E,K] or KgeTable; returns fp32 CUDA tensor [n]."""
+        tb = ent if isinstance(ent, KgeTable) else make_table(ent)
+        _chk_f32(rel, "rel")
+        _chk_i32(triples, "triples")
+        n = triples.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=self.tdev)
+        check(self.lib.kge_score(self._h, model, k, C.byref(tb), _ptr(rel), rel.shape[0], _ptr(triples), n, _ptr(out), _stream()))
+        self.launches += 1 if n else 0
+        return out
+
+    # ---------------------------------------------------------------- training
+    def train_args(self, *, model, loss, opt, k, eta, ent, rel, pos, loss_out, side=0, flags=0, margin=1.0,
+                   lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7, momentum=0.9, seed=0, step=1, neg_index_base=0,
+                   ent_m=None, ent_v=None, rel_m=None, rel_v=None, repl=None, keep_subj=None,
+                   dbg_scores=None, dbg_grad_ent=None, dbg_grad_rel=None) -> KgeTrainArgs:
+        a = KgeTrainArgs()
+        a.model, a.loss, a.opt, a.side, a.flags = model, loss, opt, side, flags
+        a.k, a.eta, a.margin = k, eta, margin
+        a.lr, a.beta1, a.beta2, a.eps, a.momentum = lr, beta1, beta2, eps, momentum
+        a.seed, a.step, a.neg_index_base = seed, step, neg_index_base
+        a.ent = ent if isinstance(ent, KgeTable) else make_table(ent)
+        K = a.ent.K
+        for name, t in (("ent_m", ent_m), ("ent_v", ent_v)):
+            if t is None:
+                tb = make_table(None, rows=a.ent.rows, rows_per_shard=a.ent.rows_per_shard, K=K)
+                tb.n_shards = a.ent.n_shards
+            else:
+                tb = t if isinstance(t, KgeTable) else make_table(t)
+            setattr(a, name, tb)
+        _chk_f32(rel, "rel")
+        a.rel, a.rel_m, a.rel_v, a.R = rel.data_ptr(), (rel_m.data_ptr() if rel_m is not None else None), \
+            (rel_v.data_ptr() if rel_v is not None else None), rel.shape[0]
+        _chk_i32(pos, "pos")
+        a.pos, a.n_pos = pos.data_ptr(), pos.shape[0]
+        if repl is not None:
+            _chk_i32(repl, "repl")
+            assert repl.numel() == eta * pos.shape[0]
+            a.repl = repl.data_ptr()
+        if keep_subj is not None:
+            assert keep_subj.is_cuda and keep_subj.dtype == torch.uint8 and keep_subj.numel() == eta * pos.shape[0]
+            a.keep_subj = keep_subj.data_ptr()
+        a.loss_out = loss_out.data_ptr()
+        a.dbg_scores = dbg_scores.data_ptr() if dbg_scores is not None else None
+        a.dbg_grad_ent = dbg_grad_ent.data_ptr() if dbg_grad_ent is not None else None
+        a.dbg_grad_rel = dbg_grad_rel.data_ptr() if dbg_grad_rel is not None else None
+        # keep python references alive for the duration of the call
+        a._keep = (ent, rel, pos, loss_out, ent_m, ent_v, rel_m, rel_v, repl, keep_subj, dbg_scores, dbg_grad_ent, dbg_grad_rel)
+        return a
+
+    # kernels per step: emit, fwd_bwd, loss-reduce, iota, radix-sort (CUB onesweep: histogram +
+    # ceil(bits/8) passes), apply
+    @staticmethod
+    def launches_per_step(E_plus_R: int) -> int:
+        bits = max(1, math.ceil(math.log2(max(2, E_plus_R))))
+        return 5 + 1 + math.ceil(bits / 8)
+
+    def train_step(self, a: KgeTrainArgs):
+        check(self.lib.kge_train_step(self._h, C.byref(a), _stream()))
+        self.launches += self.launches_per_step(a.ent.rows + a.R)
+
+    def train_emit(self, a: KgeTrainArgs, keys_out):
+        _chk_i32(keys_out, "keys_out")
+        check(self.lib.kge_train_emit(self._h, C.byref(a), _ptr(keys_out), _stream()))
+        self.launches += 1
+
+    def train_fwd_bwd(self, a: KgeTrainArgs, grad_rows):
+        check(self.lib.kge_train_fwd_bwd(self._h, C.byref(a), _ptr(grad_rows), _stream()))
+        self.launches += 2
+
+    def train_apply(self, a: KgeTrainArgs, keys_all, grads: KgeTable, row_begin: int, row_end: int):
+        _chk_i32(keys_all, "keys_all")
+        check(self.lib.kge_train_apply(self._h, C.byref(a), _ptr(keys_all), keys_all.numel(), C.byref(grads),
+                                       row_begin, row_end, _stream()))
+        self.launches += self.launches_per_step(a.ent.rows + a.R) - 3
+
+    def normalize_rows(self, emb):
+        _chk_f32(emb, "emb")
+        check(self.lib.kge_normalize_rows(self._h, _ptr(emb), emb.shape[0], emb.shape[1], _stream()))
+        self.launches += 1
+
+    # ---------------------------------------------------------------- ranking
+    def filter_build(self, triples, E: int, R: int):
+        _chk_i32(triples, "filter triples")
+        check(self.lib.kge_filter_build(self._h, _ptr(triples), triples.shape[0], E, R, _stream()))
+        self._filter_keep = triples
+        self.launches += 12 if triples.shape[0] else 0
+
+    def filter_clear(self):
+        check(self.lib.kge_filter_clear(self._h))
+
+    def filter_size(self) -> int:
+        return int(self.lib.kge_filter_size_sync(self._h))
+
+    def rank_counts(self, model: int, k: int, ent, rel, test, *, side=0, filtered=False, use_tensor_cores=False,
+                    ent_local=None, row_begin=0, row_end=None, counts=None):
+        tb = ent if isinstance(ent, KgeTable) else make_table(ent)
+        if ent_local is None:
+            assert isinstance(ent, torch.Tensor)
+            ent_local = ent
+        if row_end is None:
+            row_end = tb.rows
+        _chk_f32(ent_local, "ent_local")
+        _chk_f32(rel, "rel")
+        _chk_i32(test, "test")
+        T = test.shape[0]
+        if counts is None:
+            counts = torch.empty((T, 2, 4), dtype=torch.int32, device=self.tdev)
+        check(self.lib.kge_rank_counts(self._h, model, k, C.byref(tb), _ptr(rel), rel.shape[0], _ptr(ent_local),
+                                       row_begin, row_end, _ptr(test), T, side, int(bool(filtered)),
+                                       int(bool(use_tensor_cores)), _ptr(counts), _stream()))
+        self.launches += 3 if T else 0
+        return counts
+
+    def rank_finalize(self, counts, *, side=0, strategy=0, filtered=False):
+        T = counts.shape[0]
+        shape = (T, 2) if side == _lib.RANK_SIDE_IDS["s,o"] else (T,)
+        ranks = torch.empty(shape, dtype=torch.int32, device=self.tdev)
+        check(self.lib.kge_rank_finalize(self._h, _ptr(counts), T, side, strategy, int(bool(filtered)), _ptr(ranks), _stream()))
+        self.launches += 1 if T else 0
+        return ranks
+
+    def rank(self, model: int, k: int, ent, rel, test, *, side=0, strategy=0, filtered=False, use_tensor_cores=False):
+        counts = self.rank_counts(model, k, ent, rel, test, side=side, filtered=filtered, use_tensor_cores=use_tensor_cores)
+        return self.rank_finalize(counts, side=side, strategy=strategy, filtered=filtered)
+
+    # ---------------------------------------------------------------- IPC (multi-GPU peer shards)
+    def ipc_export(self, t) -> bytes:
+        buf = (C.c_char * 64)()
+        check(self.lib.kge_ipc_export(_ptr(t), C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (C.c_char * 64).from_buffer_copy(handle)
+        out = C.c_void_p()
+        check(self.lib.kge_ipc_open(C.cast(buf, C.c_void_p), C.byref(out)))
+        return int(out.value)
+
+    def ipc_close(self, ptr: int):
+        check(self.lib.kge_ipc_close(C.c_void_p(ptr)))
+
+
+_ENGINES: dict = {}
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """Process-wide engine per device."""
+    if not torch.cuda.is_available():
+        raise _lib.KgeError("emgraph_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    d = torch.cuda.current_device() if device is None else int(device)
+    e = _ENGINES.get(d)
+    if e is None:
+        e = _ENGINES[d] = Engine(d)
+    return e
+
+
+def to_dev_i32(x, device):
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.int32)).to(device, non_blocking=False)

@@ -1,0 +1,438 @@
+"""Host-side mirror of ``emgraph.models`` for the hot path: TransE / DistMult / ComplEx / HolE with
+the reference constructor signature, ``fit`` / ``predict`` / ``get_embeddings`` and the four methods
+``evaluate_performance`` calls.  All arithmetic runs in libkge_b200.so (CUDA, sm_100a).
+
+Reference interface mirrored (paths relative to the reference root):
+  models/EmbeddingModel.py:184-314 (ctor, registries, error conventions), :1113-1492 (fit),
+  :2101-2147 (predict), :455-488 (get_embeddings), :1494-1518, :2035-2099 (evaluation hooks);
+  models/TransE.py:142-165, DistMult.py:50-71, ComplEx.py:93-113, HolE.py:37-57 (signatures);
+  utils/constants.py (defaults).
+Documented deviations: every batch is trained once and its loss comes from
+the same pass (F6); optimizer state persists across batches unless ``engine_params
+['reset_state']`` (F5); ``get_ranks`` ranks every test triple (F3).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import get_engine, internal_k, model_id, to_dev_i32
+
+# utils/constants.py
+DEFAULT_EMBEDDING_SIZE = 100
+DEFAULT_ETA = 2
+DEFAULT_EPOCH = 100
+DEFAULT_BATCH_COUNT = 100
+DEFAULT_SEED = 0
+DEFAULT_OPTIM = "adam"
+DEFAULT_LOSS = "nll"
+DEFAULT_LR = 0.0005
+DEFAULT_MOMENTUM = 0.9
+DEFAULT_REGULARIZER = None
+DEFAULT_INITIALIZER = "glorot_uniform"
+DEFAULT_VERBOSE = False
+DEFAULT_NORM_TRANSE = 1
+DEFAULT_CORRUPT_SIDE_TRAIN = ["s,o"]
+DEFAULT_CORRUPT_SIDE_EVAL = "s,o"
+DEFAULT_CORRUPTION_ENTITIES = "all"
+DEFAULT_RANK_COMPARE_STRATEGY = "worst"
+DEFAULT_MARGIN = 1  # losses/_loss_constants.py:8
+
+MODEL_REGISTRY = {}
+
+SUPPORTED_LOSSES = ("pairwise", "nll", "multiclass_nll")
+SUPPORTED_OPTIMIZERS = ("adam", "adagrad", "momentum", "sgd")
+SUPPORTED_INITIALIZERS = ("glorot_uniform", "xavier", "normal", "uniform", "constant")
+SUPPORTED_REGULARIZERS = ()  # LP is SURVEY section 8f "next"
+
+
+def register_model(name):
+    def deco(cls):
+        MODEL_REGISTRY[name] = cls
+        cls.name = name
+        return cls
+    return deco
+
+
+# ------------------------------------------------------------------------------------------------
+# id mapping (evaluation/protocol.py:429-445, :662-723) -- same sorted-unique ids, vectorised
+# ------------------------------------------------------------------------------------------------
+class LabelIndex:
+    """label -> id with ids assigned in np.unique (sorted) order; dict view built lazily."""
+
+    def __init__(self, labels_sorted):
+        self.labels = np.asarray(labels_sorted)
+        self._dict = None
+
+    def __len__(self):
+        return len(self.labels)
+
+    def lookup(self, x, what):
+        x = np.asarray(x)
+        if len(self.labels) == 0:
+            raise ValueError(_UNSEEN_MSG.format(concept_type=what))
+        try:
+            pos = np.searchsorted(self.labels, x)
+        except TypeError:
+            raise ValueError(_UNSEEN_MSG.format(concept_type="concepts"))
+        pos = np.minimum(pos, len(self.labels) - 1)
+        ok = self.labels[pos] == x
+        if not np.all(ok):
+            raise ValueError(_UNSEEN_MSG.format(concept_type=what))
+        return pos.astype(np.int32)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        if len(self.labels) == 0:
+            return np.zeros(x.shape, bool)
+        try:
+            pos = np.minimum(np.searchsorted(self.labels, x), len(self.labels) - 1)
+        except TypeError:
+            return np.zeros(x.shape, bool)
+        return self.labels[pos] == x
+
+    def as_dict(self):
+        if self._dict is None:
+            self._dict = dict(zip(self.labels.tolist(), range(len(self.labels))))
+        return self._dict
+
+
+_UNSEEN_MSG = (
+    "Input triples include one or more {concept_type} not present in the training set. "
+    "Please filter all concepts in X that do not occur in the training test "
+    "(set filter_unseen=True in evaluate_performance) or retrain the model on a "
+    "training set that includes all the desired concept types."
+)
+
+
+def create_mappings(X):
+    """evaluation/protocol.py:429-445 -> (rel_to_idx, ent_to_idx) dicts."""
+    X = np.asarray(X)
+    ent = LabelIndex(np.unique(np.concatenate((X[:, 0], X[:, 2]))))
+    rel = LabelIndex(np.unique(X[:, 1]))
+    return rel.as_dict(), ent.as_dict()
+
+
+def to_idx(X, ent_to_idx, rel_to_idx):
+    """evaluation/protocol.py:706-723; unseen label -> ValueError."""
+    X = np.asarray(X)
+    if X.ndim == 1:
+        X = X[np.newaxis, :]
+    ei = ent_to_idx if isinstance(ent_to_idx, LabelIndex) else _index_from_dict(ent_to_idx)
+    ri = rel_to_idx if isinstance(rel_to_idx, LabelIndex) else _index_from_dict(rel_to_idx)
+    s = ei.lookup(X[:, 0], "entities")
+    p = ri.lookup(X[:, 1], "relations")
+    o = ei.lookup(X[:, 2], "entities")
+    return np.stack([s, p, o], axis=1)
+
+
+def _index_from_dict(d):
+    keys = np.asarray(list(d.keys()))
+    vals = np.asarray(list(d.values()))
+    order = np.argsort(vals)
+    li = LabelIndex(keys[order])
+    if not np.array_equal(vals[order], np.arange(len(vals))) or np.any(li.labels[:-1] > li.labels[1:]):
+        # arbitrary user mapping: fall back to an explicit permutation
+        srt = np.argsort(keys)
+        li = _PermutedIndex(keys[srt], vals[srt])
+    return li
+
+
+class _PermutedIndex(LabelIndex):
+    def __init__(self, labels_sorted, ids):
+        super().__init__(labels_sorted)
+        self.ids = np.asarray(ids)
+
+    def lookup(self, x, what):
+        return self.ids[super().lookup(x, what)].astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+# model base
+# ------------------------------------------------------------------------------------------------
+class EmbeddingModel:
+    name = None
+
+    def __init__(self, k=DEFAULT_EMBEDDING_SIZE, eta=DEFAULT_ETA, epochs=DEFAULT_EPOCH,
+                 batches_count=DEFAULT_BATCH_COUNT, seed=DEFAULT_SEED, embedding_model_params=None,
+                 optimizer=DEFAULT_OPTIM, optimizer_params=None, loss=DEFAULT_LOSS, loss_params=None,
+                 regularizer=DEFAULT_REGULARIZER, regularizer_params=None, initializer=DEFAULT_INITIALIZER,
+                 initializer_params=None, large_graphs=False, verbose=DEFAULT_VERBOSE, engine_params=None):
+        embedding_model_params = {} if embedding_model_params is None else embedding_model_params
+        optimizer_params = {"lr": DEFAULT_LR} if optimizer_params is None else optimizer_params
+        loss_params = {} if loss_params is None else loss_params
+        regularizer_params = {} if regularizer_params is None else regularizer_params
+        initializer_params = {"uniform": False} if initializer_params is None else initializer_params
+        if loss == "bce":  # models/EmbeddingModel.py:206-210
+            raise ValueError("Invalid Model - Loss combination. ConvE model can be used with BCE loss only and vice versa.")
+        self.all_params = {
+            "k": k, "eta": eta, "epochs": epochs, "batches_count": batches_count, "seed": seed,
+            "embedding_model_params": embedding_model_params, "optimizer": optimizer,
+            "optimizer_params": optimizer_params, "loss": loss, "loss_params": loss_params,
+            "regularizer": regularizer, "regularizer_params": regularizer_params,
+            "initializer": initializer, "initializer_params": initializer_params, "verbose": verbose,
+        }
+        self.seed = seed
+        self.rnd = np.random.RandomState(seed)
+        self.k = k
+        self.internal_k = internal_k(self.name, k)
+        self.epochs = epochs
+        self.eta = eta
+        self.batches_count = batches_count
+        self.embedding_model_params = embedding_model_params
+        self.loss_params = loss_params
+        self.optimizer_params = optimizer_params
+        self.regularizer_params = regularizer_params
+        self.initializer_params = initializer_params
+        self.engine_params = dict(engine_params or {})
+        self.dealing_with_large_graphs = large_graphs  # accepted, ignored: the table lives in HBM
+        self.verbose = verbose
+        if loss not in SUPPORTED_LOSSES:
+            raise ValueError("Unsupported loss function: {}".format(loss))
+        if regularizer is not None:
+            raise ValueError("Unsupported regularizer: {}".format(regularizer))
+        if optimizer not in SUPPORTED_OPTIMIZERS:
+            raise ValueError("Unsupported optimizer: {}".format(optimizer))
+        if initializer not in SUPPORTED_INITIALIZERS:
+            raise ValueError("Unsupported initializer: {}".format(initializer))
+        self.loss = loss
+        self.optimizer = optimizer
+        self.regularizer = None
+        self.initializer = initializer
+        self.trained_model_params = []
+        self.is_fitted = False
+        self.is_filtered = False
+        self.eval_config = {}
+        self.eval_dataset_handle = None
+        self.is_calibrated = False
+        self.calibration_parameters = []
+        self._ent_index = None
+        self._rel_index = None
+        self._dev = None  # device-resident parameters {ent, rel}
+        self.loss_history = []
+
+    # ---- mappings exposed like the reference attributes (utils/model_utils.py:63-72 reads them)
+    @property
+    def ent_to_idx(self):
+        return {} if self._ent_index is None else self._ent_index.as_dict()
+
+    @ent_to_idx.setter
+    def ent_to_idx(self, d):
+        self._ent_index = _index_from_dict(d)
+
+    @property
+    def rel_to_idx(self):
+        return {} if self._rel_index is None else self._rel_index.as_dict()
+
+    @rel_to_idx.setter
+    def rel_to_idx(self, d):
+        self._rel_index = _index_from_dict(d)
+
+    def get_hyperparameter_dict(self):  # models/EmbeddingModel.py:338
+        return self.all_params
+
+    # ---- ids
+    def _model_id(self):
+        return model_id(self.name, int(self.embedding_model_params.get("norm", DEFAULT_NORM_TRANSE)))
+
+    def _train_sides(self):
+        # the reference reads 'corrupt_side' though ctors document 'corrupt_sides' (SURVEY F9): accept both
+        sides = self.embedding_model_params.get("corrupt_side", self.embedding_model_params.get("corrupt_sides", DEFAULT_CORRUPT_SIDE_TRAIN))
+        if not isinstance(sides, list):
+            sides = [sides]
+        for s in sides:
+            if s not in _lib.TRAIN_SIDE_IDS:
+                raise ValueError("Invalid argument value {} for corruption side passed for evaluation.".format(s))
+        return sides
+
+    # ---- parameter initialisation (models/EmbeddingModel.py:547-601, initializers/*.py)
+    def _init_table(self, rows, cols, which):
+        ini, p = self.initializer, self.initializer_params
+        if ini in ("glorot_uniform", "xavier"):
+            if p.get("uniform", False) or True:  # TF path always uniform
+                lim = np.sqrt(6.0 / (rows + cols))
+                return self.rnd.uniform(-lim, lim, size=(rows, cols)).astype(np.float32)
+        if ini == "normal":
+            return self.rnd.normal(p.get("mean", 0), p.get("std", 0.05), size=(rows, cols)).astype(np.float32)
+        if ini == "uniform":
+            return self.rnd.uniform(p.get("low", -0.05), p.get("high", 0.05), size=(rows, cols)).astype(np.float32)
+        if ini == "constant":
+            key = "entity" if which == "entity" else "relation"
+            try:
+                arr = np.asarray(p[key], dtype=np.float32)
+            except KeyError:
+                raise Exception("Initial {} value not passed to the initializer!".format(key))
+            assert arr.shape == (rows, cols), "Invalid shape for {} initializer!".format(key)
+            return np.ascontiguousarray(arr)
+        raise ValueError("Unsupported initializer: {}".format(ini))
+
+    # ---- training (models/EmbeddingModel.py:1113-1492)
+    def fit(self, X, early_stopping=False, early_stopping_params={}, focusE_numeric_edge_values=None,
+            tensorboard_logs_path=None):
+        if not isinstance(X, np.ndarray):
+            raise ValueError("Invalid type for input X. Expected ndarray/EmgraphDataset object, got {}".format(type(X)))
+        if X.ndim != 2 or X.shape[1] != 3:
+            raise ValueError("Invalid size for input X. Expected (n,3):  got {}".format(X.shape))
+        if early_stopping:
+            raise NotImplementedError("early stopping is outside the B200 hot-path scope (SURVEY section 8f)")
+        if focusE_numeric_edge_values is not None:
+            raise NotImplementedError("FocusE edge weights are outside the B200 hot-path scope")
+        self._ent_index = LabelIndex(np.unique(np.concatenate((X[:, 0], X[:, 2]))))
+        self._rel_index = LabelIndex(np.unique(X[:, 1]))
+        Xi = to_idx(X, self._ent_index, self._rel_index)
+        self._fit_idx(Xi, len(self._ent_index), len(self._rel_index))
+        return self
+
+    def _fit_idx(self, Xi, E, R):
+        eng = get_engine(self.engine_params.get("device"))
+        dev = eng.tdev
+        N = Xi.shape[0]
+        batch_size = int(np.ceil(N / self.batches_count))
+        K = self.internal_k
+        ent = torch.from_numpy(self._init_table(E, K, "entity")).to(dev)
+        rel = torch.from_numpy(self._init_table(R, K, "relation")).to(dev)
+        opt = _lib.OPT_IDS[self.optimizer]
+        reset = bool(self.engine_params.get("reset_state", False))
+        st = {}
+        if not reset:
+            if opt == 0:
+                st = dict(ent_m=torch.zeros_like(ent), ent_v=torch.zeros_like(ent), rel_m=torch.zeros_like(rel), rel_v=torch.zeros_like(rel))
+            elif opt == 1:
+                st = dict(ent_m=torch.full_like(ent, 0.1), rel_m=torch.full_like(rel, 0.1))
+            elif opt == 2:
+                st = dict(ent_m=torch.zeros_like(ent), rel_m=torch.zeros_like(rel))
+        Xd = to_dev_i32(Xi, dev)
+        sides = self._train_sides()
+        loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        epoch_loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        normalize = bool(self.embedding_model_params.get("normalize_ent_emb", False))
+        lr = float(self.optimizer_params.get("lr", DEFAULT_LR))
+        mom = float(self.optimizer_params.get("momentum", DEFAULT_MOMENTUM))
+        margin = float(self.loss_params.get("margin", DEFAULT_MARGIN))
+        mid, lid = self._model_id(), _lib.LOSS_IDS[self.loss]
+        check_every = int(self.engine_params.get("nan_check_every", self.batches_count))
+        step = 0
+        self.loss_history = []
+        denom = batch_size * (self.eta if self.loss in ("pairwise", "nll") else 1) * self.batches_count  # :1343-1344, :1453-1457
+        for epoch in range(1, self.epochs + 1):
+            epoch_loss.zero_()
+            for b in range(self.batches_count):
+                pos = Xd[b * batch_size:(b + 1) * batch_size]
+                if pos.shape[0] == 0:
+                    continue
+                for side in sides:
+                    step += 1
+                    a = eng.train_args(model=mid, loss=lid, opt=opt, k=self.k, eta=self.eta, ent=ent, rel=rel, pos=pos,
+                                       loss_out=loss_dev, side=_lib.TRAIN_SIDE_IDS[side],
+                                       flags=_lib.F_RESET_STATE if reset else 0, margin=margin, lr=lr, momentum=mom,
+                                       seed=int(self.seed), step=step, **st)
+                    eng.train_step(a)
+                    epoch_loss += loss_dev.double()
+                if normalize:
+                    eng.normalize_rows(ent)
+                if step % check_every == 0 and not bool(torch.isfinite(epoch_loss).item()):
+                    raise ValueError("Loss is {}. Please change the hyperparameters.".format(float(epoch_loss.item())))
+            el = float(epoch_loss.item())
+            if not np.isfinite(el):  # models/EmbeddingModel.py:1422-1427
+                raise ValueError("Loss is {}. Please change the hyperparameters.".format(el))
+            self.loss_history.append(el / denom)
+            if self.verbose:
+                print("Average Loss: {:10f} -- epoch {}/{}".format(self.loss_history[-1], epoch, self.epochs))
+        self._dev = {"ent": ent, "rel": rel}
+        self._opt_state = st
+        self.trained_model_params = [ent.cpu().numpy(), rel.cpu().numpy()]
+        self.is_fitted = True
+
+    def _device_params(self):
+        """Device copies of the trained parameters (uploaded once; restored models upload lazily)."""
+        if self._dev is None:
+            eng = get_engine(self.engine_params.get("device"))
+            e, r = self.trained_model_params[0], self.trained_model_params[1]
+            self._dev = {"ent": torch.from_numpy(np.ascontiguousarray(e, dtype=np.float32)).to(eng.tdev),
+                         "rel": torch.from_numpy(np.ascontiguousarray(r, dtype=np.float32)).to(eng.tdev)}
+        return self._dev["ent"], self._dev["rel"]
+
+    # ---- predict (models/EmbeddingModel.py:2101-2147)
+    def predict(self, X, from_idx=False):
+        if not self.is_fitted:
+            raise RuntimeError("Model has not been fitted.")
+        X = np.asarray(X)
+        if X.ndim == 1:
+            X = X[np.newaxis, :]
+        Xi = X.astype(np.int32) if from_idx else to_idx(X, self._ent_index, self._rel_index)
+        eng = get_engine(self.engine_params.get("device"))
+        ent, rel = self._device_params()
+        out = eng.score(self._model_id(), self.k, ent, rel, to_dev_i32(Xi, eng.tdev))
+        return out.cpu().numpy()
+
+    # ---- get_embeddings (models/EmbeddingModel.py:455-488)
+    def get_embeddings(self, entities, embedding_type="entity"):
+        if not self.is_fitted:
+            raise RuntimeError("Model has not been fitted.")
+        if embedding_type == "entity":
+            idxs = self._ent_index.lookup(np.asarray(entities), "entities")
+            return self.trained_model_params[0][idxs]
+        if embedding_type == "relation":
+            idxs = self._rel_index.lookup(np.asarray(entities), "relations")
+            return self.trained_model_params[1][idxs]
+        raise ValueError("Invalid entity type: {}".format(embedding_type))
+
+    # ---- evaluation hooks used by evaluate_performance (models/EmbeddingModel.py:1494-1518, :2035-2099)
+    def set_filter_for_eval(self):
+        self.is_filtered = True
+
+    def configure_evaluation_protocol(self, config=None):
+        if config is None:
+            config = {"corruption_entities": DEFAULT_CORRUPTION_ENTITIES, "corrupt_side": DEFAULT_CORRUPT_SIDE_EVAL}
+        self.eval_config = config
+
+    def end_evaluation(self):
+        if self.is_filtered and self.eval_dataset_handle is not None:
+            self.eval_dataset_handle.cleanup()
+            self.eval_dataset_handle = None
+        self.is_filtered = False
+        self.eval_config = {}
+
+    def get_ranks(self, dataset_handle):
+        """dataset_handle: evaluation.EvalDataset (test ids + optional filter ids)."""
+        if not self.is_fitted:
+            raise RuntimeError("Model has not been fitted.")
+        self.eval_dataset_handle = dataset_handle
+        side = self.eval_config.get("corrupt_side", DEFAULT_CORRUPT_SIDE_EVAL)
+        strategy = self.eval_config.get("ranking_strategy", DEFAULT_RANK_COMPARE_STRATEGY)
+        assert strategy in ("worst", "best", "middle"), "Invalid score comparision type!"
+        if self.eval_config.get("corruption_entities", DEFAULT_CORRUPTION_ENTITIES) is not None and not isinstance(
+                self.eval_config.get("corruption_entities", DEFAULT_CORRUPTION_ENTITIES), str):
+            raise NotImplementedError("entities_subset ranking is outside the B200 hot-path scope (SURVEY section 8f)")
+        eng = get_engine(self.engine_params.get("device"))
+        ent, rel = self._device_params()
+        test = dataset_handle.test_device(eng.tdev)
+        filtered = bool(self.is_filtered)
+        if filtered:
+            dataset_handle.build_filter(eng, ent.shape[0], rel.shape[0])
+        mid = self._model_id()
+        use_tc = bool(self.engine_params.get("rank_tensor_cores", False)) and self.name != "TransE"
+        ranks = eng.rank(mid, self.k, ent, rel, test, side=_lib.RANK_SIDE_IDS[side],
+                         strategy=_lib.STRATEGY_IDS[strategy], filtered=filtered, use_tensor_cores=use_tc)
+        return ranks.cpu().numpy()
+
+
+@register_model("TransE")
+class TransE(EmbeddingModel):
+    """f = -||s + p - o||_n  (models/TransE.py:190-216)."""
+
+
+@register_model("DistMult")
+class DistMult(EmbeddingModel):
+    """f = sum s*p*o  (models/DistMult.py:181-201)."""
+
+
+@register_model("ComplEx")
+class ComplEx(EmbeddingModel):
+    """f = Re<p, s, conj(o)>, rows [re(k) | im(k)]  (models/ComplEx.py:267-298)."""
+
+
+@register_model("HolE")
+class HolE(EmbeddingModel):
+    """f = (2/k) * ComplEx score  (models/HolE.py:169-189)."""

@@ -1,0 +1,156 @@
+/*
+ * kge_b200.h -- C ABI of the B200-native KGE hot path (train step + filtered ranking).
+ *
+ * The reference (bi-graph/Emgraph 1.0.0-rc1) has no native boundary: its hot path is Python over
+ * TensorFlow ops.  Each entry point below therefore cites the reference *Python* interface it
+ * replaces (paths relative to the reference root).  The Python package `emgraph_b200` binds these
+ * with ctypes (emgraph_b200/_lib.py); INTEGRATION.md shows the stub a reference maintainer would
+ * add.
+ *
+ * Conventions
+ *  - plain C types only; every call returns 0 on success, <0 on error; kge_last_error() returns a
+ *    thread-local message for the last failing call.
+ *  - the CALLER owns every tensor (device pointers, e.g. torch allocations); the library owns only
+ *    the opaque kge_ctx (per device: workspace, sort scratch, filter index).
+ *  - all work is enqueued on the caller-supplied cudaStream_t (passed as void*); no hidden syncs
+ *    except workspace growth (first call at a larger size) and the *_sync getters.
+ *  - a ctx is not thread-safe; one ctx per GPU/process.  There is NO CPU fallback.
+ *  - embeddings are fp32 row-major [rows, K]; ids are int32; K = k (TransE, DistMult) or 2k
+ *    (ComplEx, HolE: row = [re(k) | im(k)], reference models/ComplEx.py:224).
+ */
+#ifndef KGE_B200_H
+#define KGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGE_ABI_VERSION 1
+#define KGE_MAX_SHARDS 8
+
+typedef struct kge_ctx kge_ctx;
+
+/* scoring functions: models/TransE.py:190-216, DistMult.py:181-201, ComplEx.py:267-298, HolE.py:169-189 */
+enum { KGE_TRANSE_L1 = 0, KGE_TRANSE_L2 = 1, KGE_DISTMULT = 2, KGE_COMPLEX = 3, KGE_HOLE = 4 };
+/* losses: losses/pairwise.py:54-70, nll.py:43-59, nll_multiclass.py:57-81 */
+enum { KGE_LOSS_PAIRWISE = 0, KGE_LOSS_NLL = 1, KGE_LOSS_MULTICLASS_NLL = 2 };
+/* optimizers: training/adam.py:31-48, adagrad.py:30-46, momentum.py:51-69, sgd.py:79-125 */
+enum { KGE_OPT_ADAM = 0, KGE_OPT_ADAGRAD = 1, KGE_OPT_MOMENTUM = 2, KGE_OPT_SGD = 3 };
+/* training corruption side: evaluation/protocol.py:587-608 ('s,o' == 's+o': per-negative coin) */
+enum { KGE_SIDE_SO = 0, KGE_SIDE_S = 1, KGE_SIDE_O = 2 };
+/* ranking: corrupt_side (evaluation/protocol.py:883-888), strategy (models/EmbeddingModel.py:1989-2033) */
+enum { KGE_RANK_S_O = 0, KGE_RANK_SPO = 1, KGE_RANK_S = 2, KGE_RANK_O = 3 };
+enum { KGE_STRAT_WORST = 0, KGE_STRAT_BEST = 1, KGE_STRAT_MIDDLE = 2 };
+
+/* train-step flags */
+#define KGE_F_RESET_STATE 1u /* reference-faithful: optimizer state re-created every batch (training/adam.py:45-46) */
+#define KGE_F_NO_UPDATE   2u /* compute loss/grads only (parity tests) */
+
+/* An embedding table, optionally split by contiguous row range over up to 8 GPUs of one NVSwitch
+ * domain.  shard[r] is a device pointer valid on THIS device (local memory for r == own rank, a
+ * peer mapping otherwise) holding rows [r*rows_per_shard, min(rows,(r+1)*rows_per_shard)).
+ * Replaces the reference's single tf.Variable ent_emb[E,K] (models/EmbeddingModel.py:547-601) and
+ * its host-paged "large graph" mode (models/EmbeddingModel.py:645-666, :1070-1097). */
+typedef struct kge_table {
+    float*  shard[KGE_MAX_SHARDS];
+    int64_t rows;
+    int64_t rows_per_shard;
+    int32_t n_shards;
+    int32_t K;
+} kge_table;
+
+/* One optimisation step on one batch == EmbeddingModel._get_model_loss + optimizer.minimize
+ * (models/EmbeddingModel.py:614-822, :1415-1418). */
+typedef struct kge_train_args {
+    int32_t  model, loss, opt, side;
+    uint32_t flags;
+    int32_t  k;            /* user embedding size */
+    int32_t  eta;          /* negatives per positive */
+    float    margin;       /* pairwise margin (losses/pairwise.py:66) */
+    float    lr, beta1, beta2, eps, momentum;
+    uint64_t seed;         /* Philox key of the in-kernel corruption generator */
+    uint64_t step;         /* 1-based global optimizer step; also the Philox counter high word */
+    uint64_t neg_index_base; /* global index of this rank's first negative (multi-GPU streams) */
+    kge_table ent, ent_m, ent_v;       /* weights + per-row optimizer state (same sharding) */
+    float   *rel, *rel_m, *rel_v;      /* [R,K] replicated */
+    int64_t  R;
+    const int32_t* pos;    /* [n_pos,3] device */
+    int64_t  n_pos;
+    const int32_t* repl;       /* optional [eta*n_pos] supplied replacement ids (parity input) */
+    const uint8_t* keep_subj;  /* optional [eta*n_pos] 1 = keep subject, replace object */
+    float*   loss_out;     /* device float[1]: batch loss (overwritten) */
+    float*   dbg_scores;   /* optional device [n_pos*(1+eta)]: positives then negatives (row j*n+i) */
+    float*   dbg_grad_ent; /* optional device dense [E,K]: summed row gradients (must be zeroed) */
+    float*   dbg_grad_rel; /* optional device dense [R,K] */
+} kge_train_args;
+
+int         kge_abi_version(void);
+const char* kge_last_error(void);
+
+/* per-device context (replaces the reference's implicit TF runtime state) */
+int kge_ctx_create(int device, kge_ctx** out);
+int kge_ctx_destroy(kge_ctx* ctx);
+/* bytes of device workspace currently held by the ctx */
+int64_t kge_ctx_workspace_bytes(kge_ctx* ctx);
+
+/* EmbeddingModel.predict / _lookup_embeddings + _fn  (models/EmbeddingModel.py:2101-2147, :490-533) */
+int kge_score(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
+              const int32_t* triples, int64_t n, float* out, void* stream);
+
+/* Whole step on one GPU (n_shards == 1): corruption generation -> fused score/loss/backward ->
+ * duplicate-row segmented reduction -> sparse row-wise optimizer. */
+int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* stream);
+
+/* The same step in three phases, for the row-sharded multi-GPU path where the host places
+ * NCCL collectives (key all-gather / barriers) between them:
+ *  1. kge_train_emit: draw corruptions, write this rank's sort keys (entity id, or E + relation id)
+ *     into keys_out[n_slots] with n_slots = (3+eta)*n_pos; slot layout documented in DESIGN.md.
+ *  2. kge_train_fwd_bwd: fused forward + loss + backward; per-slot gradient rows into grad_rows
+ *     [n_slots,K] (caller-owned so that peers can map it).
+ *  3. kge_train_apply: sort all ranks' keys, segmented-reduce duplicate rows reading gradient rows
+ *     through `grads` (shard r = rank r's grad_rows, rows_per_shard = n_slots_per_rank) and apply
+ *     the optimizer to rows in [row_begin,row_end) and to every relation row. */
+int kge_train_emit(kge_ctx* ctx, const kge_train_args* a, int32_t* keys_out, void* stream);
+int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* grad_rows, void* stream);
+int kge_train_apply(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, int64_t n_keys,
+                    const kge_table* grads, int64_t row_begin, int64_t row_end, void* stream);
+
+/* optional post-step row renormalisation (models/EmbeddingModel.py:1434-1439, clip_by_norm axes=1) */
+int kge_normalize_rows(kge_ctx* ctx, float* emb, int64_t rows, int K, void* stream);
+
+/* Known-triple filter: replaces SQLiteAdapter (datasets/sqlite_adapter.py:54-98, :234-262) and the
+ * per-test-triple queries of get_participating_entities (:449-508). Device-resident sorted
+ * (s,p)->objects and (p,o)->subjects indexes, deduplicated. */
+int kge_filter_build(kge_ctx* ctx, const int32_t* triples, int64_t F, int64_t E, int64_t R, void* stream);
+int kge_filter_clear(kge_ctx* ctx);
+/* number of distinct filter triples (host sync) */
+int64_t kge_filter_size_sync(kge_ctx* ctx);
+
+/* evaluate_performance / get_ranks (evaluation/protocol.py:726-979, models/EmbeddingModel.py:2046-2099,
+ * :1845-1986): all-entity sweep for every test triple with in-kernel x1e5 int quantisation (F7),
+ * filter applied in-kernel, rank count fused.  Sweeps candidate rows [row_begin,row_end) of the
+ * LOCAL shard `ent_local` (row 0 of ent_local == global row row_begin) and writes
+ * counts[T,2,4] int32 (side {0:object sweep, 1:subject sweep} x {gt, eq, gt_filtered, eq_filtered});
+ * counts from all shards are summed by the caller (NCCL all-reduce) before kge_rank_finalize.
+ * side (KGE_RANK_*) selects which sweeps run (KGE_RANK_S / KGE_RANK_O run one).
+ * use_tensor_cores: 1 = tcgen05 3xTF32 path (DistMult/ComplEx/HolE), 0 = fp32 CUDA-core sweep. */
+int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
+                    const float* ent_local, int64_t row_begin, int64_t row_end,
+                    const int32_t* test, int64_t T, int side, int filtered, int use_tensor_cores,
+                    int32_t* counts, void* stream);
+/* ranks_out: [T,2] (col 0 subject, col 1 object) for KGE_RANK_S_O, else [T]. */
+int kge_rank_finalize(kge_ctx* ctx, const int32_t* counts, int64_t T, int side, int strategy,
+                      int filtered, int32_t* ranks_out, void* stream);
+
+/* CUDA IPC helpers for mapping peer shards (one process per GPU). handle: 64 bytes. */
+int kge_ipc_export(void* dev_ptr, void* handle_out64);
+int kge_ipc_open(const void* handle64, void** dev_ptr_out);
+int kge_ipc_close(void* dev_ptr);
+int kge_enable_peer_access(int device, int peer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGE_B200_H */

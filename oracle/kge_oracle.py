@@ -1,0 +1,449 @@
+"""CPU oracle for the KGE hot path (train step + filtered ranking).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``emgraph_b200/`` may import this file; only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs use it, and there only as the checker / the CPU arm.
+
+It is a NumPy restatement of the reference's algorithm (bi-graph/Emgraph 1.0.0-rc1).  Every
+function cites the reference ``file:line`` it follows (paths relative to ``/root/reference``).
+The arithmetic lives in TensorFlow 2.2 in the reference, which is absent from
+``/root/reference`` and not installable here; the restatement therefore follows the reference's
+*call sites* op by op.
+
+Parity pin status
+-----------------
+* id mapping, eval-corruption layout, metrics, rank_score: pinned against the reference's own
+  golden vectors (tests/emgraph/evaluation/test_protocol.py:418-455, :490-496;
+  tests/emgraph/evaluation/test_metrics.py:6-39) in ``tests/test_oracle_golden.py``.
+* scores / losses / gradients / filtered ranks: the reference holds no golden vectors for these
+  (SURVEY.md section 8c).  They are pinned instead against outputs of the reference's OWN Python
+  (``_fn``, ``Loss._apply``, ``generate_corruptions_for_fit/_for_eval``, ``perform_comparision``,
+  ``SQLiteAdapter.get_participating_entities``) executed in the builder container through the
+  ``tensorflow`` shim in ``oracle/ref_shim.py``; the resulting vectors are committed under
+  ``tests/golden/`` together with the generating script ``oracle/make_golden.py``.
+* Keras optimizer first-step formulas (Adam/Adagrad/SGD sparse apply) come from TF's documented
+  semantics, the source being absent: "parity unpinned" for the optimizer update beyond that.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MODELS = ("TransE", "DistMult", "ComplEx", "HolE")
+LOSSES = ("pairwise", "nll", "multiclass_nll")
+
+CLIP_LO, CLIP_HI = -75.0, 75.0  # losses/_loss_constants.py:14,16
+SCORE_COMPARISON_PRECISION = 1e5  # utils/constants.py:87
+
+
+# --------------------------------------------------------------------------------------------
+# id mapping  (evaluation/protocol.py:410-445, :662-723)
+# --------------------------------------------------------------------------------------------
+def create_mappings(X):
+    """np.unique (sorted) ids for entities (subjects+objects) and relations.
+    evaluation/protocol.py:429-445."""
+    X = np.asarray(X)
+    unique_ent = np.unique(np.concatenate((X[:, 0], X[:, 2])))
+    unique_rel = np.unique(X[:, 1])
+    rel_to_idx = dict(zip(unique_rel, range(len(unique_rel))))
+    ent_to_idx = dict(zip(unique_ent, range(len(unique_ent))))
+    return rel_to_idx, ent_to_idx
+
+
+def to_idx(X, ent_to_idx, rel_to_idx):
+    """evaluation/protocol.py:662-723 -- unseen label -> ValueError."""
+    X = np.asarray(X)
+    if X.ndim == 1:
+        X = X[np.newaxis, :]
+    out = np.empty(X.shape, dtype=np.int64)
+    for c, m in ((0, ent_to_idx), (1, rel_to_idx), (2, ent_to_idx)):
+        for r in range(X.shape[0]):
+            v = m.get(X[r, c])
+            if v is None:
+                raise ValueError("Input triples include one or more concepts not present in the training set.")
+            out[r, c] = v
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# scoring functions  (models/TransE.py:208-216, DistMult.py:201, ComplEx.py:288-298, HolE.py:189)
+# --------------------------------------------------------------------------------------------
+def internal_k(model, k):
+    """ComplEx/HolE rows are [re(k) | im(k)]  (models/ComplEx.py:224)."""
+    return 2 * k if model in ("ComplEx", "HolE") else k
+
+
+def score_rows(model, k, e_s, e_p, e_o, norm=1, dtype=np.float32):
+    """_fn on already gathered rows [n, K] -> [n]."""
+    e_s = np.asarray(e_s, dtype=dtype)
+    e_p = np.asarray(e_p, dtype=dtype)
+    e_o = np.asarray(e_o, dtype=dtype)
+    if model == "TransE":
+        u = e_s + e_p - e_o
+        if norm == 1:
+            return -np.sum(np.abs(u), axis=1, dtype=dtype)
+        return -np.sqrt(np.sum(u * u, axis=1, dtype=dtype))
+    if model == "DistMult":
+        return np.sum(e_s * e_p * e_o, axis=1, dtype=dtype)
+    if model in ("ComplEx", "HolE"):
+        s_r, s_i = e_s[:, :k], e_s[:, k:]
+        p_r, p_i = e_p[:, :k], e_p[:, k:]
+        o_r, o_i = e_o[:, :k], e_o[:, k:]
+        f = (
+            np.sum(p_r * s_r * o_r, axis=1, dtype=dtype)
+            + np.sum(p_r * s_i * o_i, axis=1, dtype=dtype)
+            + np.sum(p_i * s_r * o_i, axis=1, dtype=dtype)
+            - np.sum(p_i * s_i * o_r, axis=1, dtype=dtype)
+        )
+        if model == "HolE":
+            f = dtype(2.0 / k) * f  # models/HolE.py:189
+        return f
+    raise ValueError(model)
+
+
+def score(model, k, ent, rel, triples, norm=1, dtype=np.float32):
+    """_lookup_embeddings + _fn  (models/EmbeddingModel.py:490-533, :675-677)."""
+    t = np.asarray(triples).reshape(-1, 3)
+    return score_rows(model, k, ent[t[:, 0]], rel[t[:, 1]], ent[t[:, 2]], norm, dtype)
+
+
+def score_grad_rows(model, k, e_s, e_p, e_o, norm=1, dtype=np.float64):
+    """d f / d(e_s, e_p, e_o) per triple."""
+    e_s = np.asarray(e_s, dtype=dtype)
+    e_p = np.asarray(e_p, dtype=dtype)
+    e_o = np.asarray(e_o, dtype=dtype)
+    if model == "TransE":
+        u = e_s + e_p - e_o
+        if norm == 1:
+            g = -np.sign(u)
+        else:
+            nrm = np.sqrt(np.sum(u * u, axis=1, keepdims=True))
+            g = -u / nrm
+        return g, g, -g
+    if model == "DistMult":
+        return e_p * e_o, e_s * e_o, e_s * e_p
+    s_r, s_i = e_s[:, :k], e_s[:, k:]
+    p_r, p_i = e_p[:, :k], e_p[:, k:]
+    o_r, o_i = e_o[:, :k], e_o[:, k:]
+    g_s = np.concatenate([p_r * o_r + p_i * o_i, p_r * o_i - p_i * o_r], axis=1)
+    g_o = np.concatenate([p_r * s_r - p_i * s_i, p_r * s_i + p_i * s_r], axis=1)
+    g_p = np.concatenate([s_r * o_r + s_i * o_i, s_r * o_i - s_i * o_r], axis=1)
+    if model == "HolE":
+        c = 2.0 / k
+        g_s, g_p, g_o = c * g_s, c * g_p, c * g_o
+    return g_s, g_p, g_o
+
+
+# --------------------------------------------------------------------------------------------
+# training corruptions  (evaluation/protocol.py:586-659)
+# --------------------------------------------------------------------------------------------
+def corruptions_for_fit(X, eta, keep_subj, repl):
+    """Row j*n+i corrupts positive i (tile, :598); keep_subj=1 -> object replaced (:643-653)."""
+    X = np.asarray(X)
+    n = X.shape[0]
+    ds = np.tile(X.reshape(-1), eta).reshape(n * eta, 3)
+    ks = np.asarray(keep_subj).astype(ds.dtype)
+    ko = 1 - ks
+    repl = np.asarray(repl).astype(ds.dtype)
+    subj = ks * ds[:, 0] + ko * repl
+    obj = ko * ds[:, 2] + ks * repl
+    return np.stack([subj, ds[:, 1], obj], axis=1)
+
+
+def side_mask(side, n_eta, rng=None):
+    """'s,o' == 's+o' -> Bernoulli(1/2); 'o' keeps the subject; 's' keeps the object (:587-608)."""
+    if side in ("s,o", "s+o"):
+        return rng.integers(0, 2, size=n_eta).astype(np.uint8)
+    if side == "o":
+        return np.ones(n_eta, np.uint8)
+    if side == "s":
+        return np.zeros(n_eta, np.uint8)
+    raise ValueError("Invalid argument value {} for corruption side passed for evaluation.".format(side))
+
+
+# --------------------------------------------------------------------------------------------
+# losses  (losses/pairwise.py:66-70, nll.py:55-59, nll_multiclass.py:70-81, utils.py:44-53)
+# --------------------------------------------------------------------------------------------
+def _clip(x):
+    return np.clip(x, CLIP_LO, CLIP_HI)
+
+
+def loss_and_dscore(loss, pos, neg, eta, margin=1.0, dtype=np.float32):
+    """Loss value and dL/dpos [n], dL/dneg [eta*n].  pos is NOT tiled on entry; the eta-tiling of
+    models/EmbeddingModel.py:724-729 is applied here for pairwise / nll."""
+    pos = np.asarray(pos, dtype=dtype)
+    neg = np.asarray(neg, dtype=dtype)
+    n = pos.shape[0]
+    negm = neg.reshape(eta, n)
+    if loss == "pairwise":
+        t = dtype(margin) - pos[None, :] + negm
+        val = np.sum(np.maximum(t, 0), dtype=dtype)
+        act = (t >= 0).astype(dtype)  # tf.maximum: gradient to first arg when x >= y
+        return val, -act.sum(axis=0), act.reshape(-1)
+    if loss == "nll":
+        cp, cn = _clip(pos), _clip(negm)
+        val = dtype(eta) * np.sum(np.log(1 + np.exp(-cp)), dtype=dtype) + np.sum(np.log(1 + np.exp(cn)), dtype=dtype)
+        in_p = ((pos >= CLIP_LO) & (pos <= CLIP_HI)).astype(dtype)
+        in_n = ((negm >= CLIP_LO) & (negm <= CLIP_HI)).astype(dtype)
+        dpos = -dtype(eta) * (1 / (1 + np.exp(cp))) * in_p
+        dneg = (1 / (1 + np.exp(-cn))) * in_n
+        return val, dpos, dneg.reshape(-1)
+    if loss == "multiclass_nll":
+        cp, cn = _clip(pos), _clip(negm)
+        pe, ne = np.exp(cp), np.exp(cn)
+        z = ne.sum(axis=0, dtype=dtype) + pe
+        val = -np.sum(np.log(pe / z), dtype=dtype)
+        in_p = ((pos >= CLIP_LO) & (pos <= CLIP_HI)).astype(dtype)
+        in_n = ((negm >= CLIP_LO) & (negm <= CLIP_HI)).astype(dtype)
+        dpos = -(1 - pe / z) * in_p
+        dneg = (ne / z[None, :]) * in_n
+        return val, dpos, dneg.reshape(-1)
+    raise ValueError("Unsupported loss function: {}".format(loss))
+
+
+# --------------------------------------------------------------------------------------------
+# optimizer step as the reference executes it: fresh Keras optimizer per batch (F5)
+# (training/adam.py:45-46, adagrad.py:42-45, momentum.py:63-68, sgd.py:97-124)
+# --------------------------------------------------------------------------------------------
+ADAM_B1, ADAM_B2, KERAS_EPS = 0.9, 0.999, 1e-7
+ADAGRAD_ACC0 = 0.1
+
+
+def optimizer_step(opt, w, g, touched, lr, state=None, step=1, momentum=0.9, dtype=np.float32):
+    """Update rows `touched` (bool [rows]) of w in place-free style; returns (w_new, state_new).
+    state=None => the reference's fresh-state step (F5).  Persistent state => the engine's lazy
+    stateful mode (rows without gradient skipped)."""
+    w = np.array(w, dtype=dtype)
+    g = np.asarray(g, dtype=dtype)
+    t = np.asarray(touched, dtype=bool)
+    lr = dtype(lr)
+    if opt == "adam":
+        m, v = (np.zeros_like(w), np.zeros_like(w)) if state is None else (state[0].copy(), state[1].copy())
+        b1, b2 = dtype(ADAM_B1), dtype(ADAM_B2)
+        m[t] = b1 * m[t] + (1 - b1) * g[t]
+        v[t] = b2 * v[t] + (1 - b2) * g[t] * g[t]
+        lr_t = lr * dtype(np.sqrt(1.0 - ADAM_B2 ** step) / (1.0 - ADAM_B1 ** step))
+        w[t] = w[t] - lr_t * m[t] / (np.sqrt(v[t]) + dtype(KERAS_EPS))
+        return w, (m, v)
+    if opt == "adagrad":
+        a = np.full_like(w, ADAGRAD_ACC0) if state is None else state[0].copy()
+        a[t] = a[t] + g[t] * g[t]
+        w[t] = w[t] - lr * g[t] / (np.sqrt(a[t]) + dtype(KERAS_EPS))
+        return w, (a,)
+    if opt == "momentum":
+        vel = np.zeros_like(w) if state is None else state[0].copy()
+        vel[t] = dtype(momentum) * vel[t] - lr * g[t]
+        w[t] = w[t] + vel[t]
+        return w, (vel,)
+    if opt == "sgd":
+        w[t] = w[t] - lr * g[t]
+        return w, ()
+    raise ValueError("Unsupported optimizer: {}".format(opt))
+
+
+# --------------------------------------------------------------------------------------------
+# one training step  (models/EmbeddingModel.py:614-822 + optimizer.minimize :1415-1418)
+# --------------------------------------------------------------------------------------------
+def train_step(model, k, loss, eta, ent, rel, pos, keep_subj, repl, margin=1.0, norm=1,
+               opt=None, lr=5e-4, state=None, step=1, dtype=np.float32, grad_dtype=np.float64):
+    """Forward in `dtype` (the reference is fp32), gradients in `grad_dtype`.
+    Returns dict(loss, scores_pos, scores_neg, grad_ent[E,K], grad_rel[R,K], touched_ent, touched_rel
+    [, ent_new, rel_new, state_ent, state_rel])."""
+    pos = np.asarray(pos).reshape(-1, 3)
+    n = pos.shape[0]
+    neg = corruptions_for_fit(pos, eta, keep_subj, repl)
+    sp = score(model, k, ent, rel, pos, norm, dtype)
+    sn = score(model, k, ent, rel, neg, norm, dtype)
+    val, dpos, dneg = loss_and_dscore(loss, sp, sn, eta, margin, dtype)
+    gd = grad_dtype
+    g_ent = np.zeros(ent.shape, dtype=gd)
+    g_rel = np.zeros(rel.shape, dtype=gd)
+    for trip, dsc in ((pos, dpos), (neg, dneg)):
+        gs, gp, go = score_grad_rows(model, k, ent[trip[:, 0]], rel[trip[:, 1]], ent[trip[:, 2]], norm, gd)
+        w = np.asarray(dsc, dtype=gd)[:, None]
+        np.add.at(g_ent, trip[:, 0], w * gs)
+        np.add.at(g_ent, trip[:, 2], w * go)
+        np.add.at(g_rel, trip[:, 1], w * gp)
+    t_ent = np.zeros(ent.shape[0], bool)
+    t_ent[pos[:, 0]] = True
+    t_ent[pos[:, 2]] = True
+    t_ent[neg[:, 0]] = True
+    t_ent[neg[:, 2]] = True
+    t_rel = np.zeros(rel.shape[0], bool)
+    t_rel[pos[:, 1]] = True
+    out = dict(loss=val, scores_pos=sp, scores_neg=sn, grad_ent=g_ent, grad_rel=g_rel,
+               touched_ent=t_ent, touched_rel=t_rel, neg=neg)
+    if opt is not None:
+        st_e = None if state is None else state[0]
+        st_r = None if state is None else state[1]
+        out["ent_new"], out["state_ent"] = optimizer_step(opt, ent, g_ent, t_ent, lr, st_e, step, dtype=dtype)
+        out["rel_new"], out["state_rel"] = optimizer_step(opt, rel, g_rel, t_rel, lr, st_r, step, dtype=dtype)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# evaluation corruptions + filter sets + ranking
+# --------------------------------------------------------------------------------------------
+def corruptions_for_eval(x, entities, side="s,o"):
+    """[ (s,p,e) for all e ; (e,p,o) for all e ]  (evaluation/protocol.py:448-528)."""
+    x = np.asarray(x).reshape(3)
+    ents = np.asarray(entities).reshape(-1)
+    if side == "s,o":
+        side = "s+o"
+    if side not in ("s+o", "s", "o"):
+        raise ValueError("Invalid argument value for corruption side passed for evaluation")
+    n = ents.shape[0]
+    obj_sweep = np.stack([np.full(n, x[0]), np.full(n, x[1]), ents], axis=1)
+    sub_sweep = np.stack([ents, np.full(n, x[1]), np.full(n, x[2])], axis=1)
+    if side == "s+o":
+        return np.concatenate([obj_sweep, sub_sweep], axis=0)
+    return obj_sweep if side == "o" else sub_sweep
+
+
+class FilterIndex:
+    """(s,p)->objects and (p,o)->subjects, deduplicated, self always included
+    (datasets/sqlite_adapter.py:472-489: ``select o UNION select distinct object ...``)."""
+
+    def __init__(self, filter_triples):
+        self.sp = {}
+        self.po = {}
+        for s, p, o in np.asarray(filter_triples).reshape(-1, 3):
+            self.sp.setdefault((int(s), int(p)), set()).add(int(o))
+            self.po.setdefault((int(p), int(o)), set()).add(int(s))
+
+    def participating(self, x):
+        s, p, o = (int(v) for v in np.asarray(x).reshape(3))
+        objs = sorted(self.sp.get((s, p), set()) | {o})
+        subs = sorted(self.po.get((p, o), set()) | {s})
+        return np.asarray(objs, np.int64), np.asarray(subs, np.int64)
+
+
+def quantise(x):
+    """tf.cast(x * 1e5, tf.int32): fp32 multiply then truncate toward zero
+    (models/EmbeddingModel.py:2010-2014)."""
+    return (np.asarray(x, np.float32) * np.float32(SCORE_COMPARISON_PRECISION)).astype(np.int32)
+
+
+def compare(score_corr, score_pos, strategy="worst"):
+    """perform_comparision  (models/EmbeddingModel.py:1989-2033)."""
+    assert strategy in ("worst", "best", "middle"), "Invalid score comparision type!"
+    c, p = quantise(score_corr), quantise(score_pos)
+    if strategy == "best":
+        return int(np.sum(c > p))
+    if strategy == "middle":
+        return int(np.sum(c > p)) + int(np.ceil(np.sum(c == p) / 2))
+    return int(np.sum(c >= p))
+
+
+def rank_one(model, k, ent, rel, x, filt=None, side="s,o", strategy="worst", norm=1, dtype=np.float32):
+    """Per-test-triple rank (models/EmbeddingModel.py:1856-1866, :1883-1892, :1942-1986)."""
+    E = ent.shape[0]
+    x = np.asarray(x).reshape(3)
+    corr = corruptions_for_eval(x, np.arange(E), side)
+    sc = score(model, k, ent, rel, corr, norm, dtype)
+    sp = score(model, k, ent, rel, x, norm, dtype)[0]
+    hi_o = hi_s = 0
+    if filt is not None:
+        idx_o, idx_s = filt.participating(x)
+    if side == "s,o":
+        obj_sc, sub_sc = sc[:E], sc[E:]
+        if filt is not None:
+            hi_o = compare(obj_sc[idx_o], sp, strategy)
+            hi_s = compare(sub_sc[idx_s], sp, strategy)
+        return [compare(sub_sc, sp, strategy) + 1 - hi_s, compare(obj_sc, sp, strategy) + 1 - hi_o]
+    if filt is not None:
+        if side in ("o", "s+o"):
+            hi_o = compare(sc[idx_o], sp, strategy)
+        if side == "s+o":
+            hi_s = compare(sc[idx_s + E], sp, strategy)
+        elif side == "s":
+            hi_s = compare(sc[idx_s], sp, strategy)
+    return compare(sc, sp, strategy) + 1 - hi_s - hi_o
+
+
+def ranks(model, k, ent, rel, test, filter_triples=None, side="s,o", strategy="worst", norm=1, dtype=np.float32):
+    """Intended semantics of get_ranks: the per-triple graph evaluated for EVERY test triple
+    (models/EmbeddingModel.py:2046-2099)."""
+    filt = FilterIndex(filter_triples) if filter_triples is not None else None
+    return np.asarray([rank_one(model, k, ent, rel, x, filt, side, strategy, norm, dtype)
+                       for x in np.asarray(test).reshape(-1, 3)])
+
+
+def sweep_scores(model, k, ent, rel, x, norm=1, dtype=np.float64):
+    """All-entity object-side and subject-side scores + positive score for one triple, in `dtype`.
+    Used by the tie classifier: a rank mismatch is admissible only if some candidate score sits
+    within tolerance of the positive's quantisation boundary."""
+    E = ent.shape[0]
+    corr = corruptions_for_eval(x, np.arange(E), "s+o")
+    sc = score(model, k, ent.astype(dtype), rel.astype(dtype), corr, norm, dtype)
+    sp = score(model, k, ent.astype(dtype), rel.astype(dtype), x, norm, dtype)[0]
+    return sc[:E], sc[E:], sp
+
+
+# --------------------------------------------------------------------------------------------
+# metrics  (evaluation/metrics.py:66-67, :129-130, :161-164, :221-222)
+# --------------------------------------------------------------------------------------------
+def hits_at_n_score(ranks_, n):
+    r = np.asarray(ranks_).reshape(-1)
+    return np.sum(r <= n) / len(r)
+
+
+def mrr_score(ranks_):
+    r = np.asarray(ranks_).reshape(-1)
+    return np.sum(1 / r) / len(r)
+
+
+def mr_score(ranks_):
+    r = np.asarray(ranks_).reshape(-1)
+    return np.sum(r) / len(r)
+
+
+def rank_score(y_true, y_pred, pos_lab=1):
+    idx = np.argsort(y_pred)[::-1]
+    y_ord = np.asarray(y_true)[idx]
+    return int(np.where(y_ord == pos_lab)[0][0] + 1)
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic graphs of the benchmark shapes -- shared by tests and bench
+# --------------------------------------------------------------------------------------------
+def synthetic_triples(E, R, N, seed=0, zipf=False, cover=True):
+    """Unique (s,p,o) int32 triples, no self loops, every entity appearing at least once."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if zipf:
+        w = 1.0 / np.arange(1, E + 1)
+        w /= w.sum()
+        perm = rng.permutation(E)
+        cdf = np.cumsum(w)
+
+        def draw(m):
+            return perm[np.minimum(np.searchsorted(cdf, rng.random(m)), E - 1)]
+    else:
+        def draw(m):
+            return rng.integers(0, E, size=m)
+    parts = []
+    have = 0
+    if cover:
+        chain = np.stack([np.arange(E), rng.integers(0, R, size=E), (np.arange(E) + 1) % E], axis=1)
+        parts.append(chain[: min(E, N)])
+        have = parts[0].shape[0]
+    seen = None
+    out = np.concatenate(parts, axis=0) if parts else np.zeros((0, 3), np.int64)
+    while True:
+        key = (out[:, 0].astype(np.int64) * R + out[:, 1]) * E + out[:, 2]
+        _, first = np.unique(key, return_index=True)
+        out = out[np.sort(first)]
+        if out.shape[0] >= N:
+            break
+        m = int((N - out.shape[0]) * 1.2) + 16
+        s, o, p = draw(m), draw(m), rng.integers(0, R, size=m)
+        keep = s != o
+        out = np.concatenate([out, np.stack([s[keep], p[keep], o[keep]], axis=1)], axis=0)
+    del seen, have
+    return out[:N].astype(np.int32)
+
+
+def glorot_uniform(rows, cols, seed):
+    """U(+-sqrt(6/(rows+cols)))  (initializers/glorot_uniform.py:59-99)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lim = np.sqrt(6.0 / (rows + cols))
+    return rng.uniform(-lim, lim, size=(rows, cols)).astype(np.float32)

@@ -1,0 +1,89 @@
+"""Generate tests/golden/*.npz by executing the reference's OWN Python (see oracle/ref_shim.py).
+
+Run in the builder container only (needs /root/reference):  python oracle/make_golden.py
+The outputs are results (scores, losses, gradients, ranks), not reference code; they travel to the
+GPU box with the repo, where /root/reference does not exist.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import kge_oracle as ko  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+TRAIN_CASES = [
+    # name, model, loss, k, eta, E, R, n, side, loss_params, emb_params
+    ("transe_l1_pairwise", "TransE", "pairwise", 12, 5, 64, 4, 48, "s,o", {"margin": 1.0}, {}),
+    ("transe_l2_nll", "TransE", "nll", 16, 3, 64, 4, 40, "s,o", {}, {"norm": 2}),
+    ("transe_l1_multiclass", "TransE", "multiclass_nll", 10, 4, 50, 3, 33, "o", {}, {}),
+    ("distmult_pairwise_m5", "DistMult", "pairwise", 16, 6, 64, 5, 48, "s,o", {"margin": 5.0}, {}),
+    ("distmult_nll", "DistMult", "nll", 20, 3, 40, 5, 31, "s", {}, {}),
+    ("distmult_multiclass", "DistMult", "multiclass_nll", 8, 7, 64, 5, 48, "s,o", {}, {}),
+    ("complex_nll", "ComplEx", "nll", 12, 5, 64, 6, 48, "s,o", {}, {}),
+    ("complex_pairwise", "ComplEx", "pairwise", 8, 4, 30, 2, 17, "s,o", {"margin": 2.0}, {}),
+    ("complex_multiclass", "ComplEx", "multiclass_nll", 6, 9, 64, 6, 40, "s,o", {}, {}),
+    ("hole_multiclass", "HolE", "multiclass_nll", 16, 5, 64, 3, 48, "s,o", {}, {}),
+    ("hole_nll", "HolE", "nll", 10, 2, 48, 3, 25, "s,o", {}, {}),
+    ("hole_pairwise", "HolE", "pairwise", 6, 3, 48, 3, 25, "o", {"margin": 0.5}, {}),
+]
+
+RANK_CASES = [
+    # name, model, k, E, R, F, T, emb_params, scale
+    ("rank_transe_l1", "TransE", 10, 120, 4, 900, 60, {}, 0.5),
+    ("rank_transe_l2", "TransE", 8, 90, 3, 600, 40, {"norm": 2}, 0.5),
+    ("rank_distmult", "DistMult", 16, 150, 5, 1200, 60, {}, 0.7),
+    ("rank_complex", "ComplEx", 12, 130, 4, 1000, 60, {}, 0.7),
+    ("rank_hole", "HolE", 8, 100, 3, 800, 50, {}, 1.0),
+]
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    assert ref_shim.available(), "needs /root/reference"
+    for ci, (name, model, loss, k, eta, E, R, n, side, lp, ep) in enumerate(TRAIN_CASES):
+        rng = np.random.Generator(np.random.PCG64(1000 + ci))
+        K = ko.internal_k(model, k)
+        ent = (rng.normal(size=(E, K)) * 0.6).astype(np.float32)
+        rel = (rng.normal(size=(R, K)) * 0.6).astype(np.float32)
+        pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+        keep = ko.side_mask(side, n * eta, rng)
+        repl = rng.integers(0, E, n * eta).astype(np.int32)
+        ref = ref_shim.ref_train_forward_backward(model, k, eta, loss, ent, rel, pos, keep, repl, lp, ep, side)
+        np.savez_compressed(
+            os.path.join(OUT, "train_%s.npz" % name),
+            model=model, loss_name=loss, k=k, eta=eta, side=side, margin=float(lp.get("margin", 1.0)),
+            norm=int(ep.get("norm", 1)), ent=ent, rel=rel, pos=pos, keep_subj=keep, repl=repl,
+            loss=np.float32(ref["loss"]), scores_pos=ref["scores_pos"], scores_neg=ref["scores_neg"],
+            neg=ref["neg"].astype(np.int32), grad_ent=ref["grad_ent"], grad_rel=ref["grad_rel"])
+        print("train", name, "loss", ref["loss"])
+    for ci, (name, model, k, E, R, F, T, ep, scale) in enumerate(RANK_CASES):
+        rng = np.random.Generator(np.random.PCG64(2000 + ci))
+        K = ko.internal_k(model, k)
+        ent = (rng.normal(size=(E, K)) * scale).astype(np.float32)
+        rel = (rng.normal(size=(R, K)) * scale).astype(np.float32)
+        filt = ko.synthetic_triples(E, R, F, seed=300 + ci)
+        # duplicates in the filter must be harmless (SQL UNION / DISTINCT)
+        filt = np.concatenate([filt, filt[:17]], axis=0)
+        test = filt[rng.permutation(F)[:T]].copy()
+        # a few test triples that are NOT in the filter: self must still be filtered
+        test[:5, 2] = (test[:5, 2] + 7) % E
+        out = dict(model=model, k=k, norm=int(ep.get("norm", 1)), ent=ent, rel=rel, filt=filt, test=test)
+        for side in ("s,o", "s+o", "s", "o"):
+            for strat in ("worst", "best", "middle"):
+                for fl in (0, 1):
+                    r = ref_shim.ref_ranks(model, k, ent, rel, test, filt if fl else None, side, strat, ep)
+                    out["ranks_%s_%s_%d" % (side.replace(",", "c").replace("+", "p"), strat, fl)] = r.astype(np.int32)
+        np.savez_compressed(os.path.join(OUT, "%s.npz" % name), **out)
+        print("rank", name, out["ranks_sco_worst_1"][:4].tolist())
+
+
+if __name__ == "__main__":
+    main()

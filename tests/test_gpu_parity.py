@@ -1,0 +1,293 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and against the committed
+outputs of the reference's own Python (tests/golden).  Tolerances: scores / losses / gradients
+1e-5 relative (BASELINE.json north_star); ranks identical except where a candidate's score ties
+the positive's within that tolerance (classified by ``_admissible``)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kge_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-5
+
+
+def _ids(model, norm=1):
+    from emgraph_b200.engine import model_id
+    return model_id(model, norm)
+
+
+def _dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def _close(a, b, rtol=RTOL, scale=None):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    sc = max(1.0, float(np.abs(b).max())) if scale is None else scale
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * sc)
+
+
+def run_step(engine, model, k, loss, eta, ent, rel, pos, keep, repl, margin=1.0, norm=1, opt="adam", lr=1e-3,
+             flags=0, state=None, step=1):
+    from emgraph_b200 import _lib
+    n = pos.shape[0]
+    ent_d, rel_d = _dev(ent), _dev(rel)
+    out = dict(loss=torch.zeros(1, device="cuda"), scores=torch.zeros(n * (1 + eta), device="cuda"),
+               g_ent=torch.zeros_like(ent_d), g_rel=torch.zeros_like(rel_d))
+    st = {}
+    if state is not None:
+        st = {k_: _dev(v) for k_, v in state.items()}
+    a = engine.train_args(model=_ids(model, norm), loss=_lib.LOSS_IDS[loss], opt=_lib.OPT_IDS[opt], k=k, eta=eta,
+                          ent=ent_d, rel=rel_d, pos=_dev(pos, torch.int32), loss_out=out["loss"], flags=flags,
+                          margin=margin, lr=lr, step=step, repl=_dev(repl, torch.int32), keep_subj=_dev(keep, torch.uint8),
+                          dbg_scores=out["scores"], dbg_grad_ent=out["g_ent"], dbg_grad_rel=out["g_rel"], **st)
+    engine.train_step(a)
+    torch.cuda.synchronize()
+    res = {k_: v.cpu().numpy() for k_, v in out.items()}
+    res["ent"], res["rel"] = ent_d.cpu().numpy(), rel_d.cpu().numpy()
+    res["state"] = {k_: v.cpu().numpy() for k_, v in st.items()}
+    return res
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "train_*.npz"))), ids=os.path.basename)
+def test_train_step_vs_reference_golden(engine, path):
+    """scores, loss and summed row gradients against the reference's own _fn / loss.apply / autograd."""
+    from emgraph_b200 import _lib
+    g = np.load(path)
+    model, k, eta = str(g["model"]), int(g["k"]), int(g["eta"])
+    r = run_step(engine, model, k, str(g["loss_name"]), eta, g["ent"], g["rel"], g["pos"], g["keep_subj"], g["repl"],
+                 margin=float(g["margin"]), norm=int(g["norm"]), flags=_lib.F_NO_UPDATE)
+    n = g["pos"].shape[0]
+    _close(r["scores"][:n], g["scores_pos"])
+    _close(r["scores"][n:], g["scores_neg"])
+    np.testing.assert_allclose(r["loss"][0], g["loss"], rtol=RTOL)
+    _close(r["g_ent"], g["grad_ent"])
+    _close(r["g_rel"], g["grad_rel"])
+    # NO_UPDATE leaves the parameters untouched
+    np.testing.assert_array_equal(r["ent"], g["ent"])
+    np.testing.assert_array_equal(r["rel"], g["rel"])
+    # predict path agrees too
+    sc = engine.score(_ids(model, int(g["norm"])), k, _dev(g["ent"]), _dev(g["rel"]), _dev(g["pos"], torch.int32)).cpu().numpy()
+    _close(sc, g["scores_pos"])
+
+
+@pytest.mark.parametrize("opt", ["adam", "adagrad", "momentum", "sgd"])
+def test_reset_state_update_matches_keras_first_step(engine, opt):
+    """Reference-faithful mode: fresh optimizer state on every batch."""
+    from emgraph_b200 import _lib
+    g = np.load(os.path.join(GOLD, "train_complex_nll.npz"))
+    model, k, eta = str(g["model"]), int(g["k"]), int(g["eta"])
+    r = run_step(engine, model, k, "nll", eta, g["ent"], g["rel"], g["pos"], g["keep_subj"], g["repl"], opt=opt, lr=1e-2,
+                 flags=_lib.F_RESET_STATE)
+    o = ko.train_step(model, k, "nll", eta, g["ent"], g["rel"], g["pos"], g["keep_subj"], g["repl"], opt=opt, lr=1e-2)
+    # rows without gradient are untouched, bit for bit
+    np.testing.assert_array_equal(r["ent"][~o["touched_ent"]], g["ent"][~o["touched_ent"]])
+    if opt == "adam":
+        # fresh-state Adam ~ lr*sign(g): entries with |g| ~ eps are ill-conditioned; compare where |g| >> eps
+        big = np.abs(o["grad_ent"]) > 1e-3
+        np.testing.assert_allclose(r["ent"][big], o["ent_new"][big], rtol=1e-5, atol=1e-6)
+    else:
+        np.testing.assert_allclose(r["ent"], o["ent_new"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(r["rel"], o["rel_new"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("opt", ["adam", "adagrad", "momentum"])
+def test_stateful_sparse_optimizer_three_steps(engine, opt):
+    rng = np.random.default_rng(5)
+    E, R, k, eta, n = 300, 7, 16, 4, 128
+    model = "DistMult"
+    ent = (rng.normal(size=(E, k)) * 0.5).astype(np.float32)
+    rel = (rng.normal(size=(R, k)) * 0.5).astype(np.float32)
+    if opt == "adam":
+        st = dict(ent_m=np.zeros_like(ent), ent_v=np.zeros_like(ent), rel_m=np.zeros_like(rel), rel_v=np.zeros_like(rel))
+    elif opt == "adagrad":
+        st = dict(ent_m=np.full_like(ent, 0.1), rel_m=np.full_like(rel, 0.1))
+    else:
+        st = dict(ent_m=np.zeros_like(ent), rel_m=np.zeros_like(rel))
+    o_state = None
+    e_o, r_o = ent.copy(), rel.copy()
+    for step in (1, 2, 3):
+        pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+        keep = rng.integers(0, 2, n * eta).astype(np.uint8)
+        repl = rng.integers(0, E, n * eta).astype(np.int32)
+        r = run_step(engine, model, k, "pairwise", eta, ent, rel, pos, keep, repl, opt=opt, lr=5e-3, state=st, step=step)
+        o = ko.train_step(model, k, "pairwise", eta, e_o, r_o, pos, keep, repl, opt=opt, lr=5e-3, state=o_state, step=step)
+        if o_state is None and opt == "adagrad":
+            pass
+        ent, rel, st = r["ent"], r["rel"], r["state"]
+        e_o, r_o, o_state = o["ent_new"], o["rel_new"], (o["state_ent"], o["state_rel"])
+        np.testing.assert_allclose(ent, e_o, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(rel, r_o, rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("model,loss,k,eta", [
+    ("TransE", "pairwise", 100, 20), ("DistMult", "pairwise", 200, 10), ("ComplEx", "nll", 200, 20),
+    ("HolE", "multiclass_nll", 256, 20), ("DistMult", "nll", 256, 64), ("TransE", "multiclass_nll", 7, 33),
+    ("ComplEx", "pairwise", 5, 3), ("DistMult", "multiclass_nll", 130, 40),
+])
+def test_train_step_vs_oracle_bench_shapes(engine, model, loss, k, eta):
+    """The benchmark embedding sizes (and odd sizes that take the scalar path) against the oracle."""
+    from emgraph_b200 import _lib
+    rng = np.random.default_rng(11)
+    E, R, n = 3000, 11, 257
+    K = ko.internal_k(model, k)
+    lim = 0.4 if model != "TransE" else 0.2
+    ent = rng.uniform(-lim, lim, size=(E, K)).astype(np.float32)
+    rel = rng.uniform(-lim, lim, size=(R, K)).astype(np.float32)
+    pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+    keep = rng.integers(0, 2, n * eta).astype(np.uint8)
+    repl = rng.integers(0, E, n * eta).astype(np.int32)
+    margin = 5.0 if model == "DistMult" else 1.0
+    r = run_step(engine, model, k, loss, eta, ent, rel, pos, keep, repl, margin=margin, flags=_lib.F_NO_UPDATE)
+    o = ko.train_step(model, k, loss, eta, ent, rel, pos, keep, repl, margin=margin, dtype=np.float64)
+    _close(r["scores"][:n], o["scores_pos"])
+    _close(r["scores"][n:], o["scores_neg"])
+    np.testing.assert_allclose(r["loss"][0], o["loss"], rtol=RTOL)
+    if model == "TransE" and loss == "pairwise":
+        # L1 sign gradients are exact integers unless a hinge sits exactly on the boundary
+        _close(r["g_ent"], o["grad_ent"], rtol=1e-4)
+    else:
+        _close(r["g_ent"], o["grad_ent"])
+        _close(r["g_rel"], o["grad_rel"])
+
+
+def test_in_kernel_corruptions_are_uniform_and_reproducible(engine):
+    from emgraph_b200 import _lib
+    E, R, k, eta, n = 1000, 5, 8, 16, 4096
+    rng = np.random.default_rng(0)
+    ent = _dev(rng.normal(size=(E, k)).astype(np.float32))
+    rel = _dev(rng.normal(size=(R, k)).astype(np.float32))
+    pos = _dev(np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1), torch.int32)
+    S = (3 + eta) * n
+    outs = []
+    for seed, step in ((7, 1), (7, 1), (7, 2), (8, 1)):
+        keys = torch.empty(S, dtype=torch.int32, device="cuda")
+        a = engine.train_args(model=2, loss=0, opt=0, k=k, eta=eta, ent=ent, rel=rel, pos=pos,
+                              loss_out=torch.zeros(1, device="cuda"), seed=seed, step=step)
+        engine.train_emit(a, keys)
+        torch.cuda.synchronize()
+        outs.append(keys.cpu().numpy())
+    np.testing.assert_array_equal(outs[0], outs[1])
+    assert (outs[0] != outs[2]).mean() > 0.5 and (outs[0] != outs[3]).mean() > 0.5
+    p = pos.cpu().numpy()
+    np.testing.assert_array_equal(outs[0][:n], p[:, 0])
+    np.testing.assert_array_equal(outs[0][n:2 * n], p[:, 2])
+    np.testing.assert_array_equal(outs[0][2 * n + eta * n:], E + p[:, 1])
+    repl = outs[0][2 * n:2 * n + eta * n]
+    assert repl.min() >= 0 and repl.max() < E
+    hist = np.bincount(repl, minlength=E)
+    exp = eta * n / E
+    assert abs(hist.mean() - exp) < 1e-9 and hist.std() < 2.0 * np.sqrt(exp)
+
+
+# ------------------------------------------------------------------------------------------------
+# ranking
+# ------------------------------------------------------------------------------------------------
+def _admissible(model, k, ent, rel, x, side_col, got, exp, norm):
+    """A rank may differ from the oracle's only by the number of candidates whose score sits within
+    fp32 noise of the positive's x1e5 quantisation boundary."""
+    so, ss, sp = ko.sweep_scores(model, k, ent, rel, x, norm)
+    sc = so if side_col == 1 else ss
+    tol = 1.0 + 1e-6 * 1e5 * max(1.0, np.abs(sc).max())  # quanta
+    near = np.sum(np.abs(sc * 1e5 - sp * 1e5) <= tol)
+    return abs(int(got) - int(exp)) <= near
+
+
+def _rank_gpu(engine, model, k, ent, rel, test, filt, side, strat, norm=1, tc=False):
+    from emgraph_b200 import _lib
+    ent_d, rel_d = _dev(ent), _dev(rel)
+    if filt is not None:
+        engine.filter_build(_dev(filt, torch.int32), ent.shape[0], rel.shape[0])
+    r = engine.rank(_ids(model, norm), k, ent_d, rel_d, _dev(test, torch.int32), side=_lib.RANK_SIDE_IDS[side],
+                    strategy=_lib.STRATEGY_IDS[strat], filtered=filt is not None, use_tensor_cores=tc)
+    torch.cuda.synchronize()
+    return r.cpu().numpy()
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "rank_*.npz"))), ids=os.path.basename)
+def test_ranks_vs_reference_golden(engine, path):
+    g = np.load(path)
+    model, k, norm = str(g["model"]), int(g["k"]), int(g["norm"])
+    for side in ("s,o", "s+o", "s", "o"):
+        for strat in ("worst", "best", "middle"):
+            for fl in (0, 1):
+                key = "ranks_%s_%s_%d" % (side.replace(",", "c").replace("+", "p"), strat, fl)
+                got = _rank_gpu(engine, model, k, g["ent"], g["rel"], g["test"], g["filt"] if fl else None, side, strat, norm)
+                exp = g[key]
+                assert got.shape == exp.shape, key
+                bad = np.argwhere(got != exp)
+                for idx in bad:
+                    t = idx[0]
+                    col = idx[1] if exp.ndim == 2 else (1 if side == "o" else 0)
+                    assert _admissible(model, k, g["ent"], g["rel"], g["test"][t], col, got[tuple(idx)], exp[tuple(idx)], norm), \
+                        (key, t, got[tuple(idx)], exp[tuple(idx)])
+                assert len(bad) <= max(1, exp.size // 50), (key, len(bad))
+
+
+@pytest.mark.parametrize("model,k,E,norm", [("TransE", 100, 4100, 1), ("TransE", 33, 700, 2), ("DistMult", 200, 1500, 1),
+                                             ("ComplEx", 200, 1500, 1), ("HolE", 35, 900, 1)])
+def test_ranks_vs_oracle_larger(engine, model, k, E, norm):
+    rng = np.random.default_rng(3)
+    R, F, T = 9, 6000, 150
+    K = ko.internal_k(model, k)
+    ent = (rng.normal(size=(E, K)) * 0.3).astype(np.float32)
+    rel = (rng.normal(size=(R, K)) * 0.3).astype(np.float32)
+    filt = ko.synthetic_triples(E, R, F, seed=9, zipf=True)
+    test = filt[rng.permutation(F)[:T]]
+    for side, fl in (("s,o", True), ("s,o", False), ("s+o", True)):
+        got = _rank_gpu(engine, model, k, ent, rel, test, filt if fl else None, side, "worst", norm)
+        exp = ko.ranks(model, k, ent, rel, test, filt if fl else None, side, "worst", norm)
+        bad = np.argwhere(got != exp)
+        for idx in bad:
+            t = idx[0]
+            col = idx[1] if exp.ndim == 2 else 1
+            if exp.ndim == 2:
+                assert _admissible(model, k, ent, rel, test[t], col, got[tuple(idx)], exp[tuple(idx)], norm)
+        assert len(bad) <= max(2, exp.size // 25), (side, fl, len(bad))
+    # size-independent properties (reference tests/emgraph/evaluation/test_protocol.py:174-301,
+    # tests/emgraph/models/test_models.py:203-215)
+    so_f = _rank_gpu(engine, model, k, ent, rel, test, filt, "s,o", "worst", norm)
+    s_f = _rank_gpu(engine, model, k, ent, rel, test, filt, "s", "worst", norm)
+    o_f = _rank_gpu(engine, model, k, ent, rel, test, filt, "o", "worst", norm)
+    so_u = _rank_gpu(engine, model, k, ent, rel, test, None, "s,o", "worst", norm)
+    np.testing.assert_array_equal(so_f[:, 0], s_f)
+    np.testing.assert_array_equal(so_f[:, 1], o_f)
+    assert np.all(so_f <= so_u) and so_f.min() >= 1 and so_u.min() >= 2 and so_u.max() <= E + 1
+    best = _rank_gpu(engine, model, k, ent, rel, test, filt, "s,o", "best", norm)
+    mid = _rank_gpu(engine, model, k, ent, rel, test, filt, "s,o", "middle", norm)
+    assert np.all(best <= mid) and np.all(mid <= so_f)
+
+
+def test_rank_edge_cases(engine):
+    rng = np.random.default_rng(2)
+    E, R, k = 70, 2, 8
+    ent = rng.normal(size=(E, k)).astype(np.float32)
+    rel = rng.normal(size=(R, k)).astype(np.float32)
+    # empty test set
+    got = _rank_gpu(engine, "DistMult", k, ent, rel, np.zeros((0, 3), np.int32), None, "s,o", "worst")
+    assert got.shape == (0, 2)
+    # empty filter: only self is filtered
+    test = np.array([[1, 0, 2], [3, 1, 3]], np.int32)
+    got = _rank_gpu(engine, "DistMult", k, ent, rel, test, np.zeros((0, 3), np.int32), "s,o", "worst")
+    exp = ko.ranks("DistMult", k, ent, rel, test, np.zeros((0, 3), np.int32), "s,o", "worst")
+    np.testing.assert_array_equal(got, exp)
+    # every candidate known: rank 1 on the object side
+    filt = np.array([[1, 0, e] for e in range(E)], np.int32)
+    got = _rank_gpu(engine, "DistMult", k, ent, rel, test[:1], filt, "o", "worst")
+    assert got.tolist() == [1]
+    # all-equal embeddings: every score ties (worst / best / middle differ maximally)
+    ent1 = np.ones((E, k), np.float32)
+    rel1 = np.ones((R, k), np.float32)
+    for strat in ("worst", "best", "middle"):
+        got = _rank_gpu(engine, "TransE", k, ent1, rel1, test, None, "s,o", strat)
+        exp = ko.ranks("TransE", k, ent1, rel1, test, None, "s,o", strat)
+        np.testing.assert_array_equal(got, exp)
