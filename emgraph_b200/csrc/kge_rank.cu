@@ -426,6 +426,7 @@ extern "C" int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* 
     KGE_REQUIRE(ctx != nullptr, "kge_rank_counts: null ctx");
     KGE_REQUIRE(model >= KGE_TRANSE_L1 && model <= KGE_HOLE, "kge_rank_counts: unknown model %d", model);
     KGE_REQUIRE(side >= KGE_RANK_S_O && side <= KGE_RANK_O, "Invalid value for corrupt_side.");
+    if (T == 0) return 0;
     KGE_REQUIRE(ent && rel && ent_local && counts, "kge_rank_counts: null tensor");
     KGE_REQUIRE(ent->K == model_row_width(model, k), "kge_rank_counts: table width %d != internal_k %d", ent->K,
                 model_row_width(model, k));
