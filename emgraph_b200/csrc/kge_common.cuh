@@ -61,6 +61,8 @@ struct kge_ctx {
     // training workspace
     KgeBuf keys_in, keys_out, vals_in, vals_out, sort_tmp;
     KgeBuf repl, keep, grad_rows, loss_part, neg_scores;
+    // staging for the host-buffer entry points
+    KgeBuf h_pos, h_loss, h_test, h_counts, h_ranks;
     // ranking workspace
     KgeBuf q_fold, q_hi, q_lo, e_hi, e_lo, pos_q, excl_lo, excl_hi;
     // filter index (sorted, deduplicated composites and the entity column of each)

@@ -525,3 +525,24 @@ extern "C" int kge_rank_finalize(kge_ctx* ctx, const int32_t* counts, int64_t T,
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
+
+extern "C" int kge_rank_host(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
+                             const int32_t* test_host, int64_t T, int side, int strategy, int filtered,
+                             int use_tensor_cores, int32_t* ranks_host, void* stream) {
+    KGE_REQUIRE(ctx != nullptr && ent != nullptr, "kge_rank_host: null argument");
+    KGE_REQUIRE(ent->n_shards == 1 && ent->shard[0] != nullptr, "kge_rank_host is the single-GPU entry; use kge_rank_counts per shard");
+    if (T == 0) return 0;
+    KGE_REQUIRE(test_host != nullptr && ranks_host != nullptr, "kge_rank_host: null host buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_out = (size_t)T * (side == KGE_RANK_S_O ? 2 : 1);
+    if (ctx->h_test.reserve((size_t)T * 3 * 4) || ctx->h_counts.reserve((size_t)T * 8 * 4) || ctx->h_ranks.reserve(n_out * 4)) return -2;
+    KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->h_test.p, test_host, (size_t)T * 3 * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = kge_rank_counts(ctx, model, k, ent, rel, R, ent->shard[0], 0, ent->rows, ctx->h_test.as<int32_t>(), T, side,
+                                 filtered, use_tensor_cores, ctx->h_counts.as<int32_t>(), stream))
+        return rc;
+    if (int rc = kge_rank_finalize(ctx, ctx->h_counts.as<int32_t>(), T, side, strategy, filtered, ctx->h_ranks.as<int32_t>(), stream))
+        return rc;
+    KGE_CUDA_CHECK(cudaMemcpyAsync(ranks_host, ctx->h_ranks.p, n_out * 4, cudaMemcpyDeviceToHost, st));
+    KGE_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+}

@@ -8,3 +8,5 @@ int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ
     kge_set_error("kge_rank_counts: tensor-core sweep not built in this version");
     return -4;
 }
+
+extern "C" int kge_has_tensor_core_rank(void) { return 0; }

@@ -613,7 +613,7 @@ static int validate_train(const kge_train_args* a) {
                 model_row_width(a->model, a->k));
     KGE_REQUIRE(a->ent.n_shards >= 1 && a->ent.n_shards <= KGE_MAX_SHARDS, "kge_train: bad shard count");
     KGE_REQUIRE(a->ent.rows + a->R < (int64_t)INT32_MAX, "kge_train: E+R must fit int32 sort keys");
-    KGE_REQUIRE(a->n_pos >= 0 && a->pos != nullptr, "kge_train: positives missing");
+    KGE_REQUIRE(a->n_pos >= 0 && (a->pos != nullptr || a->n_pos == 0), "kge_train: positives missing");
     return 0;
 }
 
@@ -656,6 +656,8 @@ static int ensure_train_ws(kge_ctx* ctx, const kge_train_args* a, bool need_grad
     if (need_grads && ctx->grad_rows.reserve((size_t)S * a->ent.K * sizeof(float))) return -2;
     return 0;
 }
+
+extern "C" int64_t kge_train_grad_rows(int eta, int64_t n_pos) { return (int64_t)(3 + eta) * n_pos; }
 
 extern "C" int kge_train_emit(kge_ctx* ctx, const kge_train_args* a, int32_t* keys_out, void* stream) {
     KGE_REQUIRE(ctx != nullptr, "kge_train_emit: null ctx");
@@ -798,6 +800,26 @@ extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* strea
     g.n_shards = 1;
     g.K = a->ent.K;
     return kge_train_apply(ctx, a, ctx->keys_in.as<int32_t>(), S, &g, 0, a->ent.rows, stream);
+}
+
+extern "C" int kge_train_step_host(kge_ctx* ctx, const kge_train_args* a, const int32_t* pos_host, float* loss_host,
+                                   void* stream) {
+    KGE_REQUIRE(ctx != nullptr && a != nullptr, "kge_train_step_host: null argument");
+    KGE_REQUIRE(a->n_pos >= 0 && (a->n_pos == 0 || pos_host != nullptr), "kge_train_step_host: positives missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->n_pos == 0) {
+        if (loss_host) *loss_host = 0.f;
+        return 0;
+    }
+    if (ctx->h_pos.reserve((size_t)a->n_pos * 3 * sizeof(int32_t)) || ctx->h_loss.reserve(sizeof(float))) return -2;
+    KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pos.p, pos_host, (size_t)a->n_pos * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    kge_train_args b = *a;
+    b.pos = ctx->h_pos.as<int32_t>();
+    if (b.loss_out == nullptr) b.loss_out = ctx->h_loss.as<float>();
+    if (int rc = kge_train_step(ctx, &b, stream)) return rc;
+    if (loss_host) KGE_CUDA_CHECK(cudaMemcpyAsync(loss_host, b.loss_out, sizeof(float), cudaMemcpyDeviceToHost, st));
+    KGE_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
 }
 
 extern "C" int kge_normalize_rows(kge_ctx* ctx, float* emb, int64_t rows, int K, void* stream) {

@@ -100,6 +100,12 @@ class Engine:
     def tdev(self):
         return torch.device("cuda", self.device)
 
+    def has_tensor_core_rank(self) -> bool:
+        return bool(self.lib.kge_has_tensor_core_rank())
+
+    def train_grad_rows(self, eta: int, n_pos: int) -> int:
+        return int(self.lib.kge_train_grad_rows(eta, n_pos))
+
     def workspace_bytes(self) -> int:
         return int(self.lib.kge_ctx_workspace_bytes(self._h))
 
@@ -137,8 +143,9 @@ class Engine:
         _chk_f32(rel, "rel")
         a.rel, a.rel_m, a.rel_v, a.R = rel.data_ptr(), (rel_m.data_ptr() if rel_m is not None else None), \
             (rel_v.data_ptr() if rel_v is not None else None), rel.shape[0]
-        _chk_i32(pos, "pos")
-        a.pos, a.n_pos = pos.data_ptr(), pos.shape[0]
+        if pos is not None:
+            _chk_i32(pos, "pos")
+            a.pos, a.n_pos = pos.data_ptr(), pos.shape[0]
         if repl is not None:
             _chk_i32(repl, "repl")
             assert repl.numel() == eta * pos.shape[0]
@@ -146,7 +153,7 @@ class Engine:
         if keep_subj is not None:
             assert keep_subj.is_cuda and keep_subj.dtype == torch.uint8 and keep_subj.numel() == eta * pos.shape[0]
             a.keep_subj = keep_subj.data_ptr()
-        a.loss_out = loss_out.data_ptr()
+        a.loss_out = loss_out.data_ptr() if loss_out is not None else None
         a.dbg_scores = dbg_scores.data_ptr() if dbg_scores is not None else None
         a.dbg_grad_ent = dbg_grad_ent.data_ptr() if dbg_grad_ent is not None else None
         a.dbg_grad_rel = dbg_grad_rel.data_ptr() if dbg_grad_rel is not None else None
@@ -163,6 +170,16 @@ class Engine:
 
     def train_step(self, a: KgeTrainArgs):
         check(self.lib.kge_train_step(self._h, C.byref(a), _stream()))
+        self.launches += self.launches_per_step(a.ent.rows + a.R)
+
+    def train_step_host(self, a: KgeTrainArgs, pos_host, loss_host):
+        """Host-buffer step: pos_host int32 [n,3] CPU tensor (pinned for an async copy), loss_host
+        float32 [1] CPU tensor (pinned).  Copies in, runs the step, copies the loss out, syncs."""
+        assert (not pos_host.is_cuda) and pos_host.dtype == torch.int32 and pos_host.is_contiguous()
+        assert (not loss_host.is_cuda) and loss_host.dtype == torch.float32
+        a.n_pos = pos_host.shape[0]
+        check(self.lib.kge_train_step_host(self._h, C.byref(a), C.c_void_p(pos_host.data_ptr()),
+                                           C.c_void_p(loss_host.data_ptr()), _stream()))
         self.launches += self.launches_per_step(a.ent.rows + a.R)
 
     def train_emit(self, a: KgeTrainArgs, keys_out):
@@ -229,6 +246,20 @@ class Engine:
     def rank(self, model: int, k: int, ent, rel, test, *, side=0, strategy=0, filtered=False, use_tensor_cores=False):
         counts = self.rank_counts(model, k, ent, rel, test, side=side, filtered=filtered, use_tensor_cores=use_tensor_cores)
         return self.rank_finalize(counts, side=side, strategy=strategy, filtered=filtered)
+
+    def rank_host(self, model: int, k: int, ent, rel, test_host, ranks_host, *, side=0, strategy=0, filtered=False,
+                  use_tensor_cores=False):
+        """Host-buffer ranking: test_host int32 [T,3] CPU (pinned), ranks_host int32 CPU out; syncs."""
+        tb = make_table(ent)
+        T = test_host.shape[0]
+        assert (not test_host.is_cuda) and test_host.dtype == torch.int32 and test_host.is_contiguous()
+        assert (not ranks_host.is_cuda) and ranks_host.dtype == torch.int32 and ranks_host.is_contiguous()
+        assert ranks_host.numel() == T * (2 if side == _lib.RANK_SIDE_IDS["s,o"] else 1)
+        check(self.lib.kge_rank_host(self._h, model, k, C.byref(tb), _ptr(rel), rel.shape[0],
+                                     C.c_void_p(test_host.data_ptr()), T, side, strategy, int(bool(filtered)),
+                                     int(bool(use_tensor_cores)), C.c_void_p(ranks_host.data_ptr()), _stream()))
+        self.launches += 4 if T else 0
+        return ranks_host
 
     # ---------------------------------------------------------------- IPC (multi-GPU peer shards)
     def ipc_export(self, t) -> bytes:

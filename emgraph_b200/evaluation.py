@@ -21,6 +21,7 @@ class EvalDataset:
         self.test_idx = np.ascontiguousarray(test_idx, dtype=np.int32).reshape(-1, 3)
         self.filter_idx = None if filter_idx is None else np.ascontiguousarray(filter_idx, dtype=np.int32).reshape(-1, 3)
         self._test_dev = None
+        self._test_pin = None
         self._engine = None
 
     def get_size(self, dataset_type="test"):
@@ -31,7 +32,18 @@ class EvalDataset:
             self._test_dev = to_dev_i32(self.test_idx, device)
         return self._test_dev
 
+    def test_host_pinned(self):
+        """The mapped test triples as a pinned int32 CPU tensor (source of the per-call H2D copy)."""
+        if self._test_pin is None:
+            import torch
+            self._test_pin = torch.from_numpy(self.test_idx).pin_memory()
+        return self._test_pin
+
     def build_filter(self, engine, E, R):
+        """Device filter index; built once per handle (the reference builds its SQLite DB once per
+        evaluate_performance call, datasets/numpy_adapter.py:229-247)."""
+        if self._engine is engine:
+            return
         f = self.filter_idx if self.filter_idx is not None else np.zeros((0, 3), np.int32)
         engine.filter_build(to_dev_i32(f, engine.tdev), E, R)
         self._engine = engine

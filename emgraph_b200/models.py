@@ -284,11 +284,10 @@ class EmbeddingModel:
         self._fit_idx(Xi, len(self._ent_index), len(self._rel_index))
         return self
 
-    def _fit_idx(self, Xi, E, R):
+    def _fit_prepare(self, E, R):
+        """Allocate device parameters + optimizer state and freeze the per-step arguments."""
         eng = get_engine(self.engine_params.get("device"))
         dev = eng.tdev
-        N = Xi.shape[0]
-        batch_size = int(np.ceil(N / self.batches_count))
         K = self.internal_k
         ent = torch.from_numpy(self._init_table(E, K, "entity")).to(dev)
         rel = torch.from_numpy(self._init_table(R, K, "relation")).to(dev)
@@ -302,46 +301,82 @@ class EmbeddingModel:
                 st = dict(ent_m=torch.full_like(ent, 0.1), rel_m=torch.full_like(rel, 0.1))
             elif opt == 2:
                 st = dict(ent_m=torch.zeros_like(ent), rel_m=torch.zeros_like(rel))
-        Xd = to_dev_i32(Xi, dev)
-        sides = self._train_sides()
-        loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-        epoch_loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._fit = dict(
+            eng=eng, ent=ent, rel=rel, st=st, step=0, sides=self._train_sides(),
+            loss_dev=torch.zeros(1, dtype=torch.float32, device=dev),
+            loss_host=torch.zeros(1, dtype=torch.float32).pin_memory(),
+            kw=dict(model=self._model_id(), loss=_lib.LOSS_IDS[self.loss], opt=opt, k=self.k, eta=self.eta,
+                    flags=_lib.F_RESET_STATE if reset else 0, margin=float(self.loss_params.get("margin", DEFAULT_MARGIN)),
+                    lr=float(self.optimizer_params.get("lr", DEFAULT_LR)),
+                    momentum=float(self.optimizer_params.get("momentum", DEFAULT_MOMENTUM)), seed=int(self.seed)))
+        return self._fit
+
+    def _fit_step_device(self, pos_dev, side="s,o"):
+        """One optimisation step on a device-resident batch; enqueue only, loss stays in f['loss_dev']."""
+        f = self._fit
+        f["step"] += 1
+        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=pos_dev, loss_out=f["loss_dev"],
+                                side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"])
+        f["eng"].train_step(a)
+
+    def _fit_step_host(self, pos_host, side="s,o"):
+        """One optimisation step fed like the reference feeds it: the batch comes from (pinned) host
+        memory and the batch loss is read back (models/EmbeddingModel.py:1329-1337, :1421)."""
+        f = self._fit
+        f["step"] += 1
+        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"],
+                                side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"])
+        f["eng"].train_step_host(a, pos_host, f["loss_host"])
+        return float(f["loss_host"][0])
+
+    def _fit_idx(self, Xi, E, R):
+        f = self._fit_prepare(E, R)
+        eng, ent, rel = f["eng"], f["ent"], f["rel"]
+        N = Xi.shape[0]
+        batch_size = int(np.ceil(N / self.batches_count))
+        host_batches = bool(self.engine_params.get("host_batches", False))
+        if host_batches:
+            Xh = torch.from_numpy(np.ascontiguousarray(Xi, dtype=np.int32)).pin_memory()
+        else:
+            Xd = to_dev_i32(Xi, eng.tdev)
+        epoch_loss = torch.zeros(1, dtype=torch.float64, device=eng.tdev)
         normalize = bool(self.embedding_model_params.get("normalize_ent_emb", False))
-        lr = float(self.optimizer_params.get("lr", DEFAULT_LR))
-        mom = float(self.optimizer_params.get("momentum", DEFAULT_MOMENTUM))
-        margin = float(self.loss_params.get("margin", DEFAULT_MARGIN))
-        mid, lid = self._model_id(), _lib.LOSS_IDS[self.loss]
         check_every = int(self.engine_params.get("nan_check_every", self.batches_count))
-        step = 0
         self.loss_history = []
         denom = batch_size * (self.eta if self.loss in ("pairwise", "nll") else 1) * self.batches_count  # :1343-1344, :1453-1457
         for epoch in range(1, self.epochs + 1):
             epoch_loss.zero_()
+            host_loss = 0.0
             for b in range(self.batches_count):
-                pos = Xd[b * batch_size:(b + 1) * batch_size]
-                if pos.shape[0] == 0:
+                lo, hi = b * batch_size, min(N, (b + 1) * batch_size)
+                if hi <= lo:
                     continue
-                for side in sides:
-                    step += 1
-                    a = eng.train_args(model=mid, loss=lid, opt=opt, k=self.k, eta=self.eta, ent=ent, rel=rel, pos=pos,
-                                       loss_out=loss_dev, side=_lib.TRAIN_SIDE_IDS[side],
-                                       flags=_lib.F_RESET_STATE if reset else 0, margin=margin, lr=lr, momentum=mom,
-                                       seed=int(self.seed), step=step, **st)
-                    eng.train_step(a)
-                    epoch_loss += loss_dev.double()
+                for side in f["sides"]:
+                    if host_batches:
+                        lv = self._fit_step_host(Xh[lo:hi], side)
+                        if not np.isfinite(lv):  # models/EmbeddingModel.py:1422-1427
+                            raise ValueError("Loss is {}. Please change the hyperparameters.".format(lv))
+                        host_loss += lv
+                    else:
+                        self._fit_step_device(Xd[lo:hi], side)
+                        epoch_loss += f["loss_dev"].double()
                 if normalize:
                     eng.normalize_rows(ent)
-                if step % check_every == 0 and not bool(torch.isfinite(epoch_loss).item()):
+                if not host_batches and f["step"] % check_every == 0 and not bool(torch.isfinite(epoch_loss).item()):
                     raise ValueError("Loss is {}. Please change the hyperparameters.".format(float(epoch_loss.item())))
-            el = float(epoch_loss.item())
+            el = host_loss if host_batches else float(epoch_loss.item())
             if not np.isfinite(el):  # models/EmbeddingModel.py:1422-1427
                 raise ValueError("Loss is {}. Please change the hyperparameters.".format(el))
             self.loss_history.append(el / denom)
             if self.verbose:
                 print("Average Loss: {:10f} -- epoch {}/{}".format(self.loss_history[-1], epoch, self.epochs))
-        self._dev = {"ent": ent, "rel": rel}
-        self._opt_state = st
-        self.trained_model_params = [ent.cpu().numpy(), rel.cpu().numpy()]
+        self._fit_finish()
+
+    def _fit_finish(self):
+        f = self._fit
+        self._dev = {"ent": f["ent"], "rel": f["rel"]}
+        self._opt_state = f["st"]
+        self.trained_model_params = [f["ent"].cpu().numpy(), f["rel"].cpu().numpy()]
         self.is_fitted = True
 
     def _device_params(self):
@@ -407,15 +442,18 @@ class EmbeddingModel:
             raise NotImplementedError("entities_subset ranking is outside the B200 hot-path scope (SURVEY section 8f)")
         eng = get_engine(self.engine_params.get("device"))
         ent, rel = self._device_params()
-        test = dataset_handle.test_device(eng.tdev)
         filtered = bool(self.is_filtered)
         if filtered:
             dataset_handle.build_filter(eng, ent.shape[0], rel.shape[0])
         mid = self._model_id()
         use_tc = bool(self.engine_params.get("rank_tensor_cores", False)) and self.name != "TransE"
-        ranks = eng.rank(mid, self.k, ent, rel, test, side=_lib.RANK_SIDE_IDS[side],
-                         strategy=_lib.STRATEGY_IDS[strategy], filtered=filtered, use_tensor_cores=use_tc)
-        return ranks.cpu().numpy()
+        # host buffers in, host buffers out (one H2D of the test triples, one D2H of the ranks)
+        test_h = dataset_handle.test_host_pinned()
+        T = test_h.shape[0]
+        ranks_h = torch.empty((T, 2) if side == "s,o" else (T,), dtype=torch.int32).pin_memory()
+        eng.rank_host(mid, self.k, ent, rel, test_h, ranks_h, side=_lib.RANK_SIDE_IDS[side],
+                      strategy=_lib.STRATEGY_IDS[strategy], filtered=filtered, use_tensor_cores=use_tc)
+        return ranks_h.numpy().copy()
 
 
 @register_model("TransE")

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 1
+#define KGE_ABI_VERSION 2
 #define KGE_MAX_SHARDS 8
 
 typedef struct kge_ctx kge_ctx;
@@ -87,6 +87,10 @@ typedef struct kge_train_args {
 } kge_train_args;
 
 int         kge_abi_version(void);
+/* 1 if this build carries the tcgen05 3xTF32 ranking sweep (use_tensor_cores=1 in kge_rank_counts) */
+int         kge_has_tensor_core_rank(void);
+/* rows of the caller-owned grad_rows buffer kge_train_fwd_bwd writes for a batch of n_pos positives */
+int64_t     kge_train_grad_rows(int eta, int64_t n_pos);
 const char* kge_last_error(void);
 
 /* per-device context (replaces the reference's implicit TF runtime state) */
@@ -117,6 +121,14 @@ int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* grad_rows, v
 int kge_train_apply(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, int64_t n_keys,
                     const kge_table* grads, int64_t row_begin, int64_t row_end, void* stream);
 
+/* Host-buffer form of kge_train_step: what a reference-side caller binds.  The reference feeds every
+ * batch from host numpy through tf.data (models/EmbeddingModel.py:1329-1337, :1044-1111) and reads
+ * the batch loss back with .numpy() (:1421).  pos_host [n_pos,3] int32 (pinned for an async copy) is
+ * copied to a ctx-owned device buffer (a->pos is ignored), the step runs, the loss is copied to
+ * *loss_host and the stream is synchronised before returning. */
+int kge_train_step_host(kge_ctx* ctx, const kge_train_args* a, const int32_t* pos_host, float* loss_host,
+                        void* stream);
+
 /* optional post-step row renormalisation (models/EmbeddingModel.py:1434-1439, clip_by_norm axes=1) */
 int kge_normalize_rows(kge_ctx* ctx, float* emb, int64_t rows, int K, void* stream);
 
@@ -143,6 +155,12 @@ int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* ent, const 
 /* ranks_out: [T,2] (col 0 subject, col 1 object) for KGE_RANK_S_O, else [T]. */
 int kge_rank_finalize(kge_ctx* ctx, const int32_t* counts, int64_t T, int side, int strategy,
                       int filtered, int32_t* ranks_out, void* stream);
+
+/* Host-buffer form of evaluate_performance's device work for a single-GPU table: test_host [T,3]
+ * int32 in, ranks_host ([T,2] for KGE_RANK_S_O else [T]) out; synchronises the stream. */
+int kge_rank_host(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
+                  const int32_t* test_host, int64_t T, int side, int strategy, int filtered,
+                  int use_tensor_cores, int32_t* ranks_host, void* stream);
 
 /* CUDA IPC helpers for mapping peer shards (one process per GPU). handle: 64 bytes. */
 int kge_ipc_export(void* dev_ptr, void* handle_out64);
