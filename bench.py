@@ -321,7 +321,7 @@ def single_gpu_main(args, w):
     # ---- per-kernel time of the phases (live CUDA events, L2 flushed): emit | fwd_bwd(+loss reduce) | sort+apply
     S = (3 + eta) * B
     keys = torch.empty(S, dtype=torch.int32, device=dev)
-    grad_rows = torch.empty((eng.train_grad_rows(eta, B), K), dtype=torch.float32, device=dev)
+    grad_buf = torch.empty(eng.train_grad_floats(eta, B, K), dtype=torch.float32, device=dev)
     ph = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
     for s in range(steps):
         flush.fill_(float(s))
@@ -331,9 +331,9 @@ def single_gpu_main(args, w):
         ph[s][0].record()
         eng.train_emit(a, keys)
         ph[s][1].record()
-        eng.train_fwd_bwd(a, grad_rows)
+        eng.train_fwd_bwd(a, grad_buf)
         ph[s][2].record()
-        eng.train_apply(a, keys, make_table(grad_rows), 0, E)
+        eng.train_apply(a, keys, eng.grad_table(grad_buf, eta, B, K), 0, E)
         ph[s][3].record()
         it += 1
     torch.cuda.synchronize()

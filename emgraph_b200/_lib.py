@@ -54,7 +54,7 @@ SYMBOLS = {
     "kge_abi_version": (_I, []),
     "kge_last_error": (C.c_char_p, []),
     "kge_has_tensor_core_rank": (_I, []),
-    "kge_train_grad_rows": (_L, [_I, _L]),
+    "kge_train_grad_floats": (_L, [_I, _L, _I]),
     "kge_ctx_create": (_I, [_I, C.POINTER(_P)]),
     "kge_ctx_destroy": (_I, [_P]),
     "kge_ctx_workspace_bytes": (_L, [_P]),

@@ -60,7 +60,7 @@ struct kge_ctx {
     int sm_count = 148;
     // training workspace
     KgeBuf keys_in, keys_out, vals_in, vals_out, sort_tmp;
-    KgeBuf repl, keep, grad_rows, loss_part, neg_scores;
+    KgeBuf repl, keep, grad_rows, loss_part, neg_scores, partial, span_head;
     // staging for the host-buffer entry points
     KgeBuf h_pos, h_loss, h_test, h_counts, h_ranks;
     // ranking workspace

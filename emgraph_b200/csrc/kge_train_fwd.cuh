@@ -1,0 +1,556 @@
+// Fused forward + loss + backward of one training batch (sm_100a), templated on the scoring model.
+//
+// One warp (or SPLIT cooperating warps of one CTA) per positive triple:
+//   * s, p, o rows are gathered with 128-bit coalesced loads and folded into the two "queries"
+//     Qo (object-side candidates) and Qs (subject-side candidates) that stay in registers;
+//   * the eta replacement ids of the positive are prefetched by the lanes in one coalesced round and
+//     broadcast with shuffles, so U candidate rows are in flight per warp with no index->row
+//     dependent-load chain;
+//   * score, loss term and dL/dscore are evaluated in registers; the candidate row is folded into a
+//     side accumulator (AccO / AccS) from which the gradients of the positive's own rows follow;
+//   * NO per-negative gradient row is written.  The gradient of a replacement row r of negative (j,i)
+//     is a function of (c_ji, Q_side(i), r):  c*Q (DistMult/ComplEx/HolE), c*sign(Q-r) (TransE L1),
+//     c*(Q-r) (TransE L2).  Only the scalar c_ji and the two query rows per positive are stored; the
+//     segmented reduction in kge_train.cu re-materialises the row from them.
+//
+// Per positive the kernel writes 5 rows (gs, go, gp, Qo, Qs) + eta coefficients instead of 3+eta
+// rows.  Replaces reference models/EmbeddingModel.py:614-822 (_get_model_loss), losses/*.py and the
+// GradientTape backward of training/adam.py:45-46.
+#pragma once
+#include <type_traits>
+
+#include "kge_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// gradient buffer of one rank (caller-owned so that peers can map it), n = positives in the batch:
+//   float rows[5n][K] : [0,n) gs | [n,2n) go | [2n,3n) gp | [3n,4n) Qo | [4n,5n) Qs
+//   float coef[eta*n] : c_ji at j*n+i
+//   uint8 keep[eta*n] : 1 = subject kept (object replaced -> query Qo)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int64_t gbuf_floats(int eta, int64_t n, int K) {
+    return 5 * n * (int64_t)K + (int64_t)eta * n + ((int64_t)eta * n + 3) / 4;
+}
+__host__ __device__ inline float* gbuf_coef(float* base, int64_t n, int K) { return base + 5 * n * (int64_t)K; }
+__host__ __device__ inline uint8_t* gbuf_keep(float* base, int eta, int64_t n, int K) {
+    return reinterpret_cast<uint8_t*>(gbuf_coef(base, n, K) + (int64_t)eta * n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// register-resident embedding rows: lane l owns vectors c = l + 32*i (i < NCH) of V floats; complex
+// rows keep the matching imaginary vector (offset k floats) beside the real one.
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__device__ __forceinline__ void ld_vec(float (&d)[V], const float* p) {
+    if constexpr (V == 4) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+    } else {
+        d[0] = *p;
+    }
+}
+template <int V>
+__device__ __forceinline__ void st_vec(float* p, const float (&d)[V]) {
+    if constexpr (V == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(d[0], d[1], d[2], d[3]);
+    } else {
+        *p = d[0];
+    }
+}
+
+template <int V, int NCH, bool CPLX>
+struct Row {
+    float re[NCH][V];
+    float im[CPLX ? NCH : 1][V];
+};
+
+#define ROW_FOR(i, v)                               \
+    _Pragma("unroll") for (int i = 0; i < NCH; ++i) \
+    _Pragma("unroll") for (int v = 0; v < V; ++v)
+
+template <int V, int NCH, bool CPLX>
+__device__ __forceinline__ void row_zero(Row<V, NCH, CPLX>& r) {
+    ROW_FOR(i, v) {
+        r.re[i][v] = 0.f;
+        if constexpr (CPLX) r.im[i][v] = 0.f;
+    }
+}
+
+// nvec: vectors per half (complex) or per row; half: k floats
+template <int V, int NCH, bool CPLX>
+__device__ __forceinline__ void row_load(Row<V, NCH, CPLX>& r, const float* __restrict__ base, int lane, int nvec, int half) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        int c = lane + 32 * i;
+        if (c < nvec) {
+            ld_vec<V>(r.re[i], base + (size_t)c * V);
+            if constexpr (CPLX) ld_vec<V>(r.im[i], base + half + (size_t)c * V);
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                r.re[i][v] = 0.f;
+                if constexpr (CPLX) r.im[i][v] = 0.f;
+            }
+        }
+    }
+}
+
+template <int V, int NCH, bool CPLX>
+__device__ __forceinline__ void row_store(float* __restrict__ base, const Row<V, NCH, CPLX>& r, int lane, int nvec, int half) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        int c = lane + 32 * i;
+        if (c < nvec) {
+            st_vec<V>(base + (size_t)c * V, r.re[i]);
+            if constexpr (CPLX) st_vec<V>(base + half + (size_t)c * V, r.im[i]);
+        }
+    }
+}
+
+template <int V, int NCH, bool CPLX>
+__device__ __forceinline__ void row_add(Row<V, NCH, CPLX>& a, const Row<V, NCH, CPLX>& b) {
+    ROW_FOR(i, v) {
+        a.re[i][v] += b.re[i][v];
+        if constexpr (CPLX) a.im[i][v] += b.im[i][v];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// model algebra.  MODEL: 0 TransE-L1, 1 TransE-L2, 2 DistMult, 3 ComplEx
+// (HolE = ComplEx with score scale 2/k, reference models/HolE.py:189).
+//   Qo: query for an object-side replacement (score depends on r through <Qo, r> or |Qo - r|)
+//   Qs: query for a subject-side replacement
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int V, int NCH>
+struct Algebra {
+    static constexpr bool CPLX = (MODEL == 3);
+    static constexpr bool TRANSE = (MODEL == 0 || MODEL == 1);
+    using R = Row<V, NCH, CPLX>;
+
+    __device__ __forceinline__ static void queries(const R& s, const R& p, const R& o, R& Qo, R& Qs) {
+        ROW_FOR(i, v) {
+            if constexpr (TRANSE) {
+                Qo.re[i][v] = s.re[i][v] + p.re[i][v];
+                Qs.re[i][v] = o.re[i][v] - p.re[i][v];
+            } else if constexpr (MODEL == 2) {
+                Qo.re[i][v] = s.re[i][v] * p.re[i][v];
+                Qs.re[i][v] = p.re[i][v] * o.re[i][v];
+            } else {
+                Qo.re[i][v] = p.re[i][v] * s.re[i][v] - p.im[i][v] * s.im[i][v];
+                Qo.im[i][v] = p.re[i][v] * s.im[i][v] + p.im[i][v] * s.re[i][v];
+                Qs.re[i][v] = p.re[i][v] * o.re[i][v] + p.im[i][v] * o.im[i][v];
+                Qs.im[i][v] = p.re[i][v] * o.im[i][v] - p.im[i][v] * o.re[i][v];
+            }
+        }
+    }
+
+    // lane-partial of the reduction that defines the score of (Q, r).  For TransE the two sides
+    // differ only in the sign of the difference, which |.| and (.)^2 ignore.
+    __device__ __forceinline__ static float partial(const R& Q, const R& r) {
+        float acc = 0.f;
+        ROW_FOR(i, v) {
+            if constexpr (MODEL == 0) {
+                acc += fabsf(Q.re[i][v] - r.re[i][v]);
+            } else if constexpr (MODEL == 1) {
+                float d = Q.re[i][v] - r.re[i][v];
+                acc = fmaf(d, d, acc);
+            } else if constexpr (MODEL == 2) {
+                acc = fmaf(Q.re[i][v], r.re[i][v], acc);
+            } else {
+                acc = fmaf(Q.re[i][v], r.re[i][v], acc);
+                acc = fmaf(Q.im[i][v], r.im[i][v], acc);
+            }
+        }
+        return acc;
+    }
+
+    __device__ __forceinline__ static float finish(float sum, float scale) {
+        if constexpr (MODEL == 0) return -sum;
+        else if constexpr (MODEL == 1) return -sqrtf(sum);
+        else return scale * sum;
+    }
+
+    // coefficient stored for the replacement row of a negative with dL/dscore = w:
+    //   gradient row = c*Q (trilinear) | c*sign(Q-r) (L1) | c*(Q-r) (L2)
+    __device__ __forceinline__ static float coefficient(float w, float score, float scale) {
+        if constexpr (MODEL == 0) return w;
+        else if constexpr (MODEL == 1) return score != 0.f ? w / (-score) : 0.f;
+        else return w * scale;
+    }
+
+    // acc += w * d score / d(the positive's side of the triple), expressed through the candidate r:
+    //   trilinear: acc += w*scale*r ;  TransE: acc += w*g(u), u = s+p-r (obj) or r+p-o (subj)
+    __device__ __forceinline__ static void accumulate(const R& Q, const R& r, bool obj, float w, float score, float scale, R& acc) {
+        if constexpr (TRANSE) {
+            float inv = 0.f;
+            if constexpr (MODEL == 1) inv = score != 0.f ? 1.f / (-score) : 0.f;
+            const float sg = obj ? 1.f : -1.f;
+            ROW_FOR(i, v) {
+                float u = sg * (Q.re[i][v] - r.re[i][v]);
+                float g;  // d f / d u
+                if constexpr (MODEL == 0) g = (u > 0.f) ? -1.f : ((u < 0.f) ? 1.f : 0.f);
+                else g = -u * inv;
+                acc.re[i][v] = fmaf(w, g, acc.re[i][v]);
+            }
+        } else {
+            const float ws = w * scale;
+            ROW_FOR(i, v) {
+                acc.re[i][v] = fmaf(ws, r.re[i][v], acc.re[i][v]);
+                if constexpr (CPLX) acc.im[i][v] = fmaf(ws, r.im[i][v], acc.im[i][v]);
+            }
+        }
+    }
+
+    // the positive's own object as an object-side candidate with weight w = dL/dpos:
+    //   go <- gradient row of o from this term ; AccO updated like accumulate()
+    __device__ __forceinline__ static void backward_pos(const R& Qo, const R& o, float w, float score, float scale, R& go, R& AccO) {
+        if constexpr (TRANSE) {
+            float inv = 0.f;
+            if constexpr (MODEL == 1) inv = score != 0.f ? 1.f / (-score) : 0.f;
+            ROW_FOR(i, v) {
+                float u = Qo.re[i][v] - o.re[i][v];
+                float g;
+                if constexpr (MODEL == 0) g = (u > 0.f) ? -1.f : ((u < 0.f) ? 1.f : 0.f);
+                else g = -u * inv;
+                float wg = w * g;
+                AccO.re[i][v] += wg;
+                go.re[i][v] = -wg;
+            }
+        } else {
+            const float ws = w * scale;
+            ROW_FOR(i, v) {
+                go.re[i][v] = ws * Qo.re[i][v];
+                AccO.re[i][v] = fmaf(ws, o.re[i][v], AccO.re[i][v]);
+                if constexpr (CPLX) {
+                    go.im[i][v] = ws * Qo.im[i][v];
+                    AccO.im[i][v] = fmaf(ws, o.im[i][v], AccO.im[i][v]);
+                }
+            }
+        }
+    }
+
+    // Fold the side accumulators into the gradients of the positive's own rows.
+    __device__ __forceinline__ static void fold(const R& s, const R& p, const R& o, const R& AccO, const R& AccS,
+                                                R& gs, R& gp, R& go) {
+        ROW_FOR(i, v) {
+            if constexpr (TRANSE) {
+                gs.re[i][v] = AccO.re[i][v];
+                gp.re[i][v] = AccO.re[i][v] + AccS.re[i][v];
+                go.re[i][v] = go.re[i][v] - AccS.re[i][v];
+            } else if constexpr (MODEL == 2) {
+                gs.re[i][v] = p.re[i][v] * AccO.re[i][v];
+                gp.re[i][v] = s.re[i][v] * AccO.re[i][v] + o.re[i][v] * AccS.re[i][v];
+                go.re[i][v] = fmaf(p.re[i][v], AccS.re[i][v], go.re[i][v]);
+            } else {
+                float pr = p.re[i][v], pi = p.im[i][v];
+                float ar = AccO.re[i][v], ai = AccO.im[i][v];
+                float br = AccS.re[i][v], bi = AccS.im[i][v];
+                gs.re[i][v] = pr * ar + pi * ai;
+                gs.im[i][v] = pr * ai - pi * ar;
+                gp.re[i][v] = s.re[i][v] * ar + s.im[i][v] * ai + br * o.re[i][v] + bi * o.im[i][v];
+                gp.im[i][v] = s.re[i][v] * ai - s.im[i][v] * ar + br * o.im[i][v] - bi * o.re[i][v];
+                go.re[i][v] += pr * br - pi * bi;
+                go.im[i][v] += pr * bi + pi * br;
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ float clip75(float x) { return fminf(fmaxf(x, -75.f), 75.f); }
+
+struct FwdBwdParams {
+    TableView ent;
+    const float* rel;
+    const int32_t* pos;
+    const int32_t* repl;
+    const uint8_t* keep;
+    int64_t n;
+    int eta, k, loss;
+    float margin, scale;
+    float* gbuf;        // gradient buffer (layout above)
+    float* loss_part;   // [n]
+    float* dbg_scores;  // optional [n*(1+eta)]
+};
+
+// SPLIT warps cooperate on one positive (its negatives are dealt round-robin); a CTA is 4 warps.
+// registers of one row per lane; bounds the resident CTAs the compiler is asked to allow
+template <int MODEL, int V, int NCH>
+struct RowRegs {
+    static constexpr int value = NCH * V * (MODEL == 3 ? 2 : 1);
+    static constexpr int min_ctas = value <= 16 ? 3 : (value <= 32 ? 2 : 1);
+};
+
+template <int MODEL, int V, int NCH, int U, int SPLIT>
+__global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_fwd_bwd_kernel(FwdBwdParams P) {
+    using A = Algebra<MODEL, V, NCH>;
+    using R = typename A::R;
+    constexpr int PP = 4 / SPLIT;  // positives per CTA
+    extern __shared__ __align__(16) float smem[];
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int sub = wib % SPLIT;
+    const int pl = wib / SPLIT;
+    const int64_t i = (int64_t)blockIdx.x * PP + pl;
+    const bool valid = i < P.n;
+    const int K = P.ent.K;
+    const int half = A::CPLX ? P.k : 0;
+    const int nvec = (A::CPLX ? P.k : K) / V;
+    const int64_t n = P.n;
+    const int eta = P.eta;
+    const int loss = P.loss;
+
+    // shared layout: sc[PP][eta] | red[PP][SPLIT][2] | acc[PP][SPLIT-1][2][K]
+    float* sc = smem + (size_t)pl * eta;
+    float* red = smem + (size_t)PP * eta + (size_t)pl * SPLIT * 2;
+    float* accs = smem + (((size_t)PP * eta + PP * SPLIT * 2 + 3) & ~(size_t)3) + (size_t)pl * (SPLIT - 1) * 2 * K;
+
+    float* coef = gbuf_coef(P.gbuf, n, K);
+    uint8_t* keep_out = gbuf_keep(P.gbuf, eta, n, K);
+
+    R Qo, Qs, AccO, AccS;
+    row_zero(AccO);
+    row_zero(AccS);
+    float spos = 0.f;
+    if (valid) {
+        R s, p, o;
+        const int32_t si = P.pos[3 * i + 0], pi = P.pos[3 * i + 1], oi = P.pos[3 * i + 2];
+        row_load(s, table_row(P.ent, si), lane, nvec, half);
+        row_load(p, P.rel + (size_t)pi * K, lane, nvec, half);
+        row_load(o, table_row(P.ent, oi), lane, nvec, half);
+        A::queries(s, p, o, Qo, Qs);
+        spos = A::finish(warp_sum(A::partial(Qo, o)), P.scale);
+    } else {
+        row_zero(Qo);
+        row_zero(Qs);
+    }
+    const float cpos = clip75(spos);
+    const bool pos_in = (spos >= -75.f) && (spos <= 75.f);
+    const float margin = P.margin;
+
+    float loss_acc = 0.f;  // identical on all lanes
+    float wsum = 0.f;      // pairwise: number of active hinges
+    float zinv = 0.f;      // multiclass: 1 / softmax denominator
+
+    // negatives of this warp: j = sub + SPLIT*m, m in [0,cnt)
+    const int cnt = valid ? (eta - sub + SPLIT - 1) / SPLIT : 0;
+
+    // MODE 0: single pass (pairwise / nll).  MODE 1: scores only (multiclass pass 1).
+    // MODE 2: backward with the scores in sc[] (multiclass pass 2).
+    auto sweep = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        for (int m0 = 0; m0 < cnt; m0 += 32) {
+            const int lim = min(32, cnt - m0);
+            int my_idx = 0, my_keep = 0;
+            int64_t my_q = 0;
+            if (lane < lim) {
+                my_q = (int64_t)(sub + SPLIT * (m0 + lane)) * n + i;
+                my_idx = P.repl[my_q];
+                my_keep = P.keep[my_q];
+            }
+            float my_c = 0.f, my_sn = 0.f;
+            for (int t = 0; t < lim; t += U) {
+                R r[U];
+                bool ob[U];
+                float part[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int src = min(t + u, 31);
+                    const int idx = __shfl_sync(0xffffffffu, my_idx, src);
+                    ob[u] = __shfl_sync(0xffffffffu, my_keep, src) != 0;
+                    if (t + u < lim) row_load(r[u], table_row(P.ent, idx), lane, nvec, half);
+                }
+                if constexpr (MODE != 2) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) part[u] = (t + u < lim) ? A::partial(ob[u] ? Qo : Qs, r[u]) : 0.f;
+#pragma unroll
+                    for (int o2 = 16; o2 > 0; o2 >>= 1)
+#pragma unroll
+                        for (int u = 0; u < U; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o2);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (t + u < lim) {
+                        const int j = sub + SPLIT * (m0 + t + u);
+                        float sn, w;
+                        if constexpr (MODE == 2) sn = sc[j];
+                        else sn = A::finish(part[u], P.scale);
+                        if constexpr (MODE == 1) {
+                            if (lane == 0) sc[j] = sn;
+                        } else {
+                            if constexpr (MODE == 2) {
+                                // losses/nll_multiclass.py:70-81 : softmax weight, zero outside the clip range
+                                const bool in = (sn >= -75.f) && (sn <= 75.f);
+                                w = in ? expf(sn) * zinv : 0.f;
+                            } else if (loss == KGE_LOSS_PAIRWISE) {
+                                // losses/pairwise.py:69 ; tf.maximum passes the gradient when t >= 0
+                                const float tt = margin - spos + sn;
+                                loss_acc += fmaxf(tt, 0.f);
+                                w = (tt >= 0.f) ? 1.f : 0.f;
+                                wsum += w;
+                            } else {
+                                // losses/nll.py:55-59 : log(1+exp(clip(neg)))
+                                const float e = expf(clip75(sn));
+                                loss_acc += logf(1.f + e);
+                                const bool in = (sn >= -75.f) && (sn <= 75.f);
+                                w = in ? e / (1.f + e) : 0.f;
+                            }
+                            const float c = A::coefficient(w, sn, P.scale);
+                            if (lane == t + u) {
+                                my_c = c;
+                                my_sn = sn;
+                            }
+                            if (ob[u]) A::accumulate(Qo, r[u], true, w, sn, P.scale, AccO);
+                            else A::accumulate(Qs, r[u], false, w, sn, P.scale, AccS);
+                        }
+                    }
+                }
+            }
+            if constexpr (MODE != 1) {
+                if (lane < lim) {
+                    coef[my_q] = my_c;
+                    keep_out[my_q] = (uint8_t)my_keep;
+                    if (P.dbg_scores != nullptr) P.dbg_scores[n + my_q] = my_sn;
+                }
+            }
+        }
+    };
+
+    if (loss == KGE_LOSS_MULTICLASS_NLL) {
+        sweep(std::integral_constant<int, 1>{});
+        __syncthreads();
+        float zpart = 0.f;
+        if (valid)
+            for (int j = lane; j < eta; j += 32) zpart += expf(clip75(sc[j]));
+        const float pe = expf(cpos);
+        const float z = warp_sum(zpart) + pe;
+        zinv = 1.f / z;
+        loss_acc = -logf(pe / z);
+        sweep(std::integral_constant<int, 2>{});
+    } else {
+        sweep(std::integral_constant<int, 0>{});
+    }
+
+    if constexpr (SPLIT > 1) {
+        if (sub > 0 && valid) {
+            float* a = accs + (size_t)(sub - 1) * 2 * K;
+            row_store(a, AccO, lane, nvec, half);
+            row_store(a + K, AccS, lane, nvec, half);
+            if (lane == 0) {
+                red[sub * 2 + 0] = loss_acc;
+                red[sub * 2 + 1] = wsum;
+            }
+        }
+        __syncthreads();
+        if (sub == 0 && valid) {
+#pragma unroll
+            for (int s2 = 1; s2 < SPLIT; ++s2) {
+                R t0, t1;
+                const float* a = accs + (size_t)(s2 - 1) * 2 * K;
+                row_load(t0, a, lane, nvec, half);
+                row_load(t1, a + K, lane, nvec, half);
+                row_add(AccO, t0);
+                row_add(AccS, t1);
+                if (loss != KGE_LOSS_MULTICLASS_NLL) loss_acc += red[s2 * 2 + 0];
+                wsum += red[s2 * 2 + 1];
+            }
+        }
+    }
+    if (sub != 0 || !valid) return;
+
+    float wpos;
+    if (loss == KGE_LOSS_PAIRWISE) {
+        wpos = -wsum;
+    } else if (loss == KGE_LOSS_NLL) {
+        // positives are tiled eta times (models/EmbeddingModel.py:724-729)
+        const float e = expf(-cpos);
+        loss_acc += (float)eta * logf(1.f + e);
+        wpos = pos_in ? -(float)eta * (e / (1.f + e)) : 0.f;
+    } else {
+        wpos = pos_in ? -(1.f - expf(cpos) * zinv) : 0.f;
+    }
+
+    float* G = P.gbuf;
+    row_store(G + (size_t)(3 * n + i) * K, Qo, lane, nvec, half);
+    row_store(G + (size_t)(4 * n + i) * K, Qs, lane, nvec, half);
+    {
+        // the positive itself: an object-side candidate with r = o and weight dL/dpos
+        R s, p, o, gs, gp, go;
+        const int32_t si = P.pos[3 * i + 0], pi = P.pos[3 * i + 1], oi = P.pos[3 * i + 2];
+        row_load(o, table_row(P.ent, oi), lane, nvec, half);
+        A::backward_pos(Qo, o, wpos, spos, P.scale, go, AccO);
+        row_load(s, table_row(P.ent, si), lane, nvec, half);
+        row_load(p, P.rel + (size_t)pi * K, lane, nvec, half);
+        A::fold(s, p, o, AccO, AccS, gs, gp, go);
+        row_store(G + (size_t)i * K, gs, lane, nvec, half);
+        row_store(G + (size_t)(n + i) * K, go, lane, nvec, half);
+        row_store(G + (size_t)(2 * n + i) * K, gp, lane, nvec, half);
+    }
+    if (lane == 0) {
+        P.loss_part[i] = loss_acc;
+        if (P.dbg_scores != nullptr) P.dbg_scores[i] = spos;
+    }
+}
+
+static inline size_t fwd_bwd_smem(int split, int eta, int K) {
+    const int pp = 4 / split;
+    size_t fl = (((size_t)pp * eta + pp * split * 2 + 3) & ~(size_t)3) + (size_t)pp * (split - 1) * 2 * K;
+    return fl * sizeof(float);
+}
+
+template <int MODEL, int V, int NCH, int U>
+static int launch_fwd_bwd_split(int split, const FwdBwdParams& P, cudaStream_t st) {
+    const int K = P.ent.K;
+    auto go = [&](auto kern, int sp) -> int {
+        const int pp = 4 / sp;
+        size_t smem = fwd_bwd_smem(sp, P.eta, K);
+        if (smem > 48 * 1024) KGE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)((P.n + pp - 1) / pp)), block(128);
+        kern<<<grid, block, smem, st>>>(P);
+        KGE_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    };
+    if constexpr (V == 4 && NCH <= 4) {
+        if (split >= 4) return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 4>, 4);
+        if (split == 2) return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 2>, 2);
+    }
+    return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 1>, 1);
+}
+
+template <int MODEL, int V>
+static int launch_fwd_bwd_nch(int nch, int split, const FwdBwdParams& P, cudaStream_t st) {
+    constexpr bool C = (MODEL == 3);
+    // U candidate rows in flight per warp: ~64 registers of row data
+    switch (nch) {
+        case 1: return launch_fwd_bwd_split<MODEL, V, 1, (C ? 8 : 8)>(split, P, st);
+        case 2: return launch_fwd_bwd_split<MODEL, V, 2, (C ? 4 : 8)>(split, P, st);
+        case 3:
+        case 4: return launch_fwd_bwd_split<MODEL, V, 4, (C ? 2 : 4)>(split, P, st);
+        case 5:
+        case 6:
+        case 7:
+        case 8: return launch_fwd_bwd_split<MODEL, V, 8, (C ? 1 : 2)>(split, P, st);
+        default: kge_set_error("kge_train: embedding size too large for the fused kernel (chunks/lane=%d)", nch); return -1;
+    }
+}
+
+template <int MODEL>
+static int launch_fwd_bwd_model(const FwdBwdParams& P, int sm_count, cudaStream_t st) {
+    const bool cplx = (MODEL == 3);
+    const int width = cplx ? P.k : P.ent.K;  // floats per half / per row
+    // cooperate SPLIT warps per positive when the batch alone cannot fill the machine
+    int split = 1;
+    const int64_t want = (int64_t)sm_count * 24;
+    if (P.n < want && P.eta >= 8) split = 2;
+    if (P.n * 2 < want && P.eta >= 16) split = 4;
+    if (width % 4 == 0) {
+        int nvec = width / 4;
+        return launch_fwd_bwd_nch<MODEL, 4>((nvec + 31) / 32, split, P, st);
+    }
+    return launch_fwd_bwd_nch<MODEL, 1>((width + 31) / 32, 1, P, st);
+}
+
+// one translation unit per model (parallel compilation): kge_train_fwd_m{0,1,2,3}.cu
+int kge_launch_fwd_bwd_m0(const FwdBwdParams& P, int sm_count, cudaStream_t st);
+int kge_launch_fwd_bwd_m1(const FwdBwdParams& P, int sm_count, cudaStream_t st);
+int kge_launch_fwd_bwd_m2(const FwdBwdParams& P, int sm_count, cudaStream_t st);
+int kge_launch_fwd_bwd_m3(const FwdBwdParams& P, int sm_count, cudaStream_t st);

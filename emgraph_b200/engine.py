@@ -103,8 +103,9 @@ class Engine:
     def has_tensor_core_rank(self) -> bool:
         return bool(self.lib.kge_has_tensor_core_rank())
 
-    def train_grad_rows(self, eta: int, n_pos: int) -> int:
-        return int(self.lib.kge_train_grad_rows(eta, n_pos))
+    def train_grad_floats(self, eta: int, n_pos: int, K: int) -> int:
+        """floats of the caller-owned gradient buffer for the phased (multi-GPU) calls"""
+        return int(self.lib.kge_train_grad_floats(eta, n_pos, K))
 
     def workspace_bytes(self) -> int:
         return int(self.lib.kge_ctx_workspace_bytes(self._h))
@@ -161,12 +162,12 @@ class Engine:
         a._keep = (ent, rel, pos, loss_out, ent_m, ent_v, rel_m, rel_v, repl, keep_subj, dbg_scores, dbg_grad_ent, dbg_grad_rel)
         return a
 
-    # kernels per step: emit, fwd_bwd, loss-reduce, iota, radix-sort (CUB onesweep: histogram +
-    # ceil(bits/8) passes), apply
+    # kernels per step: emit, fwd_bwd, loss-reduce, radix sort (CUB onesweep: histogram + exclusive
+    # sum + ceil(bits/8) passes), reduce_apply, span_apply
     @staticmethod
     def launches_per_step(E_plus_R: int) -> int:
         bits = max(1, math.ceil(math.log2(max(2, E_plus_R))))
-        return 5 + 1 + math.ceil(bits / 8)
+        return 3 + 2 + math.ceil(bits / 8) + 2
 
     def train_step(self, a: KgeTrainArgs):
         check(self.lib.kge_train_step(self._h, C.byref(a), _stream()))
@@ -191,11 +192,18 @@ class Engine:
         check(self.lib.kge_train_fwd_bwd(self._h, C.byref(a), _ptr(grad_rows), _stream()))
         self.launches += 2
 
+    def grad_table(self, bufs, eta: int, n_pos: int, K: int) -> KgeTable:
+        """kge_table describing the ranks' gradient buffers for train_apply (one tensor / pointer per rank)."""
+        if isinstance(bufs, torch.Tensor):
+            bufs = [bufs]
+        S = (3 + eta) * n_pos
+        return make_table(list(bufs), rows=S * len(bufs), rows_per_shard=S, K=K)
+
     def train_apply(self, a: KgeTrainArgs, keys_all, grads: KgeTable, row_begin: int, row_end: int):
         _chk_i32(keys_all, "keys_all")
         check(self.lib.kge_train_apply(self._h, C.byref(a), _ptr(keys_all), keys_all.numel(), C.byref(grads),
                                        row_begin, row_end, _stream()))
-        self.launches += self.launches_per_step(a.ent.rows + a.R) - 3
+        self.launches += self.launches_per_step(a.ent.rows + a.R) - 3 + 1  # + iota
 
     def normalize_rows(self, emb):
         _chk_f32(emb, "emb")

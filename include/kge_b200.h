@@ -89,8 +89,9 @@ typedef struct kge_train_args {
 int         kge_abi_version(void);
 /* 1 if this build carries the tcgen05 3xTF32 ranking sweep (use_tensor_cores=1 in kge_rank_counts) */
 int         kge_has_tensor_core_rank(void);
-/* rows of the caller-owned grad_rows buffer kge_train_fwd_bwd writes for a batch of n_pos positives */
-int64_t     kge_train_grad_rows(int eta, int64_t n_pos);
+/* floats in the caller-owned gradient buffer kge_train_fwd_bwd writes for a batch of n_pos positives:
+ * 5 rows per positive (grad s, grad o, grad p, query Qo, query Qs) + eta coefficients + eta side flags */
+int64_t     kge_train_grad_floats(int eta, int64_t n_pos, int K);
 const char* kge_last_error(void);
 
 /* per-device context (replaces the reference's implicit TF runtime state) */
@@ -111,13 +112,15 @@ int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* stream);
  * NCCL collectives (key all-gather / barriers) between them:
  *  1. kge_train_emit: draw corruptions, write this rank's sort keys (entity id, or E + relation id)
  *     into keys_out[n_slots] with n_slots = (3+eta)*n_pos; slot layout documented in DESIGN.md.
- *  2. kge_train_fwd_bwd: fused forward + loss + backward; per-slot gradient rows into grad_rows
- *     [n_slots,K] (caller-owned so that peers can map it).
- *  3. kge_train_apply: sort all ranks' keys, segmented-reduce duplicate rows reading gradient rows
- *     through `grads` (shard r = rank r's grad_rows, rows_per_shard = n_slots_per_rank) and apply
- *     the optimizer to rows in [row_begin,row_end) and to every relation row. */
+ *  2. kge_train_fwd_bwd: fused forward + loss + backward into grad_buf (kge_train_grad_floats floats,
+ *     caller-owned so that peers can map it): the gradient rows of the positive's s, o, p, its two
+ *     folded queries and one coefficient per negative -- the gradient row of a replacement entity is
+ *     re-materialised from (coefficient, query row, current row) by the reduction, never stored.
+ *  3. kge_train_apply: sort all ranks' keys, segmented-reduce duplicate rows reading through `grads`
+ *     (shard r = rank r's grad_buf, rows_per_shard = n_slots per rank, every rank the same n_pos) and
+ *     apply the optimizer to rows in [row_begin,row_end) and to every relation row. */
 int kge_train_emit(kge_ctx* ctx, const kge_train_args* a, int32_t* keys_out, void* stream);
-int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* grad_rows, void* stream);
+int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, void* stream);
 int kge_train_apply(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, int64_t n_keys,
                     const kge_table* grads, int64_t row_begin, int64_t row_end, void* stream);
 
