@@ -1,12 +1,441 @@
-// tcgen05 3xTF32 ranking sweep (placeholder until the tensor-core path lands).
+// tcgen05 3xTF32 ranking sweep for sm_100a (DistMult / ComplEx / HolE).
+//
+// S[m,e] = sum_k Q[m,k] * Ent[e,k]  with Q the folded queries of the test triples is a
+// dense [2T,K] x [K,E] contraction.  fp32 accuracy is kept with the 3xTF32 split: every operand is
+// pre-split into hi = top 19 bits and lo = x - hi (exact), and each k-step issues
+//     D += Qhi*Ehi ; D += Qhi*Elo ; D += Qlo*Ehi           (fp32 accumulate in TMEM)
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) of the 4 operand tiles of a k-block
+//                              (Qhi,Qlo: 128x32 fp32; Ehi,Elo: 256x32 fp32) into a 2-stage smem ring
+//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::tf32, M=128 N=256 K=8, 12 MMAs per stage,
+//                              accumulator = 128 lanes x 256 columns of TMEM, double buffered (512 cols)
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 -> each thread owns ONE query row and 32 candidate
+//                              scores; x1e5 int truncation (F7), compare with the positive's quantised
+//                              score, filter bitmask from the sorted known-triple list, popcount into the
+//                              four per-row counters.  The [T,2E] score matrix never leaves the SM.
+// The epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Replaces reference models/EmbeddingModel.py:1856-1866 (score all corruptions), :1942-1986 (filter +
+// rank) and :1989-2033 (perform_comparision) for the trilinear models.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "kge_common.cuh"
+
+#define TC_BM 128
+#define TC_BN 256
+#define TC_BK 32   // fp32 elements per k-block = 128 bytes = one SWIZZLE_128B row
+#define TC_STAGES 2
+#define TC_A_BYTES (TC_BM * TC_BK * 4)   // 16 KB
+#define TC_B_BYTES (TC_BN * TC_BK * 4)   // 32 KB
+#define TC_STAGE_BYTES (2 * TC_A_BYTES + 2 * TC_B_BYTES)  // 96 KB
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+#define TC_THREADS 192
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// spin with a watchdog: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start address >> 4,
+// LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4, version 1, layout 2.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor: D=F32 (bits 4-5 = 1), A=B=TF32 (bits 7-9, 10-12 = 2), K-major A and B,
+// N>>3 at bits 17-22, M>>4 at bits 24-28
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation: hi/lo split into zero-padded [2*rows_pad, Kp] (rows [0,rows_pad) hi, then lo)
+// ------------------------------------------------------------------------------------------------
+__global__ void kge_tf32_split_kernel(const float* __restrict__ src, int64_t rows, int K, int Kp, int64_t rows_pad,
+                                      float* __restrict__ dst) {
+    const int64_t total = rows_pad * (int64_t)Kp;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / Kp;
+        const int c = (int)(t - r * Kp);
+        float x = (r < rows && c < K) ? src[r * (int64_t)K + c] : 0.f;
+        float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        dst[t] = hi;
+        dst[total + t] = x - hi;
+    }
+}
+
+struct TcParams {
+    int k_blocks;
+    int64_t M;        // query rows handled (after side selection)
+    int64_t Mp, Np;   // padded row counts of the split operands
+    int64_t T;
+    int64_t q_row0;   // first query row handled: 0 (object sweep first) or T
+    int64_t row_begin, row_end;  // global entity ids of local rows [0, row_end-row_begin)
+    const int32_t* test;
+    const int32_t* pos_q;
+    const int32_t* excl_lo;
+    const int32_t* excl_hi;
+    const int32_t* sp_ent;
+    const int32_t* po_ent;
+    int32_t* counts;
+    int n_m_tiles, n_n_tiles, nsplit;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE, TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full = bars;                    // [TC_STAGES]
+    uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]
+    uint64_t* tfull = bars + 2 * TC_STAGES;   // [2]
+    uint64_t* tempty = bars + 2 * TC_STAGES + 2;  // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQ) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmE) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < TC_STAGES; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&tfull[b], 1);
+                mbar_init(&tempty[b], 4);  // one arrive per epilogue warp
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_units = P.n_m_tiles * P.nsplit;
+    const int tiles_per_split = (P.n_n_tiles + P.nsplit - 1) / P.nsplit;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int mt = u / P.nsplit, sp = u - mt * P.nsplit;
+                const int nt0 = sp * tiles_per_split, nt1 = min(P.n_n_tiles, nt0 + tiles_per_split);
+                const int m0 = mt * TC_BM;
+                for (int nt = nt0; nt < nt1; ++nt) {
+                    const int n0 = nt * TC_BN;
+                    for (int kb = 0; kb < P.k_blocks; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* st = smem + (size_t)stage * TC_STAGE_BYTES;
+                        mbar_expect_tx(&full[stage], TC_STAGE_BYTES);
+                        tma_load_2d(st, &tmQ, kb * TC_BK, m0, &full[stage]);
+                        tma_load_2d(st + TC_A_BYTES, &tmQ, kb * TC_BK, (int)P.Mp + m0, &full[stage]);
+                        tma_load_2d(st + 2 * TC_A_BYTES, &tmE, kb * TC_BK, n0, &full[stage]);
+                        tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmE, kb * TC_BK, (int)P.Np + n0, &full[stage]);
+                        if (++stage == TC_STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t tile_it = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int mt = u / P.nsplit, sp = u - mt * P.nsplit;
+                const int nt0 = sp * tiles_per_split, nt1 = min(P.n_n_tiles, nt0 + tiles_per_split);
+                for (int nt = nt0; nt < nt1; ++nt, ++tile_it) {
+                    const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
+                    mbar_wait(&tempty[as], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * TC_BN;
+                    for (int kb = 0; kb < P.k_blocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + (size_t)stage * TC_STAGE_BYTES);
+                        const uint64_t a_hi = make_sw128_desc(sa);
+                        const uint64_t a_lo = make_sw128_desc(sa + TC_A_BYTES);
+                        const uint64_t b_hi = make_sw128_desc(sa + 2 * TC_A_BYTES);
+                        const uint64_t b_lo = make_sw128_desc(sa + 2 * TC_A_BYTES + TC_B_BYTES);
+#pragma unroll
+                        for (int j = 0; j < TC_BK / 8; ++j) {
+                            const uint64_t off = (uint64_t)(j * 32 >> 4);  // 8 tf32 = 32 bytes along K
+                            tc_mma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, (kb | j) != 0);
+                            tc_mma_tf32(d_tmem, a_hi + off, b_lo + off, idesc, 1);
+                            tc_mma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1);
+                        }
+                        tc_commit(&empty[stage]);  // smem stage reusable once these MMAs retire
+                        if (++stage == TC_STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    tc_commit(&tfull[as]);  // accumulator complete
+                }
+            }
+        }
+    } else {
+        // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        uint32_t tile_it = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int mt = u / P.nsplit, sp = u - mt * P.nsplit;
+            const int nt0 = sp * tiles_per_split, nt1 = min(P.n_n_tiles, nt0 + tiles_per_split);
+            const int64_t m = (int64_t)mt * TC_BM + row_in_tile;
+            const bool row_ok = m < P.M;
+            int32_t pq = 0, self = -1, cur = 0, hi = 0;
+            const int32_t* list = nullptr;
+            int64_t tt = 0;
+            int side = 0;
+            const int64_t e_first = P.row_begin + (int64_t)nt0 * TC_BN;
+            if (row_ok) {
+                const int64_t r = P.q_row0 + m;
+                side = r >= P.T ? 1 : 0;
+                tt = r - (int64_t)side * P.T;
+                self = side == 0 ? P.test[3 * tt + 2] : P.test[3 * tt + 0];
+                pq = P.pos_q[tt];
+                list = side == 0 ? P.sp_ent : P.po_ent;
+                int32_t a = P.excl_lo[r], b = P.excl_hi[r];
+                hi = b;
+                while (a < b) {  // first known entity >= first candidate of this unit
+                    int32_t mid = (a + b) >> 1;
+                    if ((int64_t)list[mid] < e_first) a = mid + 1;
+                    else b = mid;
+                }
+                cur = a;
+            }
+            int64_t next_f = (cur < hi) ? (int64_t)list[cur] : (int64_t)1 << 40;
+            int c_gt = 0, c_eq = 0, c_gtf = 0, c_eqf = 0;
+            for (int nt = nt0; nt < nt1; ++nt, ++tile_it) {
+                const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
+                mbar_wait(&tfull[as], aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TC_BN;
+#pragma unroll 1
+                for (int c = 0; c < TC_BN / 32; ++c) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + c * 32, v);
+                    tc_wait_ld();
+                    const int64_t e_base = P.row_begin + (int64_t)nt * TC_BN + c * 32;
+                    uint32_t fmask = 0;
+                    while (next_f < e_base + 32) {
+                        if (next_f >= e_base) fmask |= 1u << (int)(next_f - e_base);
+                        ++cur;
+                        next_f = (cur < hi) ? (int64_t)list[cur] : (int64_t)1 << 40;
+                    }
+                    const int64_t left = P.row_end - e_base;  // valid candidates in this chunk
+                    uint32_t valid = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+                    const int64_t ds = (int64_t)self - e_base;
+                    if (ds >= 0 && ds < 32) valid &= ~(1u << (int)ds);
+                    uint32_t gtm = 0, eqm = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int q = quantise_score(__uint_as_float(v[i]));
+                        gtm |= (q > pq ? 1u : 0u) << i;
+                        eqm |= (q == pq ? 1u : 0u) << i;
+                    }
+                    gtm &= valid;
+                    eqm &= valid;
+                    c_gt += __popc(gtm);
+                    c_eq += __popc(eqm);
+                    c_gtf += __popc(gtm & fmask);
+                    c_eqf += __popc(eqm & fmask);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+            }
+            if (row_ok) {
+                int32_t* dst = P.counts + (tt * 2 + side) * 4;
+                if (c_gt) atomicAdd(dst + 0, c_gt);
+                if (c_eq) atomicAdd(dst + 1, c_eq);
+                if (c_gtf) atomicAdd(dst + 2, c_gtf);
+                if (c_eqf) atomicAdd(dst + 3, c_eqf);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_tensormap_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }
+    return fn;
+}
+
+// 2-D row-major fp32 [rows, Kp] with a (32 x box_rows) box and the 128-byte swizzle
+static int make_tmap(CUtensorMap* tm, const float* base, int64_t rows, int Kp, int box_rows) {
+    auto enc = get_tensormap_encoder();
+    KGE_REQUIRE(enc != nullptr, "kge_rank_counts: cuTensorMapEncodeTiled unavailable in this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    KGE_REQUIRE(r == CUDA_SUCCESS, "kge_rank_counts: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
 
 int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ, int64_t T, const float* ent_local,
                       int64_t row_begin, int64_t row_end, const int32_t* test, const int32_t* pos_q,
                       const int32_t* excl_lo, const int32_t* excl_hi, const int32_t* sp_ent, const int32_t* po_ent,
                       int side_mask, int32_t* counts, cudaStream_t st) {
-    kge_set_error("kge_rank_counts: tensor-core sweep not built in this version");
-    return -4;
+    (void)model;
+    (void)NQ;
+    const int64_t n_local = row_end - row_begin;
+    if (n_local <= 0 || T <= 0) return 0;
+    int64_t q_row0 = 0, M = 2 * T;
+    if (side_mask == 1) M = T;
+    if (side_mask == 2) {
+        q_row0 = T;
+        M = T;
+    }
+    const int Kp = ((K + TC_BK - 1) / TC_BK) * TC_BK;
+    const int64_t Mp = ((M + TC_BM - 1) / TC_BM) * TC_BM;
+    const int64_t Np = ((n_local + TC_BN - 1) / TC_BN) * TC_BN;
+    KGE_REQUIRE(2 * Mp < (int64_t)INT32_MAX && 2 * Np < (int64_t)INT32_MAX, "kge_rank_counts: operand too large for the TMA coordinates");
+    if (ctx->q_hi.reserve((size_t)2 * Mp * Kp * sizeof(float))) return -2;
+    if (ctx->e_hi.reserve((size_t)2 * Np * Kp * sizeof(float))) return -2;
+    {
+        int threads = 256;
+        int64_t tot = Mp * Kp;
+        int blocks = (int)std::min<int64_t>((tot + threads - 1) / threads, (int64_t)ctx->sm_count * 32);
+        kge_tf32_split_kernel<<<blocks, threads, 0, st>>>(q + (size_t)q_row0 * K, M, K, Kp, Mp, ctx->q_hi.as<float>());
+        tot = Np * Kp;
+        blocks = (int)std::min<int64_t>((tot + threads - 1) / threads, (int64_t)ctx->sm_count * 32);
+        kge_tf32_split_kernel<<<blocks, threads, 0, st>>>(ent_local, n_local, K, Kp, Np, ctx->e_hi.as<float>());
+        KGE_CUDA_CHECK(cudaGetLastError());
+    }
+    CUtensorMap tmQ, tmE;
+    if (int rc = make_tmap(&tmQ, ctx->q_hi.as<float>(), 2 * Mp, Kp, TC_BM)) return rc;
+    if (int rc = make_tmap(&tmE, ctx->e_hi.as<float>(), 2 * Np, Kp, TC_BN)) return rc;
+
+    TcParams P;
+    P.k_blocks = Kp / TC_BK;
+    P.M = M;
+    P.Mp = Mp;
+    P.Np = Np;
+    P.T = T;
+    P.q_row0 = q_row0;
+    P.row_begin = row_begin;
+    P.row_end = row_end;
+    P.test = test;
+    P.pos_q = pos_q;
+    P.excl_lo = excl_lo;
+    P.excl_hi = excl_hi;
+    P.sp_ent = sp_ent;
+    P.po_ent = po_ent;
+    P.counts = counts;
+    P.n_m_tiles = (int)(Mp / TC_BM);
+    P.n_n_tiles = (int)(Np / TC_BN);
+    // enough work units for ~12 rounds over the SMs, each unit at least 2 entity tiles when possible
+    int nsplit = (int)std::max<int64_t>(1, ((int64_t)ctx->sm_count * 12 + P.n_m_tiles - 1) / P.n_m_tiles);
+    nsplit = std::min(nsplit, std::max(1, P.n_n_tiles / 2));
+    P.nsplit = nsplit;
+    const int n_units = P.n_m_tiles * nsplit;
+    const int grid = std::min(n_units, ctx->sm_count);
+    static bool attr_set = false;
+    if (!attr_set) {
+        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    kge_rank_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmQ, tmE, P);
+    KGE_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
-extern "C" int kge_has_tensor_core_rank(void) { return 0; }
+extern "C" int kge_has_tensor_core_rank(void) { return 1; }

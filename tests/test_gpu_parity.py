@@ -291,3 +291,69 @@ def test_rank_edge_cases(engine):
         got = _rank_gpu(engine, "TransE", k, ent1, rel1, test, None, "s,o", strat)
         exp = ko.ranks("TransE", k, ent1, rel1, test, None, "s,o", strat)
         np.testing.assert_array_equal(got, exp)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05 3xTF32) ranking sweep
+# ------------------------------------------------------------------------------------------------
+def _assert_ranks_close(model, k, ent, rel, test, got, exp, norm=1, max_frac=0.04):
+    assert got.shape == exp.shape
+    bad = np.argwhere(got != exp)
+    for idx in bad:
+        t = idx[0]
+        col = idx[1] if exp.ndim == 2 else 1
+        if exp.ndim == 2:
+            assert _admissible(model, k, ent, rel, test[t], col, got[tuple(idx)], exp[tuple(idx)], norm), \
+                (t, col, got[tuple(idx)], exp[tuple(idx)])
+    assert len(bad) <= max(2, int(exp.size * max_frac)), len(bad)
+
+
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "rank_*.npz")) if "transe" not in p),
+                         ids=os.path.basename)
+def test_tc_ranks_vs_reference_golden(engine, path):
+    if not engine.has_tensor_core_rank():
+        pytest.skip("library built without the tcgen05 sweep")
+    g = np.load(path)
+    model, k, norm = str(g["model"]), int(g["k"]), int(g["norm"])
+    for side in ("s,o", "s+o", "s", "o"):
+        for strat in ("worst", "middle"):
+            for fl in (0, 1):
+                key = "ranks_%s_%s_%d" % (side.replace(",", "c").replace("+", "p"), strat, fl)
+                got = _rank_gpu(engine, model, k, g["ent"], g["rel"], g["test"], g["filt"] if fl else None, side, strat, norm, tc=True)
+                exp = g[key]
+                if exp.ndim == 2:
+                    _assert_ranks_close(model, k, g["ent"], g["rel"], g["test"], got, exp, norm)
+                else:
+                    assert got.shape == exp.shape and (got != exp).sum() <= max(1, exp.size // 25), key
+
+
+@pytest.mark.parametrize("model,k,E,T", [("DistMult", 200, 1500, 150), ("ComplEx", 200, 1500, 150), ("HolE", 35, 900, 70),
+                                          ("DistMult", 64, 5000, 700), ("ComplEx", 100, 14541, 300)])
+def test_tc_ranks_vs_fp32_sweep_and_oracle(engine, model, k, E, T):
+    """The tcgen05 path against the fp32 CUDA-core sweep (same quantisation rule) and the oracle."""
+    if not engine.has_tensor_core_rank():
+        pytest.skip("library built without the tcgen05 sweep")
+    rng = np.random.default_rng(7)
+    R, F = 9, 8000
+    K = ko.internal_k(model, k)
+    ent = (rng.normal(size=(E, K)) * 0.3).astype(np.float32)
+    rel = (rng.normal(size=(R, K)) * 0.3).astype(np.float32)
+    filt = ko.synthetic_triples(E, R, F, seed=11, zipf=True)
+    test = filt[rng.permutation(F)[:T]]
+    for side, fl in (("s,o", True), ("s,o", False), ("s+o", True), ("o", True), ("s", True)):
+        tc = _rank_gpu(engine, model, k, ent, rel, test, filt if fl else None, side, "worst", tc=True)
+        ref = _rank_gpu(engine, model, k, ent, rel, test, filt if fl else None, side, "worst", tc=False)
+        assert tc.shape == ref.shape
+        if side == "s,o":
+            _assert_ranks_close(model, k, ent, rel, test, tc, ref)
+        else:
+            assert (tc != ref).mean() <= 0.05
+        assert np.abs(tc.astype(np.int64) - ref).max() <= 3
+    if E <= 2000:
+        exp = ko.ranks(model, k, ent, rel, test, filt, "s,o", "worst")
+        got = _rank_gpu(engine, model, k, ent, rel, test, filt, "s,o", "worst", tc=True)
+        _assert_ranks_close(model, k, ent, rel, test, got, exp)
+    # size-independent properties on the tensor-core path
+    so_f = _rank_gpu(engine, model, k, ent, rel, test, filt, "s,o", "worst", tc=True)
+    so_u = _rank_gpu(engine, model, k, ent, rel, test, None, "s,o", "worst", tc=True)
+    assert np.all(so_f <= so_u) and so_f.min() >= 1 and so_u.min() >= 2 and so_u.max() <= E + 1
