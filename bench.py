@@ -215,9 +215,11 @@ def main():
         if rank_id != 0:
             return 0
         return reference_main(args, w)
-    if world > 1 or args.gpus > 1:
-        from emgraph_b200 import bench_multi
-        return bench_multi.main(args, w, WORKLOADS)
+    if world > 1:
+        return multi_gpu_main(args, w, rank_id, world)
+    if args.gpus > 1:
+        raise SystemExit("--gpus %d needs one process per GPU: launch with `python -m torch.distributed.run --nnodes=1 "
+                         "--nproc-per-node %d --master-addr 127.0.0.1 --master-port P bench.py --gpus %d ...`" % (args.gpus, args.gpus, args.gpus))
     return single_gpu_main(args, w)
 
 
@@ -399,6 +401,188 @@ def single_gpu_main(args, w):
         if do_rank and rk is not None:
             line["rank"]["cpu_baseline"] = {"value": rk["value"], "unit": "test triples/s", "cores": cores, "kind": "port", "sample": rk["sample"]}
     print(json.dumps(line), flush=True)
+    return 0
+
+
+def multi_gpu_main(args, w, rank, world):
+    """Row-sharded table over `world` GPUs.  Weak scaling for training: every
+    rank takes its own batch of B positives per step; ranking shards the entity sweep (fixed T)."""
+    import torch
+    import torch.distributed as dist
+    from emgraph_b200 import _lib
+    from emgraph_b200.distributed import ShardedKGE, batch_slice
+    from emgraph_b200.evaluation import EvalDataset
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = load_peaks()
+    E, R, k, eta = w["E"], w["R"], w["k"], w["eta"]
+    K = internal_k(w["model"], k)
+    B = int(math.ceil(w["N"] / w["batches"]))
+    steps, warmup = args.steps, args.warmup
+    do_rank = not args.no_rank
+    need = (steps * 2 + warmup + 8) * B * world
+    X = synth_triples(E, R, w["N"] if do_rank else min(w["N"], need), seed=0, zipf=not args.uniform)
+    sk = ShardedKGE(w["model"], k, eta, w["loss"], w["opt"], E, R, B, lr=w["lr"], margin=w["margin"], seed=0, device=local)
+    eng, dev = sk.eng, sk.eng.tdev
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    lim_e, lim_r = math.sqrt(6.0 / (E + K)), math.sqrt(6.0 / (R + K))
+    sk.ent.tensor.uniform_(-lim_e, lim_e, generator=g)
+    sk.rel.copy_(torch.from_numpy(glorot(R, K, 3)).to(dev))
+    dist.barrier()
+    Xd = torch.from_numpy(X).to(dev)
+    Xh = torch.from_numpy(X).pin_memory()
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    it = 0
+
+    def my_batch(i):
+        return batch_slice(X.shape[0], world, rank, i, B)
+
+    for _ in range(warmup):
+        lo, hi = my_batch(it)
+        sk.train_step(Xd[lo:hi])
+        it += 1
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    dist.barrier()
+    for s in range(steps):
+        flush.fill_(float(s))
+        lo, hi = my_batch(it)
+        evs[s][0].record()
+        sk.train_step(Xd[lo:hi])
+        evs[s][1].record()
+        it += 1
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = (eng.launches - l0) * world
+    t_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev)
+    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    t_ms = float(t_ms.item())
+    triples_per_step = world * B * (1 + eta)
+    value = steps * triples_per_step / (t_ms * 1e-3)
+
+    # e2e: every step the rank's batch comes from pinned host memory and the global loss is read back
+    stage = torch.empty((B, 3), dtype=torch.int32, device=dev)
+    for _ in range(2):
+        lo, hi = my_batch(it)
+        stage.copy_(Xh[lo:hi], non_blocking=True)
+        float(sk.train_step(stage).item())
+        it += 1
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(steps):
+        lo, hi = my_batch(it)
+        stage.copy_(Xh[lo:hi], non_blocking=True)
+        last = float(sk.train_step(stage).item())
+        it += 1
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e2e.item())
+    assert math.isfinite(last), "training diverged in the benchmark"
+    clocks = sampler.stop()
+
+    # roofline of the per-rank forward/backward kernel (gathers cross NVLink for (world-1)/world of the rows)
+    a = eng.train_args(ent=sk.ent_table, rel=sk.rel, pos=Xd[:B], loss_out=sk.loss_dev, step=sk.step + 1, **sk.kw, **sk._state_tables())
+    eng.train_emit(a, sk.keys_local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    e0.record()
+    for _ in range(5):
+        eng.train_fwd_bwd(a, sk.gbuf.tensor)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_fb = e0.elapsed_time(e1) / 5
+    bytes_fb = ((3 + eta) * 4 * K + 5 * 4 * K + 5 * eta) * B
+    nv_bytes = (3 + eta) * 4 * K * B * (world - 1) / world
+    ach = bytes_fb / (t_fb * 1e-3) / 1e9
+    roofline = {"bound": "nvlink" if world > 1 else "hbm", "kernel": "kge_fwd_bwd_kernel (peer gathers)", "achieved": nv_bytes / (t_fb * 1e-3) / 1e9,
+                "peak": 770.0, "unit": "GB/s per direction per GPU (measured peer copy, B200_PROFILING.md)",
+                "frac": nv_bytes / (t_fb * 1e-3) / 1e9 / 770.0, "traffic": None, "kernel_ms": t_fb,
+                "algorithmic_bytes_per_launch": bytes_fb, "nvlink_bytes_per_launch": nv_bytes, "local_GBps": ach}
+
+    line = {
+        "metric": TRAIN_METRIC, "value": value, "unit": "triples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "batch_positives_per_gpu": B, "global_batch": B * world, "eta": eta,
+                   "E": E, "R": R, "K": K, "entity_popularity": "uniform" if args.uniform else "zipf(1.0)",
+                   "optimizer": "stateful sparse " + w["opt"], "l2": "flushed before every timed step (%d MiB write)" % (L2_FLUSH_BYTES >> 20),
+                   "parallelism": "dp%d, entity table + optimizer state row-sharded, peer-memory gathers" % world},
+        "e2e": {"value": steps * triples_per_step / t_e2e, "unit": "triples/s", "h2d_bytes_per_step": B * 12 * world,
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * t_e2e / steps, "api": "ShardedKGE.train_step (host batch, loss read back)"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+    }
+
+    if do_rank:
+        T = w["T"]
+        rng = np.random.Generator(np.random.PCG64(1))
+        test = X[rng.permutation(X.shape[0])[:T]].copy()
+        ds = EvalDataset(test, X)
+        t0 = time.perf_counter()
+        ds.build_filter(eng, E, R)
+        torch.cuda.synchronize()
+        t_filter = time.perf_counter() - t0
+        use_tc = ((w["model"] != "TransE") if args.rank_tc < 0 else bool(args.rank_tc)) and eng.has_tensor_core_rank()
+        test_d = ds.test_device(dev)
+        test_h = ds.test_host_pinned()
+        for _ in range(2):
+            ranks = sk.rank(test_d, side=0, strategy=0, filtered=True, use_tensor_cores=use_tc)
+        torch.cuda.synchronize()
+        dist.barrier()
+        n = max(1, args.rank_steps)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        l0 = eng.launches
+        for s in range(n):
+            flush.fill_(float(s))
+            evs[s][0].record()
+            ranks = sk.rank(test_d, side=0, strategy=0, filtered=True, use_tensor_cores=use_tc)
+            evs[s][1].record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        r_launches = (eng.launches - l0) * world
+        tr = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / n], device=dev)
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        tr = float(tr.item())
+        stage_t = torch.empty((T, 3), dtype=torch.int32, device=dev)
+        out_h = torch.empty((T, 2), dtype=torch.int32).pin_memory()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for s in range(n):
+            stage_t.copy_(test_h, non_blocking=True)
+            out_h.copy_(sk.rank(stage_t, side=0, strategy=0, filtered=True, use_tensor_cores=use_tc))
+            torch.cuda.synchronize()
+        dist.barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / n], device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        te = float(te.item())
+        rk = out_h.numpy()
+        assert rk.min() >= 1
+        flops = 4.0 * E * K * T
+        peak = peaks["bf16"] / 2.0 * world
+        line["rank"] = {"metric": RANK_METRIC, "value": T / (tr * 1e-3), "unit": "test triples/s", "ms_per_step": tr, "steps": n, "T": T,
+                        "scaling": "strong (entity sweep sharded by row range, counts all-reduced)", "corrupt_side": "s,o",
+                        "filter_triples": int(X.shape[0]), "filter_build_ms": 1e3 * t_filter, "tensor_cores": bool(use_tc),
+                        "mrr": float(np.mean(1.0 / rk.reshape(-1))),
+                        "e2e": {"value": T / te, "unit": "test triples/s", "h2d_bytes_per_step": T * 12 * world, "d2h_bytes_per_step": T * 8 * world,
+                                "api": "ShardedKGE.rank (host test triples, host ranks)"},
+                        "gpu_launches": r_launches,
+                        "roofline": {"bound": "tensor" if use_tc else "fp32-alu", "achieved": flops / (tr * 1e-3) / 1e12, "peak": peak,
+                                     "unit": "TFLOP/s (logical; x3 TF32 MMAs issued), whole job", "frac": flops / (tr * 1e-3) / 1e12 / peak,
+                                     "traffic": None, "kernel_ms": tr}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
     return 0
 
 

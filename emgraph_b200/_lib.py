@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkge_b200.so")
 
 KGE_MAX_SHARDS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 MODEL_IDS = {"TransE": 0, "TransE_L2": 1, "DistMult": 2, "ComplEx": 3, "HolE": 4}
 LOSS_IDS = {"pairwise": 0, "nll": 1, "multiclass_nll": 2}
@@ -64,6 +64,7 @@ SYMBOLS = {
     "kge_train_fwd_bwd": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P]),
     "kge_train_apply": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _L, C.POINTER(KgeTable), _L, _L, _P]),
     "kge_train_step_host": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P, _P]),
+    "kge_train_select": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _L, _L, _L, _P]),
     "kge_normalize_rows": (_I, [_P, _P, _L, _I, _P]),
     "kge_filter_build": (_I, [_P, _P, _L, _L, _L, _P]),
     "kge_filter_clear": (_I, [_P]),
@@ -71,6 +72,8 @@ SYMBOLS = {
     "kge_rank_counts": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _L, _P, _L, _I, _I, _I, _P, _P]),
     "kge_rank_finalize": (_I, [_P, _P, _L, _I, _I, _I, _P, _P]),
     "kge_rank_host": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _I, _I, _I, _I, _P, _P]),
+    "kge_dev_alloc": (_I, [_L, C.POINTER(_P)]),
+    "kge_dev_free": (_I, [_P]),
     "kge_ipc_export": (_I, [_P, _P]),
     "kge_ipc_open": (_I, [_P, C.POINTER(_P)]),
     "kge_ipc_close": (_I, [_P]),

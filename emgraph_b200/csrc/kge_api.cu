@@ -41,19 +41,21 @@ extern "C" int kge_ctx_destroy(kge_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    KgeBuf* bufs[] = {&c->keys_in, &c->keys_out, &c->vals_in, &c->vals_out, &c->sort_tmp, &c->repl, &c->keep,
-                      &c->grad_rows, &c->loss_part, &c->neg_scores, &c->partial, &c->span_head, &c->h_pos, &c->h_loss, &c->h_test, &c->h_counts, &c->h_ranks, &c->q_fold, &c->q_hi, &c->q_lo, &c->e_hi, &c->e_lo,
+    KgeBuf* bufs[] = {&c->sort_tmp, &c->repl, &c->keep,
+                      &c->grad_rows, &c->loss_part, &c->neg_scores, &c->partial, &c->span_head, &c->ks_in, &c->ks_sel, &c->ks_sorted, &c->sel_flags, &c->sel_count, &c->h_pos, &c->h_loss, &c->h_test, &c->h_counts, &c->h_ranks, &c->q_fold, &c->q_hi, &c->q_lo, &c->e_hi, &c->e_lo,
                       &c->pos_q, &c->excl_lo, &c->excl_hi, &c->f_sp_comp, &c->f_po_comp, &c->f_sp_ent, &c->f_po_ent,
                       &c->f_tmp, &c->f_tmp2, &c->f_count};
     for (KgeBuf* b : bufs) b->release();
+    if (c->h_count) cudaFreeHost(c->h_count);
+    if (c->ev_count) cudaEventDestroy(c->ev_count);
     delete c;
     return 0;
 }
 
 extern "C" int64_t kge_ctx_workspace_bytes(kge_ctx* c) {
     if (!c) return 0;
-    KgeBuf* bufs[] = {&c->keys_in, &c->keys_out, &c->vals_in, &c->vals_out, &c->sort_tmp, &c->repl, &c->keep,
-                      &c->grad_rows, &c->loss_part, &c->neg_scores, &c->partial, &c->span_head, &c->h_pos, &c->h_loss, &c->h_test, &c->h_counts, &c->h_ranks, &c->q_fold, &c->q_hi, &c->q_lo, &c->e_hi, &c->e_lo,
+    KgeBuf* bufs[] = {&c->sort_tmp, &c->repl, &c->keep,
+                      &c->grad_rows, &c->loss_part, &c->neg_scores, &c->partial, &c->span_head, &c->ks_in, &c->ks_sel, &c->ks_sorted, &c->sel_flags, &c->sel_count, &c->h_pos, &c->h_loss, &c->h_test, &c->h_counts, &c->h_ranks, &c->q_fold, &c->q_hi, &c->q_lo, &c->e_hi, &c->e_lo,
                       &c->pos_q, &c->excl_lo, &c->excl_hi, &c->f_sp_comp, &c->f_po_comp, &c->f_sp_ent, &c->f_po_ent,
                       &c->f_tmp, &c->f_tmp2, &c->f_count};
     int64_t tot = 0;
@@ -125,6 +127,21 @@ extern "C" int kge_score(kge_ctx* ctx, int model, int k, const kge_table* ent, c
 // ------------------------------------------------------------------------------------------------
 // CUDA IPC: map a peer rank's shard into this process (one process per GPU, NVLink/NVSwitch P2P)
 // ------------------------------------------------------------------------------------------------
+// device memory that can be exported to peer processes (plain cudaMalloc: torch's caching allocator
+// sub-allocates, which cudaIpcGetMemHandle cannot address)
+extern "C" int kge_dev_alloc(int64_t bytes, void** out) {
+    KGE_REQUIRE(out != nullptr && bytes >= 0, "kge_dev_alloc: bad argument");
+    *out = nullptr;
+    if (bytes == 0) return 0;
+    KGE_CUDA_CHECK(cudaMalloc(out, (size_t)bytes));
+    return 0;
+}
+
+extern "C" int kge_dev_free(void* p) {
+    if (p) KGE_CUDA_CHECK(cudaFree(p));
+    return 0;
+}
+
 extern "C" int kge_ipc_export(void* dev_ptr, void* handle_out64) {
     KGE_REQUIRE(dev_ptr && handle_out64, "kge_ipc_export: null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");

@@ -59,8 +59,15 @@ struct kge_ctx {
     int device = 0;
     int sm_count = 148;
     // training workspace
-    KgeBuf keys_in, keys_out, vals_in, vals_out, sort_tmp;
+    KgeBuf sort_tmp;
     KgeBuf repl, keep, grad_rows, loss_part, neg_scores, partial, span_head;
+    KgeBuf ks_in, ks_sel, ks_sorted, sel_flags, sel_count;
+    // owner-side slot selection (kge_train_select): count travels to the host behind an event
+    int*          h_count = nullptr;
+    cudaEvent_t   ev_count = nullptr;
+    bool          sel_valid = false;
+    const int32_t* sel_keys = nullptr;
+    int64_t       sel_n = 0, sel_begin = 0, sel_end = 0;
     // staging for the host-buffer entry points
     KgeBuf h_pos, h_loss, h_test, h_counts, h_ranks;
     // ranking workspace
@@ -94,6 +101,12 @@ static inline TableView make_view(const kge_table& t) {
     v.n_shards = t.n_shards;
     v.K = t.K;
     return v;
+}
+
+static inline bool table_present(const kge_table& t) {
+    for (int i = 0; i < KGE_MAX_SHARDS; ++i)
+        if (t.shard[i]) return true;
+    return false;
 }
 
 __device__ __forceinline__ float* table_row(const TableView& t, int64_t row) {

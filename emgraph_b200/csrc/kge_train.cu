@@ -15,6 +15,7 @@
 // training/{adam,adagrad,momentum,sgd}.py (+ the Keras OptimizerV2 sparse apply with its duplicate
 // index summation).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 
 #include "kge_train_fwd.cuh"
 
@@ -30,7 +31,7 @@ __global__ void kge_emit_kernel(const int32_t* __restrict__ pos, int64_t n, int 
                                 const int32_t* __restrict__ repl_in, const uint8_t* __restrict__ keep_in,
                                 uint64_t seed, uint64_t step, uint64_t neg_base,
                                 int32_t* __restrict__ repl_out, uint8_t* __restrict__ keep_out,
-                                int32_t* __restrict__ keys, int32_t* __restrict__ slots, int32_t slot_base) {
+                                int32_t* __restrict__ keys, uint64_t* __restrict__ packed) {
     int64_t S = (int64_t)(3 + eta) * n;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < S; t += (int64_t)gridDim.x * blockDim.x) {
         int32_t key;
@@ -60,8 +61,8 @@ __global__ void kge_emit_kernel(const int32_t* __restrict__ pos, int64_t n, int 
         } else {
             key = (int32_t)E + pos[3 * (t - 2 * n - (int64_t)eta * n) + 1];
         }
-        keys[t] = key;
-        if (slots != nullptr) slots[t] = slot_base + (int32_t)t;
+        if (keys != nullptr) keys[t] = key;
+        if (packed != nullptr) packed[t] = ((uint64_t)(uint32_t)key << 32) | (uint64_t)(uint32_t)t;
     }
 }
 
@@ -92,8 +93,7 @@ struct GradView {
 };
 
 struct ApplyParams {
-    const int32_t* keys;   // sorted
-    const int32_t* slots;  // sorted alongside (global slot id = rank*S + local slot)
+    const uint64_t* ks;    // sorted (key << 32 | global slot id), global slot id = rank*S + local slot
     int64_t n_keys;
     GradView G;
     TableView ent, ent_m, ent_v;
@@ -101,6 +101,7 @@ struct ApplyParams {
     int64_t E, R;
     int64_t row_begin, row_end;  // owned entity rows
     int opt;
+    bool has_m, has_v;     // entity optimizer-state tables present
     uint32_t flags;
     float lr, lr_t, beta1, beta2, eps, momentum;
     float* partial;        // [2*n_chunks][K]
@@ -162,8 +163,8 @@ __device__ __forceinline__ RowPtrs resolve_row(const ApplyParams& P, int32_t key
         if (P.rel_v) r.v = P.rel_v + (size_t)r.row * K;
     } else {
         r.w = table_row(P.ent, r.row);
-        if (P.ent_m.shard[0]) r.m = table_row(P.ent_m, r.row);
-        if (P.ent_v.shard[0]) r.v = table_row(P.ent_v, r.row);
+        if (P.has_m) r.m = table_row(P.ent_m, r.row);
+        if (P.has_v) r.v = table_row(P.ent_v, r.row);
     }
     return r;
 }
@@ -263,12 +264,13 @@ __global__ void __launch_bounds__(256) kge_reduce_apply_kernel(ApplyParams P) {
 
     int32_t key = -2;
     if (lane < cnt) {
-        key = P.keys[b0 + lane];
-        meta[wib][lane] = decode_slot(P.G, P.slots[b0 + lane]);
+        const uint64_t kv = P.ks[b0 + lane];
+        key = (int32_t)(kv >> 32);
+        meta[wib][lane] = decode_slot(P.G, (int32_t)(kv & 0xffffffffu));
     }
     int32_t key_prev = -1, key_next = -1;
-    if (lane == 0 && b0 > 0) key_prev = P.keys[b0 - 1];
-    if (lane == 1 && b0 + cnt < P.n_keys) key_next = P.keys[b0 + cnt];
+    if (lane == 0 && b0 > 0) key_prev = (int32_t)(P.ks[b0 - 1] >> 32);
+    if (lane == 1 && b0 + cnt < P.n_keys) key_next = (int32_t)(P.ks[b0 + cnt] >> 32);
     key_prev = __shfl_sync(0xffffffffu, key_prev, 0);
     key_next = __shfl_sync(0xffffffffu, key_next, 1);
     const int32_t left = __shfl_up_sync(0xffffffffu, key, 1);
@@ -324,12 +326,12 @@ __global__ void __launch_bounds__(128) kge_span_apply_kernel(ApplyParams P) {
     const int lane = threadIdx.x & 31;
     const int K = P.ent.K;
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
-    const int32_t key = P.keys[w * KGE_CH + KGE_CH - 1];
+    const int32_t key = (int32_t)(P.ks[w * KGE_CH + KGE_CH - 1] >> 32);
     // last chunk whose first slot still carries `key` (32 chunks probed per round)
     int64_t last = w;
     for (;;) {
         const int64_t c = last + 1 + lane;
-        const bool same = c < n_chunks && P.keys[c * KGE_CH] == key;
+        const bool same = c < n_chunks && (int32_t)(P.ks[c * KGE_CH] >> 32) == key;
         const unsigned mk = __ballot_sync(0xffffffffu, same);
         if (mk == 0xffffffffu) {
             last += 32;
@@ -408,15 +410,14 @@ static int ensure_train_ws(kge_ctx* ctx, const kge_train_args* a) {
 
 extern "C" int64_t kge_train_grad_floats(int eta, int64_t n_pos, int K) { return gbuf_floats(eta, n_pos, K); }
 
-static int emit_impl(kge_ctx* ctx, const kge_train_args* a, int32_t* keys_out, int32_t* slots_out, int32_t slot_base,
-                     cudaStream_t st) {
+static int emit_impl(kge_ctx* ctx, const kge_train_args* a, int32_t* keys_out, uint64_t* packed_out, cudaStream_t st) {
     if (int rc = ensure_train_ws(ctx, a)) return rc;
     int64_t S = (int64_t)(3 + a->eta) * a->n_pos;
     int threads = 256;
     int blocks = (int)std::min<int64_t>((S + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
     kge_emit_kernel<<<blocks, threads, 0, st>>>(a->pos, a->n_pos, a->eta, a->ent.rows, a->side, a->repl, a->keep_subj,
                                                 a->seed, a->step, a->neg_index_base, ctx->repl.as<int32_t>(),
-                                                ctx->keep.as<uint8_t>(), keys_out, slots_out, slot_base);
+                                                ctx->keep.as<uint8_t>(), keys_out, packed_out);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -426,7 +427,8 @@ extern "C" int kge_train_emit(kge_ctx* ctx, const kge_train_args* a, int32_t* ke
     if (int rc = validate_train(a)) return rc;
     if (a->n_pos == 0) return 0;
     KGE_REQUIRE(keys_out != nullptr, "kge_train_emit: keys_out missing");
-    return emit_impl(ctx, a, keys_out, nullptr, 0, (cudaStream_t)stream);
+    ctx->sel_valid = false;
+    return emit_impl(ctx, a, keys_out, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, void* stream) {
@@ -467,9 +469,14 @@ extern "C" int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* g
     return 0;
 }
 
-__global__ void kge_iota_kernel(int32_t* v, int64_t n) {
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
-        v[t] = (int32_t)t;
+// owner-side selection of the slots a rank must reduce: keys of its row range + every relation key
+__global__ void kge_select_flag_kernel(const int32_t* __restrict__ keys, int64_t n, int64_t E, int64_t row_begin, int64_t row_end,
+                                       uint64_t* __restrict__ packed, uint8_t* __restrict__ flags) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t key = keys[t];
+        packed[t] = ((uint64_t)(uint32_t)key << 32) | (uint64_t)(uint32_t)t;
+        flags[t] = (key >= E || (key >= row_begin && key < row_end)) ? 1 : 0;
+    }
 }
 
 template <int V>
@@ -485,36 +492,28 @@ static int launch_apply(const ApplyParams& P, int tmode, cudaStream_t st) {
     return 0;
 }
 
-// slots_in: optional precomputed global slot ids matching keys_all (nullptr => iota)
-static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, const int32_t* slots_in, int64_t n_keys,
-                      const kge_table* grads, int64_t row_begin, int64_t row_end, cudaStream_t st) {
-    KGE_REQUIRE(n_keys < (int64_t)INT32_MAX, "kge_train_apply: too many slots");
+// packed_in: n_items (key << 32 | global slot) entries, unsorted; sorted by key (stable) into ctx->ks_sorted
+static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* packed_in, int64_t n_items, const kge_table* grads,
+                      int64_t row_begin, int64_t row_end, cudaStream_t st) {
+    KGE_REQUIRE(n_items < (int64_t)INT32_MAX, "kge_train_apply: too many slots");
+    if (n_items == 0) return 0;
     const int K = a->ent.K;
-    const int64_t n_chunks = (n_keys + KGE_CH - 1) / KGE_CH;
-    if (ctx->keys_out.reserve((size_t)n_keys * 4)) return -2;
-    if (ctx->vals_out.reserve((size_t)n_keys * 4)) return -2;
+    const int64_t n_chunks = (n_items + KGE_CH - 1) / KGE_CH;
+    if (ctx->ks_sorted.reserve((size_t)n_items * 8)) return -2;
     if (ctx->partial.reserve((size_t)2 * n_chunks * K * sizeof(float))) return -2;
     if (ctx->span_head.reserve((size_t)n_chunks)) return -2;
     int64_t E = a->ent.rows;
     int end_bit = 1;
     while (((int64_t)1 << end_bit) < E + a->R) ++end_bit;
-    if (slots_in == nullptr) {
-        if (ctx->vals_in.reserve((size_t)n_keys * 4)) return -2;
-        int threads = 256;
-        int blocks = (int)std::min<int64_t>((n_keys + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
-        kge_iota_kernel<<<blocks, threads, 0, st>>>(ctx->vals_in.as<int32_t>(), n_keys);
-        slots_in = ctx->vals_in.as<int32_t>();
-    }
     size_t tmp_bytes = 0;
-    KGE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_all, ctx->keys_out.as<int32_t>(), slots_in,
-                                                   ctx->vals_out.as<int32_t>(), (int)n_keys, 0, end_bit, st));
+    KGE_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, packed_in, ctx->ks_sorted.as<uint64_t>(), (int)n_items, 32,
+                                                  32 + end_bit, st));
     if (ctx->sort_tmp.reserve(tmp_bytes)) return -2;
-    KGE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, keys_all, ctx->keys_out.as<int32_t>(), slots_in,
-                                                   ctx->vals_out.as<int32_t>(), (int)n_keys, 0, end_bit, st));
+    KGE_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, tmp_bytes, packed_in, ctx->ks_sorted.as<uint64_t>(), (int)n_items,
+                                                  32, 32 + end_bit, st));
     ApplyParams P;
-    P.keys = ctx->keys_out.as<int32_t>();
-    P.slots = ctx->vals_out.as<int32_t>();
-    P.n_keys = n_keys;
+    P.ks = ctx->ks_sorted.as<uint64_t>();
+    P.n_keys = n_items;
     for (int i = 0; i < KGE_MAX_SHARDS; ++i) P.G.base[i] = grads->shard[i];
     P.G.n_ranks = grads->n_shards;
     P.G.S = grads->rows_per_shard;
@@ -524,6 +523,8 @@ static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys
     P.ent = make_view(a->ent);
     P.ent_m = make_view(a->ent_m);
     P.ent_v = make_view(a->ent_v);
+    P.has_m = table_present(a->ent_m);
+    P.has_v = table_present(a->ent_v);
     P.rel = a->rel;
     P.rel_m = a->rel_m;
     P.rel_v = a->rel_v;
@@ -548,13 +549,52 @@ static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys
     P.lr_t = (float)((double)a->lr * sqrt(1.0 - pow((double)a->beta2, t)) / (1.0 - pow((double)a->beta1, t)));
     if (!no_update && !reset) {
         if (a->opt == KGE_OPT_ADAM)
-            KGE_REQUIRE(a->ent_m.shard[0] && a->ent_v.shard[0] && a->rel_m && a->rel_v, "kge_train: adam state (m,v) missing");
+            KGE_REQUIRE(P.has_m && P.has_v && a->rel_m && a->rel_v, "kge_train: adam state (m,v) missing");
         if (a->opt == KGE_OPT_ADAGRAD || a->opt == KGE_OPT_MOMENTUM)
-            KGE_REQUIRE(a->ent_m.shard[0] && a->rel_m, "kge_train: optimizer state missing");
+            KGE_REQUIRE(P.has_m && a->rel_m, "kge_train: optimizer state missing");
     }
     const int tmode = a->model == KGE_TRANSE_L1 ? 1 : (a->model == KGE_TRANSE_L2 ? 2 : 0);
     if (K % 4 == 0) return launch_apply<4>(P, tmode, st);
     return launch_apply<1>(P, tmode, st);
+}
+
+// Selection of the slots this rank reduces (keys in [row_begin,row_end) or relation keys), started
+// early so that the count reaches the host while kge_train_fwd_bwd is still running.
+extern "C" int kge_train_select(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, int64_t n_keys, int64_t row_begin,
+                                int64_t row_end, void* stream) {
+    KGE_REQUIRE(ctx != nullptr, "kge_train_select: null ctx");
+    if (int rc = validate_train(a)) return rc;
+    KGE_REQUIRE(keys_all != nullptr || n_keys == 0, "kge_train_select: keys missing");
+    KGE_REQUIRE(n_keys < (int64_t)INT32_MAX, "kge_train_select: too many slots");
+    cudaStream_t st = (cudaStream_t)stream;
+    ctx->sel_valid = false;
+    if (n_keys == 0) return 0;
+    if (ctx->ks_in.reserve((size_t)n_keys * 8) || ctx->ks_sel.reserve((size_t)n_keys * 8) || ctx->sel_flags.reserve((size_t)n_keys) ||
+        ctx->sel_count.reserve(sizeof(int)))
+        return -2;
+    if (ctx->h_count == nullptr) {
+        KGE_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_count, sizeof(int)));
+        KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_count, cudaEventDisableTiming));
+    }
+    int threads = 256;
+    int blocks = (int)std::min<int64_t>((n_keys + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
+    kge_select_flag_kernel<<<blocks, threads, 0, st>>>(keys_all, n_keys, a->ent.rows, row_begin, row_end, ctx->ks_in.as<uint64_t>(),
+                                                       ctx->sel_flags.as<uint8_t>());
+    KGE_CUDA_CHECK(cudaGetLastError());
+    size_t tb = 0;
+    KGE_CUDA_CHECK(cub::DeviceSelect::Flagged(nullptr, tb, ctx->ks_in.as<uint64_t>(), ctx->sel_flags.as<uint8_t>(),
+                                              ctx->ks_sel.as<uint64_t>(), ctx->sel_count.as<int>(), (int)n_keys, st));
+    if (ctx->sort_tmp.reserve(tb)) return -2;
+    KGE_CUDA_CHECK(cub::DeviceSelect::Flagged(ctx->sort_tmp.p, tb, ctx->ks_in.as<uint64_t>(), ctx->sel_flags.as<uint8_t>(),
+                                              ctx->ks_sel.as<uint64_t>(), ctx->sel_count.as<int>(), (int)n_keys, st));
+    KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->h_count, ctx->sel_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_count, st));
+    ctx->sel_valid = true;
+    ctx->sel_keys = keys_all;
+    ctx->sel_n = n_keys;
+    ctx->sel_begin = row_begin;
+    ctx->sel_end = row_end;
+    return 0;
 }
 
 extern "C" int kge_train_apply(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, int64_t n_keys,
@@ -566,7 +606,13 @@ extern "C" int kge_train_apply(kge_ctx* ctx, const kge_train_args* a, const int3
     KGE_REQUIRE(grads->n_shards >= 1 && grads->rows_per_shard > 0 && grads->rows_per_shard % (3 + a->eta) == 0,
                 "kge_train_apply: grads.rows_per_shard must be the slots per rank, (3+eta)*n_pos");
     KGE_REQUIRE(n_keys == grads->rows_per_shard * grads->n_shards, "kge_train_apply: n_keys != n_shards * slots per rank");
-    return apply_impl(ctx, a, keys_all, nullptr, n_keys, grads, row_begin, row_end, (cudaStream_t)stream);
+    if (!(ctx->sel_valid && ctx->sel_keys == keys_all && ctx->sel_n == n_keys && ctx->sel_begin == row_begin && ctx->sel_end == row_end)) {
+        if (int rc = kge_train_select(ctx, a, keys_all, n_keys, row_begin, row_end, stream)) return rc;
+    }
+    KGE_CUDA_CHECK(cudaEventSynchronize(ctx->ev_count));
+    ctx->sel_valid = false;
+    const int64_t m = *ctx->h_count;
+    return apply_impl(ctx, a, ctx->ks_sel.as<uint64_t>(), m, grads, row_begin, row_end, (cudaStream_t)stream);
 }
 
 extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* stream) {
@@ -577,9 +623,9 @@ extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* strea
     cudaStream_t st = (cudaStream_t)stream;
     const int K = a->ent.K;
     int64_t S = (int64_t)(3 + a->eta) * a->n_pos;
-    if (ctx->keys_in.reserve((size_t)S * 4) || ctx->vals_in.reserve((size_t)S * 4)) return -2;
+    if (ctx->ks_in.reserve((size_t)S * 8)) return -2;
     if (ctx->grad_rows.reserve((size_t)gbuf_floats(a->eta, a->n_pos, K) * sizeof(float))) return -2;
-    if (int rc = emit_impl(ctx, a, ctx->keys_in.as<int32_t>(), ctx->vals_in.as<int32_t>(), 0, st)) return rc;
+    if (int rc = emit_impl(ctx, a, nullptr, ctx->ks_in.as<uint64_t>(), st)) return rc;
     if (int rc = kge_train_fwd_bwd(ctx, a, ctx->grad_rows.as<float>(), stream)) return rc;
     kge_table g;
     memset(&g, 0, sizeof(g));
@@ -588,7 +634,7 @@ extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* strea
     g.rows_per_shard = S;
     g.n_shards = 1;
     g.K = K;
-    return apply_impl(ctx, a, ctx->keys_in.as<int32_t>(), ctx->vals_in.as<int32_t>(), S, &g, 0, a->ent.rows, st);
+    return apply_impl(ctx, a, ctx->ks_in.as<uint64_t>(), S, &g, 0, a->ent.rows, st);
 }
 
 extern "C" int kge_train_step_host(kge_ctx* ctx, const kge_train_args* a, const int32_t* pos_host, float* loss_host,

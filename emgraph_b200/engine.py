@@ -188,6 +188,11 @@ class Engine:
         check(self.lib.kge_train_emit(self._h, C.byref(a), _ptr(keys_out), _stream()))
         self.launches += 1
 
+    def train_select(self, a: KgeTrainArgs, keys_all, row_begin: int, row_end: int):
+        _chk_i32(keys_all, "keys_all")
+        check(self.lib.kge_train_select(self._h, C.byref(a), _ptr(keys_all), keys_all.numel(), row_begin, row_end, _stream()))
+        self.launches += 4
+
     def train_fwd_bwd(self, a: KgeTrainArgs, grad_rows):
         check(self.lib.kge_train_fwd_bwd(self._h, C.byref(a), _ptr(grad_rows), _stream()))
         self.launches += 2
@@ -203,7 +208,7 @@ class Engine:
         _chk_i32(keys_all, "keys_all")
         check(self.lib.kge_train_apply(self._h, C.byref(a), _ptr(keys_all), keys_all.numel(), C.byref(grads),
                                        row_begin, row_end, _stream()))
-        self.launches += self.launches_per_step(a.ent.rows + a.R) - 3 + 1  # + iota
+        self.launches += self.launches_per_step(a.ent.rows + a.R) - 3
 
     def normalize_rows(self, emb):
         _chk_f32(emb, "emb")
@@ -273,6 +278,11 @@ class Engine:
     def ipc_export(self, t) -> bytes:
         buf = (C.c_char * 64)()
         check(self.lib.kge_ipc_export(_ptr(t), C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def ipc_export_ptr(self, ptr: int) -> bytes:
+        buf = (C.c_char * 64)()
+        check(self.lib.kge_ipc_export(C.c_void_p(ptr), C.cast(buf, C.c_void_p)))
         return bytes(buf)
 
     def ipc_open(self, handle: bytes) -> int:

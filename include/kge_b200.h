@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 2
+#define KGE_ABI_VERSION 3
 #define KGE_MAX_SHARDS 8
 
 typedef struct kge_ctx kge_ctx;
@@ -123,6 +123,11 @@ int kge_train_emit(kge_ctx* ctx, const kge_train_args* a, int32_t* keys_out, voi
 int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, void* stream);
 int kge_train_apply(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, int64_t n_keys,
                     const kge_table* grads, int64_t row_begin, int64_t row_end, void* stream);
+/* Optional, between the key all-gather and kge_train_fwd_bwd: start selecting the slots this rank
+ * will reduce (keys in [row_begin,row_end) + relation keys) so that their count reaches the host while
+ * the forward/backward kernel runs; kge_train_apply with the same arguments then does not stall. */
+int kge_train_select(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, int64_t n_keys,
+                     int64_t row_begin, int64_t row_end, void* stream);
 
 /* Host-buffer form of kge_train_step: what a reference-side caller binds.  The reference feeds every
  * batch from host numpy through tf.data (models/EmbeddingModel.py:1329-1337, :1044-1111) and reads
@@ -165,7 +170,10 @@ int kge_rank_host(kge_ctx* ctx, int model, int k, const kge_table* ent, const fl
                   const int32_t* test_host, int64_t T, int side, int strategy, int filtered,
                   int use_tensor_cores, int32_t* ranks_host, void* stream);
 
-/* CUDA IPC helpers for mapping peer shards (one process per GPU). handle: 64 bytes. */
+/* Device memory that peers can map (plain cudaMalloc) + CUDA IPC helpers for mapping peer shards
+ * (one process per GPU). handle: 64 bytes. */
+int kge_dev_alloc(int64_t bytes, void** out);
+int kge_dev_free(void* p);
 int kge_ipc_export(void* dev_ptr, void* handle_out64);
 int kge_ipc_open(const void* handle64, void** dev_ptr_out);
 int kge_ipc_close(void* dev_ptr);

@@ -1,0 +1,81 @@
+"""Host-side logic of the row-sharded multi-GPU path, exercised with world_size 2 on the gloo backend
+(no GPU): shard ranges, batch dealing, Philox stream bases, and that the owner selection applied to an
+all-gathered key list covers every entity slot exactly once (relation slots on every rank)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from emgraph_b200 import distributed as D
+
+
+def test_shard_ranges_cover_rows_exactly():
+    for E in (1, 7, 8, 14541, 4594485):
+        for world in (1, 2, 3, 4, 8):
+            seen = np.zeros(E, np.int32)
+            for r in range(world):
+                b, e = D.shard_range(E, world, r)
+                assert 0 <= b <= e <= E and e - b <= D.rows_per_shard(E, world)
+                seen[b:e] += 1
+                if e > b:
+                    assert np.all(D.owner_of(np.arange(b, e), E, world) == r)
+            assert np.all(seen == 1)
+
+
+def test_batches_are_disjoint_across_ranks_within_a_step():
+    n_total, n_per = 10000, 128
+    for world in (2, 4, 8):
+        for step in (0, 1, 5, 77):
+            sl = [D.batch_slice(n_total, world, r, step, n_per) for r in range(world)]
+            assert all(hi - lo == n_per and hi <= n_total for lo, hi in sl)
+            assert len({lo for lo, _ in sl}) == world
+    # negative index bases never overlap
+    assert [D.neg_index_base(r, 20, 128) for r in range(3)] == [0, 2560, 5120]
+
+
+def _worker(rank, world, port, E, R, eta, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(10 + rank)
+        pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+        repl = rng.integers(0, E, eta * n).astype(np.int32)
+        # slot keys in the library's layout: subjects | objects | replacements | E + relation
+        keys_local = torch.from_numpy(np.concatenate([pos[:, 0], pos[:, 2], repl, E + pos[:, 1]]).astype(np.int32))
+        S = (3 + eta) * n
+        assert keys_local.numel() == S
+        keys_all = torch.empty(S * world, dtype=torch.int32)
+        dist.all_gather_into_tensor(keys_all, keys_local)
+        ka = keys_all.numpy()
+        np.testing.assert_array_equal(ka[rank * S:(rank + 1) * S], keys_local.numpy())
+        mine = D.owned_mask(ka, E, world, rank)
+        cover = torch.from_numpy(mine.astype(np.int32))
+        dist.all_reduce(cover)
+        ent_slot = ka < E
+        ok = bool(np.all(cover.numpy()[ent_slot] == 1) and np.all(cover.numpy()[~ent_slot] == world))
+        # the counters of a sharded ranking sweep add up: per-shard candidate counts -> all-reduce
+        b, e = D.shard_range(E, world, rank)
+        cnt = torch.tensor([e - b], dtype=torch.int32)
+        dist.all_reduce(cnt)
+        q.put((rank, ok and int(cnt.item()) == E))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gloo_world2_key_gather_and_owner_selection():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 1001, 7, 5, 64, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
