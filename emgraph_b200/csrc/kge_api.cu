@@ -48,6 +48,9 @@ extern "C" int kge_ctx_destroy(kge_ctx* c) {
     for (KgeBuf* b : bufs) b->release();
     if (c->h_count) cudaFreeHost(c->h_count);
     if (c->ev_count) cudaEventDestroy(c->ev_count);
+    for (cudaEvent_t e : {c->ev_fork, c->ev_sorted, c->ev_fwd, c->ev_loss})
+        if (e) cudaEventDestroy(e);
+    if (c->side) cudaStreamDestroy(c->side);
     delete c;
     return 0;
 }

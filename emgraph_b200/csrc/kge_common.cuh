@@ -63,6 +63,9 @@ struct kge_ctx {
     KgeBuf repl, keep, grad_rows, loss_part, neg_scores, partial, span_head;
     KgeBuf ks_in, ks_sel, ks_sorted, sel_flags, sel_count;
     // owner-side slot selection (kge_train_select): count travels to the host behind an event
+    // side stream of the single-GPU step (sort + loss reduction beside the forward/backward kernel)
+    cudaStream_t  side = nullptr;
+    cudaEvent_t   ev_fork = nullptr, ev_sorted = nullptr, ev_fwd = nullptr, ev_loss = nullptr;
     int*          h_count = nullptr;
     cudaEvent_t   ev_count = nullptr;
     bool          sel_valid = false;

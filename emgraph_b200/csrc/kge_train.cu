@@ -105,7 +105,9 @@ struct ApplyParams {
     uint32_t flags;
     float lr, lr_t, beta1, beta2, eps, momentum;
     float* partial;        // [2*n_chunks][K]
-    uint8_t* span_head;    // [n_chunks]
+    int32_t* span_list;    // chunk ids that start a run crossing chunk borders (unordered)
+    int32_t* hub_list;     // the subset whose run covers more than KGE_SPAN_WARP_MAX chunks
+    int32_t* span_count;   // [2]: {#span heads, #hubs}, zeroed before the reduce kernel
     float* dbg_grad_ent;
     float* dbg_grad_rel;
 };
@@ -169,79 +171,27 @@ __device__ __forceinline__ RowPtrs resolve_row(const ApplyParams& P, int32_t key
     return r;
 }
 
-// optimizer update of V consecutive columns of one row given the summed gradient g
+// global (non-generic) vector load: the row pointers come out of shared memory, so the compiler cannot
+// prove their address space on its own
 template <int V>
-__device__ __forceinline__ void opt_update(const ApplyParams& P, const RowPtrs& r, int c0, const float (&g)[V], const float (&w_in)[V]) {
-    if (r.is_rel ? (P.dbg_grad_rel != nullptr) : (P.dbg_grad_ent != nullptr)) {
-        float* d = (r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent) + (size_t)r.row * P.ent.K + c0;
-        st_vec<V>(d, g);
-    }
-    if (P.flags & KGE_F_NO_UPDATE) return;
-    const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
-    float wv[V], mv[V], vv[V];
-#pragma unroll
-    for (int x = 0; x < V; ++x) wv[x] = w_in[x];
-    if (P.opt == KGE_OPT_ADAM) {
-        // Keras Adam (beta1 .9, beta2 .999, eps 1e-7): var -= lr_t * m / (sqrt(v) + eps)
-        if (reset) {
-#pragma unroll
-            for (int x = 0; x < V; ++x) mv[x] = vv[x] = 0.f;
-        } else {
-            ld_vec<V>(mv, r.m + c0);
-            ld_vec<V>(vv, r.v + c0);
-        }
-#pragma unroll
-        for (int x = 0; x < V; ++x) {
-            mv[x] = P.beta1 * mv[x] + (1.f - P.beta1) * g[x];
-            vv[x] = P.beta2 * vv[x] + (1.f - P.beta2) * g[x] * g[x];
-            wv[x] = wv[x] - P.lr_t * mv[x] / (sqrtf(vv[x]) + P.eps);
-        }
-        if (r.m) st_vec<V>(r.m + c0, mv);
-        if (r.v) st_vec<V>(r.v + c0, vv);
-    } else if (P.opt == KGE_OPT_ADAGRAD) {
-        // Keras Adagrad: accumulator starts at 0.1; var -= lr * g / (sqrt(acc) + eps)
-        if (reset) {
-#pragma unroll
-            for (int x = 0; x < V; ++x) mv[x] = 0.1f;
-        } else {
-            ld_vec<V>(mv, r.m + c0);
-        }
-#pragma unroll
-        for (int x = 0; x < V; ++x) {
-            mv[x] = mv[x] + g[x] * g[x];
-            wv[x] = wv[x] - P.lr * g[x] / (sqrtf(mv[x]) + P.eps);
-        }
-        if (r.m) st_vec<V>(r.m + c0, mv);
-    } else if (P.opt == KGE_OPT_MOMENTUM) {
-        // Keras SGD momentum: vel = mu*vel - lr*g ; var += vel
-        if (reset) {
-#pragma unroll
-            for (int x = 0; x < V; ++x) mv[x] = 0.f;
-        } else {
-            ld_vec<V>(mv, r.m + c0);
-        }
-#pragma unroll
-        for (int x = 0; x < V; ++x) {
-            mv[x] = P.momentum * mv[x] - P.lr * g[x];
-            wv[x] = wv[x] + mv[x];
-        }
-        if (r.m) st_vec<V>(r.m + c0, mv);
+__device__ __forceinline__ void ldg_vec(float (&d)[V], const float* p) {
+    if constexpr (V == 4) {
+        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "l"(p));
     } else {
-#pragma unroll
-        for (int x = 0; x < V; ++x) wv[x] = wv[x] - P.lr * g[x];
+        asm volatile("ld.global.f32 %0, [%1];" : "=f"(d[0]) : "l"(p));
     }
-    st_vec<V>(r.w + c0, wv);
 }
 
-// contribution of one slot to V columns of the gradient; rc = current value of the row being updated
+// contribution of one slot to V columns of the gradient; rc = current value of the row being updated.
+// Plain gradient rows (mode 0) carry c = 1, so the trilinear models need no branch at all.
 template <int V, int TMODE>
 __device__ __forceinline__ void add_slot(float (&g)[V], const float (&a)[V], float c, int mode, const float (&rc)[V]) {
 #pragma unroll
     for (int x = 0; x < V; ++x) {
-        if (mode == 0) {
+        if (TMODE == 0) {
+            g[x] = fmaf(c, a[x], g[x]);  // DistMult / ComplEx / HolE: c*Q, or 1*row
+        } else if (mode == 0) {
             g[x] += a[x];
-        } else if (TMODE == 0) {
-            g[x] = fmaf(c, a[x], g[x]);  // DistMult / ComplEx / HolE: c*Q
         } else if (TMODE == 1) {
             float d = a[x] - rc[x];  // TransE L1: c*sign(Q-r)
             g[x] += d > 0.f ? c : (d < 0.f ? -c : 0.f);
@@ -251,12 +201,47 @@ __device__ __forceinline__ void add_slot(float (&g)[V], const float (&a)[V], flo
     }
 }
 
-// Level 1: one warp per chunk of KGE_CH sorted slots.
-template <int V, int TMODE>
-__global__ void __launch_bounds__(256) kge_reduce_apply_kernel(ApplyParams P) {
-    __shared__ SlotMeta meta[8][KGE_CH];
+// pure-register optimizer math on V columns; m/v are the row's state (ignored when not needed)
+template <int V>
+__device__ __forceinline__ void opt_math(const ApplyParams& P, bool reset, const float (&g)[V], float (&wv)[V], float (&mv)[V], float (&vv)[V]) {
+    if (P.opt == KGE_OPT_ADAM) {
+        // Keras Adam (beta1 .9, beta2 .999, eps 1e-7): var -= lr_t * m / (sqrt(v) + eps)
+#pragma unroll
+        for (int x = 0; x < V; ++x) {
+            const float m0 = reset ? 0.f : mv[x], v0 = reset ? 0.f : vv[x];
+            mv[x] = P.beta1 * m0 + (1.f - P.beta1) * g[x];
+            vv[x] = P.beta2 * v0 + (1.f - P.beta2) * g[x] * g[x];
+            wv[x] = wv[x] - __fdividef(P.lr_t * mv[x], sqrtf(vv[x]) + P.eps);
+        }
+    } else if (P.opt == KGE_OPT_ADAGRAD) {
+        // Keras Adagrad: accumulator starts at 0.1; var -= lr * g / (sqrt(acc) + eps)
+#pragma unroll
+        for (int x = 0; x < V; ++x) {
+            mv[x] = (reset ? 0.1f : mv[x]) + g[x] * g[x];
+            wv[x] = wv[x] - __fdividef(P.lr * g[x], sqrtf(mv[x]) + P.eps);
+        }
+    } else if (P.opt == KGE_OPT_MOMENTUM) {
+        // Keras SGD momentum: vel = mu*vel - lr*g ; var += vel
+#pragma unroll
+        for (int x = 0; x < V; ++x) {
+            mv[x] = P.momentum * (reset ? 0.f : mv[x]) - P.lr * g[x];
+            wv[x] = wv[x] + mv[x];
+        }
+    } else {
+#pragma unroll
+        for (int x = 0; x < V; ++x) wv[x] = wv[x] - P.lr * g[x];
+    }
+}
+
+// Level 1: one warp per chunk of KGE_CH sorted slots.  NCA > 0: lanes own ALL their column vectors of
+// the row at once (K <= 128*NCA) so that the row's w/m/v and two slots' rows are in flight together;
+// NCA == 0: generic column loop (any K, scalar columns).
+#define KGE_RA_WARPS 4
+template <int V, int TMODE, int NCA>
+__global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(ApplyParams P) {
+    __shared__ SlotMeta meta[KGE_RA_WARPS][KGE_CH];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t w = (int64_t)blockIdx.x * 8 + wib;
+    const int64_t w = (int64_t)blockIdx.x * KGE_RA_WARPS + wib;
     const int64_t b0 = w * KGE_CH;
     if (b0 >= P.n_keys) return;
     const int cnt = (int)min((int64_t)KGE_CH, P.n_keys - b0);
@@ -278,7 +263,11 @@ __global__ void __launch_bounds__(256) kge_reduce_apply_kernel(ApplyParams P) {
     unsigned heads = __ballot_sync(0xffffffffu, head);
     __syncwarp();
 
-    bool span_head = false;
+    const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
+    const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
+    const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
+    const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
+
     while (heads) {
         const int a = __ffs(heads) - 1;
         heads &= heads - 1;
@@ -288,46 +277,107 @@ __global__ void __launch_bounds__(256) kge_reduce_apply_kernel(ApplyParams P) {
         const bool open_end = (b == cnt) && (skey == key_next);
         const RowPtrs r = resolve_row(P, skey);
         if (!r.owned) continue;
-        if (!open_start && open_end) span_head = true;
+        if (!open_start && open_end && lane == 0) P.span_list[atomicAdd(P.span_count, 1)] = (int32_t)w;
         const bool complete = !open_start && !open_end;
         float* part = P.partial + ((size_t)(2 * w + (open_start ? 0 : 1))) * K;
-        for (int c0 = lane * V; c0 < K; c0 += 32 * V) {
-            float g[V], rc[V];
+        float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
+        if constexpr (NCA > 0) {
+            // lanes past the end of the row read a clamped (valid, duplicate) vector and never store:
+            // no divergence inside the load/accumulate loops
+            float g[NCA][V], rc[NCA][V], mv[NCA][V], vv[NCA][V];
+            int cc[NCA];
 #pragma unroll
-            for (int x = 0; x < V; ++x) g[x] = rc[x] = 0.f;
-            // the row's current value: needed by the optimizer and by the TransE slot gradients
-            if (complete || TMODE != 0) ld_vec<V>(rc, r.w + c0);
+            for (int i = 0; i < NCA; ++i) {
+                cc[i] = min((lane + 32 * i) * V, K - V);
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[i][x] = rc[i][x] = mv[i][x] = vv[i][x] = 0.f;
+            }
+            if (complete || TMODE != 0) {
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) ldg_vec<V>(rc[i], r.w + cc[i]);
+            }
+            if (complete && need_m) {
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) ldg_vec<V>(mv[i], r.m + cc[i]);
+            }
+            if (complete && need_v) {
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) ldg_vec<V>(vv[i], r.v + cc[i]);
+            }
             int u = a;
-            for (; u + 4 <= b; u += 4) {
-                float v4[4][V];
+            for (; u + 2 <= b; u += 2) {
+                float v2[2][NCA][V];
+                const SlotMeta m0 = meta[wib][u], m1 = meta[wib][u + 1];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) ld_vec<V>(v4[q], meta[wib][u + q].row + c0);
+                for (int i = 0; i < NCA; ++i) ldg_vec<V>(v2[0][i], m0.row + cc[i]);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) add_slot<V, TMODE>(g, v4[q], meta[wib][u + q].c, meta[wib][u + q].mode, rc);
+                for (int i = 0; i < NCA; ++i) ldg_vec<V>(v2[1][i], m1.row + cc[i]);
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) add_slot<V, TMODE>(g[i], v2[0][i], m0.c, m0.mode, rc[i]);
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) add_slot<V, TMODE>(g[i], v2[1][i], m1.c, m1.mode, rc[i]);
             }
-            for (; u < b; ++u) {
-                float v1[V];
-                ld_vec<V>(v1, meta[wib][u].row + c0);
-                add_slot<V, TMODE>(g, v1, meta[wib][u].c, meta[wib][u].mode, rc);
+            if (u < b) {
+                float v1[NCA][V];
+                const SlotMeta m0 = meta[wib][u];
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) ldg_vec<V>(v1[i], m0.row + cc[i]);
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) add_slot<V, TMODE>(g[i], v1[i], m0.c, m0.mode, rc[i]);
             }
-            if (complete) opt_update<V>(P, r, c0, g, rc);
-            else st_vec<V>(part + c0, g);
+#pragma unroll
+            for (int i = 0; i < NCA; ++i) {
+                const int c0 = (lane + 32 * i) * V;
+                if (c0 >= K) continue;
+                if (!complete) {
+                    st_vec<V>(part + c0, g[i]);
+                    continue;
+                }
+                if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g[i]);
+                if (no_update) continue;
+                opt_math<V>(P, reset, g[i], rc[i], mv[i], vv[i]);
+                if (r.m && P.opt != KGE_OPT_SGD) st_vec<V>(r.m + c0, mv[i]);
+                if (r.v && P.opt == KGE_OPT_ADAM) st_vec<V>(r.v + c0, vv[i]);
+                st_vec<V>(r.w + c0, rc[i]);
+            }
+        } else {
+            for (int c0 = lane * V; c0 < K; c0 += 32 * V) {
+                float g[V], rc[V], mv[V], vv[V];
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[x] = rc[x] = mv[x] = vv[x] = 0.f;
+                if (complete || TMODE != 0) ld_vec<V>(rc, r.w + c0);
+                if (complete && need_m) ld_vec<V>(mv, r.m + c0);
+                if (complete && need_v) ld_vec<V>(vv, r.v + c0);
+                int u = a;
+                for (; u + 4 <= b; u += 4) {
+                    float v4[4][V];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ld_vec<V>(v4[q], meta[wib][u + q].row + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) add_slot<V, TMODE>(g, v4[q], meta[wib][u + q].c, meta[wib][u + q].mode, rc);
+                }
+                for (; u < b; ++u) {
+                    float v1[V];
+                    ld_vec<V>(v1, meta[wib][u].row + c0);
+                    add_slot<V, TMODE>(g, v1, meta[wib][u].c, meta[wib][u].mode, rc);
+                }
+                if (!complete) {
+                    st_vec<V>(part + c0, g);
+                    continue;
+                }
+                if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g);
+                if (no_update) continue;
+                opt_math<V>(P, reset, g, rc, mv, vv);
+                if (r.m && P.opt != KGE_OPT_SGD) st_vec<V>(r.m + c0, mv);
+                if (r.v && P.opt == KGE_OPT_ADAM) st_vec<V>(r.v + c0, vv);
+                st_vec<V>(r.w + c0, rc);
+            }
         }
     }
-    if (lane == 0) P.span_head[w] = span_head ? 1 : 0;
 }
 
-// Level 2: one CTA per chunk that starts a run crossing chunk borders; threads own columns and add
-// the per-chunk partial rows in chunk order.
-template <int V>
-__global__ void __launch_bounds__(128) kge_span_apply_kernel(ApplyParams P) {
-    const int64_t w = blockIdx.x;
-    if (!P.span_head[w]) return;
-    const int lane = threadIdx.x & 31;
-    const int K = P.ent.K;
-    const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
-    const int32_t key = (int32_t)(P.ks[w * KGE_CH + KGE_CH - 1] >> 32);
-    // last chunk whose first slot still carries `key` (32 chunks probed per round)
+// last chunk whose first slot still carries `key` (32 chunks probed per round)
+__device__ __forceinline__ int64_t span_last_chunk(const ApplyParams& P, int64_t w, int32_t key, int64_t n_chunks, int lane) {
     int64_t last = w;
     for (;;) {
         const int64_t c = last + 1 + lane;
@@ -340,29 +390,186 @@ __global__ void __launch_bounds__(128) kge_span_apply_kernel(ApplyParams P) {
         last += __ffs(~mk) - 1;
         break;
     }
-    const RowPtrs r = resolve_row(P, key);
-    for (int c0 = threadIdx.x * V; c0 < K; c0 += 128 * V) {
-        float g[V];
-        ld_vec<V>(g, P.partial + (size_t)(2 * w + 1) * K + c0);
-        int64_t c = w + 1;
-        for (; c + 8 <= last + 1; c += 8) {
-            float v8[8][V];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) ld_vec<V>(v8[q], P.partial + (size_t)(2 * (c + q)) * K + c0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-#pragma unroll
-                for (int x = 0; x < V; ++x) g[x] += v8[q][x];
+    return last;
+}
+
+__device__ __forceinline__ const float* span_entry(const ApplyParams& P, int64_t w, int64_t e, int K) {
+    // entry 0 is the head's own partial (2w+1); entry e >= 1 is chunk w+e's start-open partial (2(w+e))
+    return P.partial + (size_t)(e == 0 ? 2 * w + 1 : 2 * (w + e)) * K;
+}
+
+// Level 2a: one WARP per run that crosses chunk borders (most are 2-3 partials long); runs longer than
+// KGE_SPAN_WARP_MAX chunks (hub entities) are handed to the CTA-wide kernel below.
+#define KGE_SPAN_WARP_MAX 24
+template <int V, int NCA>
+__global__ void __launch_bounds__(128) kge_span_warp_kernel(ApplyParams P) {
+    const int lane = threadIdx.x & 31;
+    const int K = P.ent.K;
+    const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
+    const int n_heads = P.span_count[0];
+    const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
+    const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
+    const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
+    const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
+    const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int h = gw; h < n_heads; h += nw) {
+        const int64_t w = P.span_list[h];
+        const int32_t key = (int32_t)(P.ks[w * KGE_CH + KGE_CH - 1] >> 32);
+        const int64_t last = span_last_chunk(P, w, key, n_chunks, lane);
+        const int n_ent = (int)(last - w + 1);
+        if (n_ent > KGE_SPAN_WARP_MAX) {
+            if (lane == 0) P.hub_list[atomicAdd(P.span_count + 1, 1)] = (int32_t)w;
+            continue;
         }
-        for (; c <= last; ++c) {
-            float v1[V];
-            ld_vec<V>(v1, P.partial + (size_t)(2 * c) * K + c0);
+        const RowPtrs r = resolve_row(P, key);
+        float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
+        if constexpr (NCA > 0) {
+            float g[NCA][V], rc[NCA][V], mv[NCA][V], vv[NCA][V];
+            int cc[NCA];
 #pragma unroll
-            for (int x = 0; x < V; ++x) g[x] += v1[x];
+            for (int i = 0; i < NCA; ++i) {
+                cc[i] = min((lane + 32 * i) * V, K - V);
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[i][x] = mv[i][x] = vv[i][x] = 0.f;
+                ldg_vec<V>(rc[i], r.w + cc[i]);
+            }
+            if (need_m) {
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) ldg_vec<V>(mv[i], r.m + cc[i]);
+            }
+            if (need_v) {
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) ldg_vec<V>(vv[i], r.v + cc[i]);
+            }
+            int e = 0;
+            for (; e + 2 <= n_ent; e += 2) {
+                float t[2][NCA][V];
+                const float* p0 = span_entry(P, w, e, K);
+                const float* p1 = span_entry(P, w, e + 1, K);
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) ldg_vec<V>(t[0][i], p0 + cc[i]);
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) ldg_vec<V>(t[1][i], p1 + cc[i]);
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int i = 0; i < NCA; ++i)
+#pragma unroll
+                        for (int x = 0; x < V; ++x) g[i][x] += t[q][i][x];
+            }
+            if (e < n_ent) {
+                const float* p0 = span_entry(P, w, e, K);
+#pragma unroll
+                for (int i = 0; i < NCA; ++i) {
+                    float t[V];
+                    ldg_vec<V>(t, p0 + cc[i]);
+#pragma unroll
+                    for (int x = 0; x < V; ++x) g[i][x] += t[x];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NCA; ++i) {
+                const int c0 = (lane + 32 * i) * V;
+                if (c0 >= K) continue;
+                if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g[i]);
+                if (no_update) continue;
+                opt_math<V>(P, reset, g[i], rc[i], mv[i], vv[i]);
+                if (r.m && P.opt != KGE_OPT_SGD) st_vec<V>(r.m + c0, mv[i]);
+                if (r.v && P.opt == KGE_OPT_ADAM) st_vec<V>(r.v + c0, vv[i]);
+                st_vec<V>(r.w + c0, rc[i]);
+            }
+        } else {
+            for (int c0 = lane * V; c0 < K; c0 += 32 * V) {
+                float g[V], rc[V], mv[V], vv[V];
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[x] = mv[x] = vv[x] = 0.f;
+                ld_vec<V>(rc, r.w + c0);
+                if (need_m) ld_vec<V>(mv, r.m + c0);
+                if (need_v) ld_vec<V>(vv, r.v + c0);
+                for (int e = 0; e < n_ent; ++e) {
+                    float t[V];
+                    ld_vec<V>(t, span_entry(P, w, e, K) + c0);
+#pragma unroll
+                    for (int x = 0; x < V; ++x) g[x] += t[x];
+                }
+                if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g);
+                if (no_update) continue;
+                opt_math<V>(P, reset, g, rc, mv, vv);
+                if (r.m && P.opt != KGE_OPT_SGD) st_vec<V>(r.m + c0, mv);
+                if (r.v && P.opt == KGE_OPT_ADAM) st_vec<V>(r.v + c0, vv);
+                st_vec<V>(r.w + c0, rc);
+            }
         }
-        float rc[V];
-        ld_vec<V>(rc, r.w + c0);
-        opt_update<V>(P, r, c0, g, rc);
+    }
+}
+
+// Level 2b: hub runs.  A fixed grid walks the compacted list of hub run heads; the
+// 16 warps of a CTA add the per-chunk partial rows of one run (warp j takes partials j, j+16, ...),
+// the partial sums are combined through shared memory in warp order (deterministic) and the optimizer
+// is applied by the threads that own the columns.
+#define KGE_SPAN_WARPS 16
+template <int V>
+__global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(ApplyParams P) {
+    extern __shared__ __align__(16) float sred[];  // [KGE_SPAN_WARPS][K]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int K = P.ent.K;
+    const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
+    const int n_heads = P.span_count[1];
+    const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
+    const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
+    for (int h = blockIdx.x; h < n_heads; h += gridDim.x) {
+        const int64_t w = P.hub_list[h];
+        const int32_t key = (int32_t)(P.ks[w * KGE_CH + KGE_CH - 1] >> 32);
+        const int64_t last = span_last_chunk(P, w, key, n_chunks, lane);
+        const int64_t n_ent = last - w + 1;
+        for (int c0 = lane * V; c0 < K; c0 += 32 * V) {
+            float g[V];
+#pragma unroll
+            for (int x = 0; x < V; ++x) g[x] = 0.f;
+            int64_t e = wib;
+            for (; e + KGE_SPAN_WARPS < n_ent; e += 2 * KGE_SPAN_WARPS) {
+                float t0[V], t1[V];
+                ld_vec<V>(t0, span_entry(P, w, e, K) + c0);
+                ld_vec<V>(t1, span_entry(P, w, e + KGE_SPAN_WARPS, K) + c0);
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[x] += t0[x];
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[x] += t1[x];
+            }
+            if (e < n_ent) {
+                float t0[V];
+                ld_vec<V>(t0, span_entry(P, w, e, K) + c0);
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[x] += t0[x];
+            }
+            st_vec<V>(sred + (size_t)wib * K + c0, g);
+        }
+        __syncthreads();
+        const RowPtrs r = resolve_row(P, key);
+        float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
+        for (int c0 = threadIdx.x * V; c0 < K; c0 += KGE_SPAN_WARPS * 32 * V) {
+            float g[V], rc[V], mv[V], vv[V];
+#pragma unroll
+            for (int x = 0; x < V; ++x) g[x] = mv[x] = vv[x] = 0.f;
+            ld_vec<V>(rc, r.w + c0);
+            if (!no_update && !reset && P.opt != KGE_OPT_SGD) ld_vec<V>(mv, r.m + c0);
+            if (!no_update && !reset && P.opt == KGE_OPT_ADAM) ld_vec<V>(vv, r.v + c0);
+#pragma unroll
+            for (int j = 0; j < KGE_SPAN_WARPS; ++j) {
+                float t0[V];
+                ld_vec<V>(t0, sred + (size_t)j * K + c0);
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[x] += t0[x];
+            }
+            if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g);
+            if (!no_update) {
+                opt_math<V>(P, reset, g, rc, mv, vv);
+                if (r.m && P.opt != KGE_OPT_SGD) st_vec<V>(r.m + c0, mv);
+                if (r.v && P.opt == KGE_OPT_ADAM) st_vec<V>(r.v + c0, vv);
+                st_vec<V>(r.w + c0, rc);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -431,12 +638,10 @@ extern "C" int kge_train_emit(kge_ctx* ctx, const kge_train_args* a, int32_t* ke
     return emit_impl(ctx, a, keys_out, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, void* stream) {
-    KGE_REQUIRE(ctx != nullptr, "kge_train_fwd_bwd: null ctx");
-    if (int rc = validate_train(a)) return rc;
+// fork: when `side` is given the loss reduction runs there (behind ev_fwd) and signals ev_loss
+static int fwd_bwd_impl(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, cudaStream_t st, cudaStream_t side) {
     KGE_REQUIRE(grad_buf != nullptr, "kge_train_fwd_bwd: grad_buf missing");
     KGE_REQUIRE(a->loss_out != nullptr, "kge_train_fwd_bwd: loss_out missing");
-    cudaStream_t st = (cudaStream_t)stream;
     if (a->n_pos == 0) {
         KGE_CUDA_CHECK(cudaMemsetAsync(a->loss_out, 0, sizeof(float), st));
         return 0;
@@ -464,9 +669,22 @@ extern "C" int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* g
         default: rc = kge_launch_fwd_bwd_m3(P, ctx->sm_count, st); break;
     }
     if (rc) return rc;
-    kge_loss_reduce_kernel<<<1, 1024, 0, st>>>(ctx->loss_part.as<float>(), a->n_pos, a->loss_out);
+    cudaStream_t ls = st;
+    if (side != nullptr) {
+        KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_fwd, st));
+        KGE_CUDA_CHECK(cudaStreamWaitEvent(side, ctx->ev_fwd, 0));
+        ls = side;
+    }
+    kge_loss_reduce_kernel<<<1, 1024, 0, ls>>>(ctx->loss_part.as<float>(), a->n_pos, a->loss_out);
     KGE_CUDA_CHECK(cudaGetLastError());
+    if (side != nullptr) KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_loss, side));
     return 0;
+}
+
+extern "C" int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, void* stream) {
+    KGE_REQUIRE(ctx != nullptr, "kge_train_fwd_bwd: null ctx");
+    if (int rc = validate_train(a)) return rc;
+    return fwd_bwd_impl(ctx, a, grad_buf, (cudaStream_t)stream, nullptr);
 }
 
 // owner-side selection of the slots a rank must reduce: keys of its row range + every relation key
@@ -479,29 +697,49 @@ __global__ void kge_select_flag_kernel(const int32_t* __restrict__ keys, int64_t
     }
 }
 
-template <int V>
-static int launch_apply(const ApplyParams& P, int tmode, cudaStream_t st) {
+template <int V, int NCA>
+static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st) {
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
-    dim3 grid((unsigned)((n_chunks + 7) / 8)), block(256);
-    if (tmode == 0) kge_reduce_apply_kernel<V, 0><<<grid, block, 0, st>>>(P);
-    else if (tmode == 1) kge_reduce_apply_kernel<V, 1><<<grid, block, 0, st>>>(P);
-    else kge_reduce_apply_kernel<V, 2><<<grid, block, 0, st>>>(P);
+    dim3 grid((unsigned)((n_chunks + KGE_RA_WARPS - 1) / KGE_RA_WARPS)), block(KGE_RA_WARPS * 32);
+    KGE_CUDA_CHECK(cudaMemsetAsync(P.span_count, 0, 2 * sizeof(int32_t), st));
+    if (tmode == 0) kge_reduce_apply_kernel<V, 0, NCA><<<grid, block, 0, st>>>(P);
+    else if (tmode == 1) kge_reduce_apply_kernel<V, 1, NCA><<<grid, block, 0, st>>>(P);
+    else kge_reduce_apply_kernel<V, 2, NCA><<<grid, block, 0, st>>>(P);
     KGE_CUDA_CHECK(cudaGetLastError());
-    kge_span_apply_kernel<V><<<(unsigned)n_chunks, 128, 0, st>>>(P);
+    const size_t smem = (size_t)KGE_SPAN_WARPS * P.ent.K * sizeof(float);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_span_apply_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    kge_span_warp_kernel<V, NCA><<<sm_count * 4, 128, 0, st>>>(P);
+    KGE_CUDA_CHECK(cudaGetLastError());
+    kge_span_apply_kernel<V><<<std::min(sm_count, 64), KGE_SPAN_WARPS * 32, smem, st>>>(P);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
+static int launch_apply(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st) {
+    const int K = P.ent.K;
+    KGE_REQUIRE((size_t)KGE_SPAN_WARPS * K * sizeof(float) <= 200 * 1024, "kge_train: embedding size %d too large for the span reduction", K);
+    if (K % 4 == 0) {
+        if (K <= 128) return launch_apply_nca<4, 1>(P, tmode, sm_count, st);
+        if (K <= 256) return launch_apply_nca<4, 2>(P, tmode, sm_count, st);
+        if (K <= 512) return launch_apply_nca<4, 4>(P, tmode, sm_count, st);
+        return launch_apply_nca<4, 0>(P, tmode, sm_count, st);
+    }
+    return launch_apply_nca<1, 0>(P, tmode, sm_count, st);
+}
+
 // packed_in: n_items (key << 32 | global slot) entries, unsorted; sorted by key (stable) into ctx->ks_sorted
-static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* packed_in, int64_t n_items, const kge_table* grads,
-                      int64_t row_begin, int64_t row_end, cudaStream_t st) {
+static int sort_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* packed_in, int64_t n_items, cudaStream_t st) {
     KGE_REQUIRE(n_items < (int64_t)INT32_MAX, "kge_train_apply: too many slots");
     if (n_items == 0) return 0;
     const int K = a->ent.K;
     const int64_t n_chunks = (n_items + KGE_CH - 1) / KGE_CH;
     if (ctx->ks_sorted.reserve((size_t)n_items * 8)) return -2;
     if (ctx->partial.reserve((size_t)2 * n_chunks * K * sizeof(float))) return -2;
-    if (ctx->span_head.reserve((size_t)n_chunks)) return -2;
+    if (ctx->span_head.reserve((size_t)(2 * n_chunks + 2) * sizeof(int32_t))) return -2;
     int64_t E = a->ent.rows;
     int end_bit = 1;
     while (((int64_t)1 << end_bit) < E + a->R) ++end_bit;
@@ -511,6 +749,14 @@ static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* pac
     if (ctx->sort_tmp.reserve(tmp_bytes)) return -2;
     KGE_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, tmp_bytes, packed_in, ctx->ks_sorted.as<uint64_t>(), (int)n_items,
                                                   32, 32 + end_bit, st));
+    return 0;
+}
+
+static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, const kge_table* grads, int64_t row_begin,
+                       int64_t row_end, cudaStream_t st) {
+    if (n_items == 0) return 0;
+    const int K = a->ent.K;
+    const int64_t E = a->ent.rows;
     ApplyParams P;
     P.ks = ctx->ks_sorted.as<uint64_t>();
     P.n_keys = n_items;
@@ -540,7 +786,12 @@ static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* pac
     P.eps = a->eps;
     P.momentum = a->momentum;
     P.partial = ctx->partial.as<float>();
-    P.span_head = ctx->span_head.as<uint8_t>();
+    {
+        const int64_t n_chunks = (n_items + KGE_CH - 1) / KGE_CH;
+        P.span_count = ctx->span_head.as<int32_t>();
+        P.span_list = ctx->span_head.as<int32_t>() + 2;
+        P.hub_list = P.span_list + n_chunks;
+    }
     P.dbg_grad_ent = a->dbg_grad_ent;
     P.dbg_grad_rel = a->dbg_grad_rel;
     const bool reset = (a->flags & KGE_F_RESET_STATE) != 0;
@@ -554,8 +805,23 @@ static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* pac
             KGE_REQUIRE(P.has_m && a->rel_m, "kge_train: optimizer state missing");
     }
     const int tmode = a->model == KGE_TRANSE_L1 ? 1 : (a->model == KGE_TRANSE_L2 ? 2 : 0);
-    if (K % 4 == 0) return launch_apply<4>(P, tmode, st);
-    return launch_apply<1>(P, tmode, st);
+    return launch_apply(P, tmode, ctx->sm_count, st);
+}
+
+static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* packed_in, int64_t n_items, const kge_table* grads,
+                      int64_t row_begin, int64_t row_end, cudaStream_t st) {
+    if (int rc = sort_impl(ctx, a, packed_in, n_items, st)) return rc;
+    return reduce_impl(ctx, a, n_items, grads, row_begin, row_end, st);
+}
+
+static int ensure_side_stream(kge_ctx* ctx) {
+    if (ctx->side != nullptr) return 0;
+    KGE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming));
+    KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fwd, cudaEventDisableTiming));
+    KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_loss, cudaEventDisableTiming));
+    return 0;
 }
 
 // Selection of the slots this rank reduces (keys in [row_begin,row_end) or relation keys), started
@@ -625,8 +891,14 @@ extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* strea
     int64_t S = (int64_t)(3 + a->eta) * a->n_pos;
     if (ctx->ks_in.reserve((size_t)S * 8)) return -2;
     if (ctx->grad_rows.reserve((size_t)gbuf_floats(a->eta, a->n_pos, K) * sizeof(float))) return -2;
+    if (int rc = ensure_side_stream(ctx)) return rc;
     if (int rc = emit_impl(ctx, a, nullptr, ctx->ks_in.as<uint64_t>(), st)) return rc;
-    if (int rc = kge_train_fwd_bwd(ctx, a, ctx->grad_rows.as<float>(), stream)) return rc;
+    // fork: the radix sort only needs the keys, so it runs beside the forward/backward kernel
+    KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, st));
+    KGE_CUDA_CHECK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    if (int rc = sort_impl(ctx, a, ctx->ks_in.as<uint64_t>(), S, ctx->side)) return rc;
+    KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_sorted, ctx->side));
+    if (int rc = fwd_bwd_impl(ctx, a, ctx->grad_rows.as<float>(), st, ctx->side)) return rc;
     kge_table g;
     memset(&g, 0, sizeof(g));
     g.shard[0] = ctx->grad_rows.as<float>();
@@ -634,7 +906,10 @@ extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* strea
     g.rows_per_shard = S;
     g.n_shards = 1;
     g.K = K;
-    return apply_impl(ctx, a, ctx->ks_in.as<uint64_t>(), S, &g, 0, a->ent.rows, st);
+    KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_sorted, 0));
+    if (int rc = reduce_impl(ctx, a, S, &g, 0, a->ent.rows, st)) return rc;
+    KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_loss, 0));  // join
+    return 0;
 }
 
 extern "C" int kge_train_step_host(kge_ctx* ctx, const kge_train_args* a, const int32_t* pos_host, float* loss_host,
