@@ -94,6 +94,32 @@ __device__ __forceinline__ void row_load(Row<V, NCH, CPLX>& r, const float* __re
     }
 }
 
+// branch-free variant: lanes past the end of the row read the row's last vector (a valid duplicate)
+template <int V, int NCH, bool CPLX>
+__device__ __forceinline__ void row_load_clamped(Row<V, NCH, CPLX>& r, const float* __restrict__ base, int lane, int nvec, int half) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = min(lane + 32 * i, nvec - 1);
+        ld_vec<V>(r.re[i], base + (size_t)c * V);
+        if constexpr (CPLX) ld_vec<V>(r.im[i], base + half + (size_t)c * V);
+    }
+}
+
+// zero the vectors of the lanes past the end of the row
+template <int V, int NCH, bool CPLX>
+__device__ __forceinline__ void row_mask(Row<V, NCH, CPLX>& r, int lane, int nvec) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        if (lane + 32 * i >= nvec) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                r.re[i][v] = 0.f;
+                if constexpr (CPLX) r.im[i][v] = 0.f;
+            }
+        }
+    }
+}
+
 template <int V, int NCH, bool CPLX>
 __device__ __forceinline__ void row_store(float* __restrict__ base, const Row<V, NCH, CPLX>& r, int lane, int nvec, int half) {
 #pragma unroll
@@ -144,23 +170,27 @@ struct Algebra {
     }
 
     // lane-partial of the reduction that defines the score of (Q, r).  For TransE the two sides
-    // differ only in the sign of the difference, which |.| and (.)^2 ignore.
-    __device__ __forceinline__ static float partial(const R& Q, const R& r) {
-        float acc = 0.f;
+    // differ only in the sign of the difference, which |.| and (.)^2 ignore.  msk[i] is 1 for the
+    // lanes that hold real columns of chunk i and 0 past the end of the row: the trilinear models
+    // do not need it (their queries are zero there), the distances do.  V independent accumulators
+    // keep the FMA dependency chains short.
+    __device__ __forceinline__ static float partial(const R& Q, const R& r, const float (&msk)[NCH]) {
+        float a0 = 0.f, a1 = 0.f;  // two independent chains
         ROW_FOR(i, v) {
+            float& acc = (v & 1) ? a1 : a0;
             if constexpr (MODEL == 0) {
-                acc += fabsf(Q.re[i][v] - r.re[i][v]);
+                acc = fmaf(msk[i], fabsf(Q.re[i][v] - r.re[i][v]), acc);
             } else if constexpr (MODEL == 1) {
-                float d = Q.re[i][v] - r.re[i][v];
+                float d = (Q.re[i][v] - r.re[i][v]) * msk[i];
                 acc = fmaf(d, d, acc);
             } else if constexpr (MODEL == 2) {
                 acc = fmaf(Q.re[i][v], r.re[i][v], acc);
             } else {
-                acc = fmaf(Q.re[i][v], r.re[i][v], acc);
-                acc = fmaf(Q.im[i][v], r.im[i][v], acc);
+                a0 = fmaf(Q.re[i][v], r.re[i][v], a0);
+                a1 = fmaf(Q.im[i][v], r.im[i][v], a1);
             }
         }
-        return acc;
+        return a0 + a1;
     }
 
     __device__ __forceinline__ static float finish(float sum, float scale) {
@@ -311,14 +341,19 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
     row_zero(AccO);
     row_zero(AccS);
     float spos = 0.f;
+    float msk[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) msk[c] = (lane + 32 * c < nvec) ? 1.f : 0.f;
     if (valid) {
         R s, p, o;
         const int32_t si = P.pos[3 * i + 0], pi = P.pos[3 * i + 1], oi = P.pos[3 * i + 2];
-        row_load(s, table_row(P.ent, si), lane, nvec, half);
-        row_load(p, P.rel + (size_t)pi * K, lane, nvec, half);
-        row_load(o, table_row(P.ent, oi), lane, nvec, half);
+        row_load_clamped(s, table_row(P.ent, si), lane, nvec, half);
+        row_load_clamped(p, P.rel + (size_t)pi * K, lane, nvec, half);
+        row_load_clamped(o, table_row(P.ent, oi), lane, nvec, half);
         A::queries(s, p, o, Qo, Qs);
-        spos = A::finish(warp_sum(A::partial(Qo, o)), P.scale);
+        row_mask(Qo, lane, nvec);  // queries are zero past the end of the row: duplicate columns of
+        row_mask(Qs, lane, nvec);  // the clamped candidate loads then contribute nothing
+        spos = A::finish(warp_sum(A::partial(Qo, o, msk)), P.scale);
     } else {
         row_zero(Qo);
         row_zero(Qs);
@@ -348,63 +383,73 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
                 my_keep = P.keep[my_q];
             }
             float my_c = 0.f, my_sn = 0.f;
-            for (int t = 0; t < lim; t += U) {
-                R r[U];
-                bool ob[U];
-                float part[U];
+            // the negatives of this round, grouped by corrupted side so that the query (Qo / Qs) and the
+            // accumulator (AccO / AccS) are compile-time choices inside each group
+            auto group = [&](auto obj_tag, unsigned todo) {
+                constexpr bool OBJ = decltype(obj_tag)::value;
+                const R& Q = OBJ ? Qo : Qs;
+                R& Acc = OBJ ? AccO : AccS;
+                while (todo) {
+                    R r[U];
+                    int src[U];
+                    float part[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int src = min(t + u, 31);
-                    const int idx = __shfl_sync(0xffffffffu, my_idx, src);
-                    ob[u] = __shfl_sync(0xffffffffu, my_keep, src) != 0;
-                    if (t + u < lim) row_load(r[u], table_row(P.ent, idx), lane, nvec, half);
-                }
-                if constexpr (MODE != 2) {
+                    for (int u = 0; u < U; ++u) {
+                        src[u] = todo ? __ffs(todo) - 1 : -1;
+                        todo &= todo - 1;  // 0 stays 0
+                        const int idx = __shfl_sync(0xffffffffu, my_idx, max(src[u], 0));
+                        if (src[u] >= 0) row_load_clamped(r[u], table_row(P.ent, idx), lane, nvec, half);
+                    }
+                    if constexpr (MODE != 2) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) part[u] = (t + u < lim) ? A::partial(ob[u] ? Qo : Qs, r[u]) : 0.f;
+                        for (int u = 0; u < U; ++u) part[u] = (src[u] >= 0) ? A::partial(Q, r[u], msk) : 0.f;
 #pragma unroll
-                    for (int o2 = 16; o2 > 0; o2 >>= 1)
+                        for (int o2 = 16; o2 > 0; o2 >>= 1)
 #pragma unroll
-                        for (int u = 0; u < U; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o2);
-                }
+                            for (int u = 0; u < U; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o2);
+                    }
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (t + u < lim) {
-                        const int j = sub + SPLIT * (m0 + t + u);
-                        float sn, w;
-                        if constexpr (MODE == 2) sn = sc[j];
-                        else sn = A::finish(part[u], P.scale);
-                        if constexpr (MODE == 1) {
-                            if (lane == 0) sc[j] = sn;
-                        } else {
-                            if constexpr (MODE == 2) {
-                                // losses/nll_multiclass.py:70-81 : softmax weight, zero outside the clip range
-                                const bool in = (sn >= -75.f) && (sn <= 75.f);
-                                w = in ? expf(sn) * zinv : 0.f;
-                            } else if (loss == KGE_LOSS_PAIRWISE) {
-                                // losses/pairwise.py:69 ; tf.maximum passes the gradient when t >= 0
-                                const float tt = margin - spos + sn;
-                                loss_acc += fmaxf(tt, 0.f);
-                                w = (tt >= 0.f) ? 1.f : 0.f;
-                                wsum += w;
+                    for (int u = 0; u < U; ++u) {
+                        if (src[u] >= 0) {
+                            const int j = sub + SPLIT * (m0 + src[u]);
+                            float sn, w;
+                            if constexpr (MODE == 2) sn = sc[j];
+                            else sn = A::finish(part[u], P.scale);
+                            if constexpr (MODE == 1) {
+                                if (lane == 0) sc[j] = sn;
                             } else {
-                                // losses/nll.py:55-59 : log(1+exp(clip(neg)))
-                                const float e = expf(clip75(sn));
-                                loss_acc += logf(1.f + e);
-                                const bool in = (sn >= -75.f) && (sn <= 75.f);
-                                w = in ? e / (1.f + e) : 0.f;
+                                if constexpr (MODE == 2) {
+                                    // losses/nll_multiclass.py:70-81 : softmax weight, zero outside the clip range
+                                    const bool in = (sn >= -75.f) && (sn <= 75.f);
+                                    w = in ? expf(sn) * zinv : 0.f;
+                                } else if (loss == KGE_LOSS_PAIRWISE) {
+                                    // losses/pairwise.py:69 ; tf.maximum passes the gradient when t >= 0
+                                    const float tt = margin - spos + sn;
+                                    loss_acc += fmaxf(tt, 0.f);
+                                    w = (tt >= 0.f) ? 1.f : 0.f;
+                                    wsum += w;
+                                } else {
+                                    // losses/nll.py:55-59 : log(1+exp(clip(neg)))
+                                    const float e = expf(clip75(sn));
+                                    loss_acc += logf(1.f + e);
+                                    const bool in = (sn >= -75.f) && (sn <= 75.f);
+                                    w = in ? e / (1.f + e) : 0.f;
+                                }
+                                const float c = A::coefficient(w, sn, P.scale);
+                                if (lane == src[u]) {
+                                    my_c = c;
+                                    my_sn = sn;
+                                }
+                                A::accumulate(Q, r[u], OBJ, w, sn, P.scale, Acc);
                             }
-                            const float c = A::coefficient(w, sn, P.scale);
-                            if (lane == t + u) {
-                                my_c = c;
-                                my_sn = sn;
-                            }
-                            if (ob[u]) A::accumulate(Qo, r[u], true, w, sn, P.scale, AccO);
-                            else A::accumulate(Qs, r[u], false, w, sn, P.scale, AccS);
                         }
                     }
                 }
-            }
+            };
+            const unsigned m_obj = __ballot_sync(0xffffffffu, lane < lim && my_keep != 0);
+            const unsigned m_sub = __ballot_sync(0xffffffffu, lane < lim && my_keep == 0);
+            group(std::true_type{}, m_obj);
+            group(std::false_type{}, m_sub);
             if constexpr (MODE != 1) {
                 if (lane < lim) {
                     coef[my_q] = my_c;
@@ -476,10 +521,10 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
         // the positive itself: an object-side candidate with r = o and weight dL/dpos
         R s, p, o, gs, gp, go;
         const int32_t si = P.pos[3 * i + 0], pi = P.pos[3 * i + 1], oi = P.pos[3 * i + 2];
-        row_load(o, table_row(P.ent, oi), lane, nvec, half);
+        row_load_clamped(o, table_row(P.ent, oi), lane, nvec, half);
         A::backward_pos(Qo, o, wpos, spos, P.scale, go, AccO);
-        row_load(s, table_row(P.ent, si), lane, nvec, half);
-        row_load(p, P.rel + (size_t)pi * K, lane, nvec, half);
+        row_load_clamped(s, table_row(P.ent, si), lane, nvec, half);
+        row_load_clamped(p, P.rel + (size_t)pi * K, lane, nvec, half);
         A::fold(s, p, o, AccO, AccS, gs, gp, go);
         row_store(G + (size_t)i * K, gs, lane, nvec, half);
         row_store(G + (size_t)(n + i) * K, go, lane, nvec, half);
@@ -522,7 +567,7 @@ static int launch_fwd_bwd_nch(int nch, int split, const FwdBwdParams& P, cudaStr
     // U candidate rows in flight per warp: ~64 registers of row data
     switch (nch) {
         case 1: return launch_fwd_bwd_split<MODEL, V, 1, (C ? 8 : 8)>(split, P, st);
-        case 2: return launch_fwd_bwd_split<MODEL, V, 2, (C ? 4 : 8)>(split, P, st);
+        case 2: return launch_fwd_bwd_split<MODEL, V, 2, (C ? 2 : 4)>(split, P, st);
         case 3:
         case 4: return launch_fwd_bwd_split<MODEL, V, 4, (C ? 2 : 4)>(split, P, st);
         case 5:
