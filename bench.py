@@ -320,28 +320,28 @@ def single_gpu_main(args, w):
     t_warm_ms = e0.elapsed_time(e1)
     value_warm = steps * triples_per_step / (t_warm_ms * 1e-3)
 
-    # ---- per-kernel time of the phases (live CUDA events, L2 flushed): emit | fwd_bwd(+loss reduce) | sort+apply
-    S = (3 + eta) * B
-    keys = torch.empty(S, dtype=torch.int32, device=dev)
-    grad_buf = torch.empty(eng.train_grad_floats(eta, B, K), dtype=torch.float32, device=dev)
-    ph = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    # ---- per-kernel time inside the real step (library-side CUDA events on the launching stream, L2
+    # flushed before every step): emit | fwd_bwd | reduce_apply (after the hidden sort) | span/hub reduction
+    eng.set_timing(True)
     for s in range(steps):
         flush.fill_(float(s))
         lo, hi = batch(it)
-        f["step"] += 1
-        a = eng.train_args(ent=f["ent"], rel=f["rel"], pos=Xd[lo:hi], loss_out=f["loss_dev"], side=0, step=f["step"], **f["kw"], **f["st"])
-        ph[s][0].record()
-        eng.train_emit(a, keys)
-        ph[s][1].record()
-        eng.train_fwd_bwd(a, grad_buf)
-        ph[s][2].record()
-        eng.train_apply(a, keys, eng.grad_table(grad_buf, eta, B, K), 0, E)
-        ph[s][3].record()
+        model._fit_step_device(Xd[lo:hi])
         it += 1
     torch.cuda.synchronize()
-    t_emit = sum(p[0].elapsed_time(p[1]) for p in ph) / steps
-    t_fb = sum(p[1].elapsed_time(p[2]) for p in ph) / steps
-    t_apply = sum(p[2].elapsed_time(p[3]) for p in ph) / steps
+    phases, n_timed = eng.get_timing()
+    eng.set_timing(False)
+    t_emit, t_fb, t_apply, t_span = phases["emit"], phases["fwd_bwd"], phases["reduce_apply"], phases["spans"]
+    # distinct rows touched per step (entities + relations), from the library's own sort keys
+    S = (3 + eta) * B
+    keys = torch.empty(S, dtype=torch.int32, device=dev)
+    uniq = []
+    for j in range(3):
+        lo, hi = batch(it + j)
+        a = eng.train_args(ent=f["ent"], rel=f["rel"], pos=Xd[lo:hi], loss_out=f["loss_dev"], side=0, step=f["step"] + 1 + j, **f["kw"], **f["st"])
+        eng.train_emit(a, keys)
+        uniq.append(int(torch.unique(keys).numel()))
+    n_unique = float(np.mean(uniq))
 
     # ---- e2e: host batches through the public step (pinned H2D of the batch + D2H of the loss, every step)
     for _ in range(3):
@@ -361,20 +361,31 @@ def single_gpu_main(args, w):
     assert math.isfinite(last_loss), "training diverged in the benchmark"
     clocks = sampler.stop()
 
-    # roofline of the dominant training kernel.  Algorithmic bytes (DESIGN.md "Roofline accounting"):
-    #   fwd_bwd : every gathered row read once + every gradient row written once = 2*(3+eta)*4K per positive
-    #   apply   : every gradient row read once + (w,m,v) read and written for every touched row
-    #             = 7*(3+eta)*4K per positive (SURVEY 8d accounting; Adam)
-    bytes_fb = 2 * (3 + eta) * 4 * K * B
+    # roofline of the dominant training kernel.  Algorithmic bytes per launch:
+    #   fwd_bwd      : (3+eta) rows gathered + 5 rows + eta coefficients/flags written, per positive
+    #   reduce_apply : one row-sized read + 13 B of key/slot/coefficient per slot, plus w,m,v read and
+    #                  written once per DISTINCT touched row (Adam: 6 row-sized accesses)
     n_state = {"adam": 6, "adagrad": 4, "momentum": 4, "sgd": 2}[w["opt"]]
-    bytes_apply = (1 + n_state) * (3 + eta) * 4 * K * B
-    dom = "kge_fwd_bwd_kernel" if t_fb >= t_apply else "kge_apply_kernel(+radix sort)"
-    dom_t, dom_b = (t_fb, bytes_fb) if t_fb >= t_apply else (t_apply, bytes_apply)
+    bytes_fb = ((3 + eta) * 4 * K + 5 * 4 * K + 5 * eta) * B
+    bytes_apply = (3 + eta) * B * (4 * K + 13) + n_state * 4 * K * n_unique
+    bytes_survey = 36 * K * (3 + eta) * B  # SURVEY 8(d) per-positive figure (no duplicate-row reuse), for reference
+    t_red = t_apply + t_span
+    dom = "kge_fwd_bwd_kernel" if t_fb >= t_red else "kge_reduce_apply_kernel (+ span/hub reduction)"
+    dom_t, dom_b = (t_fb, bytes_fb) if t_fb >= t_red else (t_red, bytes_apply)
     ach = dom_b / (dom_t * 1e-3) / 1e9
+    step_ms = t_cold_ms / steps
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
                 "traffic": None, "peak_source": peaks["src"], "algorithmic_bytes_per_launch": dom_b, "kernel_ms": dom_t,
-                "phases_ms": {"emit": t_emit, "fwd_bwd": t_fb, "sort_apply": t_apply},
-                "step_algorithmic_GBps": (bytes_fb + bytes_apply) / (t_cold_ms / steps * 1e-3) / 1e9}
+                "phases_ms": {"emit": t_emit, "fwd_bwd": t_fb, "reduce_apply": t_apply, "span_hub": t_span, "timed_steps": n_timed},
+                "kernels": {"fwd_bwd": {"bytes": bytes_fb, "GBps": bytes_fb / (t_fb * 1e-3) / 1e9, "frac": bytes_fb / (t_fb * 1e-3) / 1e9 / peaks["hbm"]},
+                            "reduce_apply": {"bytes": bytes_apply, "GBps": bytes_apply / (t_red * 1e-3) / 1e9,
+                                             "frac": bytes_apply / (t_red * 1e-3) / 1e9 / peaks["hbm"]}},
+                "distinct_rows_per_step": n_unique,
+                "step_algorithmic_GBps": (bytes_fb + bytes_apply) / (step_ms * 1e-3) / 1e9,
+                "step_frac": (bytes_fb + bytes_apply) / (step_ms * 1e-3) / 1e9 / peaks["hbm"],
+                "step_survey_accounting_GBps": bytes_survey / (step_ms * 1e-3) / 1e9,
+                "note": "tables of cfg1-3 are L2-resident: the bytes are what the kernel loads/stores, mostly served by L2"
+                        if (E * K * 4 * 3) < (100 << 20) else "tables exceed L2: HBM-bound"}
 
     line = {
         "metric": TRAIN_METRIC, "value": value, "unit": "triples/s", "n_gpus": 1, "steps": steps, "warmup": warmup,

@@ -66,6 +66,11 @@ struct kge_ctx {
     // side stream of the single-GPU step (sort + loss reduction beside the forward/backward kernel)
     cudaStream_t  side = nullptr;
     cudaEvent_t   ev_fork = nullptr, ev_sorted = nullptr, ev_fwd = nullptr, ev_loss = nullptr;
+    // optional per-phase timing of kge_train_step (bench instrumentation): emit | fwd_bwd | reduce | spans
+    bool          timing = false, tpending = false;
+    cudaEvent_t   tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double        tacc[4] = {0, 0, 0, 0};
+    int           tcount = 0;
     int*          h_count = nullptr;
     cudaEvent_t   ev_count = nullptr;
     bool          sel_valid = false;

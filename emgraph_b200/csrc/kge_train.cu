@@ -698,7 +698,7 @@ __global__ void kge_select_flag_kernel(const int32_t* __restrict__ keys, int64_t
 }
 
 template <int V, int NCA>
-static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st) {
+static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st, cudaEvent_t mid) {
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
     dim3 grid((unsigned)((n_chunks + KGE_RA_WARPS - 1) / KGE_RA_WARPS)), block(KGE_RA_WARPS * 32);
     KGE_CUDA_CHECK(cudaMemsetAsync(P.span_count, 0, 2 * sizeof(int32_t), st));
@@ -712,6 +712,7 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
         KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_span_apply_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
+    if (mid != nullptr) KGE_CUDA_CHECK(cudaEventRecord(mid, st));
     kge_span_warp_kernel<V, NCA><<<sm_count * 4, 128, 0, st>>>(P);
     KGE_CUDA_CHECK(cudaGetLastError());
     kge_span_apply_kernel<V><<<std::min(sm_count, 64), KGE_SPAN_WARPS * 32, smem, st>>>(P);
@@ -719,16 +720,16 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
     return 0;
 }
 
-static int launch_apply(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st) {
+static int launch_apply(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st, cudaEvent_t mid) {
     const int K = P.ent.K;
     KGE_REQUIRE((size_t)KGE_SPAN_WARPS * K * sizeof(float) <= 200 * 1024, "kge_train: embedding size %d too large for the span reduction", K);
     if (K % 4 == 0) {
-        if (K <= 128) return launch_apply_nca<4, 1>(P, tmode, sm_count, st);
-        if (K <= 256) return launch_apply_nca<4, 2>(P, tmode, sm_count, st);
-        if (K <= 512) return launch_apply_nca<4, 4>(P, tmode, sm_count, st);
-        return launch_apply_nca<4, 0>(P, tmode, sm_count, st);
+        if (K <= 128) return launch_apply_nca<4, 1>(P, tmode, sm_count, st, mid);
+        if (K <= 256) return launch_apply_nca<4, 2>(P, tmode, sm_count, st, mid);
+        if (K <= 512) return launch_apply_nca<4, 4>(P, tmode, sm_count, st, mid);
+        return launch_apply_nca<4, 0>(P, tmode, sm_count, st, mid);
     }
-    return launch_apply_nca<1, 0>(P, tmode, sm_count, st);
+    return launch_apply_nca<1, 0>(P, tmode, sm_count, st, mid);
 }
 
 // packed_in: n_items (key << 32 | global slot) entries, unsorted; sorted by key (stable) into ctx->ks_sorted
@@ -805,7 +806,7 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
             KGE_REQUIRE(P.has_m && a->rel_m, "kge_train: optimizer state missing");
     }
     const int tmode = a->model == KGE_TRANSE_L1 ? 1 : (a->model == KGE_TRANSE_L2 ? 2 : 0);
-    return launch_apply(P, tmode, ctx->sm_count, st);
+    return launch_apply(P, tmode, ctx->sm_count, st, ctx->timing ? ctx->tev[3] : nullptr);
 }
 
 static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* packed_in, int64_t n_items, const kge_table* grads,
@@ -816,7 +817,10 @@ static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* pac
 
 static int ensure_side_stream(kge_ctx* ctx) {
     if (ctx->side != nullptr) return 0;
-    KGE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    // highest priority: the sort's small kernels must not queue behind the waves of the forward kernel
+    int prio_lo = 0, prio_hi = 0;
+    KGE_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    KGE_CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_hi));
     KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming));
     KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fwd, cudaEventDisableTiming));
@@ -881,6 +885,41 @@ extern "C" int kge_train_apply(kge_ctx* ctx, const kge_train_args* a, const int3
     return apply_impl(ctx, a, ctx->ks_sel.as<uint64_t>(), m, grads, row_begin, row_end, (cudaStream_t)stream);
 }
 
+static void timing_collect(kge_ctx* ctx) {
+    if (!ctx->tpending) return;
+    cudaEventSynchronize(ctx->tev[4]);
+    for (int i = 0; i < 4; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1]) == cudaSuccess) ctx->tacc[i] += ms;
+    }
+    ctx->tcount += 1;
+    ctx->tpending = false;
+}
+
+extern "C" int kge_ctx_set_timing(kge_ctx* ctx, int on) {
+    KGE_REQUIRE(ctx != nullptr, "kge_ctx_set_timing: null ctx");
+    if (on && ctx->tev[0] == nullptr)
+        for (int i = 0; i < 5; ++i) KGE_CUDA_CHECK(cudaEventCreate(&ctx->tev[i]));
+    timing_collect(ctx);
+    ctx->timing = on != 0;
+    for (int i = 0; i < 4; ++i) ctx->tacc[i] = 0;
+    ctx->tcount = 0;
+    return 0;
+}
+
+extern "C" int kge_ctx_get_timing(kge_ctx* ctx, float* ms_out4, int* steps_out) {
+    KGE_REQUIRE(ctx != nullptr && ms_out4 != nullptr, "kge_ctx_get_timing: null argument");
+    timing_collect(ctx);
+    for (int i = 0; i < 4; ++i) ms_out4[i] = ctx->tcount ? (float)(ctx->tacc[i] / ctx->tcount) : 0.f;
+    if (steps_out) *steps_out = ctx->tcount;
+    return 0;
+}
+
+#define KGE_TMARK(i)                                                        \
+    do {                                                                    \
+        if (ctx->timing) KGE_CUDA_CHECK(cudaEventRecord(ctx->tev[i], st));  \
+    } while (0)
+
 extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* stream) {
     KGE_REQUIRE(ctx != nullptr, "kge_train_step: null ctx");
     if (int rc = validate_train(a)) return rc;
@@ -892,13 +931,17 @@ extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* strea
     if (ctx->ks_in.reserve((size_t)S * 8)) return -2;
     if (ctx->grad_rows.reserve((size_t)gbuf_floats(a->eta, a->n_pos, K) * sizeof(float))) return -2;
     if (int rc = ensure_side_stream(ctx)) return rc;
+    if (ctx->timing) timing_collect(ctx);
+    KGE_TMARK(0);
     if (int rc = emit_impl(ctx, a, nullptr, ctx->ks_in.as<uint64_t>(), st)) return rc;
+    KGE_TMARK(1);
     // fork: the radix sort only needs the keys, so it runs beside the forward/backward kernel
     KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, st));
     KGE_CUDA_CHECK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
     if (int rc = sort_impl(ctx, a, ctx->ks_in.as<uint64_t>(), S, ctx->side)) return rc;
     KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_sorted, ctx->side));
     if (int rc = fwd_bwd_impl(ctx, a, ctx->grad_rows.as<float>(), st, ctx->side)) return rc;
+    KGE_TMARK(2);
     kge_table g;
     memset(&g, 0, sizeof(g));
     g.shard[0] = ctx->grad_rows.as<float>();
@@ -909,6 +952,10 @@ extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* strea
     KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_sorted, 0));
     if (int rc = reduce_impl(ctx, a, S, &g, 0, a->ent.rows, st)) return rc;
     KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_loss, 0));  // join
+    if (ctx->timing) {
+        KGE_CUDA_CHECK(cudaEventRecord(ctx->tev[4], st));
+        ctx->tpending = true;
+    }
     return 0;
 }
 

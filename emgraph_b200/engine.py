@@ -107,6 +107,16 @@ class Engine:
         """floats of the caller-owned gradient buffer for the phased (multi-GPU) calls"""
         return int(self.lib.kge_train_grad_floats(eta, n_pos, K))
 
+    def set_timing(self, on: bool):
+        check(self.lib.kge_ctx_set_timing(self._h, int(bool(on))))
+
+    def get_timing(self):
+        """average ms per step of the train-step phases since set_timing(True)"""
+        out = (C.c_float * 4)()
+        n = C.c_int()
+        check(self.lib.kge_ctx_get_timing(self._h, out, C.byref(n)))
+        return dict(zip(("emit", "fwd_bwd", "reduce_apply", "spans"), [float(x) for x in out])), int(n.value)
+
     def workspace_bytes(self) -> int:
         return int(self.lib.kge_ctx_workspace_bytes(self._h))
 
