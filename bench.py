@@ -376,7 +376,8 @@ def single_gpu_main(args, w):
     step_ms = t_cold_ms / steps
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
                 "traffic": None, "peak_source": peaks["src"], "algorithmic_bytes_per_launch": dom_b, "kernel_ms": dom_t,
-                "phases_ms": {"emit": t_emit, "fwd_bwd": t_fb, "reduce_apply": t_apply, "span_hub": t_span, "timed_steps": n_timed},
+                "phases_ms": {"emit": t_emit, "fwd_bwd": t_fb, "reduce_apply": t_apply, "span_hub": t_span,
+                              "sort_done_after_emit": phases.get("sort_after_emit", 0.0), "timed_steps": n_timed},
                 "kernels": {"fwd_bwd": {"bytes": bytes_fb, "GBps": bytes_fb / (t_fb * 1e-3) / 1e9, "frac": bytes_fb / (t_fb * 1e-3) / 1e9 / peaks["hbm"]},
                             "reduce_apply": {"bytes": bytes_apply, "GBps": bytes_apply / (t_red * 1e-3) / 1e9,
                                              "frac": bytes_apply / (t_red * 1e-3) / 1e9 / peaks["hbm"]}},

@@ -47,6 +47,12 @@ extern "C" int kge_ctx_destroy(kge_ctx* c) {
                       &c->f_tmp, &c->f_tmp2, &c->f_count};
     for (KgeBuf* b : bufs) b->release();
     if (c->h_count) cudaFreeHost(c->h_count);
+    if (c->h_dyn) cudaFreeHost(c->h_dyn);
+    if (c->ev_gin) cudaEventDestroy(c->ev_gin);
+    if (c->gmain) cudaStreamDestroy(c->gmain);
+    c->d_dyn.release();
+    for (KgeGraphEntry& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     if (c->ev_count) cudaEventDestroy(c->ev_count);
     for (cudaEvent_t e : {c->ev_fork, c->ev_sorted, c->ev_fwd, c->ev_loss})
         if (e) cudaEventDestroy(e);

@@ -29,6 +29,26 @@ void kge_set_error(const char* fmt, ...);
         }                                                                                     \
     } while (0)
 
+// per-step scalars read from device memory when a step runs from a captured graph
+struct KgeStepDyn {
+    uint64_t step;
+    float    lr_t;
+    float    pad;
+};
+
+#define KGE_GRAPH_SLOTS 4
+struct KgeGraphEntry {
+    kge_train_args  key;       // args with step = 0
+    cudaStream_t    stream = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int             seen = 0;  // calls with this key so far (the first runs eagerly: allocations, attributes)
+    uint64_t        ws_epoch = 0;  // g_kge_ws_epoch at capture
+    uint64_t        last_use = 0;
+};
+
+// bumped whenever a workspace buffer moves: captured graphs hold raw workspace pointers
+inline uint64_t g_kge_ws_epoch = 0;
+
 // grow-only device buffer owned by the ctx
 struct KgeBuf {
     void*  p = nullptr;
@@ -44,6 +64,7 @@ struct KgeBuf {
         size_t want = bytes + bytes / 8 + 256;
         KGE_CUDA_CHECK(cudaMalloc(&p, want));
         cap = want;
+        ++g_kge_ws_epoch;
         return 0;
     }
     void release() {
@@ -68,8 +89,8 @@ struct kge_ctx {
     cudaEvent_t   ev_fork = nullptr, ev_sorted = nullptr, ev_fwd = nullptr, ev_loss = nullptr;
     // optional per-phase timing of kge_train_step (bench instrumentation): emit | fwd_bwd | reduce | spans
     bool          timing = false, tpending = false;
-    cudaEvent_t   tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    double        tacc[4] = {0, 0, 0, 0};
+    cudaEvent_t   tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double        tacc[5] = {0, 0, 0, 0, 0};
     int           tcount = 0;
     int*          h_count = nullptr;
     cudaEvent_t   ev_count = nullptr;
@@ -78,6 +99,14 @@ struct kge_ctx {
     int64_t       sel_n = 0, sel_begin = 0, sel_end = 0;
     // staging for the host-buffer entry points
     KgeBuf h_pos, h_loss, h_test, h_counts, h_ranks;
+    // whole-step CUDA graphs of the host-buffer training entry (kge_train_step_host): the per-step
+    // scalars (step counter, Adam's bias-corrected rate) travel through a small device block that a
+    // memcpy node refreshes from pinned host memory, so one instantiated graph serves every step
+    cudaStream_t gmain = nullptr;  // capture-able stream the graphed host step runs on
+    cudaEvent_t  ev_gin = nullptr;
+    KgeStepDyn* h_dyn = nullptr;  // pinned
+    KgeBuf      d_dyn;
+    KgeGraphEntry graphs[KGE_GRAPH_SLOTS];
     // ranking workspace
     KgeBuf q_fold, q_hi, q_lo, e_hi, e_lo, pos_q, excl_lo, excl_hi;
     // filter index (sorted, deduplicated composites and the entity column of each)
@@ -136,6 +165,47 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA unit, SASS UBLKCP) wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// spin with a watchdog: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+// 1-D bulk copy global -> shared through the TMA unit; completion is signalled on `bar` as `bytes`
+// of transaction count.  dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // tf.cast(score * 1e5, tf.int32): fp32 multiply, truncate toward zero

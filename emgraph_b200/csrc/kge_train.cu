@@ -31,8 +31,9 @@ __global__ void kge_emit_kernel(const int32_t* __restrict__ pos, int64_t n, int 
                                 const int32_t* __restrict__ repl_in, const uint8_t* __restrict__ keep_in,
                                 uint64_t seed, uint64_t step, uint64_t neg_base,
                                 int32_t* __restrict__ repl_out, uint8_t* __restrict__ keep_out,
-                                int32_t* __restrict__ keys, uint64_t* __restrict__ packed) {
+                                int32_t* __restrict__ keys, uint64_t* __restrict__ packed, const KgeStepDyn* __restrict__ dyn) {
     int64_t S = (int64_t)(3 + eta) * n;
+    if (dyn != nullptr) step = dyn->step;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < S; t += (int64_t)gridDim.x * blockDim.x) {
         int32_t key;
         if (t < n) {
@@ -104,6 +105,7 @@ struct ApplyParams {
     bool has_m, has_v;     // entity optimizer-state tables present
     uint32_t flags;
     float lr, lr_t, beta1, beta2, eps, momentum;
+    const KgeStepDyn* dyn;  // when set, lr_t is read from here (graph replay)
     float* partial;        // [2*n_chunks][K]
     int32_t* span_list;    // chunk ids that start a run crossing chunk borders (unordered)
     int32_t* hub_list;     // the subset whose run covers more than KGE_SPAN_WARP_MAX chunks
@@ -206,12 +208,13 @@ template <int V>
 __device__ __forceinline__ void opt_math(const ApplyParams& P, bool reset, const float (&g)[V], float (&wv)[V], float (&mv)[V], float (&vv)[V]) {
     if (P.opt == KGE_OPT_ADAM) {
         // Keras Adam (beta1 .9, beta2 .999, eps 1e-7): var -= lr_t * m / (sqrt(v) + eps)
+        const float lr_t = P.dyn != nullptr ? P.dyn->lr_t : P.lr_t;
 #pragma unroll
         for (int x = 0; x < V; ++x) {
             const float m0 = reset ? 0.f : mv[x], v0 = reset ? 0.f : vv[x];
             mv[x] = P.beta1 * m0 + (1.f - P.beta1) * g[x];
             vv[x] = P.beta2 * v0 + (1.f - P.beta2) * g[x] * g[x];
-            wv[x] = wv[x] - __fdividef(P.lr_t * mv[x], sqrtf(vv[x]) + P.eps);
+            wv[x] = wv[x] - __fdividef(lr_t * mv[x], sqrtf(vv[x]) + P.eps);
         }
     } else if (P.opt == KGE_OPT_ADAGRAD) {
         // Keras Adagrad: accumulator starts at 0.1; var -= lr * g / (sqrt(acc) + eps)
@@ -237,9 +240,15 @@ __device__ __forceinline__ void opt_math(const ApplyParams& P, bool reset, const
 // the row at once (K <= 128*NCA) so that the row's w/m/v and two slots' rows are in flight together;
 // NCA == 0: generic column loop (any K, scalar columns).
 #define KGE_RA_WARPS 4
+// Run ownership: a run is reduced by ONE warp whenever it touches at most two chunks -- the warp that
+// holds the run's head also takes the run's slots at the front of the next chunk (lanes 16..31 decode
+// them).  Only runs that touch three or more chunks (hub entities) go through per-chunk partial rows
+// and the span kernels.  Every chunk evaluates the same predicate from the sorted keys alone:
+//   head side : the run is long  <=>  the first key of chunk w+2 still equals the run's key
+//   tail side : the run's head lies in chunk w-1  <=>  the last key of chunk w-2 differs
 template <int V, int TMODE, int NCA>
 __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(ApplyParams P) {
-    __shared__ SlotMeta meta[KGE_RA_WARPS][KGE_CH];
+    __shared__ SlotMeta meta[KGE_RA_WARPS][2 * KGE_CH];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t w = (int64_t)blockIdx.x * KGE_RA_WARPS + wib;
     const int64_t b0 = w * KGE_CH;
@@ -247,20 +256,27 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
     const int cnt = (int)min((int64_t)KGE_CH, P.n_keys - b0);
     const int K = P.ent.K;
 
+    // lanes [0,16): own chunk; lanes [16,32): the next chunk (candidates for a spill-over run)
     int32_t key = -2;
-    if (lane < cnt) {
+    if (b0 + lane < P.n_keys) {
         const uint64_t kv = P.ks[b0 + lane];
         key = (int32_t)(kv >> 32);
         meta[wib][lane] = decode_slot(P.G, (int32_t)(kv & 0xffffffffu));
     }
-    int32_t key_prev = -1, key_next = -1;
+    int32_t key_prev = -1, key_prev2 = -1, key_next2 = -1;
     if (lane == 0 && b0 > 0) key_prev = (int32_t)(P.ks[b0 - 1] >> 32);
-    if (lane == 1 && b0 + cnt < P.n_keys) key_next = (int32_t)(P.ks[b0 + cnt] >> 32);
+    if (lane == 1 && b0 > KGE_CH) key_prev2 = (int32_t)(P.ks[b0 - KGE_CH - 1] >> 32);
+    if (lane == 2 && b0 + 2 * KGE_CH < P.n_keys) key_next2 = (int32_t)(P.ks[b0 + 2 * KGE_CH] >> 32);
     key_prev = __shfl_sync(0xffffffffu, key_prev, 0);
-    key_next = __shfl_sync(0xffffffffu, key_next, 1);
+    key_prev2 = __shfl_sync(0xffffffffu, key_prev2, 1);
+    key_next2 = __shfl_sync(0xffffffffu, key_next2, 2);
+    const int32_t key_next = __shfl_sync(0xffffffffu, key, KGE_CH);  // -2 when there is no next chunk
+    const int32_t key_last = __shfl_sync(0xffffffffu, key, cnt - 1);
     const int32_t left = __shfl_up_sync(0xffffffffu, key, 1);
     const bool head = lane < cnt && (lane == 0 || key != left);
     unsigned heads = __ballot_sync(0xffffffffu, head);
+    // slots at the front of the next chunk that continue this chunk's last run
+    const int ext = __popc(__ballot_sync(0xffffffffu, lane >= KGE_CH && key == key_last && key >= 0));
     __syncwarp();
 
     const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
@@ -271,12 +287,17 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
     while (heads) {
         const int a = __ffs(heads) - 1;
         heads &= heads - 1;
-        const int b = heads ? (__ffs(heads) - 1) : cnt;
+        int b = heads ? (__ffs(heads) - 1) : cnt;
         const int32_t skey = __shfl_sync(0xffffffffu, key, a);
         const bool open_start = (a == 0) && (skey == key_prev);
-        const bool open_end = (b == cnt) && (skey == key_next);
+        bool open_end = (b == cnt) && (skey == key_next);
         const RowPtrs r = resolve_row(P, skey);
         if (!r.owned) continue;
+        if (open_start && !open_end && key_prev2 != skey) continue;  // the head's warp (chunk w-1) reduces this run
+        if (!open_start && open_end && key_next2 != skey) {
+            b = cnt + ext;  // the run ends inside the next chunk: finish it here
+            open_end = false;
+        }
         if (!open_start && open_end && lane == 0) P.span_list[atomicAdd(P.span_count, 1)] = (int32_t)w;
         const bool complete = !open_start && !open_end;
         float* part = P.partial + ((size_t)(2 * w + (open_start ? 0 : 1))) * K;
@@ -376,6 +397,234 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Staged variant (trilinear models, local buffers, K % 4 == 0, K <= 512): every row the warp will
+// read -- the gradient/query rows of its slots and, at the end of each complete run, the row's w, m, v
+// -- is one entry of a per-warp SEQUENCE that a ring of 2^ns_log2 shared-memory row slots streams in
+// by 1-D bulk async copies (TMA unit, SASS UBLKCP).  The lane that owns a slot (or a run head) issues
+// the copy as soon as the entry enters the ring window, so a warp keeps up to 2^ns_log2 rows in
+// flight instead of two, and the optimizer state is prefetched while the run is still being summed.
+// ------------------------------------------------------------------------------------------------
+struct RunPlan {
+    bool process, complete, open_start, span_head;
+    int b;
+};
+
+__device__ __forceinline__ RunPlan plan_run(int a, int b_next, int cnt, int ext, int32_t skey, int32_t key_prev, int32_t key_prev2,
+                                            int32_t key_next, int32_t key_next2, bool owned) {
+    RunPlan pl;
+    pl.b = b_next;
+    pl.open_start = (a == 0) && (skey == key_prev);
+    bool open_end = (b_next == cnt) && (skey == key_next);
+    pl.process = owned && !(pl.open_start && !open_end && key_prev2 != skey);
+    if (!pl.open_start && open_end && key_next2 != skey) {
+        pl.b = cnt + ext;
+        open_end = false;
+    }
+    pl.span_head = !pl.open_start && open_end;
+    pl.complete = !pl.open_start && !open_end;
+    return pl;
+}
+
+__device__ __forceinline__ void lds_vec4(float (&d)[4], uint32_t addr) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "r"(addr));
+}
+
+template <int NCA>
+__global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_staged_kernel(ApplyParams P, int ns_log2) {
+    constexpr int V = 4;
+    __shared__ SlotMeta meta[KGE_RA_WARPS][2 * KGE_CH];
+    __shared__ __align__(8) uint64_t bars_all[KGE_RA_WARPS][16];
+    extern __shared__ __align__(16) float ring_all[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t w = (int64_t)blockIdx.x * KGE_RA_WARPS + wib;
+    const int64_t b0 = w * KGE_CH;
+    if (b0 >= P.n_keys) return;
+    const int cnt = (int)min((int64_t)KGE_CH, P.n_keys - b0);
+    const int K = P.ent.K;
+    const int NS = 1 << ns_log2;
+    const uint32_t row_bytes = (uint32_t)K * 4u;
+    uint64_t* bars = bars_all[wib];
+    float* ring = ring_all + (size_t)wib * NS * K;
+    if (lane == 0) {
+        for (int i = 0; i < NS; ++i) mbar_init(bars + i, 1);
+        mbar_fence_init();
+    }
+
+    int32_t key = -2;
+    if (b0 + lane < P.n_keys) {
+        const uint64_t kv = P.ks[b0 + lane];
+        key = (int32_t)(kv >> 32);
+        meta[wib][lane] = decode_slot(P.G, (int32_t)(kv & 0xffffffffu));
+    }
+    int32_t key_prev = -1, key_prev2 = -1, key_next2 = -1;
+    if (lane == 0 && b0 > 0) key_prev = (int32_t)(P.ks[b0 - 1] >> 32);
+    if (lane == 1 && b0 > KGE_CH) key_prev2 = (int32_t)(P.ks[b0 - KGE_CH - 1] >> 32);
+    if (lane == 2 && b0 + 2 * KGE_CH < P.n_keys) key_next2 = (int32_t)(P.ks[b0 + 2 * KGE_CH] >> 32);
+    key_prev = __shfl_sync(0xffffffffu, key_prev, 0);
+    key_prev2 = __shfl_sync(0xffffffffu, key_prev2, 1);
+    key_next2 = __shfl_sync(0xffffffffu, key_next2, 2);
+    const int32_t key_next = __shfl_sync(0xffffffffu, key, KGE_CH);
+    const int32_t key_last = __shfl_sync(0xffffffffu, key, cnt - 1);
+    const int32_t left = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane < cnt && (lane == 0 || key != left);
+    const unsigned heads0 = __ballot_sync(0xffffffffu, head);
+    const int ext = __popc(__ballot_sync(0xffffffffu, lane >= KGE_CH && key == key_last && key >= 0));
+    __syncwarp();
+
+    const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
+    const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
+    const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
+    const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
+    const int n_state = no_update ? 0 : 1 + (need_m ? 1 : 0) + (need_v ? 1 : 0);  // w [, m [, v]]
+
+    // ---- plan: sequence position of every entry this warp will read
+    const RowPtrs mine = resolve_row(P, max(key, 0));  // the row of this lane's own slot (= its run's row)
+    int my_pos = -1, st_pos = -1, st_n = 0;
+    {
+        int seq = 0;
+        unsigned hh = heads0;
+        while (hh) {
+            const int a = __ffs(hh) - 1;
+            hh &= hh - 1;
+            const int bn = hh ? (__ffs(hh) - 1) : cnt;
+            const int32_t skey = __shfl_sync(0xffffffffu, key, a);
+            const bool owned = __shfl_sync(0xffffffffu, (int)mine.owned, a) != 0;
+            const RunPlan pl = plan_run(a, bn, cnt, ext, skey, key_prev, key_prev2, key_next, key_next2, owned);
+            if (!pl.process) continue;
+            const int nst = pl.complete ? n_state : 0;
+            if (lane >= a && lane < pl.b) my_pos = seq + (lane - a);
+            if (lane == a) {
+                st_pos = seq + (pl.b - a);
+                st_n = nst;
+            }
+            seq += (pl.b - a) + nst;
+        }
+    }
+    unsigned issued = 0;  // bit 0: slot row, bits 1..3: w, m, v of the run this lane heads
+    int consumed = 0;
+    auto issue_window = [&]() {
+        const int lim = consumed + NS;
+        if (my_pos >= 0 && !(issued & 1u) && my_pos < lim) {
+            const uint32_t sl = (uint32_t)my_pos & (uint32_t)(NS - 1);
+            mbar_expect_tx(bars + sl, row_bytes);
+            bulk_g2s(ring + (size_t)sl * K, meta[wib][lane].row, row_bytes, bars + sl);
+            issued |= 1u;
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            if (t < st_n && !(issued & (2u << t)) && st_pos + t < lim) {
+                const uint32_t sl = (uint32_t)(st_pos + t) & (uint32_t)(NS - 1);
+                const float* src = t == 0 ? mine.w : (t == 1 ? mine.m : mine.v);
+                mbar_expect_tx(bars + sl, row_bytes);
+                bulk_g2s(ring + (size_t)sl * K, src, row_bytes, bars + sl);
+                issued |= (2u << t);
+            }
+        }
+    };
+    issue_window();
+
+    int cc[NCA];
+#pragma unroll
+    for (int i = 0; i < NCA; ++i) cc[i] = min((lane + 32 * i) * V, K - V);
+    auto wait_entry = [&](int q) -> uint32_t {
+        const uint32_t sl = (uint32_t)q & (uint32_t)(NS - 1);
+        mbar_wait(bars + sl, ((uint32_t)q >> ns_log2) & 1u);
+        return smem_u32(ring + (size_t)sl * K);
+    };
+
+    unsigned heads = heads0;
+    while (heads) {
+        const int a = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const int bn = heads ? (__ffs(heads) - 1) : cnt;
+        const int32_t skey = __shfl_sync(0xffffffffu, key, a);
+        const RowPtrs r = resolve_row(P, skey);
+        const RunPlan pl = plan_run(a, bn, cnt, ext, skey, key_prev, key_prev2, key_next, key_next2, r.owned);
+        if (!pl.process) continue;
+        if (pl.span_head && lane == 0) P.span_list[atomicAdd(P.span_count, 1)] = (int32_t)w;
+        float* part = P.partial + ((size_t)(2 * w + (pl.open_start ? 0 : 1))) * K;
+        float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
+        float g[NCA][V];
+#pragma unroll
+        for (int i = 0; i < NCA; ++i)
+#pragma unroll
+            for (int x = 0; x < V; ++x) g[i][x] = 0.f;
+        int u = a;
+        for (; u + 2 <= pl.b; u += 2) {
+            float v2[2][NCA][V];
+            const float c0 = meta[wib][u].c, c1 = meta[wib][u + 1].c;
+            const uint32_t s0 = wait_entry(consumed), s1 = wait_entry(consumed + 1);
+#pragma unroll
+            for (int i = 0; i < NCA; ++i) lds_vec4(v2[0][i], s0 + (uint32_t)cc[i] * 4u);
+#pragma unroll
+            for (int i = 0; i < NCA; ++i) lds_vec4(v2[1][i], s1 + (uint32_t)cc[i] * 4u);
+            __syncwarp();
+            consumed += 2;
+            issue_window();
+#pragma unroll
+            for (int i = 0; i < NCA; ++i)
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[i][x] = fmaf(c0, v2[0][i][x], g[i][x]);
+#pragma unroll
+            for (int i = 0; i < NCA; ++i)
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[i][x] = fmaf(c1, v2[1][i][x], g[i][x]);
+        }
+        if (u < pl.b) {
+            float v1[NCA][V];
+            const float c0 = meta[wib][u].c;
+            const uint32_t s0 = wait_entry(consumed);
+#pragma unroll
+            for (int i = 0; i < NCA; ++i) lds_vec4(v1[i], s0 + (uint32_t)cc[i] * 4u);
+            __syncwarp();
+            consumed += 1;
+            issue_window();
+#pragma unroll
+            for (int i = 0; i < NCA; ++i)
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[i][x] = fmaf(c0, v1[i][x], g[i][x]);
+        }
+        if (!pl.complete) {
+#pragma unroll
+            for (int i = 0; i < NCA; ++i) {
+                const int c0 = (lane + 32 * i) * V;
+                if (c0 < K) st_vec<V>(part + c0, g[i]);
+            }
+            continue;
+        }
+        if (dbg != nullptr) {
+#pragma unroll
+            for (int i = 0; i < NCA; ++i) {
+                const int c0 = (lane + 32 * i) * V;
+                if (c0 < K) st_vec<V>(dbg + (size_t)r.row * K + c0, g[i]);
+            }
+        }
+        if (no_update) continue;
+        const uint32_t sw = wait_entry(consumed);
+        const uint32_t sm = need_m ? wait_entry(consumed + 1) : 0u;
+        const uint32_t sv = need_v ? wait_entry(consumed + 2) : 0u;
+#pragma unroll
+        for (int i = 0; i < NCA; ++i) {
+            float rc[V], mv[V], vv[V];
+#pragma unroll
+            for (int x = 0; x < V; ++x) mv[x] = vv[x] = 0.f;
+            lds_vec4(rc, sw + (uint32_t)cc[i] * 4u);
+            if (need_m) lds_vec4(mv, sm + (uint32_t)cc[i] * 4u);
+            if (need_v) lds_vec4(vv, sv + (uint32_t)cc[i] * 4u);
+            opt_math<V>(P, reset, g[i], rc, mv, vv);
+            const int c0 = (lane + 32 * i) * V;
+            if (c0 >= K) continue;
+            if (r.m && P.opt != KGE_OPT_SGD) st_vec<V>(r.m + c0, mv);
+            if (r.v && P.opt == KGE_OPT_ADAM) st_vec<V>(r.v + c0, vv);
+            st_vec<V>(r.w + c0, rc);
+        }
+        __syncwarp();
+        consumed += n_state;
+        issue_window();
+    }
+}
+
 // last chunk whose first slot still carries `key` (32 chunks probed per round)
 __device__ __forceinline__ int64_t span_last_chunk(const ApplyParams& P, int64_t w, int32_t key, int64_t n_chunks, int lane) {
     int64_t last = w;
@@ -398,12 +647,16 @@ __device__ __forceinline__ const float* span_entry(const ApplyParams& P, int64_t
     return P.partial + (size_t)(e == 0 ? 2 * w + 1 : 2 * (w + e)) * K;
 }
 
-// Level 2a: one WARP per run that crosses chunk borders (most are 2-3 partials long); runs longer than
-// KGE_SPAN_WARP_MAX chunks (hub entities) are handed to the CTA-wide kernel below.
-#define KGE_SPAN_WARP_MAX 24
-template <int V, int NCA>
-__global__ void __launch_bounds__(128) kge_span_warp_kernel(ApplyParams P) {
-    const int lane = threadIdx.x & 31;
+// Level 2: runs that touch three or more chunks (hub entities; everything shorter is finished by the
+// run-head warp in level 1).  A fixed grid walks the list of run heads; the KGE_SPAN_WARPS warps of a
+// CTA add the per-chunk partial rows of one run (warp j takes partials j, j+KGE_SPAN_WARPS, ...), the
+// partial sums are combined through shared memory in warp order (deterministic) and the optimizer is
+// applied by the threads that own the columns (their w, m, v loads are issued before the summation).
+#define KGE_SPAN_WARPS 8
+template <int V>
+__global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(ApplyParams P) {
+    extern __shared__ __align__(16) float sred[];  // [KGE_SPAN_WARPS][K]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int K = P.ent.K;
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
     const int n_heads = P.span_count[0];
@@ -411,115 +664,21 @@ __global__ void __launch_bounds__(128) kge_span_warp_kernel(ApplyParams P) {
     const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
     const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
     const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
-    const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * blockDim.x) >> 5);
-    for (int h = gw; h < n_heads; h += nw) {
+    for (int h = blockIdx.x; h < n_heads; h += gridDim.x) {
         const int64_t w = P.span_list[h];
         const int32_t key = (int32_t)(P.ks[w * KGE_CH + KGE_CH - 1] >> 32);
-        const int64_t last = span_last_chunk(P, w, key, n_chunks, lane);
-        const int n_ent = (int)(last - w + 1);
-        if (n_ent > KGE_SPAN_WARP_MAX) {
-            if (lane == 0) P.hub_list[atomicAdd(P.span_count + 1, 1)] = (int32_t)w;
-            continue;
-        }
         const RowPtrs r = resolve_row(P, key);
-        float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
-        if constexpr (NCA > 0) {
-            float g[NCA][V], rc[NCA][V], mv[NCA][V], vv[NCA][V];
-            int cc[NCA];
+        // columns owned by this thread in the final combine (at most one vector per thread when K <= 1024)
+        const int c_own = threadIdx.x * V;
+        float rc0[V], mv0[V], vv0[V];
 #pragma unroll
-            for (int i = 0; i < NCA; ++i) {
-                cc[i] = min((lane + 32 * i) * V, K - V);
-#pragma unroll
-                for (int x = 0; x < V; ++x) g[i][x] = mv[i][x] = vv[i][x] = 0.f;
-                ldg_vec<V>(rc[i], r.w + cc[i]);
-            }
-            if (need_m) {
-#pragma unroll
-                for (int i = 0; i < NCA; ++i) ldg_vec<V>(mv[i], r.m + cc[i]);
-            }
-            if (need_v) {
-#pragma unroll
-                for (int i = 0; i < NCA; ++i) ldg_vec<V>(vv[i], r.v + cc[i]);
-            }
-            int e = 0;
-            for (; e + 2 <= n_ent; e += 2) {
-                float t[2][NCA][V];
-                const float* p0 = span_entry(P, w, e, K);
-                const float* p1 = span_entry(P, w, e + 1, K);
-#pragma unroll
-                for (int i = 0; i < NCA; ++i) ldg_vec<V>(t[0][i], p0 + cc[i]);
-#pragma unroll
-                for (int i = 0; i < NCA; ++i) ldg_vec<V>(t[1][i], p1 + cc[i]);
-#pragma unroll
-                for (int q = 0; q < 2; ++q)
-#pragma unroll
-                    for (int i = 0; i < NCA; ++i)
-#pragma unroll
-                        for (int x = 0; x < V; ++x) g[i][x] += t[q][i][x];
-            }
-            if (e < n_ent) {
-                const float* p0 = span_entry(P, w, e, K);
-#pragma unroll
-                for (int i = 0; i < NCA; ++i) {
-                    float t[V];
-                    ldg_vec<V>(t, p0 + cc[i]);
-#pragma unroll
-                    for (int x = 0; x < V; ++x) g[i][x] += t[x];
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < NCA; ++i) {
-                const int c0 = (lane + 32 * i) * V;
-                if (c0 >= K) continue;
-                if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g[i]);
-                if (no_update) continue;
-                opt_math<V>(P, reset, g[i], rc[i], mv[i], vv[i]);
-                if (r.m && P.opt != KGE_OPT_SGD) st_vec<V>(r.m + c0, mv[i]);
-                if (r.v && P.opt == KGE_OPT_ADAM) st_vec<V>(r.v + c0, vv[i]);
-                st_vec<V>(r.w + c0, rc[i]);
-            }
-        } else {
-            for (int c0 = lane * V; c0 < K; c0 += 32 * V) {
-                float g[V], rc[V], mv[V], vv[V];
-#pragma unroll
-                for (int x = 0; x < V; ++x) g[x] = mv[x] = vv[x] = 0.f;
-                ld_vec<V>(rc, r.w + c0);
-                if (need_m) ld_vec<V>(mv, r.m + c0);
-                if (need_v) ld_vec<V>(vv, r.v + c0);
-                for (int e = 0; e < n_ent; ++e) {
-                    float t[V];
-                    ld_vec<V>(t, span_entry(P, w, e, K) + c0);
-#pragma unroll
-                    for (int x = 0; x < V; ++x) g[x] += t[x];
-                }
-                if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g);
-                if (no_update) continue;
-                opt_math<V>(P, reset, g, rc, mv, vv);
-                if (r.m && P.opt != KGE_OPT_SGD) st_vec<V>(r.m + c0, mv);
-                if (r.v && P.opt == KGE_OPT_ADAM) st_vec<V>(r.v + c0, vv);
-                st_vec<V>(r.w + c0, rc);
-            }
+        for (int x = 0; x < V; ++x) rc0[x] = mv0[x] = vv0[x] = 0.f;
+        const bool own_fast = c_own < K && K <= KGE_SPAN_WARPS * 32 * V;
+        if (own_fast) {
+            ld_vec<V>(rc0, r.w + c_own);
+            if (need_m) ld_vec<V>(mv0, r.m + c_own);
+            if (need_v) ld_vec<V>(vv0, r.v + c_own);
         }
-    }
-}
-
-// Level 2b: hub runs.  A fixed grid walks the compacted list of hub run heads; the
-// 16 warps of a CTA add the per-chunk partial rows of one run (warp j takes partials j, j+16, ...),
-// the partial sums are combined through shared memory in warp order (deterministic) and the optimizer
-// is applied by the threads that own the columns.
-#define KGE_SPAN_WARPS 16
-template <int V>
-__global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(ApplyParams P) {
-    extern __shared__ __align__(16) float sred[];  // [KGE_SPAN_WARPS][K]
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int K = P.ent.K;
-    const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
-    const int n_heads = P.span_count[1];
-    const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
-    const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
-    for (int h = blockIdx.x; h < n_heads; h += gridDim.x) {
-        const int64_t w = P.hub_list[h];
-        const int32_t key = (int32_t)(P.ks[w * KGE_CH + KGE_CH - 1] >> 32);
         const int64_t last = span_last_chunk(P, w, key, n_chunks, lane);
         const int64_t n_ent = last - w + 1;
         for (int c0 = lane * V; c0 < K; c0 += 32 * V) {
@@ -545,15 +704,21 @@ __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(App
             st_vec<V>(sred + (size_t)wib * K + c0, g);
         }
         __syncthreads();
-        const RowPtrs r = resolve_row(P, key);
         float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
-        for (int c0 = threadIdx.x * V; c0 < K; c0 += KGE_SPAN_WARPS * 32 * V) {
+        for (int c0 = c_own; c0 < K; c0 += KGE_SPAN_WARPS * 32 * V) {
             float g[V], rc[V], mv[V], vv[V];
 #pragma unroll
-            for (int x = 0; x < V; ++x) g[x] = mv[x] = vv[x] = 0.f;
-            ld_vec<V>(rc, r.w + c0);
-            if (!no_update && !reset && P.opt != KGE_OPT_SGD) ld_vec<V>(mv, r.m + c0);
-            if (!no_update && !reset && P.opt == KGE_OPT_ADAM) ld_vec<V>(vv, r.v + c0);
+            for (int x = 0; x < V; ++x) {
+                g[x] = 0.f;
+                rc[x] = rc0[x];
+                mv[x] = mv0[x];
+                vv[x] = vv0[x];
+            }
+            if (!own_fast) {
+                ld_vec<V>(rc, r.w + c0);
+                if (need_m) ld_vec<V>(mv, r.m + c0);
+                if (need_v) ld_vec<V>(vv, r.v + c0);
+            }
 #pragma unroll
             for (int j = 0; j < KGE_SPAN_WARPS; ++j) {
                 float t0[V];
@@ -617,14 +782,15 @@ static int ensure_train_ws(kge_ctx* ctx, const kge_train_args* a) {
 
 extern "C" int64_t kge_train_grad_floats(int eta, int64_t n_pos, int K) { return gbuf_floats(eta, n_pos, K); }
 
-static int emit_impl(kge_ctx* ctx, const kge_train_args* a, int32_t* keys_out, uint64_t* packed_out, cudaStream_t st) {
+static int emit_impl(kge_ctx* ctx, const kge_train_args* a, int32_t* keys_out, uint64_t* packed_out, cudaStream_t st,
+                     const KgeStepDyn* dyn = nullptr) {
     if (int rc = ensure_train_ws(ctx, a)) return rc;
     int64_t S = (int64_t)(3 + a->eta) * a->n_pos;
     int threads = 256;
     int blocks = (int)std::min<int64_t>((S + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
     kge_emit_kernel<<<blocks, threads, 0, st>>>(a->pos, a->n_pos, a->eta, a->ent.rows, a->side, a->repl, a->keep_subj,
                                                 a->seed, a->step, a->neg_index_base, ctx->repl.as<int32_t>(),
-                                                ctx->keep.as<uint8_t>(), keys_out, packed_out);
+                                                ctx->keep.as<uint8_t>(), keys_out, packed_out, dyn);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -697,12 +863,42 @@ __global__ void kge_select_flag_kernel(const int32_t* __restrict__ keys, int64_t
     }
 }
 
+// KGE_REDUCE_STAGED=1 selects the bulk-copy staged reduction (measured slower than the register path on
+// B200 for every benchmark shape -- the reduction is L2-throughput bound, not latency bound -- so it is
+// off by default and kept for A/B measurements)
+static inline bool reduce_staged_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KGE_REDUCE_STAGED");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
+}
+
 template <int V, int NCA>
 static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st, cudaEvent_t mid) {
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
     dim3 grid((unsigned)((n_chunks + KGE_RA_WARPS - 1) / KGE_RA_WARPS)), block(KGE_RA_WARPS * 32);
     KGE_CUDA_CHECK(cudaMemsetAsync(P.span_count, 0, 2 * sizeof(int32_t), st));
-    if (tmode == 0) kge_reduce_apply_kernel<V, 0, NCA><<<grid, block, 0, st>>>(P);
+    bool staged = false;
+    if constexpr (V == 4 && NCA > 0) {
+        // staged rows need local buffers (bulk copies of peer memory are not used) and 16-byte rows
+        staged = tmode == 0 && reduce_staged_enabled() && P.G.n_ranks == 1 && P.ent.n_shards == 1;
+        if (staged) {
+            const int K = P.ent.K;
+            int l = 4;
+            while (l > 2 && ((size_t)(1 << l)) * K * 4 > 13 * 1024) --l;
+            const size_t smem = (size_t)KGE_RA_WARPS * (1 << l) * K * sizeof(float);
+            static size_t staged_set = 0;
+            if (smem > 48 * 1024 && smem > staged_set) {
+                KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_reduce_apply_staged_kernel<NCA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                staged_set = smem;
+            }
+            kge_reduce_apply_staged_kernel<NCA><<<grid, block, smem, st>>>(P, l);
+        }
+    }
+    if (staged) {
+    } else if (tmode == 0) kge_reduce_apply_kernel<V, 0, NCA><<<grid, block, 0, st>>>(P);
     else if (tmode == 1) kge_reduce_apply_kernel<V, 1, NCA><<<grid, block, 0, st>>>(P);
     else kge_reduce_apply_kernel<V, 2, NCA><<<grid, block, 0, st>>>(P);
     KGE_CUDA_CHECK(cudaGetLastError());
@@ -713,9 +909,7 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
         smem_set = smem;
     }
     if (mid != nullptr) KGE_CUDA_CHECK(cudaEventRecord(mid, st));
-    kge_span_warp_kernel<V, NCA><<<sm_count * 4, 128, 0, st>>>(P);
-    KGE_CUDA_CHECK(cudaGetLastError());
-    kge_span_apply_kernel<V><<<std::min(sm_count, 64), KGE_SPAN_WARPS * 32, smem, st>>>(P);
+    kge_span_apply_kernel<V><<<sm_count, KGE_SPAN_WARPS * 32, smem, st>>>(P);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -753,8 +947,14 @@ static int sort_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* pack
     return 0;
 }
 
+static double adam_lr_t(const kge_train_args* a) {
+    const bool reset = (a->flags & KGE_F_RESET_STATE) != 0;
+    double t = reset ? 1.0 : (double)(a->step < 1 ? 1 : a->step);
+    return (double)a->lr * sqrt(1.0 - pow((double)a->beta2, t)) / (1.0 - pow((double)a->beta1, t));
+}
+
 static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, const kge_table* grads, int64_t row_begin,
-                       int64_t row_end, cudaStream_t st) {
+                       int64_t row_end, cudaStream_t st, const KgeStepDyn* dyn = nullptr) {
     if (n_items == 0) return 0;
     const int K = a->ent.K;
     const int64_t E = a->ent.rows;
@@ -797,8 +997,8 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
     P.dbg_grad_rel = a->dbg_grad_rel;
     const bool reset = (a->flags & KGE_F_RESET_STATE) != 0;
     const bool no_update = (a->flags & KGE_F_NO_UPDATE) != 0;
-    double t = reset ? 1.0 : (double)(a->step < 1 ? 1 : a->step);
-    P.lr_t = (float)((double)a->lr * sqrt(1.0 - pow((double)a->beta2, t)) / (1.0 - pow((double)a->beta1, t)));
+    P.lr_t = (float)adam_lr_t(a);
+    P.dyn = dyn;
     if (!no_update && !reset) {
         if (a->opt == KGE_OPT_ADAM)
             KGE_REQUIRE(P.has_m && P.has_v && a->rel_m && a->rel_v, "kge_train: adam state (m,v) missing");
@@ -892,6 +1092,10 @@ static void timing_collect(kge_ctx* ctx) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1]) == cudaSuccess) ctx->tacc[i] += ms;
     }
+    {   // side stream: end of the radix sort, measured from the end of emit
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->tev[1], ctx->tev[5]) == cudaSuccess) ctx->tacc[4] += ms;
+    }
     ctx->tcount += 1;
     ctx->tpending = false;
 }
@@ -899,18 +1103,18 @@ static void timing_collect(kge_ctx* ctx) {
 extern "C" int kge_ctx_set_timing(kge_ctx* ctx, int on) {
     KGE_REQUIRE(ctx != nullptr, "kge_ctx_set_timing: null ctx");
     if (on && ctx->tev[0] == nullptr)
-        for (int i = 0; i < 5; ++i) KGE_CUDA_CHECK(cudaEventCreate(&ctx->tev[i]));
+        for (int i = 0; i < 6; ++i) KGE_CUDA_CHECK(cudaEventCreate(&ctx->tev[i]));
     timing_collect(ctx);
     ctx->timing = on != 0;
-    for (int i = 0; i < 4; ++i) ctx->tacc[i] = 0;
+    for (int i = 0; i < 5; ++i) ctx->tacc[i] = 0;
     ctx->tcount = 0;
     return 0;
 }
 
-extern "C" int kge_ctx_get_timing(kge_ctx* ctx, float* ms_out4, int* steps_out) {
-    KGE_REQUIRE(ctx != nullptr && ms_out4 != nullptr, "kge_ctx_get_timing: null argument");
+extern "C" int kge_ctx_get_timing(kge_ctx* ctx, float* ms_out5, int* steps_out) {
+    KGE_REQUIRE(ctx != nullptr && ms_out5 != nullptr, "kge_ctx_get_timing: null argument");
     timing_collect(ctx);
-    for (int i = 0; i < 4; ++i) ms_out4[i] = ctx->tcount ? (float)(ctx->tacc[i] / ctx->tcount) : 0.f;
+    for (int i = 0; i < 5; ++i) ms_out5[i] = ctx->tcount ? (float)(ctx->tacc[i] / ctx->tcount) : 0.f;
     if (steps_out) *steps_out = ctx->tcount;
     return 0;
 }
@@ -920,7 +1124,7 @@ extern "C" int kge_ctx_get_timing(kge_ctx* ctx, float* ms_out4, int* steps_out) 
         if (ctx->timing) KGE_CUDA_CHECK(cudaEventRecord(ctx->tev[i], st));  \
     } while (0)
 
-extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* stream) {
+static int train_step_body(kge_ctx* ctx, const kge_train_args* a, void* stream, const KgeStepDyn* dyn) {
     KGE_REQUIRE(ctx != nullptr, "kge_train_step: null ctx");
     if (int rc = validate_train(a)) return rc;
     KGE_REQUIRE(a->ent.n_shards == 1, "kge_train_step is the single-GPU entry; use the phased calls when sharded");
@@ -933,13 +1137,14 @@ extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* strea
     if (int rc = ensure_side_stream(ctx)) return rc;
     if (ctx->timing) timing_collect(ctx);
     KGE_TMARK(0);
-    if (int rc = emit_impl(ctx, a, nullptr, ctx->ks_in.as<uint64_t>(), st)) return rc;
+    if (int rc = emit_impl(ctx, a, nullptr, ctx->ks_in.as<uint64_t>(), st, dyn)) return rc;
     KGE_TMARK(1);
     // fork: the radix sort only needs the keys, so it runs beside the forward/backward kernel
     KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, st));
     KGE_CUDA_CHECK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
     if (int rc = sort_impl(ctx, a, ctx->ks_in.as<uint64_t>(), S, ctx->side)) return rc;
     KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_sorted, ctx->side));
+    if (ctx->timing) KGE_CUDA_CHECK(cudaEventRecord(ctx->tev[5], ctx->side));
     if (int rc = fwd_bwd_impl(ctx, a, ctx->grad_rows.as<float>(), st, ctx->side)) return rc;
     KGE_TMARK(2);
     kge_table g;
@@ -950,12 +1155,91 @@ extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* strea
     g.n_shards = 1;
     g.K = K;
     KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_sorted, 0));
-    if (int rc = reduce_impl(ctx, a, S, &g, 0, a->ent.rows, st)) return rc;
+    if (int rc = reduce_impl(ctx, a, S, &g, 0, a->ent.rows, st, dyn)) return rc;
     KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_loss, 0));  // join
     if (ctx->timing) {
         KGE_CUDA_CHECK(cudaEventRecord(ctx->tev[4], st));
         ctx->tpending = true;
     }
+    return 0;
+}
+
+extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* stream) {
+    return train_step_body(ctx, a, stream, nullptr);
+}
+
+// KGE_GRAPH=0 disables the captured-graph replay of the host-buffer step
+static inline bool train_graph_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KGE_GRAPH");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+// The step as one graph launch.  Everything in `b` except the step counter is part of the key; the
+// first call with a new key runs eagerly (workspace growth, function attributes), the second is
+// captured (the side-stream fork/join included) and instantiated, later ones only replay.
+static int train_step_graphed(kge_ctx* ctx, const kge_train_args* b, cudaStream_t st) {
+    static uint64_t tick = 0;
+    kge_train_args key = *b;
+    key.step = 0;
+    KgeGraphEntry* e = nullptr;
+    for (KgeGraphEntry& g : ctx->graphs)
+        if (g.seen > 0 && g.stream == st && memcmp(&g.key, &key, sizeof(key)) == 0) e = &g;
+    if (e == nullptr) {
+        e = &ctx->graphs[0];
+        for (KgeGraphEntry& g : ctx->graphs)
+            if (g.last_use < e->last_use) e = &g;
+        if (e->exec) {
+            KGE_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            cudaGraphExecDestroy(e->exec);
+        }
+        e->exec = nullptr;
+        e->key = key;
+        e->stream = st;
+        e->seen = 0;
+    }
+    e->last_use = ++tick;
+    e->seen += 1;
+    if (e->seen == 1) return train_step_body(ctx, b, st, nullptr);
+    if (ctx->h_dyn == nullptr) {
+        KGE_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_dyn, sizeof(KgeStepDyn)));
+        if (ctx->d_dyn.reserve(sizeof(KgeStepDyn))) return -2;
+    }
+    // the previous replay has been synchronised by the caller (kge_train_step_host), so the pinned block is free
+    ctx->h_dyn->step = b->step;
+    ctx->h_dyn->lr_t = (float)adam_lr_t(b);
+    if (e->exec != nullptr && e->ws_epoch != g_kge_ws_epoch) {  // a workspace buffer moved since the capture
+        cudaGraphExecDestroy(e->exec);
+        e->exec = nullptr;
+    }
+    if (e->exec == nullptr) {
+        cudaGraph_t graph = nullptr;
+        e->ws_epoch = g_kge_ws_epoch;
+        KGE_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        int rc = 0;
+        if (cudaMemcpyAsync(ctx->d_dyn.p, ctx->h_dyn, sizeof(KgeStepDyn), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -2;
+        if (rc == 0) rc = train_step_body(ctx, b, st, ctx->d_dyn.as<KgeStepDyn>());
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            e->seen = 1;  // stay eager for this key
+            if (rc == 0) kge_set_error("kge_train_step_host: stream capture failed (%s)", cudaGetErrorString(ce));
+            return train_step_body(ctx, b, st, nullptr);
+        }
+        ce = cudaGraphInstantiate(&e->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+            e->exec = nullptr;
+            e->seen = 1;
+            cudaGetLastError();
+            return train_step_body(ctx, b, st, nullptr);
+        }
+    }
+    KGE_CUDA_CHECK(cudaGraphLaunch(e->exec, st));
     return 0;
 }
 
@@ -969,11 +1253,23 @@ extern "C" int kge_train_step_host(kge_ctx* ctx, const kge_train_args* a, const 
         return 0;
     }
     if (ctx->h_pos.reserve((size_t)a->n_pos * 3 * sizeof(int32_t)) || ctx->h_loss.reserve(sizeof(float))) return -2;
+    const bool graphed = train_graph_enabled() && !ctx->timing && a->ent.n_shards == 1;
+    if (graphed) {
+        // the caller's stream may be the legacy default stream, which cannot be captured: the whole call
+        // runs on a stream of the ctx, ordered behind the caller's stream (and synchronised before return)
+        if (ctx->gmain == nullptr) {
+            KGE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->gmain, cudaStreamNonBlocking));
+            KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_gin, cudaEventDisableTiming));
+        }
+        KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_gin, st));
+        KGE_CUDA_CHECK(cudaStreamWaitEvent(ctx->gmain, ctx->ev_gin, 0));
+        st = ctx->gmain;
+    }
     KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pos.p, pos_host, (size_t)a->n_pos * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     kge_train_args b = *a;
     b.pos = ctx->h_pos.as<int32_t>();
     if (b.loss_out == nullptr) b.loss_out = ctx->h_loss.as<float>();
-    if (int rc = kge_train_step(ctx, &b, stream)) return rc;
+    if (int rc = graphed ? train_step_graphed(ctx, &b, st) : train_step_body(ctx, &b, stream, nullptr)) return rc;
     if (loss_host) KGE_CUDA_CHECK(cudaMemcpyAsync(loss_host, b.loss_out, sizeof(float), cudaMemcpyDeviceToHost, st));
     KGE_CUDA_CHECK(cudaStreamSynchronize(st));
     return 0;

@@ -17,6 +17,7 @@
 // rows.  Replaces reference models/EmbeddingModel.py:614-822 (_get_model_loss), losses/*.py and the
 // GradientTape backward of training/adam.py:45-46.
 #pragma once
+#include <cstdlib>
 #include <type_traits>
 
 #include "kge_common.cuh"
@@ -301,6 +302,25 @@ struct FwdBwdParams {
     float* dbg_scores;  // optional [n*(1+eta)]
 };
 
+// shared-memory row loads (the staged rows of the PIPE variant); lanes past the end of the row read
+// the row's last vector like row_load_clamped
+template <int V, int NCH, bool CPLX>
+__device__ __forceinline__ void row_load_smem(Row<V, NCH, CPLX>& r, const float* base, int lane, int nvec, int half) {
+    static_assert(V == 4, "staged rows are 128-bit vectors");
+    const uint32_t b = smem_u32(base);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = min(lane + 32 * i, nvec - 1);
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(r.re[i][0]), "=f"(r.re[i][1]), "=f"(r.re[i][2]), "=f"(r.re[i][3])
+                     : "r"(b + (uint32_t)c * 16u));
+        if constexpr (CPLX)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(r.im[i][0]), "=f"(r.im[i][1]), "=f"(r.im[i][2]), "=f"(r.im[i][3])
+                         : "r"(b + (uint32_t)(half + c * 4) * 4u));
+    }
+}
+
 // SPLIT warps cooperate on one positive (its negatives are dealt round-robin); a CTA is 4 warps.
 // registers of one row per lane; bounds the resident CTAs the compiler is asked to allow
 template <int MODEL, int V, int NCH>
@@ -309,11 +329,31 @@ struct RowRegs {
     static constexpr int min_ctas = value <= 16 ? 3 : (value <= 32 ? 2 : 1);
 };
 
-template <int MODEL, int V, int NCH, int U, int SPLIT>
-__global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_fwd_bwd_kernel(FwdBwdParams P) {
+// PIPE: candidate rows are staged in shared memory by 1-D bulk async copies (TMA unit,
+// cp.async.bulk -> SASS UBLKCP).  Every warp owns a ring of 2^ns_log2 row slots with one mbarrier
+// each: the lane that holds a negative's replacement id issues the copy of that row as soon as its
+// position in the processing order enters the ring window.  Candidates are processed in groups of
+// KGE_FB_G rows that are all resident at once:
+//   pass 1  lane-partial dot products of the G rows, then ONE transposed warp reduction (6 shuffles
+//           for 4 candidates instead of 20) that leaves candidate c's score on the lanes with
+//           (bit4,bit3) == c
+//   loss    exp/log/divide evaluated once per group (each lane for the candidate it holds)
+//   pass 2  the rows are read again from shared memory (no registers held across the reduction) and
+//           folded into the side accumulator with the weight broadcast from the holder lane
+// Local tables only (peer shards keep the register path).
+#define KGE_FB_G 4
+template <int MODEL, int V, int NCH, bool PIPE>
+struct FwdOcc {
+    static constexpr int value = PIPE ? (RowRegs<MODEL, V, NCH>::value <= 16 ? 4 : (RowRegs<MODEL, V, NCH>::value <= 32 ? 2 : 1))
+                                      : RowRegs<MODEL, V, NCH>::min_ctas;
+};
+
+template <int MODEL, int V, int NCH, int U, int SPLIT, bool PIPE>
+__global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge_fwd_bwd_kernel(FwdBwdParams P, int ns_log2) {
     using A = Algebra<MODEL, V, NCH>;
     using R = typename A::R;
     constexpr int PP = 4 / SPLIT;  // positives per CTA
+    constexpr int G = KGE_FB_G;
     extern __shared__ __align__(16) float smem[];
 
     const int lane = threadIdx.x & 31;
@@ -329,13 +369,77 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
     const int eta = P.eta;
     const int loss = P.loss;
 
-    // shared layout: sc[PP][eta] | red[PP][SPLIT][2] | acc[PP][SPLIT-1][2][K]
+    // shared layout: sc[PP][eta] | red[PP][SPLIT][2] | acc[PP][SPLIT-1][2][K] | PIPE: per warp
+    // bars[NS] (8 B each), then ring[NS][K]
     float* sc = smem + (size_t)pl * eta;
     float* red = smem + (size_t)PP * eta + (size_t)pl * SPLIT * 2;
-    float* accs = smem + (((size_t)PP * eta + PP * SPLIT * 2 + 3) & ~(size_t)3) + (size_t)pl * (SPLIT - 1) * 2 * K;
+    const size_t acc_off = (((size_t)PP * eta + PP * SPLIT * 2 + 3) & ~(size_t)3);
+    float* accs = smem + acc_off + (size_t)pl * (SPLIT - 1) * 2 * K;
+
+    const int NS = 1 << ns_log2;
+    uint64_t* bars = nullptr;
+    float* ring = nullptr;
+    const uint32_t row_bytes = (uint32_t)K * 4u;
+    if constexpr (PIPE) {
+        const size_t pipe_off = acc_off + (size_t)PP * (SPLIT - 1) * 2 * K;  // multiple of 4 floats
+        uint64_t* bars0 = reinterpret_cast<uint64_t*>(smem + pipe_off);
+        const size_t rows_off = pipe_off + (size_t)4 * NS * 2;
+        bars = bars0 + (size_t)wib * NS;
+        ring = smem + rows_off + (size_t)wib * NS * K;
+        if (lane == 0) {
+            for (int b = 0; b < NS; ++b) mbar_init(bars + b, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+    }
 
     float* coef = gbuf_coef(P.gbuf, n, K);
     uint8_t* keep_out = gbuf_keep(P.gbuf, eta, n, K);
+
+    // negatives of this warp: j = sub + SPLIT*m, m in [0,cnt)
+    const int cnt = valid ? (eta - sub + SPLIT - 1) / SPLIT : 0;
+
+    // ---- per-batch state of the candidate pipeline (one batch = up to 32 negatives of this warp)
+    int lim = 0, my_idx = 0, my_keep = 0, mypos = 0, n_obj = 0;
+    int64_t my_q = 0;
+    unsigned m_obj = 0, m_sub = 0;
+    bool my_issued = true;
+    uint32_t seq_base = 0;  // ring sequence number of the batch's first position (PIPE)
+    int consumed = 0;       // positions of the batch already consumed (PIPE)
+
+    auto issue_window = [&]() {
+        if constexpr (PIPE) {
+            if (!my_issued && mypos < consumed + NS) {
+                const uint32_t q = seq_base + (uint32_t)mypos;
+                const uint32_t sl = q & (uint32_t)(NS - 1);
+                mbar_expect_tx(bars + sl, row_bytes);
+                bulk_g2s(ring + (size_t)sl * K, table_row(P.ent, my_idx), row_bytes, bars + sl);
+                my_issued = true;
+            }
+        }
+    };
+    // ids of the batch starting at negative m0, processing order (object-side group first), first copies
+    auto begin_batch = [&](int m0) {
+        lim = min(32, cnt - m0);
+        my_idx = 0;
+        my_keep = 0;
+        my_q = 0;
+        if (lane < lim) {
+            my_q = (int64_t)(sub + SPLIT * (m0 + lane)) * n + i;
+            my_idx = P.repl[my_q];
+            my_keep = P.keep[my_q];
+        }
+        m_obj = __ballot_sync(0xffffffffu, lane < lim && my_keep != 0);
+        m_sub = __ballot_sync(0xffffffffu, lane < lim && my_keep == 0);
+        if constexpr (PIPE) {
+            n_obj = __popc(m_obj);
+            const unsigned below = (1u << lane) - 1u;
+            mypos = my_keep ? __popc(m_obj & below) : n_obj + __popc(m_sub & below);
+            my_issued = !(lane < lim);
+            consumed = 0;
+            issue_window();
+        }
+    };
 
     R Qo, Qs, AccO, AccS;
     row_zero(AccO);
@@ -350,6 +454,7 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
         row_load_clamped(s, table_row(P.ent, si), lane, nvec, half);
         row_load_clamped(p, P.rel + (size_t)pi * K, lane, nvec, half);
         row_load_clamped(o, table_row(P.ent, oi), lane, nvec, half);
+        if constexpr (PIPE) begin_batch(0);  // the first candidate rows travel together with s, p, o
         A::queries(s, p, o, Qo, Qs);
         row_mask(Qo, lane, nvec);  // queries are zero past the end of the row: duplicate columns of
         row_mask(Qs, lane, nvec);  // the clamped candidate loads then contribute nothing
@@ -366,25 +471,130 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
     float wsum = 0.f;      // pairwise: number of active hinges
     float zinv = 0.f;      // multiclass: 1 / softmax denominator
 
-    // negatives of this warp: j = sub + SPLIT*m, m in [0,cnt)
-    const int cnt = valid ? (eta - sub + SPLIT - 1) / SPLIT : 0;
-
     // MODE 0: single pass (pairwise / nll).  MODE 1: scores only (multiclass pass 1).
     // MODE 2: backward with the scores in sc[] (multiclass pass 2).
-    auto sweep = [&](auto mode_tag) {
+    // first_ready: the first batch was already begun (PIPE prologue)
+    auto sweep = [&](auto mode_tag, bool first_ready) {
         constexpr int MODE = decltype(mode_tag)::value;
         for (int m0 = 0; m0 < cnt; m0 += 32) {
-            const int lim = min(32, cnt - m0);
-            int my_idx = 0, my_keep = 0;
-            int64_t my_q = 0;
-            if (lane < lim) {
-                my_q = (int64_t)(sub + SPLIT * (m0 + lane)) * n + i;
-                my_idx = P.repl[my_q];
-                my_keep = P.keep[my_q];
-            }
+            if (!(first_ready && m0 == 0)) begin_batch(m0);
             float my_c = 0.f, my_sn = 0.f;
-            // the negatives of this round, grouped by corrupted side so that the query (Qo / Qs) and the
-            // accumulator (AccO / AccS) are compile-time choices inside each group
+            // ---- PIPE: groups of G resident rows, transposed reduction, loss once per group
+            [[maybe_unused]] int inv = 0;       // MODE 2: lane x holds the batch lane that owns position x
+            [[maybe_unused]] float w_own = 0.f;  // MODE 2: weight of this lane's own negative
+            if constexpr (PIPE && MODE == 2) {
+                const int x = lane;
+                inv = x < n_obj ? (int)__fns(m_obj, 0, x + 1) : (int)__fns(m_sub, 0, x - n_obj + 1);
+                if (lane < lim) {
+                    // losses/nll_multiclass.py:70-81 : softmax weight, zero outside the clip range
+                    const float sn = sc[sub + SPLIT * (m0 + lane)];
+                    const bool in = (sn >= -75.f) && (sn <= 75.f);
+                    w_own = in ? expf(sn) * zinv : 0.f;
+                    my_c = A::coefficient(w_own, sn, P.scale);
+                    my_sn = sn;
+                }
+            }
+            auto group_pipe = [&](auto obj_tag, int x_begin, int x_end) {
+                constexpr bool OBJ = decltype(obj_tag)::value;
+                const R& Q = OBJ ? Qo : Qs;
+                R& Acc = OBJ ? AccO : AccS;
+                const int cidx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // candidate this lane holds after the reduction
+                for (int x0 = x_begin; x0 < x_end; x0 += G) {
+                    const int g = min(G, x_end - x0);
+                    float tot = 0.f;
+                    if constexpr (MODE != 2) {
+                        float pv[G];
+#pragma unroll
+                        for (int c = 0; c < G; ++c) {
+                            pv[c] = 0.f;
+                            if (c < g) {
+                                const uint32_t q = seq_base + (uint32_t)(x0 + c);
+                                const uint32_t sl = q & (uint32_t)(NS - 1);
+                                mbar_wait(bars + sl, (q >> ns_log2) & 1u);
+                                R r;
+                                row_load_smem(r, ring + (size_t)sl * K, lane, nvec, half);
+                                pv[c] = A::partial(Q, r, msk);
+                            }
+                        }
+                        // transposed reduction: 2 + 1 exchange steps, then a butterfly over the low 3 bits
+                        const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+                        float k0 = hi16 ? pv[2] : pv[0], k1 = hi16 ? pv[3] : pv[1];
+                        k0 += __shfl_xor_sync(0xffffffffu, hi16 ? pv[0] : pv[2], 16);
+                        k1 += __shfl_xor_sync(0xffffffffu, hi16 ? pv[1] : pv[3], 16);
+                        tot = (hi8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                    }
+                    const bool has = cidx < g;
+                    float sn = 0.f, w = 0.f;
+                    if constexpr (MODE != 2) sn = A::finish(tot, P.scale);
+                    if constexpr (MODE == 0) {
+                        float term;
+                        if (loss == KGE_LOSS_PAIRWISE) {
+                            // losses/pairwise.py:69 ; tf.maximum passes the gradient when t >= 0
+                            const float tt = margin - spos + sn;
+                            term = fmaxf(tt, 0.f);
+                            w = (tt >= 0.f) ? 1.f : 0.f;
+                        } else {
+                            // losses/nll.py:55-59 : log(1+exp(clip(neg)))
+                            const float e = expf(clip75(sn));
+                            term = logf(1.f + e);
+                            const bool in = (sn >= -75.f) && (sn <= 75.f);
+                            w = in ? e / (1.f + e) : 0.f;
+                        }
+                        if (!has) {
+                            w = 0.f;
+                            term = 0.f;
+                        }
+                        if ((lane & 7) == 0) {  // one lane per candidate feeds the (lane-partial) loss sums
+                            loss_acc += term;
+                            if (loss == KGE_LOSS_PAIRWISE) wsum += w;
+                        }
+                    }
+                    if constexpr (MODE != 2) {
+                        // hand score / coefficient to the lane that owns the negative (it stores them)
+                        const int rel = mypos - x0;
+                        const bool mine_in = lane < lim && rel >= 0 && rel < g;
+                        const int holder = (((rel >> 1) & 1) * 16 + (rel & 1) * 8) & 31;
+                        const float cv = __shfl_sync(0xffffffffu, A::coefficient(w, sn, P.scale), holder);
+                        const float sv = __shfl_sync(0xffffffffu, sn, holder);
+                        if (mine_in) {
+                            my_c = cv;
+                            my_sn = sv;
+                        }
+                    }
+                    if constexpr (MODE != 1) {
+#pragma unroll
+                        for (int c = 0; c < G; ++c) {
+                            if (c < g) {
+                                float wc, sc_c = 0.f;
+                                if constexpr (MODE == 2) {
+                                    const int own = __shfl_sync(0xffffffffu, inv, (x0 + c) & 31);
+                                    wc = __shfl_sync(0xffffffffu, w_own, own);
+                                    if constexpr (MODEL == 1) sc_c = __shfl_sync(0xffffffffu, my_sn, own);
+                                } else {
+                                    const int holder = (c >> 1) * 16 + (c & 1) * 8;
+                                    wc = __shfl_sync(0xffffffffu, w, holder);
+                                    if constexpr (MODEL == 1) sc_c = __shfl_sync(0xffffffffu, sn, holder);
+                                }
+                                const uint32_t q = seq_base + (uint32_t)(x0 + c);
+                                const uint32_t sl = q & (uint32_t)(NS - 1);
+                                if constexpr (MODE == 2) mbar_wait(bars + sl, (q >> ns_log2) & 1u);
+                                R r;
+                                row_load_smem(r, ring + (size_t)sl * K, lane, nvec, half);
+                                A::accumulate(Q, r, OBJ, wc, sc_c, P.scale, Acc);
+                            }
+                        }
+                    }
+                    // the group's rows are no longer needed: their ring slots take the next positions
+                    __syncwarp();
+                    consumed += g;
+                    issue_window();
+                }
+            };
+            // ---- register path: the negatives of this round, grouped by corrupted side so that the query
+            // (Qo / Qs) and the accumulator (AccO / AccS) are compile-time choices inside each group
             auto group = [&](auto obj_tag, unsigned todo) {
                 constexpr bool OBJ = decltype(obj_tag)::value;
                 const R& Q = OBJ ? Qo : Qs;
@@ -446,10 +656,17 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
                     }
                 }
             };
-            const unsigned m_obj = __ballot_sync(0xffffffffu, lane < lim && my_keep != 0);
-            const unsigned m_sub = __ballot_sync(0xffffffffu, lane < lim && my_keep == 0);
-            group(std::true_type{}, m_obj);
-            group(std::false_type{}, m_sub);
+            if constexpr (PIPE) {
+                group_pipe(std::true_type{}, 0, n_obj);
+                group_pipe(std::false_type{}, n_obj, lim);
+                seq_base += (uint32_t)lim;
+                if constexpr (MODE == 1) {
+                    if (lane < lim) sc[sub + SPLIT * (m0 + lane)] = my_sn;
+                }
+            } else {
+                group(std::true_type{}, m_obj);
+                group(std::false_type{}, m_sub);
+            }
             if constexpr (MODE != 1) {
                 if (lane < lim) {
                     coef[my_q] = my_c;
@@ -461,7 +678,7 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
     };
 
     if (loss == KGE_LOSS_MULTICLASS_NLL) {
-        sweep(std::integral_constant<int, 1>{});
+        sweep(std::integral_constant<int, 1>{}, PIPE);
         __syncthreads();
         float zpart = 0.f;
         if (valid)
@@ -470,9 +687,13 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
         const float z = warp_sum(zpart) + pe;
         zinv = 1.f / z;
         loss_acc = -logf(pe / z);
-        sweep(std::integral_constant<int, 2>{});
+        sweep(std::integral_constant<int, 2>{}, false);
     } else {
-        sweep(std::integral_constant<int, 0>{});
+        sweep(std::integral_constant<int, 0>{}, PIPE);
+        if constexpr (PIPE) {  // the staged path keeps lane-partial loss sums
+            loss_acc = warp_sum(loss_acc);
+            wsum = warp_sum(wsum);
+        }
     }
 
     if constexpr (SPLIT > 1) {
@@ -514,9 +735,9 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
         wpos = pos_in ? -(1.f - expf(cpos) * zinv) : 0.f;
     }
 
-    float* G = P.gbuf;
-    row_store(G + (size_t)(3 * n + i) * K, Qo, lane, nvec, half);
-    row_store(G + (size_t)(4 * n + i) * K, Qs, lane, nvec, half);
+    float* GB = P.gbuf;
+    row_store(GB + (size_t)(3 * n + i) * K, Qo, lane, nvec, half);
+    row_store(GB + (size_t)(4 * n + i) * K, Qs, lane, nvec, half);
     {
         // the positive itself: an object-side candidate with r = o and weight dL/dpos
         R s, p, o, gs, gp, go;
@@ -526,9 +747,9 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
         row_load_clamped(s, table_row(P.ent, si), lane, nvec, half);
         row_load_clamped(p, P.rel + (size_t)pi * K, lane, nvec, half);
         A::fold(s, p, o, AccO, AccS, gs, gp, go);
-        row_store(G + (size_t)i * K, gs, lane, nvec, half);
-        row_store(G + (size_t)(n + i) * K, go, lane, nvec, half);
-        row_store(G + (size_t)(2 * n + i) * K, gp, lane, nvec, half);
+        row_store(GB + (size_t)i * K, gs, lane, nvec, half);
+        row_store(GB + (size_t)(n + i) * K, go, lane, nvec, half);
+        row_store(GB + (size_t)(2 * n + i) * K, gp, lane, nvec, half);
     }
     if (lane == 0) {
         P.loss_part[i] = loss_acc;
@@ -536,46 +757,90 @@ __global__ void __launch_bounds__(128, (RowRegs<MODEL, V, NCH>::min_ctas)) kge_f
     }
 }
 
-static inline size_t fwd_bwd_smem(int split, int eta, int K) {
+static inline int fwd_bwd_max_ctas() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KGE_FWD_MAXCTAS");
+        v = (e != nullptr && e[0] >= '1' && e[0] <= '8') ? (e[0] - '0') : 3;
+    }
+    return v;
+}
+
+// ring slots per warp (log2) of the PIPE variant: 16 when four 4-warp CTAs still fit one SM, else 8
+// (two groups of KGE_FB_G rows: one being processed, one in flight)
+static inline int fwd_bwd_ns_log2(int K) {
+    const size_t row = (size_t)K * 4;
+    return (16 * row * 4 <= 54 * 1024) ? 4 : 3;
+}
+
+static inline size_t fwd_bwd_smem(int split, int eta, int K, bool pipe, int ns_log2) {
     const int pp = 4 / split;
     size_t fl = (((size_t)pp * eta + pp * split * 2 + 3) & ~(size_t)3) + (size_t)pp * (split - 1) * 2 * K;
+    if (pipe) {
+        const int ns = 1 << ns_log2;
+        fl += (size_t)4 * ns * 2 + (size_t)4 * ns * K;
+    }
     return fl * sizeof(float);
 }
 
 template <int MODEL, int V, int NCH, int U>
-static int launch_fwd_bwd_split(int split, const FwdBwdParams& P, cudaStream_t st) {
+static int launch_fwd_bwd_split(int split, bool pipe, const FwdBwdParams& P, cudaStream_t st) {
     const int K = P.ent.K;
-    auto go = [&](auto kern, int sp) -> int {
+    const int ns_log2 = fwd_bwd_ns_log2(K);
+    auto go = [&](auto kern, int sp, bool pp_) -> int {
         const int pp = 4 / sp;
-        size_t smem = fwd_bwd_smem(sp, P.eta, K);
+        size_t smem = fwd_bwd_smem(sp, P.eta, K, pp_, ns_log2);
+        if (pp_) {
+            // leave room on every SM for the CTAs of the radix sort that runs beside this kernel on the
+            // side stream: at most `m` resident CTAs of this kernel (KGE_FWD_MAXCTAS, default 3)
+            const int m = fwd_bwd_max_ctas();
+            const size_t floor_bytes = 233472 / (size_t)(m + 1) - 1024 + 16;
+            if (smem < floor_bytes) smem = floor_bytes;
+        }
+        KGE_REQUIRE(smem <= 220 * 1024, "kge_train: embedding size %d needs %zu bytes of shared memory", K, smem);
         if (smem > 48 * 1024) KGE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)((P.n + pp - 1) / pp)), block(128);
-        kern<<<grid, block, smem, st>>>(P);
+        kern<<<grid, block, smem, st>>>(P, ns_log2);
         KGE_CUDA_CHECK(cudaGetLastError());
         return 0;
     };
     if constexpr (V == 4 && NCH <= 4) {
-        if (split >= 4) return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 4>, 4);
-        if (split == 2) return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 2>, 2);
+        if (pipe) {
+            if (split >= 4) return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 4, true>, 4, true);
+            if (split == 2) return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 2, true>, 2, true);
+            return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 1, true>, 1, true);
+        }
+        if (split >= 4) return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 4, false>, 4, false);
+        if (split == 2) return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 2, false>, 2, false);
     }
-    return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 1>, 1);
+    return go(kge_fwd_bwd_kernel<MODEL, V, NCH, U, 1, false>, 1, false);
 }
 
 template <int MODEL, int V>
-static int launch_fwd_bwd_nch(int nch, int split, const FwdBwdParams& P, cudaStream_t st) {
+static int launch_fwd_bwd_nch(int nch, int split, bool pipe, const FwdBwdParams& P, cudaStream_t st) {
     constexpr bool C = (MODEL == 3);
     // U candidate rows in flight per warp: ~64 registers of row data
     switch (nch) {
-        case 1: return launch_fwd_bwd_split<MODEL, V, 1, (C ? 8 : 8)>(split, P, st);
-        case 2: return launch_fwd_bwd_split<MODEL, V, 2, (C ? 2 : 4)>(split, P, st);
+        case 1: return launch_fwd_bwd_split<MODEL, V, 1, (C ? 8 : 8)>(split, pipe, P, st);
+        case 2: return launch_fwd_bwd_split<MODEL, V, 2, (C ? 2 : 4)>(split, pipe, P, st);
         case 3:
-        case 4: return launch_fwd_bwd_split<MODEL, V, 4, (C ? 2 : 4)>(split, P, st);
+        case 4: return launch_fwd_bwd_split<MODEL, V, 4, (C ? 2 : 4)>(split, pipe, P, st);
         case 5:
         case 6:
         case 7:
-        case 8: return launch_fwd_bwd_split<MODEL, V, 8, (C ? 1 : 2)>(split, P, st);
+        case 8: return launch_fwd_bwd_split<MODEL, V, 8, (C ? 1 : 2)>(split, false, P, st);
         default: kge_set_error("kge_train: embedding size too large for the fused kernel (chunks/lane=%d)", nch); return -1;
     }
+}
+
+// KGE_FWD_PIPE=0 forces the register path (A/B measurements)
+static inline bool fwd_bwd_pipe_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KGE_FWD_PIPE");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
 }
 
 template <int MODEL>
@@ -589,9 +854,11 @@ static int launch_fwd_bwd_model(const FwdBwdParams& P, int sm_count, cudaStream_
     if (P.n * 2 < want && P.eta >= 16) split = 4;
     if (width % 4 == 0) {
         int nvec = width / 4;
-        return launch_fwd_bwd_nch<MODEL, 4>((nvec + 31) / 32, split, P, st);
+        // staged (bulk-copy) rows need 16-byte row pitch and local memory
+        const bool pipe = fwd_bwd_pipe_enabled() && P.ent.n_shards == 1 && (P.ent.K % 4 == 0);
+        return launch_fwd_bwd_nch<MODEL, 4>((nvec + 31) / 32, split, pipe, P, st);
     }
-    return launch_fwd_bwd_nch<MODEL, 1>((width + 31) / 32, 1, P, st);
+    return launch_fwd_bwd_nch<MODEL, 1>((width + 31) / 32, 1, false, P, st);
 }
 
 // one translation unit per model (parallel compilation): kge_train_fwd_m{0,1,2,3}.cu

@@ -112,10 +112,10 @@ class Engine:
 
     def get_timing(self):
         """average ms per step of the train-step phases since set_timing(True)"""
-        out = (C.c_float * 4)()
+        out = (C.c_float * 5)()
         n = C.c_int()
         check(self.lib.kge_ctx_get_timing(self._h, out, C.byref(n)))
-        return dict(zip(("emit", "fwd_bwd", "reduce_apply", "spans"), [float(x) for x in out])), int(n.value)
+        return dict(zip(("emit", "fwd_bwd", "reduce_apply", "spans", "sort_after_emit"), [float(x) for x in out])), int(n.value)
 
     def workspace_bytes(self) -> int:
         return int(self.lib.kge_ctx_workspace_bytes(self._h))

@@ -99,9 +99,10 @@ int kge_ctx_create(int device, kge_ctx** out);
 int kge_ctx_destroy(kge_ctx* ctx);
 /* Bench instrumentation: when on, kge_train_step brackets its phases with CUDA events on the caller's
  * stream; kge_ctx_get_timing returns the average ms per step of {emit, fwd_bwd, sort-wait + reduce_apply,
- * span/hub reduction} since timing was switched on (synchronises). */
+ * span/hub reduction, end of the side-stream radix sort measured from the end of emit} since timing was
+ * switched on (synchronises). */
 int kge_ctx_set_timing(kge_ctx* ctx, int on);
-int kge_ctx_get_timing(kge_ctx* ctx, float* ms_out4, int* steps_out);
+int kge_ctx_get_timing(kge_ctx* ctx, float* ms_out5, int* steps_out);
 /* bytes of device workspace currently held by the ctx */
 int64_t kge_ctx_workspace_bytes(kge_ctx* ctx);
 

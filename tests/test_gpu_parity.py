@@ -160,6 +160,60 @@ def test_train_step_vs_oracle_bench_shapes(engine, model, loss, k, eta):
         _close(r["g_rel"], o["grad_rel"])
 
 
+@pytest.mark.parametrize("E,n,eta", [(12, 300, 6), (40, 257, 20), (700, 64, 3)])
+def test_hub_rows_long_and_short_runs(engine, E, n, eta):
+    """Few entities, many slots: sorted runs of one row span many 16-slot chunks (hub path), two chunks
+    (finished by the run-head warp) or one; the summed gradients and the update must match the oracle."""
+    from emgraph_b200 import _lib
+    rng = np.random.default_rng(E)
+    R, k, model = 3, 24, "ComplEx"
+    K = ko.internal_k(model, k)
+    ent = rng.uniform(-0.4, 0.4, size=(E, K)).astype(np.float32)
+    rel = rng.uniform(-0.4, 0.4, size=(R, K)).astype(np.float32)
+    pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+    keep = rng.integers(0, 2, n * eta).astype(np.uint8)
+    repl = rng.integers(0, E, n * eta).astype(np.int32)
+    r = run_step(engine, model, k, "nll", eta, ent, rel, pos, keep, repl, opt="sgd", lr=1e-2, flags=_lib.F_RESET_STATE)
+    o = ko.train_step(model, k, "nll", eta, ent, rel, pos, keep, repl, opt="sgd", lr=1e-2, dtype=np.float64)
+    _close(r["g_ent"], o["grad_ent"])
+    _close(r["g_rel"], o["grad_rel"])
+    np.testing.assert_allclose(r["ent"], o["ent_new"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r["rel"], o["rel_new"], rtol=1e-5, atol=1e-6)
+
+
+def test_host_step_graph_replay_matches_device_step(engine):
+    """kge_train_step_host (eager first call, then a captured CUDA graph replayed with a fresh step
+    counter) must leave the same parameters and losses as the device-resident step, bit for bit."""
+    from emgraph_b200 import models
+    rng = np.random.default_rng(3)
+    E, R, k, eta, n = 900, 9, 32, 8, 512
+    X = np.stack([rng.integers(0, E, 4 * n), rng.integers(0, R, 4 * n), rng.integers(0, E, 4 * n)], 1).astype(np.int32)
+    ent0 = rng.uniform(-0.3, 0.3, size=(E, 2 * k)).astype(np.float32)
+    rel0 = rng.uniform(-0.3, 0.3, size=(R, 2 * k)).astype(np.float32)
+    out = {}
+    for mode in ("device", "host"):
+        m = models.ComplEx(k=k, eta=eta, epochs=1, batches_count=4, seed=5, optimizer="adam", optimizer_params={"lr": 1e-2},
+                           loss="nll", initializer="constant", initializer_params={"entity": ent0, "relation": rel0})
+        f = m._fit_prepare(E, R)
+        losses = []
+        Xd = torch.from_numpy(X).cuda()
+        Xh = torch.from_numpy(X).pin_memory()
+        for step in range(6):
+            lo, hi = (step % 4) * n, (step % 4 + 1) * n
+            if mode == "device":
+                m._fit_step_device(Xd[lo:hi])
+                torch.cuda.synchronize()
+                losses.append(float(f["loss_dev"].item()))
+            else:
+                losses.append(m._fit_step_host(Xh[lo:hi]))
+        torch.cuda.synchronize()
+        out[mode] = (f["ent"].cpu().numpy(), f["rel"].cpu().numpy(), np.asarray(losses))
+    np.testing.assert_array_equal(out["device"][0], out["host"][0])
+    np.testing.assert_array_equal(out["device"][1], out["host"][1])
+    np.testing.assert_array_equal(out["device"][2], out["host"][2])
+    assert np.all(np.isfinite(out["host"][2])) and out["host"][2][-1] < out["host"][2][0]
+
+
 def test_in_kernel_corruptions_are_uniform_and_reproducible(engine):
     from emgraph_b200 import _lib
     E, R, k, eta, n = 1000, 5, 8, 16, 4096
