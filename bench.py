@@ -502,25 +502,29 @@ def multi_gpu_main(args, w, rank, world):
     assert math.isfinite(last), "training diverged in the benchmark"
     clocks = sampler.stop()
 
-    # roofline of the per-rank forward/backward kernel (gathers cross NVLink for (world-1)/world of the rows)
-    a = eng.train_args(ent=sk.ent_table, rel=sk.rel, pos=Xd[:B], loss_out=sk.loss_dev, step=sk.step + 1, **sk.kw, **sk._state_tables())
-    eng.train_emit(a, sk.keys_local)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier()
-    e0.record()
-    for _ in range(5):
-        eng.train_fwd_bwd(a, sk.gbuf.tensor)
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    t_fb = e0.elapsed_time(e1) / 5
-    bytes_fb = ((3 + eta) * 4 * K + 5 * 4 * K + 5 * eta) * B
-    nv_bytes = (3 + eta) * 4 * K * B * (world - 1) / world
-    ach = bytes_fb / (t_fb * 1e-3) / 1e9
-    roofline = {"bound": "nvlink" if world > 1 else "hbm", "kernel": "kge_fwd_bwd_kernel (peer gathers)", "achieved": nv_bytes / (t_fb * 1e-3) / 1e9,
+    # per-phase time inside the real step (CUDA events on the launching stream, L2 flushed, max over ranks)
+    sk.timing = True
+    for s in range(min(steps, 10)):
+        flush.fill_(float(s))
+        lo, hi = my_batch(it)
+        sk.train_step(Xd[lo:hi])
+        it += 1
+    ph = sk.phase_times()
+    sk.timing = False
+    names = sorted(ph)
+    pt = torch.tensor([ph[k_] for k_ in names], device=dev)
+    dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+    ph = {k_: float(v) for k_, v in zip(names, pt.tolist())}
+    # roofline of the exchange: rows pushed to the other ranks cross NVLink once ((world-1)/world of the
+    # entity slots), plus the all-gathered [Qo|Qs|coef|keep] tails
+    nv_bytes = (2 + eta) * 4 * K * B * (world - 1) / world
+    t_push = ph.get("push", 0.0) + ph.get("push_barrier", 0.0)
+    roofline = {"bound": "nvlink", "kernel": "kge_push_rows_kernel (owner-side row push, peer stores)",
+                "achieved": nv_bytes / (max(t_push, 1e-6) * 1e-3) / 1e9,
                 "peak": 770.0, "unit": "GB/s per direction per GPU (measured peer copy, B200_PROFILING.md)",
-                "frac": nv_bytes / (t_fb * 1e-3) / 1e9 / 770.0, "traffic": None, "kernel_ms": t_fb,
-                "algorithmic_bytes_per_launch": bytes_fb, "nvlink_bytes_per_launch": nv_bytes, "local_GBps": ach}
+                "frac": nv_bytes / (max(t_push, 1e-6) * 1e-3) / 1e9 / 770.0, "traffic": None, "kernel_ms": t_push,
+                "algorithmic_bytes_per_launch": nv_bytes, "phases_ms_max_over_ranks": ph,
+                "tails_allgather_bytes": (world - 1) * sk.tail_stride * 4}
 
     line = {
         "metric": TRAIN_METRIC, "value": value, "unit": "triples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -529,7 +533,7 @@ def multi_gpu_main(args, w, rank, world):
         "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "batch_positives_per_gpu": B, "global_batch": B * world, "eta": eta,
                    "E": E, "R": R, "K": K, "entity_popularity": "uniform" if args.uniform else "zipf(1.0)",
                    "optimizer": "stateful sparse " + w["opt"], "l2": "flushed before every timed step (%d MiB write)" % (L2_FLUSH_BYTES >> 20),
-                   "parallelism": "dp%d, entity table + optimizer state row-sharded, peer-memory gathers" % world},
+                   "parallelism": "dp%d, entity table + optimizer state row-sharded, owner-push row exchange over peer memory" % world},
         "e2e": {"value": steps * triples_per_step / t_e2e, "unit": "triples/s", "h2d_bytes_per_step": B * 12 * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * t_e2e / steps, "api": "ShardedKGE.train_step (host batch, loss read back)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,

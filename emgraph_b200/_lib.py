@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkge_b200.so")
 
 KGE_MAX_SHARDS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 MODEL_IDS = {"TransE": 0, "TransE_L2": 1, "DistMult": 2, "ComplEx": 3, "HolE": 4}
 LOSS_IDS = {"pairwise": 0, "nll": 1, "multiclass_nll": 2}
@@ -45,6 +45,7 @@ class KgeTrainArgs(C.Structure):
         ("pos", C.c_void_p), ("n_pos", C.c_int64),
         ("repl", C.c_void_p), ("keep_subj", C.c_void_p),
         ("loss_out", C.c_void_p), ("dbg_scores", C.c_void_p), ("dbg_grad_ent", C.c_void_p), ("dbg_grad_rel", C.c_void_p),
+        ("stage", C.c_void_p), ("grad_tails", C.c_void_p), ("grad_tail_stride", C.c_int64),
     ]
 
 
@@ -55,6 +56,8 @@ SYMBOLS = {
     "kge_last_error": (C.c_char_p, []),
     "kge_has_tensor_core_rank": (_I, []),
     "kge_train_grad_floats": (_L, [_I, _L, _I]),
+    "kge_train_grad_head_floats": (_L, [_I, _L, _I]),
+    "kge_train_push_rows": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _L, C.POINTER(KgeTable), _L, _L, _P]),
     "kge_ctx_create": (_I, [_I, C.POINTER(_P)]),
     "kge_ctx_destroy": (_I, [_P]),
     "kge_ctx_workspace_bytes": (_L, [_P]),

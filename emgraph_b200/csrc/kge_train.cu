@@ -88,6 +88,8 @@ __global__ void kge_loss_reduce_kernel(const float* __restrict__ part, int64_t n
 
 struct GradView {
     float*  base[KGE_MAX_SHARDS];  // rank r's gradient buffer (local or peer mapping)
+    float*  tail[KGE_MAX_SHARDS];  // base to address rank r's [Qo|Qs|coef|keep] tail with the same offsets:
+                                   // == base[r], or a local all-gathered copy minus the head size
     int64_t S;                     // slots per rank
     int64_t n;                     // positives per rank
     int     eta, K, n_ranks;
@@ -128,6 +130,7 @@ __device__ __forceinline__ SlotMeta decode_slot(const GradView& G, int32_t slot)
         t -= (int64_t)rr * G.S;
     }
     float* base = G.base[rr];
+    float* tbase = G.tail[rr];
     const int64_t n = G.n;
     SlotMeta m;
     m.c = 1.f;
@@ -137,10 +140,10 @@ __device__ __forceinline__ SlotMeta decode_slot(const GradView& G, int32_t slot)
     } else if (t < 2 * n + (int64_t)G.eta * n) {
         const int64_t q = t - 2 * n;
         const int64_t i = q % n;
-        const float* coef = gbuf_coef(base, n, G.K);
-        const uint8_t* keep = gbuf_keep(base, G.eta, n, G.K);
+        const float* coef = gbuf_coef(tbase, n, G.K);
+        const uint8_t* keep = gbuf_keep(tbase, G.eta, n, G.K);
         m.c = coef[q];
-        m.row = base + ((keep[q] ? 3 : 4) * n + i) * G.K;
+        m.row = tbase + ((keep[q] ? 3 : 4) * n + i) * G.K;
         m.mode = 1;
     } else {
         m.row = base + (2 * n + (t - 2 * n - (int64_t)G.eta * n)) * G.K;
@@ -781,6 +784,7 @@ static int ensure_train_ws(kge_ctx* ctx, const kge_train_args* a) {
 }
 
 extern "C" int64_t kge_train_grad_floats(int eta, int64_t n_pos, int K) { return gbuf_floats(eta, n_pos, K); }
+extern "C" int64_t kge_train_grad_head_floats(int eta, int64_t n_pos, int K) { (void)eta; return 3 * n_pos * (int64_t)K; }
 
 static int emit_impl(kge_ctx* ctx, const kge_train_args* a, int32_t* keys_out, uint64_t* packed_out, cudaStream_t st,
                      const KgeStepDyn* dyn = nullptr) {
@@ -827,6 +831,7 @@ static int fwd_bwd_impl(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, 
     P.gbuf = grad_buf;
     P.loss_part = ctx->loss_part.as<float>();
     P.dbg_scores = a->dbg_scores;
+    P.stage = a->stage;
     int rc;
     switch (a->model) {
         case KGE_TRANSE_L1: rc = kge_launch_fwd_bwd_m0(P, ctx->sm_count, st); break;
@@ -851,6 +856,88 @@ extern "C" int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* g
     KGE_REQUIRE(ctx != nullptr, "kge_train_fwd_bwd: null ctx");
     if (int rc = validate_train(a)) return rc;
     return fwd_bwd_impl(ctx, a, grad_buf, (cudaStream_t)stream, nullptr);
+}
+
+// Owner-side push (row-sharded multi-GPU): one warp per slot of the all-gathered keys; slots whose row
+// this rank owns are copied into the staging buffer of the rank whose batch holds the slot.  The local
+// shard is read at random (fast locally), the peer is written with contiguous 1-row stores.
+template <int V>
+__global__ void __launch_bounds__(256) kge_push_rows_kernel(const int32_t* __restrict__ keys, int64_t n_keys, int64_t S, int64_t ent_slots,
+                                                            const float* __restrict__ shard, int64_t row_begin, int64_t row_end, int K,
+                                                            TableView stage) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nvec = K / V;
+    // every lane tests one slot; owned slots are then copied by the whole warp, two rows in flight
+    for (int64_t t0 = warp * 32; t0 < n_keys; t0 += nwarps * 32) {
+        const int64_t t = t0 + lane;
+        int32_t key = -1;
+        int rr = 0;
+        int64_t tl = 0;
+        if (t < n_keys) {
+            rr = (int)(t / S);
+            tl = t - (int64_t)rr * S;
+            if (tl < ent_slots) key = keys[t];
+        }
+        unsigned own = __ballot_sync(0xffffffffu, key >= row_begin && key < row_end);
+        while (own) {
+            const int l0 = __ffs(own) - 1;
+            own &= own - 1;
+            const int l1 = own ? __ffs(own) - 1 : -1;
+            if (l1 >= 0) own &= own - 1;
+            const int32_t k0 = __shfl_sync(0xffffffffu, key, l0);
+            const int r0 = __shfl_sync(0xffffffffu, rr, l0);
+            const int64_t s0 = __shfl_sync(0xffffffffu, tl, l0);
+            const int32_t k1 = __shfl_sync(0xffffffffu, key, max(l1, 0));
+            const int r1 = __shfl_sync(0xffffffffu, rr, max(l1, 0));
+            const int64_t s1 = __shfl_sync(0xffffffffu, tl, max(l1, 0));
+            const float* a = shard + (int64_t)(k0 - row_begin) * K;
+            const float* b = shard + (int64_t)(k1 - row_begin) * K;
+            float* da = stage.shard[r0] + s0 * K;
+            float* db = stage.shard[r1] + s1 * K;
+            for (int c = lane; c < nvec; c += 64) {
+                float va[V], vb[V], vc[V], vd[V];
+                const bool two = c + 32 < nvec;
+                ld_vec<V>(va, a + (size_t)c * V);
+                if (two) ld_vec<V>(vc, a + (size_t)(c + 32) * V);
+                if (l1 >= 0) {
+                    ld_vec<V>(vb, b + (size_t)c * V);
+                    if (two) ld_vec<V>(vd, b + (size_t)(c + 32) * V);
+                }
+                st_vec<V>(da + (size_t)c * V, va);
+                if (two) st_vec<V>(da + (size_t)(c + 32) * V, vc);
+                if (l1 >= 0) {
+                    st_vec<V>(db + (size_t)c * V, vb);
+                    if (two) st_vec<V>(db + (size_t)(c + 32) * V, vd);
+                }
+            }
+        }
+    }
+}
+
+extern "C" int kge_train_push_rows(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, int64_t n_keys,
+                                   const kge_table* stage, int64_t row_begin, int64_t row_end, void* stream) {
+    KGE_REQUIRE(ctx != nullptr, "kge_train_push_rows: null ctx");
+    if (int rc = validate_train(a)) return rc;
+    KGE_REQUIRE(stage != nullptr && keys_all != nullptr, "kge_train_push_rows: missing keys/stage");
+    if (n_keys == 0 || row_end <= row_begin) return 0;
+    const int K = a->ent.K;
+    const int64_t S = (int64_t)(3 + a->eta) * a->n_pos, ent_slots = (int64_t)(2 + a->eta) * a->n_pos;
+    KGE_REQUIRE(stage->K == K && stage->rows_per_shard == ent_slots && stage->n_shards >= 1 && n_keys == S * stage->n_shards,
+                "kge_train_push_rows: stage must hold (2+eta)*n_pos rows per rank and n_keys = n_ranks*(3+eta)*n_pos");
+    const int64_t rps = a->ent.rows_per_shard > 0 ? a->ent.rows_per_shard : a->ent.rows;
+    const int own = a->ent.n_shards == 1 ? 0 : (int)(row_begin / rps);
+    KGE_REQUIRE(own < a->ent.n_shards && a->ent.shard[own] != nullptr && row_begin == (int64_t)own * rps,
+                "kge_train_push_rows: [row_begin,row_end) must be this rank's shard of a->ent");
+    const int blocks = ctx->sm_count * 8;
+    const TableView sv = make_view(*stage);
+    if (K % 4 == 0)
+        kge_push_rows_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(keys_all, n_keys, S, ent_slots, a->ent.shard[own], row_begin, row_end, K, sv);
+    else
+        kge_push_rows_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(keys_all, n_keys, S, ent_slots, a->ent.shard[own], row_begin, row_end, K, sv);
+    KGE_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 // owner-side selection of the slots a rank must reduce: keys of its row range + every relation key
@@ -961,10 +1048,15 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
     ApplyParams P;
     P.ks = ctx->ks_sorted.as<uint64_t>();
     P.n_keys = n_items;
-    for (int i = 0; i < KGE_MAX_SHARDS; ++i) P.G.base[i] = grads->shard[i];
     P.G.n_ranks = grads->n_shards;
     P.G.S = grads->rows_per_shard;
     P.G.n = grads->rows_per_shard / (3 + a->eta);
+    for (int i = 0; i < KGE_MAX_SHARDS; ++i) {
+        P.G.base[i] = grads->shard[i];
+        P.G.tail[i] = grads->shard[i];
+        if (a->grad_tails != nullptr && i < grads->n_shards)  // never dereferenced below the tail
+            P.G.tail[i] = a->grad_tails + (int64_t)i * a->grad_tail_stride - 3 * P.G.n * (int64_t)K;
+    }
     P.G.eta = a->eta;
     P.G.K = K;
     P.ent = make_view(a->ent);

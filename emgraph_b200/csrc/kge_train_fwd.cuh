@@ -300,7 +300,14 @@ struct FwdBwdParams {
     float* gbuf;        // gradient buffer (layout above)
     float* loss_part;   // [n]
     float* dbg_scores;  // optional [n*(1+eta)]
+    const float* stage; // optional local [(2+eta)*n][K]: entity row of slot t (subjects, objects, replacements)
 };
+
+// entity row `idx` that sits in entity slot `slot` of this batch: from the staging copy when the
+// owners pushed it (row-sharded multi-GPU), else from the table
+__device__ __forceinline__ const float* slot_row(const FwdBwdParams& P, int64_t idx, int64_t slot) {
+    return P.stage != nullptr ? P.stage + slot * (int64_t)P.ent.K : table_row(P.ent, idx);
+}
 
 // shared-memory row loads (the staged rows of the PIPE variant); lanes past the end of the row read
 // the row's last vector like row_load_clamped
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
                 const uint32_t q = seq_base + (uint32_t)mypos;
                 const uint32_t sl = q & (uint32_t)(NS - 1);
                 mbar_expect_tx(bars + sl, row_bytes);
-                bulk_g2s(ring + (size_t)sl * K, table_row(P.ent, my_idx), row_bytes, bars + sl);
+                bulk_g2s(ring + (size_t)sl * K, slot_row(P, my_idx, 2 * n + my_q), row_bytes, bars + sl);
                 my_issued = true;
             }
         }
@@ -451,9 +458,9 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
     if (valid) {
         R s, p, o;
         const int32_t si = P.pos[3 * i + 0], pi = P.pos[3 * i + 1], oi = P.pos[3 * i + 2];
-        row_load_clamped(s, table_row(P.ent, si), lane, nvec, half);
+        row_load_clamped(s, slot_row(P, si, i), lane, nvec, half);
         row_load_clamped(p, P.rel + (size_t)pi * K, lane, nvec, half);
-        row_load_clamped(o, table_row(P.ent, oi), lane, nvec, half);
+        row_load_clamped(o, slot_row(P, oi, n + i), lane, nvec, half);
         if constexpr (PIPE) begin_batch(0);  // the first candidate rows travel together with s, p, o
         A::queries(s, p, o, Qo, Qs);
         row_mask(Qo, lane, nvec);  // queries are zero past the end of the row: duplicate columns of
@@ -608,7 +615,8 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
                         src[u] = todo ? __ffs(todo) - 1 : -1;
                         todo &= todo - 1;  // 0 stays 0
                         const int idx = __shfl_sync(0xffffffffu, my_idx, max(src[u], 0));
-                        if (src[u] >= 0) row_load_clamped(r[u], table_row(P.ent, idx), lane, nvec, half);
+                        if (src[u] >= 0)
+                            row_load_clamped(r[u], slot_row(P, idx, 2 * n + (int64_t)(sub + SPLIT * (m0 + src[u])) * n + i), lane, nvec, half);
                     }
                     if constexpr (MODE != 2) {
 #pragma unroll
@@ -742,9 +750,9 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
         // the positive itself: an object-side candidate with r = o and weight dL/dpos
         R s, p, o, gs, gp, go;
         const int32_t si = P.pos[3 * i + 0], pi = P.pos[3 * i + 1], oi = P.pos[3 * i + 2];
-        row_load_clamped(o, table_row(P.ent, oi), lane, nvec, half);
+        row_load_clamped(o, slot_row(P, oi, n + i), lane, nvec, half);
         A::backward_pos(Qo, o, wpos, spos, P.scale, go, AccO);
-        row_load_clamped(s, table_row(P.ent, si), lane, nvec, half);
+        row_load_clamped(s, slot_row(P, si, i), lane, nvec, half);
         row_load_clamped(p, P.rel + (size_t)pi * K, lane, nvec, half);
         A::fold(s, p, o, AccO, AccS, gs, gp, go);
         row_store(GB + (size_t)i * K, gs, lane, nvec, half);
@@ -855,7 +863,7 @@ static int launch_fwd_bwd_model(const FwdBwdParams& P, int sm_count, cudaStream_
     if (width % 4 == 0) {
         int nvec = width / 4;
         // staged (bulk-copy) rows need 16-byte row pitch and local memory
-        const bool pipe = fwd_bwd_pipe_enabled() && P.ent.n_shards == 1 && (P.ent.K % 4 == 0);
+        const bool pipe = fwd_bwd_pipe_enabled() && (P.ent.n_shards == 1 || P.stage != nullptr) && (P.ent.K % 4 == 0);
         return launch_fwd_bwd_nch<MODEL, 4>((nvec + 31) / 32, split, pipe, P, st);
     }
     return launch_fwd_bwd_nch<MODEL, 1>((width + 31) / 32, 1, false, P, st);

@@ -139,11 +139,24 @@ class ShardedKGE:
             self.state = dict(ent_m=torch.full((rps, K), 0.1, device=eng.tdev), rel_m=torch.full_like(self.rel, 0.1))
         elif opt == 2:
             self.state = dict(ent_m=torch.zeros((rps, K), device=eng.tdev), rel_m=torch.zeros_like(self.rel))
-        self.gbuf = PeerBuffer(eng, (eng.train_grad_floats(eta, self.n, K),))
-        exchange_peers(eng, [self.ent, self.gbuf], self.rank_id, self.world)
+        # gradient buffer: [gs|go|gp] head (read by the owners over peer memory) + [Qo|Qs|coef|keep] tail
+        # (all-gathered so that the per-negative reads of the reduction stay local)
+        g_floats = eng.train_grad_floats(eta, self.n, K)
+        self.g_head = eng.train_grad_head_floats(eta, self.n, K)
+        self.tail_stride = (g_floats - self.g_head + 3) // 4 * 4
+        self.gbuf = PeerBuffer(eng, (self.g_head + self.tail_stride,))
+        # staging copy of the entity row of every entity slot of this rank's batch, pushed by the owners
+        self.ent_slots = (2 + eta) * self.n
+        self.stage = PeerBuffer(eng, (self.ent_slots, K))
+        exchange_peers(eng, [self.ent, self.gbuf, self.stage], self.rank_id, self.world)
         self.ent_table = make_table(self.ent.peers, rows=self.E, rows_per_shard=rps, K=K)
         self.S = (3 + eta) * self.n
         self.grads_table = make_table(self.gbuf.peers, rows=self.S * self.world, rows_per_shard=self.S, K=K)
+        self.stage_table = make_table(self.stage.peers, rows=self.ent_slots * self.world, rows_per_shard=self.ent_slots, K=K)
+        self.tails_all = torch.empty(self.tail_stride * self.world, dtype=torch.float32, device=eng.tdev)
+        self.exchange = "push"  # "pull": fine-grained peer loads inside the kernels (the first design; A/B)
+        self.timing = False
+        self._marks = []
         self.keys_local = torch.empty(self.S, dtype=torch.int32, device=eng.tdev)
         self.keys_all = torch.empty(self.S * self.world, dtype=torch.int32, device=eng.tdev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=eng.tdev)
@@ -166,26 +179,70 @@ class ShardedKGE:
                 st[name] = self.state[name]
         return st
 
+    def make_args(self, pos_dev, repl=None, keep_subj=None, flags=0, step=None):
+        push = self.exchange == "push"
+        a = self.eng.train_args(ent=self.ent_table, rel=self.rel, pos=pos_dev, loss_out=self.loss_dev,
+                                step=self.step if step is None else step, repl=repl, keep_subj=keep_subj, flags=flags,
+                                **self.kw, **self._state_tables(),
+                                stage=self.stage.tensor if push else None, grad_tails=self.tails_all if push else None,
+                                grad_tail_stride=self.tail_stride)
+        a._keep_more = (self.state, self.ent, self.gbuf, self.stage)
+        return a
+
     def train_step(self, pos_dev, repl=None, keep_subj=None, flags=0):
         """pos_dev: this rank's int32 [n,3] positives (device).  Collective.  repl / keep_subj: optional
         supplied corruptions of this rank's positives (parity input), else in-kernel Philox."""
         assert pos_dev.shape[0] == self.n
         eng = self.eng
         self.step += 1
-        a = eng.train_args(ent=self.ent_table, rel=self.rel, pos=pos_dev, loss_out=self.loss_dev, step=self.step,
-                           repl=repl, keep_subj=keep_subj, flags=flags, **self.kw, **self._state_tables())
-        a._keep_more = (self.state, self.ent, self.gbuf)
+        push = self.exchange == "push"
+        a = self.make_args(pos_dev, repl, keep_subj, flags)
+        marks = []
+
+        def mark(name):
+            if self.timing:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         eng.train_emit(a, self.keys_local)
         dist.all_gather_into_tensor(self.keys_all, self.keys_local)
         eng.train_select(a, self.keys_all, self.row_begin, self.row_end)
+        mark("emit+keys")
+        if push:
+            # owners copy the rows of every rank's entity slots into that rank's staging buffer (peer stores)
+            eng.train_push_rows(a, self.keys_all, self.stage_table, self.row_begin, self.row_end)
+            mark("push")
+            dist.all_reduce(self.sync_tok)  # every rank's pushes have landed once this returns on the stream
+            mark("push_barrier")
         eng.train_fwd_bwd(a, self.gbuf.tensor)
+        mark("fwd_bwd")
+        if push:
+            dist.all_gather_into_tensor(self.tails_all, self.gbuf.tensor[self.g_head:self.g_head + self.tail_stride])
         # every rank's forward reads and gradient buffer are complete once this returns on the stream
         self.loss_sum.copy_(self.loss_dev)
         dist.all_reduce(self.loss_sum)
+        mark("tails+loss")
         eng.train_apply(a, self.keys_all, self.grads_table, self.row_begin, self.row_end)
+        mark("apply")
         # owners have finished reading the peers' gradient buffers / writing their rows
         dist.all_reduce(self.sync_tok)
+        mark("end_barrier")
+        if self.timing:
+            self._marks.append(marks)
         return self.loss_sum
+
+    def phase_times(self):
+        """Average ms per phase over the steps run with self.timing = True (synchronises)."""
+        torch.cuda.synchronize()
+        acc = {}
+        for marks in self._marks:
+            for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+                acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1)
+        n = max(1, len(self._marks))
+        self._marks = []
+        return {k: v / n for k, v in acc.items()}
 
     def rank_counts(self, test_dev, *, side=0, filtered=False, use_tensor_cores=False):
         """Per-shard sweep + all-reduce of the [T,2,4] counters.  Collective."""

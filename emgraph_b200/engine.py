@@ -136,7 +136,8 @@ class Engine:
     def train_args(self, *, model, loss, opt, k, eta, ent, rel, pos, loss_out, side=0, flags=0, margin=1.0,
                    lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7, momentum=0.9, seed=0, step=1, neg_index_base=0,
                    ent_m=None, ent_v=None, rel_m=None, rel_v=None, repl=None, keep_subj=None,
-                   dbg_scores=None, dbg_grad_ent=None, dbg_grad_rel=None) -> KgeTrainArgs:
+                   dbg_scores=None, dbg_grad_ent=None, dbg_grad_rel=None, stage=None, grad_tails=None,
+                   grad_tail_stride=0) -> KgeTrainArgs:
         a = KgeTrainArgs()
         a.model, a.loss, a.opt, a.side, a.flags = model, loss, opt, side, flags
         a.k, a.eta, a.margin = k, eta, margin
@@ -168,8 +169,16 @@ class Engine:
         a.dbg_scores = dbg_scores.data_ptr() if dbg_scores is not None else None
         a.dbg_grad_ent = dbg_grad_ent.data_ptr() if dbg_grad_ent is not None else None
         a.dbg_grad_rel = dbg_grad_rel.data_ptr() if dbg_grad_rel is not None else None
+        if stage is not None:
+            _chk_f32(stage, "stage")
+            assert stage.numel() >= (2 + eta) * a.n_pos * K
+            a.stage = stage.data_ptr()
+        if grad_tails is not None:
+            _chk_f32(grad_tails, "grad_tails")
+            a.grad_tails, a.grad_tail_stride = grad_tails.data_ptr(), int(grad_tail_stride)
         # keep python references alive for the duration of the call
-        a._keep = (ent, rel, pos, loss_out, ent_m, ent_v, rel_m, rel_v, repl, keep_subj, dbg_scores, dbg_grad_ent, dbg_grad_rel)
+        a._keep = (ent, rel, pos, loss_out, ent_m, ent_v, rel_m, rel_v, repl, keep_subj, dbg_scores, dbg_grad_ent, dbg_grad_rel,
+                   stage, grad_tails)
         return a
 
     # kernels per step: emit, fwd_bwd, loss-reduce, radix sort (CUB onesweep: histogram + exclusive
@@ -196,6 +205,16 @@ class Engine:
     def train_emit(self, a: KgeTrainArgs, keys_out):
         _chk_i32(keys_out, "keys_out")
         check(self.lib.kge_train_emit(self._h, C.byref(a), _ptr(keys_out), _stream()))
+        self.launches += 1
+
+    def train_grad_head_floats(self, eta: int, n_pos: int, K: int) -> int:
+        return int(self.lib.kge_train_grad_head_floats(eta, n_pos, K))
+
+    def train_push_rows(self, a: KgeTrainArgs, keys_all, stage: KgeTable, row_begin: int, row_end: int):
+        """Owner-side push of this rank's rows into every rank's staging buffer (see kge_b200.h)."""
+        _chk_i32(keys_all, "keys_all")
+        check(self.lib.kge_train_push_rows(self._h, C.byref(a), _ptr(keys_all), keys_all.numel(), C.byref(stage),
+                                           row_begin, row_end, _stream()))
         self.launches += 1
 
     def train_select(self, a: KgeTrainArgs, keys_all, row_begin: int, row_end: int):

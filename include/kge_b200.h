@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 3
+#define KGE_ABI_VERSION 4
 #define KGE_MAX_SHARDS 8
 
 typedef struct kge_ctx kge_ctx;
@@ -84,6 +84,16 @@ typedef struct kge_train_args {
     float*   dbg_scores;   /* optional device [n_pos*(1+eta)]: positives then negatives (row j*n+i) */
     float*   dbg_grad_ent; /* optional device dense [E,K]: summed row gradients (must be zeroed) */
     float*   dbg_grad_rel; /* optional device dense [R,K] */
+    /* row-sharded multi-GPU exchange (all optional, NULL on one GPU):
+     * stage       local [(2+eta)*n_pos, K] copy of the entity row of every entity slot of this rank's batch
+     *             (slot order: subjects, objects, replacements), filled by the owners' kge_train_push_rows;
+     *             kge_train_fwd_bwd then reads entity rows from it instead of a->ent (no peer loads).
+     * grad_tails  local buffer holding every rank's gradient-buffer tail [Qo | Qs | coef | keep] back to
+     *             back (rank r at r*grad_tail_stride floats, all-gathered by the host); kge_train_apply then
+     *             reads queries and coefficients locally and only the gs/go/gp rows through `grads`. */
+    float*   stage;
+    float*   grad_tails;
+    int64_t  grad_tail_stride;
 } kge_train_args;
 
 int         kge_abi_version(void);
@@ -92,6 +102,8 @@ int         kge_has_tensor_core_rank(void);
 /* floats in the caller-owned gradient buffer kge_train_fwd_bwd writes for a batch of n_pos positives:
  * 5 rows per positive (grad s, grad o, grad p, query Qo, query Qs) + eta coefficients + eta side flags */
 int64_t     kge_train_grad_floats(int eta, int64_t n_pos, int K);
+/* floats of that buffer before its [Qo | Qs | coef | keep] tail (= 3*n_pos*K: the gs, go, gp rows) */
+int64_t     kge_train_grad_head_floats(int eta, int64_t n_pos, int K);
 const char* kge_last_error(void);
 
 /* per-device context (replaces the reference's implicit TF runtime state) */
@@ -129,6 +141,15 @@ int kge_train_emit(kge_ctx* ctx, const kge_train_args* a, int32_t* keys_out, voi
 int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, void* stream);
 int kge_train_apply(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, int64_t n_keys,
                     const kge_table* grads, int64_t row_begin, int64_t row_end, void* stream);
+/* Owner-side push of the rows the other ranks' batches need (replaces fine-grained peer loads: a
+ * peer's random 1 KiB row reads through an IPC mapping of a multi-GB shard run at ~130 GB/s on B200,
+ * contiguous peer stores at ~710 GB/s).  For every entity slot t of keys_all (all ranks' keys, n_keys =
+ * n_ranks * (3+eta)*n_pos) whose key lies in [row_begin,row_end): copy row `key` of the local shard of
+ * a->ent into stage->shard[t / slots_per_rank] at row (t % slots_per_rank).  stage->shard[r] = rank r's
+ * staging buffer (local or peer mapping), stage->rows_per_shard = (2+eta)*n_pos.  The caller places a
+ * cross-rank barrier between this and kge_train_fwd_bwd with a->stage set. */
+int kge_train_push_rows(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, int64_t n_keys,
+                        const kge_table* stage, int64_t row_begin, int64_t row_end, void* stream);
 /* Optional, between the key all-gather and kge_train_fwd_bwd: start selecting the slots this rank
  * will reduce (keys in [row_begin,row_end) + relation keys) so that their count reaches the host while
  * the forward/backward kernel runs; kge_train_apply with the same arguments then does not stall. */

@@ -167,9 +167,11 @@ def _clip(x):
     return np.clip(x, CLIP_LO, CLIP_HI)
 
 
-def loss_and_dscore(loss, pos, neg, eta, margin=1.0, dtype=np.float32):
+def loss_and_dscore(loss, pos, neg, eta, margin=1.0, dtype=np.float32, alpha=0.5):
     """Loss value and dL/dpos [n], dL/dneg [eta*n].  pos is NOT tiled on entry; the eta-tiling of
-    models/EmbeddingModel.py:724-729 is applied here for pairwise / nll."""
+    models/EmbeddingModel.py:724-729 is applied here for pairwise / nll / absolute_margin
+    (require_same_size_pos_neg, losses/utils.py:24); multiclass_nll and self_adversarial take the
+    positives untiled (losses/nll_multiclass.py:7, self_adversarial.py:12)."""
     pos = np.asarray(pos, dtype=dtype)
     neg = np.asarray(neg, dtype=dtype)
     n = pos.shape[0]
@@ -197,6 +199,31 @@ def loss_and_dscore(loss, pos, neg, eta, margin=1.0, dtype=np.float32):
         dpos = -(1 - pe / z) * in_p
         dneg = (ne / z[None, :]) * in_n
         return val, dpos, dneg.reshape(-1)
+    if loss == "absolute_margin":
+        # losses/absolute_margin.py:69 : sum(max(margin + neg, 0) - pos_tiled)
+        t = dtype(margin) + negm
+        val = np.sum(np.maximum(t, 0) - pos[None, :], dtype=dtype)
+        act = (t >= 0).astype(dtype)
+        return val, np.full(n, -dtype(eta), dtype=dtype), act.reshape(-1)
+    if loss == "self_adversarial":
+        # losses/self_adversarial.py:97-110 : p = softmax(alpha*neg) over the eta axis (gradient flows
+        # through p); loss = sum -logsigmoid(margin + pos) - sum p * logsigmoid(-neg - margin)
+        a, mg = dtype(alpha), dtype(margin)
+        zmax = (a * negm).max(axis=0, keepdims=True)
+        ex = np.exp(a * negm - zmax)
+        p = ex / ex.sum(axis=0, keepdims=True, dtype=dtype)
+
+        def logsig(x):
+            return np.minimum(x, 0) - np.log1p(np.exp(-np.abs(x)))
+
+        def sig(x):
+            return 1 / (1 + np.exp(-x))
+        ln = logsig(-negm - mg)
+        val = np.sum(-logsig(mg + pos), dtype=dtype) - np.sum(p * ln, dtype=dtype)
+        lbar = np.sum(p * ln, axis=0, keepdims=True, dtype=dtype)
+        dneg = p * sig(negm + mg) - a * p * (ln - lbar)
+        dpos = -sig(-(mg + pos))
+        return val, dpos.astype(dtype), dneg.reshape(-1).astype(dtype)
     raise ValueError("Unsupported loss function: {}".format(loss))
 
 
@@ -244,7 +271,7 @@ def optimizer_step(opt, w, g, touched, lr, state=None, step=1, momentum=0.9, dty
 # one training step  (models/EmbeddingModel.py:614-822 + optimizer.minimize :1415-1418)
 # --------------------------------------------------------------------------------------------
 def train_step(model, k, loss, eta, ent, rel, pos, keep_subj, repl, margin=1.0, norm=1,
-               opt=None, lr=5e-4, state=None, step=1, dtype=np.float32, grad_dtype=np.float64):
+               opt=None, lr=5e-4, state=None, step=1, dtype=np.float32, grad_dtype=np.float64, alpha=0.5):
     """Forward in `dtype` (the reference is fp32), gradients in `grad_dtype`.
     Returns dict(loss, scores_pos, scores_neg, grad_ent[E,K], grad_rel[R,K], touched_ent, touched_rel
     [, ent_new, rel_new, state_ent, state_rel])."""
@@ -253,7 +280,7 @@ def train_step(model, k, loss, eta, ent, rel, pos, keep_subj, repl, margin=1.0, 
     neg = corruptions_for_fit(pos, eta, keep_subj, repl)
     sp = score(model, k, ent, rel, pos, norm, dtype)
     sn = score(model, k, ent, rel, neg, norm, dtype)
-    val, dpos, dneg = loss_and_dscore(loss, sp, sn, eta, margin, dtype)
+    val, dpos, dneg = loss_and_dscore(loss, sp, sn, eta, margin, dtype, alpha)
     gd = grad_dtype
     g_ent = np.zeros(ent.shape, dtype=gd)
     g_rel = np.zeros(rel.shape, dtype=gd)

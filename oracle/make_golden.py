@@ -33,6 +33,13 @@ TRAIN_CASES = [
     ("hole_multiclass", "HolE", "multiclass_nll", 16, 5, 64, 3, 48, "s,o", {}, {}),
     ("hole_nll", "HolE", "nll", 10, 2, 48, 3, 25, "s,o", {}, {}),
     ("hole_pairwise", "HolE", "pairwise", 6, 3, 48, 3, 25, "o", {"margin": 0.5}, {}),
+    # section 8(f).4 plug-ins: losses/absolute_margin.py:54-70, losses/self_adversarial.py:78-112
+    ("distmult_absmargin", "DistMult", "absolute_margin", 12, 5, 64, 5, 40, "s,o", {"margin": 0.5}, {}),
+    ("transe_l1_absmargin", "TransE", "absolute_margin", 10, 4, 50, 3, 33, "s,o", {"margin": 3.0}, {}),
+    ("complex_selfadv", "ComplEx", "self_adversarial", 12, 6, 64, 6, 40, "s,o", {"margin": 3.0, "alpha": 0.5}, {}),
+    ("distmult_selfadv", "DistMult", "self_adversarial", 16, 9, 64, 5, 48, "s,o", {"margin": 1.0, "alpha": 1.5}, {}),
+    ("transe_l1_selfadv", "TransE", "self_adversarial", 10, 4, 50, 3, 33, "o", {"margin": 2.0, "alpha": 0.5}, {}),
+    ("hole_selfadv", "HolE", "self_adversarial", 8, 5, 48, 3, 30, "s,o", {}, {}),
 ]
 
 RANK_CASES = [
@@ -48,7 +55,14 @@ RANK_CASES = [
 def main():
     os.makedirs(OUT, exist_ok=True)
     assert ref_shim.available(), "needs /root/reference"
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]  # optional name substrings: regenerate a subset
+
+    def wanted(name):
+        return not only or any(o in name for o in only)
+
     for ci, (name, model, loss, k, eta, E, R, n, side, lp, ep) in enumerate(TRAIN_CASES):
+        if not wanted("train_" + name):
+            continue
         rng = np.random.Generator(np.random.PCG64(1000 + ci))
         K = ko.internal_k(model, k)
         ent = (rng.normal(size=(E, K)) * 0.6).astype(np.float32)
@@ -59,12 +73,15 @@ def main():
         ref = ref_shim.ref_train_forward_backward(model, k, eta, loss, ent, rel, pos, keep, repl, lp, ep, side)
         np.savez_compressed(
             os.path.join(OUT, "train_%s.npz" % name),
-            model=model, loss_name=loss, k=k, eta=eta, side=side, margin=float(lp.get("margin", 1.0)),
+            model=model, loss_name=loss, k=k, eta=eta, side=side,
+            margin=float(lp.get("margin", 3.0 if loss == "self_adversarial" else 1.0)), alpha=float(lp.get("alpha", 0.5)),
             norm=int(ep.get("norm", 1)), ent=ent, rel=rel, pos=pos, keep_subj=keep, repl=repl,
             loss=np.float32(ref["loss"]), scores_pos=ref["scores_pos"], scores_neg=ref["scores_neg"],
             neg=ref["neg"].astype(np.int32), grad_ent=ref["grad_ent"], grad_rel=ref["grad_rel"])
         print("train", name, "loss", ref["loss"])
     for ci, (name, model, k, E, R, F, T, ep, scale) in enumerate(RANK_CASES):
+        if not wanted(name):
+            continue
         rng = np.random.Generator(np.random.PCG64(2000 + ci))
         K = ko.internal_k(model, k)
         ent = (rng.normal(size=(E, K)) * scale).astype(np.float32)

@@ -64,6 +64,7 @@ def _build_tf():
     tf.convert_to_tensor = constant
     nn = types.ModuleType("tensorflow.nn")
     nn.embedding_lookup = lambda p, ids, **k: p[_t(ids).long()]
+    nn.softmax = lambda x, axis=-1: torch.softmax(_t(x), dim=axis)
     tf.nn = nn
     tf.reduce_sum = lambda x, axis=None, **k: torch.sum(_t(x)) if axis is None else torch.sum(_t(x), dim=axis)
     tf.reduce_mean = lambda x, axis=None, **k: torch.mean(_t(x)) if axis is None else torch.mean(_t(x), dim=axis)
@@ -107,6 +108,10 @@ def _build_tf():
     m.log, m.add, m.multiply, m.ceil = torch.log, torch.add, torch.mul, torch.ceil
     m.log = lambda x: torch.log(_t(x))
     m.ceil = lambda x: torch.ceil(_t(x, torch.float32))
+    m.log_sigmoid = lambda x: torch.nn.functional.logsigmoid(_t(x))
+    tf.multiply = lambda a, b: torch.mul(_t(a), _t(b))
+    tf.pow = lambda a, b: torch.pow(_t(a), b)
+    tf.abs = lambda a: torch.abs(_t(a))
     tf.math = m
 
     rnd = types.ModuleType("tensorflow.random")

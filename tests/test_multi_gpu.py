@@ -25,6 +25,7 @@ def _worker(rank, world, port, cfg, q):
         ent, rel = cfg["ent"], cfg["rel"]
         sk = ShardedKGE(model, k, eta, loss, "adam", E, R, n, lr=1e-2, init_ent=lambda b, e: ent[b:e], init_rel=lambda: rel,
                         device=rank)
+        sk.exchange = cfg["exchange"]
         dev = sk.eng.tdev
         pos = torch.from_numpy(cfg["pos"][rank]).to(dev)
         repl = torch.from_numpy(cfg["repl"][rank]).to(dev)
@@ -51,8 +52,10 @@ def _worker(rank, world, port, cfg, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("model,loss,k", [("ComplEx", "nll", 12), ("TransE", "pairwise", 16), ("DistMult", "multiclass_nll", 8)])
-def test_sharded_step_and_ranking_match_oracle(model, loss, k):
+@pytest.mark.parametrize("model,loss,k,exchange", [("ComplEx", "nll", 12, "push"), ("TransE", "pairwise", 16, "push"),
+                                                   ("DistMult", "multiclass_nll", 8, "push"), ("ComplEx", "nll", 12, "pull"),
+                                                   ("TransE", "pairwise", 16, "pull")])
+def test_sharded_step_and_ranking_match_oracle(model, loss, k, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     world, E, R, eta, n = 2, 301, 5, 6, 96
@@ -65,7 +68,7 @@ def test_sharded_step_and_ranking_match_oracle(model, loss, k):
     keep = [rng.integers(0, 2, eta * n).astype(np.uint8) for _ in range(world)]
     filt = ko.synthetic_triples(E, R, 1500, seed=5)
     test = filt[:40]
-    cfg = dict(model=model, loss=loss, k=k, eta=eta, E=E, R=R, n=n, ent=ent, rel=rel, pos=pos, repl=repl, keep=keep, filt=filt, test=test)
+    cfg = dict(exchange=exchange, model=model, loss=loss, k=k, eta=eta, E=E, R=R, n=n, ent=ent, rel=rel, pos=pos, repl=repl, keep=keep, filt=filt, test=test)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 2000)
