@@ -12,7 +12,7 @@ KGE_MAX_SHARDS = 8
 ABI_VERSION = 4
 
 MODEL_IDS = {"TransE": 0, "TransE_L2": 1, "DistMult": 2, "ComplEx": 3, "HolE": 4}
-LOSS_IDS = {"pairwise": 0, "nll": 1, "multiclass_nll": 2}
+LOSS_IDS = {"pairwise": 0, "nll": 1, "multiclass_nll": 2, "absolute_margin": 3, "self_adversarial": 4}
 OPT_IDS = {"adam": 0, "adagrad": 1, "momentum": 2, "sgd": 3}
 TRAIN_SIDE_IDS = {"s,o": 0, "s+o": 0, "s": 1, "o": 2}
 RANK_SIDE_IDS = {"s,o": 0, "s+o": 1, "s": 2, "o": 3}
@@ -46,6 +46,7 @@ class KgeTrainArgs(C.Structure):
         ("repl", C.c_void_p), ("keep_subj", C.c_void_p),
         ("loss_out", C.c_void_p), ("dbg_scores", C.c_void_p), ("dbg_grad_ent", C.c_void_p), ("dbg_grad_rel", C.c_void_p),
         ("stage", C.c_void_p), ("grad_tails", C.c_void_p), ("grad_tail_stride", C.c_int64),
+        ("alpha", C.c_float),
     ]
 
 

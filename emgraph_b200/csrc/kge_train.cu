@@ -763,7 +763,7 @@ __global__ void kge_normalize_rows_kernel(float* emb, int64_t rows, int K) {
 static int validate_train(const kge_train_args* a) {
     KGE_REQUIRE(a != nullptr, "kge_train: null args");
     KGE_REQUIRE(a->model >= KGE_TRANSE_L1 && a->model <= KGE_HOLE, "kge_train: unknown model %d", a->model);
-    KGE_REQUIRE(a->loss >= KGE_LOSS_PAIRWISE && a->loss <= KGE_LOSS_MULTICLASS_NLL, "Unsupported loss function: %d", a->loss);
+    KGE_REQUIRE(a->loss >= KGE_LOSS_PAIRWISE && a->loss <= KGE_LOSS_SELF_ADVERSARIAL, "Unsupported loss function: %d", a->loss);
     KGE_REQUIRE(a->opt >= KGE_OPT_ADAM && a->opt <= KGE_OPT_SGD, "Unsupported optimizer: %d", a->opt);
     KGE_REQUIRE(a->side >= KGE_SIDE_SO && a->side <= KGE_SIDE_O, "Invalid corruption side %d", a->side);
     KGE_REQUIRE(a->k > 0 && a->eta > 0, "kge_train: k and eta must be positive");
@@ -827,6 +827,7 @@ static int fwd_bwd_impl(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, 
     P.k = a->k;
     P.loss = a->loss;
     P.margin = a->margin;
+    P.alpha = a->alpha;
     P.scale = a->model == KGE_HOLE ? 2.0f / (float)a->k : 1.0f;
     P.gbuf = grad_buf;
     P.loss_part = ctx->loss_part.as<float>();

@@ -287,6 +287,11 @@ struct Algebra {
 };
 
 __device__ __forceinline__ float clip75(float x) { return fminf(fmaxf(x, -75.f), 75.f); }
+// log(sigmoid(x)) = -softplus(-x) (tf.math.log_sigmoid) and sigmoid(x)
+__device__ __forceinline__ float log_sigmoid(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+// losses whose per-negative weight depends on all eta scores of the positive: two passes over the rows
+__device__ __forceinline__ bool loss_two_pass(int loss) { return loss == KGE_LOSS_MULTICLASS_NLL || loss == KGE_LOSS_SELF_ADVERSARIAL; }
 
 struct FwdBwdParams {
     TableView ent;
@@ -296,7 +301,7 @@ struct FwdBwdParams {
     const uint8_t* keep;
     int64_t n;
     int eta, k, loss;
-    float margin, scale;
+    float margin, scale, alpha;
     float* gbuf;        // gradient buffer (layout above)
     float* loss_part;   // [n]
     float* dbg_scores;  // optional [n*(1+eta)]
@@ -476,7 +481,22 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
 
     float loss_acc = 0.f;  // identical on all lanes
     float wsum = 0.f;      // pairwise: number of active hinges
-    float zinv = 0.f;      // multiclass: 1 / softmax denominator
+    float zinv = 0.f;      // multiclass / self-adversarial: 1 / softmax denominator
+    float amax = 0.f;      // self-adversarial: max_j alpha*s_j (softmax shift)
+    float lbar = 0.f;      // self-adversarial: sum_j p_j * logsigmoid(-s_j - margin)
+    const float alpha = P.alpha;
+    // pass-2 weight dL/ds_j of the two-pass losses
+    auto weight2 = [&](float sn) -> float {
+        if (loss == KGE_LOSS_MULTICLASS_NLL) {
+            // losses/nll_multiclass.py:70-81 : softmax weight, zero outside the clip range
+            const bool in = (sn >= -75.f) && (sn <= 75.f);
+            return in ? expf(sn) * zinv : 0.f;
+        }
+        // losses/self_adversarial.py:97-110 : L = -sum_j p_j*l_j, p = softmax(alpha*s), l_j = logsigmoid(-s_j - margin);
+        // the gradient flows through p as well: dL/ds_j = p_j*(sigmoid(s_j + margin) - alpha*(l_j - sum_i p_i*l_i))
+        const float pj = expf(alpha * sn - amax) * zinv;
+        return pj * (sigmoidf(sn + margin) - alpha * (log_sigmoid(-sn - margin) - lbar));
+    };
 
     // MODE 0: single pass (pairwise / nll).  MODE 1: scores only (multiclass pass 1).
     // MODE 2: backward with the scores in sc[] (multiclass pass 2).
@@ -493,10 +513,8 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
                 const int x = lane;
                 inv = x < n_obj ? (int)__fns(m_obj, 0, x + 1) : (int)__fns(m_sub, 0, x - n_obj + 1);
                 if (lane < lim) {
-                    // losses/nll_multiclass.py:70-81 : softmax weight, zero outside the clip range
                     const float sn = sc[sub + SPLIT * (m0 + lane)];
-                    const bool in = (sn >= -75.f) && (sn <= 75.f);
-                    w_own = in ? expf(sn) * zinv : 0.f;
+                    w_own = weight2(sn);
                     my_c = A::coefficient(w_own, sn, P.scale);
                     my_sn = sn;
                 }
@@ -538,9 +556,9 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
                     if constexpr (MODE != 2) sn = A::finish(tot, P.scale);
                     if constexpr (MODE == 0) {
                         float term;
-                        if (loss == KGE_LOSS_PAIRWISE) {
-                            // losses/pairwise.py:69 ; tf.maximum passes the gradient when t >= 0
-                            const float tt = margin - spos + sn;
+                        if (loss == KGE_LOSS_PAIRWISE || loss == KGE_LOSS_ABSOLUTE_MARGIN) {
+                            // losses/pairwise.py:69, absolute_margin.py:69 ; tf.maximum passes the gradient when t >= 0
+                            const float tt = loss == KGE_LOSS_PAIRWISE ? margin - spos + sn : margin + sn;
                             term = fmaxf(tt, 0.f);
                             w = (tt >= 0.f) ? 1.f : 0.f;
                         } else {
@@ -637,12 +655,10 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
                                 if (lane == 0) sc[j] = sn;
                             } else {
                                 if constexpr (MODE == 2) {
-                                    // losses/nll_multiclass.py:70-81 : softmax weight, zero outside the clip range
-                                    const bool in = (sn >= -75.f) && (sn <= 75.f);
-                                    w = in ? expf(sn) * zinv : 0.f;
-                                } else if (loss == KGE_LOSS_PAIRWISE) {
-                                    // losses/pairwise.py:69 ; tf.maximum passes the gradient when t >= 0
-                                    const float tt = margin - spos + sn;
+                                    w = weight2(sn);
+                                } else if (loss == KGE_LOSS_PAIRWISE || loss == KGE_LOSS_ABSOLUTE_MARGIN) {
+                                    // losses/pairwise.py:69, absolute_margin.py:69 ; tf.maximum passes the gradient when t >= 0
+                                    const float tt = loss == KGE_LOSS_PAIRWISE ? margin - spos + sn : margin + sn;
                                     loss_acc += fmaxf(tt, 0.f);
                                     w = (tt >= 0.f) ? 1.f : 0.f;
                                     wsum += w;
@@ -685,16 +701,37 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
         }
     };
 
-    if (loss == KGE_LOSS_MULTICLASS_NLL) {
+    if (loss_two_pass(loss)) {
         sweep(std::integral_constant<int, 1>{}, PIPE);
         __syncthreads();
-        float zpart = 0.f;
-        if (valid)
-            for (int j = lane; j < eta; j += 32) zpart += expf(clip75(sc[j]));
-        const float pe = expf(cpos);
-        const float z = warp_sum(zpart) + pe;
-        zinv = 1.f / z;
-        loss_acc = -logf(pe / z);
+        if (loss == KGE_LOSS_MULTICLASS_NLL) {
+            float zpart = 0.f;
+            if (valid)
+                for (int j = lane; j < eta; j += 32) zpart += expf(clip75(sc[j]));
+            const float pe = expf(cpos);
+            const float z = warp_sum(zpart) + pe;
+            zinv = 1.f / z;
+            loss_acc = -logf(pe / z);
+        } else {
+            // softmax over the eta negatives of this positive (tf.nn.softmax subtracts the max)
+            float mx = -INFINITY;
+            if (valid)
+                for (int j = lane; j < eta; j += 32) mx = fmaxf(mx, alpha * sc[j]);
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+            amax = valid ? mx : 0.f;
+            float zpart = 0.f, lpart = 0.f;
+            if (valid)
+                for (int j = lane; j < eta; j += 32) {
+                    const float e = expf(alpha * sc[j] - amax);
+                    zpart += e;
+                    lpart += e * log_sigmoid(-sc[j] - margin);
+                }
+            const float z = warp_sum(zpart);
+            zinv = valid ? 1.f / z : 0.f;
+            lbar = warp_sum(lpart) * zinv;
+            loss_acc = -log_sigmoid(margin + spos) - lbar;
+        }
         sweep(std::integral_constant<int, 2>{}, false);
     } else {
         sweep(std::integral_constant<int, 0>{}, PIPE);
@@ -724,7 +761,7 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
                 row_load(t1, a + K, lane, nvec, half);
                 row_add(AccO, t0);
                 row_add(AccS, t1);
-                if (loss != KGE_LOSS_MULTICLASS_NLL) loss_acc += red[s2 * 2 + 0];
+                if (!loss_two_pass(loss)) loss_acc += red[s2 * 2 + 0];
                 wsum += red[s2 * 2 + 1];
             }
         }
@@ -739,6 +776,12 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
         const float e = expf(-cpos);
         loss_acc += (float)eta * logf(1.f + e);
         wpos = pos_in ? -(float)eta * (e / (1.f + e)) : 0.f;
+    } else if (loss == KGE_LOSS_ABSOLUTE_MARGIN) {
+        // positives are tiled eta times: sum(max(margin + neg, 0) - pos_tiled)
+        loss_acc -= (float)eta * spos;
+        wpos = -(float)eta;
+    } else if (loss == KGE_LOSS_SELF_ADVERSARIAL) {
+        wpos = -sigmoidf(-(margin + spos));
     } else {
         wpos = pos_in ? -(1.f - expf(cpos) * zinv) : 0.f;
     }

@@ -137,10 +137,10 @@ class Engine:
                    lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7, momentum=0.9, seed=0, step=1, neg_index_base=0,
                    ent_m=None, ent_v=None, rel_m=None, rel_v=None, repl=None, keep_subj=None,
                    dbg_scores=None, dbg_grad_ent=None, dbg_grad_rel=None, stage=None, grad_tails=None,
-                   grad_tail_stride=0) -> KgeTrainArgs:
+                   grad_tail_stride=0, alpha=0.5) -> KgeTrainArgs:
         a = KgeTrainArgs()
         a.model, a.loss, a.opt, a.side, a.flags = model, loss, opt, side, flags
-        a.k, a.eta, a.margin = k, eta, margin
+        a.k, a.eta, a.margin, a.alpha = k, eta, margin, alpha
         a.lr, a.beta1, a.beta2, a.eps, a.momentum = lr, beta1, beta2, eps, momentum
         a.seed, a.step, a.neg_index_base = seed, step, neg_index_base
         a.ent = ent if isinstance(ent, KgeTable) else make_table(ent)

@@ -41,7 +41,10 @@ DEFAULT_MARGIN = 1  # losses/_loss_constants.py:8
 
 MODEL_REGISTRY = {}
 
-SUPPORTED_LOSSES = ("pairwise", "nll", "multiclass_nll")
+DEFAULT_MARGIN_ADVERSARIAL = 3  # losses/_loss_constants.py:12
+DEFAULT_ALPHA_ADVERSARIAL = 0.5  # losses/_loss_constants.py:10
+SUPPORTED_LOSSES = ("pairwise", "nll", "multiclass_nll", "absolute_margin", "self_adversarial")
+TILED_POSITIVE_LOSSES = ("pairwise", "nll", "absolute_margin")  # require_same_size_pos_neg (losses/utils.py:24)
 SUPPORTED_OPTIMIZERS = ("adam", "adagrad", "momentum", "sgd")
 SUPPORTED_INITIALIZERS = ("glorot_uniform", "xavier", "normal", "uniform", "constant")
 SUPPORTED_REGULARIZERS = ()  # LP is SURVEY section 8f "next"
@@ -306,7 +309,8 @@ class EmbeddingModel:
             loss_dev=torch.zeros(1, dtype=torch.float32, device=dev),
             loss_host=torch.zeros(1, dtype=torch.float32).pin_memory(),
             kw=dict(model=self._model_id(), loss=_lib.LOSS_IDS[self.loss], opt=opt, k=self.k, eta=self.eta,
-                    flags=_lib.F_RESET_STATE if reset else 0, margin=float(self.loss_params.get("margin", DEFAULT_MARGIN)),
+                    flags=_lib.F_RESET_STATE if reset else 0, margin=float(self.loss_params.get("margin", DEFAULT_MARGIN_ADVERSARIAL if self.loss == "self_adversarial" else DEFAULT_MARGIN)),
+                    alpha=float(self.loss_params.get("alpha", DEFAULT_ALPHA_ADVERSARIAL)),
                     lr=float(self.optimizer_params.get("lr", DEFAULT_LR)),
                     momentum=float(self.optimizer_params.get("momentum", DEFAULT_MOMENTUM)), seed=int(self.seed)))
         return self._fit
@@ -343,7 +347,7 @@ class EmbeddingModel:
         normalize = bool(self.embedding_model_params.get("normalize_ent_emb", False))
         check_every = int(self.engine_params.get("nan_check_every", self.batches_count))
         self.loss_history = []
-        denom = batch_size * (self.eta if self.loss in ("pairwise", "nll") else 1) * self.batches_count  # :1343-1344, :1453-1457
+        denom = batch_size * (self.eta if self.loss in TILED_POSITIVE_LOSSES else 1) * self.batches_count  # :1343-1344, :1453-1457
         for epoch in range(1, self.epochs + 1):
             epoch_loss.zero_()
             host_loss = 0.0

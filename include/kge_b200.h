@@ -34,8 +34,10 @@ typedef struct kge_ctx kge_ctx;
 
 /* scoring functions: models/TransE.py:190-216, DistMult.py:181-201, ComplEx.py:267-298, HolE.py:169-189 */
 enum { KGE_TRANSE_L1 = 0, KGE_TRANSE_L2 = 1, KGE_DISTMULT = 2, KGE_COMPLEX = 3, KGE_HOLE = 4 };
-/* losses: losses/pairwise.py:54-70, nll.py:43-59, nll_multiclass.py:57-81 */
-enum { KGE_LOSS_PAIRWISE = 0, KGE_LOSS_NLL = 1, KGE_LOSS_MULTICLASS_NLL = 2 };
+/* losses: losses/pairwise.py:54-70, nll.py:43-59, nll_multiclass.py:57-81, absolute_margin.py:54-70,
+ * self_adversarial.py:78-112 */
+enum { KGE_LOSS_PAIRWISE = 0, KGE_LOSS_NLL = 1, KGE_LOSS_MULTICLASS_NLL = 2, KGE_LOSS_ABSOLUTE_MARGIN = 3,
+       KGE_LOSS_SELF_ADVERSARIAL = 4 };
 /* optimizers: training/adam.py:31-48, adagrad.py:30-46, momentum.py:51-69, sgd.py:79-125 */
 enum { KGE_OPT_ADAM = 0, KGE_OPT_ADAGRAD = 1, KGE_OPT_MOMENTUM = 2, KGE_OPT_SGD = 3 };
 /* training corruption side: evaluation/protocol.py:587-608 ('s,o' == 's+o': per-negative coin) */
@@ -94,6 +96,7 @@ typedef struct kge_train_args {
     float*   stage;
     float*   grad_tails;
     int64_t  grad_tail_stride;
+    float    alpha;        /* self_adversarial sampling temperature (losses/self_adversarial.py:75) */
 } kge_train_args;
 
 int         kge_abi_version(void);

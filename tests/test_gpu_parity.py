@@ -37,7 +37,7 @@ def _close(a, b, rtol=RTOL, scale=None):
 
 
 def run_step(engine, model, k, loss, eta, ent, rel, pos, keep, repl, margin=1.0, norm=1, opt="adam", lr=1e-3,
-             flags=0, state=None, step=1):
+             flags=0, state=None, step=1, alpha=0.5):
     from emgraph_b200 import _lib
     n = pos.shape[0]
     ent_d, rel_d = _dev(ent), _dev(rel)
@@ -48,7 +48,7 @@ def run_step(engine, model, k, loss, eta, ent, rel, pos, keep, repl, margin=1.0,
         st = {k_: _dev(v) for k_, v in state.items()}
     a = engine.train_args(model=_ids(model, norm), loss=_lib.LOSS_IDS[loss], opt=_lib.OPT_IDS[opt], k=k, eta=eta,
                           ent=ent_d, rel=rel_d, pos=_dev(pos, torch.int32), loss_out=out["loss"], flags=flags,
-                          margin=margin, lr=lr, step=step, repl=_dev(repl, torch.int32), keep_subj=_dev(keep, torch.uint8),
+                          margin=margin, alpha=alpha, lr=lr, step=step, repl=_dev(repl, torch.int32), keep_subj=_dev(keep, torch.uint8),
                           dbg_scores=out["scores"], dbg_grad_ent=out["g_ent"], dbg_grad_rel=out["g_rel"], **st)
     engine.train_step(a)
     torch.cuda.synchronize()
@@ -65,7 +65,8 @@ def test_train_step_vs_reference_golden(engine, path):
     g = np.load(path)
     model, k, eta = str(g["model"]), int(g["k"]), int(g["eta"])
     r = run_step(engine, model, k, str(g["loss_name"]), eta, g["ent"], g["rel"], g["pos"], g["keep_subj"], g["repl"],
-                 margin=float(g["margin"]), norm=int(g["norm"]), flags=_lib.F_NO_UPDATE)
+                 margin=float(g["margin"]), norm=int(g["norm"]), flags=_lib.F_NO_UPDATE,
+                 alpha=float(g["alpha"]) if "alpha" in g.files else 0.5)
     n = g["pos"].shape[0]
     _close(r["scores"][:n], g["scores_pos"])
     _close(r["scores"][n:], g["scores_neg"])
@@ -133,6 +134,8 @@ def test_stateful_sparse_optimizer_three_steps(engine, opt):
     ("TransE", "pairwise", 100, 20), ("DistMult", "pairwise", 200, 10), ("ComplEx", "nll", 200, 20),
     ("HolE", "multiclass_nll", 256, 20), ("DistMult", "nll", 256, 64), ("TransE", "multiclass_nll", 7, 33),
     ("ComplEx", "pairwise", 5, 3), ("DistMult", "multiclass_nll", 130, 40),
+    ("ComplEx", "self_adversarial", 200, 20), ("DistMult", "absolute_margin", 200, 10), ("HolE", "self_adversarial", 256, 20),
+    ("TransE", "self_adversarial", 100, 40), ("TransE", "absolute_margin", 9, 5), ("DistMult", "self_adversarial", 256, 64),
 ])
 def test_train_step_vs_oracle_bench_shapes(engine, model, loss, k, eta):
     """The benchmark embedding sizes (and odd sizes that take the scalar path) against the oracle."""
