@@ -8,5 +8,6 @@ ABI of include/kge_b200.h; there is no CPU fallback.
 """
 __version__ = "0.1.0"
 
-from . import _lib, evaluation, models  # noqa: F401
+from . import _lib, evaluation, models, utils  # noqa: F401
 from .models import ComplEx, DistMult, HolE, TransE  # noqa: F401
+from .utils import restore_model, save_model  # noqa: F401

@@ -47,6 +47,8 @@ class KgeTrainArgs(C.Structure):
         ("loss_out", C.c_void_p), ("dbg_scores", C.c_void_p), ("dbg_grad_ent", C.c_void_p), ("dbg_grad_rel", C.c_void_p),
         ("stage", C.c_void_p), ("grad_tails", C.c_void_p), ("grad_tail_stride", C.c_int64),
         ("alpha", C.c_float),
+        ("reg_p", C.c_int32), ("reg_lambda_ent", C.c_float), ("reg_lambda_rel", C.c_float),
+        ("neg_entities", C.c_void_p), ("neg_entities_n", C.c_int64),
     ]
 
 
@@ -76,7 +78,7 @@ SYMBOLS = {
     "kge_filter_clear": (_I, [_P]),
     "kge_filter_size_sync": (_L, [_P]),
     "kge_rank_counts": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _L, _P, _L, _I, _I, _I, _P, _P]),
-    "kge_rank_finalize": (_I, [_P, _P, _L, _I, _I, _I, _P, _P]),
+    "kge_rank_finalize": (_I, [_P, _P, _L, _I, _I, _I, _P, _P, _P]),
     "kge_rank_host": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _I, _I, _I, _I, _P, _P]),
     "kge_dev_alloc": (_I, [_L, C.POINTER(_P)]),
     "kge_dev_free": (_I, [_P]),

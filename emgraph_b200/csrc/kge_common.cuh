@@ -81,7 +81,7 @@ struct kge_ctx {
     int sm_count = 148;
     // training workspace
     KgeBuf sort_tmp;
-    KgeBuf repl, keep, grad_rows, loss_part, neg_scores, partial, span_head;
+    KgeBuf repl, keep, grad_rows, loss_part, neg_scores, partial, span_head, reg_partial, touched;
     KgeBuf ks_in, ks_sel, ks_sorted, sel_flags, sel_count;
     // owner-side slot selection (kge_train_select): count travels to the host behind an event
     // side stream of the single-GPU step (sort + loss reduction beside the forward/backward kernel)

@@ -398,14 +398,17 @@ __device__ __forceinline__ int cmp_count(int gt, int eq, int strategy) {
 }
 
 __global__ void kge_rank_finalize_kernel(const int32_t* __restrict__ counts, int64_t T, int side, int strategy,
-                                         int filtered, int32_t* __restrict__ ranks) {
+                                         int filtered, const uint8_t* __restrict__ self_cand, int32_t* __restrict__ ranks) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= T) return;
-    // object sweep = side 0, subject sweep = side 1; +1 on eq: the test triple's own candidate
+    // object sweep = side 0, subject sweep = side 1; +1 on eq: the test triple's own candidate (when its
+    // entity is among the swept candidates at all)
     const int32_t* co = counts + (t * 2 + 0) * 4;
     const int32_t* cs = counts + (t * 2 + 1) * 4;
-    int go = co[0], eo = co[1] + 1, gfo = filtered ? co[2] : 0, efo = filtered ? co[3] + 1 : 0;
-    int gs = cs[0], es = cs[1] + 1, gfs = filtered ? cs[2] : 0, efs = filtered ? cs[3] + 1 : 0;
+    const int so = self_cand != nullptr ? (self_cand[2 * t + 1] ? 1 : 0) : 1;
+    const int ss = self_cand != nullptr ? (self_cand[2 * t + 0] ? 1 : 0) : 1;
+    int go = co[0], eo = co[1] + so, gfo = filtered ? co[2] : 0, efo = filtered ? co[3] + so : 0;
+    int gs = cs[0], es = cs[1] + ss, gfs = filtered ? cs[2] : 0, efs = filtered ? cs[3] + ss : 0;
     int fo = filtered ? cmp_count(gfo, efo, strategy) : 0;
     int fs = filtered ? cmp_count(gfs, efs, strategy) : 0;
     if (side == KGE_RANK_S_O) {
@@ -514,13 +517,14 @@ extern "C" int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* 
 }
 
 extern "C" int kge_rank_finalize(kge_ctx* ctx, const int32_t* counts, int64_t T, int side, int strategy, int filtered,
+                                 const uint8_t* self_is_candidate,
                                  int32_t* ranks_out, void* stream) {
     KGE_REQUIRE(ctx != nullptr, "kge_rank_finalize: null ctx");
     KGE_REQUIRE(side >= KGE_RANK_S_O && side <= KGE_RANK_O, "Invalid value for corrupt_side.");
     KGE_REQUIRE(strategy >= KGE_STRAT_WORST && strategy <= KGE_STRAT_MIDDLE, "Invalid ranking_strategy!");
     if (T == 0) return 0;
     KGE_REQUIRE(counts && ranks_out, "kge_rank_finalize: null tensor");
-    kge_rank_finalize_kernel<<<(unsigned)((T + 255) / 256), 256, 0, (cudaStream_t)stream>>>(counts, T, side, strategy, filtered,
+    kge_rank_finalize_kernel<<<(unsigned)((T + 255) / 256), 256, 0, (cudaStream_t)stream>>>(counts, T, side, strategy, filtered, self_is_candidate,
                                                                                         ranks_out);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -540,7 +544,7 @@ extern "C" int kge_rank_host(kge_ctx* ctx, int model, int k, const kge_table* en
     if (int rc = kge_rank_counts(ctx, model, k, ent, rel, R, ent->shard[0], 0, ent->rows, ctx->h_test.as<int32_t>(), T, side,
                                  filtered, use_tensor_cores, ctx->h_counts.as<int32_t>(), stream))
         return rc;
-    if (int rc = kge_rank_finalize(ctx, ctx->h_counts.as<int32_t>(), T, side, strategy, filtered, ctx->h_ranks.as<int32_t>(), stream))
+    if (int rc = kge_rank_finalize(ctx, ctx->h_counts.as<int32_t>(), T, side, strategy, filtered, nullptr, ctx->h_ranks.as<int32_t>(), stream))
         return rc;
     KGE_CUDA_CHECK(cudaMemcpyAsync(ranks_host, ctx->h_ranks.p, n_out * 4, cudaMemcpyDeviceToHost, st));
     KGE_CUDA_CHECK(cudaStreamSynchronize(st));

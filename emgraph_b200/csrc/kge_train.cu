@@ -30,6 +30,7 @@
 __global__ void kge_emit_kernel(const int32_t* __restrict__ pos, int64_t n, int eta, int64_t E, int side,
                                 const int32_t* __restrict__ repl_in, const uint8_t* __restrict__ keep_in,
                                 uint64_t seed, uint64_t step, uint64_t neg_base,
+                                const int32_t* __restrict__ neg_list, int64_t neg_n,
                                 int32_t* __restrict__ repl_out, uint8_t* __restrict__ keep_out,
                                 int32_t* __restrict__ keys, uint64_t* __restrict__ packed, const KgeStepDyn* __restrict__ dyn) {
     int64_t S = (int64_t)(3 + eta) * n;
@@ -52,8 +53,10 @@ __global__ void kge_emit_kernel(const int32_t* __restrict__ pos, int64_t n, int 
                 uint32_t o[4];
                 philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32),
                               (uint32_t)seed, (uint32_t)(seed >> 32), o);
-                // replacement ~ U{0..E-1} (evaluation/protocol.py:616-619); multiply-shift mapping
-                r = (int32_t)(((uint64_t)o[0] * (uint64_t)E) >> 32);
+                // replacement ~ U{0..entities_size-1} (evaluation/protocol.py:616-619), or a uniform pick from
+                // entities_list (:620-641); multiply-shift mapping
+                r = (int32_t)(((uint64_t)o[0] * (uint64_t)(neg_n > 0 ? neg_n : E)) >> 32);
+                if (neg_list != nullptr) r = neg_list[r];
                 ks = side == KGE_SIDE_SO ? (uint8_t)(o[1] >> 31) : (side == KGE_SIDE_O ? 1 : 0);
             }
             repl_out[q] = r;
@@ -114,7 +117,25 @@ struct ApplyParams {
     int32_t* span_count;   // [2]: {#span heads, #hubs}, zeroed before the reduce kernel
     float* dbg_grad_ent;
     float* dbg_grad_rel;
+    // LP regulariser (regularizers/lp.py:81-113): lambda * sum |w|^p over the WHOLE tables, so every row has
+    // a gradient.  Rows touched by the batch get it added in the reduction; `touched` (one bit per sort
+    // key, entity ids then E + relation id) tells kge_reg_dense_kernel which rows are left.
+    int reg_p;
+    float reg_lambda_ent, reg_lambda_rel;
+    uint32_t* touched;
 };
+
+__device__ __forceinline__ float reg_grad1(float w, int p, float lam) {
+    if (p == 2) return 2.f * lam * w;
+    if (p == 1) return w > 0.f ? lam : (w < 0.f ? -lam : 0.f);
+    if (p == 3) return 3.f * lam * w * fabsf(w);
+    const float a = fabsf(w);
+    return a > 0.f ? lam * (float)p * powf(a, (float)(p - 1)) * (w > 0.f ? 1.f : -1.f) : 0.f;
+}
+__device__ __forceinline__ float reg_term1(float w, int p) {
+    const float a = fabsf(w);
+    return p == 2 ? a * a : (p == 1 ? a : (p == 3 ? a * a * a : powf(a, (float)p)));
+}
 
 struct SlotMeta {
     const float* row;
@@ -239,6 +260,18 @@ __device__ __forceinline__ void opt_math(const ApplyParams& P, bool reset, const
     }
 }
 
+// gradient of the LP penalty on V columns of a row whose current values are w
+template <int V>
+__device__ __forceinline__ void reg_add(const ApplyParams& P, bool is_rel, float (&g)[V], const float (&w)[V]) {
+    if (P.reg_p <= 0) return;
+    const float lam = is_rel ? P.reg_lambda_rel : P.reg_lambda_ent;
+#pragma unroll
+    for (int x = 0; x < V; ++x) g[x] += reg_grad1(w[x], P.reg_p, lam);
+}
+__device__ __forceinline__ void mark_touched(const ApplyParams& P, int32_t key) {
+    if (P.touched != nullptr) atomicOr(P.touched + (key >> 5), 1u << (key & 31));
+}
+
 // Level 1: one warp per chunk of KGE_CH sorted slots.  NCA > 0: lanes own ALL their column vectors of
 // the row at once (K <= 128*NCA) so that the row's w/m/v and two slots' rows are in flight together;
 // NCA == 0: generic column loop (any K, scalar columns).
@@ -303,6 +336,7 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
         }
         if (!open_start && open_end && lane == 0) P.span_list[atomicAdd(P.span_count, 1)] = (int32_t)w;
         const bool complete = !open_start && !open_end;
+        if (complete && lane == 0) mark_touched(P, skey);
         float* part = P.partial + ((size_t)(2 * w + (open_start ? 0 : 1))) * K;
         float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
         if constexpr (NCA > 0) {
@@ -357,6 +391,7 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
                     st_vec<V>(part + c0, g[i]);
                     continue;
                 }
+                reg_add<V>(P, r.is_rel, g[i], rc[i]);
                 if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g[i]);
                 if (no_update) continue;
                 opt_math<V>(P, reset, g[i], rc[i], mv[i], vv[i]);
@@ -389,6 +424,7 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
                     st_vec<V>(part + c0, g);
                     continue;
                 }
+                reg_add<V>(P, r.is_rel, g, rc);
                 if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g);
                 if (no_update) continue;
                 opt_math<V>(P, reset, g, rc, mv, vv);
@@ -671,6 +707,7 @@ __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(App
         const int64_t w = P.span_list[h];
         const int32_t key = (int32_t)(P.ks[w * KGE_CH + KGE_CH - 1] >> 32);
         const RowPtrs r = resolve_row(P, key);
+        if (threadIdx.x == 0) mark_touched(P, key);
         // columns owned by this thread in the final combine (at most one vector per thread when K <= 1024)
         const int c_own = threadIdx.x * V;
         float rc0[V], mv0[V], vv0[V];
@@ -729,6 +766,7 @@ __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(App
 #pragma unroll
                 for (int x = 0; x < V; ++x) g[x] += t0[x];
             }
+            reg_add<V>(P, r.is_rel, g, rc);
             if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g);
             if (!no_update) {
                 opt_math<V>(P, reset, g, rc, mv, vv);
@@ -738,6 +776,64 @@ __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(App
             }
         }
         __syncthreads();
+    }
+}
+
+// LP regulariser, rows the batch did not touch: g = d(lambda*|w|^p)/dw, fed to the same optimizer math.
+// One warp per owned row (entity rows [row_begin,row_end), then every relation row).
+template <int V>
+__global__ void __launch_bounds__(256) kge_reg_dense_kernel(ApplyParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int K = P.ent.K;
+    const int64_t n_own = P.row_end - P.row_begin;
+    const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
+    const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
+    const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
+    const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
+    for (int64_t t = warp; t < n_own + P.R; t += nwarps) {
+        const int32_t key = (int32_t)(t < n_own ? P.row_begin + t : P.E + (t - n_own));
+        if ((P.touched[key >> 5] >> (key & 31)) & 1u) continue;
+        const RowPtrs r = resolve_row(P, key);
+        float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
+        for (int c0 = lane * V; c0 < K; c0 += 32 * V) {
+            float g[V], rc[V], mv[V], vv[V];
+#pragma unroll
+            for (int x = 0; x < V; ++x) g[x] = mv[x] = vv[x] = 0.f;
+            ld_vec<V>(rc, r.w + c0);
+            if (need_m) ld_vec<V>(mv, r.m + c0);
+            if (need_v) ld_vec<V>(vv, r.v + c0);
+            reg_add<V>(P, r.is_rel, g, rc);
+            if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g);
+            if (no_update) continue;
+            opt_math<V>(P, reset, g, rc, mv, vv);
+            if (r.m && P.opt != KGE_OPT_SGD) st_vec<V>(r.m + c0, mv);
+            if (r.v && P.opt == KGE_OPT_ADAM) st_vec<V>(r.v + c0, vv);
+            st_vec<V>(r.w + c0, rc);
+        }
+    }
+}
+
+// lambda * sum |w|^p over n floats: per-block partial sums (fixed grid, fixed order => reproducible)
+__global__ void __launch_bounds__(256) kge_reg_loss_kernel(const float* __restrict__ w, int64_t n, int p, float lam, double* __restrict__ partial) {
+    __shared__ double sm[256];
+    double acc = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        acc += (double)reg_term1(w[t], p);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = (double)lam * sm[0];
+}
+__global__ void kge_reg_loss_add_kernel(const double* __restrict__ partial, int n, float* __restrict__ loss_out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) acc += partial[i];
+        loss_out[0] = (float)((double)loss_out[0] + acc);
     }
 }
 
@@ -772,6 +868,8 @@ static int validate_train(const kge_train_args* a) {
     KGE_REQUIRE(a->ent.n_shards >= 1 && a->ent.n_shards <= KGE_MAX_SHARDS, "kge_train: bad shard count");
     KGE_REQUIRE(a->ent.rows + a->R < (int64_t)INT32_MAX, "kge_train: E+R must fit int32 sort keys");
     KGE_REQUIRE(a->n_pos >= 0 && (a->pos != nullptr || a->n_pos == 0), "kge_train: positives missing");
+    KGE_REQUIRE(a->neg_entities_n >= 0 && a->neg_entities_n <= a->ent.rows && (a->neg_entities == nullptr || a->neg_entities_n > 0),
+                "kge_train: bad negative_corruption_entities (n=%lld)", (long long)a->neg_entities_n);
     return 0;
 }
 
@@ -793,7 +891,8 @@ static int emit_impl(kge_ctx* ctx, const kge_train_args* a, int32_t* keys_out, u
     int threads = 256;
     int blocks = (int)std::min<int64_t>((S + threads - 1) / threads, (int64_t)ctx->sm_count * 16);
     kge_emit_kernel<<<blocks, threads, 0, st>>>(a->pos, a->n_pos, a->eta, a->ent.rows, a->side, a->repl, a->keep_subj,
-                                                a->seed, a->step, a->neg_index_base, ctx->repl.as<int32_t>(),
+                                                a->seed, a->step, a->neg_index_base, a->neg_entities, a->neg_entities_n,
+                                                ctx->repl.as<int32_t>(),
                                                 ctx->keep.as<uint8_t>(), keys_out, packed_out, dyn);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -971,7 +1070,7 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
     bool staged = false;
     if constexpr (V == 4 && NCA > 0) {
         // staged rows need local buffers (bulk copies of peer memory are not used) and 16-byte rows
-        staged = tmode == 0 && reduce_staged_enabled() && P.G.n_ranks == 1 && P.ent.n_shards == 1;
+        staged = tmode == 0 && reduce_staged_enabled() && P.G.n_ranks == 1 && P.ent.n_shards == 1 && P.reg_p <= 0;
         if (staged) {
             const int K = P.ent.K;
             int l = 4;
@@ -1088,6 +1187,30 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
     }
     P.dbg_grad_ent = a->dbg_grad_ent;
     P.dbg_grad_rel = a->dbg_grad_rel;
+    P.reg_p = a->reg_p;
+    P.reg_lambda_ent = a->reg_lambda_ent;
+    P.reg_lambda_rel = a->reg_lambda_rel;
+    P.touched = nullptr;
+    const bool reg = a->reg_p > 0 && (a->reg_lambda_ent != 0.f || a->reg_lambda_rel != 0.f);
+    if (!reg) P.reg_p = 0;
+    if (reg) {
+        // penalty of the pre-update parameters of this rank's rows (+ the replicated relation table, counted
+        // by the rank that owns row 0), then the touched-row bitmap for the dense pass
+        const int nb = ctx->sm_count * 4;
+        const size_t words = (size_t)((E + a->R + 31) / 32);
+        if (ctx->reg_partial.reserve((size_t)2 * nb * sizeof(double)) || ctx->touched.reserve(words * sizeof(uint32_t))) return -2;
+        const int64_t rps = a->ent.rows_per_shard > 0 ? a->ent.rows_per_shard : a->ent.rows;
+        const int own = a->ent.n_shards == 1 ? 0 : (int)(row_begin / rps);
+        double* part = ctx->reg_partial.as<double>();
+        KGE_CUDA_CHECK(cudaMemsetAsync(part, 0, (size_t)2 * nb * sizeof(double), st));
+        if (row_end > row_begin)
+            kge_reg_loss_kernel<<<nb, 256, 0, st>>>(a->ent.shard[own] + (row_begin - (int64_t)own * rps) * K, (row_end - row_begin) * (int64_t)K,
+                                                    a->reg_p, a->reg_lambda_ent, part);
+        if (row_begin == 0) kge_reg_loss_kernel<<<nb, 256, 0, st>>>(a->rel, a->R * (int64_t)K, a->reg_p, a->reg_lambda_rel, part + nb);
+        KGE_CUDA_CHECK(cudaGetLastError());
+        KGE_CUDA_CHECK(cudaMemsetAsync(ctx->touched.p, 0, words * sizeof(uint32_t), st));
+        P.touched = ctx->touched.as<uint32_t>();
+    }
     const bool reset = (a->flags & KGE_F_RESET_STATE) != 0;
     const bool no_update = (a->flags & KGE_F_NO_UPDATE) != 0;
     P.lr_t = (float)adam_lr_t(a);
@@ -1099,7 +1222,21 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
             KGE_REQUIRE(P.has_m && a->rel_m, "kge_train: optimizer state missing");
     }
     const int tmode = a->model == KGE_TRANSE_L1 ? 1 : (a->model == KGE_TRANSE_L2 ? 2 : 0);
-    return launch_apply(P, tmode, ctx->sm_count, st, ctx->timing ? ctx->tev[3] : nullptr);
+    if (int rc = launch_apply(P, tmode, ctx->sm_count, st, ctx->timing ? ctx->tev[3] : nullptr)) return rc;
+    if (reg) {
+        if (K % 4 == 0) kge_reg_dense_kernel<4><<<ctx->sm_count * 8, 256, 0, st>>>(P);
+        else kge_reg_dense_kernel<1><<<ctx->sm_count * 8, 256, 0, st>>>(P);
+        KGE_CUDA_CHECK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// adds the LP penalty computed by reduce_impl to the batch loss; `st` must be ordered behind the loss reduction
+static int reg_loss_finish(kge_ctx* ctx, const kge_train_args* a, cudaStream_t st) {
+    if (!(a->reg_p > 0 && (a->reg_lambda_ent != 0.f || a->reg_lambda_rel != 0.f))) return 0;
+    kge_reg_loss_add_kernel<<<1, 32, 0, st>>>(ctx->reg_partial.as<double>(), 2 * ctx->sm_count * 4, a->loss_out);
+    KGE_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 static int apply_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* packed_in, int64_t n_items, const kge_table* grads,
@@ -1175,7 +1312,10 @@ extern "C" int kge_train_apply(kge_ctx* ctx, const kge_train_args* a, const int3
     KGE_CUDA_CHECK(cudaEventSynchronize(ctx->ev_count));
     ctx->sel_valid = false;
     const int64_t m = *ctx->h_count;
-    return apply_impl(ctx, a, ctx->ks_sel.as<uint64_t>(), m, grads, row_begin, row_end, (cudaStream_t)stream);
+    if (int rc = apply_impl(ctx, a, ctx->ks_sel.as<uint64_t>(), m, grads, row_begin, row_end, (cudaStream_t)stream)) return rc;
+    // phased API: kge_train_fwd_bwd reduced the batch loss on this stream already; the LP penalty of this
+    // rank's rows is added to a->loss_out here
+    return reg_loss_finish(ctx, a, (cudaStream_t)stream);
 }
 
 static void timing_collect(kge_ctx* ctx) {
@@ -1250,6 +1390,7 @@ static int train_step_body(kge_ctx* ctx, const kge_train_args* a, void* stream, 
     KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_sorted, 0));
     if (int rc = reduce_impl(ctx, a, S, &g, 0, a->ent.rows, st, dyn)) return rc;
     KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_loss, 0));  // join
+    if (int rc = reg_loss_finish(ctx, a, st)) return rc;
     if (ctx->timing) {
         KGE_CUDA_CHECK(cudaEventRecord(ctx->tev[4], st));
         ctx->tpending = true;

@@ -137,10 +137,12 @@ class Engine:
                    lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-7, momentum=0.9, seed=0, step=1, neg_index_base=0,
                    ent_m=None, ent_v=None, rel_m=None, rel_v=None, repl=None, keep_subj=None,
                    dbg_scores=None, dbg_grad_ent=None, dbg_grad_rel=None, stage=None, grad_tails=None,
-                   grad_tail_stride=0, alpha=0.5) -> KgeTrainArgs:
+                   grad_tail_stride=0, alpha=0.5, reg_p=0, reg_lambda_ent=0.0, reg_lambda_rel=0.0,
+                   neg_entities=None, neg_entities_n=0) -> KgeTrainArgs:
         a = KgeTrainArgs()
         a.model, a.loss, a.opt, a.side, a.flags = model, loss, opt, side, flags
         a.k, a.eta, a.margin, a.alpha = k, eta, margin, alpha
+        a.reg_p, a.reg_lambda_ent, a.reg_lambda_rel = int(reg_p), float(reg_lambda_ent), float(reg_lambda_rel)
         a.lr, a.beta1, a.beta2, a.eps, a.momentum = lr, beta1, beta2, eps, momentum
         a.seed, a.step, a.neg_index_base = seed, step, neg_index_base
         a.ent = ent if isinstance(ent, KgeTable) else make_table(ent)
@@ -176,9 +178,14 @@ class Engine:
         if grad_tails is not None:
             _chk_f32(grad_tails, "grad_tails")
             a.grad_tails, a.grad_tail_stride = grad_tails.data_ptr(), int(grad_tail_stride)
+        if neg_entities is not None:
+            _chk_i32(neg_entities, "neg_entities")
+            a.neg_entities, a.neg_entities_n = neg_entities.data_ptr(), neg_entities.numel()
+        else:
+            a.neg_entities_n = int(neg_entities_n)
         # keep python references alive for the duration of the call
         a._keep = (ent, rel, pos, loss_out, ent_m, ent_v, rel_m, rel_v, repl, keep_subj, dbg_scores, dbg_grad_ent, dbg_grad_rel,
-                   stage, grad_tails)
+                   stage, grad_tails, neg_entities)
         return a
 
     # kernels per step: emit, fwd_bwd, loss-reduce, radix sort (CUB onesweep: histogram + exclusive
@@ -277,11 +284,17 @@ class Engine:
         self.launches += 3 if T else 0
         return counts
 
-    def rank_finalize(self, counts, *, side=0, strategy=0, filtered=False):
+    def rank_finalize(self, counts, *, side=0, strategy=0, filtered=False, self_is_candidate=None):
+        """self_is_candidate: optional uint8 [T,2] (col 0 subject, col 1 object), 0 where the test triple's own
+        entity was not among the swept candidates (entities_subset ranking)."""
         T = counts.shape[0]
         shape = (T, 2) if side == _lib.RANK_SIDE_IDS["s,o"] else (T,)
         ranks = torch.empty(shape, dtype=torch.int32, device=self.tdev)
-        check(self.lib.kge_rank_finalize(self._h, _ptr(counts), T, side, strategy, int(bool(filtered)), _ptr(ranks), _stream()))
+        if self_is_candidate is not None:
+            assert self_is_candidate.is_cuda and self_is_candidate.dtype == torch.uint8 and self_is_candidate.is_contiguous()
+            assert self_is_candidate.numel() == 2 * T
+        check(self.lib.kge_rank_finalize(self._h, _ptr(counts), T, side, strategy, int(bool(filtered)),
+                                         _ptr(self_is_candidate) if self_is_candidate is not None else None, _ptr(ranks), _stream()))
         self.launches += 1 if T else 0
         return ranks
 

@@ -23,6 +23,7 @@ class EvalDataset:
         self._test_dev = None
         self._test_pin = None
         self._engine = None
+        self._perm_built = False
 
     def get_size(self, dataset_type="test"):
         return self.test_idx.shape[0] if dataset_type == "test" else (0 if self.filter_idx is None else self.filter_idx.shape[0])
@@ -39,14 +40,21 @@ class EvalDataset:
             self._test_pin = torch.from_numpy(self.test_idx).pin_memory()
         return self._test_pin
 
-    def build_filter(self, engine, E, R):
+    def build_filter(self, engine, E, R, perm=None):
         """Device filter index; built once per handle (the reference builds its SQLite DB once per
-        evaluate_performance call, datasets/numpy_adapter.py:229-247)."""
-        if self._engine is engine:
+        evaluate_performance call, datasets/numpy_adapter.py:229-247).  perm: optional device int64 [E]
+        re-labelling of the entities (entities_subset ranking sweeps a permuted table)."""
+        if self._engine is engine and perm is None and not self._perm_built:
             return
         f = self.filter_idx if self.filter_idx is not None else np.zeros((0, 3), np.int32)
-        engine.filter_build(to_dev_i32(f, engine.tdev), E, R)
+        fd = to_dev_i32(f, engine.tdev)
+        if perm is not None and fd.shape[0]:
+            import torch
+            fl = fd.long()
+            fd = torch.stack([perm[fl[:, 0]], fl[:, 1], perm[fl[:, 2]]], 1).to(torch.int32).contiguous()
+        engine.filter_build(fd, E, R)
         self._engine = engine
+        self._perm_built = perm is not None
 
     def cleanup(self):
         if self._engine is not None:
@@ -115,8 +123,9 @@ def evaluate_performance(X, model, filter_triples=None, verbose=False, filter_un
             dataset_handle = EvalDataset(test_idx, filt_idx)
         eval_dict = {}
         check_filter_size(model, entities_subset)
-        if entities_subset is not None:
-            raise NotImplementedError("entities_subset ranking is outside the B200 hot-path scope (SURVEY section 8f)")
+        if entities_subset is not None:  # evaluation/protocol.py:940-944
+            idx_entities = model._ent_index.lookup_known(np.asarray(entities_subset))
+            eval_dict["corruption_entities"] = idx_entities
         eval_dict["corrupt_side"] = corrupt_side
         assert ranking_strategy in ["worst", "best", "middle"], "Invalid ranking_strategy!"
         eval_dict["ranking_strategy"] = ranking_strategy

@@ -41,13 +41,19 @@ DEFAULT_MARGIN = 1  # losses/_loss_constants.py:8
 
 MODEL_REGISTRY = {}
 
+DEFAULT_BURN_IN_EARLY_STOPPING = 100  # utils/constants.py:12
+DEFAULT_CHECK_INTERVAL_EARLY_STOPPING = 10  # utils/constants.py:15
+DEFAULT_STOP_INTERVAL_EARLY_STOPPING = 3  # utils/constants.py:18
+DEFAULT_CRITERIA_EARLY_STOPPING = "mrr"  # utils/constants.py:21
 DEFAULT_MARGIN_ADVERSARIAL = 3  # losses/_loss_constants.py:12
 DEFAULT_ALPHA_ADVERSARIAL = 0.5  # losses/_loss_constants.py:10
 SUPPORTED_LOSSES = ("pairwise", "nll", "multiclass_nll", "absolute_margin", "self_adversarial")
 TILED_POSITIVE_LOSSES = ("pairwise", "nll", "absolute_margin")  # require_same_size_pos_neg (losses/utils.py:24)
 SUPPORTED_OPTIMIZERS = ("adam", "adagrad", "momentum", "sgd")
 SUPPORTED_INITIALIZERS = ("glorot_uniform", "xavier", "normal", "uniform", "constant")
-SUPPORTED_REGULARIZERS = ()  # LP is SURVEY section 8f "next"
+SUPPORTED_REGULARIZERS = ("LP",)  # regularizers/lp.py
+DEFAULT_LAMBDA = 1e-5  # regularizers/_regularizer_constants.py:8
+DEFAULT_REG_NORM = 2  # regularizers/_regularizer_constants.py:10
 
 
 def register_model(name):
@@ -94,6 +100,15 @@ class LabelIndex:
         except TypeError:
             return np.zeros(x.shape, bool)
         return self.labels[pos] == x
+
+    def lookup_known(self, x):
+        """ids of the labels in x the index knows, sorted by id; unknown labels are dropped (the reference's
+        ``[idx for uri, idx in ent_to_idx.items() if uri in x]``, evaluation/protocol.py:941-944)."""
+        x = np.asarray(x).reshape(-1)
+        if x.size == 0 or len(self.labels) == 0:
+            return np.zeros(0, np.int32)
+        x = x[self.contains(x)]
+        return np.unique(self.lookup(x, "entities")).astype(np.int32)
 
     def as_dict(self):
         if self._dict is None:
@@ -193,15 +208,16 @@ class EmbeddingModel:
         self.verbose = verbose
         if loss not in SUPPORTED_LOSSES:
             raise ValueError("Unsupported loss function: {}".format(loss))
-        if regularizer is not None:
+        if regularizer is not None and regularizer not in SUPPORTED_REGULARIZERS:
             raise ValueError("Unsupported regularizer: {}".format(regularizer))
+        self._reg = self._parse_regularizer(regularizer, regularizer_params)
         if optimizer not in SUPPORTED_OPTIMIZERS:
             raise ValueError("Unsupported optimizer: {}".format(optimizer))
         if initializer not in SUPPORTED_INITIALIZERS:
             raise ValueError("Unsupported initializer: {}".format(initializer))
         self.loss = loss
         self.optimizer = optimizer
-        self.regularizer = None
+        self.regularizer = regularizer
         self.initializer = initializer
         self.trained_model_params = []
         self.is_fitted = False
@@ -231,6 +247,45 @@ class EmbeddingModel:
     @rel_to_idx.setter
     def rel_to_idx(self, d):
         self._rel_index = _index_from_dict(d)
+
+    @staticmethod
+    def _parse_regularizer(regularizer, params):
+        """LP regulariser hyper-parameters (regularizers/lp.py:41-104): p int, lambda scalar or [ent, rel]."""
+        if regularizer is None:
+            return dict(reg_p=0, reg_lambda_ent=0.0, reg_lambda_rel=0.0)
+        p = params.get("p", DEFAULT_REG_NORM)
+        if not isinstance(p, (int, np.integer)):
+            raise Exception("Invalid value for regularizer parameter p:{}. Supported type int, np.int32 or np.int64".format(p))
+        lam = params.get("lambda", DEFAULT_LAMBDA)
+        if np.isscalar(lam):
+            lam = [lam, lam]
+        elif not (isinstance(lam, list) and len(lam) == 2):
+            raise ValueError("Regularizer weight must be a scalar or a list with length equal to number of params passes")
+        return dict(reg_p=int(p), reg_lambda_ent=float(lam[0]), reg_lambda_rel=float(lam[1]))
+
+    def get_embedding_model_params(self, output_dict):  # models/EmbeddingModel.py:347-358
+        output_dict["model_params"] = [np.asarray(p) for p in self.trained_model_params]
+        output_dict["large_graph"] = self.dealing_with_large_graphs
+        output_dict["calibration_parameters"] = self.calibration_parameters
+
+    def restore_model_params(self, in_dict):  # models/EmbeddingModel.py:360-383
+        self.trained_model_params = [np.asarray(p, dtype=np.float32) for p in in_dict["model_params"]]
+        self.calibration_parameters = in_dict.get("calibration_parameters", [])
+        self.dealing_with_large_graphs = in_dict.get("large_graph", False)
+        self._dev = None  # uploaded lazily on the first predict / get_ranks
+        st = in_dict.get("b200_optimizer_state")
+        if st:
+            self._opt_state = {k_: torch.from_numpy(np.ascontiguousarray(v)) for k_, v in st.items()}
+            self._opt_step = int(in_dict.get("b200_optimizer_step", 0))
+
+    def is_fitted_on(self, X):  # models/EmbeddingModel.py:2188-2210
+        """Heuristic of the reference: same NUMBER of distinct entities and relations as the training set."""
+        if not self.is_fitted:
+            raise RuntimeError("Model has not been fitted.")
+        X = np.asarray(X)
+        unique_ent = np.unique(np.concatenate((X[:, 0], X[:, 2])))
+        unique_rel = np.unique(X[:, 1])
+        return len(unique_ent) == len(self._ent_index) and len(unique_rel) == len(self._rel_index)
 
     def get_hyperparameter_dict(self):  # models/EmbeddingModel.py:338
         return self.all_params
@@ -277,15 +332,99 @@ class EmbeddingModel:
             raise ValueError("Invalid type for input X. Expected ndarray/EmgraphDataset object, got {}".format(type(X)))
         if X.ndim != 2 or X.shape[1] != 3:
             raise ValueError("Invalid size for input X. Expected (n,3):  got {}".format(X.shape))
-        if early_stopping:
-            raise NotImplementedError("early stopping is outside the B200 hot-path scope (SURVEY section 8f)")
         if focusE_numeric_edge_values is not None:
             raise NotImplementedError("FocusE edge weights are outside the B200 hot-path scope")
         self._ent_index = LabelIndex(np.unique(np.concatenate((X[:, 0], X[:, 2]))))
         self._rel_index = LabelIndex(np.unique(X[:, 1]))
         Xi = to_idx(X, self._ent_index, self._rel_index)
-        self._fit_idx(Xi, len(self._ent_index), len(self._rel_index))
+        self.early_stopping_params = early_stopping_params
+        try:
+            self._fit_idx(Xi, len(self._ent_index), len(self._rel_index), early_stopping=early_stopping)
+        finally:
+            self._after_training()
         return self
+
+    def _after_training(self):  # models/EmbeddingModel.py:1022-1042
+        if self.eval_dataset_handle is not None:
+            self.eval_dataset_handle.cleanup()
+            self.eval_dataset_handle = None
+        self.is_filtered = False
+        self.eval_config = {}
+
+    # ---- early stopping on the ranking kernel (models/EmbeddingModel.py:824-1020)
+    def _initialize_early_stopping(self):
+        from .evaluation import EvalDataset  # late import: evaluation imports this module
+        try:
+            x_valid = self.early_stopping_params["x_valid"]
+        except KeyError:
+            raise KeyError("x_valid must be passed for early fitting.")
+        if isinstance(x_valid, np.ndarray):
+            if x_valid.ndim <= 1 or np.shape(x_valid)[1] != 3:
+                raise ValueError("Invalid size for input x_valid. Expected (n,3):  got {}".format(np.shape(x_valid)))
+            valid_idx = to_idx(x_valid, self._ent_index, self._rel_index)
+        elif isinstance(x_valid, EvalDataset):
+            valid_idx = x_valid.test_idx
+        else:
+            raise ValueError("Invalid type for input X. Expected ndarray/EmgraphDataset object, got {}".format(type(x_valid)))
+        self.early_stopping_criteria = self.early_stopping_params.get("criteria", DEFAULT_CRITERIA_EARLY_STOPPING)
+        if self.early_stopping_criteria not in ["hits10", "hits1", "hits3", "mrr"]:
+            raise ValueError("Unsupported early stopping criteria.")
+        ce = self.early_stopping_params.get("corruption_entities", DEFAULT_CORRUPTION_ENTITIES)
+        if isinstance(ce, list):  # raw labels -> entity ids (:872-884)
+            ce = self._ent_index.lookup_known(np.asarray(ce))
+        elif isinstance(ce, str) and ce not in ("all", "batch"):
+            raise ValueError("Invalid value for corruption_entities: {}".format(ce))
+        self.eval_config["corruption_entities"] = ce
+        self.eval_config["corrupt_side"] = self.early_stopping_params.get("corrupt_side", DEFAULT_CORRUPT_SIDE_EVAL)
+        self.early_stopping_best_value = None
+        self.early_stopping_stop_counter = 0
+        self.early_stopping_epoch = None
+        filt_idx = None
+        if "x_filter" in self.early_stopping_params:
+            x_filter = self.early_stopping_params["x_filter"]
+            if isinstance(x_filter, np.ndarray):
+                if x_filter.ndim <= 1 or np.shape(x_filter)[1] != 3:
+                    raise ValueError("Invalid size for input x_valid. Expected (n,3):  got {}".format(np.shape(x_filter)))
+                filt_idx = to_idx(x_filter, self._ent_index, self._rel_index)
+            elif isinstance(x_valid, EvalDataset):
+                filt_idx = x_valid.filter_idx
+            self.set_filter_for_eval()
+        self.eval_dataset_handle = EvalDataset(valid_idx, filt_idx)
+
+    def _save_trained_params(self):  # models/EmbeddingModel.py:385-401 (device snapshot of the best parameters)
+        f = self._fit
+        self._best_params = (f["ent"].clone(), f["rel"].clone())
+
+    def _perform_early_stopping_test(self, epoch):
+        p = self.early_stopping_params
+        if not (epoch >= p.get("burn_in", DEFAULT_BURN_IN_EARLY_STOPPING)
+                and epoch % p.get("check_interval", DEFAULT_CHECK_INTERVAL_EARLY_STOPPING) == 0):
+            return False
+        from .evaluation import hits_at_n_score, mrr_score
+        f = self._fit
+        ranks = self._rank_with_params(f["eng"], f["ent"], f["rel"], self.eval_dataset_handle)
+        crit = self.early_stopping_criteria
+        current = mrr_score(ranks) if crit == "mrr" else hits_at_n_score(ranks, int(crit[4:]))
+        self.early_stopping_history.append((epoch, float(current)))
+        if self.early_stopping_best_value is None:  # first validation
+            self.early_stopping_best_value = current
+            self.early_stopping_first_value = current
+        elif self.early_stopping_best_value >= current:
+            self.early_stopping_stop_counter += 1
+            if self.early_stopping_stop_counter == p.get("stop_interval", DEFAULT_STOP_INTERVAL_EARLY_STOPPING):
+                # the best value never moved from the first one: keep the current parameters (:991-996)
+                if self.early_stopping_best_value == self.early_stopping_first_value:
+                    self._save_trained_params()
+                if self.verbose:
+                    print("Early stopping at epoch:{}".format(epoch))
+                    print("Best {}: {:10f}".format(crit, self.early_stopping_best_value))
+                self.early_stopping_epoch = epoch
+                return True
+        else:
+            self.early_stopping_best_value = current
+            self.early_stopping_stop_counter = 0
+            self._save_trained_params()
+        return False
 
     def _fit_prepare(self, E, R):
         """Allocate device parameters + optimizer state and freeze the per-step arguments."""
@@ -304,13 +443,33 @@ class EmbeddingModel:
                 st = dict(ent_m=torch.full_like(ent, 0.1), rel_m=torch.full_like(rel, 0.1))
             elif opt == 2:
                 st = dict(ent_m=torch.zeros_like(ent), rel_m=torch.zeros_like(rel))
+        # embedding_model_params['negative_corruption_entities'] (models/EmbeddingModel.py:732-777)
+        nce = self.embedding_model_params.get("negative_corruption_entities", DEFAULT_CORRUPTION_ENTITIES)
+        neg = {}
+        self._neg_batch = False
+        if isinstance(nce, str):
+            if nce == "batch":
+                self._neg_batch = True
+            elif nce != "all":
+                raise ValueError("Invalid value for negative_corruption_entities: {}".format(nce))
+        elif isinstance(nce, list):
+            ids = self._ent_index.lookup_known(np.asarray(nce)) if self._ent_index is not None else np.asarray(nce)
+            if len(ids) == 0:
+                raise ValueError("negative_corruption_entities: none of the supplied entities is known to the model")
+            neg["neg_entities"] = to_dev_i32(np.asarray(ids, dtype=np.int32), dev)
+        elif isinstance(nce, (int, np.integer)):
+            if not 0 < int(nce) <= E:
+                raise ValueError("negative_corruption_entities must be in (0, {}]".format(E))
+            neg["neg_entities_n"] = int(nce)
+        else:
+            raise ValueError("Invalid type for negative_corruption_entities: {}".format(type(nce)))
         self._fit = dict(
-            eng=eng, ent=ent, rel=rel, st=st, step=0, sides=self._train_sides(),
+            eng=eng, ent=ent, rel=rel, st=st, step=0, sides=self._train_sides(), neg=neg,
             loss_dev=torch.zeros(1, dtype=torch.float32, device=dev),
             loss_host=torch.zeros(1, dtype=torch.float32).pin_memory(),
             kw=dict(model=self._model_id(), loss=_lib.LOSS_IDS[self.loss], opt=opt, k=self.k, eta=self.eta,
                     flags=_lib.F_RESET_STATE if reset else 0, margin=float(self.loss_params.get("margin", DEFAULT_MARGIN_ADVERSARIAL if self.loss == "self_adversarial" else DEFAULT_MARGIN)),
-                    alpha=float(self.loss_params.get("alpha", DEFAULT_ALPHA_ADVERSARIAL)),
+                    alpha=float(self.loss_params.get("alpha", DEFAULT_ALPHA_ADVERSARIAL)), **self._reg,
                     lr=float(self.optimizer_params.get("lr", DEFAULT_LR)),
                     momentum=float(self.optimizer_params.get("momentum", DEFAULT_MOMENTUM)), seed=int(self.seed)))
         return self._fit
@@ -319,8 +478,11 @@ class EmbeddingModel:
         """One optimisation step on a device-resident batch; enqueue only, loss stays in f['loss_dev']."""
         f = self._fit
         f["step"] += 1
+        neg = f["neg"]
+        if self._neg_batch:  # corruptions drawn from the batch's own entities (evaluation/protocol.py:620-641)
+            neg = dict(neg_entities=torch.unique(pos_dev[:, [0, 2]]).to(torch.int32))
         a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=pos_dev, loss_out=f["loss_dev"],
-                                side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"])
+                                side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"], **neg)
         f["eng"].train_step(a)
 
     def _fit_step_host(self, pos_host, side="s,o"):
@@ -328,13 +490,20 @@ class EmbeddingModel:
         memory and the batch loss is read back (models/EmbeddingModel.py:1329-1337, :1421)."""
         f = self._fit
         f["step"] += 1
+        neg = f["neg"]
+        if self._neg_batch:
+            neg = dict(neg_entities=to_dev_i32(np.unique(pos_host[:, [0, 2]].numpy()), f["eng"].tdev))
         a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"],
-                                side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"])
+                                side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"], **neg)
         f["eng"].train_step_host(a, pos_host, f["loss_host"])
         return float(f["loss_host"][0])
 
-    def _fit_idx(self, Xi, E, R):
+    def _fit_idx(self, Xi, E, R, early_stopping=False):
         f = self._fit_prepare(E, R)
+        self._best_params = None
+        self.early_stopping_history = []
+        if early_stopping:
+            self._initialize_early_stopping()
         eng, ent, rel = f["eng"], f["ent"], f["rel"]
         N = Xi.shape[0]
         batch_size = int(np.ceil(N / self.batches_count))
@@ -373,13 +542,24 @@ class EmbeddingModel:
                 raise ValueError("Loss is {}. Please change the hyperparameters.".format(el))
             self.loss_history.append(el / denom)
             if self.verbose:
-                print("Average Loss: {:10f} -- epoch {}/{}".format(self.loss_history[-1], epoch, self.epochs))
+                msg = "Average Loss: {:10f} -- epoch {}/{}".format(self.loss_history[-1], epoch, self.epochs)
+                if early_stopping and self.early_stopping_best_value is not None:
+                    msg += " -- Best validation ({}): {:5f}".format(self.early_stopping_criteria, self.early_stopping_best_value)
+                print(msg)
+            if early_stopping and self._perform_early_stopping_test(epoch):
+                # the reference returns with the parameters of the best validation (:1471-1476)
+                if self._best_params is not None:
+                    f["ent"], f["rel"] = self._best_params
+                self._fit_finish()
+                return
         self._fit_finish()
 
     def _fit_finish(self):
         f = self._fit
+        self._best_params = None
         self._dev = {"ent": f["ent"], "rel": f["rel"]}
         self._opt_state = f["st"]
+        self._opt_step = f["step"]
         self.trained_model_params = [f["ent"].cpu().numpy(), f["rel"].cpu().numpy()]
         self.is_fitted = True
 
@@ -438,26 +618,58 @@ class EmbeddingModel:
         if not self.is_fitted:
             raise RuntimeError("Model has not been fitted.")
         self.eval_dataset_handle = dataset_handle
-        side = self.eval_config.get("corrupt_side", DEFAULT_CORRUPT_SIDE_EVAL)
-        strategy = self.eval_config.get("ranking_strategy", DEFAULT_RANK_COMPARE_STRATEGY)
-        assert strategy in ("worst", "best", "middle"), "Invalid score comparision type!"
-        if self.eval_config.get("corruption_entities", DEFAULT_CORRUPTION_ENTITIES) is not None and not isinstance(
-                self.eval_config.get("corruption_entities", DEFAULT_CORRUPTION_ENTITIES), str):
-            raise NotImplementedError("entities_subset ranking is outside the B200 hot-path scope (SURVEY section 8f)")
         eng = get_engine(self.engine_params.get("device"))
         ent, rel = self._device_params()
+        return self._rank_with_params(eng, ent, rel, dataset_handle)
+
+    def _rank_with_params(self, eng, ent, rel, dataset_handle):
+        """Ranks of the handle's triples under eval_config with the given device parameters (shared by
+        get_ranks and the early-stopping check, which ranks with the parameters being trained)."""
+        side = self.eval_config.get("corrupt_side", DEFAULT_CORRUPT_SIDE_EVAL)
+        strategy = self.eval_config.get("ranking_strategy", DEFAULT_RANK_COMPARE_STRATEGY)
+        assert side in _lib.RANK_SIDE_IDS, "Invalid value for corrupt_side."
+        assert strategy in ("worst", "best", "middle"), "Invalid score comparision type!"
+        ce = self.eval_config.get("corruption_entities", DEFAULT_CORRUPTION_ENTITIES)
         filtered = bool(self.is_filtered)
-        if filtered:
-            dataset_handle.build_filter(eng, ent.shape[0], rel.shape[0])
         mid = self._model_id()
         use_tc = bool(self.engine_params.get("rank_tensor_cores", False)) and self.name != "TransE"
-        # host buffers in, host buffers out (one H2D of the test triples, one D2H of the ranks)
-        test_h = dataset_handle.test_host_pinned()
-        T = test_h.shape[0]
-        ranks_h = torch.empty((T, 2) if side == "s,o" else (T,), dtype=torch.int32).pin_memory()
-        eng.rank_host(mid, self.k, ent, rel, test_h, ranks_h, side=_lib.RANK_SIDE_IDS[side],
-                      strategy=_lib.STRATEGY_IDS[strategy], filtered=filtered, use_tensor_cores=use_tc)
-        return ranks_h.numpy().copy()
+        E, R = ent.shape[0], rel.shape[0]
+        if ce is None or isinstance(ce, str):
+            if filtered:
+                dataset_handle.build_filter(eng, E, R)
+            # host buffers in, host buffers out (one H2D of the test triples, one D2H of the ranks)
+            test_h = dataset_handle.test_host_pinned()
+            T = test_h.shape[0]
+            ranks_h = torch.empty((T, 2) if side == "s,o" else (T,), dtype=torch.int32).pin_memory()
+            eng.rank_host(mid, self.k, ent, rel, test_h, ranks_h, side=_lib.RANK_SIDE_IDS[side],
+                          strategy=_lib.STRATEGY_IDS[strategy], filtered=filtered, use_tensor_cores=use_tc)
+            return ranks_h.numpy().copy()
+        # ---- entities_subset: corruptions only from `ce` (models/EmbeddingModel.py:1845-1857, :1898-1940).
+        # The entities are re-labelled so that the subset occupies rows [0,|C|) of a permuted table; the sweep
+        # then covers exactly those rows and the (re-labelled) filter applies unchanged.
+        dev = eng.tdev
+        C = torch.unique(torch.as_tensor(np.asarray(ce, dtype=np.int64).reshape(-1), device=dev))
+        assert C.numel() > 0 and int(C.min()) >= 0 and int(C.max()) < E, "corruption_entities out of range"
+        in_c = torch.zeros(E, dtype=torch.bool, device=dev)
+        in_c[C] = True
+        order = torch.cat([C, (~in_c).nonzero().squeeze(1)])  # new row -> old id
+        perm = torch.empty(E, dtype=torch.int64, device=dev)
+        perm[order] = torch.arange(E, device=dev)  # old id -> new row
+        ent_p = ent.index_select(0, order).contiguous()
+        test = dataset_handle.test_device(dev).long()
+        T = test.shape[0]
+        if T == 0:
+            return np.zeros((0, 2) if side == "s,o" else (0,), np.int32)
+        test_p = torch.stack([perm[test[:, 0]], test[:, 1], perm[test[:, 2]]], 1).to(torch.int32).contiguous()
+        if filtered:
+            dataset_handle.build_filter(eng, E, R, perm=perm)
+        nC = int(C.numel())
+        counts = eng.rank_counts(mid, self.k, ent_p, rel, test_p, side=_lib.RANK_SIDE_IDS[side], filtered=filtered,
+                                 use_tensor_cores=use_tc, ent_local=ent_p[:nC], row_begin=0, row_end=nC)
+        self_cand = torch.stack([in_c[test[:, 0]], in_c[test[:, 2]]], 1).to(torch.uint8).contiguous()
+        ranks = eng.rank_finalize(counts, side=_lib.RANK_SIDE_IDS[side], strategy=_lib.STRATEGY_IDS[strategy], filtered=filtered,
+                                  self_is_candidate=self_cand)
+        return ranks.cpu().numpy()
 
 
 @register_model("TransE")

@@ -97,6 +97,18 @@ typedef struct kge_train_args {
     float*   grad_tails;
     int64_t  grad_tail_stride;
     float    alpha;        /* self_adversarial sampling temperature (losses/self_adversarial.py:75) */
+    /* LP regulariser (regularizers/lp.py:81-113): loss += lambda_ent*sum|ent|^p + lambda_rel*sum|rel|^p over the
+     * WHOLE tables (reg_p = 0: off).  Every row then has a gradient: touched rows get it added in the
+     * reduction, the others are updated by a dense pass; the penalty is added to loss_out (by
+     * kge_train_apply for the rows of [row_begin,row_end), relations counted where row_begin == 0). */
+    int32_t  reg_p;
+    float    reg_lambda_ent, reg_lambda_rel;
+    /* embedding_model_params['negative_corruption_entities'] (models/EmbeddingModel.py:732-777,
+     * evaluation/protocol.py:610-641): in-kernel replacements are drawn uniformly from neg_entities
+     * [neg_entities_n] (device int32 ids: a supplied list, or the batch's unique entities), or from the first
+     * neg_entities_n entities when neg_entities is NULL and neg_entities_n > 0; 0 / NULL = all entities. */
+    const int32_t* neg_entities;
+    int64_t  neg_entities_n;
 } kge_train_args;
 
 int         kge_abi_version(void);
@@ -190,9 +202,12 @@ int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* ent, const 
                     const float* ent_local, int64_t row_begin, int64_t row_end,
                     const int32_t* test, int64_t T, int side, int filtered, int use_tensor_cores,
                     int32_t* counts, void* stream);
-/* ranks_out: [T,2] (col 0 subject, col 1 object) for KGE_RANK_S_O, else [T]. */
+/* ranks_out: [T,2] (col 0 subject, col 1 object) for KGE_RANK_S_O, else [T].
+ * self_is_candidate: optional device uint8 [T,2] (col 0 subject, col 1 object): 0 when the test triple's own
+ * entity was NOT among the swept candidates (entities_subset ranking, models/EmbeddingModel.py:1845-1857,
+ * :1898-1940); NULL = every test entity is a candidate (all-entity sweep). */
 int kge_rank_finalize(kge_ctx* ctx, const int32_t* counts, int64_t T, int side, int strategy,
-                      int filtered, int32_t* ranks_out, void* stream);
+                      int filtered, const uint8_t* self_is_candidate, int32_t* ranks_out, void* stream);
 
 /* Host-buffer form of evaluate_performance's device work for a single-GPU table: test_host [T,3]
  * int32 in, ranks_host ([T,2] for KGE_RANK_S_O else [T]) out; synchronises the stream. */

@@ -271,7 +271,8 @@ def optimizer_step(opt, w, g, touched, lr, state=None, step=1, momentum=0.9, dty
 # one training step  (models/EmbeddingModel.py:614-822 + optimizer.minimize :1415-1418)
 # --------------------------------------------------------------------------------------------
 def train_step(model, k, loss, eta, ent, rel, pos, keep_subj, repl, margin=1.0, norm=1,
-               opt=None, lr=5e-4, state=None, step=1, dtype=np.float32, grad_dtype=np.float64, alpha=0.5):
+               opt=None, lr=5e-4, state=None, step=1, dtype=np.float32, grad_dtype=np.float64, alpha=0.5,
+               reg_p=0, reg_lambda_ent=0.0, reg_lambda_rel=0.0):
     """Forward in `dtype` (the reference is fp32), gradients in `grad_dtype`.
     Returns dict(loss, scores_pos, scores_neg, grad_ent[E,K], grad_rel[R,K], touched_ent, touched_rel
     [, ent_new, rel_new, state_ent, state_rel])."""
@@ -297,6 +298,15 @@ def train_step(model, k, loss, eta, ent, rel, pos, keep_subj, repl, margin=1.0, 
     t_ent[neg[:, 2]] = True
     t_rel = np.zeros(rel.shape[0], bool)
     t_rel[pos[:, 1]] = True
+    if reg_p > 0 and (reg_lambda_ent != 0 or reg_lambda_rel != 0):
+        # regularizers/lp.py:106-111 : loss += lambda_i * sum(|param_i|^p) over the whole tables
+        # (models/EmbeddingModel.py:818-820) => every row has a gradient
+        for w, gacc, lam in ((ent, g_ent, reg_lambda_ent), (rel, g_rel, reg_lambda_rel)):
+            w64 = np.asarray(w, dtype=gd)
+            val = dtype(val + dtype(lam) * np.sum(np.abs(np.asarray(w, dtype=dtype)) ** reg_p, dtype=dtype))
+            gacc += lam * reg_p * np.abs(w64) ** (reg_p - 1) * np.sign(w64)
+        t_ent[:] = True
+        t_rel[:] = True
     out = dict(loss=val, scores_pos=sp, scores_neg=sn, grad_ent=g_ent, grad_rel=g_rel,
                touched_ent=t_ent, touched_rel=t_rel, neg=neg)
     if opt is not None:
@@ -361,18 +371,29 @@ def compare(score_corr, score_pos, strategy="worst"):
     return int(np.sum(c >= p))
 
 
-def rank_one(model, k, ent, rel, x, filt=None, side="s,o", strategy="worst", norm=1, dtype=np.float32):
-    """Per-test-triple rank (models/EmbeddingModel.py:1856-1866, :1883-1892, :1942-1986)."""
+def rank_one(model, k, ent, rel, x, filt=None, side="s,o", strategy="worst", norm=1, dtype=np.float32, subset=None):
+    """Per-test-triple rank (models/EmbeddingModel.py:1856-1866, :1883-1892, :1942-1986).
+
+    subset: optional entity ids used to generate the corruptions (eval_config['corruption_entities'],
+    :1845-1857); the filter indices are then re-mapped to positions in that list and the entities outside it
+    masked out (:1898-1940).  That branch of the reference is dead code under TF2 (tf.contrib hash table,
+    SURVEY F3), so it is restated from its body and NOT pinned against reference-executed outputs."""
     E = ent.shape[0]
     x = np.asarray(x).reshape(3)
-    corr = corruptions_for_eval(x, np.arange(E), side)
+    cand = np.arange(E) if subset is None else np.asarray(subset, dtype=np.int64).reshape(-1)
+    C = cand.shape[0]
+    corr = corruptions_for_eval(x, cand, side)
     sc = score(model, k, ent, rel, corr, norm, dtype)
     sp = score(model, k, ent, rel, x, norm, dtype)[0]
     hi_o = hi_s = 0
     if filt is not None:
         idx_o, idx_s = filt.participating(x)
+        if subset is not None:
+            pos_of = {int(e): i for i, e in enumerate(cand)}
+            idx_o = np.asarray([pos_of[int(e)] for e in idx_o if int(e) in pos_of], np.int64)
+            idx_s = np.asarray([pos_of[int(e)] for e in idx_s if int(e) in pos_of], np.int64)
     if side == "s,o":
-        obj_sc, sub_sc = sc[:E], sc[E:]
+        obj_sc, sub_sc = sc[:C], sc[C:]
         if filt is not None:
             hi_o = compare(obj_sc[idx_o], sp, strategy)
             hi_s = compare(sub_sc[idx_s], sp, strategy)
@@ -381,17 +402,18 @@ def rank_one(model, k, ent, rel, x, filt=None, side="s,o", strategy="worst", nor
         if side in ("o", "s+o"):
             hi_o = compare(sc[idx_o], sp, strategy)
         if side == "s+o":
-            hi_s = compare(sc[idx_s + E], sp, strategy)
+            hi_s = compare(sc[idx_s + C], sp, strategy)
         elif side == "s":
             hi_s = compare(sc[idx_s], sp, strategy)
     return compare(sc, sp, strategy) + 1 - hi_s - hi_o
 
 
-def ranks(model, k, ent, rel, test, filter_triples=None, side="s,o", strategy="worst", norm=1, dtype=np.float32):
+def ranks(model, k, ent, rel, test, filter_triples=None, side="s,o", strategy="worst", norm=1, dtype=np.float32,
+          subset=None):
     """Intended semantics of get_ranks: the per-triple graph evaluated for EVERY test triple
     (models/EmbeddingModel.py:2046-2099)."""
     filt = FilterIndex(filter_triples) if filter_triples is not None else None
-    return np.asarray([rank_one(model, k, ent, rel, x, filt, side, strategy, norm, dtype)
+    return np.asarray([rank_one(model, k, ent, rel, x, filt, side, strategy, norm, dtype, subset)
                        for x in np.asarray(test).reshape(-1, 3)])
 
 

@@ -42,6 +42,14 @@ TRAIN_CASES = [
     ("hole_selfadv", "HolE", "self_adversarial", 8, 5, 48, 3, 30, "s,o", {}, {}),
 ]
 
+# LP regulariser (regularizers/lp.py:81-113): name, base train case fields..., regularizer_params
+REG_CASES = [
+    ("distmult_nll_l2", "DistMult", "nll", 12, 4, 64, 5, 40, "s,o", {}, {}, {"p": 2, "lambda": 1e-2}),
+    ("complex_pairwise_l3", "ComplEx", "pairwise", 8, 4, 48, 4, 30, "s,o", {"margin": 1.0}, {}, {"p": 3, "lambda": [1e-2, 5e-2]}),
+    ("transe_l1_pairwise_l1", "TransE", "pairwise", 10, 3, 50, 3, 25, "s,o", {"margin": 2.0}, {}, {"p": 1, "lambda": 1e-3}),
+]
+TRAIN_CASES = [c + (None,) for c in TRAIN_CASES] + REG_CASES
+
 RANK_CASES = [
     # name, model, k, E, R, F, T, emb_params, scale
     ("rank_transe_l1", "TransE", 10, 120, 4, 900, 60, {}, 0.5),
@@ -60,7 +68,7 @@ def main():
     def wanted(name):
         return not only or any(o in name for o in only)
 
-    for ci, (name, model, loss, k, eta, E, R, n, side, lp, ep) in enumerate(TRAIN_CASES):
+    for ci, (name, model, loss, k, eta, E, R, n, side, lp, ep, rp) in enumerate(TRAIN_CASES):
         if not wanted("train_" + name):
             continue
         rng = np.random.Generator(np.random.PCG64(1000 + ci))
@@ -70,11 +78,15 @@ def main():
         pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
         keep = ko.side_mask(side, n * eta, rng)
         repl = rng.integers(0, E, n * eta).astype(np.int32)
-        ref = ref_shim.ref_train_forward_backward(model, k, eta, loss, ent, rel, pos, keep, repl, lp, ep, side)
+        ref = ref_shim.ref_train_forward_backward(model, k, eta, loss, ent, rel, pos, keep, repl, lp, ep, side,
+                                                  "LP" if rp else None, rp)
+        lam = (rp or {}).get("lambda", 0.0)
+        lam = [lam, lam] if np.isscalar(lam) else list(lam)
         np.savez_compressed(
             os.path.join(OUT, "train_%s.npz" % name),
             model=model, loss_name=loss, k=k, eta=eta, side=side,
             margin=float(lp.get("margin", 3.0 if loss == "self_adversarial" else 1.0)), alpha=float(lp.get("alpha", 0.5)),
+            reg_p=int((rp or {}).get("p", 0)), reg_lambda_ent=float(lam[0]), reg_lambda_rel=float(lam[1]),
             norm=int(ep.get("norm", 1)), ent=ent, rel=rel, pos=pos, keep_subj=keep, repl=repl,
             loss=np.float32(ref["loss"]), scores_pos=ref["scores_pos"], scores_neg=ref["scores_neg"],
             neg=ref["neg"].astype(np.int32), grad_ent=ref["grad_ent"], grad_rel=ref["grad_rel"])

@@ -186,20 +186,22 @@ def load():
 # ------------------------------------------------------------------------------------------------
 # harness: drives the reference's own methods the way _get_model_loss / the eval graph do
 # ------------------------------------------------------------------------------------------------
-def make_model(name, k, eta, loss, loss_params=None, embedding_model_params=None):
+def make_model(name, k, eta, loss, loss_params=None, embedding_model_params=None, regularizer=None, regularizer_params=None):
     ns = load()
     cls = getattr(ns.models, name)
     return cls(k=k, eta=eta, loss=loss, loss_params=loss_params or {},
-               embedding_model_params=embedding_model_params or {})
+               embedding_model_params=embedding_model_params or {}, regularizer=regularizer,
+               regularizer_params=dict(regularizer_params or {}))
 
 
 def ref_train_forward_backward(name, k, eta, loss, ent, rel, pos, keep_subj, repl,
-                               loss_params=None, embedding_model_params=None, side="s,o"):
+                               loss_params=None, embedding_model_params=None, side="s,o", regularizer=None,
+                               regularizer_params=None):
     """models/EmbeddingModel.py:675-677, :724-729, :788-816 executed with the reference's own
     _lookup_embeddings/_fn/generate_corruptions_for_fit/loss.apply; backward by torch autograd
     (stands in for tf.GradientTape).  Returns loss, scores, dense row gradients."""
     ns = load()
-    model = make_model(name, k, eta, loss, loss_params, embedding_model_params)
+    model = make_model(name, k, eta, loss, loss_params, embedding_model_params, regularizer, regularizer_params)
     model.ent_emb = torch.tensor(ent, dtype=torch.float32, requires_grad=True)
     model.rel_emb = torch.tensor(rel, dtype=torch.float32, requires_grad=True)
     x_pos = torch.as_tensor(np.asarray(pos), dtype=torch.int32)
@@ -218,6 +220,8 @@ def ref_train_forward_backward(name, k, eta, loss, ent, rel, pos, keep_subj, rep
     e_s, e_p, e_o = model._lookup_embeddings(x_neg)
     scores_neg = model._fn(e_s, e_p, e_o)
     loss_t = model.loss.apply(scores_pos, scores_neg)
+    if model.regularizer is not None:  # models/EmbeddingModel.py:818-820
+        loss_t = loss_t + model.regularizer.apply([model.ent_emb, model.rel_emb])
     loss_t.backward()
     return dict(loss=float(loss_t.detach()), scores_pos=sp_out,
                 scores_neg=scores_neg.detach().numpy().copy(), neg=x_neg.numpy().copy(),

@@ -54,14 +54,17 @@ def test_struct_layout_matches_header():
     import subprocess
     import tempfile
     L = _lib()
-    src = '#include <stdio.h>\n#include <stddef.h>\n#include "kge_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(kge_table), sizeof(kge_train_args), offsetof(kge_train_args, ent), offsetof(kge_train_args, pos), offsetof(kge_train_args, dbg_grad_rel));return 0;}\n'
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "kge_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(kge_table), sizeof(kge_train_args), offsetof(kge_train_args, ent), offsetof(kge_train_args, pos), offsetof(kge_train_args, dbg_grad_rel), offsetof(kge_train_args, stage), offsetof(kge_train_args, alpha), offsetof(kge_train_args, neg_entities_n));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         p = os.path.join(d, "t.c")
         open(p, "w").write(src)
         exe = os.path.join(d, "t")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), p, "-o", exe], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
-    st, sa, o_ent, o_pos, o_last = (int(v) for v in out)
+    st, sa, o_ent, o_pos, o_last, o_stage, o_alpha, o_negn = (int(v) for v in out)
+    assert L.KgeTrainArgs.stage.offset == o_stage
+    assert L.KgeTrainArgs.alpha.offset == o_alpha
+    assert L.KgeTrainArgs.neg_entities_n.offset == o_negn
     assert C.sizeof(L.KgeTable) == st
     assert C.sizeof(L.KgeTrainArgs) == sa
     assert L.KgeTrainArgs.ent.offset == o_ent
@@ -131,3 +134,67 @@ def test_evaluate_performance_argument_checks():
     m = DistMult(k=4)
     with pytest.raises(AssertionError):
         evaluate_performance(np.zeros((0, 3)), m, corrupt_side="x")
+
+
+def test_regularizer_and_loss_hyperparameters():
+    # regularizers/lp.py:41-104, losses/_loss_constants.py:8-12
+    from emgraph_b200.models import ComplEx
+    m = ComplEx(k=4, regularizer="LP", regularizer_params={"p": 3, "lambda": [1e-3, 1e-2]})
+    assert m._reg == dict(reg_p=3, reg_lambda_ent=1e-3, reg_lambda_rel=1e-2)
+    assert ComplEx(k=4, regularizer="LP", regularizer_params={})._reg == dict(reg_p=2, reg_lambda_ent=1e-5, reg_lambda_rel=1e-5)
+    assert ComplEx(k=4)._reg["reg_p"] == 0
+    with pytest.raises(Exception):
+        ComplEx(k=4, regularizer="LP", regularizer_params={"p": 1.5})
+    with pytest.raises(ValueError):
+        ComplEx(k=4, regularizer="LP", regularizer_params={"lambda": [1.0, 2.0, 3.0]})
+    for loss in ("absolute_margin", "self_adversarial"):
+        assert ComplEx(k=4, loss=loss).loss == loss
+
+
+def test_save_restore_roundtrip_host(tmp_path):
+    # utils/model_utils.py:22-160 : same pickle dictionary as the reference
+    import pickle
+    from emgraph_b200 import restore_model, save_model
+    from emgraph_b200.models import DistMult, LabelIndex
+    m = DistMult(k=3, eta=2, epochs=7, batches_count=2, seed=5, loss="pairwise", loss_params={"margin": 2.0})
+    m._ent_index = LabelIndex(np.array(["a", "b", "c"]))
+    m._rel_index = LabelIndex(np.array(["x"]))
+    m.trained_model_params = [np.arange(9, dtype=np.float32).reshape(3, 3), np.ones((1, 3), np.float32)]
+    m.is_fitted = True
+    path = str(tmp_path / "m.pkl")
+    save_model(m, path)
+    obj = pickle.load(open(path, "rb"))
+    assert set(obj) >= {"class_name", "hyperparams", "is_fitted", "ent_to_idx", "rel_to_idx", "is_calibrated", "model_params",
+                        "large_graph", "calibration_parameters"}
+    assert obj["class_name"] == "DistMult" and obj["ent_to_idx"] == {"a": 0, "b": 1, "c": 2}
+    r = restore_model(path)
+    assert type(r) is DistMult and r.is_fitted and r.all_params == m.all_params
+    assert r.ent_to_idx == m.ent_to_idx and r.rel_to_idx == m.rel_to_idx
+    np.testing.assert_array_equal(r.trained_model_params[0], m.trained_model_params[0])
+    np.testing.assert_array_equal(r.get_embeddings(np.array(["c", "a"])), m.trained_model_params[0][[2, 0]])
+    assert r.is_fitted_on(np.array([["a", "x", "b"], ["b", "x", "c"]])) and not r.is_fitted_on(np.array([["a", "x", "b"]]))
+    with pytest.raises(FileNotFoundError):
+        restore_model(str(tmp_path / "missing.pkl"))
+
+
+def test_lookup_known_drops_unknown_labels():
+    from emgraph_b200.models import LabelIndex
+    li = LabelIndex(np.array(["a", "b", "d", "e"]))
+    np.testing.assert_array_equal(li.lookup_known(np.array(["e", "zz", "a", "a"])), [0, 3])
+    assert li.lookup_known(np.array(["q"])).size == 0
+
+
+def test_early_stopping_argument_checks():
+    from emgraph_b200.models import DistMult, LabelIndex
+    m = DistMult(k=3)
+    m._ent_index = LabelIndex(np.array(["a", "b"]))
+    m._rel_index = LabelIndex(np.array(["x"]))
+    m.early_stopping_params = {}
+    with pytest.raises(KeyError):
+        m._initialize_early_stopping()
+    m.early_stopping_params = {"x_valid": np.array([["a", "x", "b"]]), "criteria": "nope"}
+    with pytest.raises(ValueError):
+        m._initialize_early_stopping()
+    m.early_stopping_params = {"x_valid": np.array(["a", "x", "b"])}
+    with pytest.raises(ValueError):
+        m._initialize_early_stopping()

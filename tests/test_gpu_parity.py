@@ -36,8 +36,14 @@ def _close(a, b, rtol=RTOL, scale=None):
     np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * sc)
 
 
+def _reg_kw(g):
+    if "reg_p" not in g.files or int(g["reg_p"]) == 0:
+        return {}
+    return dict(reg_p=int(g["reg_p"]), reg_lambda_ent=float(g["reg_lambda_ent"]), reg_lambda_rel=float(g["reg_lambda_rel"]))
+
+
 def run_step(engine, model, k, loss, eta, ent, rel, pos, keep, repl, margin=1.0, norm=1, opt="adam", lr=1e-3,
-             flags=0, state=None, step=1, alpha=0.5):
+             flags=0, state=None, step=1, alpha=0.5, **reg):
     from emgraph_b200 import _lib
     n = pos.shape[0]
     ent_d, rel_d = _dev(ent), _dev(rel)
@@ -49,7 +55,7 @@ def run_step(engine, model, k, loss, eta, ent, rel, pos, keep, repl, margin=1.0,
     a = engine.train_args(model=_ids(model, norm), loss=_lib.LOSS_IDS[loss], opt=_lib.OPT_IDS[opt], k=k, eta=eta,
                           ent=ent_d, rel=rel_d, pos=_dev(pos, torch.int32), loss_out=out["loss"], flags=flags,
                           margin=margin, alpha=alpha, lr=lr, step=step, repl=_dev(repl, torch.int32), keep_subj=_dev(keep, torch.uint8),
-                          dbg_scores=out["scores"], dbg_grad_ent=out["g_ent"], dbg_grad_rel=out["g_rel"], **st)
+                          dbg_scores=out["scores"], dbg_grad_ent=out["g_ent"], dbg_grad_rel=out["g_rel"], **st, **reg)
     engine.train_step(a)
     torch.cuda.synchronize()
     res = {k_: v.cpu().numpy() for k_, v in out.items()}
@@ -66,7 +72,7 @@ def test_train_step_vs_reference_golden(engine, path):
     model, k, eta = str(g["model"]), int(g["k"]), int(g["eta"])
     r = run_step(engine, model, k, str(g["loss_name"]), eta, g["ent"], g["rel"], g["pos"], g["keep_subj"], g["repl"],
                  margin=float(g["margin"]), norm=int(g["norm"]), flags=_lib.F_NO_UPDATE,
-                 alpha=float(g["alpha"]) if "alpha" in g.files else 0.5)
+                 alpha=float(g["alpha"]) if "alpha" in g.files else 0.5, **_reg_kw(g))
     n = g["pos"].shape[0]
     _close(r["scores"][:n], g["scores_pos"])
     _close(r["scores"][n:], g["scores_neg"])
@@ -161,6 +167,34 @@ def test_train_step_vs_oracle_bench_shapes(engine, model, loss, k, eta):
     else:
         _close(r["g_ent"], o["grad_ent"])
         _close(r["g_rel"], o["grad_rel"])
+
+
+@pytest.mark.parametrize("opt,p", [("sgd", 2), ("adam", 3), ("adagrad", 1), ("momentum", 2)])
+def test_lp_regulariser_updates_every_row(engine, opt, p):
+    """LP penalty (regularizers/lp.py:81-113): rows the batch touches get the penalty gradient added in the
+    reduction, all other rows are updated by the dense pass; loss includes the penalty of the whole tables."""
+    from emgraph_b200 import _lib
+    rng = np.random.default_rng(17 + p)
+    E, R, k, eta, n, model = 900, 6, 20, 5, 100, "ComplEx"
+    K = ko.internal_k(model, k)
+    ent = rng.uniform(-0.4, 0.4, size=(E, K)).astype(np.float32)
+    rel = rng.uniform(-0.4, 0.4, size=(R, K)).astype(np.float32)
+    pos = np.stack([rng.integers(0, E, n), rng.integers(0, R - 1, n), rng.integers(0, E, n)], 1).astype(np.int32)
+    keep = rng.integers(0, 2, n * eta).astype(np.uint8)
+    repl = rng.integers(0, E, n * eta).astype(np.int32)
+    reg = dict(reg_p=p, reg_lambda_ent=3e-2, reg_lambda_rel=1e-1)
+    r = run_step(engine, model, k, "nll", eta, ent, rel, pos, keep, repl, opt=opt, lr=1e-2, flags=_lib.F_RESET_STATE, **reg)
+    o = ko.train_step(model, k, "nll", eta, ent, rel, pos, keep, repl, opt=opt, lr=1e-2, **reg)
+    np.testing.assert_allclose(r["loss"][0], o["loss"], rtol=RTOL)
+    _close(r["g_ent"], o["grad_ent"])
+    _close(r["g_rel"], o["grad_rel"])
+    if opt == "adam":
+        big = np.abs(o["grad_ent"]) > 1e-4
+        np.testing.assert_allclose(r["ent"][big], o["ent_new"][big], rtol=1e-5, atol=1e-6)
+        assert (r["ent"] != ent).mean() > 0.99  # every row moved, touched or not
+    else:
+        np.testing.assert_allclose(r["ent"], o["ent_new"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(r["rel"], o["rel_new"], rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("E,n,eta", [(12, 300, 6), (40, 257, 20), (700, 64, 3)])
