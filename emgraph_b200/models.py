@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .optimizers import SGDSchedule
 from .engine import get_engine, internal_k, model_id, to_dev_i32
 
 # utils/constants.py
@@ -516,6 +517,7 @@ class EmbeddingModel:
         normalize = bool(self.embedding_model_params.get("normalize_ent_emb", False))
         check_every = int(self.engine_params.get("nan_check_every", self.batches_count))
         self.loss_history = []
+        sched = SGDSchedule(self.optimizer_params, self.batches_count) if self.optimizer == "sgd" else None
         denom = batch_size * (self.eta if self.loss in TILED_POSITIVE_LOSSES else 1) * self.batches_count  # :1343-1344, :1453-1457
         for epoch in range(1, self.epochs + 1):
             epoch_loss.zero_()
@@ -524,6 +526,8 @@ class EmbeddingModel:
                 lo, hi = b * batch_size, min(N, (b + 1) * batch_size)
                 if hi <= lo:
                     continue
+                if sched is not None:  # sgd: decayed rate of this batch (training/sgd.py:127-185)
+                    f["kw"]["lr"] = float(sched(b + 1, epoch))
                 for side in f["sides"]:
                     if host_batches:
                         lv = self._fit_step_host(Xh[lo:hi], side)

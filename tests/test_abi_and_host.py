@@ -198,3 +198,21 @@ def test_early_stopping_argument_checks():
     m.early_stopping_params = {"x_valid": np.array(["a", "x", "b"])}
     with pytest.raises(ValueError):
         m._initialize_early_stopping()
+
+
+def test_sgd_schedule_reference_goldens():
+    # reference tests/emgraph/models/test_optimizers.py:6-79 (exact values, compared with == there too)
+    from emgraph_b200.optimizers import SGDSchedule
+    s = SGDSchedule({"lr": 0.001}, 10)
+    v = [s(b, e) for e in range(1, 11) for b in range(1, 11)][-1]
+    assert v == 0.001
+    s = SGDSchedule({"lr": 0.001, "decay_lr_rate": 2, "cosine_decay": False, "decay_cycle": 10}, 10)
+    v = [s(b, e) for e in range(1, 11) for b in range(1, 11)][-1]
+    assert v == 0.001 and s(1, 11) == 0.0005
+    s = SGDSchedule({"lr": 0.001, "end_lr": 0.00001, "decay_lr_rate": 2, "expand_factor": 2, "cosine_decay": True, "decay_cycle": 10}, 10)
+    seen = {}
+    for e in range(1, 31):
+        for b in range(1, 11):
+            seen[(e, b)] = s(b, e)
+    assert seen[(11, 1)] == 0.0005 and seen[(6, 1)] == 0.000505 and seen[(21, 1)] == 0.000255
+    assert s(1, 31) == 0.00025
