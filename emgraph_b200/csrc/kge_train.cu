@@ -964,22 +964,22 @@ extern "C" int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* g
 template <int V>
 __global__ void __launch_bounds__(256) kge_push_rows_kernel(const int32_t* __restrict__ keys, int64_t n_keys, int64_t S, int64_t ent_slots,
                                                             const float* __restrict__ shard, int64_t row_begin, int64_t row_end, int K,
-                                                            TableView stage) {
+                                                            TableView stage, int64_t t_start) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int nvec = K / V;
-    // every lane tests one slot; owned slots are then copied by the whole warp, two rows in flight
-    for (int64_t t0 = warp * 32; t0 < n_keys; t0 += nwarps * 32) {
-        const int64_t t = t0 + lane;
+    // every lane tests one slot; owned slots are then copied by the whole warp, two rows in flight.
+    // Blocks of 32 slots are dealt round-robin over the destination ranks, starting behind this owner
+    // (t_start = own + 1): at any moment every owner's stores are spread over all W destinations, so no
+    // rank's NVLink ingress is the target of all owners at once (the all-to-all pattern)
+    const int W = stage.n_shards;
+    const int64_t bpr = (S + 31) / 32;  // blocks per rank
+    for (int64_t vb = warp; vb < bpr * W; vb += nwarps) {
+        const int rr = (int)((vb + t_start) % W);
+        const int64_t tl = (vb / W) * 32 + lane;
         int32_t key = -1;
-        int rr = 0;
-        int64_t tl = 0;
-        if (t < n_keys) {
-            rr = (int)(t / S);
-            tl = t - (int64_t)rr * S;
-            if (tl < ent_slots) key = keys[t];
-        }
+        if (tl < ent_slots) key = keys[(int64_t)rr * S + tl];
         unsigned own = __ballot_sync(0xffffffffu, key >= row_begin && key < row_end);
         while (own) {
             const int l0 = __ffs(own) - 1;
@@ -987,29 +987,28 @@ __global__ void __launch_bounds__(256) kge_push_rows_kernel(const int32_t* __res
             const int l1 = own ? __ffs(own) - 1 : -1;
             if (l1 >= 0) own &= own - 1;
             const int32_t k0 = __shfl_sync(0xffffffffu, key, l0);
-            const int r0 = __shfl_sync(0xffffffffu, rr, l0);
-            const int64_t s0 = __shfl_sync(0xffffffffu, tl, l0);
+            const int r0 = rr, r1 = rr;
+            const int64_t s0 = (vb / W) * 32 + l0;
             const int32_t k1 = __shfl_sync(0xffffffffu, key, max(l1, 0));
-            const int r1 = __shfl_sync(0xffffffffu, rr, max(l1, 0));
-            const int64_t s1 = __shfl_sync(0xffffffffu, tl, max(l1, 0));
+            const int64_t s1 = (vb / W) * 32 + max(l1, 0);
             const float* a = shard + (int64_t)(k0 - row_begin) * K;
             const float* b = shard + (int64_t)(k1 - row_begin) * K;
             float* da = stage.shard[r0] + s0 * K;
             float* db = stage.shard[r1] + s1 * K;
             for (int c = lane; c < nvec; c += 64) {
-                float va[V], vb[V], vc[V], vd[V];
+                float xa[V], xb[V], xc[V], xd[V];
                 const bool two = c + 32 < nvec;
-                ld_vec<V>(va, a + (size_t)c * V);
-                if (two) ld_vec<V>(vc, a + (size_t)(c + 32) * V);
+                ld_vec<V>(xa, a + (size_t)c * V);
+                if (two) ld_vec<V>(xc, a + (size_t)(c + 32) * V);
                 if (l1 >= 0) {
-                    ld_vec<V>(vb, b + (size_t)c * V);
-                    if (two) ld_vec<V>(vd, b + (size_t)(c + 32) * V);
+                    ld_vec<V>(xb, b + (size_t)c * V);
+                    if (two) ld_vec<V>(xd, b + (size_t)(c + 32) * V);
                 }
-                st_vec<V>(da + (size_t)c * V, va);
-                if (two) st_vec<V>(da + (size_t)(c + 32) * V, vc);
+                st_vec<V>(da + (size_t)c * V, xa);
+                if (two) st_vec<V>(da + (size_t)(c + 32) * V, xc);
                 if (l1 >= 0) {
-                    st_vec<V>(db + (size_t)c * V, vb);
-                    if (two) st_vec<V>(db + (size_t)(c + 32) * V, vd);
+                    st_vec<V>(db + (size_t)c * V, xb);
+                    if (two) st_vec<V>(db + (size_t)(c + 32) * V, xd);
                 }
             }
         }
@@ -1032,10 +1031,11 @@ extern "C" int kge_train_push_rows(kge_ctx* ctx, const kge_train_args* a, const 
                 "kge_train_push_rows: [row_begin,row_end) must be this rank's shard of a->ent");
     const int blocks = ctx->sm_count * 8;
     const TableView sv = make_view(*stage);
+    const int64_t t_start = (own + 1) % stage->n_shards;
     if (K % 4 == 0)
-        kge_push_rows_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(keys_all, n_keys, S, ent_slots, a->ent.shard[own], row_begin, row_end, K, sv);
+        kge_push_rows_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(keys_all, n_keys, S, ent_slots, a->ent.shard[own], row_begin, row_end, K, sv, t_start);
     else
-        kge_push_rows_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(keys_all, n_keys, S, ent_slots, a->ent.shard[own], row_begin, row_end, K, sv);
+        kge_push_rows_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(keys_all, n_keys, S, ent_slots, a->ent.shard[own], row_begin, row_end, K, sv, t_start);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -219,16 +219,25 @@ class ShardedKGE:
         eng.train_fwd_bwd(a, self.gbuf.tensor)
         mark("fwd_bwd")
         if push:
+            # the all-gather of the tails also orders every rank's forward (and its gradient buffer) before
+            # the reduction below; the loss all-reduce at the end doubles as the closing barrier
             dist.all_gather_into_tensor(self.tails_all, self.gbuf.tensor[self.g_head:self.g_head + self.tail_stride])
-        # every rank's forward reads and gradient buffer are complete once this returns on the stream
-        self.loss_sum.copy_(self.loss_dev)
-        dist.all_reduce(self.loss_sum)
-        mark("tails+loss")
-        eng.train_apply(a, self.keys_all, self.grads_table, self.row_begin, self.row_end)
-        mark("apply")
-        # owners have finished reading the peers' gradient buffers / writing their rows
-        dist.all_reduce(self.sync_tok)
-        mark("end_barrier")
+            mark("tails")
+            eng.train_apply(a, self.keys_all, self.grads_table, self.row_begin, self.row_end)
+            mark("apply")
+            # owners have finished reading the peers' gradient buffers / writing their rows once this returns
+            self.loss_sum.copy_(self.loss_dev)
+            dist.all_reduce(self.loss_sum)
+            mark("loss+end_barrier")
+        else:
+            # every rank's forward reads and gradient buffer are complete once this returns on the stream
+            self.loss_sum.copy_(self.loss_dev)
+            dist.all_reduce(self.loss_sum)
+            mark("loss")
+            eng.train_apply(a, self.keys_all, self.grads_table, self.row_begin, self.row_end)
+            mark("apply")
+            dist.all_reduce(self.sync_tok)
+            mark("end_barrier")
         if self.timing:
             self._marks.append(marks)
         return self.loss_sum
