@@ -964,7 +964,7 @@ extern "C" int kge_train_fwd_bwd(kge_ctx* ctx, const kge_train_args* a, float* g
 template <int V>
 __global__ void __launch_bounds__(256) kge_push_rows_kernel(const int32_t* __restrict__ keys, int64_t n_keys, int64_t S, int64_t ent_slots,
                                                             const float* __restrict__ shard, int64_t row_begin, int64_t row_end, int K,
-                                                            TableView stage, int64_t t_start) {
+                                                            TableView stage, int64_t t_start, int64_t group) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -975,9 +975,16 @@ __global__ void __launch_bounds__(256) kge_push_rows_kernel(const int32_t* __res
     // rank's NVLink ingress is the target of all owners at once (the all-to-all pattern)
     const int W = stage.n_shards;
     const int64_t bpr = (S + 31) / 32;  // blocks per rank
-    for (int64_t vb = warp; vb < bpr * W; vb += nwarps) {
-        const int rr = (int)((vb + t_start) % W);
-        const int64_t tl = (vb / W) * 32 + lane;
+    // `group` consecutive blocks go to the same destination before the deal moves on (group = blocks per rank:
+    // one destination region at a time, rotated per owner; group = 1: finest interleave)
+    const int64_t gpr = (bpr + group - 1) / group;  // groups per rank
+    for (int64_t vb0 = warp; vb0 < gpr * group * W; vb0 += nwarps) {
+        const int64_t g = vb0 / group, in_g = vb0 - g * group;
+        const int rr = (int)((g + t_start) % W);
+        const int64_t lb = (g / W) * group + in_g;  // block inside the destination's slots
+        if (lb >= bpr) continue;
+        const int64_t vb = lb * W;  // (vb / W) == lb below
+        const int64_t tl = lb * 32 + lane;
         int32_t key = -1;
         if (tl < ent_slots) key = keys[(int64_t)rr * S + tl];
         unsigned own = __ballot_sync(0xffffffffu, key >= row_begin && key < row_end);
@@ -1029,13 +1036,23 @@ extern "C" int kge_train_push_rows(kge_ctx* ctx, const kge_train_args* a, const 
     const int own = a->ent.n_shards == 1 ? 0 : (int)(row_begin / rps);
     KGE_REQUIRE(own < a->ent.n_shards && a->ent.shard[own] != nullptr && row_begin == (int64_t)own * rps,
                 "kge_train_push_rows: [row_begin,row_end) must be this rank's shard of a->ent");
-    const int blocks = ctx->sm_count * 8;
+    // A/B knobs (read per call): KGE_PUSH_CTAS = CTAs per SM, KGE_PUSH_GROUP = blocks of 32 slots that go to
+    // one destination before the deal moves to the next (0 = a whole rank's slots).  Measured on 8 x B200
+    // (profiles/r01_n_push_sweep_n8.txt): the all-to-all of 1 KiB stores saturates at ~470 GB/s per GPU whatever
+    // the grid; few CTAs and one destination region at a time (rotated per owner) give the least skew.
+    int ctas = 2;
+    int64_t group = 0;
+    if (const char* e = getenv("KGE_PUSH_CTAS")) ctas = std::max(1, std::min(16, atoi(e)));
+    if (const char* e = getenv("KGE_PUSH_GROUP")) group = atoll(e);
+    const int64_t bpr = (S + 31) / 32;
+    if (group <= 0 || group > bpr) group = bpr;
+    const int blocks = ctx->sm_count * ctas;
     const TableView sv = make_view(*stage);
     const int64_t t_start = (own + 1) % stage->n_shards;
     if (K % 4 == 0)
-        kge_push_rows_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(keys_all, n_keys, S, ent_slots, a->ent.shard[own], row_begin, row_end, K, sv, t_start);
+        kge_push_rows_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(keys_all, n_keys, S, ent_slots, a->ent.shard[own], row_begin, row_end, K, sv, t_start, group);
     else
-        kge_push_rows_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(keys_all, n_keys, S, ent_slots, a->ent.shard[own], row_begin, row_end, K, sv, t_start);
+        kge_push_rows_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(keys_all, n_keys, S, ent_slots, a->ent.shard[own], row_begin, row_end, K, sv, t_start, group);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
