@@ -150,6 +150,16 @@ def load_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback (B200_PROFILING.md)")
 
 
+def load_traffic(workload, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic_r01.json);
+    None when the workload / kernel was not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    try:
+        return float(json.load(open(p))[workload][kernel])
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference-equivalent op graph (oracle/torch_port.py) on the host cores
 # ------------------------------------------------------------------------------------------------
@@ -375,7 +385,8 @@ def single_gpu_main(args, w):
     ach = dom_b / (dom_t * 1e-3) / 1e9
     step_ms = t_cold_ms / steps
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                "traffic": None, "peak_source": peaks["src"], "algorithmic_bytes_per_launch": dom_b, "kernel_ms": dom_t,
+                "traffic": load_traffic(args.workload, dom.split(" ")[0]), "traffic_source": "ncu --set full capture, profiles/traffic_r01.json",
+                "peak_source": peaks["src"], "algorithmic_bytes_per_launch": dom_b, "kernel_ms": dom_t,
                 "phases_ms": {"emit": t_emit, "fwd_bwd": t_fb, "reduce_apply": t_apply, "span_hub": t_span,
                               "sort_done_after_emit": phases.get("sort_after_emit", 0.0), "timed_steps": n_timed},
                 "kernels": {"fwd_bwd": {"bytes": bytes_fb, "GBps": bytes_fb / (t_fb * 1e-3) / 1e9, "frac": bytes_fb / (t_fb * 1e-3) / 1e9 / peaks["hbm"]},
@@ -667,7 +678,7 @@ def bench_rank(args, w, eng, model, f, X, test, peaks):
         peak = peaks["bf16"] / 2.0
         ach = flops / (t_sweep_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (logical fp32-accurate flops; x3 TF32 MMAs issued)",
-                "frac": ach / peak, "frac_issued_3x": 3 * ach / peak, "traffic": None, "peak_source": peaks["src"] + " bf16/2"}
+                "frac": ach / peak, "frac_issued_3x": 3 * ach / peak, "traffic": load_traffic(args.workload, "kge_rank_tc_kernel"), "peak_source": peaks["src"] + " bf16/2"}
     else:
         peak = 148 * 128 * 2 * 1.965e9 / 1e12
         ach = flops / (t_sweep_ms * 1e-3) / 1e12
