@@ -72,6 +72,8 @@ SYMBOLS = {
     "kge_train_fwd_bwd": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P]),
     "kge_train_apply": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _L, C.POINTER(KgeTable), _L, _L, _P]),
     "kge_train_step_host": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P, _P]),
+    "kge_train_step_host_async": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P, _P, C.POINTER(_I)]),
+    "kge_train_host_wait": (_I, [_P, _I]),
     "kge_train_select": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _L, _L, _L, _P]),
     "kge_normalize_rows": (_I, [_P, _P, _L, _I, _P]),
     "kge_filter_build": (_I, [_P, _P, _L, _L, _L, _P]),

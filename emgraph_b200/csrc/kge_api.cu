@@ -49,6 +49,8 @@ extern "C" int kge_ctx_destroy(kge_ctx* c) {
     if (c->h_count) cudaFreeHost(c->h_count);
     if (c->h_dyn) cudaFreeHost(c->h_dyn);
     if (c->ev_gin) cudaEventDestroy(c->ev_gin);
+    for (int i = 0; i < 4; ++i)
+        if (c->ev_host[i]) cudaEventDestroy(c->ev_host[i]);
     if (c->gmain) cudaStreamDestroy(c->gmain);
     c->d_dyn.release();
     for (KgeGraphEntry& g : c->graphs)

@@ -30,6 +30,7 @@ void kge_set_error(const char* fmt, ...);
     } while (0)
 
 // per-step scalars read from device memory when a step runs from a captured graph
+#define KGE_HOST_RING 4
 struct KgeStepDyn {
     uint64_t step;
     float    lr_t;
@@ -95,6 +96,7 @@ struct kge_ctx {
     int*          h_count = nullptr;
     cudaEvent_t   ev_count = nullptr;
     bool          sel_valid = false;
+    int           rank_nl = 0;  // non-linearity of the kge_rank_counts call in progress
     const int32_t* sel_keys = nullptr;
     int64_t       sel_n = 0, sel_begin = 0, sel_end = 0;
     // staging for the host-buffer entry points
@@ -104,7 +106,9 @@ struct kge_ctx {
     // memcpy node refreshes from pinned host memory, so one instantiated graph serves every step
     cudaStream_t gmain = nullptr;  // capture-able stream the graphed host step runs on
     cudaEvent_t  ev_gin = nullptr;
-    KgeStepDyn* h_dyn = nullptr;  // pinned
+    KgeStepDyn* h_dyn = nullptr;  // pinned ring of KGE_HOST_RING blocks (one per in-flight host step)
+    cudaEvent_t  ev_host[4] = {nullptr, nullptr, nullptr, nullptr};  // end of the host step that used ring slot i
+    uint64_t     host_tick = 0;   // host steps submitted so far
     KgeBuf      d_dyn;
     KgeGraphEntry graphs[KGE_GRAPH_SLOTS];
     // ranking workspace
@@ -212,6 +216,29 @@ __device__ __forceinline__ void mbar_fence_init() {
 // (reference models/EmbeddingModel.py:2010-2014; utils/constants.py:87)
 __device__ __forceinline__ int quantise_score(float s) {
     return __float2int_rz(__fmul_rn(s, 1e5f));
+}
+
+// embedding_model_params['non_linearity'] applied to every score before the loss / the rank comparison
+// (models/EmbeddingModel.py:679-689, :801-812, :1868-1881): linear | tanh | sigmoid | softplus, the last one the
+// reference's custom_softplus log(1 + 9999*exp(x)) with gradient 1 - 1/(1 + 9999*exp(x)) (:89-96)
+__device__ __forceinline__ float apply_nl(int nl, float s) {
+    if (nl == KGE_NL_LINEAR) return s;
+    if (nl == KGE_NL_TANH) return tanhf(s);
+    if (nl == KGE_NL_SIGMOID) return 1.f / (1.f + expf(-s));
+    return logf(1.f + 9999.f * expf(s));
+}
+// d nl(s) / ds from the raw score
+__device__ __forceinline__ float apply_nl_grad(int nl, float s) {
+    if (nl == KGE_NL_LINEAR) return 1.f;
+    if (nl == KGE_NL_TANH) {
+        const float t = tanhf(s);
+        return 1.f - t * t;
+    }
+    if (nl == KGE_NL_SIGMOID) {
+        const float g = 1.f / (1.f + expf(-s));
+        return g * (1.f - g);
+    }
+    return 1.f - 1.f / (1.f + 9999.f * expf(s));
 }
 
 // Philox4x32-10 counter-based RNG (Salmon et al. 2011), one call per negative.

@@ -118,6 +118,7 @@ struct PrepParams {
     const int32_t* test;
     int64_t T;
     int filtered;
+    int nl;  // KGE_NL_*
     const uint64_t* sp_comp;
     const uint64_t* po_comp;
     const int32_t* f_cnt;
@@ -172,7 +173,7 @@ __global__ void kge_rank_prepare_kernel(PrepParams P) {
         }
         acc = hs * warp_sum(acc);
     }
-    if (lane == 0) P.pos_q[t] = quantise_score(acc);
+    if (lane == 0) P.pos_q[t] = quantise_score(apply_nl(P.nl, acc));
     if (lane < 2) {
         int32_t lo = 0, hi = 0;
         if (P.filtered) {
@@ -208,6 +209,7 @@ struct SweepParams {
     int64_t q_row0;          // first query row handled (side selection)
     int64_t q_rows;          // number of query rows handled
     int32_t* counts;         // [T,2,4]
+    int nl;                  // KGE_NL_*
 };
 
 #define SW_BM 64
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(256) kge_rank_sweep_kernel(SweepParams P) {
                 const int cl = tx * 4 + j;
                 const int64_t e = n0 + cl;
                 float sc = MODE == 0 ? acc[i][j] : (MODE == 1 ? -acc[i][j] : -sqrtf(acc[i][j]));
-                int qv2 = quantise_score(sc);
+                int qv2 = quantise_score(apply_nl(P.nl, sc));
                 bool valid = (e < e1) && (e != (int64_t)self) && (self >= 0);
                 int gt = valid && (qv2 > pq), eq = valid && (qv2 == pq);
                 int f = (int)((mk >> cl) & 1ull);
@@ -425,8 +427,9 @@ __global__ void kge_rank_finalize_kernel(const int32_t* __restrict__ counts, int
 
 extern "C" int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
                                const float* ent_local, int64_t row_begin, int64_t row_end, const int32_t* test, int64_t T,
-                               int side, int filtered, int use_tensor_cores, int32_t* counts, void* stream) {
+                               int side, int filtered, int use_tensor_cores, int non_linearity, int32_t* counts, void* stream) {
     KGE_REQUIRE(ctx != nullptr, "kge_rank_counts: null ctx");
+    KGE_REQUIRE(non_linearity >= KGE_NL_LINEAR && non_linearity <= KGE_NL_SOFTPLUS, "Invalid non-linearity");
     KGE_REQUIRE(model >= KGE_TRANSE_L1 && model <= KGE_HOLE, "kge_rank_counts: unknown model %d", model);
     KGE_REQUIRE(side >= KGE_RANK_S_O && side <= KGE_RANK_O, "Invalid value for corrupt_side.");
     if (T == 0) return 0;
@@ -455,6 +458,8 @@ extern "C" int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* 
     pp.test = test;
     pp.T = T;
     pp.filtered = filtered && ctx->f_n_sp > 0;
+    pp.nl = non_linearity;
+    ctx->rank_nl = non_linearity;
     pp.sp_comp = ctx->f_sp_comp.as<uint64_t>();
     pp.po_comp = ctx->f_po_comp.as<uint64_t>();
     pp.f_cnt = ctx->f_count.as<int32_t>();
@@ -499,6 +504,7 @@ extern "C" int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* 
     sp.q_row0 = q_row0;
     sp.q_rows = q_rows;
     sp.counts = counts;
+    sp.nl = non_linearity;
     int64_t row_tiles = (q_rows + SW_BM - 1) / SW_BM;
     int64_t n_ent = row_end - row_begin;
     // enough CTAs for >= 4 waves, entity chunks a multiple of the tile
@@ -532,7 +538,7 @@ extern "C" int kge_rank_finalize(kge_ctx* ctx, const int32_t* counts, int64_t T,
 
 extern "C" int kge_rank_host(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
                              const int32_t* test_host, int64_t T, int side, int strategy, int filtered,
-                             int use_tensor_cores, int32_t* ranks_host, void* stream) {
+                             int use_tensor_cores, int non_linearity, int32_t* ranks_host, void* stream) {
     KGE_REQUIRE(ctx != nullptr && ent != nullptr, "kge_rank_host: null argument");
     KGE_REQUIRE(ent->n_shards == 1 && ent->shard[0] != nullptr, "kge_rank_host is the single-GPU entry; use kge_rank_counts per shard");
     if (T == 0) return 0;
@@ -542,7 +548,7 @@ extern "C" int kge_rank_host(kge_ctx* ctx, int model, int k, const kge_table* en
     if (ctx->h_test.reserve((size_t)T * 3 * 4) || ctx->h_counts.reserve((size_t)T * 8 * 4) || ctx->h_ranks.reserve(n_out * 4)) return -2;
     KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->h_test.p, test_host, (size_t)T * 3 * 4, cudaMemcpyHostToDevice, st));
     if (int rc = kge_rank_counts(ctx, model, k, ent, rel, R, ent->shard[0], 0, ent->rows, ctx->h_test.as<int32_t>(), T, side,
-                                 filtered, use_tensor_cores, ctx->h_counts.as<int32_t>(), stream))
+                                 filtered, use_tensor_cores, non_linearity, ctx->h_counts.as<int32_t>(), stream))
         return rc;
     if (int rc = kge_rank_finalize(ctx, ctx->h_counts.as<int32_t>(), T, side, strategy, filtered, nullptr, ctx->h_ranks.as<int32_t>(), stream))
         return rc;

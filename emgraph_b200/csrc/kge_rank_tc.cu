@@ -118,6 +118,7 @@ struct TcParams {
     const int32_t* po_ent;
     int32_t* counts;
     int n_m_tiles, n_n_tiles, nsplit;
+    int nl;  // KGE_NL_*: non-linearity applied to the scores before the quantisation
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -281,11 +282,20 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     const int64_t ds = (int64_t)self - e_base;
                     if (ds >= 0 && ds < 32) valid &= ~(1u << (int)ds);
                     uint32_t gtm = 0, eqm = 0;
+                    if (P.nl == KGE_NL_LINEAR) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int q = quantise_score(__uint_as_float(v[i]));
-                        gtm |= (q > pq ? 1u : 0u) << i;
-                        eqm |= (q == pq ? 1u : 0u) << i;
+                        for (int i = 0; i < 32; ++i) {
+                            const int q = quantise_score(__uint_as_float(v[i]));
+                            gtm |= (q > pq ? 1u : 0u) << i;
+                            eqm |= (q == pq ? 1u : 0u) << i;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int q = quantise_score(apply_nl(P.nl, __uint_as_float(v[i])));
+                            gtm |= (q > pq ? 1u : 0u) << i;
+                            eqm |= (q == pq ? 1u : 0u) << i;
+                        }
                     }
                     gtm &= valid;
                     eqm &= valid;
@@ -400,6 +410,7 @@ int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ
     int nsplit = (int)std::max<int64_t>(1, ((int64_t)ctx->sm_count * 12 + P.n_m_tiles - 1) / P.n_m_tiles);
     nsplit = std::min(nsplit, std::max(1, P.n_n_tiles / 2));
     P.nsplit = nsplit;
+    P.nl = ctx->rank_nl;
     const int n_units = P.n_m_tiles * nsplit;
     const int grid = std::min(n_units, ctx->sm_count);
     static bool attr_set = false;

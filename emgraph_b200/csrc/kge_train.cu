@@ -868,6 +868,7 @@ static int validate_train(const kge_train_args* a) {
     KGE_REQUIRE(a->ent.n_shards >= 1 && a->ent.n_shards <= KGE_MAX_SHARDS, "kge_train: bad shard count");
     KGE_REQUIRE(a->ent.rows + a->R < (int64_t)INT32_MAX, "kge_train: E+R must fit int32 sort keys");
     KGE_REQUIRE(a->n_pos >= 0 && (a->pos != nullptr || a->n_pos == 0), "kge_train: positives missing");
+    KGE_REQUIRE(a->non_linearity >= KGE_NL_LINEAR && a->non_linearity <= KGE_NL_SOFTPLUS, "Invalid non-linearity");
     KGE_REQUIRE(a->neg_entities_n >= 0 && a->neg_entities_n <= a->ent.rows && (a->neg_entities == nullptr || a->neg_entities_n > 0),
                 "kge_train: bad negative_corruption_entities (n=%lld)", (long long)a->neg_entities_n);
     return 0;
@@ -927,6 +928,7 @@ static int fwd_bwd_impl(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, 
     P.loss = a->loss;
     P.margin = a->margin;
     P.alpha = a->alpha;
+    P.nl = a->non_linearity;
     P.scale = a->model == KGE_HOLE ? 2.0f / (float)a->k : 1.0f;
     P.gbuf = grad_buf;
     P.loss_part = ctx->loss_part.as<float>();
@@ -1456,12 +1458,14 @@ static int train_step_graphed(kge_ctx* ctx, const kge_train_args* b, cudaStream_
     e->seen += 1;
     if (e->seen == 1) return train_step_body(ctx, b, st, nullptr);
     if (ctx->h_dyn == nullptr) {
-        KGE_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_dyn, sizeof(KgeStepDyn)));
+        KGE_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_dyn, KGE_HOST_RING * sizeof(KgeStepDyn)));
         if (ctx->d_dyn.reserve(sizeof(KgeStepDyn))) return -2;
     }
-    // the previous replay has been synchronised by the caller (kge_train_step_host), so the pinned block is free
-    ctx->h_dyn->step = b->step;
-    ctx->h_dyn->lr_t = (float)adam_lr_t(b);
+    // ring slot of this host step: kge_train_step_host_async has waited for the step that used it last, so
+    // the pinned block is free; the copy below is stream-ordered behind the previous replay
+    KgeStepDyn* hd = ctx->h_dyn + (ctx->host_tick % KGE_HOST_RING);
+    hd->step = b->step;
+    hd->lr_t = (float)adam_lr_t(b);
     if (e->exec != nullptr && e->ws_epoch != g_kge_ws_epoch) {  // a workspace buffer moved since the capture
         cudaGraphExecDestroy(e->exec);
         e->exec = nullptr;
@@ -1470,9 +1474,7 @@ static int train_step_graphed(kge_ctx* ctx, const kge_train_args* b, cudaStream_
         cudaGraph_t graph = nullptr;
         e->ws_epoch = g_kge_ws_epoch;
         KGE_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-        int rc = 0;
-        if (cudaMemcpyAsync(ctx->d_dyn.p, ctx->h_dyn, sizeof(KgeStepDyn), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -2;
-        if (rc == 0) rc = train_step_body(ctx, b, st, ctx->d_dyn.as<KgeStepDyn>());
+        int rc = train_step_body(ctx, b, st, ctx->d_dyn.as<KgeStepDyn>());
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
             if (graph) cudaGraphDestroy(graph);
@@ -1490,24 +1492,32 @@ static int train_step_graphed(kge_ctx* ctx, const kge_train_args* b, cudaStream_
             return train_step_body(ctx, b, st, nullptr);
         }
     }
+    // step counter / lr_t of this replay (outside the graph: a different pinned slot every step)
+    KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->d_dyn.p, hd, sizeof(KgeStepDyn), cudaMemcpyHostToDevice, st));
     KGE_CUDA_CHECK(cudaGraphLaunch(e->exec, st));
     return 0;
 }
 
-extern "C" int kge_train_step_host(kge_ctx* ctx, const kge_train_args* a, const int32_t* pos_host, float* loss_host,
-                                   void* stream) {
+extern "C" int kge_train_step_host_async(kge_ctx* ctx, const kge_train_args* a, const int32_t* pos_host, float* loss_host,
+                                         void* stream, int* ticket_out) {
     KGE_REQUIRE(ctx != nullptr && a != nullptr, "kge_train_step_host: null argument");
     KGE_REQUIRE(a->n_pos >= 0 && (a->n_pos == 0 || pos_host != nullptr), "kge_train_step_host: positives missing");
     cudaStream_t st = (cudaStream_t)stream;
+    const int slot = (int)(ctx->host_tick % KGE_HOST_RING);
+    if (ticket_out) *ticket_out = slot;
+    if (ctx->ev_host[slot] == nullptr) KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_host[slot], cudaEventDisableTiming));
+    else KGE_CUDA_CHECK(cudaEventSynchronize(ctx->ev_host[slot]));  // the step that used this ring slot last is done
     if (a->n_pos == 0) {
         if (loss_host) *loss_host = 0.f;
+        KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_host[slot], st));
+        ctx->host_tick += 1;
         return 0;
     }
     if (ctx->h_pos.reserve((size_t)a->n_pos * 3 * sizeof(int32_t)) || ctx->h_loss.reserve(sizeof(float))) return -2;
     const bool graphed = train_graph_enabled() && !ctx->timing && a->ent.n_shards == 1;
     if (graphed) {
         // the caller's stream may be the legacy default stream, which cannot be captured: the whole call
-        // runs on a stream of the ctx, ordered behind the caller's stream (and synchronised before return)
+        // runs on a stream of the ctx, ordered behind the caller's stream (kge_train_host_wait joins it)
         if (ctx->gmain == nullptr) {
             KGE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->gmain, cudaStreamNonBlocking));
             KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_gin, cudaEventDisableTiming));
@@ -1520,10 +1530,24 @@ extern "C" int kge_train_step_host(kge_ctx* ctx, const kge_train_args* a, const 
     kge_train_args b = *a;
     b.pos = ctx->h_pos.as<int32_t>();
     if (b.loss_out == nullptr) b.loss_out = ctx->h_loss.as<float>();
-    if (int rc = graphed ? train_step_graphed(ctx, &b, st) : train_step_body(ctx, &b, stream, nullptr)) return rc;
+    if (int rc = graphed ? train_step_graphed(ctx, &b, st) : train_step_body(ctx, &b, st, nullptr)) return rc;
     if (loss_host) KGE_CUDA_CHECK(cudaMemcpyAsync(loss_host, b.loss_out, sizeof(float), cudaMemcpyDeviceToHost, st));
-    KGE_CUDA_CHECK(cudaStreamSynchronize(st));
+    KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_host[slot], st));
+    ctx->host_tick += 1;
     return 0;
+}
+
+extern "C" int kge_train_host_wait(kge_ctx* ctx, int ticket) {
+    KGE_REQUIRE(ctx != nullptr && ticket >= 0 && ticket < KGE_HOST_RING, "kge_train_host_wait: bad ticket %d", ticket);
+    if (ctx->ev_host[ticket] != nullptr) KGE_CUDA_CHECK(cudaEventSynchronize(ctx->ev_host[ticket]));
+    return 0;
+}
+
+extern "C" int kge_train_step_host(kge_ctx* ctx, const kge_train_args* a, const int32_t* pos_host, float* loss_host,
+                                   void* stream) {
+    int ticket = 0;
+    if (int rc = kge_train_step_host_async(ctx, a, pos_host, loss_host, stream, &ticket)) return rc;
+    return kge_train_host_wait(ctx, ticket);
 }
 
 extern "C" int kge_normalize_rows(kge_ctx* ctx, float* emb, int64_t rows, int K, void* stream) {

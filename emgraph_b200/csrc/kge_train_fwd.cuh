@@ -302,6 +302,7 @@ struct FwdBwdParams {
     int64_t n;
     int eta, k, loss;
     float margin, scale, alpha;
+    int nl;             // KGE_NL_*: non-linearity on the scores before the loss
     float* gbuf;        // gradient buffer (layout above)
     float* loss_part;   // [n]
     float* dbg_scores;  // optional [n*(1+eta)]
@@ -475,6 +476,12 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
         row_zero(Qo);
         row_zero(Qs);
     }
+    // the loss sees nl(score) (models/EmbeddingModel.py:679-689, :801-812); the raw score stays around for the
+    // backward (TransE L2 divides by the norm) and dL/draw = dL/dnl * nl'(raw)
+    const int nl = P.nl;
+    const float spos_raw = spos;
+    const float dpos_nl = apply_nl_grad(nl, spos_raw);
+    spos = apply_nl(nl, spos_raw);
     const float cpos = clip75(spos);
     const bool pos_in = (spos >= -75.f) && (spos <= 75.f);
     const float margin = P.margin;
@@ -486,16 +493,18 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
     float lbar = 0.f;      // self-adversarial: sum_j p_j * logsigmoid(-s_j - margin)
     const float alpha = P.alpha;
     // pass-2 weight dL/ds_j of the two-pass losses
-    auto weight2 = [&](float sn) -> float {
+    auto weight2 = [&](float sn_raw) -> float {
+        const float sn = apply_nl(nl, sn_raw);
+        const float dn = apply_nl_grad(nl, sn_raw);
         if (loss == KGE_LOSS_MULTICLASS_NLL) {
             // losses/nll_multiclass.py:70-81 : softmax weight, zero outside the clip range
             const bool in = (sn >= -75.f) && (sn <= 75.f);
-            return in ? expf(sn) * zinv : 0.f;
+            return in ? expf(sn) * zinv * dn : 0.f;
         }
         // losses/self_adversarial.py:97-110 : L = -sum_j p_j*l_j, p = softmax(alpha*s), l_j = logsigmoid(-s_j - margin);
         // the gradient flows through p as well: dL/ds_j = p_j*(sigmoid(s_j + margin) - alpha*(l_j - sum_i p_i*l_i))
         const float pj = expf(alpha * sn - amax) * zinv;
-        return pj * (sigmoidf(sn + margin) - alpha * (log_sigmoid(-sn - margin) - lbar));
+        return pj * (sigmoidf(sn + margin) - alpha * (log_sigmoid(-sn - margin) - lbar)) * dn;
     };
 
     // MODE 0: single pass (pairwise / nll).  MODE 1: scores only (multiclass pass 1).
@@ -552,20 +561,21 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
                         tot += __shfl_xor_sync(0xffffffffu, tot, 1);
                     }
                     const bool has = cidx < g;
-                    float sn = 0.f, w = 0.f;
+                    float sn = 0.f, w = 0.f;  // sn: RAW score of the candidate this lane holds
                     if constexpr (MODE != 2) sn = A::finish(tot, P.scale);
                     if constexpr (MODE == 0) {
                         float term;
+                        const float st = apply_nl(nl, sn);
                         if (loss == KGE_LOSS_PAIRWISE || loss == KGE_LOSS_ABSOLUTE_MARGIN) {
                             // losses/pairwise.py:69, absolute_margin.py:69 ; tf.maximum passes the gradient when t >= 0
-                            const float tt = loss == KGE_LOSS_PAIRWISE ? margin - spos + sn : margin + sn;
+                            const float tt = loss == KGE_LOSS_PAIRWISE ? margin - spos + st : margin + st;
                             term = fmaxf(tt, 0.f);
                             w = (tt >= 0.f) ? 1.f : 0.f;
                         } else {
                             // losses/nll.py:55-59 : log(1+exp(clip(neg)))
-                            const float e = expf(clip75(sn));
+                            const float e = expf(clip75(st));
                             term = logf(1.f + e);
-                            const bool in = (sn >= -75.f) && (sn <= 75.f);
+                            const bool in = (st >= -75.f) && (st <= 75.f);
                             w = in ? e / (1.f + e) : 0.f;
                         }
                         if (!has) {
@@ -576,6 +586,7 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
                             loss_acc += term;
                             if (loss == KGE_LOSS_PAIRWISE) wsum += w;
                         }
+                        w *= apply_nl_grad(nl, sn);  // dL/d(raw score)
                     }
                     if constexpr (MODE != 2) {
                         // hand score / coefficient to the lane that owns the negative (it stores them)
@@ -658,16 +669,19 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
                                     w = weight2(sn);
                                 } else if (loss == KGE_LOSS_PAIRWISE || loss == KGE_LOSS_ABSOLUTE_MARGIN) {
                                     // losses/pairwise.py:69, absolute_margin.py:69 ; tf.maximum passes the gradient when t >= 0
-                                    const float tt = loss == KGE_LOSS_PAIRWISE ? margin - spos + sn : margin + sn;
+                                    const float st = apply_nl(nl, sn);
+                                    const float tt = loss == KGE_LOSS_PAIRWISE ? margin - spos + st : margin + st;
                                     loss_acc += fmaxf(tt, 0.f);
                                     w = (tt >= 0.f) ? 1.f : 0.f;
                                     wsum += w;
+                                    w *= apply_nl_grad(nl, sn);
                                 } else {
                                     // losses/nll.py:55-59 : log(1+exp(clip(neg)))
-                                    const float e = expf(clip75(sn));
+                                    const float st = apply_nl(nl, sn);
+                                    const float e = expf(clip75(st));
                                     loss_acc += logf(1.f + e);
-                                    const bool in = (sn >= -75.f) && (sn <= 75.f);
-                                    w = in ? e / (1.f + e) : 0.f;
+                                    const bool in = (st >= -75.f) && (st <= 75.f);
+                                    w = in ? e / (1.f + e) * apply_nl_grad(nl, sn) : 0.f;
                                 }
                                 const float c = A::coefficient(w, sn, P.scale);
                                 if (lane == src[u]) {
@@ -695,7 +709,7 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
                 if (lane < lim) {
                     coef[my_q] = my_c;
                     keep_out[my_q] = (uint8_t)my_keep;
-                    if (P.dbg_scores != nullptr) P.dbg_scores[n + my_q] = my_sn;
+                    if (P.dbg_scores != nullptr) P.dbg_scores[n + my_q] = apply_nl(nl, my_sn);
                 }
             }
         }
@@ -707,7 +721,7 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
         if (loss == KGE_LOSS_MULTICLASS_NLL) {
             float zpart = 0.f;
             if (valid)
-                for (int j = lane; j < eta; j += 32) zpart += expf(clip75(sc[j]));
+                for (int j = lane; j < eta; j += 32) zpart += expf(clip75(apply_nl(nl, sc[j])));
             const float pe = expf(cpos);
             const float z = warp_sum(zpart) + pe;
             zinv = 1.f / z;
@@ -716,16 +730,17 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
             // softmax over the eta negatives of this positive (tf.nn.softmax subtracts the max)
             float mx = -INFINITY;
             if (valid)
-                for (int j = lane; j < eta; j += 32) mx = fmaxf(mx, alpha * sc[j]);
+                for (int j = lane; j < eta; j += 32) mx = fmaxf(mx, alpha * apply_nl(nl, sc[j]));
 #pragma unroll
             for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
             amax = valid ? mx : 0.f;
             float zpart = 0.f, lpart = 0.f;
             if (valid)
                 for (int j = lane; j < eta; j += 32) {
-                    const float e = expf(alpha * sc[j] - amax);
+                    const float st = apply_nl(nl, sc[j]);
+                    const float e = expf(alpha * st - amax);
                     zpart += e;
-                    lpart += e * log_sigmoid(-sc[j] - margin);
+                    lpart += e * log_sigmoid(-st - margin);
                 }
             const float z = warp_sum(zpart);
             zinv = valid ? 1.f / z : 0.f;
@@ -785,6 +800,7 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
     } else {
         wpos = pos_in ? -(1.f - expf(cpos) * zinv) : 0.f;
     }
+    wpos *= dpos_nl;  // dL/d(raw positive score)
 
     float* GB = P.gbuf;
     row_store(GB + (size_t)(3 * n + i) * K, Qo, lane, nvec, half);
@@ -794,7 +810,7 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
         R s, p, o, gs, gp, go;
         const int32_t si = P.pos[3 * i + 0], pi = P.pos[3 * i + 1], oi = P.pos[3 * i + 2];
         row_load_clamped(o, slot_row(P, oi, n + i), lane, nvec, half);
-        A::backward_pos(Qo, o, wpos, spos, P.scale, go, AccO);
+        A::backward_pos(Qo, o, wpos, spos_raw, P.scale, go, AccO);
         row_load_clamped(s, slot_row(P, si, i), lane, nvec, half);
         row_load_clamped(p, P.rel + (size_t)pi * K, lane, nvec, half);
         A::fold(s, p, o, AccO, AccS, gs, gp, go);

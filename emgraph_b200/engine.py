@@ -209,6 +209,21 @@ class Engine:
                                            C.c_void_p(loss_host.data_ptr()), _stream()))
         self.launches += self.launches_per_step(a.ent.rows + a.R)
 
+    def train_step_host_async(self, a: KgeTrainArgs, pos_host, loss_host) -> int:
+        """Enqueue [H2D batch, step, D2H loss] without waiting; returns the ticket for train_host_wait.
+        pos_host / loss_host must stay alive and untouched until the ticket has been waited for."""
+        assert (not pos_host.is_cuda) and pos_host.dtype == torch.int32 and pos_host.is_contiguous()
+        assert (not loss_host.is_cuda) and loss_host.dtype == torch.float32
+        a.n_pos = pos_host.shape[0]
+        t = C.c_int(0)
+        check(self.lib.kge_train_step_host_async(self._h, C.byref(a), C.c_void_p(pos_host.data_ptr()),
+                                                 C.c_void_p(loss_host.data_ptr()), _stream(), C.byref(t)))
+        self.launches += self.launches_per_step(a.ent.rows + a.R)
+        return int(t.value)
+
+    def train_host_wait(self, ticket: int):
+        check(self.lib.kge_train_host_wait(self._h, int(ticket)))
+
     def train_emit(self, a: KgeTrainArgs, keys_out):
         _chk_i32(keys_out, "keys_out")
         check(self.lib.kge_train_emit(self._h, C.byref(a), _ptr(keys_out), _stream()))

@@ -499,6 +499,36 @@ class EmbeddingModel:
         f["eng"].train_step_host(a, pos_host, f["loss_host"])
         return float(f["loss_host"][0])
 
+    def _fit_step_host_pipelined(self, pos_host, side="s,o"):
+        """Like _fit_step_host, but the call returns as soon as the step is queued and hands back the loss of
+        the step submitted ONE call earlier (None on the first call): the GPU always has the next step queued
+        while the host checks the previous loss.  Every step still copies its batch in and its loss out;
+        _fit_host_flush() returns the loss of the last step."""
+        f = self._fit
+        f["step"] += 1
+        neg = f["neg"]
+        if self._neg_batch:
+            neg = dict(neg_entities=to_dev_i32(np.unique(pos_host[:, [0, 2]].numpy()), f["eng"].tdev))
+        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"],
+                                side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"], **neg)
+        ring = f.setdefault("loss_ring", torch.zeros(4, dtype=torch.float32).pin_memory())
+        i = f["step"] % 4
+        ticket = f["eng"].train_step_host_async(a, pos_host, ring[i:i + 1])
+        prev = f.get("pending")
+        f["pending"] = (ticket, i, a, pos_host)  # keeps the args and the batch alive while in flight
+        if prev is None:
+            return None
+        f["eng"].train_host_wait(prev[0])
+        return float(ring[prev[1]])
+
+    def _fit_host_flush(self):
+        f = self._fit
+        prev = f.pop("pending", None)
+        if prev is None:
+            return None
+        f["eng"].train_host_wait(prev[0])
+        return float(f["loss_ring"][prev[1]])
+
     def _fit_idx(self, Xi, E, R, early_stopping=False):
         f = self._fit_prepare(E, R)
         self._best_params = None
@@ -509,6 +539,7 @@ class EmbeddingModel:
         N = Xi.shape[0]
         batch_size = int(np.ceil(N / self.batches_count))
         host_batches = bool(self.engine_params.get("host_batches", False))
+        pipelined = bool(self.engine_params.get("host_pipeline", True))
         if host_batches:
             Xh = torch.from_numpy(np.ascontiguousarray(Xi, dtype=np.int32)).pin_memory()
         else:
@@ -530,17 +561,24 @@ class EmbeddingModel:
                     f["kw"]["lr"] = float(sched(b + 1, epoch))
                 for side in f["sides"]:
                     if host_batches:
-                        lv = self._fit_step_host(Xh[lo:hi], side)
-                        if not np.isfinite(lv):  # models/EmbeddingModel.py:1422-1427
-                            raise ValueError("Loss is {}. Please change the hyperparameters.".format(lv))
-                        host_loss += lv
+                        lv = self._fit_step_host_pipelined(Xh[lo:hi], side) if pipelined else self._fit_step_host(Xh[lo:hi], side)
+                        if lv is not None:
+                            if not np.isfinite(lv):  # models/EmbeddingModel.py:1422-1427
+                                raise ValueError("Loss is {}. Please change the hyperparameters.".format(lv))
+                            host_loss += lv
                     else:
                         self._fit_step_device(Xd[lo:hi], side)
                         epoch_loss += f["loss_dev"].double()
                 if normalize:
+                    if host_batches and pipelined:
+                        lv = self._fit_host_flush()
+                        host_loss += lv if lv is not None else 0.0
                     eng.normalize_rows(ent)
                 if not host_batches and f["step"] % check_every == 0 and not bool(torch.isfinite(epoch_loss).item()):
                     raise ValueError("Loss is {}. Please change the hyperparameters.".format(float(epoch_loss.item())))
+            if host_batches and pipelined:  # the epoch's last step
+                lv = self._fit_host_flush()
+                host_loss += lv if lv is not None else 0.0
             el = host_loss if host_batches else float(epoch_loss.item())
             if not np.isfinite(el):  # models/EmbeddingModel.py:1422-1427
                 raise ValueError("Loss is {}. Please change the hyperparameters.".format(el))

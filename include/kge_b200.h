@@ -46,6 +46,9 @@ enum { KGE_SIDE_SO = 0, KGE_SIDE_S = 1, KGE_SIDE_O = 2 };
 enum { KGE_RANK_S_O = 0, KGE_RANK_SPO = 1, KGE_RANK_S = 2, KGE_RANK_O = 3 };
 enum { KGE_STRAT_WORST = 0, KGE_STRAT_BEST = 1, KGE_STRAT_MIDDLE = 2 };
 
+/* embedding_model_params['non_linearity'] on the scores (models/EmbeddingModel.py:679-689, :801-812, :1868-1881) */
+enum { KGE_NL_LINEAR = 0, KGE_NL_TANH = 1, KGE_NL_SIGMOID = 2, KGE_NL_SOFTPLUS = 3 };
+
 /* train-step flags */
 #define KGE_F_RESET_STATE 1u /* reference-faithful: optimizer state re-created every batch (training/adam.py:45-46) */
 #define KGE_F_NO_UPDATE   2u /* compute loss/grads only (parity tests) */
@@ -109,6 +112,7 @@ typedef struct kge_train_args {
      * neg_entities_n entities when neg_entities is NULL and neg_entities_n > 0; 0 / NULL = all entities. */
     const int32_t* neg_entities;
     int64_t  neg_entities_n;
+    int32_t  non_linearity; /* KGE_NL_*: applied to positive and negative scores before the loss */
 } kge_train_args;
 
 int         kge_abi_version(void);
@@ -178,6 +182,15 @@ int kge_train_select(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_
  * *loss_host and the stream is synchronised before returning. */
 int kge_train_step_host(kge_ctx* ctx, const kge_train_args* a, const int32_t* pos_host, float* loss_host,
                         void* stream);
+/* The same call split in two so that a training loop can keep the next step queued while it reads the loss of
+ * the previous one (the copies and the step are enqueued exactly as above, nothing is skipped):
+ * kge_train_step_host_async enqueues [H2D of the batch, the step, D2H of the loss into *loss_host] and returns
+ * a ticket; kge_train_host_wait(ticket) blocks until that step, including its loss copy, has finished.  Up to
+ * 3 steps may be in flight (the 4th call waits for the oldest); pos_host / loss_host of an in-flight step must
+ * stay valid and distinct (pinned). */
+int kge_train_step_host_async(kge_ctx* ctx, const kge_train_args* a, const int32_t* pos_host, float* loss_host,
+                              void* stream, int* ticket_out);
+int kge_train_host_wait(kge_ctx* ctx, int ticket);
 
 /* optional post-step row renormalisation (models/EmbeddingModel.py:1434-1439, clip_by_norm axes=1) */
 int kge_normalize_rows(kge_ctx* ctx, float* emb, int64_t rows, int K, void* stream);
@@ -197,11 +210,12 @@ int64_t kge_filter_size_sync(kge_ctx* ctx);
  * counts[T,2,4] int32 (side {0:object sweep, 1:subject sweep} x {gt, eq, gt_filtered, eq_filtered});
  * counts from all shards are summed by the caller (NCCL all-reduce) before kge_rank_finalize.
  * side (KGE_RANK_*) selects which sweeps run (KGE_RANK_S / KGE_RANK_O run one).
- * use_tensor_cores: 1 = tcgen05 3xTF32 path (DistMult/ComplEx/HolE), 0 = fp32 CUDA-core sweep. */
+ * use_tensor_cores: 1 = tcgen05 3xTF32 path (DistMult/ComplEx/HolE), 0 = fp32 CUDA-core sweep.
+ * non_linearity (KGE_NL_*) is applied to every score before the x1e5 quantisation (models/EmbeddingModel.py:1868-1881). */
 int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
                     const float* ent_local, int64_t row_begin, int64_t row_end,
                     const int32_t* test, int64_t T, int side, int filtered, int use_tensor_cores,
-                    int32_t* counts, void* stream);
+                    int non_linearity, int32_t* counts, void* stream);
 /* ranks_out: [T,2] (col 0 subject, col 1 object) for KGE_RANK_S_O, else [T].
  * self_is_candidate: optional device uint8 [T,2] (col 0 subject, col 1 object): 0 when the test triple's own
  * entity was NOT among the swept candidates (entities_subset ranking, models/EmbeddingModel.py:1845-1857,
@@ -213,7 +227,7 @@ int kge_rank_finalize(kge_ctx* ctx, const int32_t* counts, int64_t T, int side, 
  * int32 in, ranks_host ([T,2] for KGE_RANK_S_O else [T]) out; synchronises the stream. */
 int kge_rank_host(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
                   const int32_t* test_host, int64_t T, int side, int strategy, int filtered,
-                  int use_tensor_cores, int32_t* ranks_host, void* stream);
+                  int use_tensor_cores, int non_linearity, int32_t* ranks_host, void* stream);
 
 /* Device memory that peers can map (plain cudaMalloc) + CUDA IPC helpers for mapping peer shards
  * (one process per GPU). handle: 64 bytes. */

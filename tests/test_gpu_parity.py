@@ -228,26 +228,36 @@ def test_host_step_graph_replay_matches_device_step(engine):
     ent0 = rng.uniform(-0.3, 0.3, size=(E, 2 * k)).astype(np.float32)
     rel0 = rng.uniform(-0.3, 0.3, size=(R, 2 * k)).astype(np.float32)
     out = {}
-    for mode in ("device", "host"):
+    for mode in ("device", "host", "pipelined"):
         m = models.ComplEx(k=k, eta=eta, epochs=1, batches_count=4, seed=5, optimizer="adam", optimizer_params={"lr": 1e-2},
                            loss="nll", initializer="constant", initializer_params={"entity": ent0, "relation": rel0})
         f = m._fit_prepare(E, R)
         losses = []
         Xd = torch.from_numpy(X).cuda()
         Xh = torch.from_numpy(X).pin_memory()
-        for step in range(6):
+        for step in range(9):
             lo, hi = (step % 4) * n, (step % 4 + 1) * n
             if mode == "device":
                 m._fit_step_device(Xd[lo:hi])
                 torch.cuda.synchronize()
                 losses.append(float(f["loss_dev"].item()))
-            else:
+            elif mode == "host":
                 losses.append(m._fit_step_host(Xh[lo:hi]))
+            else:  # the loss of step t comes back from the call that submits step t+1, the last one from the flush
+                lv = m._fit_step_host_pipelined(Xh[lo:hi])
+                assert (lv is None) == (step == 0)
+                if lv is not None:
+                    losses.append(lv)
+        if mode == "pipelined":
+            losses.append(m._fit_host_flush())
+            assert m._fit_host_flush() is None
         torch.cuda.synchronize()
         out[mode] = (f["ent"].cpu().numpy(), f["rel"].cpu().numpy(), np.asarray(losses))
     np.testing.assert_array_equal(out["device"][0], out["host"][0])
     np.testing.assert_array_equal(out["device"][1], out["host"][1])
     np.testing.assert_array_equal(out["device"][2], out["host"][2])
+    for j in range(3):
+        np.testing.assert_array_equal(out["host"][j], out["pipelined"][j])
     assert np.all(np.isfinite(out["host"][2])) and out["host"][2][-1] < out["host"][2][0]
 
 
