@@ -17,6 +17,7 @@ OPT_IDS = {"adam": 0, "adagrad": 1, "momentum": 2, "sgd": 3}
 TRAIN_SIDE_IDS = {"s,o": 0, "s+o": 0, "s": 1, "o": 2}
 RANK_SIDE_IDS = {"s,o": 0, "s+o": 1, "s": 2, "o": 3}
 STRATEGY_IDS = {"worst": 0, "best": 1, "middle": 2}
+NL_IDS = {"linear": 0, "tanh": 1, "sigmoid": 2, "softplus": 3}
 F_RESET_STATE = 1
 F_NO_UPDATE = 2
 
@@ -49,6 +50,7 @@ class KgeTrainArgs(C.Structure):
         ("alpha", C.c_float),
         ("reg_p", C.c_int32), ("reg_lambda_ent", C.c_float), ("reg_lambda_rel", C.c_float),
         ("neg_entities", C.c_void_p), ("neg_entities_n", C.c_int64),
+        ("non_linearity", C.c_int32),
     ]
 
 
@@ -79,9 +81,9 @@ SYMBOLS = {
     "kge_filter_build": (_I, [_P, _P, _L, _L, _L, _P]),
     "kge_filter_clear": (_I, [_P]),
     "kge_filter_size_sync": (_L, [_P]),
-    "kge_rank_counts": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _L, _P, _L, _I, _I, _I, _P, _P]),
+    "kge_rank_counts": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _L, _P, _L, _I, _I, _I, _I, _P, _P]),
     "kge_rank_finalize": (_I, [_P, _P, _L, _I, _I, _I, _P, _P, _P]),
-    "kge_rank_host": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _I, _I, _I, _I, _P, _P]),
+    "kge_rank_host": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _P]),
     "kge_dev_alloc": (_I, [_L, C.POINTER(_P)]),
     "kge_dev_free": (_I, [_P]),
     "kge_ipc_export": (_I, [_P, _P]),

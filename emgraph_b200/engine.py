@@ -138,11 +138,12 @@ class Engine:
                    ent_m=None, ent_v=None, rel_m=None, rel_v=None, repl=None, keep_subj=None,
                    dbg_scores=None, dbg_grad_ent=None, dbg_grad_rel=None, stage=None, grad_tails=None,
                    grad_tail_stride=0, alpha=0.5, reg_p=0, reg_lambda_ent=0.0, reg_lambda_rel=0.0,
-                   neg_entities=None, neg_entities_n=0) -> KgeTrainArgs:
+                   neg_entities=None, neg_entities_n=0, non_linearity=0) -> KgeTrainArgs:
         a = KgeTrainArgs()
         a.model, a.loss, a.opt, a.side, a.flags = model, loss, opt, side, flags
         a.k, a.eta, a.margin, a.alpha = k, eta, margin, alpha
         a.reg_p, a.reg_lambda_ent, a.reg_lambda_rel = int(reg_p), float(reg_lambda_ent), float(reg_lambda_rel)
+        a.non_linearity = int(non_linearity)
         a.lr, a.beta1, a.beta2, a.eps, a.momentum = lr, beta1, beta2, eps, momentum
         a.seed, a.step, a.neg_index_base = seed, step, neg_index_base
         a.ent = ent if isinstance(ent, KgeTable) else make_table(ent)
@@ -280,7 +281,7 @@ class Engine:
         return int(self.lib.kge_filter_size_sync(self._h))
 
     def rank_counts(self, model: int, k: int, ent, rel, test, *, side=0, filtered=False, use_tensor_cores=False,
-                    ent_local=None, row_begin=0, row_end=None, counts=None):
+                    ent_local=None, row_begin=0, row_end=None, counts=None, non_linearity=0):
         tb = ent if isinstance(ent, KgeTable) else make_table(ent)
         if ent_local is None:
             assert isinstance(ent, torch.Tensor)
@@ -295,7 +296,7 @@ class Engine:
             counts = torch.empty((T, 2, 4), dtype=torch.int32, device=self.tdev)
         check(self.lib.kge_rank_counts(self._h, model, k, C.byref(tb), _ptr(rel), rel.shape[0], _ptr(ent_local),
                                        row_begin, row_end, _ptr(test), T, side, int(bool(filtered)),
-                                       int(bool(use_tensor_cores)), _ptr(counts), _stream()))
+                                       int(bool(use_tensor_cores)), int(non_linearity), _ptr(counts), _stream()))
         self.launches += 3 if T else 0
         return counts
 
@@ -313,12 +314,14 @@ class Engine:
         self.launches += 1 if T else 0
         return ranks
 
-    def rank(self, model: int, k: int, ent, rel, test, *, side=0, strategy=0, filtered=False, use_tensor_cores=False):
-        counts = self.rank_counts(model, k, ent, rel, test, side=side, filtered=filtered, use_tensor_cores=use_tensor_cores)
+    def rank(self, model: int, k: int, ent, rel, test, *, side=0, strategy=0, filtered=False, use_tensor_cores=False,
+             non_linearity=0):
+        counts = self.rank_counts(model, k, ent, rel, test, side=side, filtered=filtered, use_tensor_cores=use_tensor_cores,
+                                  non_linearity=non_linearity)
         return self.rank_finalize(counts, side=side, strategy=strategy, filtered=filtered)
 
     def rank_host(self, model: int, k: int, ent, rel, test_host, ranks_host, *, side=0, strategy=0, filtered=False,
-                  use_tensor_cores=False):
+                  use_tensor_cores=False, non_linearity=0):
         """Host-buffer ranking: test_host int32 [T,3] CPU (pinned), ranks_host int32 CPU out; syncs."""
         tb = make_table(ent)
         T = test_host.shape[0]
@@ -327,7 +330,7 @@ class Engine:
         assert ranks_host.numel() == T * (2 if side == _lib.RANK_SIDE_IDS["s,o"] else 1)
         check(self.lib.kge_rank_host(self._h, model, k, C.byref(tb), _ptr(rel), rel.shape[0],
                                      C.c_void_p(test_host.data_ptr()), T, side, strategy, int(bool(filtered)),
-                                     int(bool(use_tensor_cores)), C.c_void_p(ranks_host.data_ptr()), _stream()))
+                                     int(bool(use_tensor_cores)), int(non_linearity), C.c_void_p(ranks_host.data_ptr()), _stream()))
         self.launches += 4 if T else 0
         return ranks_host
 

@@ -295,6 +295,12 @@ class EmbeddingModel:
     def _model_id(self):
         return model_id(self.name, int(self.embedding_model_params.get("norm", DEFAULT_NORM_TRANSE)))
 
+    def _non_linearity(self):  # models/EmbeddingModel.py:679-689
+        nl = self.embedding_model_params.get("non_linearity", "linear")
+        if nl not in _lib.NL_IDS:
+            raise ValueError("Invalid non-linearity")
+        return _lib.NL_IDS[nl]
+
     def _train_sides(self):
         # the reference reads 'corrupt_side' though ctors document 'corrupt_sides' (SURVEY F9): accept both
         sides = self.embedding_model_params.get("corrupt_side", self.embedding_model_params.get("corrupt_sides", DEFAULT_CORRUPT_SIDE_TRAIN))
@@ -471,6 +477,7 @@ class EmbeddingModel:
             kw=dict(model=self._model_id(), loss=_lib.LOSS_IDS[self.loss], opt=opt, k=self.k, eta=self.eta,
                     flags=_lib.F_RESET_STATE if reset else 0, margin=float(self.loss_params.get("margin", DEFAULT_MARGIN_ADVERSARIAL if self.loss == "self_adversarial" else DEFAULT_MARGIN)),
                     alpha=float(self.loss_params.get("alpha", DEFAULT_ALPHA_ADVERSARIAL)), **self._reg,
+                    non_linearity=self._non_linearity(),
                     lr=float(self.optimizer_params.get("lr", DEFAULT_LR)),
                     momentum=float(self.optimizer_params.get("momentum", DEFAULT_MOMENTUM)), seed=int(self.seed)))
         return self._fit
@@ -684,7 +691,8 @@ class EmbeddingModel:
             T = test_h.shape[0]
             ranks_h = torch.empty((T, 2) if side == "s,o" else (T,), dtype=torch.int32).pin_memory()
             eng.rank_host(mid, self.k, ent, rel, test_h, ranks_h, side=_lib.RANK_SIDE_IDS[side],
-                          strategy=_lib.STRATEGY_IDS[strategy], filtered=filtered, use_tensor_cores=use_tc)
+                          strategy=_lib.STRATEGY_IDS[strategy], filtered=filtered, use_tensor_cores=use_tc,
+                          non_linearity=self._non_linearity())
             return ranks_h.numpy().copy()
         # ---- entities_subset: corruptions only from `ce` (models/EmbeddingModel.py:1845-1857, :1898-1940).
         # The entities are re-labelled so that the subset occupies rows [0,|C|) of a permuted table; the sweep
@@ -707,7 +715,8 @@ class EmbeddingModel:
             dataset_handle.build_filter(eng, E, R, perm=perm)
         nC = int(C.numel())
         counts = eng.rank_counts(mid, self.k, ent_p, rel, test_p, side=_lib.RANK_SIDE_IDS[side], filtered=filtered,
-                                 use_tensor_cores=use_tc, ent_local=ent_p[:nC], row_begin=0, row_end=nC)
+                                 use_tensor_cores=use_tc, ent_local=ent_p[:nC], row_begin=0, row_end=nC,
+                                 non_linearity=self._non_linearity())
         self_cand = torch.stack([in_c[test[:, 0]], in_c[test[:, 2]]], 1).to(torch.uint8).contiguous()
         ranks = eng.rank_finalize(counts, side=_lib.RANK_SIDE_IDS[side], strategy=_lib.STRATEGY_IDS[strategy], filtered=filtered,
                                   self_is_candidate=self_cand)

@@ -163,6 +163,24 @@ def side_mask(side, n_eta, rng=None):
 # --------------------------------------------------------------------------------------------
 # losses  (losses/pairwise.py:66-70, nll.py:55-59, nll_multiclass.py:70-81, utils.py:44-53)
 # --------------------------------------------------------------------------------------------
+def non_linearity(name, x, dtype=np.float32):
+    """(g(x), g'(x)) of embedding_model_params['non_linearity'] (models/EmbeddingModel.py:679-689, :801-812);
+    'softplus' is the reference's custom_softplus log(1 + 9999*exp(x)), gradient 1 - 1/(1 + 9999*exp(x)) (:89-96)."""
+    x = np.asarray(x, dtype=dtype)
+    if name in (None, "linear"):
+        return x, np.ones_like(x)
+    if name == "tanh":
+        t = np.tanh(x)
+        return t, 1 - t * t
+    if name == "sigmoid":
+        g = 1 / (1 + np.exp(-x))
+        return g, g * (1 - g)
+    if name == "softplus":
+        e = dtype(9999) * np.exp(x)
+        return np.log(1 + e), 1 - 1 / (1 + e)
+    raise ValueError("Invalid non-linearity")
+
+
 def _clip(x):
     return np.clip(x, CLIP_LO, CLIP_HI)
 
@@ -272,7 +290,7 @@ def optimizer_step(opt, w, g, touched, lr, state=None, step=1, momentum=0.9, dty
 # --------------------------------------------------------------------------------------------
 def train_step(model, k, loss, eta, ent, rel, pos, keep_subj, repl, margin=1.0, norm=1,
                opt=None, lr=5e-4, state=None, step=1, dtype=np.float32, grad_dtype=np.float64, alpha=0.5,
-               reg_p=0, reg_lambda_ent=0.0, reg_lambda_rel=0.0):
+               reg_p=0, reg_lambda_ent=0.0, reg_lambda_rel=0.0, nl="linear"):
     """Forward in `dtype` (the reference is fp32), gradients in `grad_dtype`.
     Returns dict(loss, scores_pos, scores_neg, grad_ent[E,K], grad_rel[R,K], touched_ent, touched_rel
     [, ent_new, rel_new, state_ent, state_rel])."""
@@ -281,7 +299,10 @@ def train_step(model, k, loss, eta, ent, rel, pos, keep_subj, repl, margin=1.0, 
     neg = corruptions_for_fit(pos, eta, keep_subj, repl)
     sp = score(model, k, ent, rel, pos, norm, dtype)
     sn = score(model, k, ent, rel, neg, norm, dtype)
+    sp, gsp = non_linearity(nl, sp, dtype)
+    sn, gsn = non_linearity(nl, sn, dtype)
     val, dpos, dneg = loss_and_dscore(loss, sp, sn, eta, margin, dtype, alpha)
+    dpos, dneg = dpos * gsp, dneg * gsn
     gd = grad_dtype
     g_ent = np.zeros(ent.shape, dtype=gd)
     g_rel = np.zeros(rel.shape, dtype=gd)
@@ -371,7 +392,8 @@ def compare(score_corr, score_pos, strategy="worst"):
     return int(np.sum(c >= p))
 
 
-def rank_one(model, k, ent, rel, x, filt=None, side="s,o", strategy="worst", norm=1, dtype=np.float32, subset=None):
+def rank_one(model, k, ent, rel, x, filt=None, side="s,o", strategy="worst", norm=1, dtype=np.float32, subset=None,
+             nl="linear"):
     """Per-test-triple rank (models/EmbeddingModel.py:1856-1866, :1883-1892, :1942-1986).
 
     subset: optional entity ids used to generate the corruptions (eval_config['corruption_entities'],
@@ -383,8 +405,8 @@ def rank_one(model, k, ent, rel, x, filt=None, side="s,o", strategy="worst", nor
     cand = np.arange(E) if subset is None else np.asarray(subset, dtype=np.int64).reshape(-1)
     C = cand.shape[0]
     corr = corruptions_for_eval(x, cand, side)
-    sc = score(model, k, ent, rel, corr, norm, dtype)
-    sp = score(model, k, ent, rel, x, norm, dtype)[0]
+    sc = non_linearity(nl, score(model, k, ent, rel, corr, norm, dtype), dtype)[0]  # models/EmbeddingModel.py:1868-1881
+    sp = non_linearity(nl, score(model, k, ent, rel, x, norm, dtype), dtype)[0][0]
     hi_o = hi_s = 0
     if filt is not None:
         idx_o, idx_s = filt.participating(x)
@@ -409,11 +431,11 @@ def rank_one(model, k, ent, rel, x, filt=None, side="s,o", strategy="worst", nor
 
 
 def ranks(model, k, ent, rel, test, filter_triples=None, side="s,o", strategy="worst", norm=1, dtype=np.float32,
-          subset=None):
+          subset=None, nl="linear"):
     """Intended semantics of get_ranks: the per-triple graph evaluated for EVERY test triple
     (models/EmbeddingModel.py:2046-2099)."""
     filt = FilterIndex(filter_triples) if filter_triples is not None else None
-    return np.asarray([rank_one(model, k, ent, rel, x, filt, side, strategy, norm, dtype, subset)
+    return np.asarray([rank_one(model, k, ent, rel, x, filt, side, strategy, norm, dtype, subset, nl)
                        for x in np.asarray(test).reshape(-1, 3)])
 
 

@@ -48,7 +48,14 @@ REG_CASES = [
     ("complex_pairwise_l3", "ComplEx", "pairwise", 8, 4, 48, 4, 30, "s,o", {"margin": 1.0}, {}, {"p": 3, "lambda": [1e-2, 5e-2]}),
     ("transe_l1_pairwise_l1", "TransE", "pairwise", 10, 3, 50, 3, 25, "s,o", {"margin": 2.0}, {}, {"p": 1, "lambda": 1e-3}),
 ]
-TRAIN_CASES = [c + (None,) for c in TRAIN_CASES] + REG_CASES
+# embedding_model_params['non_linearity'] (models/EmbeddingModel.py:679-689, :801-812)
+NL_CASES = [
+    ("distmult_nll_tanh", "DistMult", "nll", 12, 4, 64, 5, 40, "s,o", {}, {"non_linearity": "tanh"}, None),
+    ("complex_pairwise_sigmoid", "ComplEx", "pairwise", 8, 4, 48, 4, 30, "s,o", {"margin": 0.3}, {"non_linearity": "sigmoid"}, None),
+    ("transe_l2_multiclass_softplus", "TransE", "multiclass_nll", 10, 5, 50, 3, 25, "s,o", {}, {"non_linearity": "softplus", "norm": 2}, None),
+    ("hole_selfadv_tanh", "HolE", "self_adversarial", 8, 4, 48, 3, 30, "s,o", {"margin": 0.5}, {"non_linearity": "tanh"}, None),
+]
+TRAIN_CASES = [c + (None,) for c in TRAIN_CASES] + REG_CASES + NL_CASES
 
 RANK_CASES = [
     # name, model, k, E, R, F, T, emb_params, scale
@@ -57,6 +64,8 @@ RANK_CASES = [
     ("rank_distmult", "DistMult", 16, 150, 5, 1200, 60, {}, 0.7),
     ("rank_complex", "ComplEx", 12, 130, 4, 1000, 60, {}, 0.7),
     ("rank_hole", "HolE", 8, 100, 3, 800, 50, {}, 1.0),
+    ("rank_distmult_tanh", "DistMult", 12, 110, 4, 800, 40, {"non_linearity": "tanh"}, 0.6),
+    ("rank_transe_l1_sigmoid", "TransE", 8, 90, 3, 600, 40, {"non_linearity": "sigmoid"}, 0.4),
 ]
 
 
@@ -87,7 +96,7 @@ def main():
             model=model, loss_name=loss, k=k, eta=eta, side=side,
             margin=float(lp.get("margin", 3.0 if loss == "self_adversarial" else 1.0)), alpha=float(lp.get("alpha", 0.5)),
             reg_p=int((rp or {}).get("p", 0)), reg_lambda_ent=float(lam[0]), reg_lambda_rel=float(lam[1]),
-            norm=int(ep.get("norm", 1)), ent=ent, rel=rel, pos=pos, keep_subj=keep, repl=repl,
+            norm=int(ep.get("norm", 1)), nl=str(ep.get("non_linearity", "linear")), ent=ent, rel=rel, pos=pos, keep_subj=keep, repl=repl,
             loss=np.float32(ref["loss"]), scores_pos=ref["scores_pos"], scores_neg=ref["scores_neg"],
             neg=ref["neg"].astype(np.int32), grad_ent=ref["grad_ent"], grad_rel=ref["grad_rel"])
         print("train", name, "loss", ref["loss"])
@@ -104,7 +113,8 @@ def main():
         test = filt[rng.permutation(F)[:T]].copy()
         # a few test triples that are NOT in the filter: self must still be filtered
         test[:5, 2] = (test[:5, 2] + 7) % E
-        out = dict(model=model, k=k, norm=int(ep.get("norm", 1)), ent=ent, rel=rel, filt=filt, test=test)
+        out = dict(model=model, k=k, norm=int(ep.get("norm", 1)), nl=str(ep.get("non_linearity", "linear")), ent=ent, rel=rel, filt=filt,
+                   test=test)
         for side in ("s,o", "s+o", "s", "o"):
             for strat in ("worst", "best", "middle"):
                 for fl in (0, 1):

@@ -101,7 +101,21 @@ def _build_tf():
     tf.unique = lambda x: (torch.unique(x), None)
     tf.Assert = lambda *a, **k: None
     tf.control_dependencies = lambda deps: contextlib.nullcontext()
-    tf.custom_gradient = lambda f: f
+    def custom_gradient(f):
+        """tf.custom_gradient: f(x) -> (y, grad_fn); backward calls grad_fn(dy)."""
+        class _Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x):
+                y, g = f(x.detach())
+                ctx.grad_fn_ = g
+                return y
+
+            @staticmethod
+            def backward(ctx, dy):
+                return ctx.grad_fn_(dy)
+        return _Fn.apply
+
+    tf.custom_gradient = custom_gradient
     tf.device = lambda name: contextlib.nullcontext()
 
     m = types.ModuleType("tensorflow.math")
@@ -175,6 +189,7 @@ def load():
         ns.numpy_adapter = importlib.import_module("emgraph.datasets.numpy_adapter")
         ns.sqlite_adapter = importlib.import_module("emgraph.datasets.sqlite_adapter")
         ns.losses = importlib.import_module("emgraph.losses")
+        ns.embedding_model = importlib.import_module("emgraph.models.EmbeddingModel")
     finally:
         sys.path.remove(REF_ROOT)
         if saved is not None:
@@ -194,6 +209,20 @@ def make_model(name, k, eta, loss, loss_params=None, embedding_model_params=None
                regularizer_params=dict(regularizer_params or {}))
 
 
+def _ref_non_linearity(ns, model, scores):
+    """models/EmbeddingModel.py:679-689 / :801-812 / :1868-1881 with the reference's own ops."""
+    nl = model.embedding_model_params.get("non_linearity", "linear")
+    if nl == "linear":
+        return scores
+    if nl == "tanh":
+        return ns.tf.tanh(scores)
+    if nl == "sigmoid":
+        return ns.tf.sigmoid(scores)
+    if nl == "softplus":
+        return ns.embedding_model.custom_softplus(scores)
+    raise ValueError("Invalid non-linearity")
+
+
 def ref_train_forward_backward(name, k, eta, loss, ent, rel, pos, keep_subj, repl,
                                loss_params=None, embedding_model_params=None, side="s,o", regularizer=None,
                                regularizer_params=None):
@@ -206,7 +235,7 @@ def ref_train_forward_backward(name, k, eta, loss, ent, rel, pos, keep_subj, rep
     model.rel_emb = torch.tensor(rel, dtype=torch.float32, requires_grad=True)
     x_pos = torch.as_tensor(np.asarray(pos), dtype=torch.int32)
     e_s, e_p, e_o = model._lookup_embeddings(x_pos)
-    scores_pos = model._fn(e_s, e_p, e_o)
+    scores_pos = _ref_non_linearity(ns, model, model._fn(e_s, e_p, e_o))
     sp_out = scores_pos.detach().numpy().copy()
     if model.loss.get_state("require_same_size_pos_neg"):
         scores_pos = ns.tf.reshape(ns.tf.tile(scores_pos, [eta]), [ns.tf.shape(scores_pos)[0] * eta])
@@ -218,7 +247,7 @@ def ref_train_forward_backward(name, k, eta, loss, ent, rel, pos, keep_subj, rep
         x_pos, entities_list=None, eta=eta, corrupt_side=side, entities_size=ent.shape[0], rnd=0)
     assert not RANDOM_FIFO
     e_s, e_p, e_o = model._lookup_embeddings(x_neg)
-    scores_neg = model._fn(e_s, e_p, e_o)
+    scores_neg = _ref_non_linearity(ns, model, model._fn(e_s, e_p, e_o))
     loss_t = model.loss.apply(scores_pos, scores_neg)
     if model.regularizer is not None:  # models/EmbeddingModel.py:818-820
         loss_t = loss_t + model.regularizer.apply([model.ent_emb, model.rel_emb])
@@ -254,9 +283,9 @@ def ref_ranks(name, k, ent, rel, test, filter_triples=None, side="s,o", strategy
             xt = torch.as_tensor(x[None, :].astype(np.int32))
             corr = ns.protocol.generate_corruptions_for_eval(xt, all_ent, side)
             e_s, e_p, e_o = model._lookup_embeddings(corr)
-            scores_predict = model._fn(e_s, e_p, e_o)
+            scores_predict = _ref_non_linearity(ns, model, model._fn(e_s, e_p, e_o))
             e_s, e_p, e_o = model._lookup_embeddings(xt)
-            score_positive = tf.squeeze(model._fn(e_s, e_p, e_o))
+            score_positive = _ref_non_linearity(ns, model, tf.squeeze(model._fn(e_s, e_p, e_o)))
             hi_o = hi_s = 0
             if side == "s,o":
                 half = scores_predict.shape[0] // 2

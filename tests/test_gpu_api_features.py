@@ -179,3 +179,52 @@ def test_save_restore_predict_and_resume(engine, tmp_path):
     np.testing.assert_array_equal(evaluate_performance(X[:30], r, filter_triples=X), evaluate_performance(X[:30], m, filter_triples=X))
     np.testing.assert_array_equal(r.predict(tri[:50], from_idx=True), y0)  # reference tests/.../test_models.py:967-992
     assert set(r._opt_state) == {"ent_m", "ent_v", "rel_m", "rel_v"} and r._opt_step == m._opt_step
+
+
+@pytest.mark.parametrize("nl", ["tanh", "sigmoid", "softplus"])
+def test_non_linearity_train_and_rank_match_oracle(engine, nl):
+    """embedding_model_params['non_linearity'] (models/EmbeddingModel.py:679-689, :801-812, :1868-1881): the loss and
+    the rank comparison see nl(score); predict returns the raw score."""
+    from emgraph_b200 import _lib
+    from emgraph_b200.engine import model_id
+    from emgraph_b200.evaluation import evaluate_performance
+    from emgraph_b200.models import ComplEx
+    rng = np.random.default_rng(12)
+    E, R, k, eta, n, model = 160, 4, 20, 6, 200, "ComplEx"
+    K = ko.internal_k(model, k)
+    ent = (rng.normal(size=(E, K)) * 0.35).astype(np.float32)
+    rel = (rng.normal(size=(R, K)) * 0.35).astype(np.float32)
+    pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+    keep = rng.integers(0, 2, n * eta).astype(np.uint8)
+    repl = rng.integers(0, E, n * eta).astype(np.int32)
+    for loss in ("nll", "pairwise", "multiclass_nll", "self_adversarial", "absolute_margin"):
+        ent_d, rel_d = torch.from_numpy(ent).cuda(), torch.from_numpy(rel).cuda()
+        out = dict(loss=torch.zeros(1, device="cuda"), scores=torch.zeros(n * (1 + eta), device="cuda"),
+                   g_ent=torch.zeros_like(ent_d), g_rel=torch.zeros_like(rel_d))
+        a = engine.train_args(model=model_id(model), loss=_lib.LOSS_IDS[loss], opt=0, k=k, eta=eta, ent=ent_d, rel=rel_d,
+                              pos=torch.from_numpy(pos).cuda(), loss_out=out["loss"], flags=_lib.F_NO_UPDATE, margin=0.7, alpha=0.8,
+                              repl=torch.from_numpy(repl).cuda(), keep_subj=torch.from_numpy(keep).cuda(),
+                              dbg_scores=out["scores"], dbg_grad_ent=out["g_ent"], dbg_grad_rel=out["g_rel"],
+                              non_linearity=_lib.NL_IDS[nl])
+        engine.train_step(a)
+        torch.cuda.synchronize()
+        o = ko.train_step(model, k, loss, eta, ent, rel, pos, keep, repl, margin=0.7, alpha=0.8, nl=nl, dtype=np.float64)
+        np.testing.assert_allclose(out["scores"].cpu().numpy()[:n], o["scores_pos"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(out["scores"].cpu().numpy()[n:], o["scores_neg"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(out["loss"].item(), o["loss"], rtol=1e-5)
+        sc = max(1.0, np.abs(o["grad_ent"]).max())
+        np.testing.assert_allclose(out["g_ent"].cpu().numpy(), o["grad_ent"], rtol=1e-4, atol=1e-5 * sc)
+        np.testing.assert_allclose(out["g_rel"].cpu().numpy(), o["grad_rel"], rtol=1e-4, atol=1e-5 * max(1.0, np.abs(o["grad_rel"]).max()))
+    # ranking through the model API
+    tri = ko.synthetic_triples(E, R, 1000, seed=9)
+    X = _labels(tri)
+    m = _fitted(ComplEx, k, E, R, ent, rel, X, embedding_model_params={"non_linearity": nl})
+    test = tri[:40]
+    for tc in (False, True):
+        m.engine_params["rank_tensor_cores"] = tc
+        got = evaluate_performance(_labels(test), m, filter_triples=X, corrupt_side="s,o")
+        exp = ko.ranks(model, k, ent, rel, test, tri, "s,o", "worst", nl=nl)
+        assert got.shape == exp.shape and (got != exp).sum() <= max(2, exp.size // 20), (nl, tc, (got != exp).sum())
+    np.testing.assert_allclose(m.predict(X[:20]), ko.score(model, k, ent, rel, tri[:20]), rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        ComplEx(k=4, epochs=1, batches_count=1, embedding_model_params={"non_linearity": "relu"}).fit(X)

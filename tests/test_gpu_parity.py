@@ -36,6 +36,11 @@ def _close(a, b, rtol=RTOL, scale=None):
     np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * sc)
 
 
+def _nl_id(g):
+    from emgraph_b200 import _lib
+    return _lib.NL_IDS[str(g["nl"])] if "nl" in g.files else 0
+
+
 def _reg_kw(g):
     if "reg_p" not in g.files or int(g["reg_p"]) == 0:
         return {}
@@ -72,7 +77,7 @@ def test_train_step_vs_reference_golden(engine, path):
     model, k, eta = str(g["model"]), int(g["k"]), int(g["eta"])
     r = run_step(engine, model, k, str(g["loss_name"]), eta, g["ent"], g["rel"], g["pos"], g["keep_subj"], g["repl"],
                  margin=float(g["margin"]), norm=int(g["norm"]), flags=_lib.F_NO_UPDATE,
-                 alpha=float(g["alpha"]) if "alpha" in g.files else 0.5, **_reg_kw(g))
+                 alpha=float(g["alpha"]) if "alpha" in g.files else 0.5, non_linearity=_nl_id(g), **_reg_kw(g))
     n = g["pos"].shape[0]
     _close(r["scores"][:n], g["scores_pos"])
     _close(r["scores"][n:], g["scores_neg"])
@@ -82,6 +87,8 @@ def test_train_step_vs_reference_golden(engine, path):
     # NO_UPDATE leaves the parameters untouched
     np.testing.assert_array_equal(r["ent"], g["ent"])
     np.testing.assert_array_equal(r["rel"], g["rel"])
+    if _nl_id(g):
+        return  # predict returns raw scores (models/EmbeddingModel.py:2132-2133 applies no non-linearity)
     # predict path agrees too
     sc = engine.score(_ids(model, int(g["norm"])), k, _dev(g["ent"]), _dev(g["rel"]), _dev(g["pos"], torch.int32)).cpu().numpy()
     _close(sc, g["scores_pos"])
@@ -293,23 +300,24 @@ def test_in_kernel_corruptions_are_uniform_and_reproducible(engine):
 # ------------------------------------------------------------------------------------------------
 # ranking
 # ------------------------------------------------------------------------------------------------
-def _admissible(model, k, ent, rel, x, side_col, got, exp, norm):
+def _admissible(model, k, ent, rel, x, side_col, got, exp, norm, nl="linear"):
     """A rank may differ from the oracle's only by the number of candidates whose score sits within
     fp32 noise of the positive's x1e5 quantisation boundary."""
     so, ss, sp = ko.sweep_scores(model, k, ent, rel, x, norm)
+    so, ss, sp = (ko.non_linearity(nl, np.asarray(v, np.float64), np.float64)[0] for v in (so, ss, sp))
     sc = so if side_col == 1 else ss
     tol = 1.0 + 1e-6 * 1e5 * max(1.0, np.abs(sc).max())  # quanta
     near = np.sum(np.abs(sc * 1e5 - sp * 1e5) <= tol)
     return abs(int(got) - int(exp)) <= near
 
 
-def _rank_gpu(engine, model, k, ent, rel, test, filt, side, strat, norm=1, tc=False):
+def _rank_gpu(engine, model, k, ent, rel, test, filt, side, strat, norm=1, tc=False, nl=0):
     from emgraph_b200 import _lib
     ent_d, rel_d = _dev(ent), _dev(rel)
     if filt is not None:
         engine.filter_build(_dev(filt, torch.int32), ent.shape[0], rel.shape[0])
     r = engine.rank(_ids(model, norm), k, ent_d, rel_d, _dev(test, torch.int32), side=_lib.RANK_SIDE_IDS[side],
-                    strategy=_lib.STRATEGY_IDS[strat], filtered=filt is not None, use_tensor_cores=tc)
+                    strategy=_lib.STRATEGY_IDS[strat], filtered=filt is not None, use_tensor_cores=tc, non_linearity=nl)
     torch.cuda.synchronize()
     return r.cpu().numpy()
 
@@ -322,15 +330,16 @@ def test_ranks_vs_reference_golden(engine, path):
         for strat in ("worst", "best", "middle"):
             for fl in (0, 1):
                 key = "ranks_%s_%s_%d" % (side.replace(",", "c").replace("+", "p"), strat, fl)
-                got = _rank_gpu(engine, model, k, g["ent"], g["rel"], g["test"], g["filt"] if fl else None, side, strat, norm)
+                got = _rank_gpu(engine, model, k, g["ent"], g["rel"], g["test"], g["filt"] if fl else None, side, strat, norm,
+                                nl=_nl_id(g))
                 exp = g[key]
                 assert got.shape == exp.shape, key
                 bad = np.argwhere(got != exp)
                 for idx in bad:
                     t = idx[0]
                     col = idx[1] if exp.ndim == 2 else (1 if side == "o" else 0)
-                    assert _admissible(model, k, g["ent"], g["rel"], g["test"][t], col, got[tuple(idx)], exp[tuple(idx)], norm), \
-                        (key, t, got[tuple(idx)], exp[tuple(idx)])
+                    assert _admissible(model, k, g["ent"], g["rel"], g["test"][t], col, got[tuple(idx)], exp[tuple(idx)], norm,
+                                       str(g["nl"]) if "nl" in g.files else "linear"), (key, t, got[tuple(idx)], exp[tuple(idx)])
                 assert len(bad) <= max(1, exp.size // 50), (key, len(bad))
 
 
@@ -397,14 +406,14 @@ def test_rank_edge_cases(engine):
 # ------------------------------------------------------------------------------------------------
 # tensor-core (tcgen05 3xTF32) ranking sweep
 # ------------------------------------------------------------------------------------------------
-def _assert_ranks_close(model, k, ent, rel, test, got, exp, norm=1, max_frac=0.04):
+def _assert_ranks_close(model, k, ent, rel, test, got, exp, norm=1, max_frac=0.04, nl="linear"):
     assert got.shape == exp.shape
     bad = np.argwhere(got != exp)
     for idx in bad:
         t = idx[0]
         col = idx[1] if exp.ndim == 2 else 1
         if exp.ndim == 2:
-            assert _admissible(model, k, ent, rel, test[t], col, got[tuple(idx)], exp[tuple(idx)], norm), \
+            assert _admissible(model, k, ent, rel, test[t], col, got[tuple(idx)], exp[tuple(idx)], norm, nl), \
                 (t, col, got[tuple(idx)], exp[tuple(idx)])
     assert len(bad) <= max(2, int(exp.size * max_frac)), len(bad)
 
@@ -420,10 +429,12 @@ def test_tc_ranks_vs_reference_golden(engine, path):
         for strat in ("worst", "middle"):
             for fl in (0, 1):
                 key = "ranks_%s_%s_%d" % (side.replace(",", "c").replace("+", "p"), strat, fl)
-                got = _rank_gpu(engine, model, k, g["ent"], g["rel"], g["test"], g["filt"] if fl else None, side, strat, norm, tc=True)
+                got = _rank_gpu(engine, model, k, g["ent"], g["rel"], g["test"], g["filt"] if fl else None, side, strat, norm, tc=True,
+                                nl=_nl_id(g))
                 exp = g[key]
                 if exp.ndim == 2:
-                    _assert_ranks_close(model, k, g["ent"], g["rel"], g["test"], got, exp, norm)
+                    _assert_ranks_close(model, k, g["ent"], g["rel"], g["test"], got, exp, norm,
+                                        nl=str(g["nl"]) if "nl" in g.files else "linear")
                 else:
                     assert got.shape == exp.shape and (got != exp).sum() <= max(1, exp.size // 25), key
 
