@@ -61,6 +61,36 @@ def owned_mask(keys, E: int, world: int, rank: int):
     return (keys >= E) | ((keys >= b) & (keys < e))
 
 
+def push_block_order(S: int, world: int, own: int, group: int = 0):
+    """Host mirror of kge_push_rows_kernel's schedule (csrc/kge_train.cu): the order in which owner `own`
+    visits the 32-slot blocks of every rank's S slots, as (destination rank, block index) pairs.  `group`
+    consecutive blocks go to one destination before the deal moves to the next; 0 = a whole rank's blocks, so
+    each owner works through one destination region at a time, starting with the rank behind it (no two owners
+    begin on the same destination).  Used by the host tests to pin that every block is visited exactly once."""
+    bpr = (S + 31) // 32
+    if group <= 0 or group > bpr:
+        group = bpr
+    gpr = (bpr + group - 1) // group
+    t_start = (own + 1) % world
+    out = []
+    for vb0 in range(gpr * group * world):
+        g, in_g = divmod(vb0, group)
+        rr = (g + t_start) % world
+        lb = (g // world) * group + in_g
+        if lb < bpr:
+            out.append((rr, lb))
+    return out
+
+
+def grad_tail_layout(eta: int, n: int, K: int):
+    """(head floats, tail floats, padded tail stride) of a rank's gradient buffer: head = gs | go | gp rows, tail =
+    Qo | Qs rows + eta*n coefficients + eta*n side flags (bytes); the stride keeps every rank's tail 16-byte aligned
+    inside the all-gathered buffer (csrc/kge_train_fwd.cuh gbuf_floats)."""
+    head = 3 * n * K
+    tail = 2 * n * K + eta * n + (eta * n + 3) // 4
+    return head, tail, (tail + 3) // 4 * 4
+
+
 # ------------------------------------------------------------------------------------------------
 # device memory that peers can map
 # ------------------------------------------------------------------------------------------------
@@ -144,6 +174,7 @@ class ShardedKGE:
         g_floats = eng.train_grad_floats(eta, self.n, K)
         self.g_head = eng.train_grad_head_floats(eta, self.n, K)
         self.tail_stride = (g_floats - self.g_head + 3) // 4 * 4
+        assert (self.g_head, g_floats - self.g_head, self.tail_stride) == grad_tail_layout(eta, self.n, K)
         self.gbuf = PeerBuffer(eng, (self.g_head + self.tail_stride,))
         # staging copy of the entity row of every entity slot of this rank's batch, pushed by the owners
         self.ent_slots = (2 + eta) * self.n

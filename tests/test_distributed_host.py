@@ -36,6 +36,29 @@ def test_batches_are_disjoint_across_ranks_within_a_step():
     assert [D.neg_index_base(r, 20, 128) for r in range(3)] == [0, 2560, 5120]
 
 
+def test_push_schedule_visits_every_block_once_and_spreads_destinations():
+    for S, world in ((67 * 10308, 8), (23 * 4252, 2), (100, 4), (31, 3), (32 * 5, 5)):
+        bpr = (S + 31) // 32
+        for group in (0, 1, 3, 64):
+            firsts = []
+            for own in range(world):
+                order = D.push_block_order(S, world, own, group)
+                assert len(order) == bpr * world and len(set(order)) == bpr * world
+                assert all(0 <= r < world and 0 <= b < bpr for r, b in order)
+                firsts.append(order[0][0])
+            assert sorted(firsts) == list(range(world))  # no two owners start on the same destination
+    # default grouping: one destination region at a time
+    order = D.push_block_order(320, 4, 1, 0)
+    assert [r for r, _ in order] == [2] * 10 + [3] * 10 + [0] * 10 + [1] * 10
+
+
+def test_grad_tail_layout_alignment():
+    for eta, n, K in ((64, 10308, 256), (20, 4252, 400), (5, 3, 8), (7, 33, 10)):
+        head, tail, stride = D.grad_tail_layout(eta, n, K)
+        assert head == 3 * n * K and stride >= tail and stride % 4 == 0 and stride - tail < 4
+        assert tail * 4 >= 2 * n * K * 4 + eta * n * 4 + eta * n  # rows + coefficients + one byte per negative
+
+
 def _worker(rank, world, port, E, R, eta, n, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

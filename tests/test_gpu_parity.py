@@ -225,6 +225,52 @@ def test_hub_rows_long_and_short_runs(engine, E, n, eta):
     np.testing.assert_allclose(r["rel"], o["rel_new"], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("model,k,n,eta,E", [("DistMult", 4, 1, 1, 3), ("ComplEx", 2, 3, 2, 5), ("TransE", 1, 5, 3, 4), ("HolE", 3, 2, 33, 40),
+                                             ("DistMult", 1000, 7, 2, 50), ("ComplEx", 256, 9, 3, 60), ("TransE", 516, 4, 5, 30)])
+def test_train_step_edge_shapes(engine, model, k, n, eta, E):
+    """Tiny and ragged shapes: a single positive, eta = 1, k below one vector, rows that need more than one pass
+    of a warp (K = 1000, 1024 floats), fewer entities than negatives (every row a duplicate run)."""
+    from emgraph_b200 import _lib
+    rng = np.random.default_rng(n * 31 + eta)
+    R = 2
+    K = ko.internal_k(model, k)
+    ent = rng.uniform(-0.5, 0.5, size=(E, K)).astype(np.float32)
+    rel = rng.uniform(-0.5, 0.5, size=(R, K)).astype(np.float32)
+    pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+    keep = rng.integers(0, 2, n * eta).astype(np.uint8)
+    repl = rng.integers(0, E, n * eta).astype(np.int32)
+    for loss in ("nll", "multiclass_nll"):
+        r = run_step(engine, model, k, loss, eta, ent, rel, pos, keep, repl, opt="sgd", lr=1e-2, flags=_lib.F_RESET_STATE)
+        o = ko.train_step(model, k, loss, eta, ent, rel, pos, keep, repl, opt="sgd", lr=1e-2, dtype=np.float64)
+        np.testing.assert_allclose(r["loss"][0], o["loss"], rtol=RTOL)
+        _close(r["scores"][:n], o["scores_pos"])
+        _close(r["scores"][n:], o["scores_neg"])
+        if not (model == "TransE" and k == 1):  # |x| has no gradient at exact ties of 1-d L1 distances
+            _close(r["g_ent"], o["grad_ent"], rtol=1e-4)
+            _close(r["g_rel"], o["grad_rel"], rtol=1e-4)
+            np.testing.assert_allclose(r["ent"], o["ent_new"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_array_equal(r["ent"][~o["touched_ent"]], ent[~o["touched_ent"]])
+
+
+def test_train_step_rejects_bad_arguments(engine):
+    """Error conventions of the C ABI: status < 0 + kge_last_error, surfaced as KgeError (never a CPU fallback)."""
+    from emgraph_b200 import _lib
+    ent, rel = torch.zeros((10, 8), device="cuda"), torch.zeros((2, 8), device="cuda")
+    pos = torch.zeros((4, 3), dtype=torch.int32, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    base = dict(model=2, loss=1, opt=0, k=8, eta=2, ent=ent, rel=rel, pos=pos, loss_out=loss)
+    for bad in (dict(model=9), dict(loss=7), dict(opt=5), dict(k=16), dict(eta=0), dict(non_linearity=4), dict(neg_entities_n=11)):
+        with pytest.raises(_lib.KgeError):
+            engine.train_step(engine.train_args(**{**base, **bad}))
+    # an embedding too wide for the fused kernel is refused loudly
+    wide_e, wide_r = torch.zeros((4, 8192), device="cuda"), torch.zeros((2, 8192), device="cuda")
+    with pytest.raises(_lib.KgeError):
+        engine.train_step(engine.train_args(**{**base, "k": 8192, "ent": wide_e, "rel": wide_r, "flags": _lib.F_NO_UPDATE}))
+    # an empty batch is a no-op
+    engine.train_step(engine.train_args(**{**base, "pos": torch.zeros((0, 3), dtype=torch.int32, device="cuda")}))
+    torch.cuda.synchronize()
+
+
 def test_host_step_graph_replay_matches_device_step(engine):
     """kge_train_step_host (eager first call, then a captured CUDA graph replayed with a fresh step
     counter) must leave the same parameters and losses as the device-resident step, bit for bit."""
