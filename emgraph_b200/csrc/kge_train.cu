@@ -45,9 +45,12 @@ __global__ void kge_emit_kernel(const int32_t* __restrict__ pos, int64_t n, int 
             int64_t q = t - 2 * n;  // j*n + i
             int32_t r;
             uint8_t ks;
+            // keep_in[q]: 0 / 1 fix the side of this negative; >= 2 (or no array) leaves it to `side`.  It may
+            // come without repl_in: a list-valued corrupt_side stacked into one batch
+            const uint8_t kin = keep_in != nullptr ? keep_in[q] : (uint8_t)2;
             if (repl_in != nullptr) {
                 r = repl_in[q];
-                ks = keep_in != nullptr ? keep_in[q] : (side == KGE_SIDE_O ? 1 : 0);
+                ks = kin < 2 ? kin : (side == KGE_SIDE_O ? 1 : 0);
             } else {
                 uint64_t g = neg_base + (uint64_t)q;
                 uint32_t o[4];
@@ -57,7 +60,7 @@ __global__ void kge_emit_kernel(const int32_t* __restrict__ pos, int64_t n, int 
                 // entities_list (:620-641); multiply-shift mapping
                 r = (int32_t)(((uint64_t)o[0] * (uint64_t)(neg_n > 0 ? neg_n : E)) >> 32);
                 if (neg_list != nullptr) r = neg_list[r];
-                ks = side == KGE_SIDE_SO ? (uint8_t)(o[1] >> 31) : (side == KGE_SIDE_O ? 1 : 0);
+                ks = kin < 2 ? kin : (side == KGE_SIDE_SO ? (uint8_t)(o[1] >> 31) : (side == KGE_SIDE_O ? 1 : 0));
             }
             repl_out[q] = r;
             keep_out[q] = ks;

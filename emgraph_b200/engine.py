@@ -138,7 +138,8 @@ class Engine:
                    ent_m=None, ent_v=None, rel_m=None, rel_v=None, repl=None, keep_subj=None,
                    dbg_scores=None, dbg_grad_ent=None, dbg_grad_rel=None, stage=None, grad_tails=None,
                    grad_tail_stride=0, alpha=0.5, reg_p=0, reg_lambda_ent=0.0, reg_lambda_rel=0.0,
-                   neg_entities=None, neg_entities_n=0, non_linearity=0) -> KgeTrainArgs:
+                   neg_entities=None, neg_entities_n=0, non_linearity=0, n_pos=None) -> KgeTrainArgs:
+        """n_pos: batch size when `pos` is None (host-buffer step: the positives arrive with the call)."""
         a = KgeTrainArgs()
         a.model, a.loss, a.opt, a.side, a.flags = model, loss, opt, side, flags
         a.k, a.eta, a.margin, a.alpha = k, eta, margin, alpha
@@ -166,7 +167,9 @@ class Engine:
             assert repl.numel() == eta * pos.shape[0]
             a.repl = repl.data_ptr()
         if keep_subj is not None:
-            assert keep_subj.is_cuda and keep_subj.dtype == torch.uint8 and keep_subj.numel() == eta * pos.shape[0]
+            n_chk = pos.shape[0] if pos is not None else n_pos
+            assert n_chk is not None, "keep_subj without pos needs n_pos"
+            assert keep_subj.is_cuda and keep_subj.dtype == torch.uint8 and keep_subj.numel() == eta * n_chk
             a.keep_subj = keep_subj.data_ptr()
         a.loss_out = loss_out.data_ptr() if loss_out is not None else None
         a.dbg_scores = dbg_scores.data_ptr() if dbg_scores is not None else None

@@ -10,6 +10,8 @@ import numpy as np
 from .engine import to_dev_i32
 from .models import EmbeddingModel, create_mappings, to_idx  # noqa: F401  (re-exported like the reference)
 
+from .model_selection import select_best_model_ranking  # noqa: E402,F401  (evaluation/__init__.py:6 exports it)
+
 TOO_MANY_ENTITIES_TH = 50000  # evaluation/protocol.py:21
 
 

@@ -482,18 +482,35 @@ class EmbeddingModel:
                     momentum=float(self.optimizer_params.get("momentum", DEFAULT_MOMENTUM)), seed=int(self.seed)))
         return self._fit
 
-    def _fit_step_device(self, pos_dev, side="s,o"):
+    # A list-valued corrupt_side (models/EmbeddingModel.py:780-816) sums one loss term per side, each over fresh
+    # corruptions of the same positives, into ONE optimizer step.  Every loss is a sum of per-positive terms,
+    # so the step runs as one batch that holds the positives once per side (n' = S*n) with the side of every
+    # negative fixed through keep_subj codes (0: 's', 1: 'o', 2: per-negative coin) -- negative row
+    # j*n' + s*n + i belongs to side s.  Pinned against the reference by tests/golden/train_multiside_*.npz.
+    _SIDE_CODE = {"s": 0, "o": 1, "s,o": 2, "s+o": 2}
+
+    def _stack_sides(self, pos):
+        """(stacked positives, keep_subj codes) for the model's side list; pos is a [n,3] int32 tensor."""
+        f = self._fit
+        sides, n = f["sides"], pos.shape[0]
+        cache = f.setdefault("side_keep", {})
+        if n not in cache:
+            codes = torch.tensor([self._SIDE_CODE[s] for s in sides], dtype=torch.uint8)
+            cache[n] = codes.repeat_interleave(n).repeat(self.eta).to(f["eng"].tdev)
+        return pos.repeat(len(sides), 1), cache[n]
+
+    def _fit_step_device(self, pos_dev, side="s,o", keep_subj=None):
         """One optimisation step on a device-resident batch; enqueue only, loss stays in f['loss_dev']."""
         f = self._fit
         f["step"] += 1
         neg = f["neg"]
         if self._neg_batch:  # corruptions drawn from the batch's own entities (evaluation/protocol.py:620-641)
             neg = dict(neg_entities=torch.unique(pos_dev[:, [0, 2]]).to(torch.int32))
-        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=pos_dev, loss_out=f["loss_dev"],
+        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=pos_dev, loss_out=f["loss_dev"], keep_subj=keep_subj,
                                 side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"], **neg)
         f["eng"].train_step(a)
 
-    def _fit_step_host(self, pos_host, side="s,o"):
+    def _fit_step_host(self, pos_host, side="s,o", keep_subj=None):
         """One optimisation step fed like the reference feeds it: the batch comes from (pinned) host
         memory and the batch loss is read back (models/EmbeddingModel.py:1329-1337, :1421)."""
         f = self._fit
@@ -501,12 +518,12 @@ class EmbeddingModel:
         neg = f["neg"]
         if self._neg_batch:
             neg = dict(neg_entities=to_dev_i32(np.unique(pos_host[:, [0, 2]].numpy()), f["eng"].tdev))
-        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"],
-                                side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"], **neg)
+        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"], keep_subj=keep_subj,
+                                n_pos=pos_host.shape[0], side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"], **neg)
         f["eng"].train_step_host(a, pos_host, f["loss_host"])
         return float(f["loss_host"][0])
 
-    def _fit_step_host_pipelined(self, pos_host, side="s,o"):
+    def _fit_step_host_pipelined(self, pos_host, side="s,o", keep_subj=None):
         """Like _fit_step_host, but the call returns as soon as the step is queued and hands back the loss of
         the step submitted ONE call earlier (None on the first call): the GPU always has the next step queued
         while the host checks the previous loss.  Every step still copies its batch in and its loss out;
@@ -516,8 +533,8 @@ class EmbeddingModel:
         neg = f["neg"]
         if self._neg_batch:
             neg = dict(neg_entities=to_dev_i32(np.unique(pos_host[:, [0, 2]].numpy()), f["eng"].tdev))
-        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"],
-                                side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"], **neg)
+        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"], keep_subj=keep_subj,
+                                n_pos=pos_host.shape[0], side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"], **neg)
         ring = f.setdefault("loss_ring", torch.zeros(4, dtype=torch.float32).pin_memory())
         i = f["step"] % 4
         ticket = f["eng"].train_step_host_async(a, pos_host, ring[i:i + 1])
@@ -555,6 +572,7 @@ class EmbeddingModel:
         normalize = bool(self.embedding_model_params.get("normalize_ent_emb", False))
         check_every = int(self.engine_params.get("nan_check_every", self.batches_count))
         self.loss_history = []
+        multi_side = len(f["sides"]) > 1
         sched = SGDSchedule(self.optimizer_params, self.batches_count) if self.optimizer == "sgd" else None
         denom = batch_size * (self.eta if self.loss in TILED_POSITIVE_LOSSES else 1) * self.batches_count  # :1343-1344, :1453-1457
         for epoch in range(1, self.epochs + 1):
@@ -566,16 +584,24 @@ class EmbeddingModel:
                     continue
                 if sched is not None:  # sgd: decayed rate of this batch (training/sgd.py:127-185)
                     f["kw"]["lr"] = float(sched(b + 1, epoch))
-                for side in f["sides"]:
-                    if host_batches:
-                        lv = self._fit_step_host_pipelined(Xh[lo:hi], side) if pipelined else self._fit_step_host(Xh[lo:hi], side)
-                        if lv is not None:
-                            if not np.isfinite(lv):  # models/EmbeddingModel.py:1422-1427
-                                raise ValueError("Loss is {}. Please change the hyperparameters.".format(lv))
-                            host_loss += lv
-                    else:
-                        self._fit_step_device(Xd[lo:hi], side)
-                        epoch_loss += f["loss_dev"].double()
+                side, keep = f["sides"][0], None
+                if host_batches:
+                    pos_b = Xh[lo:hi]
+                    if multi_side:  # one step over the positives stacked once per side
+                        pos_b, keep = self._stack_sides(pos_b)
+                        pos_b, side = pos_b.pin_memory(), "s,o"
+                    lv = self._fit_step_host_pipelined(pos_b, side, keep) if pipelined else self._fit_step_host(pos_b, side, keep)
+                    if lv is not None:
+                        if not np.isfinite(lv):  # models/EmbeddingModel.py:1422-1427
+                            raise ValueError("Loss is {}. Please change the hyperparameters.".format(lv))
+                        host_loss += lv
+                else:
+                    pos_b = Xd[lo:hi]
+                    if multi_side:
+                        pos_b, keep = self._stack_sides(pos_b)
+                        side = "s,o"
+                    self._fit_step_device(pos_b, side, keep)
+                    epoch_loss += f["loss_dev"].double()
                 if normalize:
                     if host_batches and pipelined:
                         lv = self._fit_host_flush()

@@ -84,7 +84,10 @@ typedef struct kge_train_args {
     const int32_t* pos;    /* [n_pos,3] device */
     int64_t  n_pos;
     const int32_t* repl;       /* optional [eta*n_pos] supplied replacement ids (parity input) */
-    const uint8_t* keep_subj;  /* optional [eta*n_pos] 1 = keep subject, replace object */
+    const uint8_t* keep_subj;  /* optional [eta*n_pos]: 1 = keep subject, replace object; 0 = the reverse; >= 2 =
+                                * decide by `side`.  May be given WITHOUT repl (in-kernel replacements, fixed
+                                * sides): a list-valued corrupt_side (models/EmbeddingModel.py:780-816) is run as
+                                * one batch holding the positives once per side, see DESIGN.md section 3.1 */
     float*   loss_out;     /* device float[1]: batch loss (overwritten) */
     float*   dbg_scores;   /* optional device [n_pos*(1+eta)]: positives then negatives (row j*n+i) */
     float*   dbg_grad_ent; /* optional device dense [E,K]: summed row gradients (must be zeroed) */

@@ -339,6 +339,77 @@ def train_step(model, k, loss, eta, ent, rel, pos, keep_subj, repl, margin=1.0, 
 
 
 # --------------------------------------------------------------------------------------------
+# the engine's own corruption stream (no reference counterpart: the reference draws from TF's RNG, whose stream
+# is a parity INPUT -- SURVEY 8a row a11).  Philox4x32-10 (Salmon et al., SC'11; Random123), keyed as
+# emgraph_b200/csrc/kge_train.cu:kge_emit_kernel keys it, so that throughput runs are checkable too.
+# --------------------------------------------------------------------------------------------
+def philox4x32_10(counter, key):
+    """counter [..., 4], key [..., 2] uint32 -> [..., 4] uint32."""
+    c = [np.asarray(counter)[..., i].astype(np.uint64) for i in range(4)]
+    k0 = np.asarray(key)[..., 0].astype(np.uint64)
+    k1 = np.asarray(key)[..., 1].astype(np.uint64)
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    for _ in range(10):
+        p0 = np.uint64(M0) * c[0]
+        p1 = np.uint64(M1) * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & np.uint64(MASK)
+        hi1, lo1 = p1 >> np.uint64(32), p1 & np.uint64(MASK)
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(W0)) & np.uint64(MASK)
+        k1 = (k1 + np.uint64(W1)) & np.uint64(MASK)
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def draw_corruptions(seed, step, n, eta, E, side="s,o", neg_index_base=0, neg_entities=None, neg_entities_n=0,
+                     keep_codes=None):
+    """(repl[eta*n] int32, keep_subj[eta*n] uint8) as the engine draws them for negative q = j*n + i:
+    counter = (g_lo, g_hi, step_lo, step_hi) with g = neg_index_base + q, key = (seed_lo, seed_hi);
+    replacement = mulhi(word0, #candidates) (uniform over [0,E), the first neg_entities_n ids, or the list
+    neg_entities, evaluation/protocol.py:610-641); side coin = top bit of word1 for 's,o' (:600-604), fixed for
+    's' / 'o' (:605-608); keep_codes[q] in {0,1} overrides the side of negative q (>= 2: by `side`)."""
+    q = np.arange(n * eta, dtype=np.uint64) + np.uint64(neg_index_base)
+    ctr = np.stack([q & np.uint64(0xFFFFFFFF), q >> np.uint64(32),
+                    np.full_like(q, int(step) & 0xFFFFFFFF), np.full_like(q, int(step) >> 32)], -1)
+    key = np.stack([np.full_like(q, int(seed) & 0xFFFFFFFF), np.full_like(q, int(seed) >> 32)], -1)
+    o = philox4x32_10(ctr, key).astype(np.uint64)
+    ncand = len(neg_entities) if neg_entities is not None else (int(neg_entities_n) if neg_entities_n else int(E))
+    repl = ((o[:, 0] * np.uint64(ncand)) >> np.uint64(32)).astype(np.int64)
+    if neg_entities is not None:
+        repl = np.asarray(neg_entities)[repl]
+    if side in ("s,o", "s+o"):
+        keep = (o[:, 1] >> np.uint64(31)).astype(np.uint8)
+    else:
+        keep = side_mask(side, n * eta)
+    if keep_codes is not None:
+        kc = np.asarray(keep_codes).astype(np.uint8)
+        keep = np.where(kc < 2, kc, keep).astype(np.uint8)
+    return repl.astype(np.int32), keep
+
+
+def stack_sides(pos, eta, sides, keep_subj_list, repl_list):
+    """A LIST-valued corrupt_side (models/EmbeddingModel.py:780-816) sums one loss term per side, each over its
+    own corruptions of the SAME positives, before the single optimizer step.  Every loss is a sum of
+    per-positive terms over that positive's eta negatives, so the summed loss equals the loss of ONE batch in
+    which the positives appear once per side: positives [pos ; pos ; ...] (n' = S*n) and negative row
+    j*n' + s*n + i = side s's negative (j, i).  Returns (pos', keep_subj', repl') in that layout."""
+    pos = np.asarray(pos).reshape(-1, 3)
+    n, S = pos.shape[0], len(sides)
+    keep = np.zeros((eta, S, n), np.uint8)
+    repl = np.zeros((eta, S, n), np.int32)
+    for s, side in enumerate(sides):
+        ks = np.asarray(keep_subj_list[s]) if side in ("s,o", "s+o") else side_mask(side, n * eta)
+        keep[:, s, :] = ks.reshape(eta, n)
+        repl[:, s, :] = np.asarray(repl_list[s]).reshape(eta, n)
+    return np.tile(pos, (S, 1)), keep.reshape(-1), repl.reshape(-1)
+
+
+def train_step_sides(model, k, loss, eta, ent, rel, pos, sides, keep_subj_list, repl_list, **kw):
+    """train_step for a list of corruption sides (one summed loss, one optimizer step)."""
+    pos2, keep2, repl2 = stack_sides(pos, eta, sides, keep_subj_list, repl_list)
+    return train_step(model, k, loss, eta, ent, rel, pos2, keep2, repl2, **kw)
+
+
+# --------------------------------------------------------------------------------------------
 # evaluation corruptions + filter sets + ranking
 # --------------------------------------------------------------------------------------------
 def corruptions_for_eval(x, entities, side="s,o"):

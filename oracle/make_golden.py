@@ -57,6 +57,16 @@ NL_CASES = [
 ]
 TRAIN_CASES = [c + (None,) for c in TRAIN_CASES] + REG_CASES + NL_CASES
 
+# a LIST-valued corrupt_side: one loss term per side, summed before the single step (models/EmbeddingModel.py:780-816)
+# name, model, loss, k, eta, E, R, n, sides, loss_params, emb_params, regularizer_params
+MULTISIDE_CASES = [
+    ("complex_nll_s_o", "ComplEx", "nll", 8, 4, 48, 4, 30, ["s", "o"], {}, {}, None),
+    ("distmult_multiclass_so_s", "DistMult", "multiclass_nll", 12, 5, 64, 5, 40, ["s,o", "s"], {}, {}, None),
+    ("transe_l1_pairwise_o_s_so", "TransE", "pairwise", 10, 3, 50, 3, 25, ["o", "s", "s+o"], {"margin": 2.0}, {}, None),
+    ("hole_selfadv_s_o_l2", "HolE", "self_adversarial", 8, 4, 48, 3, 30, ["s", "o"], {"margin": 1.0, "alpha": 0.5}, {},
+     {"p": 2, "lambda": 1e-2}),
+]
+
 RANK_CASES = [
     # name, model, k, E, R, F, T, emb_params, scale
     ("rank_transe_l1", "TransE", 10, 120, 4, 900, 60, {}, 0.5),
@@ -100,6 +110,34 @@ def main():
             loss=np.float32(ref["loss"]), scores_pos=ref["scores_pos"], scores_neg=ref["scores_neg"],
             neg=ref["neg"].astype(np.int32), grad_ent=ref["grad_ent"], grad_rel=ref["grad_rel"])
         print("train", name, "loss", ref["loss"])
+    for ci, (name, model, loss, k, eta, E, R, n, sides, lp, ep, rp) in enumerate(MULTISIDE_CASES):
+        if not wanted("train_multiside_" + name):
+            continue
+        rng = np.random.Generator(np.random.PCG64(3000 + ci))
+        K = ko.internal_k(model, k)
+        ent = (rng.normal(size=(E, K)) * 0.6).astype(np.float32)
+        rel = (rng.normal(size=(R, K)) * 0.6).astype(np.float32)
+        pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+        keeps = [ko.side_mask(sd, n * eta, rng) for sd in sides]
+        repls = [rng.integers(0, E, n * eta).astype(np.int32) for _ in sides]
+        ref = ref_shim.ref_train_forward_backward_sides(model, k, eta, loss, ent, rel, pos, sides, keeps, repls, lp, ep,
+                                                        "LP" if rp else None, rp)
+        # stored in the stacked layout the engine consumes (oracle/kge_oracle.py:stack_sides)
+        pos2, keep2, repl2 = ko.stack_sides(pos, eta, sides, keeps, repls)
+        S = len(sides)
+        sneg = np.stack([x.reshape(eta, n) for x in ref["scores_neg"]], 1).reshape(-1)
+        neg2 = np.stack([x.reshape(eta, n, 3) for x in ref["neg"]], 1).reshape(-1, 3)
+        lam = (rp or {}).get("lambda", 0.0)
+        lam = [lam, lam] if np.isscalar(lam) else list(lam)
+        np.savez_compressed(
+            os.path.join(OUT, "train_multiside_%s.npz" % name),
+            model=model, loss_name=loss, k=k, eta=eta, side="|".join(sides), n_sides=S,
+            margin=float(lp.get("margin", 3.0 if loss == "self_adversarial" else 1.0)), alpha=float(lp.get("alpha", 0.5)),
+            reg_p=int((rp or {}).get("p", 0)), reg_lambda_ent=float(lam[0]), reg_lambda_rel=float(lam[1]),
+            norm=int(ep.get("norm", 1)), nl=str(ep.get("non_linearity", "linear")), ent=ent, rel=rel, pos=pos2, pos_single=pos,
+            keep_subj=keep2, repl=repl2, loss=np.float32(ref["loss"]), scores_pos=np.tile(ref["scores_pos"], S), scores_neg=sneg,
+            neg=neg2.astype(np.int32), grad_ent=ref["grad_ent"], grad_rel=ref["grad_rel"])
+        print("train multiside", name, "loss", ref["loss"])
     for ci, (name, model, k, E, R, F, T, ep, scale) in enumerate(RANK_CASES):
         if not wanted(name):
             continue

@@ -257,6 +257,45 @@ def ref_train_forward_backward(name, k, eta, loss, ent, rel, pos, keep_subj, rep
                 grad_ent=model.ent_emb.grad.numpy().copy(), grad_rel=model.rel_emb.grad.numpy().copy())
 
 
+def ref_train_forward_backward_sides(name, k, eta, loss, ent, rel, pos, sides, keep_subj_list, repl_list,
+                                     loss_params=None, embedding_model_params=None, regularizer=None,
+                                     regularizer_params=None):
+    """A LIST-valued corrupt_side (models/EmbeddingModel.py:780-816): one loss term per side, each with its own
+    corruptions, summed into one loss before the single backward / optimizer step.  keep_subj_list[i] is only
+    consumed for 's,o' / 's+o' entries.  Returns the summed loss, the positives' scores, per-side negative
+    scores / triples and the dense row gradients of the sum."""
+    ns = load()
+    model = make_model(name, k, eta, loss, loss_params, embedding_model_params, regularizer, regularizer_params)
+    model.ent_emb = torch.tensor(ent, dtype=torch.float32, requires_grad=True)
+    model.rel_emb = torch.tensor(rel, dtype=torch.float32, requires_grad=True)
+    x_pos = torch.as_tensor(np.asarray(pos), dtype=torch.int32)
+    e_s, e_p, e_o = model._lookup_embeddings(x_pos)
+    scores_pos = _ref_non_linearity(ns, model, model._fn(e_s, e_p, e_o))
+    sp_out = scores_pos.detach().numpy().copy()
+    if model.loss.get_state("require_same_size_pos_neg"):
+        scores_pos = ns.tf.reshape(ns.tf.tile(scores_pos, [eta]), [ns.tf.shape(scores_pos)[0] * eta])
+    loss_t = 0
+    negs, sneg = [], []
+    for side, keep_subj, repl in zip(sides, keep_subj_list, repl_list):
+        RANDOM_FIFO.clear()
+        if side in ("s,o", "s+o"):
+            RANDOM_FIFO.append(np.asarray(keep_subj, np.int64))
+        RANDOM_FIFO.append(np.asarray(repl, np.int64))
+        x_neg = ns.protocol.generate_corruptions_for_fit(
+            x_pos, entities_list=None, eta=eta, corrupt_side=side, entities_size=ent.shape[0], rnd=0)
+        assert not RANDOM_FIFO
+        e_s, e_p, e_o = model._lookup_embeddings(x_neg)
+        scores_neg = _ref_non_linearity(ns, model, model._fn(e_s, e_p, e_o))
+        loss_t = loss_t + model.loss.apply(scores_pos, scores_neg)
+        negs.append(x_neg.numpy().copy())
+        sneg.append(scores_neg.detach().numpy().copy())
+    if model.regularizer is not None:  # models/EmbeddingModel.py:818-820 (once, after the side loop)
+        loss_t = loss_t + model.regularizer.apply([model.ent_emb, model.rel_emb])
+    loss_t.backward()
+    return dict(loss=float(loss_t.detach()), scores_pos=sp_out, scores_neg=sneg, neg=negs,
+                grad_ent=model.ent_emb.grad.numpy().copy(), grad_rel=model.rel_emb.grad.numpy().copy())
+
+
 def ref_ranks(name, k, ent, rel, test, filter_triples=None, side="s,o", strategy="worst",
               embedding_model_params=None):
     """Per test triple: the body of _initialize_eval_graph small-graph branch
