@@ -696,10 +696,13 @@ def bench_rank(args, w, eng, model, f, X, test, peaks):
     mrr = float(np.mean(1.0 / r_host.reshape(-1)))
     flops = 4.0 * E * K * T  # 2 sides x E candidates x K MACs x 2
     if w["model"] == "TransE":
-        # fp32 CUDA-core sweep: 3 element-ops per (query, candidate, dim); report against HBM min traffic as well
-        ach = 3.0 * 2 * E * K * T / (t_sweep_ms * 1e-3) / 1e12
-        peak = 148 * 128 * 2 * 1.965e9 / 1e12  # fp32 FMA peak at max clock (2 flop/FMA)
-        roof = {"bound": "fp32-alu", "achieved": ach, "peak": peak, "unit": "Tops/s (sub,abs,add)", "frac": ach / peak, "traffic": None}
+        # fp32 CUDA-core sweep: per (query, candidate, column) two ALU instructions -- FADD d = q - e, then FADD
+        # acc += |d| (the abs is a source modifier; checked in SASS) -- against the fp32 pipe's issue rate of
+        # 128 lanes per SM per clock (the FMA peak counts 2 flop per lane-slot; an add fills a slot all the same)
+        ach = 2.0 * 2 * E * K * T / (t_sweep_ms * 1e-3) / 1e12
+        peak = 148 * 128 * 1.965e9 / 1e12
+        roof = {"bound": "fp32-alu", "achieved": ach, "peak": peak, "unit": "T lane-instr/s (FADD sub + FADD |.| accumulate per element)",
+                "frac": ach / peak, "traffic": None, "peak_source": "148 SMs x 128 fp32 lanes x 1.965 GHz (max SM clock)"}
     elif use_tc:
         # 3xTF32: three tensor-core MMAs per logical MAC; TF32 dense peak = 1/2 of the measured bf16 peak
         peak = peaks["bf16"] / 2.0
@@ -710,7 +713,8 @@ def bench_rank(args, w, eng, model, f, X, test, peaks):
         peak = 148 * 128 * 2 * 1.965e9 / 1e12
         ach = flops / (t_sweep_ms * 1e-3) / 1e12
         roof = {"bound": "fp32-alu", "achieved": ach, "peak": peak, "unit": "TFLOP/s fp32 FMA", "frac": ach / peak, "traffic": None}
-    roof["kernel"] = "kge_rank_sweep_tc" if use_tc else "kge_rank_sweep_kernel"
+    v1 = os.environ.get("KGE_SWEEP_V1", "0")[:1] == "1"
+    roof["kernel"] = "kge_rank_sweep_tc" if use_tc else ("kge_rank_sweep2_kernel" if w["model"] == "TransE" and not v1 else "kge_rank_sweep_kernel")
     roof["kernel_ms"] = t_sweep_ms
     return {"metric": RANK_METRIC, "value": value, "unit": "test triples/s", "ms_per_step": t_ms, "steps": n, "T": T,
             "corrupt_side": "s,o", "filter_triples": int(X.shape[0]), "filter_build_ms": 1e3 * t_filter, "tensor_cores": bool(use_tc),

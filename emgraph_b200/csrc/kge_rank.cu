@@ -391,6 +391,266 @@ __global__ void __launch_bounds__(256) kge_rank_sweep_kernel(SweepParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// TransE distance sweep, second generation (MODE 1: L1, MODE 2: L2).  The bound is the fp32 ALU pipe --
+// two FADDs per (query, entity, column) for L1 (subtract, then add with the |x| source modifier), FADD +
+// FFMA for L2 -- so everything else is kept off the issue slots:
+//   * 128 x 64 CTA tile, 8 x 4 outputs per thread: 3 LDS.128 feed 64 ALU instructions per column
+//     (the 64 x 64 / 4 x 4 kernel above: 2 per 32);
+//   * two shared-memory stages, the next k-tile's global loads are issued before the current tile's
+//     arithmetic and stored after it: ONE __syncthreads per k-tile instead of two, no exposed load latency;
+//   * the last k-tile runs K - k0 columns instead of a zero-padded 16 (K = 100: 100 instead of 112);
+//   * the filter mask of an entity tile is double-buffered by tile parity, so its rebuild needs no barrier.
+//   * the epilogue compares in the float domain: trunc(y) >= n and trunc(y) > n (y = score * 1e5, n the
+//     positive's quantised score) are each ONE float comparison against a per-row threshold computed once per
+//     CTA (kge_quant_thresholds), so no F2I and no 64-bit index compares sit between two tiles' FADD streams;
+//     the candidate that is the test triple itself and filter hits are patched in on a rare path.
+// The columns of a score are accumulated in ascending order by one accumulator, exactly as above: both
+// kernels produce bit-identical scores, hence identical counts (NaN scores excepted: F2I maps NaN to 0, a
+// float comparison to "not counted").
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float f32_at_least(long long m, bool strictly) {
+    // smallest fp32 value >= m (strictly: > m); m is exact in double
+    float f = __ll2float_rn(m);
+    if (strictly ? (double)f <= (double)m : (double)f < (double)m) f = nextafterf(f, INFINITY);
+    return f;
+}
+// With q(y) = trunc_toward_zero(y) (saturating F2I) and n = the positive's quantised score:
+//   q(y) >= n  <=>  y >= t_ge,   q(y) > n  <=>  y >= t_gt      (models/EmbeddingModel.py:2010-2029)
+// because trunc(y) >= m <=> y >= m for an integer m > 0 and <=> y > m - 1 for m <= 0.
+__device__ __forceinline__ void kge_quant_thresholds(int32_t n, float& t_ge, float& t_gt) {
+    const long long m0 = n, m1 = (long long)n + 1;
+    t_ge = m0 > 0 ? f32_at_least(m0, false) : f32_at_least(m0 - 1, true);
+    // nothing is greater than a saturated positive: NaN compares false against everything
+    t_gt = n == INT32_MAX ? __int_as_float(0x7fc00000) : (m1 > 0 ? f32_at_least(m1, false) : f32_at_least(m1 - 1, true));
+}
+
+#define S2_BM 128
+#define S2_BN 64
+#define S2_BK 16
+
+// LINEAR: no score non-linearity (the common case) -- keeps tanhf/expf/logf out of the instruction stream
+template <int MODE, bool LINEAR>
+__global__ void __launch_bounds__(256, 2) kge_rank_sweep2_kernel(SweepParams P) {
+    __shared__ __align__(16) float Qs[2][S2_BK][S2_BM + 4];
+    __shared__ __align__(16) float Es[2][S2_BK][S2_BN + 4];
+    __shared__ unsigned long long s_mask[2][S2_BM];
+    __shared__ int32_t s_cur[S2_BM], s_hi[S2_BM], s_self[S2_BM];
+    __shared__ float s_tge[S2_BM], s_tgt[S2_BM];
+    __shared__ const int32_t* s_list[S2_BM];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = P.q_row0 + (int64_t)blockIdx.x * S2_BM;
+    const int64_t m_end = P.q_row0 + P.q_rows;
+    const int64_t e0 = P.row_begin + (int64_t)blockIdx.y * P.chunk;
+    const int64_t e1 = min(P.row_end, e0 + P.chunk);
+    if (e0 >= e1) return;
+    const int K = P.K;
+    const bool vec_ok = (K & 3) == 0;
+    const int ktiles = (K + S2_BK - 1) / S2_BK;
+
+    if (tid < S2_BM) {
+        const int64_t r = m0 + tid;
+        int32_t cur = 0, hi = 0, self = -1;
+        float tge = __int_as_float(0x7fc00000), tgt = tge;  // rows past the end never count (NaN compares false)
+        const int32_t* list = nullptr;
+        if (r < m_end) {
+            const int side = r >= P.T ? 1 : 0;
+            const int64_t t = r - (int64_t)side * P.T;
+            self = side == 0 ? P.test[3 * t + 2] : P.test[3 * t + 0];
+            kge_quant_thresholds(P.pos_q[t], tge, tgt);
+            list = side == 0 ? P.sp_ent : P.po_ent;
+            int32_t a = P.excl_lo[r], b = P.excl_hi[r];
+            hi = b;
+            while (a < b) {  // first filter entry >= e0
+                const int32_t mid = (a + b) >> 1;
+                if ((int64_t)list[mid] < e0) a = mid + 1;
+                else b = mid;
+            }
+            cur = a;
+        }
+        s_cur[tid] = cur;
+        s_hi[tid] = hi;
+        s_self[tid] = self;
+        s_tge[tid] = tge;
+        s_tgt[tid] = tgt;
+        s_list[tid] = list;
+    }
+    int cnt[8][4];  // per query row: {gt, ge, gt & filtered, ge & filtered}; eq = ge - gt at the end
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cnt[i][c] = 0;
+
+    // loader mapping: 256 threads x float4: rows lr and lr + 64 of the query tile, row lr of the entity tile
+    const int lr = tid >> 2, lc = (tid & 3) * 4;
+    const float* qrow0 = P.q + (size_t)min(m0 + lr, m_end - 1) * K;       // clamped: rows past the end are
+    const float* qrow1 = P.q + (size_t)min(m0 + lr + 64, m_end - 1) * K;  // computed and never counted
+
+    auto load4 = [&](float (&v)[4], const float* row, int k0) {
+        const int c = k0 + lc;
+        if (vec_ok && c + 3 < K) {
+            const float4 t4 = *reinterpret_cast<const float4*>(row + c);
+            v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+        } else {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) v[x] = c + x < K ? row[c + x] : 0.f;
+        }
+    };
+
+    int par = 0;
+    for (int64_t n0 = e0; n0 < e1; n0 += S2_BN, par ^= 1) {
+        if (tid < S2_BM) {
+            unsigned long long mk = 0ull;
+            int32_t cur = s_cur[tid];
+            const int32_t hi = s_hi[tid];
+            const int32_t* list = s_list[tid];
+            while (cur < hi) {
+                const int64_t e = list[cur];
+                if (e >= n0 + S2_BN) break;
+                mk |= 1ull << (int)(e - n0);
+                ++cur;
+            }
+            s_cur[tid] = cur;
+            s_mask[par][tid] = mk;
+        }
+        const float* erow = P.ent_local + (size_t)(min(n0 + lr, e1 - 1) - P.row_begin) * K;
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+        float q0[4], q1[4], ev[4];
+        load4(q0, qrow0, 0);
+        load4(q1, qrow1, 0);
+        load4(ev, erow, 0);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            Qs[0][lc + x][lr] = q0[x];
+            Qs[0][lc + x][lr + 64] = q1[x];
+            Es[0][lc + x][lr] = ev[x];
+        }
+        __syncthreads();
+        for (int kt = 0; kt < ktiles; ++kt) {
+            const int cur = kt & 1;
+            const bool more = kt + 1 < ktiles;
+            if (more) {
+                load4(q0, qrow0, (kt + 1) * S2_BK);
+                load4(q1, qrow1, (kt + 1) * S2_BK);
+                load4(ev, erow, (kt + 1) * S2_BK);
+            }
+            auto column = [&](int kk) {
+                const float4 a0 = *reinterpret_cast<const float4*>(&Qs[cur][kk][ty * 8]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&Qs[cur][kk][ty * 8 + 4]);
+                const float4 b4 = *reinterpret_cast<const float4*>(&Es[cur][kk][tx * 4]);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float d = a[i] - b[j];
+                        if (MODE == 1) acc[i][j] += fabsf(d);
+                        else acc[i][j] = fmaf(d, d, acc[i][j]);
+                    }
+            };
+            const int kend = min(S2_BK, K - kt * S2_BK);
+            if (kend == S2_BK) {
+#pragma unroll
+                for (int kk = 0; kk < S2_BK; ++kk) column(kk);
+            } else {
+                for (int kk = 0; kk < kend; ++kk) column(kk);
+            }
+            if (more) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    Qs[cur ^ 1][lc + x][lr] = q0[x];
+                    Qs[cur ^ 1][lc + x][lr + 64] = q1[x];
+                    Es[cur ^ 1][lc + x][lr] = ev[x];
+                }
+            }
+            __syncthreads();
+        }
+        // compare against the per-row thresholds, count.  lim = this thread's columns inside [n0, e1)
+        const int lim = (int)min((int64_t)4, e1 - n0 - tx * 4);
+        const int col0 = (int)(n0 - P.row_begin) + tx * 4;  // local index of this thread's first candidate
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rl = ty * 8 + i;
+            const float tge = s_tge[rl], tgt = s_tgt[rl];
+            bool g[4], h[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float sc = MODE == 1 ? -acc[i][j] : -sqrtf(acc[i][j]);
+                const float y = __fmul_rn(LINEAR ? sc : apply_nl(P.nl, sc), 1e5f);
+                g[j] = y >= tgt;
+                h[j] = y >= tge;
+            }
+            if (lim < 4) {  // last tile of the range (block-uniform per tx; rare)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    g[j] = g[j] && j < lim;
+                    h[j] = h[j] && j < lim;
+                }
+            }
+            cnt[i][0] += (int)g[0] + (int)g[1] + (int)g[2] + (int)g[3];
+            cnt[i][1] += (int)h[0] + (int)h[1] + (int)h[2] + (int)h[3];
+            // rare: the test triple's own entity is one of these candidates (never counted), or filter hits
+            const int selfrel = s_self[rl] - (int)P.row_begin - col0;
+            const unsigned fm = (unsigned)(s_mask[par][rl] >> (tx * 4)) & 0xfu;
+            if ((unsigned)selfrel < 4u || fm != 0u) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j == selfrel) {
+                        cnt[i][0] -= (int)g[j];
+                        cnt[i][1] -= (int)h[j];
+                    } else if ((fm >> j) & 1u) {
+                        cnt[i][2] += (int)g[j];
+                        cnt[i][3] += (int)h[j];
+                    }
+                }
+            }
+        }
+    }
+    // reduce over the 16 threads (tx) that share a query row, then one atomic per (row, counter)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int v = cnt[i][c];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            cnt[i][c] = v;
+        }
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t r = m0 + ty * 8 + i;
+            if (r < m_end) {
+                const int side = r >= P.T ? 1 : 0;
+                const int64_t t = r - (int64_t)side * P.T;
+                // counts layout: {gt, eq, gt_filtered, eq_filtered}
+                const int out[4] = {cnt[i][0], cnt[i][1] - cnt[i][0], cnt[i][2], cnt[i][3] - cnt[i][2]};
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (out[c]) atomicAdd(&P.counts[(t * 2 + side) * 4 + c], out[c]);
+            }
+        }
+    }
+}
+
+// KGE_SWEEP_V1=1 selects the first-generation 64 x 64 kernel for TransE as well (A/B)
+static inline bool sweep_v1_forced() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KGE_SWEEP_V1");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // rank assembly (models/EmbeddingModel.py:1966-1986 with perform_comparision :1989-2033)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int cmp_count(int gt, int eq, int strategy) {
@@ -505,8 +765,30 @@ extern "C" int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* 
     sp.q_rows = q_rows;
     sp.counts = counts;
     sp.nl = non_linearity;
-    int64_t row_tiles = (q_rows + SW_BM - 1) / SW_BM;
     int64_t n_ent = row_end - row_begin;
+    if (!trilinear && !sweep_v1_forced()) {
+        const int64_t row_tiles2 = (q_rows + S2_BM - 1) / S2_BM;
+        // two 256-thread CTAs per SM; ~16 waves of CTAs so that the last, partly filled wave costs a few percent
+        // (4 waves left the SMs idle 10 % of the kernel, ncu r01_t); entity chunks a multiple of the tile
+        int64_t want = std::max<int64_t>(1, ((int64_t)ctx->sm_count * 32 + row_tiles2 - 1) / row_tiles2);
+        int64_t chunk2 = (n_ent + want - 1) / want;
+        chunk2 = std::max<int64_t>(S2_BN * 4, ((chunk2 + S2_BN - 1) / S2_BN) * S2_BN);
+        const int64_t n_chunks2 = (n_ent + chunk2 - 1) / chunk2;
+        KGE_REQUIRE(n_chunks2 <= 65535, "kge_rank_counts: too many entity chunks");
+        sp.chunk = chunk2;
+        dim3 grid2((unsigned)row_tiles2, (unsigned)n_chunks2), block2(256);
+        const bool lin = non_linearity == KGE_NL_LINEAR;
+        if (model == KGE_TRANSE_L1) {
+            if (lin) kge_rank_sweep2_kernel<1, true><<<grid2, block2, 0, st>>>(sp);
+            else kge_rank_sweep2_kernel<1, false><<<grid2, block2, 0, st>>>(sp);
+        } else {
+            if (lin) kge_rank_sweep2_kernel<2, true><<<grid2, block2, 0, st>>>(sp);
+            else kge_rank_sweep2_kernel<2, false><<<grid2, block2, 0, st>>>(sp);
+        }
+        KGE_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
+    int64_t row_tiles = (q_rows + SW_BM - 1) / SW_BM;
     // enough CTAs for >= 4 waves, entity chunks a multiple of the tile
     int64_t want_chunks = std::max<int64_t>(1, ((int64_t)ctx->sm_count * 8 + row_tiles - 1) / row_tiles);
     int64_t chunk = (n_ent + want_chunks - 1) / want_chunks;

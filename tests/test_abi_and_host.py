@@ -216,3 +216,48 @@ def test_sgd_schedule_reference_goldens():
             seen[(e, b)] = s(b, e)
     assert seen[(11, 1)] == 0.0005 and seen[(6, 1)] == 0.000505 and seen[(21, 1)] == 0.000255
     assert s(1, 31) == 0.00025
+
+
+def test_quantised_comparison_thresholds_mirror():
+    """Host mirror of csrc/kge_rank.cu:kge_quant_thresholds -- the TransE sweep compares y = score*1e5 against
+    two fp32 thresholds instead of quantising every candidate: trunc(y) >= n <=> y >= t_ge and
+    trunc(y) > n <=> y >= t_gt must hold for every fp32 y (reference models/EmbeddingModel.py:2010-2029)."""
+    INF = np.float32(np.inf)
+
+    def at_least(m, strictly):
+        f = np.float32(m)  # round to nearest, like __ll2float_rn
+        if (float(f) <= m) if strictly else (float(f) < m):
+            f = np.nextafter(f, INF)
+        return f
+
+    def thresholds(n):
+        m0, m1 = n, n + 1
+        t_ge = at_least(m0, False) if m0 > 0 else at_least(m0 - 1, True)
+        t_gt = np.float32(np.nan) if n == 2**31 - 1 else (at_least(m1, False) if m1 > 0 else at_least(m1 - 1, True))  # NaN: never
+        return t_ge, t_gt
+
+    def trunc_sat(y):  # F2I.TRUNC saturates
+        if not np.isfinite(y):
+            return 2**31 - 1 if y > 0 else -2**31
+        return int(max(-2**31, min(2**31 - 1, int(np.trunc(np.float64(y))))))
+
+    rng = np.random.default_rng(0)
+    ns = [0, 1, -1, 2, -2, 7, -7, 2**24 - 1, 2**24, 2**24 + 1, 2**24 + 3, -2**24 - 1, -2**24 - 3, 33554433, -33554435,
+          2**31 - 1, 2**31 - 2, 2**31 - 200, -2**31 + 1, -2**31 + 300] + [int(v) for v in rng.integers(-2**31 + 2, 2**31 - 2, 40)] \
+        + [int(v) for v in rng.integers(-3000000, 3000000, 40)]
+    for n in ns:
+        t_ge, t_gt = thresholds(n)
+        ys = []
+        for c in (n - 2, n - 1, n, n + 1, n + 2):
+            y = np.float32(c)
+            lo = hi = y
+            for _ in range(6):  # the fp32 neighbourhood of every nearby integer
+                lo, hi = np.nextafter(lo, -INF), np.nextafter(hi, INF)
+                ys += [lo, hi]
+            ys.append(y)
+        ys += list(rng.normal(scale=max(4.0, abs(n) * 1e-3), size=50).astype(np.float32) + np.float32(n))
+        ys += [np.float32(0.0), np.float32(-0.0), np.float32(0.5), np.float32(-0.5), np.float32(-0.99999994), np.float32(3e9), INF]
+        for y in ys:
+            q = trunc_sat(y)
+            assert (q >= n) == bool(y >= t_ge), (n, float(y), q, float(t_ge))
+            assert (q > n) == bool(y >= t_gt), (n, float(y), q, float(t_gt))
