@@ -52,6 +52,12 @@ extern "C" int kge_ctx_destroy(kge_ctx* c) {
     for (int i = 0; i < 4; ++i)
         if (c->ev_host[i]) cudaEventDestroy(c->ev_host[i]);
     if (c->gmain) cudaStreamDestroy(c->gmain);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_posfree[i]) cudaEventDestroy(c->ev_posfree[i]);
+        c->h_pos2[i].release();
+    }
+    if (c->cstream) cudaStreamDestroy(c->cstream);
     c->d_dyn.release();
     for (KgeGraphEntry& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -69,7 +75,7 @@ extern "C" int64_t kge_ctx_workspace_bytes(kge_ctx* c) {
                       &c->grad_rows, &c->loss_part, &c->neg_scores, &c->partial, &c->span_head, &c->ks_in, &c->ks_sel, &c->ks_sorted, &c->sel_flags, &c->sel_count, &c->h_pos, &c->h_loss, &c->h_test, &c->h_counts, &c->h_ranks, &c->q_fold, &c->q_hi, &c->q_lo, &c->e_hi, &c->e_lo,
                       &c->pos_q, &c->excl_lo, &c->excl_hi, &c->f_sp_comp, &c->f_po_comp, &c->f_sp_ent, &c->f_po_ent,
                       &c->f_tmp, &c->f_tmp2, &c->f_count};
-    int64_t tot = 0;
+    int64_t tot = (int64_t)c->h_pos2[0].cap + (int64_t)c->h_pos2[1].cap;
     for (KgeBuf* b : bufs) tot += (int64_t)b->cap;
     return tot;
 }

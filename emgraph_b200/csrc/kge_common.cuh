@@ -37,7 +37,7 @@ struct KgeStepDyn {
     float    pad;
 };
 
-#define KGE_GRAPH_SLOTS 4
+#define KGE_GRAPH_SLOTS 8  // {full batch, last batch} x two batch buffers, with room to spare
 struct KgeGraphEntry {
     kge_train_args  key;       // args with step = 0
     cudaStream_t    stream = nullptr;
@@ -106,6 +106,11 @@ struct kge_ctx {
     // memcpy node refreshes from pinned host memory, so one instantiated graph serves every step
     cudaStream_t gmain = nullptr;  // capture-able stream the graphed host step runs on
     cudaEvent_t  ev_gin = nullptr;
+    // the batch of host step t+1 is copied in on its own stream while step t runs: two device batch buffers,
+    // ev_h2d[i] = copy into buffer i done, ev_posfree[i] = the step that read buffer i last has finished
+    cudaStream_t cstream = nullptr;
+    KgeBuf       h_pos2[2];
+    cudaEvent_t  ev_h2d[2] = {nullptr, nullptr}, ev_posfree[2] = {nullptr, nullptr};
     KgeStepDyn* h_dyn = nullptr;  // pinned ring of KGE_HOST_RING blocks (one per in-flight host step)
     cudaEvent_t  ev_host[4] = {nullptr, nullptr, nullptr, nullptr};  // end of the host step that used ring slot i
     uint64_t     host_tick = 0;   // host steps submitted so far

@@ -1516,24 +1516,43 @@ extern "C" int kge_train_step_host_async(kge_ctx* ctx, const kge_train_args* a, 
         ctx->host_tick += 1;
         return 0;
     }
-    if (ctx->h_pos.reserve((size_t)a->n_pos * 3 * sizeof(int32_t)) || ctx->h_loss.reserve(sizeof(float))) return -2;
+    if (ctx->h_loss.reserve(sizeof(float))) return -2;
     const bool graphed = train_graph_enabled() && !ctx->timing && a->ent.n_shards == 1;
+    const size_t pos_bytes = (size_t)a->n_pos * 3 * sizeof(int32_t);
+    kge_train_args b = *a;
+    int pb = -1;  // batch buffer of this step (graphed path)
     if (graphed) {
         // the caller's stream may be the legacy default stream, which cannot be captured: the whole call
         // runs on a stream of the ctx, ordered behind the caller's stream (kge_train_host_wait joins it)
         if (ctx->gmain == nullptr) {
             KGE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->gmain, cudaStreamNonBlocking));
             KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_gin, cudaEventDisableTiming));
+            KGE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+                KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_posfree[i], cudaEventDisableTiming));
+            }
         }
         KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_gin, st));
         KGE_CUDA_CHECK(cudaStreamWaitEvent(ctx->gmain, ctx->ev_gin, 0));
         st = ctx->gmain;
+        // H2D of the batch on the copy stream, into the buffer the step before the previous one used: it
+        // overlaps the previous step instead of sitting between two graph launches
+        pb = (int)(ctx->host_tick & 1);
+        if (ctx->h_pos2[pb].reserve(pos_bytes)) return -2;
+        KGE_CUDA_CHECK(cudaStreamWaitEvent(ctx->cstream, ctx->ev_posfree[pb], 0));  // no-op until first recorded
+        KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pos2[pb].p, pos_host, pos_bytes, cudaMemcpyHostToDevice, ctx->cstream));
+        KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_h2d[pb], ctx->cstream));
+        KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_h2d[pb], 0));
+        b.pos = ctx->h_pos2[pb].as<int32_t>();
+    } else {
+        if (ctx->h_pos.reserve(pos_bytes)) return -2;
+        KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pos.p, pos_host, pos_bytes, cudaMemcpyHostToDevice, st));
+        b.pos = ctx->h_pos.as<int32_t>();
     }
-    KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pos.p, pos_host, (size_t)a->n_pos * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    kge_train_args b = *a;
-    b.pos = ctx->h_pos.as<int32_t>();
     if (b.loss_out == nullptr) b.loss_out = ctx->h_loss.as<float>();
     if (int rc = graphed ? train_step_graphed(ctx, &b, st) : train_step_body(ctx, &b, st, nullptr)) return rc;
+    if (pb >= 0) KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_posfree[pb], st));
     if (loss_host) KGE_CUDA_CHECK(cudaMemcpyAsync(loss_host, b.loss_out, sizeof(float), cudaMemcpyDeviceToHost, st));
     KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_host[slot], st));
     ctx->host_tick += 1;
