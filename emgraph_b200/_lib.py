@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkge_b200.so")
 
 KGE_MAX_SHARDS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 MODEL_IDS = {"TransE": 0, "TransE_L2": 1, "DistMult": 2, "ComplEx": 3, "HolE": 4}
 LOSS_IDS = {"pairwise": 0, "nll": 1, "multiclass_nll": 2, "absolute_margin": 3, "self_adversarial": 4}
@@ -20,6 +20,7 @@ STRATEGY_IDS = {"worst": 0, "best": 1, "middle": 2}
 NL_IDS = {"linear": 0, "tanh": 1, "sigmoid": 2, "softplus": 3}
 F_RESET_STATE = 1
 F_NO_UPDATE = 2
+F_PIPELINE = 4
 
 
 class KgeTable(C.Structure):

@@ -58,6 +58,10 @@ extern "C" int kge_ctx_destroy(kge_ctx* c) {
         c->h_pos2[i].release();
     }
     if (c->cstream) cudaStreamDestroy(c->cstream);
+    for (int i = 0; i < 2; ++i)
+        for (cudaEvent_t e : {c->ev_set_free[i], c->ev_pro_emit[i], c->ev_pro_sorted[i]})
+            if (e) cudaEventDestroy(e);
+    for (KgeBuf* b : {&c->alt_repl, &c->alt_keep, &c->alt_ks_in, &c->alt_ks_sorted}) b->release();
     c->d_dyn.release();
     for (KgeGraphEntry& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -76,6 +80,7 @@ extern "C" int64_t kge_ctx_workspace_bytes(kge_ctx* c) {
                       &c->pos_q, &c->excl_lo, &c->excl_hi, &c->f_sp_comp, &c->f_po_comp, &c->f_sp_ent, &c->f_po_ent,
                       &c->f_tmp, &c->f_tmp2, &c->f_count};
     int64_t tot = (int64_t)c->h_pos2[0].cap + (int64_t)c->h_pos2[1].cap;
+    for (KgeBuf* b : {&c->alt_repl, &c->alt_keep, &c->alt_ks_in, &c->alt_ks_sorted}) tot += (int64_t)b->cap;
     for (KgeBuf* b : bufs) tot += (int64_t)b->cap;
     return tot;
 }

@@ -44,6 +44,7 @@ struct KgeGraphEntry {
     cudaGraphExec_t exec = nullptr;
     int             seen = 0;  // calls with this key so far (the first runs eagerly: allocations, attributes)
     uint64_t        ws_epoch = 0;  // g_kge_ws_epoch at capture
+    int             variant = 0;   // 0: whole step captured; 1 + set: pipelined main part reading buffer set `set`
     uint64_t        last_use = 0;
 };
 
@@ -84,6 +85,13 @@ struct kge_ctx {
     KgeBuf sort_tmp;
     KgeBuf repl, keep, grad_rows, loss_part, neg_scores, partial, span_head, reg_partial, touched;
     KgeBuf ks_in, ks_sel, ks_sorted, sel_flags, sel_count;
+    // second set of the per-step corruption / sort-key buffers {repl, keep, ks_in, ks_sorted}: a pipelined step
+    // (KGE_F_PIPELINE) swaps the sets and runs emit + sort on the side stream, beside the previous step.
+    // set_id names the physical set the four members above hold right now; ev_set_free[i] = the last step that
+    // read set i has finished (recorded by every single-GPU step), ev_pro[i] = emit + sort into set i done
+    KgeBuf alt_repl, alt_keep, alt_ks_in, alt_ks_sorted;
+    int    set_id = 0;
+    cudaEvent_t ev_set_free[2] = {nullptr, nullptr}, ev_pro_emit[2] = {nullptr, nullptr}, ev_pro_sorted[2] = {nullptr, nullptr};
     // owner-side slot selection (kge_train_select): count travels to the host behind an event
     // side stream of the single-GPU step (sort + loss reduction beside the forward/backward kernel)
     cudaStream_t  side = nullptr;

@@ -1277,6 +1277,11 @@ static int ensure_side_stream(kge_ctx* ctx) {
     KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming));
     KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fwd, cudaEventDisableTiming));
     KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_loss, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_set_free[i], cudaEventDisableTiming));
+        KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_pro_emit[i], cudaEventDisableTiming));
+        KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_pro_sorted[i], cudaEventDisableTiming));
+    }
     return 0;
 }
 
@@ -1420,8 +1425,89 @@ static int train_step_body(kge_ctx* ctx, const kge_train_args* a, void* stream, 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Software-pipelined step (KGE_F_PIPELINE).  emit (corruptions + sort keys) and the radix sort read the batch
+// and the (seed, step) counters only, so the step is cut in two:
+//   prologue : emit + sort on the side stream into the buffer set {repl, keep, ks_in, ks_sorted} that the step
+//              before the previous one used (the two sets alternate); it waits for that step's end
+//              (ev_set_free) and, for host batches, for the batch copy -- not for the previous step
+//   main     : forward/backward, loss, segmented reduction + optimizer on the caller's stream, behind the
+//              previous step as always, and behind the prologue's two events
+// Submitting step t+1 while step t runs (any asynchronous caller does) therefore overlaps prologue(t+1) with
+// main(t): emit and the sort leave the critical path.  Same kernels, same inputs, same order of every
+// floating-point sum => bit-identical to the in-order step.  KGE_PIPELINE=0 forces the in-order step (A/B).
+// ------------------------------------------------------------------------------------------------
+static inline bool pipeline_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KGE_PIPELINE");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+static inline bool step_is_pipelined(const kge_ctx* ctx, const kge_train_args* a) {
+    return (a->flags & KGE_F_PIPELINE) != 0 && !ctx->timing && a->ent.n_shards == 1 && a->n_pos > 0 && pipeline_enabled();
+}
+
+// every single-GPU step: the buffer set it read is free again once `st` gets here
+static int mark_set_free(kge_ctx* ctx, cudaStream_t st) {
+    KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_set_free[ctx->set_id], st));
+    return 0;
+}
+
+static int pipeline_prologue(kge_ctx* ctx, const kge_train_args* a, cudaEvent_t batch_ready) {
+    if (int rc = validate_train(a)) return rc;
+    KGE_REQUIRE(a->ent.n_shards == 1, "kge_train_step is the single-GPU entry; use the phased calls when sharded");
+    if (int rc = ensure_side_stream(ctx)) return rc;
+    std::swap(ctx->repl, ctx->alt_repl);
+    std::swap(ctx->keep, ctx->alt_keep);
+    std::swap(ctx->ks_in, ctx->alt_ks_in);
+    std::swap(ctx->ks_sorted, ctx->alt_ks_sorted);
+    ctx->set_id ^= 1;
+    const int sid = ctx->set_id;
+    const int64_t S = (int64_t)(3 + a->eta) * a->n_pos;
+    if (ctx->ks_in.reserve((size_t)S * 8)) return -2;
+    if (ctx->grad_rows.reserve((size_t)gbuf_floats(a->eta, a->n_pos, a->ent.K) * sizeof(float))) return -2;
+    if (batch_ready != nullptr) KGE_CUDA_CHECK(cudaStreamWaitEvent(ctx->side, batch_ready, 0));
+    KGE_CUDA_CHECK(cudaStreamWaitEvent(ctx->side, ctx->ev_set_free[sid], 0));  // no-op until first recorded
+    if (int rc = emit_impl(ctx, a, nullptr, ctx->ks_in.as<uint64_t>(), ctx->side, nullptr)) return rc;
+    KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_pro_emit[sid], ctx->side));
+    if (int rc = sort_impl(ctx, a, ctx->ks_in.as<uint64_t>(), S, ctx->side)) return rc;
+    KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_pro_sorted[sid], ctx->side));
+    return 0;
+}
+
+// wait_inside: enqueue the waits for the prologue here (eager step); false when this is captured into a graph
+// (the caller then waits on the launching stream, outside the graph)
+static int pipeline_main(kge_ctx* ctx, const kge_train_args* a, cudaStream_t st, const KgeStepDyn* dyn, bool wait_inside) {
+    const int sid = ctx->set_id;
+    const int K = a->ent.K;
+    const int64_t S = (int64_t)(3 + a->eta) * a->n_pos;
+    if (wait_inside) KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_pro_emit[sid], 0));
+    if (int rc = fwd_bwd_impl(ctx, a, ctx->grad_rows.as<float>(), st, ctx->side)) return rc;
+    kge_table g;
+    memset(&g, 0, sizeof(g));
+    g.shard[0] = ctx->grad_rows.as<float>();
+    g.rows = S;
+    g.rows_per_shard = S;
+    g.n_shards = 1;
+    g.K = K;
+    if (wait_inside) KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_pro_sorted[sid], 0));
+    if (int rc = reduce_impl(ctx, a, S, &g, 0, a->ent.rows, st, dyn)) return rc;
+    KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_loss, 0));  // join
+    return reg_loss_finish(ctx, a, st);
+}
+
 extern "C" int kge_train_step(kge_ctx* ctx, const kge_train_args* a, void* stream) {
-    return train_step_body(ctx, a, stream, nullptr);
+    KGE_REQUIRE(ctx != nullptr && a != nullptr, "kge_train_step: null argument");
+    if (step_is_pipelined(ctx, a)) {
+        if (int rc = pipeline_prologue(ctx, a, nullptr)) return rc;
+        if (int rc = pipeline_main(ctx, a, (cudaStream_t)stream, nullptr, true)) return rc;
+        return mark_set_free(ctx, (cudaStream_t)stream);
+    }
+    if (int rc = train_step_body(ctx, a, stream, nullptr)) return rc;
+    return a->n_pos > 0 ? mark_set_free(ctx, (cudaStream_t)stream) : 0;
 }
 
 // KGE_GRAPH=0 disables the captured-graph replay of the host-buffer step
@@ -1437,13 +1523,19 @@ static inline bool train_graph_enabled() {
 // The step as one graph launch.  Everything in `b` except the step counter is part of the key; the
 // first call with a new key runs eagerly (workspace growth, function attributes), the second is
 // captured (the side-stream fork/join included) and instantiated, later ones only replay.
-static int train_step_graphed(kge_ctx* ctx, const kge_train_args* b, cudaStream_t st) {
+// pipelined: only the main part of the step is captured (the caller has issued the prologue and the waits for it)
+static int train_step_graphed(kge_ctx* ctx, const kge_train_args* b, cudaStream_t st, const KgeStepDyn* dd, bool pipelined) {
     static uint64_t tick = 0;
     kge_train_args key = *b;
     key.step = 0;
+    // a graph holds the raw pointers of the buffer set that was current at capture
+    const int variant = (pipelined ? 10 : 0) + ctx->set_id;
+    auto body = [&](const KgeStepDyn* dyn) -> int {
+        return pipelined ? pipeline_main(ctx, b, st, dyn, false) : train_step_body(ctx, b, st, dyn);
+    };
     KgeGraphEntry* e = nullptr;
     for (KgeGraphEntry& g : ctx->graphs)
-        if (g.seen > 0 && g.stream == st && memcmp(&g.key, &key, sizeof(key)) == 0) e = &g;
+        if (g.seen > 0 && g.stream == st && g.variant == variant && memcmp(&g.key, &key, sizeof(key)) == 0) e = &g;
     if (e == nullptr) {
         e = &ctx->graphs[0];
         for (KgeGraphEntry& g : ctx->graphs)
@@ -1455,20 +1547,15 @@ static int train_step_graphed(kge_ctx* ctx, const kge_train_args* b, cudaStream_
         e->exec = nullptr;
         e->key = key;
         e->stream = st;
+        e->variant = variant;
         e->seen = 0;
     }
     e->last_use = ++tick;
     e->seen += 1;
-    if (e->seen == 1) return train_step_body(ctx, b, st, nullptr);
-    if (ctx->h_dyn == nullptr) {
-        KGE_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_dyn, KGE_HOST_RING * sizeof(KgeStepDyn)));
-        if (ctx->d_dyn.reserve(sizeof(KgeStepDyn))) return -2;
-    }
-    // ring slot of this host step: kge_train_step_host_async has waited for the step that used it last, so
-    // the pinned block is free; the copy below is stream-ordered behind the previous replay
-    KgeStepDyn* hd = ctx->h_dyn + (ctx->host_tick % KGE_HOST_RING);
-    hd->step = b->step;
-    hd->lr_t = (float)adam_lr_t(b);
+    if (e->seen == 1) return body(nullptr);
+    // `dd`: this step's {step counter, lr_t} block in device memory, refreshed by the caller on the copy stream
+    // (one block per batch buffer, and b->pos -- part of the key -- names the batch buffer: a graph always
+    // reads the same block)
     if (e->exec != nullptr && e->ws_epoch != g_kge_ws_epoch) {  // a workspace buffer moved since the capture
         cudaGraphExecDestroy(e->exec);
         e->exec = nullptr;
@@ -1477,14 +1564,14 @@ static int train_step_graphed(kge_ctx* ctx, const kge_train_args* b, cudaStream_
         cudaGraph_t graph = nullptr;
         e->ws_epoch = g_kge_ws_epoch;
         KGE_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-        int rc = train_step_body(ctx, b, st, ctx->d_dyn.as<KgeStepDyn>());
+        int rc = body(dd);
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
             e->seen = 1;  // stay eager for this key
             if (rc == 0) kge_set_error("kge_train_step_host: stream capture failed (%s)", cudaGetErrorString(ce));
-            return train_step_body(ctx, b, st, nullptr);
+            return body(nullptr);
         }
         ce = cudaGraphInstantiate(&e->exec, graph, 0);
         cudaGraphDestroy(graph);
@@ -1492,11 +1579,9 @@ static int train_step_graphed(kge_ctx* ctx, const kge_train_args* b, cudaStream_
             e->exec = nullptr;
             e->seen = 1;
             cudaGetLastError();
-            return train_step_body(ctx, b, st, nullptr);
+            return body(nullptr);
         }
     }
-    // step counter / lr_t of this replay (outside the graph: a different pinned slot every step)
-    KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->d_dyn.p, hd, sizeof(KgeStepDyn), cudaMemcpyHostToDevice, st));
     KGE_CUDA_CHECK(cudaGraphLaunch(e->exec, st));
     return 0;
 }
@@ -1521,6 +1606,7 @@ extern "C" int kge_train_step_host_async(kge_ctx* ctx, const kge_train_args* a, 
     const size_t pos_bytes = (size_t)a->n_pos * 3 * sizeof(int32_t);
     kge_train_args b = *a;
     int pb = -1;  // batch buffer of this step (graphed path)
+    bool pipelined = false;
     if (graphed) {
         // the caller's stream may be the legacy default stream, which cannot be captured: the whole call
         // runs on a stream of the ctx, ordered behind the caller's stream (kge_train_host_wait joins it)
@@ -1542,17 +1628,36 @@ extern "C" int kge_train_step_host_async(kge_ctx* ctx, const kge_train_args* a, 
         if (ctx->h_pos2[pb].reserve(pos_bytes)) return -2;
         KGE_CUDA_CHECK(cudaStreamWaitEvent(ctx->cstream, ctx->ev_posfree[pb], 0));  // no-op until first recorded
         KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pos2[pb].p, pos_host, pos_bytes, cudaMemcpyHostToDevice, ctx->cstream));
+        // the step counter / Adam's bias-corrected rate of this step travel the same way, from the pinned ring
+        // slot of this host step (free: the step that used it last has been waited for above)
+        if (ctx->h_dyn == nullptr) {
+            KGE_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_dyn, KGE_HOST_RING * sizeof(KgeStepDyn)));
+            if (ctx->d_dyn.reserve(2 * sizeof(KgeStepDyn))) return -2;
+        }
+        KgeStepDyn* hd = ctx->h_dyn + slot;
+        hd->step = b.step;
+        hd->lr_t = (float)adam_lr_t(&b);
+        KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->d_dyn.as<KgeStepDyn>() + pb, hd, sizeof(KgeStepDyn), cudaMemcpyHostToDevice, ctx->cstream));
         KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_h2d[pb], ctx->cstream));
         KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_h2d[pb], 0));
         b.pos = ctx->h_pos2[pb].as<int32_t>();
+        if (b.loss_out == nullptr) b.loss_out = ctx->h_loss.as<float>();
+        pipelined = step_is_pipelined(ctx, &b);
+        if (pipelined) {
+            // emit + sort of this step start as soon as its batch is in, beside the previous step
+            if (int rc = pipeline_prologue(ctx, &b, ctx->ev_h2d[pb])) return rc;
+            KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_pro_emit[ctx->set_id], 0));
+            KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_pro_sorted[ctx->set_id], 0));
+        }
     } else {
         if (ctx->h_pos.reserve(pos_bytes)) return -2;
         KGE_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pos.p, pos_host, pos_bytes, cudaMemcpyHostToDevice, st));
         b.pos = ctx->h_pos.as<int32_t>();
     }
     if (b.loss_out == nullptr) b.loss_out = ctx->h_loss.as<float>();
-    if (int rc = graphed ? train_step_graphed(ctx, &b, st) : train_step_body(ctx, &b, st, nullptr)) return rc;
+    if (int rc = graphed ? train_step_graphed(ctx, &b, st, ctx->d_dyn.as<KgeStepDyn>() + pb, pipelined) : train_step_body(ctx, &b, st, nullptr)) return rc;
     if (pb >= 0) KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_posfree[pb], st));
+    if (int rc = mark_set_free(ctx, st)) return rc;
     if (loss_host) KGE_CUDA_CHECK(cudaMemcpyAsync(loss_host, b.loss_out, sizeof(float), cudaMemcpyDeviceToHost, st));
     KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_host[slot], st));
     ctx->host_tick += 1;

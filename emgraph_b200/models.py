@@ -470,8 +470,10 @@ class EmbeddingModel:
             neg["neg_entities_n"] = int(nce)
         else:
             raise ValueError("Invalid type for negative_corruption_entities: {}".format(type(nce)))
+        torch.cuda.synchronize(dev)  # parameters, state and entity lists are resident before the first step
         self._fit = dict(
             eng=eng, ent=ent, rel=rel, st=st, step=0, sides=self._train_sides(), neg=neg,
+            pipeline=bool(self.engine_params.get("pipeline", True)),
             loss_dev=torch.zeros(1, dtype=torch.float32, device=dev),
             loss_host=torch.zeros(1, dtype=torch.float32).pin_memory(),
             kw=dict(model=self._model_id(), loss=_lib.LOSS_IDS[self.loss], opt=opt, k=self.k, eta=self.eta,
@@ -499,6 +501,18 @@ class EmbeddingModel:
             cache[n] = codes.repeat_interleave(n).repeat(self.eta).to(f["eng"].tdev)
         return pos.repeat(len(sides), 1), cache[n]
 
+    def _step_kw(self, keep_subj=None):
+        """Per-step scalar arguments.  KGE_F_PIPELINE (corruption generation + radix sort of step t+1 overlap step
+        t, include/kge_b200.h) is requested when everything the corruption generator reads was resident before
+        the previous step was submitted: batches are slices of the resident training array (or host buffers the
+        library copies in itself); per-step device tensors made on torch's stream (the stacked batch of a side
+        list, the entity list of negative_corruption_entities='batch') keep the in-order step."""
+        f = self._fit
+        kw = f["kw"]
+        if f["pipeline"] and keep_subj is None and not self._neg_batch:
+            kw = dict(kw, flags=kw["flags"] | _lib.F_PIPELINE)
+        return kw
+
     def _fit_step_device(self, pos_dev, side="s,o", keep_subj=None):
         """One optimisation step on a device-resident batch; enqueue only, loss stays in f['loss_dev']."""
         f = self._fit
@@ -507,7 +521,7 @@ class EmbeddingModel:
         if self._neg_batch:  # corruptions drawn from the batch's own entities (evaluation/protocol.py:620-641)
             neg = dict(neg_entities=torch.unique(pos_dev[:, [0, 2]]).to(torch.int32))
         a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=pos_dev, loss_out=f["loss_dev"], keep_subj=keep_subj,
-                                side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"], **neg)
+                                side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **self._step_kw(keep_subj), **f["st"], **neg)
         f["eng"].train_step(a)
 
     def _fit_step_host(self, pos_host, side="s,o", keep_subj=None):
@@ -519,7 +533,7 @@ class EmbeddingModel:
         if self._neg_batch:
             neg = dict(neg_entities=to_dev_i32(np.unique(pos_host[:, [0, 2]].numpy()), f["eng"].tdev))
         a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"], keep_subj=keep_subj,
-                                n_pos=pos_host.shape[0], side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"], **neg)
+                                n_pos=pos_host.shape[0], side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **self._step_kw(keep_subj), **f["st"], **neg)
         f["eng"].train_step_host(a, pos_host, f["loss_host"])
         return float(f["loss_host"][0])
 
@@ -534,7 +548,7 @@ class EmbeddingModel:
         if self._neg_batch:
             neg = dict(neg_entities=to_dev_i32(np.unique(pos_host[:, [0, 2]].numpy()), f["eng"].tdev))
         a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"], keep_subj=keep_subj,
-                                n_pos=pos_host.shape[0], side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **f["kw"], **f["st"], **neg)
+                                n_pos=pos_host.shape[0], side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **self._step_kw(keep_subj), **f["st"], **neg)
         ring = f.setdefault("loss_ring", torch.zeros(4, dtype=torch.float32).pin_memory())
         i = f["step"] % 4
         ticket = f["eng"].train_step_host_async(a, pos_host, ring[i:i + 1])
@@ -568,6 +582,7 @@ class EmbeddingModel:
             Xh = torch.from_numpy(np.ascontiguousarray(Xi, dtype=np.int32)).pin_memory()
         else:
             Xd = to_dev_i32(Xi, eng.tdev)
+            torch.cuda.synchronize(eng.tdev)  # KGE_F_PIPELINE: the batches are resident before the first step
         epoch_loss = torch.zeros(1, dtype=torch.float64, device=eng.tdev)
         normalize = bool(self.embedding_model_params.get("normalize_ent_emb", False))
         check_every = int(self.engine_params.get("nan_check_every", self.batches_count))

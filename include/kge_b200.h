@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 4
+#define KGE_ABI_VERSION 5
 #define KGE_MAX_SHARDS 8
 
 typedef struct kge_ctx kge_ctx;
@@ -52,6 +52,14 @@ enum { KGE_NL_LINEAR = 0, KGE_NL_TANH = 1, KGE_NL_SIGMOID = 2, KGE_NL_SOFTPLUS =
 /* train-step flags */
 #define KGE_F_RESET_STATE 1u /* reference-faithful: optimizer state re-created every batch (training/adam.py:45-46) */
 #define KGE_F_NO_UPDATE   2u /* compute loss/grads only (parity tests) */
+/* kge_train_step / kge_train_step_host(_async) only: software-pipeline consecutive steps.  The corruption
+ * generator and the radix sort of a step depend on the batch and on the (seed, step) counters, never on the
+ * parameters, so they run on the library's side stream into the second of two buffer sets and overlap the
+ * forward/backward/reduction of the PREVIOUS step; results are bit-identical to the in-order step.  For the
+ * device-batch entry the caller promises that a->pos (and neg_entities / repl / keep_subj when given) were
+ * resident before the previous step was submitted, i.e. are not produced by work still pending on `stream`
+ * (the reference's batches are slices of one resident array, datasets/numpy_adapter.py:105-111). */
+#define KGE_F_PIPELINE    4u
 
 /* An embedding table, optionally split by contiguous row range over up to 8 GPUs of one NVSwitch
  * domain.  shard[r] is a device pointer valid on THIS device (local memory for r == own rank, a

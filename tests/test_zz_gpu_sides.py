@@ -136,3 +136,58 @@ def test_select_best_model_ranking_on_the_engine(engine):
     grid2 = {"batches_count": [4], "epochs": [5], "k": [4, 8], "eta": [2], "optimizer_params": {"lr": lambda: float(np.random.uniform(1e-3, 1e-2))}}
     out = select_best_model_ranking(models.TransE, Xtr, Xva, Xte, grid2, max_combinations=3, use_filter=False, corrupt_side="o")
     assert len(out[5]) == 3 and out[3].ndim == 1
+
+
+@pytest.mark.parametrize("model,loss,opt", [("ComplEx", "nll", "adam"), ("TransE", "pairwise", "adagrad"), ("DistMult", "multiclass_nll", "adam")])
+@pytest.mark.parametrize("host_batches", [False, True])
+def test_pipelined_steps_are_bit_identical_to_in_order_steps(engine, model, loss, opt, host_batches):
+    """KGE_F_PIPELINE (emit + sort of step t+1 on the side stream beside step t, two buffer sets, main-part graphs
+    for host batches) must not change a single bit: same kernels, same inputs, same summation order.  Hub-heavy
+    Zipf batches of two sizes (the last batch is short) over several epochs, device and host batches."""
+    from emgraph_b200 import models
+    E, R, N = 500, 6, 5000
+    tri = ko.synthetic_triples(E, R, N, seed=21, zipf=True)
+    X = np.empty(tri.shape, dtype=object)
+    X[:, 0] = ["e%04d" % v for v in tri[:, 0]]
+    X[:, 1] = ["r%d" % v for v in tri[:, 1]]
+    X[:, 2] = ["e%04d" % v for v in tri[:, 2]]
+    X = X.astype(str)
+    out = []
+    for pipeline in (False, True):
+        m = getattr(models, model)(k=12, eta=5, epochs=4, batches_count=7, seed=3, optimizer=opt, optimizer_params={"lr": 1e-2},
+                                   loss=loss, engine_params={"pipeline": pipeline, "host_batches": host_batches})
+        m.fit(X)
+        out.append((m.trained_model_params[0].copy(), m.trained_model_params[1].copy(), list(m.loss_history)))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    assert out[0][2] == out[1][2]
+    assert np.all(np.isfinite(out[0][2])) and out[0][2][-1] < out[0][2][0]
+
+
+def test_pipelined_and_in_order_steps_interleave(engine):
+    """Alternating pipelined and in-order calls on one ctx (buffer-set bookkeeping) == all in-order."""
+    from emgraph_b200 import _lib
+    from emgraph_b200.engine import model_id
+    ent, rel, pos, k = _case(seed=4, E=200, n=160)
+    eta = 6
+    res = []
+    for pattern in ([0] * 8, [1, 0, 1, 1, 0, 0, 1, 1]):
+        ent_d, rel_d = torch.from_numpy(ent).cuda(), torch.from_numpy(rel).cuda()
+        m_d, v_d = torch.zeros_like(ent_d), torch.zeros_like(ent_d)
+        rm, rv = torch.zeros_like(rel_d), torch.zeros_like(rel_d)
+        pos_d = torch.from_numpy(pos).cuda()
+        loss_d = torch.zeros(1, device="cuda")
+        torch.cuda.synchronize()
+        losses = []
+        for step, pipe in enumerate(pattern, 1):
+            lo = (step % 3) * 40
+            a = engine.train_args(model=model_id("ComplEx"), loss=_lib.LOSS_IDS["nll"], opt=_lib.OPT_IDS["adam"], k=k, eta=eta,
+                                  ent=ent_d, rel=rel_d, ent_m=m_d, ent_v=v_d, rel_m=rm, rel_v=rv, pos=pos_d[lo:lo + 80 + 8 * (step % 2)],
+                                  loss_out=loss_d, lr=1e-2, seed=5, step=step, flags=_lib.F_PIPELINE if pipe else 0)
+            engine.train_step(a)
+            losses.append(loss_d.clone())
+        torch.cuda.synchronize()
+        res.append((ent_d.cpu().numpy(), rel_d.cpu().numpy(), [float(x) for x in losses]))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    assert res[0][2] == res[1][2]
