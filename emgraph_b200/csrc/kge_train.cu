@@ -694,8 +694,10 @@ __device__ __forceinline__ const float* span_entry(const ApplyParams& P, int64_t
 // CTA add the per-chunk partial rows of one run (warp j takes partials j, j+KGE_SPAN_WARPS, ...), the
 // partial sums are combined through shared memory in warp order (deterministic) and the optimizer is
 // applied by the threads that own the columns (their w, m, v loads are issued before the summation).
-#define KGE_SPAN_WARPS 8
-template <int V>
+// KGE_SPAN_WARPS is a template parameter: the longest run (the top hub of a Zipf graph: ~10 % of all slots,
+// hundreds of partial rows) is one CTA's serial chain, so the kernel's duration is that run's partial count
+// divided by the warps of a CTA.
+template <int V, int KGE_SPAN_WARPS>
 __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(ApplyParams P) {
     extern __shared__ __align__(16) float sred[];  // [KGE_SPAN_WARPS][K]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1084,6 +1086,32 @@ static inline bool reduce_staged_enabled() {
     return v != 0;
 }
 
+// Warps per CTA of the span/hub reduction.  32 (one 1024-thread CTA per run head) unless the [32][K] staging
+// rows would crowd shared memory; KGE_SPAN_WARPS=8|32 overrides (A/B knob, read once).  Measured on B200
+// (profiles/r01_x_*): cfg3 span phase 17.2 -> 13.8 us, cfg4 23.3 -> 16.4 us with 32 warps.
+static inline int span_warps(int K) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("KGE_SPAN_WARPS");
+        forced = (e != nullptr && atoi(e) == 32) ? 32 : (e != nullptr && atoi(e) == 8 ? 8 : 0);
+    }
+    if (forced > 0) return forced;
+    return (size_t)32 * K * sizeof(float) <= 100 * 1024 ? 32 : 8;
+}
+
+template <int V, int W>
+static int launch_span(const ApplyParams& P, int sm_count, cudaStream_t st) {
+    const size_t smem = (size_t)W * P.ent.K * sizeof(float);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_span_apply_kernel<V, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    kge_span_apply_kernel<V, W><<<sm_count, W * 32, smem, st>>>(P);
+    KGE_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 template <int V, int NCA>
 static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st, cudaEvent_t mid) {
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
@@ -1111,21 +1139,13 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
     else if (tmode == 1) kge_reduce_apply_kernel<V, 1, NCA><<<grid, block, 0, st>>>(P);
     else kge_reduce_apply_kernel<V, 2, NCA><<<grid, block, 0, st>>>(P);
     KGE_CUDA_CHECK(cudaGetLastError());
-    const size_t smem = (size_t)KGE_SPAN_WARPS * P.ent.K * sizeof(float);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_span_apply_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
     if (mid != nullptr) KGE_CUDA_CHECK(cudaEventRecord(mid, st));
-    kge_span_apply_kernel<V><<<sm_count, KGE_SPAN_WARPS * 32, smem, st>>>(P);
-    KGE_CUDA_CHECK(cudaGetLastError());
-    return 0;
+    return span_warps(P.ent.K) == 32 ? launch_span<V, 32>(P, sm_count, st) : launch_span<V, 8>(P, sm_count, st);
 }
 
 static int launch_apply(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st, cudaEvent_t mid) {
     const int K = P.ent.K;
-    KGE_REQUIRE((size_t)KGE_SPAN_WARPS * K * sizeof(float) <= 200 * 1024, "kge_train: embedding size %d too large for the span reduction", K);
+    KGE_REQUIRE((size_t)span_warps(K) * K * sizeof(float) <= 200 * 1024, "kge_train: embedding size %d too large for the span reduction", K);
     if (K % 4 == 0) {
         if (K <= 128) return launch_apply_nca<4, 1>(P, tmode, sm_count, st, mid);
         if (K <= 256) return launch_apply_nca<4, 2>(P, tmode, sm_count, st, mid);
