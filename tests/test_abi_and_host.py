@@ -261,3 +261,18 @@ def test_quantised_comparison_thresholds_mirror():
             q = trunc_sat(y)
             assert (q >= n) == bool(y >= t_ge), (n, float(y), q, float(t_ge))
             assert (q > n) == bool(y >= t_gt), (n, float(y), q, float(t_gt))
+
+
+def test_integration_stub_matches_the_binding():
+    """INTEGRATION.md shows the ctypes stub a reference maintainer would add: its kge_train_args fields must be the
+    binding's (same names, same order), and every entry point it calls must be declared in include/kge_b200.h."""
+    import re
+    from emgraph_b200 import _lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = doc[doc.index("class KgeTrainArgs(C.Structure)"):doc.index("lib.kge_last_error.restype")]
+    names = re.findall(r'\("(\w+)",\s*(?:C\.|KgeTable)', block)
+    assert names == [f[0] for f in L.KgeTrainArgs._fields_]
+    header = open(os.path.join(root, "include", "kge_b200.h")).read()
+    for fn in set(re.findall(r"lib\.(kge_\w+)", doc)):
+        assert re.search(r"\b%s\s*\(" % fn, header), fn
