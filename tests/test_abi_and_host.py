@@ -276,3 +276,29 @@ def test_integration_stub_matches_the_binding():
     header = open(os.path.join(root, "include", "kge_b200.h")).read()
     for fn in set(re.findall(r"lib\.(kge_\w+)", doc)):
         assert re.search(r"\b%s\s*\(" % fn, header), fn
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/kge_b200.h is the boundary a non-Python host binds (cgo / JNI / FFI): it must compile as C99 and as
+    C++ on its own, and a C translation unit that references every declared entry point must link against the
+    library (no torch, no C++ types in the signatures)."""
+    import re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "kge_b200.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
+    names = sorted(set(re.findall(r"^(?:int|int64_t|const char\*)\s+(kge_[a-z0-9_]+)\s*\(", open(hdr).read(), re.M)))
+    src = tmp_path / "link_all.c"
+    src.write_text('#include "kge_b200.h"\n#include <stdio.h>\nint main(void) {\n  void* p[] = {%s};\n'
+                   '  printf("%%d %%d\\n", kge_abi_version(), (int)(sizeof(p) / sizeof(p[0])));\n  return kge_abi_version() == KGE_ABI_VERSION ? 0 : 1;\n}\n'
+                   % ", ".join("(void*)%s" % n for n in names))
+    lib_dir = os.path.join(root, "emgraph_b200")
+    exe = tmp_path / "link_all"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", lib_dir,
+                    "-l:libkge_b200.so", "-Wl,-rpath," + lib_dir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[1]) == len(names) >= 30
