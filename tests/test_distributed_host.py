@@ -102,3 +102,63 @@ def test_gloo_world2_key_gather_and_owner_selection():
         p.join(timeout=30)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ------------------------------------------------------------------------------------------------
+# owner-compute exchange (the round-2 plan): the decomposition must be exact
+# ------------------------------------------------------------------------------------------------
+import pytest  # noqa: E402
+
+from oracle import kge_oracle as ko  # noqa: E402
+from oracle import sharded_oracle as so  # noqa: E402
+
+
+def _rank_batches(rng, E, R, n, eta, W):
+    out = []
+    for _ in range(W):
+        pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+        out.append((pos, rng.integers(0, 2, n * eta).astype(np.uint8), rng.integers(0, E, n * eta).astype(np.int32)))
+    return out
+
+
+@pytest.mark.parametrize("model,loss,norm,nl", [("DistMult", "nll", 1, "linear"), ("ComplEx", "multiclass_nll", 1, "linear"),
+                                                ("HolE", "self_adversarial", 1, "tanh"), ("TransE", "pairwise", 1, "linear"),
+                                                ("TransE", "nll", 2, "linear"), ("ComplEx", "absolute_margin", 1, "sigmoid")])
+def test_owner_compute_step_equals_the_oracle_step(model, loss, norm, nl):
+    """Folded queries shipped to the owners, owner-side scores, per-owner partial sums of c*dF/dQ sent back: the
+    summed loss and gradients of W ranks equal the single-process oracle step on the same batches."""
+    rng = np.random.default_rng(7)
+    E, R, k, eta, n, W = 97, 5, 6, 5, 23, 4
+    K = ko.internal_k(model, k)
+    ent = (rng.normal(size=(E, K)) * 0.5).astype(np.float32)
+    rel = (rng.normal(size=(R, K)) * 0.5).astype(np.float32)
+    batches = _rank_batches(rng, E, R, n, eta, W)
+    got = so.owner_compute_step(model, k, loss, eta, ent, rel, batches, W, margin=2.0, norm=norm, nl=nl)
+    exp_loss, exp_ge, exp_gr = 0.0, np.zeros((E, K)), np.zeros((R, K))
+    for pos, keep, repl in batches:
+        o = ko.train_step(model, k, loss, eta, ent, rel, pos, keep, repl, margin=2.0, norm=norm, dtype=np.float64, nl=nl)
+        exp_loss += float(o["loss"])
+        exp_ge += o["grad_ent"]
+        exp_gr += o["grad_rel"]
+    np.testing.assert_allclose(got["loss"], exp_loss, rtol=1e-10)
+    np.testing.assert_allclose(got["grad_ent"], exp_ge, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(got["grad_rel"], exp_gr, rtol=1e-9, atol=1e-11)
+
+
+def test_owner_compute_volume_against_the_row_push():
+    """Per-rank NVLink volume of the two exchanges at a cfg5-like shape (eta = 64, 8 ranks, 1 KiB rows): shipping
+    queries and partial sums moves under half of what shipping rows moves (DESIGN.md section 7 sizes round 2 with
+    this: ~33 rows per positive against ~74)."""
+    rng = np.random.default_rng(3)
+    E, R, k, eta, n, W = 20000, 9, 256, 64, 120, 8
+    ent = np.zeros((E, k), np.float32)
+    rel = np.zeros((R, k), np.float32)
+    batches = _rank_batches(rng, E, R, n, eta, W)
+    oc = so.owner_compute_step("DistMult", k, "nll", eta, ent, rel, batches, W)
+    push = so.push_step_bytes(eta, n, k, W, E, batches)
+    row = 4 * k
+    assert oc["bytes"]["queries_in"] == 2 * n * (W - 1) * row
+    assert oc["bytes"]["partials_in"] <= 2 * n * (W - 1) * row
+    assert abs(push["rows_in"] - (2 + eta) * n * row * (W - 1) / W) < 0.05 * push["rows_in"]
+    assert 30 * n * row < oc["bytes_total"] < 36 * n * row
+    assert 72 * n * row < push["total"] < 76 * n * row
