@@ -409,6 +409,51 @@ def train_step_sides(model, k, loss, eta, ent, rel, pos, sides, keep_subj_list, 
     return train_step(model, k, loss, eta, ent, rel, pos2, keep2, repl2, **kw)
 
 
+def fit_emulation(model, k, eta, epochs, batches_count, seed, loss, opt, lr, Xi, E, R, margin=1.0, norm=1, alpha=0.5,
+                  reg_p=0, reg_lambda_ent=0.0, reg_lambda_rel=0.0, nl="linear", side="s,o"):
+    """The engine's fit() loop restated on the oracle: Glorot-uniform tables from RandomState(seed) (entities first,
+    initializers/glorot_uniform.py:59-99 as emgraph_b200/models.py:_init_table draws them), sequential unshuffled
+    batches of ceil(N / batches_count) positives (datasets/numpy_adapter.py:105-111), the engine's own corruption
+    stream per (seed, step) (draw_corruptions), one train_step per batch with PERSISTENT optimizer state (the
+    engine's default).  Returns (ent, rel, per-epoch summed loss)."""
+    K = internal_k(model, k)
+    rnd = np.random.RandomState(seed)
+    lim_e, lim_r = np.sqrt(6.0 / (E + K)), np.sqrt(6.0 / (R + K))
+    ent = rnd.uniform(-lim_e, lim_e, size=(E, K)).astype(np.float32)
+    rel = rnd.uniform(-lim_r, lim_r, size=(R, K)).astype(np.float32)
+
+    def init_state(w):
+        if opt == "adam":
+            return (np.zeros_like(w), np.zeros_like(w))
+        if opt == "adagrad":
+            return (np.full_like(w, ADAGRAD_ACC0),)
+        if opt == "momentum":
+            return (np.zeros_like(w),)
+        return ()
+
+    state = (init_state(ent), init_state(rel))
+    Xi = np.asarray(Xi).reshape(-1, 3)
+    N = Xi.shape[0]
+    bs = int(np.ceil(N / batches_count))
+    step, losses = 0, []
+    for _ in range(epochs):
+        tot = 0.0
+        for b in range(batches_count):
+            pos = Xi[b * bs:min(N, (b + 1) * bs)]
+            if pos.shape[0] == 0:
+                continue
+            step += 1
+            repl, keep = draw_corruptions(seed, step, pos.shape[0], eta, E, side)
+            o = train_step(model, k, loss, eta, ent, rel, pos, keep, repl, margin=margin, norm=norm, opt=opt, lr=lr,
+                           state=state, step=step, alpha=alpha, reg_p=reg_p, reg_lambda_ent=reg_lambda_ent,
+                           reg_lambda_rel=reg_lambda_rel, nl=nl)
+            ent, rel = o["ent_new"], o["rel_new"]
+            state = (o["state_ent"], o["state_rel"])
+            tot += float(o["loss"])
+        losses.append(tot)
+    return ent, rel, losses
+
+
 # --------------------------------------------------------------------------------------------
 # evaluation corruptions + filter sets + ranking
 # --------------------------------------------------------------------------------------------
