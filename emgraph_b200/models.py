@@ -433,8 +433,16 @@ class EmbeddingModel:
             self._save_trained_params()
         return False
 
+    def _reseed_if_refit(self):
+        """Re-fitting a fitted model starts from the seed again (models/EmbeddingModel.py:1285-1290), so that
+        fit(X); fit(X) reproduces the first fit (reference tests/emgraph/models/test_models.py:338-367) and
+        select_best_model_ranking(retrain_best_model=True) retrains deterministically."""
+        if self.is_fitted:
+            self.rnd = np.random.RandomState(self.seed)
+
     def _fit_prepare(self, E, R):
         """Allocate device parameters + optimizer state and freeze the per-step arguments."""
+        self._reseed_if_refit()
         eng = get_engine(self.engine_params.get("device"))
         dev = eng.tdev
         K = self.internal_k

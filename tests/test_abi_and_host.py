@@ -302,3 +302,17 @@ def test_header_is_plain_c(tmp_path):
                     "-l:libkge_b200.so", "-Wl,-rpath," + lib_dir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[1]) == len(names) >= 30
+
+
+def test_refit_starts_from_the_seed_again():
+    """models/EmbeddingModel.py:1285-1290: a fitted model re-seeds its RNG when fit() is called again (host logic only;
+    the GPU test tests/test_zzz_gpu_reference_properties.py::test_refit_is_deterministic runs the real thing)."""
+    from emgraph_b200 import models
+    m = models.ComplEx(k=4, seed=555)
+    first = (m._init_table(6, 8, "entity"), m._init_table(1, 8, "relation"))
+    m._reseed_if_refit()  # not fitted yet: the stream simply continues
+    assert not np.array_equal(m._init_table(6, 8, "entity"), first[0])
+    m.is_fitted = True
+    m._reseed_if_refit()
+    np.testing.assert_array_equal(m._init_table(6, 8, "entity"), first[0])
+    np.testing.assert_array_equal(m._init_table(1, 8, "relation"), first[1])
