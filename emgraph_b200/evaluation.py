@@ -143,6 +143,160 @@ def evaluate_performance(X, model, filter_triples=None, verbose=False, filter_un
 
 
 # ------------------------------------------------------------------------------------------------
+# host-side protocol utilities a reference script imports next to evaluate_performance
+# (evaluation/__init__.py:6-16).  The engine itself never materialises corruptions: kge_emit_kernel draws the
+# training negatives and the ranking sweeps enumerate the candidates in place; these return the same triples as
+# arrays for callers that want to look at them.
+# ------------------------------------------------------------------------------------------------
+def generate_corruptions_for_eval(X, entities_for_corruption, corrupt_side="s,o"):
+    """Every corruption of the triple(s) X over `entities_for_corruption` (evaluation/protocol.py:448-528): for
+    's,o' / 's+o' the object sweep [(s, p, e) for all e] followed by the subject sweep [(e, p, o) for all e];
+    'o' / 's' one sweep.  int ids in, ndarray [m, 3] out."""
+    if corrupt_side == "s,o":
+        corrupt_side = "s+o"
+    if corrupt_side not in ("s+o", "s", "o"):
+        raise ValueError("Invalid argument value for corruption side passed for evaluation")
+    X = np.asarray(X).reshape(-1, 3)
+    ents = np.asarray(entities_for_corruption).reshape(-1)
+    n, m = X.shape[0], ents.shape[0]
+    out = []
+    if corrupt_side in ("s+o", "o"):
+        o_sweep = np.empty((n, m, 3), dtype=X.dtype)
+        o_sweep[:, :, 0] = X[:, None, 0]
+        o_sweep[:, :, 1] = X[:, None, 1]
+        o_sweep[:, :, 2] = ents[None, :]
+        out.append(o_sweep.reshape(-1, 3))
+    if corrupt_side in ("s+o", "s"):
+        s_sweep = np.empty((n, m, 3), dtype=X.dtype)
+        s_sweep[:, :, 0] = ents[None, :]
+        s_sweep[:, :, 1] = X[:, None, 1]
+        s_sweep[:, :, 2] = X[:, None, 2]
+        out.append(s_sweep.reshape(-1, 3))
+    return np.concatenate(out, axis=0)
+
+
+def generate_corruptions_for_fit(X, entities_list=None, eta=1, corrupt_side="s,o", entities_size=0, rnd=None):
+    """Training corruptions as arrays (evaluation/protocol.py:531-659): X tiled eta times (row j*n+i corrupts
+    positive i), per row either the subject or the object replaced -- 's,o' / 's+o': a fair coin per row, 'o' the
+    object, 's' the subject -- by a uniform draw from range(entities_size), or from entities_list when given.  No
+    check for accidental positives, as in the reference.  `rnd`: seed or numpy RandomState (the reference draws
+    from TensorFlow's stream, which no other library reproduces; the engine's own stream is Philox)."""
+    if corrupt_side not in ("s+o", "s", "o", "s,o"):
+        raise ValueError("Invalid argument value {} for corruption side passed for evaluation.".format(corrupt_side))
+    rs = rnd if isinstance(rnd, np.random.RandomState) else np.random.RandomState(rnd)
+    X = np.asarray(X).reshape(-1, 3)
+    ds = np.tile(X, (eta, 1))
+    rows = ds.shape[0]
+    if corrupt_side in ("s+o", "s,o"):
+        keep_subj = rs.randint(0, 2, size=rows).astype(bool)
+    else:
+        keep_subj = np.full(rows, corrupt_side == "o")
+    if entities_list is not None:
+        pool = np.asarray(entities_list).reshape(-1)
+        repl = pool[rs.randint(0, pool.shape[0], size=rows)]
+    else:
+        repl = rs.randint(0, int(entities_size), size=rows)
+    out = ds.copy()
+    out[:, 0] = np.where(keep_subj, ds[:, 0], repl)
+    out[:, 2] = np.where(keep_subj, repl, ds[:, 2])
+    return out
+
+
+_SPLIT_ERROR = ("Cannot create a test split of the desired size. Some entities will not occur in both training and test set. "
+                "Set allow_duplication=True,{}remove filter on test predicates or set test_size to a smaller value.")
+
+
+def _split_shuffled(X, test_size, seed, allow_duplication, filtered_test_predicates):
+    """evaluation/protocol.py:24-181: walk the candidates in one random order and move a triple to the test set
+    whenever every entity and relation of it still occurs elsewhere.  Integer ids and count arrays instead of
+    label-keyed dictionaries; the random draws are made in the reference's order from numpy's global stream, so a
+    given seed yields the reference's split."""
+    np.random.seed(seed)
+    if filtered_test_predicates:
+        is_cand = np.isin(X[:, 1], filtered_test_predicates)
+        cand, fixed_train = X[is_cand], X[~is_cand]
+    else:
+        cand, fixed_train = X, None
+    n = cand.shape[0]
+    _, ent_inv = np.unique(np.concatenate([cand[:, 0], cand[:, 2]]), return_inverse=True)
+    s_id, o_id = ent_inv[:n], ent_inv[n:]
+    _, p_id = np.unique(cand[:, 1], return_inverse=True)
+    ent_left = np.bincount(ent_inv).tolist()  # occurrences still in the training part
+    rel_left = np.bincount(p_id).tolist()
+    s_id, o_id, p_id = s_id.tolist(), o_id.tolist(), p_id.tolist()
+    order = np.random.permutation(np.arange(n))
+    test_idx, train_idx = [], []
+    for at, idx in enumerate(order.tolist()):
+        s, p, o = s_id[idx], p_id[idx], o_id[idx]
+        ent_left[s] -= 1
+        rel_left[p] -= 1
+        ent_left[o] -= 1
+        if ent_left[s] > 0 and rel_left[p] > 0 and ent_left[o] > 0:
+            test_idx.append(idx)
+            if len(test_idx) == test_size:
+                train_idx.extend(order[at + 1:].tolist())
+                break
+        else:  # taking it out would leave an entity or a relation unseen: it stays in the training set
+            ent_left[s] += 1
+            rel_left[p] += 1
+            ent_left[o] += 1
+            train_idx.append(idx)
+    if len(test_idx) != test_size:
+        if not allow_duplication:
+            raise Exception(_SPLIT_ERROR.format(""))
+        test_idx.extend(np.random.choice(test_idx, size=(test_size - len(test_idx))).tolist())
+    X_train = cand[train_idx] if fixed_train is None else np.concatenate([fixed_train, cand[train_idx]])
+    X_test = cand[test_idx]
+    return np.random.permutation(X_train), np.random.permutation(X_test)
+
+
+def _split_random_search(X, test_size, seed, allow_duplication, filtered_test_predicates):
+    """evaluation/protocol.py:184-320 (backward_compatible=True): draw candidates one at a time from
+    RandomState(seed); a drawn triple joins the test set when its subject, object and relation each still occur
+    more than once in their own role."""
+    rnd = np.random.RandomState(seed)
+    _, s_id, s_left = np.unique(X[:, 0], return_inverse=True, return_counts=True)
+    _, o_id, o_left = np.unique(X[:, 2], return_inverse=True, return_counts=True)
+    _, p_id, p_left = np.unique(X[:, 1], return_inverse=True, return_counts=True)
+    pool = np.where(np.isin(X[:, 1], filtered_test_predicates))[0] if filtered_test_predicates else np.arange(len(X))
+    chosen = []
+    taken = set()
+    budget = len(X) * 10
+    tries = 0
+    while len(chosen) < test_size:
+        i = int(rnd.choice(pool))
+        s, p, o = s_id[i], p_id[i], o_id[i]
+        if s_left[s] > 1 and o_left[o] > 1 and p_left[p] > 1:
+            s_left[s] -= 1
+            o_left[o] -= 1
+            p_left[p] -= 1
+            if allow_duplication:
+                chosen.append(i)
+            elif i not in taken:
+                taken.add(i)
+                chosen.append(i)
+        tries += 1
+        if tries == budget:
+            raise Exception(_SPLIT_ERROR.format("change seed values, ") if not allow_duplication else
+                            "Cannot create a test split of the desired size. Some entities will not occur in both training and "
+                            "test set. Change seed values, remove filter on test predicates or set test_size to a smaller value.")
+    idx_test = np.asarray(chosen, dtype=int) if allow_duplication else np.unique(np.asarray(chosen, dtype=int))
+    idx_train = np.setdiff1d(np.arange(len(X)), idx_test)
+    return X[idx_train, :], X[idx_test, :]
+
+
+def train_test_split_no_unseen(X, test_size=100, seed=0, allow_duplication=False, filtered_test_predicates=None,
+                               backward_compatible=False):
+    """Split X [n, 3] into (train, test) such that every entity and relation of the test set also occurs in the
+    training set (evaluation/protocol.py:323-407).  test_size: a count, or a fraction of len(X) when float."""
+    X = np.asarray(X)
+    if type(test_size) is float:
+        test_size = int(len(X) * test_size)
+    split = _split_random_search if backward_compatible else _split_shuffled
+    return split(X, test_size, seed, allow_duplication, filtered_test_predicates)
+
+
+# ------------------------------------------------------------------------------------------------
 # metrics (evaluation/metrics.py:11-67, :70-130, :133-164, :167-222)
 # ------------------------------------------------------------------------------------------------
 def hits_at_n_score(ranks, n):

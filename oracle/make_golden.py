@@ -138,6 +138,30 @@ def main():
             keep_subj=keep2, repl=repl2, loss=np.float32(ref["loss"]), scores_pos=np.tile(ref["scores_pos"], S), scores_neg=sneg,
             neg=neg2.astype(np.int32), grad_ent=ref["grad_ent"], grad_rel=ref["grad_rel"])
         print("train multiside", name, "loss", ref["loss"])
+    if wanted("split_cases"):
+        # train_test_split_no_unseen (evaluation/protocol.py:24-407), both algorithms, executed by the reference
+        rng = np.random.Generator(np.random.PCG64(4000))
+        out, ci = {}, 0
+        for trial in range(12):
+            E, R, n = int(rng.integers(5, 40)), int(rng.integers(1, 5)), int(rng.integers(10, 200))
+            X = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(str)
+            X[:, 1] = np.char.add("r", X[:, 1])
+            for bc in (False, True):
+                for dup, filt in ((False, None), (True, None), (False, ["r0"])):
+                    ts, seed = int(rng.integers(1, max(2, n // 3))), int(rng.integers(0, 1000))
+                    try:
+                        a, b = ref_shim.load().protocol.train_test_split_no_unseen(
+                            X, test_size=ts, seed=seed, allow_duplication=dup, filtered_test_predicates=filt, backward_compatible=bc)
+                        err = ""
+                    except Exception as e:  # noqa: BLE001
+                        a = b = np.zeros((0, 3), dtype=X.dtype)
+                        err = str(e)
+                    out.update({"X_%d" % ci: X, "par_%d" % ci: np.array([ts, seed, int(dup), int(bc), int(filt is not None)]),
+                                "train_%d" % ci: a, "test_%d" % ci: b, "err_%d" % ci: np.array(err)})
+                    ci += 1
+        out["n_cases"] = np.array(ci)
+        np.savez_compressed(os.path.join(OUT, "split_cases.npz"), **out)
+        print("split cases", ci, "of which raising", sum(1 for i in range(ci) if str(out["err_%d" % i])))
     for ci, (name, model, k, E, R, F, T, ep, scale) in enumerate(RANK_CASES):
         if not wanted(name):
             continue

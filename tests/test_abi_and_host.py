@@ -316,3 +316,67 @@ def test_refit_starts_from_the_seed_again():
     m._reseed_if_refit()
     np.testing.assert_array_equal(m._init_table(6, 8, "entity"), first[0])
     np.testing.assert_array_equal(m._init_table(1, 8, "relation"), first[1])
+
+
+def test_train_test_split_matches_the_reference():
+    """train_test_split_no_unseen against (a) the reference's own golden (tests/emgraph/evaluation/test_protocol.py:608-639),
+    (b) 72 splits the reference itself produced (tests/golden/split_cases.npz, oracle/make_golden.py), error messages
+    included, and (c) the properties of reference test_protocol.py:642-677."""
+    from emgraph_b200.evaluation import train_test_split_no_unseen
+    X = np.array([["a", "y", "b"], ["a", "y", "c"], ["c", "y", "a"], ["d", "y", "e"], ["e", "y", "f"], ["f", "y", "c"], ["f", "y", "c"]])
+    tr, te = train_test_split_no_unseen(X, test_size=2, seed=0, backward_compatible=True)
+    np.testing.assert_array_equal(tr, [["a", "y", "b"], ["c", "y", "a"], ["d", "y", "e"], ["e", "y", "f"], ["f", "y", "c"]])
+    np.testing.assert_array_equal(te, [["a", "y", "c"], ["f", "y", "c"]])
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "split_cases.npz"))
+    raised = 0
+    for i in range(int(g["n_cases"])):
+        ts, seed, dup, bc, filt = [int(v) for v in g["par_%d" % i]]
+        kw = dict(test_size=ts, seed=seed, allow_duplication=bool(dup), filtered_test_predicates=["r0"] if filt else None,
+                  backward_compatible=bool(bc))
+        err = str(g["err_%d" % i])
+        if err:
+            raised += 1
+            with pytest.raises(Exception) as e:
+                train_test_split_no_unseen(g["X_%d" % i], **kw)
+            assert str(e.value) == err
+        else:
+            tr, te = train_test_split_no_unseen(g["X_%d" % i], **kw)
+            np.testing.assert_array_equal(tr, g["train_%d" % i])
+            np.testing.assert_array_equal(te, g["test_%d" % i])
+    assert raised >= 1
+    # a fraction as test_size; nothing unseen; sizes add up; too large a request raises unless duplicates are allowed
+    rng = np.random.default_rng(1)
+    X = np.stack([rng.integers(0, 300, 4000), rng.integers(0, 6, 4000), rng.integers(0, 300, 4000)], 1).astype(str)
+    tr, te = train_test_split_no_unseen(X, 0.5)
+    assert tr.shape[0] + te.shape[0] == 4000 and te.shape[0] == 2000
+    assert set(te[:, 0]) | set(te[:, 2]) <= set(tr[:, 0]) | set(tr[:, 2]) and set(te[:, 1]) <= set(tr[:, 1])
+    with pytest.raises(Exception, match="Cannot create a test split of the desired size"):
+        train_test_split_no_unseen(X, 0.99)
+    tr, te = train_test_split_no_unseen(X, 0.99, allow_duplication=True)
+    assert tr.shape[0] + te.shape[0] > 4000
+
+
+def test_corruption_utilities():
+    """generate_corruptions_for_eval layout (reference tests/emgraph/evaluation/test_protocol.py:418-455) and the
+    invariants of generate_corruptions_for_fit (reference :530-605: one side of every row is the positive's)."""
+    from emgraph_b200.evaluation import generate_corruptions_for_eval, generate_corruptions_for_fit
+    got = generate_corruptions_for_eval(np.array([[0, 0, 1]]), np.arange(8))
+    np.testing.assert_array_equal(got, [[0, 0, e] for e in range(8)] + [[e, 0, 1] for e in range(8)])
+    np.testing.assert_array_equal(generate_corruptions_for_eval(np.array([[0, 0, 1]]), np.arange(3), "s"), [[e, 0, 1] for e in range(3)])
+    np.testing.assert_array_equal(generate_corruptions_for_eval(np.array([[0, 0, 1]]), np.arange(3), "o"), [[0, 0, e] for e in range(3)])
+    with pytest.raises(ValueError):
+        generate_corruptions_for_eval(np.array([[0, 0, 1]]), np.arange(3), "x")
+    X = np.array([[0, 0, 1], [2, 1, 3], [4, 0, 5]])
+    for side in ("s,o", "s+o", "s", "o"):
+        neg = generate_corruptions_for_fit(X, eta=4, corrupt_side=side, entities_size=50, rnd=7)
+        pos = np.tile(X, (4, 1))
+        assert neg.shape == (12, 3) and np.array_equal(neg[:, 1], pos[:, 1]) and neg.min() >= 0 and neg[:, [0, 2]].max() < 50
+        same_s, same_o = neg[:, 0] == pos[:, 0], neg[:, 2] == pos[:, 2]
+        assert np.all(same_s | same_o)
+        if side == "s":
+            assert np.all(same_o)
+        if side == "o":
+            assert np.all(same_s)
+    neg = generate_corruptions_for_fit(X, entities_list=[7, 9], eta=50, corrupt_side="o", rnd=np.random.RandomState(0))
+    assert set(np.unique(neg[:, 2])) == {7, 9} and np.array_equal(neg[:, 0], np.tile(X[:, 0], 50))
+    np.testing.assert_array_equal(generate_corruptions_for_fit(X, eta=2, entities_size=9, rnd=3), generate_corruptions_for_fit(X, eta=2, entities_size=9, rnd=3))
