@@ -9,5 +9,5 @@ ABI of include/kge_b200.h; there is no CPU fallback.
 __version__ = "0.1.0"
 
 from . import _lib, evaluation, models, utils  # noqa: F401
-from .models import ComplEx, DistMult, HolE, TransE  # noqa: F401
-from .utils import restore_model, save_model  # noqa: F401
+from .models import ComplEx, DistMult, EmbeddingModel, HolE, TransE, reset_entity_threshold, set_entity_threshold  # noqa: F401
+from .utils import dataframe_to_triples, get_entity_triples, restore_model, save_model  # noqa: F401

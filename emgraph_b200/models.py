@@ -42,6 +42,21 @@ DEFAULT_MARGIN = 1  # losses/_loss_constants.py:8
 
 MODEL_REGISTRY = {}
 
+# models/EmbeddingModel.py:37-58: number of entities above which the reference pages the table through host memory
+# ("large graph mode", SGD only).  The table lives in HBM here (sharded over GPUs when it must be, DESIGN.md
+# section 7), so the threshold changes nothing; the two functions exist so that scripts calling them keep running.
+ENTITY_THRESHOLD = 5e5
+
+
+def set_entity_threshold(threshold):
+    global ENTITY_THRESHOLD
+    ENTITY_THRESHOLD = threshold
+
+
+def reset_entity_threshold():
+    global ENTITY_THRESHOLD
+    ENTITY_THRESHOLD = 5e5
+
 DEFAULT_BURN_IN_EARLY_STOPPING = 100  # utils/constants.py:12
 DEFAULT_CHECK_INTERVAL_EARLY_STOPPING = 10  # utils/constants.py:15
 DEFAULT_STOP_INTERVAL_EARLY_STOPPING = 3  # utils/constants.py:18

@@ -59,3 +59,28 @@ def restore_model(model_name_path=None):
     except (IOError, FileNotFoundError):
         raise FileNotFoundError("No model found: {}.".format(model_name_path))
     return model
+
+
+# ------------------------------------------------------------------------------------------------
+# small data-format helpers a reference script uses on the way to fit() (utils/__init__.py)
+# ------------------------------------------------------------------------------------------------
+def dataframe_to_triples(X, schema):
+    """Rows of a DataFrame as triples (utils/model_utils.py:326-365).  schema: (subject column, relation name, object
+    column) tuples; one triple per row and schema entry, in schema order."""
+    schema = [tuple(t) for t in schema]
+    missing = {c for s, _, o in schema for c in (s, o)} - set(X.columns)
+    if missing:
+        raise Exception("Subject/Object {} are not in data frame headers".format(missing))
+    blocks = []
+    for s, p, o in schema:
+        block = np.empty((len(X), 3), dtype=object)
+        block[:, 0], block[:, 1], block[:, 2] = X[s].to_numpy(), p, X[o].to_numpy()
+        blocks.append(block)
+    # one homogeneous (string) array, as np.array(list of mixed lists) gives in the reference
+    return np.array(np.concatenate(blocks).tolist()) if blocks else np.array([])
+
+
+def get_entity_triples(entity, graph):
+    """All triples of `graph` [n, 3] with `entity` as subject or object, in graph order (utils/misc.py:28-56)."""
+    graph = np.asarray(graph)
+    return graph[(graph[:, 0] == entity) | (graph[:, 2] == entity)]

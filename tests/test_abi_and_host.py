@@ -380,3 +380,18 @@ def test_corruption_utilities():
     neg = generate_corruptions_for_fit(X, entities_list=[7, 9], eta=50, corrupt_side="o", rnd=np.random.RandomState(0))
     assert set(np.unique(neg[:, 2])) == {7, 9} and np.array_equal(neg[:, 0], np.tile(X[:, 0], 50))
     np.testing.assert_array_equal(generate_corruptions_for_fit(X, eta=2, entities_size=9, rnd=3), generate_corruptions_for_fit(X, eta=2, entities_size=9, rnd=3))
+
+
+def test_data_format_helpers():
+    """reference tests/emgraph/models/test_misc.py:6-28 and tests/emgraph/utils/test_model_utils.py:120-140."""
+    import pandas as pd
+    from emgraph_b200.utils import dataframe_to_triples, get_entity_triples
+    X = np.array([["a", "y", "b"], ["a", "y", "c"], ["c", "y", "a"], ["d", "y", "e"], ["e", "y", "f"], ["f", "y", "c"]])
+    np.testing.assert_array_equal(get_entity_triples("c", X), [["a", "y", "c"], ["c", "y", "a"], ["f", "y", "c"]])
+    assert get_entity_triples("zz", X).shape == (0, 3)
+    df = pd.DataFrame({"species": ["setosa", "virginica"], "sepal_length": [5.1, 6.3], "petal_width": [0.2, 1.8]})
+    t = dataframe_to_triples(df, [("species", "has_sepal_length", "sepal_length"), ("species", "has_petal_width", "petal_width")])
+    np.testing.assert_array_equal(t[0], ["setosa", "has_sepal_length", "5.1"])
+    assert t.shape == (4, 3) and t[3].tolist() == ["virginica", "has_petal_width", "1.8"]
+    with pytest.raises(Exception, match="not in data frame headers"):
+        dataframe_to_triples(df, [("species", "has_sepal_length", "abc")])
