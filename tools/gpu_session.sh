@@ -21,5 +21,20 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'kge
   -o $O/${TAG}_prof_rank python bench.py --steps 3 --warmup 3 --no-cpu --rank-steps 1 > $O/${TAG}_ncu_fullr.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'kge_fwd_bwd|kge_reduce_apply|kge_span' -s 12 -c 6 \
   -o $O/${TAG}_prof_cfg5 python bench.py --workload cfg5 --steps 3 --warmup 3 --no-cpu --no-rank > $O/${TAG}_ncu_full5.log 2>&1
+# TransE distance sweep (cfg1) and the A/B knobs: one line each
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:kge_rank_sweep2 -s 1 -c 1 \
+  -o $O/${TAG}_prof_sweep2 python bench.py --workload cfg1 --steps 3 --warmup 3 --no-cpu --rank-steps 1 > $O/${TAG}_ncu_sweep2.log 2>&1
+for kv in KGE_PIPELINE=0 KGE_SPAN_WARPS=8 KGE_FWD_MAXCTAS=4 KGE_FWD_MAXCTAS=5 KGE_FWD_PIPE=0 KGE_REDUCE_STAGED=1; do
+  env $kv timeout 200 python bench.py --steps 50 --warmup 5 --no-cpu --no-rank > $O/${TAG}_ab_${kv}.json 2> $O/${TAG}_ab_${kv}.err
+done
+python - <<PY
+import glob, json
+for f in sorted(glob.glob("$O/${TAG}_ab_*.json")) + ["$O/${TAG}_bench_cfg3.json"]:
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print("%-46s flushed %.4f warm %.4f e2e %.4f" % (f.split("/")[-1], d["ms_per_step"], d["ms_per_step_warm"], d["e2e"]["ms_per_step"]))
+    except Exception as e:
+        print(f, "ERR", e)
+PY
 tail -3 $O/${TAG}_pytest.log
 head -c 600 $O/${TAG}_bench_cfg3.json
