@@ -536,14 +536,16 @@ class EmbeddingModel:
             kw = dict(kw, flags=kw["flags"] | _lib.F_PIPELINE)
         return kw
 
-    def _fit_step_device(self, pos_dev, side="s,o", keep_subj=None):
-        """One optimisation step on a device-resident batch; enqueue only, loss stays in f['loss_dev']."""
+    def _fit_step_device(self, pos_dev, side="s,o", keep_subj=None, loss_out=None):
+        """One optimisation step on a device-resident batch; enqueue only, the batch loss is written to `loss_out`
+        (a 1-element fp32 device tensor; default f['loss_dev'])."""
         f = self._fit
         f["step"] += 1
         neg = f["neg"]
         if self._neg_batch:  # corruptions drawn from the batch's own entities (evaluation/protocol.py:620-641)
             neg = dict(neg_entities=torch.unique(pos_dev[:, [0, 2]]).to(torch.int32))
-        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=pos_dev, loss_out=f["loss_dev"], keep_subj=keep_subj,
+        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=pos_dev, loss_out=f["loss_dev"] if loss_out is None else loss_out,
+                                keep_subj=keep_subj,
                                 side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **self._step_kw(keep_subj), **f["st"], **neg)
         f["eng"].train_step(a)
 
@@ -606,7 +608,9 @@ class EmbeddingModel:
         else:
             Xd = to_dev_i32(Xi, eng.tdev)
             torch.cuda.synchronize(eng.tdev)  # KGE_F_PIPELINE: the batches are resident before the first step
-        epoch_loss = torch.zeros(1, dtype=torch.float64, device=eng.tdev)
+        # every step of an epoch writes its batch loss into its own slot: no per-step accumulation kernels between
+        # two steps, one float64 sum per epoch (and per NaN check)
+        loss_steps = torch.zeros(self.batches_count, dtype=torch.float32, device=eng.tdev)
         normalize = bool(self.embedding_model_params.get("normalize_ent_emb", False))
         check_every = int(self.engine_params.get("nan_check_every", self.batches_count))
         self.loss_history = []
@@ -614,7 +618,7 @@ class EmbeddingModel:
         sched = SGDSchedule(self.optimizer_params, self.batches_count) if self.optimizer == "sgd" else None
         denom = batch_size * (self.eta if self.loss in TILED_POSITIVE_LOSSES else 1) * self.batches_count  # :1343-1344, :1453-1457
         for epoch in range(1, self.epochs + 1):
-            epoch_loss.zero_()
+            loss_steps.zero_()
             host_loss = 0.0
             for b in range(self.batches_count):
                 lo, hi = b * batch_size, min(N, (b + 1) * batch_size)
@@ -638,19 +642,18 @@ class EmbeddingModel:
                     if multi_side:
                         pos_b, keep = self._stack_sides(pos_b)
                         side = "s,o"
-                    self._fit_step_device(pos_b, side, keep)
-                    epoch_loss += f["loss_dev"].double()
+                    self._fit_step_device(pos_b, side, keep, loss_out=loss_steps[b:b + 1])
                 if normalize:
                     if host_batches and pipelined:
                         lv = self._fit_host_flush()
                         host_loss += lv if lv is not None else 0.0
                     eng.normalize_rows(ent)
-                if not host_batches and f["step"] % check_every == 0 and not bool(torch.isfinite(epoch_loss).item()):
-                    raise ValueError("Loss is {}. Please change the hyperparameters.".format(float(epoch_loss.item())))
+                if not host_batches and f["step"] % check_every == 0 and not bool(torch.isfinite(loss_steps).all().item()):
+                    raise ValueError("Loss is {}. Please change the hyperparameters.".format(float(loss_steps.double().sum().item())))
             if host_batches and pipelined:  # the epoch's last step
                 lv = self._fit_host_flush()
                 host_loss += lv if lv is not None else 0.0
-            el = host_loss if host_batches else float(epoch_loss.item())
+            el = host_loss if host_batches else float(loss_steps.double().sum().item())
             if not np.isfinite(el):  # models/EmbeddingModel.py:1422-1427
                 raise ValueError("Loss is {}. Please change the hyperparameters.".format(el))
             self.loss_history.append(el / denom)
