@@ -1,0 +1,96 @@
+"""TEST-ONLY stand-in for emgraph_b200.engine.Engine: the same method surface, CPU tensors, every step computed by
+the oracle.  It exists so that the HOST logic of fit() / predict() -- batch slicing, step and seed counters, flags,
+side stacking, loss bookkeeping, re-fit seeding -- runs end to end in the CPU test tier (`-m "not gpu"`).  It is
+installed by monkeypatching inside tests/test_fit_host_logic.py only; the product never sees it and still raises
+without the CUDA library (tests/test_abi_and_host.py::test_no_cpu_fallback)."""
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from emgraph_b200 import _lib
+from oracle import kge_oracle as ko
+
+_MODEL = {0: ("TransE", 1), 1: ("TransE", 2), 2: ("DistMult", 1), 3: ("ComplEx", 1), 4: ("HolE", 1)}
+_LOSS = {v: k for k, v in _lib.LOSS_IDS.items()}
+_OPT = {v: k for k, v in _lib.OPT_IDS.items()}
+_SIDE = {0: "s,o", 1: "s", 2: "o"}
+_NL = {v: k for k, v in _lib.NL_IDS.items()}
+
+
+class FakeEngine:
+    tdev = torch.device("cpu")
+
+    def __init__(self):
+        self.launches = 0
+        self.calls = []  # one record per step: what the host asked for
+
+    # ---- argument block: keep what the host passed
+    def train_args(self, **kw):
+        kw.setdefault("side", 0)
+        kw.setdefault("flags", 0)
+        kw.setdefault("step", 1)
+        kw.setdefault("seed", 0)
+        return SimpleNamespace(**kw)
+
+    def _state(self, a, which):
+        m, v = getattr(a, which + "_m", None), getattr(a, which + "_v", None)
+        opt = _OPT[a.opt]
+        if (a.flags & _lib.F_RESET_STATE) or opt == "sgd":
+            return None, ()
+        if opt == "adam":
+            return (m.numpy().copy(), v.numpy().copy()), (m, v)
+        return (m.numpy().copy(),), (m,)
+
+    def _step(self, a, pos):
+        model, norm = _MODEL[a.model]
+        n, eta, E = pos.shape[0], a.eta, a.ent.shape[0]
+        keep_codes = None if getattr(a, "keep_subj", None) is None else a.keep_subj.numpy()
+        if getattr(a, "repl", None) is not None:
+            repl = a.repl.numpy()
+            keep = keep_codes if keep_codes is not None else np.full(n * eta, 1 if a.side == 2 else 0, np.uint8)
+        else:
+            neg_list = getattr(a, "neg_entities", None)
+            repl, keep = ko.draw_corruptions(a.seed, a.step, n, eta, E, _SIDE[a.side], neg_index_base=getattr(a, "neg_index_base", 0),
+                                             neg_entities=None if neg_list is None else neg_list.numpy(),
+                                             neg_entities_n=getattr(a, "neg_entities_n", 0), keep_codes=keep_codes)
+        st_e, t_e = self._state(a, "ent")
+        st_r, t_r = self._state(a, "rel")
+        state = None if st_e is None else (st_e, st_r)
+        o = ko.train_step(model, a.k, _LOSS[a.loss], eta, a.ent.numpy(), a.rel.numpy(), pos, keep, repl, margin=getattr(a, "margin", 1.0),
+                          norm=norm, opt=_OPT[a.opt], lr=a.lr, state=state, step=a.step, alpha=getattr(a, "alpha", 0.5),
+                          reg_p=getattr(a, "reg_p", 0), reg_lambda_ent=getattr(a, "reg_lambda_ent", 0.0),
+                          reg_lambda_rel=getattr(a, "reg_lambda_rel", 0.0), nl=_NL[getattr(a, "non_linearity", 0)])
+        if not (a.flags & _lib.F_NO_UPDATE):
+            a.ent.copy_(torch.from_numpy(o["ent_new"]))
+            a.rel.copy_(torch.from_numpy(o["rel_new"]))
+            for tens, new in ((t_e, o["state_ent"]), (t_r, o["state_rel"])):
+                for t, x in zip(tens, new):
+                    t.copy_(torch.from_numpy(x))
+        a.loss_out[0] = float(o["loss"])
+        self.calls.append(dict(step=a.step, seed=a.seed, n=n, flags=a.flags, side=a.side, lr=a.lr, keep_codes=keep_codes is not None,
+                               neg_entities=getattr(a, "neg_entities", None) is not None, pos=pos.copy()))
+        self.launches += 1
+
+    def train_step(self, a):
+        self._step(a, a.pos.numpy())
+
+    def train_step_host(self, a, pos_host, loss_host):
+        self._step(a, pos_host.numpy())
+        loss_host[0] = a.loss_out[0]
+
+    def train_step_host_async(self, a, pos_host, loss_slot):
+        self._step(a, pos_host.numpy())
+        loss_slot[0] = a.loss_out[0]
+        return len(self.calls) % 4
+
+    def train_host_wait(self, ticket):
+        assert 0 <= ticket < 4
+
+    def normalize_rows(self, emb):
+        nrm = emb.norm(dim=1, keepdim=True).clamp(min=1.0)
+        emb.div_(nrm)
+
+    def score(self, model, k, ent, rel, triples):
+        name, norm = _MODEL[model]
+        return torch.from_numpy(ko.score(name, k, ent.numpy(), rel.numpy(), triples.numpy(), norm))

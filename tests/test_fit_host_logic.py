@@ -1,0 +1,110 @@
+"""CPU: the host logic of fit() / predict() end to end, with the engine replaced by tests/fake_engine.py (every step
+computed by the oracle on CPU tensors).  What is checked is the Python around the kernels -- batch slicing, step / seed
+counters, flags, side stacking, loss bookkeeping, re-fit seeding, the sgd schedule plumbing -- against the oracle's
+restatement of the loop (oracle/kge_oracle.py:fit_emulation).  The kernels themselves are checked on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from emgraph_b200 import _lib, models
+from fake_engine import FakeEngine
+from oracle import kge_oracle as ko
+from toy_graph import TOY_CASES, TOY_QUERY, TOY_X, toy_fit_emulation
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    eng = FakeEngine()
+    monkeypatch.setattr(models, "get_engine", lambda device=None: eng)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    return eng
+
+
+def _toy_model(model, bc, margin, reg, **kw):
+    extra = dict(regularizer="LP", regularizer_params={"lambda": reg[0], "p": reg[1]}) if reg else {}
+    return getattr(models, model)(batches_count=bc, seed=555, epochs=20, k=10, loss="pairwise", loss_params={"margin": margin},
+                                  optimizer="adagrad", optimizer_params={"lr": 0.1}, **extra, **kw)
+
+
+@pytest.mark.parametrize("host_batches,host_pipeline", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("model,bc,margin,reg", TOY_CASES)
+def test_fit_loop_equals_the_emulation(fake, model, bc, margin, reg, host_batches, host_pipeline):
+    m = _toy_model(model, bc, margin, reg, engine_params={"host_batches": host_batches, "host_pipeline": host_pipeline})
+    m.fit(TOY_X)
+    y_ref, losses_ref = toy_fit_emulation(model, bc, margin, reg)
+    np.testing.assert_array_equal(m.predict(TOY_QUERY), y_ref)
+    np.testing.assert_allclose(m.loss_history, np.asarray(losses_ref) / 16.0, rtol=1e-6)
+    assert [c["step"] for c in fake.calls] == list(range(1, 20 * bc + 1)) and all(c["seed"] == 555 for c in fake.calls)
+    assert all(c["n"] == 8 // bc for c in fake.calls) and m._opt_step == 20 * bc
+    # batches are resident slices / library-copied host buffers: every step may be software-pipelined
+    assert all(c["flags"] & _lib.F_PIPELINE for c in fake.calls)
+    # a second fit starts from the seed again (models/EmbeddingModel.py:1285-1290)
+    m.fit(TOY_X)
+    np.testing.assert_array_equal(m.predict(TOY_QUERY), y_ref)
+
+
+def test_engine_params_switch_pipelining_off(fake):
+    m = _toy_model("DistMult", 2, 5.0, None, engine_params={"pipeline": False})
+    m.fit(TOY_X)
+    assert not any(c["flags"] & _lib.F_PIPELINE for c in fake.calls)
+
+
+def test_side_list_is_one_stacked_step_per_batch(fake):
+    """corrupt_side=['s', 'o', 's,o'] -> one step per batch over the positives stacked three times, per-negative side
+    codes, in-order step (the stacked batch is made on torch's stream); equals the oracle on the stacked batch."""
+    r2i, e2i = ko.create_mappings(TOY_X)
+    Xi = ko.to_idx(TOY_X, e2i, r2i)
+    E, R, k, eta = len(e2i), len(r2i), 6, 3
+    m = models.ComplEx(k=k, eta=eta, epochs=3, batches_count=2, seed=9, loss="multiclass_nll", optimizer="adam", optimizer_params={"lr": 0.05},
+                       embedding_model_params={"corrupt_side": ["s", "o", "s,o"]})
+    m.fit(TOY_X)
+    assert len(fake.calls) == 6 and all(c["n"] == 12 and c["keep_codes"] and not (c["flags"] & _lib.F_PIPELINE) for c in fake.calls)
+    np.testing.assert_array_equal(fake.calls[0]["pos"], np.tile(Xi[:4], (3, 1)))
+    # the same loop on the oracle
+    K = 2 * k
+    rnd = np.random.RandomState(9)
+    ent = rnd.uniform(-np.sqrt(6 / (E + K)), np.sqrt(6 / (E + K)), size=(E, K)).astype(np.float32)
+    rel = rnd.uniform(-np.sqrt(6 / (R + K)), np.sqrt(6 / (R + K)), size=(R, K)).astype(np.float32)
+    state = ((np.zeros_like(ent), np.zeros_like(ent)), (np.zeros_like(rel), np.zeros_like(rel)))
+    step = 0
+    for _ in range(3):
+        for b in range(2):
+            step += 1
+            pos = np.tile(Xi[b * 4:(b + 1) * 4], (3, 1))
+            codes = np.tile(np.repeat(np.array([0, 1, 2], np.uint8), 4), eta)
+            repl, keep = ko.draw_corruptions(9, step, 12, eta, E, "s,o", keep_codes=codes)
+            o = ko.train_step("ComplEx", k, "multiclass_nll", eta, ent, rel, pos, keep, repl, opt="adam", lr=0.05, state=state, step=step)
+            ent, rel, state = o["ent_new"], o["rel_new"], (o["state_ent"], o["state_rel"])
+    np.testing.assert_array_equal(m.trained_model_params[0], ent)
+    np.testing.assert_array_equal(m.trained_model_params[1], rel)
+
+
+def test_batch_corruption_entities_keep_the_in_order_step(fake):
+    m = models.DistMult(k=4, eta=2, epochs=1, batches_count=2, seed=1, embedding_model_params={"negative_corruption_entities": "batch"})
+    m.fit(TOY_X)
+    assert all(c["neg_entities"] and not (c["flags"] & _lib.F_PIPELINE) for c in fake.calls)
+
+
+def test_sgd_schedule_reaches_every_step(fake):
+    from emgraph_b200.optimizers import SGDSchedule
+    params = {"lr": 0.1, "decay_cycle": 3, "end_lr": 0.01, "cosine_decay": True}
+    m = models.TransE(k=4, eta=2, epochs=2, batches_count=4, seed=1, optimizer="sgd", optimizer_params=params, loss="nll")
+    m.fit(TOY_X)
+    sched = SGDSchedule(params, 4)
+    want = [float(sched(b + 1, e)) for e in (1, 2) for b in range(4)]
+    np.testing.assert_allclose([c["lr"] for c in fake.calls], want, rtol=0, atol=0)
+
+
+def test_divergence_raises_like_the_reference(fake):
+    """models/EmbeddingModel.py:1422-1427: a NaN / Inf batch loss aborts the fit with ValueError."""
+    m = models.DistMult(k=4, eta=2, epochs=3, batches_count=1, seed=0, optimizer="sgd", optimizer_params={"lr": 1e18}, loss="pairwise")
+    with np.errstate(all="ignore"), pytest.raises(ValueError, match="Please change the hyperparameters"):
+        m.fit(TOY_X)
+
+
+def test_normalize_ent_emb_after_every_batch(fake):
+    m = models.TransE(k=4, eta=2, epochs=2, batches_count=2, seed=0, optimizer="sgd", optimizer_params={"lr": 5.0}, loss="pairwise",
+                      embedding_model_params={"normalize_ent_emb": True})
+    m.fit(TOY_X)
+    assert np.all(np.linalg.norm(m.trained_model_params[0], axis=1) <= 1.0 + 1e-6)
