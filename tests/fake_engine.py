@@ -94,3 +94,25 @@ class FakeEngine:
     def score(self, model, k, ent, rel, triples):
         name, norm = _MODEL[model]
         return torch.from_numpy(ko.score(name, k, ent.numpy(), rel.numpy(), triples.numpy(), norm))
+
+    # ---- evaluation: the filter is the raw triple array, ranks come from the oracle
+    def filter_build(self, triples, E, R):
+        self._filter = triples.numpy().copy()
+        self._filter_shape = (E, R)
+
+    def filter_clear(self):
+        self._filter = None
+
+    def rank_host(self, model, k, ent, rel, test_host, ranks_host, *, side=0, strategy=0, filtered=False, use_tensor_cores=False,
+                  non_linearity=0):
+        name, norm = _MODEL[model]
+        side_s = {v: s for s, v in _lib.RANK_SIDE_IDS.items()}[side]
+        strat_s = {v: s for s, v in _lib.STRATEGY_IDS.items()}[strategy]
+        if test_host.shape[0] == 0:
+            return
+        filt = getattr(self, "_filter", None) if filtered else None
+        if filtered:
+            assert filt is not None and self._filter_shape == (ent.shape[0], rel.shape[0])
+        r = ko.ranks(name, k, ent.numpy(), rel.numpy(), test_host.numpy(), filt, side_s, strat_s, norm, nl=_NL[non_linearity])
+        ranks_host.copy_(torch.from_numpy(np.asarray(r, np.int32)).reshape(ranks_host.shape))
+        self.rank_calls = getattr(self, "rank_calls", 0) + 1

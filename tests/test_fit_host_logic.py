@@ -108,3 +108,64 @@ def test_normalize_ent_emb_after_every_batch(fake):
                       embedding_model_params={"normalize_ent_emb": True})
     m.fit(TOY_X)
     assert np.all(np.linalg.norm(m.trained_model_params[0], axis=1) <= 1.0 + 1e-6)
+
+
+def _synthetic(E=40, R=3, n=500, seed=5):
+    tri = ko.synthetic_triples(E, R, n, seed=seed)
+    X = np.empty(tri.shape, dtype=object)
+    X[:, 0] = ["e%03d" % v for v in tri[:, 0]]
+    X[:, 1] = ["r%d" % v for v in tri[:, 1]]
+    X[:, 2] = ["e%03d" % v for v in tri[:, 2]]
+    return tri, X.astype(str)
+
+
+def test_evaluate_performance_host_path(fake):
+    """evaluate_performance -> set_filter_for_eval / configure_evaluation_protocol / get_ranks / end_evaluation
+    (evaluation/protocol.py:726-979): label mapping, unseen-entity filtering, output shapes, filter hand-over."""
+    from emgraph_b200.evaluation import evaluate_performance, hits_at_n_score, mrr_score
+    tri, X = _synthetic()
+    m = models.DistMult(k=6, eta=2, epochs=5, batches_count=4, seed=0, optimizer="adam", optimizer_params={"lr": 0.05})
+    m.fit(X[:400])
+    test = np.concatenate([X[400:430], np.array([["never-seen", "r0", "e001"]])])
+    ent, rel = m.trained_model_params
+    seen = tri[400:430]
+    for side in ("s,o", "s+o", "o"):
+        got = evaluate_performance(test, m, filter_triples=X, corrupt_side=side)
+        exp = ko.ranks("DistMult", 6, ent, rel, seen, tri, side, "worst")
+        np.testing.assert_array_equal(got, exp)  # the unseen triple was dropped, ids follow the sorted label order
+    raw = evaluate_performance(test, m, corrupt_side="s,o", ranking_strategy="best")
+    np.testing.assert_array_equal(raw, ko.ranks("DistMult", 6, ent, rel, seen, None, "s,o", "best"))
+    assert 0 < mrr_score(raw) <= 1 and 0 <= hits_at_n_score(raw, 10) <= 1
+    assert m.is_filtered is False and m.eval_config == {}  # end_evaluation cleaned up
+    with pytest.raises(AssertionError):
+        evaluate_performance(test, m, corrupt_side="x")
+
+
+def test_early_stopping_host_logic(fake):
+    """models/EmbeddingModel.py:824-1020: validation every check_interval epochs after burn_in, stop after
+    stop_interval checks without improvement, return with the best parameters."""
+    tri, X = _synthetic(seed=6)
+    m = models.ComplEx(k=4, eta=2, epochs=40, batches_count=2, seed=0, optimizer="adam", optimizer_params={"lr": 0.5}, loss="nll")
+    m.fit(X[:400], early_stopping=True,
+          early_stopping_params={"x_valid": X[400:440], "criteria": "mrr", "burn_in": 2, "check_interval": 2, "stop_interval": 2,
+                                 "x_filter": X})
+    hist = m.early_stopping_history
+    assert [e for e, _ in hist] == list(range(2, 2 * len(hist) + 1, 2)) and fake.rank_calls == len(hist)
+    if m.early_stopping_epoch is not None:  # stopped early: the last two checks did not beat the best one
+        best = max(v for _, v in hist)
+        assert all(v <= best for _, v in hist[-2:]) and len(m.loss_history) == m.early_stopping_epoch < 40
+    with pytest.raises(KeyError):
+        models.ComplEx(k=4, epochs=1, batches_count=1).fit(X[:50], early_stopping=True, early_stopping_params={})
+
+
+def test_select_best_model_ranking_end_to_end(fake):
+    from emgraph_b200.evaluation import select_best_model_ranking
+    _, X = _synthetic(seed=7)
+    grid = {"batches_count": [2], "seed": 0, "epochs": [8], "k": [4, 8], "eta": [2], "loss": ["nll"], "loss_params": {},
+            "embedding_model_params": {}, "regularizer": [None], "regularizer_params": {}, "optimizer": ["adam"],
+            "optimizer_params": {"lr": [1e-9, 5e-2]}}
+    best, params, mrr_valid, ranks_test, res, hist = select_best_model_ranking(models.DistMult, X[:400], X[400:450], X[450:], grid,
+                                                                              retrain_best_model=True)
+    assert len(hist) == 4 and params["optimizer_params"]["lr"] in (1e-9, 5e-2) and best.is_fitted
+    assert {(h["model_params"]["k"], h["model_params"]["optimizer_params"]["lr"]) for h in hist} == {(4, 1e-9), (4, 5e-2), (8, 1e-9), (8, 5e-2)}
+    assert mrr_valid == max(h["results"]["mrr"] for h in hist) and ranks_test.shape[1] == 2 and np.isfinite(res["mrr"])
