@@ -356,8 +356,17 @@ class EmbeddingModel:
             raise ValueError("Invalid size for input X. Expected (n,3):  got {}".format(X.shape))
         if focusE_numeric_edge_values is not None:
             raise NotImplementedError("FocusE edge weights are outside the B200 hot-path scope")
-        self._ent_index = LabelIndex(np.unique(np.concatenate((X[:, 0], X[:, 2]))))
-        self._rel_index = LabelIndex(np.unique(X[:, 1]))
+        ent_index = LabelIndex(np.unique(np.concatenate((X[:, 0], X[:, 2]))))
+        rel_index = LabelIndex(np.unique(X[:, 1]))
+        # engine_params['resume']: continue from the current parameters, the saved sparse-optimizer state and the
+        # global step (no reference counterpart: its optimizers are re-created every batch)
+        self._resume = bool(self.engine_params.get("resume", False)) and self.is_fitted
+        if self._resume and not (type(self._ent_index) is LabelIndex and type(self._rel_index) is LabelIndex  # ids in sorted order
+                                 and np.array_equal(self._ent_index.labels, ent_index.labels)
+                                 and np.array_equal(self._rel_index.labels, rel_index.labels)):
+            self._resume = False
+            raise ValueError("resume needs the entities and relations the model was fitted on")
+        self._ent_index, self._rel_index = ent_index, rel_index
         Xi = to_idx(X, self._ent_index, self._rel_index)
         self.early_stopping_params = early_stopping_params
         try:
@@ -461,8 +470,15 @@ class EmbeddingModel:
         eng = get_engine(self.engine_params.get("device"))
         dev = eng.tdev
         K = self.internal_k
-        ent = torch.from_numpy(self._init_table(E, K, "entity")).to(dev)
-        rel = torch.from_numpy(self._init_table(R, K, "relation")).to(dev)
+        resume = bool(getattr(self, "_resume", False))
+        if resume:
+            ent = torch.from_numpy(np.ascontiguousarray(self.trained_model_params[0], dtype=np.float32)).to(dev)
+            rel = torch.from_numpy(np.ascontiguousarray(self.trained_model_params[1], dtype=np.float32)).to(dev)
+            if tuple(ent.shape) != (E, K) or tuple(rel.shape) != (R, K):
+                raise ValueError("resume: parameter shapes {} / {} do not fit this model".format(tuple(ent.shape), tuple(rel.shape)))
+        else:
+            ent = torch.from_numpy(self._init_table(E, K, "entity")).to(dev)
+            rel = torch.from_numpy(self._init_table(R, K, "relation")).to(dev)
         opt = _lib.OPT_IDS[self.optimizer]
         reset = bool(self.engine_params.get("reset_state", False))
         st = {}
@@ -473,6 +489,10 @@ class EmbeddingModel:
                 st = dict(ent_m=torch.full_like(ent, 0.1), rel_m=torch.full_like(rel, 0.1))
             elif opt == 2:
                 st = dict(ent_m=torch.zeros_like(ent), rel_m=torch.zeros_like(rel))
+            saved = getattr(self, "_opt_state", None) or {}
+            if resume and st and set(saved) == set(st) and all(tuple(saved[k_].shape) == tuple(st[k_].shape) for k_ in st):
+                st = {k_: saved[k_].detach().clone().to(dev) for k_ in st}  # rows' m / v / accumulator as they were left
+        step0 = int(getattr(self, "_opt_step", 0)) if resume else 0
         # embedding_model_params['negative_corruption_entities'] (models/EmbeddingModel.py:732-777)
         nce = self.embedding_model_params.get("negative_corruption_entities", DEFAULT_CORRUPTION_ENTITIES)
         neg = {}
@@ -495,7 +515,7 @@ class EmbeddingModel:
             raise ValueError("Invalid type for negative_corruption_entities: {}".format(type(nce)))
         torch.cuda.synchronize(dev)  # parameters, state and entity lists are resident before the first step
         self._fit = dict(
-            eng=eng, ent=ent, rel=rel, st=st, step=0, sides=self._train_sides(), neg=neg,
+            eng=eng, ent=ent, rel=rel, st=st, step=step0, sides=self._train_sides(), neg=neg,
             pipeline=bool(self.engine_params.get("pipeline", True)),
             loss_dev=torch.zeros(1, dtype=torch.float32, device=dev),
             loss_host=torch.zeros(1, dtype=torch.float32).pin_memory(),

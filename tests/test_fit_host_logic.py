@@ -169,3 +169,33 @@ def test_select_best_model_ranking_end_to_end(fake):
     assert len(hist) == 4 and params["optimizer_params"]["lr"] in (1e-9, 5e-2) and best.is_fitted
     assert {(h["model_params"]["k"], h["model_params"]["optimizer_params"]["lr"]) for h in hist} == {(4, 1e-9), (4, 5e-2), (8, 1e-9), (8, 5e-2)}
     assert mrr_valid == max(h["results"]["mrr"] for h in hist) and ranks_test.shape[1] == 2 and np.isfinite(res["mrr"])
+
+
+@pytest.mark.parametrize("opt", ["adam", "adagrad", "momentum"])
+def test_resume_continues_from_saved_optimizer_state(fake, tmp_path, opt):
+    """engine_params['resume'] (checkpoint + optimizer-state resume): 2 epochs, save with the optimizer
+    state, restore, 2 more epochs == 4 epochs in one go, bit for bit (parameters, per-row state and the global step
+    -- which also keys the corruption stream -- carry over)."""
+    from emgraph_b200 import restore_model, save_model
+    _, X = _synthetic(E=30, n=240, seed=8)
+    kw = dict(k=4, eta=3, batches_count=3, seed=4, optimizer=opt, optimizer_params={"lr": 0.05}, loss="nll")
+    straight = models.DistMult(epochs=4, **kw)
+    straight.fit(X)
+    first = models.DistMult(epochs=2, **kw)
+    first.fit(X)
+    path = save_model(first, str(tmp_path / "m.pkl"), save_optimizer_state=True)
+    second = restore_model(path)
+    assert second._opt_step == 6
+    second.engine_params["resume"] = True
+    second.fit(X)
+    assert second._opt_step == 12
+    np.testing.assert_array_equal(second.trained_model_params[0], straight.trained_model_params[0])
+    np.testing.assert_array_equal(second.trained_model_params[1], straight.trained_model_params[1])
+    np.testing.assert_allclose(second.loss_history, straight.loss_history[2:], rtol=1e-6)
+    # a different entity set cannot be resumed
+    with pytest.raises(ValueError, match="resume needs the entities"):
+        second.fit(X[(X[:, 0] != "e000") & (X[:, 2] != "e000")])
+    # without the flag a re-fit starts over from the seed
+    second.engine_params["resume"] = False
+    second.fit(X)
+    np.testing.assert_array_equal(second.trained_model_params[0], first.trained_model_params[0])

@@ -41,3 +41,28 @@ def test_refit_is_deterministic(engine):
     mh = _toy_model("ComplEx", 1, 1.0, (0.1, 2), engine_params={"host_batches": True})
     mh.fit(TOY_X)
     np.testing.assert_array_equal(mh.predict(TOY_QUERY), y1)
+
+
+def test_resume_equals_training_in_one_go(engine, tmp_path):
+    """engine_params['resume']: 2 epochs + save (with the sparse optimizer's state) + restore + 2 epochs == 4 epochs,
+    bit for bit -- the kernels are deterministic and parameters, per-row Adam state and the global step carry over
+    (host logic pinned on CPU by tests/test_fit_host_logic.py::test_resume_continues_from_saved_optimizer_state)."""
+    from emgraph_b200 import models, restore_model, save_model
+    from oracle import kge_oracle as ko
+    tri = ko.synthetic_triples(200, 4, 3000, seed=12, zipf=True)
+    X = np.empty(tri.shape, dtype=object)
+    X[:, 0] = ["e%04d" % v for v in tri[:, 0]]
+    X[:, 1] = ["r%d" % v for v in tri[:, 1]]
+    X[:, 2] = ["e%04d" % v for v in tri[:, 2]]
+    X = X.astype(str)
+    kw = dict(k=16, eta=4, batches_count=5, seed=4, optimizer="adam", optimizer_params={"lr": 0.01}, loss="nll")
+    straight = models.ComplEx(epochs=4, **kw)
+    straight.fit(X)
+    first = models.ComplEx(epochs=2, **kw)
+    first.fit(X)
+    second = restore_model(save_model(first, str(tmp_path / "m.pkl"), save_optimizer_state=True))
+    second.engine_params["resume"] = True
+    second.fit(X)
+    assert second._opt_step == straight._opt_step == 20
+    np.testing.assert_array_equal(second.trained_model_params[0], straight.trained_model_params[0])
+    np.testing.assert_array_equal(second.trained_model_params[1], straight.trained_model_params[1])
