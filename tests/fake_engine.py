@@ -116,3 +116,50 @@ class FakeEngine:
         r = ko.ranks(name, k, ent.numpy(), rel.numpy(), test_host.numpy(), filt, side_s, strat_s, norm, nl=_NL[non_linearity])
         ranks_host.copy_(torch.from_numpy(np.asarray(r, np.int32)).reshape(ranks_host.shape))
         self.rank_calls = getattr(self, "rank_calls", 0) + 1
+
+    def rank_counts(self, model, k, ent, rel, test, *, side=0, filtered=False, use_tensor_cores=False, ent_local=None, row_begin=0,
+                    row_end=None, counts=None, non_linearity=0):
+        """counts[T,2,4]: {object sweep, subject sweep} x {gt, eq, gt & filtered, eq & filtered} over candidate rows
+        [row_begin,row_end), the test triple's own entity skipped (include/kge_b200.h:kge_rank_counts)."""
+        name, norm = _MODEL[model]
+        E = ent.shape[0]
+        row_end = E if row_end is None else row_end
+        cand = np.arange(row_begin, row_end)
+        entn, reln, tst = ent.numpy(), rel.numpy(), test.numpy()
+        filt = ko.FilterIndex(self._filter) if filtered else None
+        out = np.zeros((tst.shape[0], 2, 4), np.int32)
+        nl = _NL[non_linearity]
+        for t, x in enumerate(tst):
+            qp = ko.quantise(ko.non_linearity(nl, ko.score(name, k, entn, reln, x, norm))[0])[0]
+            idx_o, idx_s = filt.participating(x) if filt is not None else ((), ())
+            for sd, (col, known) in enumerate(((2, idx_o), (0, idx_s))):
+                if (side == 3 and sd == 1) or (side == 2 and sd == 0):  # KGE_RANK_O / KGE_RANK_S sweep one side
+                    continue
+                c = cand[cand != x[col]]
+                tri = np.tile(x, (c.shape[0], 1))
+                tri[:, col] = c
+                q = ko.quantise(ko.non_linearity(nl, ko.score(name, k, entn, reln, tri, norm))[0])
+                f = np.isin(c, np.asarray(list(known), dtype=np.int64))
+                out[t, sd] = [(q > qp).sum(), (q == qp).sum(), ((q > qp) & f).sum(), ((q == qp) & f).sum()]
+        return torch.from_numpy(out)
+
+    def rank_finalize(self, counts, *, side=0, strategy=0, filtered=False, self_is_candidate=None):
+        c = counts.numpy().astype(np.int64)
+        T = c.shape[0]
+        sc = np.ones((T, 2), np.int64) if self_is_candidate is None else (self_is_candidate.numpy() != 0).astype(np.int64)
+
+        def cmpc(gt, eq):
+            return gt if strategy == 1 else (gt + (eq + 1) // 2 if strategy == 2 else gt + eq)
+
+        go, eo, gs, es = c[:, 0, 0], c[:, 0, 1] + sc[:, 1], c[:, 1, 0], c[:, 1, 1] + sc[:, 0]
+        fo = cmpc(c[:, 0, 2], c[:, 0, 3] + sc[:, 1]) if filtered else 0
+        fs = cmpc(c[:, 1, 2], c[:, 1, 3] + sc[:, 0]) if filtered else 0
+        if side == 0:
+            r = np.stack([cmpc(gs, es) + 1 - fs, cmpc(go, eo) + 1 - fo], 1)
+        elif side == 1:
+            r = cmpc(go + gs, eo + es) + 1 - fs - fo
+        elif side == 2:
+            r = cmpc(gs, es) + 1 - fs
+        else:
+            r = cmpc(go, eo) + 1 - fo
+        return torch.from_numpy(np.asarray(r, np.int32))

@@ -199,3 +199,37 @@ def test_resume_continues_from_saved_optimizer_state(fake, tmp_path, opt):
     second.engine_params["resume"] = False
     second.fit(X)
     np.testing.assert_array_equal(second.trained_model_params[0], first.trained_model_params[0])
+
+
+def test_entities_subset_host_logic(fake):
+    """evaluate_performance(entities_subset=...) (evaluation/protocol.py:940-944, models/EmbeddingModel.py:1845-1857,
+    :1898-1940): the host re-labels the entities so that the subset occupies the first rows of a permuted table,
+    re-labels test and filter triples alike, sweeps those rows only and tells rank_finalize whether the test triple's
+    own entity was a candidate.  Checked against the oracle's subset ranking; the stand-in engine implements the
+    documented contract of kge_rank_counts / kge_rank_finalize."""
+    from emgraph_b200.evaluation import evaluate_performance
+    rng = np.random.default_rng(31)
+    E, R, k = 60, 3, 5
+    ent = (rng.normal(size=(E, k)) * 0.6).astype(np.float32)
+    rel = (rng.normal(size=(R, k)) * 0.6).astype(np.float32)
+    tri = ko.synthetic_triples(E, R, 400, seed=8)
+    X = np.empty(tri.shape, dtype=object)
+    X[:, 0] = ["e%05d" % v for v in tri[:, 0]]
+    X[:, 1] = ["r%03d" % v for v in tri[:, 1]]
+    X[:, 2] = ["e%05d" % v for v in tri[:, 2]]
+    X = X.astype(str)
+    m = models.DistMult(k=k, eta=2, epochs=1, batches_count=1, seed=0, optimizer="sgd", optimizer_params={"lr": 0.0}, loss="nll",
+                        initializer="constant", initializer_params={"entity": ent, "relation": rel})
+    m.fit(X)
+    sel = rng.permutation(len(tri))[:25]
+    subset_ids = np.sort(rng.permutation(E)[:17])
+    subset_labels = ["e%05d" % v for v in subset_ids] + ["not-an-entity"]
+    for side in ("s,o", "s+o", "o", "s"):
+        for strat in ("worst", "middle", "best"):
+            for filt in (None, tri):
+                got = evaluate_performance(X[sel], m, filter_triples=None if filt is None else X, entities_subset=subset_labels,
+                                           corrupt_side=side, ranking_strategy=strat)
+                exp = ko.ranks("DistMult", k, ent, rel, tri[sel], filt, side, strat, subset=subset_ids)
+                np.testing.assert_array_equal(got, exp, err_msg="%s %s %s" % (side, strat, filt is not None))
+    # the full sweep afterwards uses the un-permuted filter again
+    np.testing.assert_array_equal(evaluate_performance(X[sel], m, filter_triples=X), ko.ranks("DistMult", k, ent, rel, tri[sel], tri))
