@@ -89,20 +89,57 @@ class LabelIndex:
     def __init__(self, labels_sorted):
         self.labels = np.asarray(labels_sorted)
         self._dict = None
+        self._hash = None  # lazily: hash table over the labels for bulk lookups
 
     def __len__(self):
         return len(self.labels)
+
+    _HASH_MIN = 4096  # below this many lookups the binary search over the labels is as fast
+
+    def _hashed(self):
+        """(hashes of the labels in id order, pandas Index over them or None): built once, None when hashing does not
+        apply (labels not fixed-width str / bytes, or two labels share a hash)."""
+        if self._hash is None:
+            self._hash = False
+            if self.labels.ndim == 1 and self.labels.dtype.kind in "US" and len(self.labels) > 0:
+                h = _hash_fixed_width(self.labels)
+                if np.unique(h).shape[0] == h.shape[0]:
+                    try:
+                        import pandas as pd
+                        self._hash = (h, pd.Index(h))
+                    except ImportError:
+                        order = np.argsort(h, kind="stable")
+                        self._hash = (h, (h[order], order))
+        return self._hash or None
+
+    def _positions(self, x):
+        """(candidate id of every element of x, whether the label there IS that element).  Large fixed-width str / bytes
+        inputs are hashed (one pass, then an integer table) instead of binary-searched label by label; the label
+        comparison at the end makes the result exact either way."""
+        n = len(self.labels)
+        if x.size >= self._HASH_MIN and x.ndim == 1 and x.dtype.kind == self.labels.dtype.kind and x.dtype.kind in "US":
+            tab = self._hashed()
+            if tab is not None:
+                hx = _hash_fixed_width(x if x.dtype == self.labels.dtype else x.astype(self.labels.dtype))
+                if isinstance(tab[1], tuple):
+                    hs, order = tab[1]
+                    p = np.minimum(np.searchsorted(hs, hx), n - 1)
+                    pos = order[p]
+                else:
+                    pos = tab[1].get_indexer(hx)
+                    pos = np.where(pos < 0, 0, pos)
+                return pos, self.labels[pos] == x
+        pos = np.minimum(np.searchsorted(self.labels, x), n - 1)
+        return pos, self.labels[pos] == x
 
     def lookup(self, x, what):
         x = np.asarray(x)
         if len(self.labels) == 0:
             raise ValueError(_UNSEEN_MSG.format(concept_type=what))
         try:
-            pos = np.searchsorted(self.labels, x)
+            pos, ok = self._positions(x)
         except TypeError:
             raise ValueError(_UNSEEN_MSG.format(concept_type="concepts"))
-        pos = np.minimum(pos, len(self.labels) - 1)
-        ok = self.labels[pos] == x
         if not np.all(ok):
             raise ValueError(_UNSEEN_MSG.format(concept_type=what))
         return pos.astype(np.int32)
@@ -112,10 +149,9 @@ class LabelIndex:
         if len(self.labels) == 0:
             return np.zeros(x.shape, bool)
         try:
-            pos = np.minimum(np.searchsorted(self.labels, x), len(self.labels) - 1)
+            return self._positions(x)[1]
         except TypeError:
             return np.zeros(x.shape, bool)
-        return self.labels[pos] == x
 
     def lookup_known(self, x):
         """ids of the labels in x the index knows, sorted by id; unknown labels are dropped (the reference's
@@ -159,6 +195,69 @@ def to_idx(X, ent_to_idx, rel_to_idx):
     p = ri.lookup(X[:, 1], "relations")
     o = ei.lookup(X[:, 2], "entities")
     return np.stack([s, p, o], axis=1)
+
+
+def _hash_fixed_width(a):
+    """64-bit FNV-1a-style hash of every element of a 1-D fixed-width str / bytes array, eight bytes at a time."""
+    unit = 4 if a.dtype.kind == "U" else 1
+    chars = a.dtype.itemsize // unit
+    if chars == 0:
+        return np.zeros(a.shape[0], np.uint64)
+    if (chars * unit) % 8:  # pad the items to whole 8-byte words (zero padding, like the dtype's own)
+        chars += (8 - (chars * unit) % 8) // unit
+        a = a.astype("%s%d" % ("<U" if unit == 4 else "S", chars))
+    lanes = np.ascontiguousarray(a).view(np.uint64).reshape(a.shape[0], -1)
+    h = np.full(a.shape[0], 0xCBF29CE484222325, np.uint64)
+    for j in range(lanes.shape[1]):
+        h ^= lanes[:, j]
+        h *= np.uint64(0x100000001B3)
+        h ^= h >> np.uint64(29)
+    return h
+
+
+def _sorted_factorize(values):
+    """(sorted unique labels, code of every value in that order) == np.unique(values, return_inverse=True).
+
+    Fixed-width str / bytes arrays (what np.loadtxt / np.array of labels give) take a hashing pass instead of a sort of
+    all n labels: 64-bit hashes -> integer factorisation -> one representative label per hash, VERIFIED against every
+    input (a hash collision falls back to the sort) -> only the distinct labels are sorted."""
+    values = np.asarray(values)
+    n = values.shape[0]
+    if values.ndim == 1 and values.dtype.kind in "US" and n > 0:
+        h = _hash_fixed_width(values)
+        try:
+            import pandas as pd
+            codes, _ = pd.factorize(h)  # codes in order of first appearance
+        except ImportError:
+            _, first_u, inv = np.unique(h, return_index=True, return_inverse=True)
+            order_fa = np.argsort(first_u, kind="stable")  # re-number in order of first appearance
+            renum = np.empty(order_fa.shape[0], np.int64)
+            renum[order_fa] = np.arange(order_fa.shape[0])
+            codes = renum[inv.reshape(-1)]
+        n_codes = int(codes.max()) + 1
+        first = np.empty(n_codes, np.int64)
+        first[codes[::-1]] = np.arange(n - 1, -1, -1)  # the last write wins: position of the first occurrence
+        reps = values[first]
+        if np.array_equal(reps[codes], values):  # no two different labels share a hash
+            order = np.argsort(reps, kind="stable")
+            rank = np.empty(n_codes, np.int64)
+            rank[order] = np.arange(n_codes)
+            return reps[order], rank[codes]
+    uniq, inv = np.unique(values, return_inverse=True)
+    return uniq, inv.reshape(-1)
+
+
+def index_training_triples(X):
+    """create_mappings + to_idx of a training set (evaluation/protocol.py:429-445, :662-723) in one pass: the ids are the
+    positions of the labels in np.unique (sorted) order, exactly as the reference assigns them, but every label is
+    hashed once instead of being binary-searched (or looked up through np.vectorize(dict.get)) after a full sort.
+    Returns (entity LabelIndex, relation LabelIndex, ids [n,3] int32)."""
+    X = np.asarray(X)
+    n = X.shape[0]
+    ent_labels, ent_codes = _sorted_factorize(np.concatenate((X[:, 0], X[:, 2])))
+    rel_labels, rel_codes = _sorted_factorize(X[:, 1])
+    Xi = np.stack([ent_codes[:n], rel_codes, ent_codes[n:]], axis=1).astype(np.int32)
+    return LabelIndex(ent_labels), LabelIndex(rel_labels), Xi
 
 
 def _index_from_dict(d):
@@ -356,8 +455,7 @@ class EmbeddingModel:
             raise ValueError("Invalid size for input X. Expected (n,3):  got {}".format(X.shape))
         if focusE_numeric_edge_values is not None:
             raise NotImplementedError("FocusE edge weights are outside the B200 hot-path scope")
-        ent_index = LabelIndex(np.unique(np.concatenate((X[:, 0], X[:, 2]))))
-        rel_index = LabelIndex(np.unique(X[:, 1]))
+        ent_index, rel_index, Xi = index_training_triples(X)
         # engine_params['resume']: continue from the current parameters, the saved sparse-optimizer state and the
         # global step (no reference counterpart: its optimizers are re-created every batch)
         self._resume = bool(self.engine_params.get("resume", False)) and self.is_fitted
@@ -367,7 +465,6 @@ class EmbeddingModel:
             self._resume = False
             raise ValueError("resume needs the entities and relations the model was fitted on")
         self._ent_index, self._rel_index = ent_index, rel_index
-        Xi = to_idx(X, self._ent_index, self._rel_index)
         self.early_stopping_params = early_stopping_params
         try:
             self._fit_idx(Xi, len(self._ent_index), len(self._rel_index), early_stopping=early_stopping)

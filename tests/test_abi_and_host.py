@@ -395,3 +395,94 @@ def test_data_format_helpers():
     assert t.shape == (4, 3) and t[3].tolist() == ["virginica", "has_petal_width", "1.8"]
     with pytest.raises(Exception, match="not in data frame headers"):
         dataframe_to_triples(df, [("species", "has_sepal_length", "abc")])
+
+
+def test_index_training_triples_equals_unique_plus_to_idx():
+    """fit()'s one-pass id mapping == the reference's create_mappings + to_idx (sorted-unique ids,
+    evaluation/protocol.py:429-445, :662-723) for ASCII, non-ASCII, numeric-looking and object-dtype labels."""
+    from emgraph_b200 import models
+    from oracle import kge_oracle as ko
+    rng = np.random.default_rng(0)
+    pools = [np.array(["e%03d" % i for i in range(50)]), np.array(["é", "z", "a", "Ω", "ab", "aB", "10", "9", "", " x"]),
+             np.array(["Q1", "Q10", "Q2", "q1", "P31"], dtype=object)]
+    for pool in pools:
+        for n in (0, 1, 7, 500):
+            X = np.stack([pool[rng.integers(0, len(pool), n)], pool[rng.integers(0, min(3, len(pool)), n)],
+                          pool[rng.integers(0, len(pool), n)]], 1) if n else np.zeros((0, 3), dtype=pool.dtype)
+            ei, ri, Xi = models.index_training_triples(X)
+            r2i, e2i = ko.create_mappings(X) if n else ({}, {})
+            assert list(ei.labels) == list(e2i.keys()) and list(ri.labels) == list(r2i.keys())
+            if n:
+                np.testing.assert_array_equal(Xi, ko.to_idx(X, e2i, r2i))
+                np.testing.assert_array_equal(Xi, models.to_idx(X, ei, ri))  # later lookups agree with the training ids
+            assert Xi.dtype == np.int32 and Xi.shape == (n, 3)
+
+
+def test_sorted_factorize_is_exact(monkeypatch):
+    """The hashing pass behind fit()'s id mapping equals np.unique(return_inverse=True) -- for odd item widths, bytes,
+    empty strings, labels differing only in the last character, with and without pandas -- and a hash collision
+    (forced here) falls back to the sort instead of merging two labels."""
+    import builtins
+    from emgraph_b200 import models
+    rng = np.random.default_rng(2)
+    cases = [np.array(["a", "b", "", "ab", "ba", "aa"])[rng.integers(0, 6, 300)],
+             np.array(["entity_%d" % i for i in range(1000)])[rng.integers(0, 1000, 5000)],       # width 10: padded to 12 chars
+             np.array([b"x1", b"x2", b"y"])[rng.integers(0, 3, 50)],
+             np.array(["Ωmega", "omega", "Omega", "omegb"])[rng.integers(0, 4, 64)],
+             np.array(["%033d" % i for i in range(40)])[rng.integers(0, 40, 200)]]
+    for v in cases:
+        u, inv = np.unique(v, return_inverse=True)
+        for no_pandas in (False, True):
+            if no_pandas:
+                real_import = builtins.__import__
+                monkeypatch.setattr(builtins, "__import__", lambda name, *a, **k: (_ for _ in ()).throw(ImportError(name))
+                                    if name == "pandas" else real_import(name, *a, **k))
+            labels, codes = models._sorted_factorize(v)
+            if no_pandas:
+                monkeypatch.undo()
+            np.testing.assert_array_equal(labels, u)
+            np.testing.assert_array_equal(codes, inv.reshape(-1))
+            assert labels.dtype == v.dtype
+    monkeypatch.setattr(models, "_hash_fixed_width", lambda a: np.zeros(a.shape[0], np.uint64))  # everything collides
+    labels, codes = models._sorted_factorize(cases[1])
+    u, inv = np.unique(cases[1], return_inverse=True)
+    np.testing.assert_array_equal(labels, u)
+    np.testing.assert_array_equal(codes, inv.reshape(-1))
+
+
+def test_label_index_bulk_lookup_is_exact(monkeypatch):
+    """LabelIndex.lookup / contains on large inputs take the hashed path: same ids as the binary search, unseen labels
+    still raise (evaluation/protocol.py:684-701), wider / narrower query dtypes and truncation look-alikes included."""
+    import builtins
+    from emgraph_b200 import models
+    rng = np.random.default_rng(3)
+    labels = np.unique(np.array(["ent%05d" % i for i in rng.integers(0, 90000, 30000)]))
+    idx = models.LabelIndex(labels)
+    q = labels[rng.integers(0, len(labels), 20000)]
+    want = np.searchsorted(labels, q).astype(np.int32)
+    for no_pandas in (False, True):
+        idx._hash = None
+        if no_pandas:
+            real_import = builtins.__import__
+            monkeypatch.setattr(builtins, "__import__", lambda name, *a, **k: (_ for _ in ()).throw(ImportError(name))
+                                if name == "pandas" else real_import(name, *a, **k))
+        got = idx.lookup(q, "entities")
+        wide = idx.lookup(q.astype("<U20"), "entities")
+        has = idx.contains(np.concatenate([q[:5000], np.array(["ent00000x", "zzz", ""])]))
+        if no_pandas:
+            monkeypatch.undo()
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(wide, want)
+        assert has[:5000].all() and not has[5000:].any()
+    assert idx._hashed() is not None
+    bad = q.astype("<U20").copy()
+    bad[7] = q[7] + "-longer-than-any-label"  # truncating to the index's width would look like a known label
+    with pytest.raises(ValueError, match="not present in the training set"):
+        idx.lookup(bad, "entities")
+    with pytest.raises(ValueError):
+        idx.lookup(np.concatenate([q, np.array(["nope"])]), "entities")
+    # small inputs and non-string labels keep the binary search
+    np.testing.assert_array_equal(idx.lookup(q[:10], "entities"), want[:10])
+    ints = models.LabelIndex(np.arange(0, 100000, 3))
+    np.testing.assert_array_equal(ints.lookup(np.arange(0, 30000, 3), "entities"), np.arange(10000))
+    assert ints._hashed() is None
