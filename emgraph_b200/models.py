@@ -117,6 +117,8 @@ class LabelIndex:
         inputs are hashed (one pass, then an integer table) instead of binary-searched label by label; the label
         comparison at the end makes the result exact either way."""
         n = len(self.labels)
+        if self.labels.dtype.kind in "US":
+            x = _fixed_width(x)
         if x.size >= self._HASH_MIN and x.ndim == 1 and x.dtype.kind == self.labels.dtype.kind and x.dtype.kind in "US":
             tab = self._hashed()
             if tab is not None:
@@ -197,6 +199,21 @@ def to_idx(X, ent_to_idx, rel_to_idx):
     return np.stack([s, p, o], axis=1)
 
 
+def _fixed_width(x):
+    """Object arrays whose elements are all `str` (what `DataFrame.values` / `read_csv` hand over) as fixed-width
+    unicode arrays: same labels, same (code-point) order, but sortable and hashable without Python-level comparisons.
+    Anything else is returned unchanged."""
+    if x.dtype != object or x.size == 0:
+        return x
+    try:
+        import pandas as pd
+        if pd.api.types.infer_dtype(x.reshape(-1), skipna=False) == "string":
+            return x.astype(str)
+    except ImportError:
+        pass
+    return x
+
+
 def _hash_fixed_width(a):
     """64-bit FNV-1a-style hash of every element of a 1-D fixed-width str / bytes array, eight bytes at a time."""
     unit = 4 if a.dtype.kind == "U" else 1
@@ -254,8 +271,8 @@ def index_training_triples(X):
     Returns (entity LabelIndex, relation LabelIndex, ids [n,3] int32)."""
     X = np.asarray(X)
     n = X.shape[0]
-    ent_labels, ent_codes = _sorted_factorize(np.concatenate((X[:, 0], X[:, 2])))
-    rel_labels, rel_codes = _sorted_factorize(X[:, 1])
+    ent_labels, ent_codes = _sorted_factorize(_fixed_width(np.concatenate((X[:, 0], X[:, 2]))))
+    rel_labels, rel_codes = _sorted_factorize(_fixed_width(X[:, 1]))
     Xi = np.stack([ent_codes[:n], rel_codes, ent_codes[n:]], axis=1).astype(np.int32)
     return LabelIndex(ent_labels), LabelIndex(rel_labels), Xi
 

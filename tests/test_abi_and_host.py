@@ -486,3 +486,25 @@ def test_label_index_bulk_lookup_is_exact(monkeypatch):
     ints = models.LabelIndex(np.arange(0, 100000, 3))
     np.testing.assert_array_equal(ints.lookup(np.arange(0, 30000, 3), "entities"), np.arange(10000))
     assert ints._hashed() is None
+
+
+def test_object_dtype_labels_take_the_fast_path_and_keep_their_ids():
+    """Labels arriving as object arrays of str (DataFrame.values) map to the same ids as their fixed-width twins; a
+    mixed-type object array keeps numpy's own ordering (no silent stringification)."""
+    from emgraph_b200 import models
+    rng = np.random.default_rng(5)
+    pool = np.array(["n%04d" % i for i in range(3000)])
+    Xs = np.stack([pool[rng.integers(0, 3000, 9000)], pool[rng.integers(0, 7, 9000)], pool[rng.integers(0, 3000, 9000)]], 1)
+    Xo = Xs.astype(object)
+    e1, r1, i1 = models.index_training_triples(Xs)
+    e2, r2, i2 = models.index_training_triples(Xo)
+    np.testing.assert_array_equal(i1, i2)
+    assert list(e1.labels) == list(e2.labels) and e2.labels.dtype.kind == "U"
+    np.testing.assert_array_equal(models.to_idx(Xo, e2, r2), i1)          # object queries against a str index
+    np.testing.assert_array_equal(models.to_idx(Xo[:20], e1, r1), i1[:20])  # small inputs too
+    assert e2.contains(np.array(["n0001", "nope"], dtype=object)).tolist() == [True, False]
+    with pytest.raises(ValueError):
+        models.to_idx(np.array([["n0001", "n0000", "unknown"]], dtype=object), e2, r2)
+    mixed = np.array([[1, "r", 2], [2, "r", 10]], dtype=object)
+    e3, _, i3 = models.index_training_triples(mixed)
+    assert list(e3.labels) == [1, 2, 10] and i3[:, 2].tolist() == [1, 2]
