@@ -8,7 +8,7 @@ import warnings
 import numpy as np
 
 from .engine import to_dev_i32
-from .models import EmbeddingModel, create_mappings, to_idx  # noqa: F401  (re-exported like the reference)
+from .models import EmbeddingModel, _fixed_width, _sorted_factorize, create_mappings, to_idx  # noqa: F401  (re-exported like the reference)
 
 from .model_selection import select_best_model_ranking  # noqa: E402,F401  (evaluation/__init__.py:6 exports it)
 
@@ -206,6 +206,13 @@ _SPLIT_ERROR = ("Cannot create a test split of the desired size. Some entities w
                 "Set allow_duplication=True,{}remove filter on test predicates or set test_size to a smaller value.")
 
 
+def _label_codes(labels):
+    """Dense integer code per label (equal labels, equal codes) -- the hashing pass of fit()'s id mapping."""
+    if labels.shape[0] == 0:
+        return np.zeros(0, np.int64)
+    return _sorted_factorize(_fixed_width(np.asarray(labels)))[1]
+
+
 def _split_shuffled(X, test_size, seed, allow_duplication, filtered_test_predicates):
     """evaluation/protocol.py:24-181: walk the candidates in one random order and move a triple to the test set
     whenever every entity and relation of it still occurs elsewhere.  Integer ids and count arrays instead of
@@ -218,9 +225,9 @@ def _split_shuffled(X, test_size, seed, allow_duplication, filtered_test_predica
     else:
         cand, fixed_train = X, None
     n = cand.shape[0]
-    _, ent_inv = np.unique(np.concatenate([cand[:, 0], cand[:, 2]]), return_inverse=True)
+    ent_inv = _label_codes(np.concatenate([cand[:, 0], cand[:, 2]]))
     s_id, o_id = ent_inv[:n], ent_inv[n:]
-    _, p_id = np.unique(cand[:, 1], return_inverse=True)
+    p_id = _label_codes(cand[:, 1])
     ent_left = np.bincount(ent_inv).tolist()  # occurrences still in the training part
     rel_left = np.bincount(p_id).tolist()
     s_id, o_id, p_id = s_id.tolist(), o_id.tolist(), p_id.tolist()
@@ -255,9 +262,8 @@ def _split_random_search(X, test_size, seed, allow_duplication, filtered_test_pr
     RandomState(seed); a drawn triple joins the test set when its subject, object and relation each still occur
     more than once in their own role."""
     rnd = np.random.RandomState(seed)
-    _, s_id, s_left = np.unique(X[:, 0], return_inverse=True, return_counts=True)
-    _, o_id, o_left = np.unique(X[:, 2], return_inverse=True, return_counts=True)
-    _, p_id, p_left = np.unique(X[:, 1], return_inverse=True, return_counts=True)
+    s_id, o_id, p_id = _label_codes(X[:, 0]), _label_codes(X[:, 2]), _label_codes(X[:, 1])
+    s_left, o_left, p_left = np.bincount(s_id), np.bincount(o_id), np.bincount(p_id)
     pool = np.where(np.isin(X[:, 1], filtered_test_predicates))[0] if filtered_test_predicates else np.arange(len(X))
     chosen = []
     taken = set()
