@@ -233,3 +233,13 @@ def test_entities_subset_host_logic(fake):
                 np.testing.assert_array_equal(got, exp, err_msg="%s %s %s" % (side, strat, filt is not None))
     # the full sweep afterwards uses the un-permuted filter again
     np.testing.assert_array_equal(evaluate_performance(X[sel], m, filter_triples=X), ko.ranks("DistMult", k, ent, rel, tri[sel], tri))
+
+
+def test_gpu_tier_property_tests_also_hold_on_the_stand_in_engine(fake, tmp_path):
+    """The bodies of the GPU-tier end-to-end tests (toy-graph fit/predict vs the emulation, re-fit determinism, resume)
+    are host logic over the engine: run them here too, so a Python-level mistake in them shows up in the CPU tier."""
+    import test_zzz_gpu_reference_properties as gpu_tests
+    for case in TOY_CASES:
+        gpu_tests.test_fit_predict_toy_graph(None, *case)
+    gpu_tests.test_refit_is_deterministic(None)
+    gpu_tests.test_resume_equals_training_in_one_go(None, tmp_path)
