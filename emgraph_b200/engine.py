@@ -192,6 +192,17 @@ class Engine:
                    stage, grad_tails, neg_entities)
         return a
 
+    def train_args_update(self, a: KgeTrainArgs, *, pos, step, lr, loss_out, flags) -> KgeTrainArgs:
+        """Refresh the per-step fields of an argument block built by train_args (everything else of a fit() loop --
+        tables, state, hyper-parameters -- stays what it was): the block is then byte-identical to a freshly built one
+        (tests/test_abi_and_host.py::test_cached_argument_block_equals_a_fresh_one) at a fraction of the host cost."""
+        _chk_i32(pos, "pos")
+        a.pos, a.n_pos = pos.data_ptr(), pos.shape[0]
+        a.step, a.lr, a.flags = step, lr, flags
+        a.loss_out = loss_out.data_ptr()
+        a._keep_step = (pos, loss_out)  # keep this step's tensors alive for the duration of the call
+        return a
+
     # kernels per step: emit, fwd_bwd, loss-reduce, radix sort (CUB onesweep: histogram + exclusive
     # sum + ceil(bits/8) passes), reduce_apply, span_apply
     @staticmethod

@@ -675,10 +675,23 @@ class EmbeddingModel:
         (a 1-element fp32 device tensor; default f['loss_dev'])."""
         f = self._fit
         f["step"] += 1
+        loss_out = f["loss_dev"] if loss_out is None else loss_out
+        if keep_subj is None and not self._neg_batch:
+            # the common step: only the batch, the counters and the loss slot change -> refresh the cached block
+            kw = self._step_kw()
+            a = f.get("args_dev")
+            if a is not None and f.get("args_dev_side") == side:
+                f["eng"].train_args_update(a, pos=pos_dev, step=f["step"], lr=kw["lr"], loss_out=loss_out, flags=kw["flags"])
+            else:
+                a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=pos_dev, loss_out=loss_out, side=_lib.TRAIN_SIDE_IDS[side],
+                                        step=f["step"], **kw, **f["st"], **f["neg"])
+                f["args_dev"], f["args_dev_side"] = a, side
+            f["eng"].train_step(a)
+            return
         neg = f["neg"]
         if self._neg_batch:  # corruptions drawn from the batch's own entities (evaluation/protocol.py:620-641)
             neg = dict(neg_entities=torch.unique(pos_dev[:, [0, 2]]).to(torch.int32))
-        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=pos_dev, loss_out=f["loss_dev"] if loss_out is None else loss_out,
+        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=pos_dev, loss_out=loss_out,
                                 keep_subj=keep_subj,
                                 side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **self._step_kw(keep_subj), **f["st"], **neg)
         f["eng"].train_step(a)

@@ -33,6 +33,10 @@ class FakeEngine:
         kw.setdefault("seed", 0)
         return SimpleNamespace(**kw)
 
+    def train_args_update(self, a, *, pos, step, lr, loss_out, flags):
+        a.pos, a.step, a.lr, a.loss_out, a.flags = pos, step, lr, loss_out, flags
+        return a
+
     def _state(self, a, which):
         m, v = getattr(a, which + "_m", None), getattr(a, which + "_v", None)
         opt = _OPT[a.opt]

@@ -508,3 +508,46 @@ def test_object_dtype_labels_take_the_fast_path_and_keep_their_ids():
     mixed = np.array([[1, "r", 2], [2, "r", 10]], dtype=object)
     e3, _, i3 = models.index_training_triples(mixed)
     assert list(e3.labels) == [1, 2, 10] and i3[:, 2].tolist() == [1, 2]
+
+
+def test_cached_argument_block_equals_a_fresh_one(monkeypatch):
+    """fit()'s device-batch step refreshes a cached kge_train_args block instead of rebuilding it: what reaches the C ABI
+    must be byte-identical to a freshly built block at every step -- changing batch (pointer, size), step counter,
+    learning rate (sgd schedule), loss slot and flags (pipelining toggled) included."""
+    import torch
+    from emgraph_b200 import _lib as L
+    from emgraph_b200 import engine as en
+    from emgraph_b200 import models
+    monkeypatch.setattr(en, "_chk_f32", lambda t, n: None)
+    monkeypatch.setattr(en, "_chk_i32", lambda t, n: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    seen = []
+
+    class Recorder(en.Engine):
+        tdev = torch.device("cpu")
+
+        def __init__(self):
+            self.launches = 0
+
+        def train_step(self, a):
+            seen.append(bytes(a))
+
+    eng = Recorder()
+    monkeypatch.setattr(models, "get_engine", lambda device=None: eng)
+    m = models.ComplEx(k=8, eta=3, epochs=1, batches_count=4, seed=5, optimizer="adam", optimizer_params={"lr": 1e-3},
+                       embedding_model_params={"negative_corruption_entities": 17})
+    f = m._fit_prepare(40, 3)
+    X = torch.zeros(100, 3, dtype=torch.int32)
+    slots = torch.zeros(6, dtype=torch.float32)
+    for i, (lo, hi) in enumerate([(0, 30), (30, 60), (60, 90), (90, 100), (0, 30), (30, 60)]):
+        if i == 2:
+            f["kw"]["lr"] = 5e-4
+        if i == 4:
+            f["pipeline"] = False
+        pos, out = X[lo:hi], slots[i:i + 1]
+        m._fit_step_device(pos, loss_out=out)
+        fresh = eng.train_args(ent=f["ent"], rel=f["rel"], pos=pos, loss_out=out, side=0, step=f["step"], **m._step_kw(), **f["st"], **f["neg"])
+        assert seen[-1] == bytes(fresh), i
+        assert fresh.step == i + 1 and fresh.n_pos == hi - lo and bool(fresh.flags & L.F_PIPELINE) == (i < 4)
+    assert len(set(seen)) == 6
