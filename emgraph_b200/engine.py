@@ -196,8 +196,9 @@ class Engine:
         """Refresh the per-step fields of an argument block built by train_args (everything else of a fit() loop --
         tables, state, hyper-parameters -- stays what it was): the block is then byte-identical to a freshly built one
         (tests/test_abi_and_host.py::test_cached_argument_block_equals_a_fresh_one) at a fraction of the host cost."""
-        _chk_i32(pos, "pos")
-        a.pos, a.n_pos = pos.data_ptr(), pos.shape[0]
+        if pos is not None:  # host-buffer steps pass pos=None: the batch arrives with the call, which sets n_pos
+            _chk_i32(pos, "pos")
+            a.pos, a.n_pos = pos.data_ptr(), pos.shape[0]
         a.step, a.lr, a.flags = step, lr, flags
         a.loss_out = loss_out.data_ptr()
         a._keep_step = (pos, loss_out)  # keep this step's tensors alive for the duration of the call

@@ -696,16 +696,32 @@ class EmbeddingModel:
                                 side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **self._step_kw(keep_subj), **f["st"], **neg)
         f["eng"].train_step(a)
 
+    def _host_step_args(self, pos_host, side, keep_subj):
+        """Argument block of a host-buffer step (pos=None: the library copies the batch in itself); the common step
+        refreshes a cached block, like _fit_step_device."""
+        f = self._fit
+        if keep_subj is None and not self._neg_batch:
+            kw = self._step_kw()
+            a = f.get("args_host")
+            if a is not None and f.get("args_host_side") == side:
+                return f["eng"].train_args_update(a, pos=None, step=f["step"], lr=kw["lr"], loss_out=f["loss_dev"], flags=kw["flags"])
+            a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"], n_pos=pos_host.shape[0],
+                                    side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **kw, **f["st"], **f["neg"])
+            f["args_host"], f["args_host_side"] = a, side
+            return a
+        neg = f["neg"]
+        if self._neg_batch:
+            neg = dict(neg_entities=to_dev_i32(np.unique(pos_host[:, [0, 2]].numpy()), f["eng"].tdev))
+        return f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"], keep_subj=keep_subj,
+                                   n_pos=pos_host.shape[0], side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **self._step_kw(keep_subj),
+                                   **f["st"], **neg)
+
     def _fit_step_host(self, pos_host, side="s,o", keep_subj=None):
         """One optimisation step fed like the reference feeds it: the batch comes from (pinned) host
         memory and the batch loss is read back (models/EmbeddingModel.py:1329-1337, :1421)."""
         f = self._fit
         f["step"] += 1
-        neg = f["neg"]
-        if self._neg_batch:
-            neg = dict(neg_entities=to_dev_i32(np.unique(pos_host[:, [0, 2]].numpy()), f["eng"].tdev))
-        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"], keep_subj=keep_subj,
-                                n_pos=pos_host.shape[0], side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **self._step_kw(keep_subj), **f["st"], **neg)
+        a = self._host_step_args(pos_host, side, keep_subj)
         f["eng"].train_step_host(a, pos_host, f["loss_host"])
         return float(f["loss_host"][0])
 
@@ -716,11 +732,7 @@ class EmbeddingModel:
         _fit_host_flush() returns the loss of the last step."""
         f = self._fit
         f["step"] += 1
-        neg = f["neg"]
-        if self._neg_batch:
-            neg = dict(neg_entities=to_dev_i32(np.unique(pos_host[:, [0, 2]].numpy()), f["eng"].tdev))
-        a = f["eng"].train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"], keep_subj=keep_subj,
-                                n_pos=pos_host.shape[0], side=_lib.TRAIN_SIDE_IDS[side], step=f["step"], **self._step_kw(keep_subj), **f["st"], **neg)
+        a = self._host_step_args(pos_host, side, keep_subj)  # the library copies the block during the call
         ring = f.setdefault("loss_ring", torch.zeros(4, dtype=torch.float32).pin_memory())
         i = f["step"] % 4
         ticket = f["eng"].train_step_host_async(a, pos_host, ring[i:i + 1])

@@ -551,3 +551,50 @@ def test_cached_argument_block_equals_a_fresh_one(monkeypatch):
         assert seen[-1] == bytes(fresh), i
         assert fresh.step == i + 1 and fresh.n_pos == hi - lo and bool(fresh.flags & L.F_PIPELINE) == (i < 4)
     assert len(set(seen)) == 6
+
+
+def test_cached_host_step_argument_block_equals_a_fresh_one(monkeypatch):
+    """Same guarantee for the host-buffer steps (synchronous and ticketed): the refreshed cached block is byte-identical
+    to a freshly built one at every call."""
+    import torch
+    from emgraph_b200 import engine as en
+    from emgraph_b200 import models
+    monkeypatch.setattr(en, "_chk_f32", lambda t, n: None)
+    monkeypatch.setattr(en, "_chk_i32", lambda t, n: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    seen = []
+
+    class Recorder(en.Engine):
+        tdev = torch.device("cpu")
+
+        def __init__(self):
+            self.launches = 0
+
+        def train_step_host(self, a, pos_host, loss_host):
+            a.n_pos = pos_host.shape[0]
+            seen.append(bytes(a))
+
+        def train_step_host_async(self, a, pos_host, loss_slot):
+            a.n_pos = pos_host.shape[0]
+            seen.append(bytes(a))
+            return len(seen) % 4
+
+        def train_host_wait(self, ticket):
+            pass
+
+    eng = Recorder()
+    monkeypatch.setattr(models, "get_engine", lambda device=None: eng)
+    m = models.DistMult(k=8, eta=3, epochs=1, batches_count=4, seed=5, optimizer="momentum", optimizer_params={"lr": 1e-3, "momentum": 0.8})
+    f = m._fit_prepare(40, 3)
+    X = torch.zeros(100, 3, dtype=torch.int32)
+    for i, (lo, hi) in enumerate([(0, 30), (30, 60), (90, 100), (0, 30), (30, 60), (60, 90)]):
+        if i == 3:
+            f["kw"]["lr"] = 5e-4
+            f["pipeline"] = False
+        (m._fit_step_host if i % 2 else m._fit_step_host_pipelined)(X[lo:hi])
+        fresh = eng.train_args(ent=f["ent"], rel=f["rel"], pos=None, loss_out=f["loss_dev"], n_pos=hi - lo, side=0, step=f["step"],
+                               **m._step_kw(), **f["st"], **f["neg"])
+        fresh.n_pos = hi - lo
+        assert seen[-1] == bytes(fresh), i
+    assert len(set(seen)) == 6
