@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkge_b200.so")
 
 KGE_MAX_SHARDS = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 MODEL_IDS = {"TransE": 0, "TransE_L2": 1, "DistMult": 2, "ComplEx": 3, "HolE": 4}
 LOSS_IDS = {"pairwise": 0, "nll": 1, "multiclass_nll": 2, "absolute_margin": 3, "self_adversarial": 4}
@@ -52,6 +52,7 @@ class KgeTrainArgs(C.Structure):
         ("reg_p", C.c_int32), ("reg_lambda_ent", C.c_float), ("reg_lambda_rel", C.c_float),
         ("neg_entities", C.c_void_p), ("neg_entities_n", C.c_int64),
         ("non_linearity", C.c_int32),
+        ("k_model", C.c_int32),
     ]
 
 
@@ -74,6 +75,9 @@ SYMBOLS = {
     "kge_train_emit": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P]),
     "kge_train_fwd_bwd": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P]),
     "kge_train_apply": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _L, C.POINTER(KgeTable), _L, _L, _P]),
+    "kge_train_partial": (_I, [_P, C.POINTER(KgeTrainArgs), _L, _L, _P, _P]),
+    "kge_train_backward": (_I, [_P, C.POINTER(KgeTrainArgs), _L, _L, _P, _P]),
+    "kge_train_reduce": (_I, [_P, C.POINTER(KgeTrainArgs), _P]),
     "kge_train_step_host": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P, _P]),
     "kge_train_step_host_async": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P, _P, C.POINTER(_I)]),
     "kge_train_host_wait": (_I, [_P, _I]),
@@ -83,6 +87,7 @@ SYMBOLS = {
     "kge_filter_clear": (_I, [_P]),
     "kge_filter_size_sync": (_L, [_P]),
     "kge_rank_counts": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _L, _P, _L, _I, _I, _I, _I, _P, _P]),
+    "kge_rank_counts_rows": (_I, [_P, _I, _I, _L, _P, _L, _P, _P, _P, _L, _L, _P, _L, _I, _I, _I, _I, _P, _P]),
     "kge_rank_finalize": (_I, [_P, _P, _L, _I, _I, _I, _P, _P, _P]),
     "kge_rank_host": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _P]),
     "kge_dev_alloc": (_I, [_L, C.POINTER(_P)]),

@@ -91,6 +91,7 @@ struct kge_ctx {
     // read set i has finished (recorded by every single-GPU step), ev_pro[i] = emit + sort into set i done
     KgeBuf alt_repl, alt_keep, alt_ks_in, alt_ks_sorted;
     int    set_id = 0;
+    bool   dim_pipelined = false;  // the dimension-sharded step in progress ran its prologue on the side stream
     cudaEvent_t ev_set_free[2] = {nullptr, nullptr}, ev_pro_emit[2] = {nullptr, nullptr}, ev_pro_sorted[2] = {nullptr, nullptr};
     // owner-side slot selection (kge_train_select): count travels to the host behind an event
     // side stream of the single-GPU step (sort + loss reduction beside the forward/backward kernel)

@@ -1,0 +1,385 @@
+// Dimension-sharded ("column-parallel") training step for one NVSwitch domain (sm_100a).
+//
+// Every GPU holds a contiguous COLUMN slice of every embedding row (ent[E,Kc], rel[R,Kc], Kc = K/W, plus the
+// optimizer state of that slice) and processes the WHOLE global batch on its slice.  All four scoring functions
+// are sums over columns (TransE-L2: the square of the distance is), so the only cross-GPU coupling of a step is
+// one sum of (1+eta) floats per positive:
+//
+//   phase 1  kge_dim_partial_kernel   column-slice partial sums of the positive and its eta negatives
+//   ------   all-reduce(sum) of the partial sums over the ranks (4*(1+eta) bytes per positive; the host places it)
+//   phase 2  kge_dim_backward_kernel  scores from the totals -> loss, dL/dscore -> gradient rows of the slice
+//   then the single-GPU duplicate-row reduction + sparse optimizer runs unchanged on the slice (kge_train.cu).
+//
+// Against the row-sharded exchange (rows or folded queries travel: >= 2+2W rows of 4K bytes per positive) the
+// NVLink volume per positive drops from ~33 KiB to 260 bytes at K = 256, eta = 64, W = 8; every other byte of
+// the step stays in local HBM.  Corruptions, sort keys and the loss are replicated: every rank draws the same
+// Philox stream for the whole global batch and evaluates the same loss from the same totals.
+//
+// Rows are narrow here (Kc = 32 floats at W = 8), so one GROUP of GS lanes (8, 16 or 32) owns a positive and
+// a warp works on 32/GS positives at once; lanes of a group fetch the replacement ids of U negatives in one
+// load, and the loss terms of those U negatives are evaluated one per lane instead of redundantly.
+//
+// Replaces reference models/EmbeddingModel.py:614-822 (_get_model_loss) for a model whose table is split over
+// GPUs; the reference's only answer to large tables is host paging (models/EmbeddingModel.py:645-666, :1251-1281).
+#pragma once
+#include "kge_train_fwd.cuh"
+
+struct DimParams {
+    const float* ent;     // local column slice [E, K]
+    const float* rel;     // [R, K]
+    const int32_t* pos;   // [n,3] the global batch
+    const int32_t* repl;  // [eta*n] replacement of negative (j,i) at j*n+i
+    const uint8_t* keep;  // [eta*n] 1 = subject kept
+    int64_t n;            // positives of the global batch
+    int64_t i0, i1;       // positives handled by this launch
+    int eta, k, K, loss, nl;  // k: floats per half (complex) / per row of the local slice
+    float margin, scale, alpha;
+    // raw sums of the launch's positives, chunk-local layout with nc = i1 - i0:
+    //   [0,nc) positives | nc + j*nc + (i - i0) negative (j,i)
+    float* sums;
+    float* gbuf;        // gradient buffer of the whole batch (layout in kge_train_fwd.cuh)
+    float* loss_part;   // [n]
+    float* dbg_scores;  // optional [n*(1+eta)]
+};
+
+template <int GS>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int GS>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = GS / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// lane lg of a group owns vectors c = lg + GS*i (i < NCH) of 4 floats; columns past the end of the slice are 0
+template <int GS, int NCH, bool CPLX>
+__device__ __forceinline__ void grow_load(Row<4, NCH, CPLX>& r, const float* __restrict__ base, int lg, int nvec, int half) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = lg + GS * i;
+        if (c < nvec) {
+            ld_vec<4>(r.re[i], base + (size_t)c * 4);
+            if constexpr (CPLX) ld_vec<4>(r.im[i], base + half + (size_t)c * 4);
+        } else {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                r.re[i][v] = 0.f;
+                if constexpr (CPLX) r.im[i][v] = 0.f;
+            }
+        }
+    }
+}
+template <int GS, int NCH, bool CPLX>
+__device__ __forceinline__ void grow_store(float* __restrict__ base, const Row<4, NCH, CPLX>& r, int lg, int nvec, int half) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = lg + GS * i;
+        if (c < nvec) {
+            st_vec<4>(base + (size_t)c * 4, r.re[i]);
+            if constexpr (CPLX) st_vec<4>(base + half + (size_t)c * 4, r.im[i]);
+        }
+    }
+}
+template <int NCH, bool CPLX>
+__device__ __forceinline__ void row_select(Row<4, NCH, CPLX>& d, bool first, const Row<4, NCH, CPLX>& a, const Row<4, NCH, CPLX>& b) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            d.re[i][v] = first ? a.re[i][v] : b.re[i][v];
+            if constexpr (CPLX) d.im[i][v] = first ? a.im[i][v] : b.im[i][v];
+        }
+}
+
+#define KGE_DIM_THREADS 256
+
+// ---------------------------------------------------------------------------------------------- phase 1
+template <int MODEL, int GS, int NCH, int U>
+__global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_partial_kernel(DimParams P) {
+    using A = Algebra<MODEL, 4, NCH>;
+    using R = typename A::R;
+    static_assert(U <= GS, "the lanes of a group fetch the ids of one round of U negatives");
+    const int lane = threadIdx.x & 31, lg = lane & (GS - 1), gbase = lane & ~(GS - 1);
+    const int64_t nc = P.i1 - P.i0;
+    const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GS;
+    const bool valid = grp < nc;
+    const int64_t il = valid ? grp : nc - 1;  // surplus groups shadow the last positive (warp stays convergent)
+    const int64_t i = P.i0 + il, n = P.n;
+    const int K = P.K, eta = P.eta;
+    const int half = A::CPLX ? P.k : 0;
+    const int nvec = (A::CPLX ? P.k : K) / 4;
+    float msk[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) msk[c] = 1.f;  // rows are zero-filled past the end: no mask needed
+
+    R Qo, Qs;
+    {
+        R s, p, o;
+        const int32_t si = P.pos[3 * i + 0], pi = P.pos[3 * i + 1], oi = P.pos[3 * i + 2];
+        grow_load<GS>(s, P.ent + (size_t)si * K, lg, nvec, half);
+        grow_load<GS>(p, P.rel + (size_t)pi * K, lg, nvec, half);
+        grow_load<GS>(o, P.ent + (size_t)oi * K, lg, nvec, half);
+        A::queries(s, p, o, Qo, Qs);
+        const float sp = group_sum<GS>(A::partial(Qo, o, msk));
+        if (valid && lg == 0) P.sums[il] = sp;
+    }
+    float* out = P.sums + nc + il;
+    for (int j0 = 0; j0 < eta; j0 += U) {
+        // one id / side load per group serves U negatives
+        int my_idx = 0, my_keep = 0;
+        if (lg < U) {
+            const int64_t q = (int64_t)min(j0 + lg, eta - 1) * n + i;
+            my_idx = P.repl[q];
+            my_keep = P.keep[q];
+        }
+        R r[U];
+        bool kp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = __shfl_sync(0xffffffffu, my_idx, gbase + u);
+            kp[u] = __shfl_sync(0xffffffffu, my_keep, gbase + u) != 0;
+            grow_load<GS>(r[u], P.ent + (size_t)idx * K, lg, nvec, half);
+        }
+        float pv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            R Q;
+            row_select(Q, kp[u], Qo, Qs);
+            pv[u] = A::partial(Q, r[u], msk);
+        }
+#pragma unroll
+        for (int o2 = GS / 2; o2 > 0; o2 >>= 1)
+#pragma unroll
+            for (int u = 0; u < U; ++u) pv[u] += __shfl_xor_sync(0xffffffffu, pv[u], o2);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (valid && j0 + u < eta && lg == u) out[(int64_t)(j0 + u) * nc] = pv[u];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- phase 2
+template <int MODEL, int GS, int NCH, int U>
+__global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_backward_kernel(DimParams P) {
+    using A = Algebra<MODEL, 4, NCH>;
+    using R = typename A::R;
+    constexpr bool TRANSE = A::TRANSE;
+    constexpr int V = 4;  // ROW_FOR
+    const int lane = threadIdx.x & 31, lg = lane & (GS - 1), gbase = lane & ~(GS - 1);
+    const int64_t nc = P.i1 - P.i0;
+    const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GS;
+    const bool valid = grp < nc;
+    const int64_t il = valid ? grp : nc - 1;
+    const int64_t i = P.i0 + il, n = P.n;
+    const int K = P.K, eta = P.eta, loss = P.loss, nl = P.nl;
+    const int half = A::CPLX ? P.k : 0;
+    const int nvec = (A::CPLX ? P.k : K) / 4;
+    const float margin = P.margin, alpha = P.alpha, scale = P.scale;
+    const float* tot = P.sums + nc + il;  // negative (j,i) at tot[j*nc]
+
+    R s, p, o, Qo, Qs, AccO, AccS;
+    const int32_t si = P.pos[3 * i + 0], pi = P.pos[3 * i + 1], oi = P.pos[3 * i + 2];
+    grow_load<GS>(s, P.ent + (size_t)si * K, lg, nvec, half);
+    grow_load<GS>(p, P.rel + (size_t)pi * K, lg, nvec, half);
+    grow_load<GS>(o, P.ent + (size_t)oi * K, lg, nvec, half);
+    A::queries(s, p, o, Qo, Qs);
+    row_zero(AccO);
+    row_zero(AccS);
+
+    // the loss sees nl(score); dL/draw = dL/dnl * nl'(raw)  (models/EmbeddingModel.py:679-689, :801-812)
+    const float spos_raw = A::finish(P.sums[il], scale);
+    const float dpos_nl = apply_nl_grad(nl, spos_raw);
+    const float spos = apply_nl(nl, spos_raw);
+    const float cpos = clip75(spos);
+    const bool pos_in = (spos >= -75.f) && (spos <= 75.f);
+
+    float loss_acc = 0.f, wsum = 0.f;  // lane-partial until the group sums below
+    float zinv = 0.f, amax = 0.f, lbar = 0.f;
+    const bool two_pass = loss_two_pass(loss);
+    if (two_pass) {
+        // softmax statistics over the eta totals of this positive (losses/nll_multiclass.py:70-81,
+        // losses/self_adversarial.py:97-110); lanes stride over j
+        if (loss == KGE_LOSS_MULTICLASS_NLL) {
+            float zpart = 0.f;
+            for (int j = lg; j < eta; j += GS) zpart += expf(clip75(apply_nl(nl, A::finish(tot[(int64_t)j * nc], scale))));
+            const float pe = expf(cpos);
+            const float z = group_sum<GS>(zpart) + pe;
+            zinv = 1.f / z;
+            loss_acc = (lg == 0) ? -logf(pe / z) : 0.f;
+        } else {
+            float mx = -INFINITY;
+            for (int j = lg; j < eta; j += GS) mx = fmaxf(mx, alpha * apply_nl(nl, A::finish(tot[(int64_t)j * nc], scale)));
+            amax = group_max<GS>(mx);
+            float zpart = 0.f, lpart = 0.f;
+            for (int j = lg; j < eta; j += GS) {
+                const float st = apply_nl(nl, A::finish(tot[(int64_t)j * nc], scale));
+                const float e = expf(alpha * st - amax);
+                zpart += e;
+                lpart += e * log_sigmoid(-st - margin);
+            }
+            zinv = 1.f / group_sum<GS>(zpart);
+            lbar = group_sum<GS>(lpart) * zinv;
+            loss_acc = (lg == 0) ? -log_sigmoid(margin + spos) - lbar : 0.f;
+        }
+    }
+
+    float* coef = gbuf_coef(P.gbuf, n, K);
+    uint8_t* keep_out = gbuf_keep(P.gbuf, eta, n, K);
+    for (int j0 = 0; j0 < eta; j0 += U) {
+        // lane lg < U owns negative j0+lg of this round: id, side, total -> dL/dscore, coefficient, loss term
+        int my_idx = 0, my_keep = 0;
+        float my_w = 0.f, my_sn = 0.f;
+        if (lg < U) {
+            const int j = min(j0 + lg, eta - 1);
+            const bool real = j0 + lg < eta;
+            const int64_t q = (int64_t)j * n + i;
+            my_idx = P.repl[q];
+            my_keep = P.keep[q];
+            const float sn = A::finish(tot[(int64_t)j * nc], scale);
+            const float st = apply_nl(nl, sn);
+            const float dn = apply_nl_grad(nl, sn);
+            float w;
+            if (loss == KGE_LOSS_MULTICLASS_NLL) {
+                const bool in = (st >= -75.f) && (st <= 75.f);
+                w = in ? expf(st) * zinv * dn : 0.f;
+            } else if (loss == KGE_LOSS_SELF_ADVERSARIAL) {
+                const float pj = expf(alpha * st - amax) * zinv;
+                w = pj * (sigmoidf(st + margin) - alpha * (log_sigmoid(-st - margin) - lbar)) * dn;
+            } else if (loss == KGE_LOSS_PAIRWISE || loss == KGE_LOSS_ABSOLUTE_MARGIN) {
+                // losses/pairwise.py:69, absolute_margin.py:69 ; tf.maximum passes the gradient when t >= 0
+                const float tt = loss == KGE_LOSS_PAIRWISE ? margin - spos + st : margin + st;
+                w = (tt >= 0.f) ? 1.f : 0.f;
+                if (real) {
+                    loss_acc += fmaxf(tt, 0.f);
+                    wsum += w;
+                }
+                w *= dn;
+            } else {
+                // losses/nll.py:55-59 : log(1+exp(clip(neg)))
+                const float e = expf(clip75(st));
+                const bool in = (st >= -75.f) && (st <= 75.f);
+                if (real) loss_acc += logf(1.f + e);
+                w = in ? e / (1.f + e) * dn : 0.f;
+            }
+            if (!real) w = 0.f;
+            my_w = w;
+            my_sn = sn;
+            if (valid && real) {
+                coef[q] = A::coefficient(w, sn, scale);
+                keep_out[q] = (uint8_t)my_keep;
+                if (P.dbg_scores != nullptr) P.dbg_scores[n + q] = st;
+            }
+        }
+        R r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = __shfl_sync(0xffffffffu, my_idx, gbase + u);
+            grow_load<GS>(r[u], P.ent + (size_t)idx * K, lg, nvec, half);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool kp = __shfl_sync(0xffffffffu, my_keep, gbase + u) != 0;
+            const float w = __shfl_sync(0xffffffffu, my_w, gbase + u);
+            const float wO = kp ? w : 0.f, wS = kp ? 0.f : w;
+            if constexpr (TRANSE) {
+                const float sn = __shfl_sync(0xffffffffu, my_sn, gbase + u);
+                float inv = 0.f;
+                if constexpr (MODEL == 1) inv = sn != 0.f ? 1.f / (-sn) : 0.f;
+                const float sg = kp ? 1.f : -1.f;
+                ROW_FOR(c, v) {
+                    const float q = kp ? Qo.re[c][v] : Qs.re[c][v];
+                    const float uu = sg * (q - r[u].re[c][v]);
+                    float g;  // d f / d u
+                    if constexpr (MODEL == 0) g = (uu > 0.f) ? -1.f : ((uu < 0.f) ? 1.f : 0.f);
+                    else g = -uu * inv;
+                    AccO.re[c][v] = fmaf(wO, g, AccO.re[c][v]);
+                    AccS.re[c][v] = fmaf(wS, g, AccS.re[c][v]);
+                }
+            } else {
+                const float a = wO * scale, b = wS * scale;
+                ROW_FOR(c, v) {
+                    AccO.re[c][v] = fmaf(a, r[u].re[c][v], AccO.re[c][v]);
+                    AccS.re[c][v] = fmaf(b, r[u].re[c][v], AccS.re[c][v]);
+                    if constexpr (A::CPLX) {
+                        AccO.im[c][v] = fmaf(a, r[u].im[c][v], AccO.im[c][v]);
+                        AccS.im[c][v] = fmaf(b, r[u].im[c][v], AccS.im[c][v]);
+                    }
+                }
+            }
+        }
+    }
+    loss_acc = group_sum<GS>(loss_acc);
+    wsum = group_sum<GS>(wsum);
+
+    float wpos;
+    if (loss == KGE_LOSS_PAIRWISE) {
+        wpos = -wsum;
+    } else if (loss == KGE_LOSS_NLL) {
+        // positives are tiled eta times (models/EmbeddingModel.py:724-729)
+        const float e = expf(-cpos);
+        loss_acc += (float)eta * logf(1.f + e);
+        wpos = pos_in ? -(float)eta * (e / (1.f + e)) : 0.f;
+    } else if (loss == KGE_LOSS_ABSOLUTE_MARGIN) {
+        loss_acc -= (float)eta * spos;
+        wpos = -(float)eta;
+    } else if (loss == KGE_LOSS_SELF_ADVERSARIAL) {
+        wpos = -sigmoidf(-(margin + spos));
+    } else {
+        wpos = pos_in ? -(1.f - expf(cpos) * zinv) : 0.f;
+    }
+    wpos *= dpos_nl;
+    if (!valid) return;
+
+    float* GB = P.gbuf;
+    grow_store<GS>(GB + (size_t)(3 * n + i) * K, Qo, lg, nvec, half);
+    grow_store<GS>(GB + (size_t)(4 * n + i) * K, Qs, lg, nvec, half);
+    {
+        R gs, gp, go;
+        A::backward_pos(Qo, o, wpos, spos_raw, scale, go, AccO);
+        A::fold(s, p, o, AccO, AccS, gs, gp, go);
+        grow_store<GS>(GB + (size_t)i * K, gs, lg, nvec, half);
+        grow_store<GS>(GB + (size_t)(n + i) * K, go, lg, nvec, half);
+        grow_store<GS>(GB + (size_t)(2 * n + i) * K, gp, lg, nvec, half);
+    }
+    if (lg == 0) {
+        P.loss_part[i] = loss_acc;
+        if (P.dbg_scores != nullptr) P.dbg_scores[i] = spos;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- launch
+template <int MODEL, int GS, int NCH, int U>
+static int launch_dim_one(int phase, const DimParams& P, cudaStream_t st) {
+    const int64_t nc = P.i1 - P.i0;
+    const int gpb = KGE_DIM_THREADS / GS;
+    dim3 grid((unsigned)((nc + gpb - 1) / gpb)), block(KGE_DIM_THREADS);
+    if (phase == 1) kge_dim_partial_kernel<MODEL, GS, NCH, U><<<grid, block, 0, st>>>(P);
+    else kge_dim_backward_kernel<MODEL, GS, NCH, U><<<grid, block, 0, st>>>(P);
+    KGE_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// group size / chunks per lane from the vectors per half of the local slice
+template <int MODEL>
+static int launch_dim_model(int phase, const DimParams& P, cudaStream_t st) {
+    constexpr bool C = (MODEL == 3);
+    const int width = C ? P.k : P.K;
+    KGE_REQUIRE(width % 4 == 0 && P.K % 4 == 0, "kge_train (dimension-sharded): the local slice needs a multiple of 4 columns per half, got %d", width);
+    const int nvec = width / 4;
+    if (nvec <= 8) return launch_dim_one<MODEL, 8, 1, (C ? 4 : 8)>(phase, P, st);
+    if (nvec <= 16) return launch_dim_one<MODEL, 16, 1, (C ? 4 : 8)>(phase, P, st);
+    if (nvec <= 32) return launch_dim_one<MODEL, 32, 1, (C ? 4 : 8)>(phase, P, st);
+    if (nvec <= 64) return launch_dim_one<MODEL, 32, 2, (C ? 2 : 4)>(phase, P, st);
+    if (nvec <= 128) return launch_dim_one<MODEL, 32, 4, (C ? 1 : 2)>(phase, P, st);
+    kge_set_error("kge_train (dimension-sharded): local slice of %d columns per half is too wide (max 512)", width);
+    return -1;
+}
+
+// one translation unit per model (parallel compilation): kge_dim_m{0,1,2,3}.cu
+int kge_launch_dim_m0(int phase, const DimParams& P, cudaStream_t st);
+int kge_launch_dim_m1(int phase, const DimParams& P, cudaStream_t st);
+int kge_launch_dim_m2(int phase, const DimParams& P, cudaStream_t st);
+int kge_launch_dim_m3(int phase, const DimParams& P, cudaStream_t st);

@@ -116,6 +116,8 @@ struct PrepParams {
     TableView ent;
     const float* rel;
     const int32_t* test;
+    const float* s_rows;  // optional [T,K]: subject / object rows of the test triples, supplied by the caller (the
+    const float* o_rows;  // table is sharded and the owners contributed them); NULL: read through `ent`
     int64_t T;
     int filtered;
     int nl;  // KGE_NL_*
@@ -135,9 +137,9 @@ __global__ void kge_rank_prepare_kernel(PrepParams P) {
     if (t >= P.T) return;
     const int K = P.ent.K, k = P.k, model = P.model;
     const int32_t si = P.test[3 * t], pi = P.test[3 * t + 1], oi = P.test[3 * t + 2];
-    const float* s = table_row(P.ent, si);
+    const float* s = P.s_rows != nullptr ? P.s_rows + (size_t)t * K : table_row(P.ent, si);
     const float* p = P.rel + (size_t)pi * K;
-    const float* o = table_row(P.ent, oi);
+    const float* o = P.o_rows != nullptr ? P.o_rows + (size_t)t * K : table_row(P.ent, oi);
     float* qo = P.q + (size_t)t * K;
     float* qs = P.q + (size_t)(P.T + t) * K;
     float acc = 0.f;
@@ -685,9 +687,37 @@ __global__ void kge_rank_finalize_kernel(const int32_t* __restrict__ counts, int
     }
 }
 
+static int rank_counts_impl(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
+                            const float* ent_local, int64_t row_begin, int64_t row_end, const int32_t* test, int64_t T,
+                            int side, int filtered, int use_tensor_cores, int non_linearity, int32_t* counts, void* stream,
+                            const float* s_rows, const float* o_rows);
+
 extern "C" int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
                                const float* ent_local, int64_t row_begin, int64_t row_end, const int32_t* test, int64_t T,
                                int side, int filtered, int use_tensor_cores, int non_linearity, int32_t* counts, void* stream) {
+    return rank_counts_impl(ctx, model, k, ent, rel, R, ent_local, row_begin, row_end, test, T, side, filtered, use_tensor_cores,
+                            non_linearity, counts, stream, nullptr, nullptr);
+}
+
+extern "C" int kge_rank_counts_rows(kge_ctx* ctx, int model, int k, int64_t E, const float* rel, int64_t R,
+                                    const float* s_rows, const float* o_rows, const float* ent_local, int64_t row_begin,
+                                    int64_t row_end, const int32_t* test, int64_t T, int side, int filtered,
+                                    int use_tensor_cores, int non_linearity, int32_t* counts, void* stream) {
+    KGE_REQUIRE(T == 0 || (s_rows != nullptr && o_rows != nullptr), "kge_rank_counts_rows: subject / object rows missing");
+    kge_table tb;
+    memset(&tb, 0, sizeof(tb));
+    tb.rows = E;
+    tb.rows_per_shard = E;
+    tb.n_shards = 1;
+    tb.K = model_row_width(model, k);
+    return rank_counts_impl(ctx, model, k, &tb, rel, R, ent_local, row_begin, row_end, test, T, side, filtered, use_tensor_cores,
+                            non_linearity, counts, stream, s_rows, o_rows);
+}
+
+static int rank_counts_impl(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
+                            const float* ent_local, int64_t row_begin, int64_t row_end, const int32_t* test, int64_t T,
+                            int side, int filtered, int use_tensor_cores, int non_linearity, int32_t* counts, void* stream,
+                            const float* s_rows, const float* o_rows) {
     KGE_REQUIRE(ctx != nullptr, "kge_rank_counts: null ctx");
     KGE_REQUIRE(non_linearity >= KGE_NL_LINEAR && non_linearity <= KGE_NL_SOFTPLUS, "Invalid non-linearity");
     KGE_REQUIRE(model >= KGE_TRANSE_L1 && model <= KGE_HOLE, "kge_rank_counts: unknown model %d", model);
@@ -716,6 +746,8 @@ extern "C" int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* 
     pp.ent = make_view(*ent);
     pp.rel = rel;
     pp.test = test;
+    pp.s_rows = s_rows;
+    pp.o_rows = o_rows;
     pp.T = T;
     pp.filtered = filtered && ctx->f_n_sp > 0;
     pp.nl = non_linearity;

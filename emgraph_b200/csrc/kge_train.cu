@@ -87,193 +87,11 @@ __global__ void kge_loss_reduce_kernel(const float* __restrict__ part, int64_t n
     if (threadIdx.x == 0) out[0] = (float)sm[0];
 }
 
-// ------------------------------------------------------------------------------------------------
-// segmented reduction of duplicate rows + sparse row-wise optimizer
-// ------------------------------------------------------------------------------------------------
-#define KGE_CH 16  // sorted slots per warp
+#include "kge_apply.cuh"
+#include "kge_dim.cuh"
 
-struct GradView {
-    float*  base[KGE_MAX_SHARDS];  // rank r's gradient buffer (local or peer mapping)
-    float*  tail[KGE_MAX_SHARDS];  // base to address rank r's [Qo|Qs|coef|keep] tail with the same offsets:
-                                   // == base[r], or a local all-gathered copy minus the head size
-    int64_t S;                     // slots per rank
-    int64_t n;                     // positives per rank
-    int     eta, K, n_ranks;
-};
+int kge_launch_apply_group(const ApplyParams& P, int tmode, cudaStream_t st);  // kge_apply_group.cu
 
-struct ApplyParams {
-    const uint64_t* ks;    // sorted (key << 32 | global slot id), global slot id = rank*S + local slot
-    int64_t n_keys;
-    GradView G;
-    TableView ent, ent_m, ent_v;
-    float *rel, *rel_m, *rel_v;
-    int64_t E, R;
-    int64_t row_begin, row_end;  // owned entity rows
-    int opt;
-    bool has_m, has_v;     // entity optimizer-state tables present
-    uint32_t flags;
-    float lr, lr_t, beta1, beta2, eps, momentum;
-    const KgeStepDyn* dyn;  // when set, lr_t is read from here (graph replay)
-    float* partial;        // [2*n_chunks][K]
-    int32_t* span_list;    // chunk ids that start a run crossing chunk borders (unordered)
-    int32_t* hub_list;     // the subset whose run covers more than KGE_SPAN_WARP_MAX chunks
-    int32_t* span_count;   // [2]: {#span heads, #hubs}, zeroed before the reduce kernel
-    float* dbg_grad_ent;
-    float* dbg_grad_rel;
-    // LP regulariser (regularizers/lp.py:81-113): lambda * sum |w|^p over the WHOLE tables, so every row has
-    // a gradient.  Rows touched by the batch get it added in the reduction; `touched` (one bit per sort
-    // key, entity ids then E + relation id) tells kge_reg_dense_kernel which rows are left.
-    int reg_p;
-    float reg_lambda_ent, reg_lambda_rel;
-    uint32_t* touched;
-};
-
-__device__ __forceinline__ float reg_grad1(float w, int p, float lam) {
-    if (p == 2) return 2.f * lam * w;
-    if (p == 1) return w > 0.f ? lam : (w < 0.f ? -lam : 0.f);
-    if (p == 3) return 3.f * lam * w * fabsf(w);
-    const float a = fabsf(w);
-    return a > 0.f ? lam * (float)p * powf(a, (float)(p - 1)) * (w > 0.f ? 1.f : -1.f) : 0.f;
-}
-__device__ __forceinline__ float reg_term1(float w, int p) {
-    const float a = fabsf(w);
-    return p == 2 ? a * a : (p == 1 ? a : (p == 3 ? a * a * a : powf(a, (float)p)));
-}
-
-struct SlotMeta {
-    const float* row;
-    float c;
-    int mode;  // 0: add row ; 1: replacement row of a negative, F(c, Q, r)
-};
-
-__device__ __forceinline__ SlotMeta decode_slot(const GradView& G, int32_t slot) {
-    int rr = 0;
-    int64_t t = slot;
-    if (G.n_ranks > 1) {
-        rr = (int)(t / G.S);
-        t -= (int64_t)rr * G.S;
-    }
-    float* base = G.base[rr];
-    float* tbase = G.tail[rr];
-    const int64_t n = G.n;
-    SlotMeta m;
-    m.c = 1.f;
-    m.mode = 0;
-    if (t < 2 * n) {
-        m.row = base + t * G.K;
-    } else if (t < 2 * n + (int64_t)G.eta * n) {
-        const int64_t q = t - 2 * n;
-        const int64_t i = q % n;
-        const float* coef = gbuf_coef(tbase, n, G.K);
-        const uint8_t* keep = gbuf_keep(tbase, G.eta, n, G.K);
-        m.c = coef[q];
-        m.row = tbase + ((keep[q] ? 3 : 4) * n + i) * G.K;
-        m.mode = 1;
-    } else {
-        m.row = base + (2 * n + (t - 2 * n - (int64_t)G.eta * n)) * G.K;
-    }
-    return m;
-}
-
-struct RowPtrs {
-    float *w, *m, *v;
-    bool is_rel, owned;
-    int64_t row;
-};
-
-__device__ __forceinline__ RowPtrs resolve_row(const ApplyParams& P, int32_t key) {
-    RowPtrs r;
-    r.is_rel = key >= P.E;
-    r.row = r.is_rel ? key - P.E : key;
-    r.owned = r.is_rel || (r.row >= P.row_begin && r.row < P.row_end);
-    r.m = r.v = nullptr;
-    const int K = P.ent.K;
-    if (r.is_rel) {
-        r.w = P.rel + (size_t)r.row * K;
-        if (P.rel_m) r.m = P.rel_m + (size_t)r.row * K;
-        if (P.rel_v) r.v = P.rel_v + (size_t)r.row * K;
-    } else {
-        r.w = table_row(P.ent, r.row);
-        if (P.has_m) r.m = table_row(P.ent_m, r.row);
-        if (P.has_v) r.v = table_row(P.ent_v, r.row);
-    }
-    return r;
-}
-
-// global (non-generic) vector load: the row pointers come out of shared memory, so the compiler cannot
-// prove their address space on its own
-template <int V>
-__device__ __forceinline__ void ldg_vec(float (&d)[V], const float* p) {
-    if constexpr (V == 4) {
-        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "l"(p));
-    } else {
-        asm volatile("ld.global.f32 %0, [%1];" : "=f"(d[0]) : "l"(p));
-    }
-}
-
-// contribution of one slot to V columns of the gradient; rc = current value of the row being updated.
-// Plain gradient rows (mode 0) carry c = 1, so the trilinear models need no branch at all.
-template <int V, int TMODE>
-__device__ __forceinline__ void add_slot(float (&g)[V], const float (&a)[V], float c, int mode, const float (&rc)[V]) {
-#pragma unroll
-    for (int x = 0; x < V; ++x) {
-        if (TMODE == 0) {
-            g[x] = fmaf(c, a[x], g[x]);  // DistMult / ComplEx / HolE: c*Q, or 1*row
-        } else if (mode == 0) {
-            g[x] += a[x];
-        } else if (TMODE == 1) {
-            float d = a[x] - rc[x];  // TransE L1: c*sign(Q-r)
-            g[x] += d > 0.f ? c : (d < 0.f ? -c : 0.f);
-        } else {
-            g[x] = fmaf(c, a[x] - rc[x], g[x]);  // TransE L2: c*(Q-r)
-        }
-    }
-}
-
-// pure-register optimizer math on V columns; m/v are the row's state (ignored when not needed)
-template <int V>
-__device__ __forceinline__ void opt_math(const ApplyParams& P, bool reset, const float (&g)[V], float (&wv)[V], float (&mv)[V], float (&vv)[V]) {
-    if (P.opt == KGE_OPT_ADAM) {
-        // Keras Adam (beta1 .9, beta2 .999, eps 1e-7): var -= lr_t * m / (sqrt(v) + eps)
-        const float lr_t = P.dyn != nullptr ? P.dyn->lr_t : P.lr_t;
-#pragma unroll
-        for (int x = 0; x < V; ++x) {
-            const float m0 = reset ? 0.f : mv[x], v0 = reset ? 0.f : vv[x];
-            mv[x] = P.beta1 * m0 + (1.f - P.beta1) * g[x];
-            vv[x] = P.beta2 * v0 + (1.f - P.beta2) * g[x] * g[x];
-            wv[x] = wv[x] - __fdividef(lr_t * mv[x], sqrtf(vv[x]) + P.eps);
-        }
-    } else if (P.opt == KGE_OPT_ADAGRAD) {
-        // Keras Adagrad: accumulator starts at 0.1; var -= lr * g / (sqrt(acc) + eps)
-#pragma unroll
-        for (int x = 0; x < V; ++x) {
-            mv[x] = (reset ? 0.1f : mv[x]) + g[x] * g[x];
-            wv[x] = wv[x] - __fdividef(P.lr * g[x], sqrtf(mv[x]) + P.eps);
-        }
-    } else if (P.opt == KGE_OPT_MOMENTUM) {
-        // Keras SGD momentum: vel = mu*vel - lr*g ; var += vel
-#pragma unroll
-        for (int x = 0; x < V; ++x) {
-            mv[x] = P.momentum * (reset ? 0.f : mv[x]) - P.lr * g[x];
-            wv[x] = wv[x] + mv[x];
-        }
-    } else {
-#pragma unroll
-        for (int x = 0; x < V; ++x) wv[x] = wv[x] - P.lr * g[x];
-    }
-}
-
-// gradient of the LP penalty on V columns of a row whose current values are w
-template <int V>
-__device__ __forceinline__ void reg_add(const ApplyParams& P, bool is_rel, float (&g)[V], const float (&w)[V]) {
-    if (P.reg_p <= 0) return;
-    const float lam = is_rel ? P.reg_lambda_rel : P.reg_lambda_ent;
-#pragma unroll
-    for (int x = 0; x < V; ++x) g[x] += reg_grad1(w[x], P.reg_p, lam);
-}
-__device__ __forceinline__ void mark_touched(const ApplyParams& P, int32_t key) {
-    if (P.touched != nullptr) atomicOr(P.touched + (key >> 5), 1u << (key & 31));
-}
 
 // Level 1: one warp per chunk of KGE_CH sorted slots.  NCA > 0: lanes own ALL their column vectors of
 // the row at once (K <= 128*NCA) so that the row's w/m/v and two slots' rows are in flight together;
@@ -934,7 +752,7 @@ static int fwd_bwd_impl(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, 
     P.margin = a->margin;
     P.alpha = a->alpha;
     P.nl = a->non_linearity;
-    P.scale = a->model == KGE_HOLE ? 2.0f / (float)a->k : 1.0f;
+    P.scale = a->model == KGE_HOLE ? 2.0f / (float)(a->k_model > 0 ? a->k_model : a->k) : 1.0f;
     P.gbuf = grad_buf;
     P.loss_part = ctx->loss_part.as<float>();
     P.dbg_scores = a->dbg_scores;
@@ -1134,7 +952,19 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
             kge_reduce_apply_staged_kernel<NCA><<<grid, block, smem, st>>>(P, l);
         }
     }
-    if (staged) {
+    bool grouped = false;
+    if constexpr (V == 4 && NCA == 1) {
+        // narrow rows: a group of 8 / 16 lanes per chunk instead of a warp (kge_apply_group.cu); KGE_APPLY_GROUP=0: A/B
+        static int grp_on = -1;
+        if (grp_on < 0) {
+            const char* e = getenv("KGE_APPLY_GROUP");
+            grp_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+        }
+        grouped = !staged && grp_on != 0 && P.ent.K <= 64;
+        if (grouped)
+            if (int rc = kge_launch_apply_group(P, tmode, st)) return rc;
+    }
+    if (staged || grouped) {
     } else if (tmode == 0) kge_reduce_apply_kernel<V, 0, NCA><<<grid, block, 0, st>>>(P);
     else if (tmode == 1) kge_reduce_apply_kernel<V, 1, NCA><<<grid, block, 0, st>>>(P);
     else kge_reduce_apply_kernel<V, 2, NCA><<<grid, block, 0, st>>>(P);
@@ -1695,6 +1525,118 @@ extern "C" int kge_train_step_host(kge_ctx* ctx, const kge_train_args* a, const 
     int ticket = 0;
     if (int rc = kge_train_step_host_async(ctx, a, pos_host, loss_host, stream, &ticket)) return rc;
     return kge_train_host_wait(ctx, ticket);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dimension-sharded multi-GPU step (kge_dim.cuh): the local engine of one rank.  a->ent / a->rel are this
+// rank's COLUMN slices ([E,Kc], [R,Kc], n_shards == 1, a->k = columns per half of the slice, a->k_model = the
+// whole model's k), a->pos the GLOBAL batch.  Per step:
+//   kge_train_partial (first chunk: corruptions + sort keys + radix sort, pipelined like the single-GPU step)
+//   -> the caller all-reduces the sums over the ranks -> kge_train_backward -> kge_train_reduce.
+// The positives may be cut into chunks [i_begin,i_end) so that the all-reduce of one chunk overlaps the
+// kernels of its neighbours; the chunks of a step must be submitted in order and cover [0,n_pos).
+// ------------------------------------------------------------------------------------------------
+static int dim_params(kge_ctx* ctx, const kge_train_args* a, int64_t i0, int64_t i1, float* sums, DimParams& P) {
+    KGE_REQUIRE(a->ent.n_shards == 1 && a->ent.shard[0] != nullptr, "kge_train (dimension-sharded): a->ent must be the local column slice");
+    KGE_REQUIRE(0 <= i0 && i0 < i1 && i1 <= a->n_pos, "kge_train (dimension-sharded): bad positive range [%lld,%lld) of %lld",
+                (long long)i0, (long long)i1, (long long)a->n_pos);
+    KGE_REQUIRE(sums != nullptr, "kge_train (dimension-sharded): sums missing");
+    KGE_REQUIRE(a->stage == nullptr && a->grad_tails == nullptr, "kge_train (dimension-sharded): the row-sharded exchange buffers do not apply");
+    P.ent = a->ent.shard[0];
+    P.rel = a->rel;
+    P.pos = a->pos;
+    P.repl = ctx->repl.as<int32_t>();
+    P.keep = ctx->keep.as<uint8_t>();
+    P.n = a->n_pos;
+    P.i0 = i0;
+    P.i1 = i1;
+    P.eta = a->eta;
+    P.k = a->k;
+    P.K = a->ent.K;
+    P.loss = a->loss;
+    P.nl = a->non_linearity;
+    P.margin = a->margin;
+    P.alpha = a->alpha;
+    P.scale = a->model == KGE_HOLE ? 2.0f / (float)(a->k_model > 0 ? a->k_model : a->k) : 1.0f;
+    P.sums = sums;
+    P.gbuf = ctx->grad_rows.as<float>();
+    P.loss_part = ctx->loss_part.as<float>();
+    P.dbg_scores = a->dbg_scores;
+    return 0;
+}
+
+static int launch_dim(int phase, const kge_train_args* a, const DimParams& P, cudaStream_t st) {
+    switch (a->model) {
+        case KGE_TRANSE_L1: return kge_launch_dim_m0(phase, P, st);
+        case KGE_TRANSE_L2: return kge_launch_dim_m1(phase, P, st);
+        case KGE_DISTMULT: return kge_launch_dim_m2(phase, P, st);
+        default: return kge_launch_dim_m3(phase, P, st);
+    }
+}
+
+extern "C" int kge_train_partial(kge_ctx* ctx, const kge_train_args* a, int64_t i_begin, int64_t i_end, float* sums, void* stream) {
+    KGE_REQUIRE(ctx != nullptr, "kge_train_partial: null ctx");
+    if (int rc = validate_train(a)) return rc;
+    if (a->n_pos == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (i_begin == 0) {
+        // a new step: corruptions + sort keys of the whole global batch, sort beside the phase kernels
+        const int64_t S = (int64_t)(3 + a->eta) * a->n_pos;
+        if (int rc = ensure_side_stream(ctx)) return rc;
+        ctx->dim_pipelined = (a->flags & KGE_F_PIPELINE) != 0 && pipeline_enabled();
+        if (ctx->dim_pipelined) {
+            if (int rc = pipeline_prologue(ctx, a, nullptr)) return rc;
+            KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_pro_emit[ctx->set_id], 0));
+        } else {
+            if (ctx->ks_in.reserve((size_t)S * 8)) return -2;
+            if (ctx->grad_rows.reserve((size_t)gbuf_floats(a->eta, a->n_pos, a->ent.K) * sizeof(float))) return -2;
+            // a step that was started but never reduced may still be sorting these keys on the side stream
+            KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_sorted, 0));
+            if (int rc = emit_impl(ctx, a, nullptr, ctx->ks_in.as<uint64_t>(), st, nullptr)) return rc;
+            KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, st));
+            KGE_CUDA_CHECK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+            if (int rc = sort_impl(ctx, a, ctx->ks_in.as<uint64_t>(), S, ctx->side)) return rc;
+            KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_sorted, ctx->side));
+        }
+    }
+    DimParams P;
+    if (int rc = dim_params(ctx, a, i_begin, i_end, sums, P)) return rc;
+    return launch_dim(1, a, P, st);
+}
+
+extern "C" int kge_train_backward(kge_ctx* ctx, const kge_train_args* a, int64_t i_begin, int64_t i_end, const float* sums, void* stream) {
+    KGE_REQUIRE(ctx != nullptr, "kge_train_backward: null ctx");
+    if (int rc = validate_train(a)) return rc;
+    if (a->n_pos == 0) return 0;
+    DimParams P;
+    if (int rc = dim_params(ctx, a, i_begin, i_end, const_cast<float*>(sums), P)) return rc;
+    return launch_dim(2, a, P, (cudaStream_t)stream);
+}
+
+extern "C" int kge_train_reduce(kge_ctx* ctx, const kge_train_args* a, void* stream) {
+    KGE_REQUIRE(ctx != nullptr, "kge_train_reduce: null ctx");
+    if (int rc = validate_train(a)) return rc;
+    KGE_REQUIRE(a->loss_out != nullptr, "kge_train_reduce: loss_out missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->n_pos == 0) {
+        KGE_CUDA_CHECK(cudaMemsetAsync(a->loss_out, 0, sizeof(float), st));
+        return 0;
+    }
+    KGE_REQUIRE(a->ent.n_shards == 1, "kge_train_reduce: a->ent must be the local column slice");
+    const int64_t S = (int64_t)(3 + a->eta) * a->n_pos;
+    kge_loss_reduce_kernel<<<1, 1024, 0, st>>>(ctx->loss_part.as<float>(), a->n_pos, a->loss_out);
+    KGE_CUDA_CHECK(cudaGetLastError());
+    kge_table g;
+    memset(&g, 0, sizeof(g));
+    g.shard[0] = ctx->grad_rows.as<float>();
+    g.rows = S;
+    g.rows_per_shard = S;
+    g.n_shards = 1;
+    g.K = a->ent.K;
+    KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->dim_pipelined ? ctx->ev_pro_sorted[ctx->set_id] : ctx->ev_sorted, 0));
+    if (int rc = reduce_impl(ctx, a, S, &g, 0, a->ent.rows, st, nullptr)) return rc;
+    if (int rc = reg_loss_finish(ctx, a, st)) return rc;
+    return mark_set_free(ctx, st);
 }
 
 extern "C" int kge_normalize_rows(kge_ctx* ctx, float* emb, int64_t rows, int K, void* stream) {

@@ -1,11 +1,14 @@
-"""One-process-per-GPU driver of the row-sharded path.
+"""One-process-per-GPU drivers of the multi-GPU path.
 
-The entity table (and its optimizer state) is split by contiguous row range over the ranks of one
-NVSwitch domain.  ``torch.distributed`` (NCCL) carries the plumbing -- the all-gather of sort keys,
-two tiny all-reduces that double as device-side barriers, the all-reduce of rank counts -- while the
-data path runs over peer memory: every rank maps its peers' shards and gradient buffers with CUDA IPC
-and the kernels read them directly (P2P loads over NVLink inside ``kge_fwd_bwd_kernel`` and
-``kge_reduce_apply_kernel``).
+``ShardedKGE`` (the product path): the embedding tables and their optimizer state are split by COLUMN range over
+the ranks of one NVSwitch domain and every rank processes the whole global batch on its slice; the only exchange
+of a training step is the sum of one partial score per scored triple (260 bytes per positive at eta = 64).  For
+ranking the column slices are transposed once into row-range shards (all-to-all) and every rank sweeps its rows;
+the per-shard rank counts are all-reduced.
+
+``RowShardedKGE`` (round-1 design, kept for A/B measurements): the entity table is split by contiguous row range;
+``torch.distributed`` (NCCL) carries the all-gather of sort keys and the barriers, the rows travel over peer
+memory (CUDA IPC mappings, owner-side push).
 
 Replaces the reference's host-paged "large graph" mode (models/EmbeddingModel.py:645-666,
 :1070-1097, :1251-1281), which is single-process and SGD-only.
@@ -136,8 +139,9 @@ def exchange_peers(eng, bufs, rank, world):
 # ------------------------------------------------------------------------------------------------
 # sharded training + ranking
 # ------------------------------------------------------------------------------------------------
-class ShardedKGE:
-    """Row-sharded parameters of one model on `world` GPUs; `train_step` and `rank` are collective."""
+class RowShardedKGE:
+    """Row-sharded parameters of one model on `world` GPUs (round-1 design, kept for A/B: the exchange is NVLink-volume
+    bound); `train_step` and `rank` are collective."""
 
     def __init__(self, model, k, eta, loss, optimizer, E, R, n_per_rank, *, lr=5e-4, margin=1.0, norm=1, seed=0,
                  init_ent=None, init_rel=None, device=None):
@@ -303,3 +307,247 @@ class ShardedKGE:
         parts = [torch.empty((self.rps, self.K), dtype=torch.float32, device=self.eng.tdev) for _ in range(self.world)]
         dist.all_gather(parts, self.ent.tensor.contiguous())
         return torch.cat(parts, 0)[: self.E].cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# dimension-sharded ("column-parallel") training, row-sharded ranking
+# ------------------------------------------------------------------------------------------------
+def dim_width(k: int, world: int) -> int:
+    """Columns per half of every rank's slice: ceil(k / world) rounded up to a multiple of 4 (128-bit vectors);
+    slices past the end of the model are zero columns, which every scoring function ignores and whose
+    gradient is exactly zero."""
+    return (-(-k // world) + 3) // 4 * 4
+
+
+def dim_range(k: int, world: int, rank: int):
+    """Logical columns [c0, c1) of the model's k that `rank` holds."""
+    kc = dim_width(k, world)
+    return min(k, rank * kc), min(k, (rank + 1) * kc)
+
+
+def slice_columns(full, model: str, k: int, world: int, rank: int):
+    """[rows, K] -> this rank's [rows, Kc] slice (ComplEx / HolE: the same column range of both halves, [re | im])."""
+    full = np.asarray(full)
+    kc = dim_width(k, world)
+    c0, c1 = dim_range(k, world, rank)
+    halves = 2 if model in ("ComplEx", "HolE") else 1
+    out = np.zeros((full.shape[0], halves * kc), full.dtype)
+    for h in range(halves):
+        out[:, h * kc:h * kc + (c1 - c0)] = full[:, h * k + c0:h * k + c1]
+    return out
+
+
+def merge_columns(parts, model: str, k: int):
+    """Inverse of slice_columns over all ranks: list of [rows, Kc] -> [rows, K]."""
+    world = len(parts)
+    kc = dim_width(k, world)
+    halves = 2 if model in ("ComplEx", "HolE") else 1
+    out = np.zeros((np.asarray(parts[0]).shape[0], halves * k), np.asarray(parts[0]).dtype)
+    for r, p in enumerate(parts):
+        c0, c1 = dim_range(k, world, r)
+        for h in range(halves):
+            out[:, h * k + c0:h * k + c1] = np.asarray(p)[:, h * kc:h * kc + (c1 - c0)]
+    return out
+
+
+def merge_index(model: str, k: int, world: int):
+    """Column index into the rank-major concatenation [rank0 slice | rank1 slice | ...] (each Kc wide) that yields the
+    model's [K] row: full[:, j] = cat[:, merge_index[j]]."""
+    kc = dim_width(k, world)
+    halves = 2 if model in ("ComplEx", "HolE") else 1
+    Kc = halves * kc
+    idx = np.empty(halves * k, np.int64)
+    for r in range(world):
+        c0, c1 = dim_range(k, world, r)
+        for h in range(halves):
+            idx[h * k + c0:h * k + c1] = r * Kc + h * kc + np.arange(c1 - c0)
+    return idx
+
+
+def chunk_bounds(n: int, chunks: int):
+    """Positive ranges of the `chunks` pieces a step is cut into (the all-reduce of one piece overlaps the kernels
+    of its neighbours); every piece non-empty."""
+    chunks = max(1, min(int(chunks), n))
+    base, extra = divmod(n, chunks)
+    out, lo = [], 0
+    for c in range(chunks):
+        hi = lo + base + (1 if c < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+class ShardedKGE:
+    """One model on `world` GPUs, tables split by column range; `train_step`, `rank`, `gather_*` are collective.
+
+    n_per_rank positives per rank and step (weak scaling: the global batch is the concatenation of the ranks'
+    batches in rank order; its corruption stream, loss and update are those of ONE GPU running that batch)."""
+
+    def __init__(self, model, k, eta, loss, optimizer, E, R, n_per_rank, *, lr=5e-4, margin=1.0, norm=1, seed=0,
+                 init_ent=None, init_rel=None, device=None, chunks=2, alpha=0.5, non_linearity="linear", side="s,o",
+                 optimizer_params=None, pipeline=True, group=None):
+        self.group = group
+        assert dist.is_initialized(), "init torch.distributed first"
+        self.rank_id, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.eng = get_engine(device)
+        eng = self.eng
+        self.model, self.k, self.eta, self.loss, self.optimizer = model, int(k), int(eta), loss, optimizer
+        self.E, self.R, self.n_local = int(E), int(R), int(n_per_rank)
+        self.n = self.n_local * self.world
+        self.K = internal_k(model, k)
+        self.mid = model_id(model, norm)
+        self.kc = dim_width(self.k, self.world)
+        self.Kc = internal_k(model, self.kc)
+        dev = eng.tdev
+
+        def local(full_or_fn, rows):
+            if full_or_fn is None:
+                return torch.zeros((rows, self.Kc), dtype=torch.float32, device=dev)
+            full = full_or_fn() if callable(full_or_fn) else full_or_fn
+            return torch.from_numpy(np.ascontiguousarray(slice_columns(full, model, self.k, self.world, self.rank_id), dtype=np.float32)).to(dev)
+
+        self.ent = local(init_ent, self.E)
+        self.rel = local(init_rel, self.R)
+        opt = _lib.OPT_IDS[optimizer]
+        self.state = {}
+        if opt == 0:
+            self.state = dict(ent_m=torch.zeros_like(self.ent), ent_v=torch.zeros_like(self.ent),
+                              rel_m=torch.zeros_like(self.rel), rel_v=torch.zeros_like(self.rel))
+        elif opt == 1:
+            self.state = dict(ent_m=torch.full_like(self.ent, 0.1), rel_m=torch.full_like(self.rel, 0.1))
+        elif opt == 2:
+            self.state = dict(ent_m=torch.zeros_like(self.ent), rel_m=torch.zeros_like(self.rel))
+        self.bounds = chunk_bounds(self.n, chunks)
+        self.sums = [torch.zeros((1 + self.eta) * (hi - lo), dtype=torch.float32, device=dev) for lo, hi in self.bounds]
+        self.pos_all = torch.empty((self.n, 3), dtype=torch.int32, device=dev)
+        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.step = 0
+        self.pipeline = bool(pipeline)
+        op = dict(optimizer_params or {})
+        self.kw = dict(model=self.mid, loss=_lib.LOSS_IDS[loss], opt=opt, k=self.kc, k_model=self.k, eta=self.eta, margin=float(margin),
+                       lr=float(op.get("lr", lr)), seed=int(seed), alpha=float(alpha), side=_lib.TRAIN_SIDE_IDS[side],
+                       non_linearity=_lib.NL_IDS[non_linearity], beta1=float(op.get("beta1", 0.9)), beta2=float(op.get("beta2", 0.999)),
+                       eps=float(op.get("epsilon", 1e-7)), momentum=float(op.get("momentum", 0.9)))
+        self.timing = False
+        self._marks = []
+        self._rows = None      # cached row-range shard [rps, K] of the current parameters (ranking)
+        self._rows_step = -1
+        self.rps = rows_per_shard(self.E, self.world)
+        self.row_begin, self.row_end = shard_range(self.E, self.world, self.rank_id)
+        self._merge_idx = torch.from_numpy(merge_index(model, self.k, self.world)).to(dev)
+        dist.barrier(group)
+
+    # ---------------------------------------------------------------- training
+    def gather_batch(self, pos_local):
+        """This rank's [n_local,3] positives -> the global batch (rank order) on every rank."""
+        assert pos_local.shape[0] == self.n_local
+        if self.world == 1:
+            return pos_local
+        dist.all_gather_into_tensor(self.pos_all, pos_local.contiguous(), group=self.group)
+        return self.pos_all
+
+    def make_args(self, pos_all, repl=None, keep_subj=None, flags=0, step=None, **dbg):
+        a = self.eng.train_args(ent=self.ent, rel=self.rel, pos=pos_all, loss_out=self.loss_dev,
+                                step=self.step if step is None else step, repl=repl, keep_subj=keep_subj, flags=flags,
+                                **self.kw, **self.state, **dbg)
+        return a
+
+    def train_step(self, pos_local, repl=None, keep_subj=None, flags=0, pos_is_global=False, **dbg):
+        """One optimisation step on the global batch.  pos_local: this rank's int32 [n_local,3] positives (device), or
+        the whole [n,3] global batch when pos_is_global (every rank must pass the same).  repl / keep_subj: optional
+        corruptions of the GLOBAL batch (parity input, identical on every rank), else the in-kernel Philox stream of
+        the global batch.  Returns the device scalar holding the batch loss (identical on every rank)."""
+        eng = self.eng
+        pos_all = pos_local if pos_is_global else self.gather_batch(pos_local)
+        assert pos_all.shape[0] == self.n
+        self.step += 1
+        # the side-stream prologue may only read batches that were resident before the previous step was submitted
+        pipe = self.pipeline and pos_is_global and repl is None and keep_subj is None
+        a = self.make_args(pos_all, repl, keep_subj, flags | (_lib.F_PIPELINE if pipe else 0), **dbg)
+        marks = []
+
+        def mark(name):
+            if self.timing:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
+        works = []
+        for c, (lo, hi) in enumerate(self.bounds):
+            eng.train_partial(a, self.sums[c], lo, hi)
+            mark("partial%d" % c)
+            works.append(dist.all_reduce(self.sums[c], group=self.group, async_op=True) if self.world > 1 else None)
+        for c, (lo, hi) in enumerate(self.bounds):
+            if works[c] is not None:
+                works[c].wait()
+            mark("allreduce%d" % c)
+            eng.train_backward(a, self.sums[c], lo, hi)
+            mark("backward%d" % c)
+        eng.train_reduce(a)
+        mark("reduce_apply")
+        if self.timing:
+            self._marks.append(marks)
+        return self.loss_dev
+
+    def phase_times(self):
+        """Average ms per phase over the steps run with self.timing = True (synchronises)."""
+        torch.cuda.synchronize()
+        acc = {}
+        for marks in self._marks:
+            for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+                acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1)
+        n = max(1, len(self._marks))
+        self._marks = []
+        return {k: v / n for k, v in acc.items()}
+
+    # ---------------------------------------------------------------- parameters
+    def _gather_cols(self, t):
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t.contiguous(), group=self.group)
+        return torch.cat(parts, 1).index_select(1, self._merge_idx)
+
+    def gather_entities(self):
+        """Full [E,K] table on every rank (host); for checks and checkpoints of small models."""
+        return self._gather_cols(self.ent).cpu().numpy()
+
+    def gather_relations(self, device=False):
+        full = self._gather_cols(self.rel)
+        return full if device else full.cpu().numpy()
+
+    def row_shard(self):
+        """[rps, K] full-width rows [row_begin,row_end) of the CURRENT parameters (zero rows past the end): the
+        column slices are transposed into row-range shards by one all-to-all; cached until the next step."""
+        if self._rows is not None and self._rows_step == self.step:
+            return self._rows
+        W, rps, Kc = self.world, self.rps, self.Kc
+        send = torch.zeros((W * rps, Kc), dtype=torch.float32, device=self.eng.tdev)
+        send[: self.E].copy_(self.ent)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        # recv[r*rps + t] = rank r's columns of my row t  ->  [rps, W*Kc]  ->  the model's column order
+        cat = recv.view(W, rps, Kc).permute(1, 0, 2).reshape(rps, W * Kc)
+        self._rows = cat.index_select(1, self._merge_idx).contiguous()
+        self._rows_step = self.step
+        return self._rows
+
+    # ---------------------------------------------------------------- ranking
+    def rank_counts(self, test_dev, *, side=0, filtered=False, use_tensor_cores=False, non_linearity=0):
+        """Per-shard sweep of this rank's rows + all-reduce of the [T,2,4] counters.  Collective."""
+        eng = self.eng
+        rows = self.row_shard()
+        rel = self.gather_relations(device=True)
+        T = test_dev.shape[0]
+        # subject / object rows of the test triples: every rank has their columns, one all-gather makes them whole
+        s_rows = self._gather_cols(self.ent.index_select(0, test_dev[:, 0].long()))
+        o_rows = self._gather_cols(self.ent.index_select(0, test_dev[:, 2].long()))
+        n_loc = self.row_end - self.row_begin
+        counts = eng.rank_counts_rows(self.mid, self.k, self.E, rel, s_rows, o_rows, rows[:max(n_loc, 1)], test_dev,
+                                      row_begin=self.row_begin, row_end=self.row_end, side=side, filtered=filtered,
+                                      use_tensor_cores=use_tensor_cores, non_linearity=non_linearity)
+        dist.all_reduce(counts, group=self.group)
+        return counts
+
+    def rank(self, test_dev, *, side=0, strategy=0, filtered=False, use_tensor_cores=False, non_linearity=0):
+        counts = self.rank_counts(test_dev, side=side, filtered=filtered, use_tensor_cores=use_tensor_cores, non_linearity=non_linearity)
+        return self.eng.rank_finalize(counts, side=side, strategy=strategy, filtered=filtered)

@@ -138,13 +138,14 @@ class Engine:
                    ent_m=None, ent_v=None, rel_m=None, rel_v=None, repl=None, keep_subj=None,
                    dbg_scores=None, dbg_grad_ent=None, dbg_grad_rel=None, stage=None, grad_tails=None,
                    grad_tail_stride=0, alpha=0.5, reg_p=0, reg_lambda_ent=0.0, reg_lambda_rel=0.0,
-                   neg_entities=None, neg_entities_n=0, non_linearity=0, n_pos=None) -> KgeTrainArgs:
+                   neg_entities=None, neg_entities_n=0, non_linearity=0, n_pos=None, k_model=0) -> KgeTrainArgs:
         """n_pos: batch size when `pos` is None (host-buffer step: the positives arrive with the call)."""
         a = KgeTrainArgs()
         a.model, a.loss, a.opt, a.side, a.flags = model, loss, opt, side, flags
         a.k, a.eta, a.margin, a.alpha = k, eta, margin, alpha
         a.reg_p, a.reg_lambda_ent, a.reg_lambda_rel = int(reg_p), float(reg_lambda_ent), float(reg_lambda_rel)
         a.non_linearity = int(non_linearity)
+        a.k_model = int(k_model)
         a.lr, a.beta1, a.beta2, a.eps, a.momentum = lr, beta1, beta2, eps, momentum
         a.seed, a.step, a.neg_index_base = seed, step, neg_index_base
         a.ent = ent if isinstance(ent, KgeTable) else make_table(ent)
@@ -277,6 +278,26 @@ class Engine:
                                        row_begin, row_end, _stream()))
         self.launches += self.launches_per_step(a.ent.rows + a.R) - 3
 
+    # dimension-sharded multi-GPU step (include/kge_b200.h: kge_train_partial / _backward / _reduce)
+    def train_partial(self, a: KgeTrainArgs, sums, i_begin: int = 0, i_end: int | None = None):
+        """Column-slice partial sums of positives [i_begin,i_end) and their negatives into `sums`
+        ((1+eta)*(i_end-i_begin) floats); i_begin == 0 also draws the step's corruptions and starts the key sort."""
+        _chk_f32(sums, "sums")
+        i_end = a.n_pos if i_end is None else i_end
+        assert sums.numel() >= (1 + a.eta) * (i_end - i_begin)
+        check(self.lib.kge_train_partial(self._h, C.byref(a), i_begin, i_end, _ptr(sums), _stream()))
+        self.launches += 1 + ((1 + self.launches_per_step(a.ent.rows + a.R) - 5) if i_begin == 0 else 0)
+
+    def train_backward(self, a: KgeTrainArgs, sums, i_begin: int = 0, i_end: int | None = None):
+        _chk_f32(sums, "sums")
+        i_end = a.n_pos if i_end is None else i_end
+        check(self.lib.kge_train_backward(self._h, C.byref(a), i_begin, i_end, _ptr(sums), _stream()))
+        self.launches += 1
+
+    def train_reduce(self, a: KgeTrainArgs):
+        check(self.lib.kge_train_reduce(self._h, C.byref(a), _stream()))
+        self.launches += 3
+
     def normalize_rows(self, emb):
         _chk_f32(emb, "emb")
         check(self.lib.kge_normalize_rows(self._h, _ptr(emb), emb.shape[0], emb.shape[1], _stream()))
@@ -312,6 +333,22 @@ class Engine:
         check(self.lib.kge_rank_counts(self._h, model, k, C.byref(tb), _ptr(rel), rel.shape[0], _ptr(ent_local),
                                        row_begin, row_end, _ptr(test), T, side, int(bool(filtered)),
                                        int(bool(use_tensor_cores)), int(non_linearity), _ptr(counts), _stream()))
+        self.launches += 3 if T else 0
+        return counts
+
+    def rank_counts_rows(self, model: int, k: int, E: int, rel, s_rows, o_rows, ent_local, test, *, row_begin, row_end, side=0,
+                         filtered=False, use_tensor_cores=False, non_linearity=0, counts=None):
+        """kge_rank_counts for a shard of a table this process cannot address: the test triples' subject / object rows
+        come from the caller ([T,K] each)."""
+        for t, nm in ((rel, "rel"), (s_rows, "s_rows"), (o_rows, "o_rows"), (ent_local, "ent_local")):
+            _chk_f32(t, nm)
+        _chk_i32(test, "test")
+        T = test.shape[0]
+        if counts is None:
+            counts = torch.empty((T, 2, 4), dtype=torch.int32, device=self.tdev)
+        check(self.lib.kge_rank_counts_rows(self._h, model, k, E, _ptr(rel), rel.shape[0], _ptr(s_rows), _ptr(o_rows), _ptr(ent_local),
+                                            row_begin, row_end, _ptr(test), T, side, int(bool(filtered)), int(bool(use_tensor_cores)),
+                                            int(non_linearity), _ptr(counts), _stream()))
         self.launches += 3 if T else 0
         return counts
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 5
+#define KGE_ABI_VERSION 6
 #define KGE_MAX_SHARDS 8
 
 typedef struct kge_ctx kge_ctx;
@@ -124,6 +124,9 @@ typedef struct kge_train_args {
     const int32_t* neg_entities;
     int64_t  neg_entities_n;
     int32_t  non_linearity; /* KGE_NL_*: applied to positive and negative scores before the loss */
+    /* dimension-sharded multi-GPU step: the tables passed are this rank's COLUMN slice, k the columns per half of the
+     * slice, k_model the k of the whole model (HolE's 2/k score scale, models/HolE.py:189); 0 = k */
+    int32_t  k_model;
 } kge_train_args;
 
 int         kge_abi_version(void);
@@ -186,6 +189,26 @@ int kge_train_push_rows(kge_ctx* ctx, const kge_train_args* a, const int32_t* ke
 int kge_train_select(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_all, int64_t n_keys,
                      int64_t row_begin, int64_t row_end, void* stream);
 
+/* Dimension-sharded ("column-parallel") multi-GPU step: the table of a model too large or too slow for one GPU is
+ * split by COLUMN range over the GPUs of one NVSwitch domain -- rank r holds ent[E, Kc], rel[R, Kc] and the
+ * optimizer state of columns [r*Kc, (r+1)*Kc) of every row (for ComplEx / HolE: the same range of the real and of
+ * the imaginary half, stored [re | im]) -- and every rank processes the WHOLE global batch on its slice.  Every
+ * scoring function of models/{TransE,DistMult,ComplEx,HolE}.py is a sum over columns (TransE norm 2: the squared
+ * distance is), so the ranks exchange one sum per scored triple and nothing else:
+ *   kge_train_partial   draws the corruptions of the global batch (same Philox stream on every rank), starts the
+ *                       sort of the slot keys, writes the slice's raw partial sums of positives [i_begin,i_end):
+ *                       sums[0,nc) positives, sums[nc + j*nc + (i-i_begin)] negative (j,i), nc = i_end-i_begin
+ *   (caller)            all-reduce(sum) of `sums` over the ranks (NCCL / peer memory); 4*(1+eta) bytes per positive
+ *   kge_train_backward  scores from the totals, loss terms, dL/dscore, gradient rows of the slice (ctx-owned buffer)
+ *   kge_train_reduce    batch loss (identical on every rank) -> a->loss_out; duplicate-row segmented reduction +
+ *                       sparse optimizer on the slice: the single-GPU kernels, unchanged
+ * Chunks [i_begin,i_end) of one step must be submitted in order and cover [0,n_pos); i_begin == 0 starts a step.
+ * a->ent.n_shards == 1, a->k = columns per half of the slice (a multiple of 4), a->k_model = the model's k.
+ * Replaces the reference's host-paged "large graph" mode (models/EmbeddingModel.py:645-666, :1070-1097, :1251-1281). */
+int kge_train_partial(kge_ctx* ctx, const kge_train_args* a, int64_t i_begin, int64_t i_end, float* sums, void* stream);
+int kge_train_backward(kge_ctx* ctx, const kge_train_args* a, int64_t i_begin, int64_t i_end, const float* sums, void* stream);
+int kge_train_reduce(kge_ctx* ctx, const kge_train_args* a, void* stream);
+
 /* Host-buffer form of kge_train_step: what a reference-side caller binds.  The reference feeds every
  * batch from host numpy through tf.data (models/EmbeddingModel.py:1329-1337, :1044-1111) and reads
  * the batch loss back with .numpy() (:1421).  pos_host [n_pos,3] int32 (pinned for an async copy) is
@@ -227,6 +250,13 @@ int kge_rank_counts(kge_ctx* ctx, int model, int k, const kge_table* ent, const 
                     const float* ent_local, int64_t row_begin, int64_t row_end,
                     const int32_t* test, int64_t T, int side, int filtered, int use_tensor_cores,
                     int non_linearity, int32_t* counts, void* stream);
+/* The same sweep for a table whose rows this process cannot address (column-sharded training, row-range shards for
+ * ranking): the caller supplies the subject and object rows of the test triples (s_rows, o_rows: [T,K] each, gathered
+ * from their owners) and E, the number of entities of the whole table; everything else as kge_rank_counts. */
+int kge_rank_counts_rows(kge_ctx* ctx, int model, int k, int64_t E, const float* rel, int64_t R,
+                         const float* s_rows, const float* o_rows, const float* ent_local, int64_t row_begin,
+                         int64_t row_end, const int32_t* test, int64_t T, int side, int filtered,
+                         int use_tensor_cores, int non_linearity, int32_t* counts, void* stream);
 /* ranks_out: [T,2] (col 0 subject, col 1 object) for KGE_RANK_S_O, else [T].
  * self_is_candidate: optional device uint8 [T,2] (col 0 subject, col 1 object): 0 when the test triple's own
  * entity was NOT among the swept candidates (entities_subset ranking, models/EmbeddingModel.py:1845-1857,

@@ -164,3 +164,106 @@ def push_step_bytes(eta, n, K, W, E, batches):
         worst = max(worst, 4 * K * int(np.count_nonzero(own(slots) != w)))
     tail = (2 * n * K + eta * n) * 4 + eta * n
     return dict(rows_in=worst, tails_in=tail * (W - 1), total=worst + tail * (W - 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# Dimension-sharded step (the exchange the product runs, emgraph_b200/csrc/kge_dim.cuh): rank r holds a COLUMN
+# slice of every row and sees the whole global batch; the ranks exchange one partial sum per scored triple.
+# Every reference scoring function is a sum over columns -- models/TransE.py:208-216 (norm 2: its square),
+# DistMult.py:201, ComplEx.py:288-298, HolE.py:189 -- so score = finish(sum_r raw_r) and
+# d score / d(local columns) = finish'(total) * d raw_r / d(local columns).
+# ------------------------------------------------------------------------------------------------
+def raw_partial(model, kc, e_s, e_p, e_o, norm=1, dtype=np.float64):
+    """Raw column-slice sum of one rank: sum|u| (TransE-1), sum u^2 (TransE-2), the trilinear form without HolE's 2/k."""
+    e_s, e_p, e_o = (np.asarray(x, dtype=dtype) for x in (e_s, e_p, e_o))
+    if model == "TransE":
+        u = e_s + e_p - e_o
+        return np.sum(np.abs(u), axis=1, dtype=dtype) if norm == 1 else np.sum(u * u, axis=1, dtype=dtype)
+    if model == "DistMult":
+        return np.sum(e_s * e_p * e_o, axis=1, dtype=dtype)
+    return ko.score_rows("ComplEx", kc, e_s, e_p, e_o, 1, dtype)
+
+
+def finish_total(model, k, total, norm=1):
+    """(score, d score / d total) from the all-reduced raw sum; k = the WHOLE model's k (HolE's scale)."""
+    total = np.asarray(total)
+    if model == "TransE":
+        if norm == 1:
+            return -total, -np.ones_like(total)
+        nrm = np.sqrt(total)
+        with np.errstate(divide="ignore"):
+            return -nrm, np.where(nrm != 0, -0.5 / nrm, 0.0)
+    c = 2.0 / k if model == "HolE" else 1.0
+    return c * total, np.full_like(total, c)
+
+
+def raw_partial_grads(model, kc, e_s, e_p, e_o, norm=1, dtype=np.float64):
+    """d raw_partial / d(e_s, e_p, e_o) on one rank's slice."""
+    e_s, e_p, e_o = (np.asarray(x, dtype=dtype) for x in (e_s, e_p, e_o))
+    if model == "TransE":
+        u = e_s + e_p - e_o
+        g = np.sign(u) if norm == 1 else 2.0 * u
+        return g, g, -g
+    return ko.score_grad_rows("DistMult" if model == "DistMult" else "ComplEx", kc, e_s, e_p, e_o, 1, dtype)
+
+
+def dim_slice(full, model, k, W, r):
+    """Rank r's column slice (emgraph_b200/distributed.py:slice_columns restated: ceil(k/W) rounded up to 4 columns per
+    half, zero columns past the end of the model)."""
+    kc = (-(-k // W) + 3) // 4 * 4
+    c0, c1 = min(k, r * kc), min(k, (r + 1) * kc)
+    halves = 2 if model in ("ComplEx", "HolE") else 1
+    out = np.zeros((np.asarray(full).shape[0], halves * kc), np.asarray(full).dtype)
+    for h in range(halves):
+        out[:, h * kc:h * kc + (c1 - c0)] = np.asarray(full)[:, h * k + c0:h * k + c1]
+    return out, kc, (c0, c1)
+
+
+def dim_sharded_step(model, k, loss, eta, ent, rel, pos, keep_subj, repl, W, margin=1.0, norm=1, alpha=0.5, nl="linear",
+                     dtype=np.float64):
+    """One step of the global batch on W column-sharded ranks.  Returns dict(loss, scores_pos, scores_neg, grad_ent,
+    grad_rel (merged to the model's column order), bytes_per_rank = all-reduce payload)."""
+    pos = np.asarray(pos).reshape(-1, 3)
+    neg = ko.corruptions_for_fit(pos, eta, keep_subj, repl)
+    halves = 2 if model in ("ComplEx", "HolE") else 1
+    sl = []
+    tot_p = np.zeros(pos.shape[0], dtype)
+    tot_n = np.zeros(neg.shape[0], dtype)
+    for r in range(W):  # phase 1 on every rank, then the all-reduce (sum in rank order)
+        e, kc, cr = dim_slice(ent, model, k, W, r)
+        rl, _, _ = dim_slice(rel, model, k, W, r)
+        sl.append((e, rl, kc, cr))
+        tot_p = tot_p + raw_partial(model, kc, e[pos[:, 0]], rl[pos[:, 1]], e[pos[:, 2]], norm, dtype)
+        tot_n = tot_n + raw_partial(model, kc, e[neg[:, 0]], rl[neg[:, 1]], e[neg[:, 2]], norm, dtype)
+    val, sp, sn, wp, wn = dim_loss_weights(model, k, loss, eta, tot_p, tot_n, margin, norm, alpha, nl, dtype)
+    g_ent = np.zeros(np.asarray(ent).shape, dtype)
+    g_rel = np.zeros(np.asarray(rel).shape, dtype)
+    for r, (e, rl, kc, (c0, c1)) in enumerate(sl):  # phase 2: gradient rows of the slice, no exchange
+        ge, gr = dim_slice_grads(model, kc, e, rl, pos, neg, wp, wn, norm, dtype)
+        for h in range(halves):
+            g_ent[:, h * k + c0:h * k + c1] = ge[:, h * kc:h * kc + (c1 - c0)]
+            g_rel[:, h * k + c0:h * k + c1] = gr[:, h * kc:h * kc + (c1 - c0)]
+    return dict(loss=val, scores_pos=sp, scores_neg=sn, grad_ent=g_ent, grad_rel=g_rel,
+                bytes_per_rank=4 * (1 + eta) * pos.shape[0])
+
+
+def dim_loss_weights(model, k, loss, eta, tot_p, tot_n, margin=1.0, norm=1, alpha=0.5, nl="linear", dtype=np.float64):
+    """From the all-reduced raw sums: (loss, scores_pos, scores_neg, dL/d total_pos, dL/d total_neg).  Evaluated
+    identically on every rank (losses/*.py through the oracle)."""
+    sp_raw, fp = finish_total(model, k, np.asarray(tot_p, dtype), norm)
+    sn_raw, fn = finish_total(model, k, np.asarray(tot_n, dtype), norm)
+    sp, gsp = ko.non_linearity(nl, sp_raw, dtype)
+    sn, gsn = ko.non_linearity(nl, sn_raw, dtype)
+    val, dpos, dneg = ko.loss_and_dscore(loss, sp, sn, eta, margin, dtype, alpha)
+    return val, sp, sn, np.asarray(dpos, np.float64) * gsp * fp, np.asarray(dneg, np.float64) * gsn * fn
+
+
+def dim_slice_grads(model, kc, e, rl, pos, neg, wp, wn, norm=1, dtype=np.float64):
+    """Summed gradient rows of ONE rank's slice ([E,Kc], [R,Kc]) given dL/d total of every scored triple."""
+    ge, gr = np.zeros(e.shape, dtype), np.zeros(rl.shape, dtype)
+    for trip, w in ((pos, wp), (neg, wn)):
+        gs, gp, go = raw_partial_grads(model, kc, e[trip[:, 0]], rl[trip[:, 1]], e[trip[:, 2]], norm, dtype)
+        np.add.at(ge, trip[:, 0], w[:, None] * gs)
+        np.add.at(ge, trip[:, 2], w[:, None] * go)
+        np.add.at(gr, trip[:, 1], w[:, None] * gp)
+    return ge, gr

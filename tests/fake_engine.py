@@ -10,6 +10,7 @@ import torch
 
 from emgraph_b200 import _lib
 from oracle import kge_oracle as ko
+from oracle import sharded_oracle as so
 
 _MODEL = {0: ("TransE", 1), 1: ("TransE", 2), 2: ("DistMult", 1), 3: ("ComplEx", 1), 4: ("HolE", 1)}
 _LOSS = {v: k for k, v in _lib.LOSS_IDS.items()}
@@ -90,6 +91,105 @@ class FakeEngine:
 
     def train_host_wait(self, ticket):
         assert 0 <= ticket < 4
+
+    # ---- dimension-sharded step (include/kge_b200.h: kge_train_partial / _backward / _reduce) on one rank's column slice
+    def _dim_corruptions(self, a):
+        n, eta = a.pos.shape[0], a.eta
+        keep_codes = None if getattr(a, "keep_subj", None) is None else a.keep_subj.numpy()
+        if getattr(a, "repl", None) is not None:
+            return a.repl.numpy(), (keep_codes if keep_codes is not None else np.full(n * eta, 1 if a.side == 2 else 0, np.uint8))
+        return ko.draw_corruptions(a.seed, a.step, n, eta, a.ent.shape[0], _SIDE[a.side], keep_codes=keep_codes)
+
+    def train_partial(self, a, sums, i_begin=0, i_end=None):
+        model, norm = _MODEL[a.model]
+        pos = a.pos.numpy()
+        n, eta = pos.shape[0], a.eta
+        i_end = n if i_end is None else i_end
+        if i_begin == 0:
+            repl, keep = self._dim_corruptions(a)
+            self._dim = dict(neg=ko.corruptions_for_fit(pos, eta, keep, repl), totals={}, step=a.step)
+        e, rl, neg = a.ent.numpy(), a.rel.numpy(), self._dim["neg"]
+        nc = i_end - i_begin
+        out = np.zeros((1 + eta) * nc, np.float32)
+        p = pos[i_begin:i_end]
+        out[:nc] = so.raw_partial(model, a.k, e[p[:, 0]], rl[p[:, 1]], e[p[:, 2]], norm, np.float32)
+        for j in range(eta):
+            t = neg[j * n + i_begin:j * n + i_end]
+            out[nc + j * nc:nc + (j + 1) * nc] = so.raw_partial(model, a.k, e[t[:, 0]], rl[t[:, 1]], e[t[:, 2]], norm, np.float32)
+        sums[:out.size].copy_(torch.from_numpy(out))
+        self.launches += 1
+
+    def train_backward(self, a, sums, i_begin=0, i_end=None):
+        i_end = a.pos.shape[0] if i_end is None else i_end
+        self._dim["totals"][(i_begin, i_end)] = sums.numpy()[:(1 + a.eta) * (i_end - i_begin)].copy()
+        self.launches += 1
+
+    def train_reduce(self, a):
+        model, norm = _MODEL[a.model]
+        pos = a.pos.numpy()
+        n, eta = pos.shape[0], a.eta
+        tot_p, tot_n = np.zeros(n, np.float32), np.zeros(n * eta, np.float32)
+        covered = 0
+        for (lo, hi), t in sorted(self._dim["totals"].items()):
+            nc = hi - lo
+            tot_p[lo:hi] = t[:nc]
+            for j in range(eta):
+                tot_n[j * n + lo:j * n + hi] = t[nc + j * nc:nc + (j + 1) * nc]
+            covered += nc
+        assert covered == n, "the chunks of a step must cover the global batch"
+        k_model = getattr(a, "k_model", 0) or a.k
+        val, _, _, wp, wn = so.dim_loss_weights(model, k_model, _LOSS[a.loss], eta, tot_p, tot_n, getattr(a, "margin", 1.0), norm,
+                                                getattr(a, "alpha", 0.5), _NL[getattr(a, "non_linearity", 0)], np.float32)
+        e, rl, neg = a.ent.numpy(), a.rel.numpy(), self._dim["neg"]
+        ge, gr = so.dim_slice_grads(model, a.k, e, rl, pos, neg, wp, wn, norm)
+        t_ent = np.zeros(e.shape[0], bool)
+        for trip in (pos, neg):
+            t_ent[trip[:, 0]] = True
+            t_ent[trip[:, 2]] = True
+        t_rel = np.zeros(rl.shape[0], bool)
+        t_rel[pos[:, 1]] = True
+        st_e, ten_e = self._state(a, "ent")
+        st_r, ten_r = self._state(a, "rel")
+        if not (a.flags & _lib.F_NO_UPDATE):
+            e_new, se = ko.optimizer_step(_OPT[a.opt], e, ge, t_ent, a.lr, st_e, a.step)
+            r_new, sr = ko.optimizer_step(_OPT[a.opt], rl, gr, t_rel, a.lr, st_r, a.step)
+            a.ent.copy_(torch.from_numpy(e_new))
+            a.rel.copy_(torch.from_numpy(r_new))
+            for tens, new in ((ten_e, se), (ten_r, sr)):
+                for t, x in zip(tens, new):
+                    t.copy_(torch.from_numpy(x))
+        a.loss_out[0] = float(val)
+        self.calls.append(dict(step=a.step, seed=a.seed, n=n, flags=a.flags, side=a.side, lr=a.lr, pos=pos.copy(), dim=True))
+        self.launches += 1
+
+    def rank_counts_rows(self, model, k, E, rel, s_rows, o_rows, ent_local, test, *, row_begin, row_end, side=0, filtered=False,
+                         use_tensor_cores=False, non_linearity=0, counts=None):
+        """kge_rank_counts_rows: candidates are the rows of ent_local (global ids row_begin..row_end-1), the test triples'
+        own subject / object rows come from the caller."""
+        name, norm = _MODEL[model]
+        cand = np.arange(row_begin, row_end)
+        loc, reln, tst = ent_local.numpy()[:row_end - row_begin], rel.numpy(), test.numpy()
+        sr, orr = s_rows.numpy(), o_rows.numpy()
+        filt = ko.FilterIndex(self._filter) if filtered else None
+        out = np.zeros((tst.shape[0], 2, 4), np.int32)
+        nl = _NL[non_linearity]
+        for t, x in enumerate(tst):
+            p = reln[x[1]][None]
+            qp = ko.quantise(ko.non_linearity(nl, ko.score_rows(name, k, sr[t][None], p, orr[t][None], norm))[0])[0]
+            idx_o, idx_s = filt.participating(x) if filt is not None else ((), ())
+            for sd, (col, known) in enumerate(((2, idx_o), (0, idx_s))):
+                if (side == 3 and sd == 1) or (side == 2 and sd == 0):
+                    continue
+                m = cand != x[col]
+                c, rows = cand[m], loc[m]
+                if col == 2:
+                    sc = ko.score_rows(name, k, np.repeat(sr[t][None], len(c), 0), np.repeat(p, len(c), 0), rows, norm)
+                else:
+                    sc = ko.score_rows(name, k, rows, np.repeat(p, len(c), 0), np.repeat(orr[t][None], len(c), 0), norm)
+                q = ko.quantise(ko.non_linearity(nl, sc)[0])
+                f = np.isin(c, np.asarray(list(known), dtype=np.int64))
+                out[t, sd] = [(q > qp).sum(), (q == qp).sum(), ((q > qp) & f).sum(), ((q == qp) & f).sum()]
+        return torch.from_numpy(out)
 
     def normalize_rows(self, emb):
         nrm = emb.norm(dim=1, keepdim=True).clamp(min=1.0)

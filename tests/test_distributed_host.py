@@ -162,3 +162,117 @@ def test_owner_compute_volume_against_the_row_push():
     assert abs(push["rows_in"] - (2 + eta) * n * row * (W - 1) / W) < 0.05 * push["rows_in"]
     assert 30 * n * row < oc["bytes_total"] < 36 * n * row
     assert 72 * n * row < push["total"] < 76 * n * row
+
+
+# ------------------------------------------------------------------------------------------------
+# dimension-sharded path (the product's multi-GPU exchange): decomposition exact, column bookkeeping, and the
+# ShardedKGE driver end to end on 2 gloo ranks with the oracle-backed stand-in engine
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model,loss,norm,nl,k,W", [("DistMult", "nll", 1, "linear", 10, 4), ("ComplEx", "multiclass_nll", 1, "linear", 12, 8),
+                                                   ("HolE", "self_adversarial", 1, "tanh", 6, 2), ("TransE", "pairwise", 1, "linear", 9, 3),
+                                                   ("TransE", "nll", 2, "linear", 16, 4), ("ComplEx", "absolute_margin", 1, "sigmoid", 5, 2)])
+def test_dim_sharded_step_equals_the_oracle_step(model, loss, norm, nl, k, W):
+    """Column-slice partial sums, one sum per scored triple over the ranks, slice-local backward: loss and gradients
+    of the W slices equal the single-process oracle step (the decomposition is exact, not an approximation)."""
+    rng = np.random.default_rng(0)
+    E, R, eta, n = 97, 5, 5, 23
+    K = ko.internal_k(model, k)
+    ent = (rng.normal(size=(E, K)) * 0.5).astype(np.float32)
+    rel = (rng.normal(size=(R, K)) * 0.5).astype(np.float32)
+    pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+    keep = rng.integers(0, 2, n * eta).astype(np.uint8)
+    repl = rng.integers(0, E, n * eta).astype(np.int32)
+    g = so.dim_sharded_step(model, k, loss, eta, ent, rel, pos, keep, repl, W, margin=2.0, norm=norm, nl=nl)
+    o = ko.train_step(model, k, loss, eta, ent, rel, pos, keep, repl, margin=2.0, norm=norm, dtype=np.float64, nl=nl)
+    np.testing.assert_allclose(g["loss"], o["loss"], rtol=1e-12)
+    np.testing.assert_allclose(g["grad_ent"], o["grad_ent"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(g["grad_rel"], o["grad_rel"], rtol=1e-9, atol=1e-12)
+    assert g["bytes_per_rank"] == 4 * (1 + eta) * n  # the whole exchange: one float per scored triple
+
+
+def test_column_slices_round_trip_and_match_the_oracle_layout():
+    rng = np.random.default_rng(1)
+    for model in ("TransE", "DistMult", "ComplEx", "HolE"):
+        for k, W in ((200, 8), (256, 8), (100, 2), (10, 4), (7, 3), (4, 8), (512, 1)):
+            K = ko.internal_k(model, k)
+            full = rng.normal(size=(5, K)).astype(np.float32)
+            kc = D.dim_width(k, W)
+            assert kc % 4 == 0 and kc * W >= k
+            parts = [D.slice_columns(full, model, k, W, r) for r in range(W)]
+            for r, p in enumerate(parts):
+                ref, kc2, cr = so.dim_slice(full, model, k, W, r)
+                assert kc2 == kc and cr == D.dim_range(k, W, r)
+                np.testing.assert_array_equal(p, ref)
+            np.testing.assert_array_equal(D.merge_columns(parts, model, k), full)
+            cat = np.concatenate(parts, 1)
+            np.testing.assert_array_equal(cat[:, D.merge_index(model, k, W)], full)
+    assert D.chunk_bounds(10, 3) == [(0, 4), (4, 7), (7, 10)] and D.chunk_bounds(2, 5) == [(0, 1), (1, 2)]
+
+
+def _dim_worker(rank, world, port, cfg, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_engine import FakeEngine
+        fake = FakeEngine()
+        D.get_engine = lambda device=None: fake  # the stand-in engine computes every phase with the oracle
+        model, loss, k, eta, E, R, n = cfg["model"], cfg["loss"], cfg["k"], cfg["eta"], cfg["E"], cfg["R"], cfg["n"]
+        sk = D.ShardedKGE(model, k, eta, loss, "adam", E, R, n, lr=1e-2, seed=11, init_ent=cfg["ent"], init_rel=cfg["rel"], chunks=2)
+        losses = []
+        for step in range(2):
+            pos = torch.from_numpy(cfg["pos"][step][rank])
+            losses.append(float(sk.train_step(pos)[0]))
+        ent_new, rel_new = sk.gather_entities(), sk.gather_relations()
+        fake.filter_build(torch.from_numpy(cfg["filt"]), E, R)
+        ranks = sk.rank(torch.from_numpy(cfg["test"]), side=0, strategy=0, filtered=True).numpy()
+        rows = sk.row_shard().numpy()
+        q.put((rank, dict(losses=losses, ent=ent_new, rel=rel_new, ranks=ranks, rows=rows, range=(sk.row_begin, sk.row_end))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("model,loss,k", [("ComplEx", "nll", 10), ("TransE", "pairwise", 8)])
+def test_gloo_world2_sharded_driver_matches_single_process_oracle(model, loss, k):
+    """ShardedKGE on 2 ranks (gloo, stand-in engine): batch all-gather, the per-chunk all-reduce of partial sums, the
+    column all-gather and the all-to-all that builds the ranking shards -- two optimisation steps and a filtered
+    ranking equal the single-process oracle on the concatenated global batches and the same Philox stream."""
+    world, E, R, eta, n = 2, 61, 4, 3, 17
+    rng = np.random.default_rng(5)
+    K = ko.internal_k(model, k)
+    ent = (rng.normal(size=(E, K)) * 0.4).astype(np.float32)
+    rel = (rng.normal(size=(R, K)) * 0.4).astype(np.float32)
+    pos = [[np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32) for _ in range(world)]
+           for _ in range(2)]
+    filt = ko.synthetic_triples(E, R, 300, seed=5)
+    test = filt[:12]
+    cfg = dict(model=model, loss=loss, k=k, eta=eta, E=E, R=R, n=n, ent=ent, rel=rel, pos=pos, filt=filt, test=test)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + ((os.getpid() * 7 + k) % 2000)
+    procs = [ctx.Process(target=_dim_worker, args=(r, world, port, cfg, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=200) for _ in procs)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    e_o, r_o, state = ent, rel, None
+    for step in range(2):
+        P = np.concatenate(pos[step], 0)
+        repl, keep = ko.draw_corruptions(11, step + 1, P.shape[0], eta, E, "s,o")
+        o = ko.train_step(model, k, loss, eta, e_o, r_o, P, keep, repl, opt="adam", lr=1e-2, step=step + 1,
+                          state=state if state is not None else ((np.zeros_like(ent), np.zeros_like(ent)), (np.zeros_like(rel), np.zeros_like(rel))))
+        e_o, r_o, state = o["ent_new"], o["rel_new"], (o["state_ent"], o["state_rel"])
+        for r in range(world):
+            np.testing.assert_allclose(res[r]["losses"][step], o["loss"], rtol=1e-5)
+    exp = ko.ranks(model, k, res[0]["ent"], res[0]["rel"], test, filt, "s,o", "worst")
+    for r in range(world):
+        np.testing.assert_array_equal(res[r]["ent"], res[0]["ent"])
+        big = np.abs(state[0][0]) > 1e-4
+        np.testing.assert_allclose(res[r]["ent"][big], e_o[big], rtol=2e-4, atol=2e-6)
+        np.testing.assert_allclose(res[r]["rel"], r_o, rtol=2e-3, atol=2e-5)
+        b, e = res[r]["range"]
+        np.testing.assert_array_equal(res[r]["rows"][:e - b], res[0]["ent"][b:e])  # the transposed shard holds whole rows
+        np.testing.assert_array_equal(res[r]["ranks"], exp)
