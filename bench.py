@@ -8,13 +8,17 @@ Prints ONE JSON line (rank 0).  Contract (see DESIGN.md "Measurement"):
   value      train triples/sec (eta negatives incl.), inputs resident in HBM, L2 flushed between the
              timed steps, CUDA-event timed on the launching stream, max over ranks
   e2e        the same metric through the public API with HOST buffers: every step copies its batch
-             from pinned host memory and reads the batch loss back (EmbeddingModel._fit_step_host ->
-             C ABI kge_train_step_host)
+             from pinned host memory and reads the batch loss back
   roofline   dominant training kernel: algorithmic bytes / live CUDA-event kernel time vs the measured
              HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline  the reference-equivalent CPU op graph (oracle/torch_port.py) on the host cores, on a
              bounded sample
   rank       the second half of BASELINE.json's metric: filtered-rank test triples/sec (same keys)
+  cfg5       the same train measurement on the Wikidata5M-shaped config (the one BASELINE.json asks to
+             scale over 1/2/4/8 GPUs), carried by EVERY line so the driver's 1->8 sweep records it
+  others     one-line summaries of the remaining BASELINE configs (N = 1 only)
+  rank_parity  ranks of the seeded, untrained model: identical for every N (a correctness witness of
+             the multi-GPU path inside the scaling record itself)
 `--impl reference` times only the CPU arm (all host threads) on the same config.
 """
 from __future__ import annotations
@@ -49,6 +53,8 @@ WORKLOADS = {
 TRAIN_METRIC = "train triples/sec (eta negatives incl.)"
 RANK_METRIC = "filtered-rank test triples/sec"
 L2_FLUSH_BYTES = 512 << 20
+TIMED_REGION_MS = 100.0  # every timed region is at least this long: steps are repeated (config.inner_repeat)
+TABLE_SEED = 2
 
 
 def internal_k(model, k):
@@ -92,6 +98,57 @@ def glorot(rows, cols, seed):
     return rng.uniform(-lim, lim, size=(rows, cols)).astype(np.float32)
 
 
+def seeded_table(rows, model, k, dev, seed, c0=0, c1=None, pad_to=None):
+    """Glorot-uniform table drawn on the device in blocks of 4 columns, each block from its own generator seed, so that
+    ANY column range of the table can be produced without the rest: rank r of a column-sharded run draws exactly the
+    values the single-GPU run holds in those columns (rank_parity below depends on it).  Returns columns [c0,c1) of each
+    half, zero-padded to pad_to columns per half: [rows, halves*width]."""
+    import torch
+    halves = 2 if model in ("ComplEx", "HolE") else 1
+    c1 = k if c1 is None else c1
+    width = (c1 - c0) if pad_to is None else pad_to
+    K = internal_k(model, k)
+    lim = math.sqrt(6.0 / (rows + K))
+    out = torch.zeros((rows, halves * width), dtype=torch.float32, device=dev)
+    assert c0 % 4 == 0
+    for h in range(halves):
+        for b in range(c0 // 4, (c1 + 3) // 4):
+            g = torch.Generator(device=dev).manual_seed(seed * 1000003 + h * 50021 + b)
+            blk = torch.empty((rows, 4), dtype=torch.float32, device=dev).uniform_(-lim, lim, generator=g)
+            lo, hi = 4 * b, min(4 * b + 4, c1)
+            out[:, h * width + lo - c0:h * width + hi - c0] = blk[:, :hi - lo]
+    return out
+
+
+def batch_positives(w):
+    return int(math.ceil(w["N"] / w["batches"]))
+
+
+def make_dataset(w, need_train, with_test, zipf=True):
+    """(X, test): the first min(N, need_train) synthetic triples of the shape + T test triples sampled from them."""
+    n = w["N"] if with_test and w["N"] <= 2_000_000 else min(w["N"], max(need_train, w["T"] * 8 if with_test else 0))
+    X = synth_triples(w["E"], w["R"], n, seed=0, zipf=zipf)
+    test = None
+    if with_test:
+        rng = np.random.Generator(np.random.PCG64(1))
+        test = X[rng.permutation(X.shape[0])[: w["T"]]].copy()
+    return X, test
+
+
+def config_for(args, name, w, world):
+    """The SAME dictionary in both arms (GPU and --impl reference) and at every N except for `parallelism`."""
+    K = internal_k(w["model"], w["k"])
+    return {"workload": "%s: %s" % (name, w["desc"]), "batch_positives_per_gpu": batch_positives(w), "global_batch": batch_positives(w) * world,
+            "eta": w["eta"], "E": w["E"], "R": w["R"], "K": K, "test_triples": w["T"],
+            "entity_popularity": "uniform" if args.uniform else "zipf(1.0)", "optimizer": w["opt"],
+            "l2": "GPU arm: flushed before every timed step (%d MiB write); CPU arm: n/a" % (L2_FLUSH_BYTES >> 20),
+            "inner_repeat": "every one of the --steps is the mean of R back-to-back-submitted, individually timed steps, R chosen so "
+                            "that the timed region is >= %d ms (R is in measurement.inner_repeat)" % int(TIMED_REGION_MS),
+            "parallelism": "1 GPU" if world == 1 else
+                           "%d GPUs: tables + optimizer state column-sharded (dimension-parallel), global batch on every GPU, one "
+                           "all-reduce of (1+eta) partial scores per positive" % world}
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks during the timed region (B200_PROFILING.md)
 # ------------------------------------------------------------------------------------------------
@@ -126,7 +183,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def start(self):
         if self.nv is not None:
@@ -151,13 +208,42 @@ def load_peaks():
 
 
 def load_traffic(workload, kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic_r01.json);
-    None when the workload / kernel was not captured."""
-    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    """DRAM bytes per launch of `kernel` from an `ncu --set full` capture of this command: the capture of the current
+    gpurun session when tools/ncu_traffic.py left one in gpurun_out/ (its session tag is returned too), else the
+    committed capture of the round (profiles/traffic_r02.json, then r01).  (bytes, source) or (None, None)."""
+    for p in (os.path.join(ROOT, "gpurun_out", "traffic_session.json"), os.path.join(ROOT, "profiles", "traffic_r02.json"),
+              os.path.join(ROOT, "profiles", "traffic_r01.json")):
+        try:
+            d = json.load(open(p))
+            return float(d[workload][kernel]), "%s (session %s)" % (os.path.relpath(p, ROOT), d.get("session", "r01"))
+        except Exception:
+            continue
+    return None, None
+
+
+def measure_tf32_peak(dev):
+    """Dense TF32 tensor throughput of THIS GPU, measured the way MEASURED_PEAKS.json measures bf16: cuBLAS fp32 GEMM
+    with TF32 tensor cores, 8192^3, best of 10 after warm-up (TFLOP/s).  The ranking roofline divides by it."""
+    import torch
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
     try:
-        return float(json.load(open(p))[workload][kernel])
-    except Exception:
-        return None
+        n = 8192
+        a = torch.randn((n, n), device=dev)
+        b = torch.randn((n, n), device=dev)
+        for _ in range(3):
+            a @ b
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 # ------------------------------------------------------------------------------------------------
@@ -169,7 +255,7 @@ def cpu_arm(w, X, test, filt_for_rank, steps, warmup, budget_s, rank_budget_s, d
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     K = internal_k(w["model"], w["k"])
-    B = int(math.ceil(w["N"] / w["batches"]))
+    B = batch_positives(w)
     ent, rel = glorot(w["E"], K, 2), glorot(w["R"], K, 3)
     tr = tp.CpuTrainer(w["model"], w["k"], w["loss"], w["eta"], ent, rel, margin=w["margin"], lr=w["lr"], optimizer=w["opt"])
     g = torch.Generator().manual_seed(0)
@@ -198,7 +284,7 @@ def cpu_arm(w, X, test, filt_for_rank, steps, warmup, budget_s, rank_budget_s, d
             rk.rank(test[n])
             n += 1
         dt = time.perf_counter() - t0
-        rank = dict(value=n / dt, sample="%d of %d test triples, per-triple 2E-corruption sweep, dict filter, torch-CPU %d threads"
+        rank = dict(value=n / dt, sample="the first %d of the GPU arm's %d test triples, per-triple 2E-corruption sweep, dict filter, torch-CPU %d threads"
                     % (n, test.shape[0], cores), n=n)
     return train, rank, cores
 
@@ -213,9 +299,11 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-rank", action="store_true", help="skip the ranking half")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sub", action="store_true", help="skip the cfg5 sub-record and the other configs' summaries")
     ap.add_argument("--rank-steps", type=int, default=3)
     ap.add_argument("--rank-tc", type=int, default=-1, help="1/0 force the tensor-core ranking sweep on/off")
     ap.add_argument("--uniform", action="store_true", help="uniform instead of Zipf entity popularity")
+    ap.add_argument("--chunks", type=int, default=2, help="multi-GPU: pieces a step is cut into (all-reduce / kernel overlap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = dict(WORKLOADS[args.workload])
@@ -234,17 +322,15 @@ def main():
 
 
 def reference_main(args, w):
-    B = int(math.ceil(w["N"] / w["batches"]))
-    need = (args.steps + args.warmup + 1) * B
-    X = synth_triples(w["E"], w["R"], min(w["N"], max(need, B)), seed=0, zipf=not args.uniform)
-    test = X[:: max(1, X.shape[0] // 512)][:512]
-    train, rank, cores = cpu_arm(w, X, test, X, args.steps, args.warmup, budget_s=150.0, rank_budget_s=20.0, do_rank=not args.no_rank)
+    B = batch_positives(w)
+    X, test = make_dataset(w, (args.steps + args.warmup + 1) * B, not args.no_rank, zipf=not args.uniform)
+    train, rank, cores = cpu_arm(w, X, test if test is not None else X[:8], X, args.steps, args.warmup, budget_s=150.0, rank_budget_s=20.0,
+                                 do_rank=not args.no_rank)
     line = {
         "impl": "reference", "metric": TRAIN_METRIC, "value": train["value"], "unit": "triples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": train["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "batch_positives": B, "eta": w["eta"], "E": w["E"],
-                   "K": internal_k(w["model"], w["k"])},
+        "config": config_for(args, args.workload, w, max(1, args.gpus)),
         "cpu_baseline": {"value": train["value"], "unit": "triples/s", "cores": cores, "kind": "port", "sample": train["sample"]},
         "e2e": {"value": train["value"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -257,32 +343,61 @@ def reference_main(args, w):
     return 0
 
 
-def single_gpu_main(args, w):
-    import torch
-    from emgraph_b200 import _lib, models
-    from emgraph_b200.engine import get_engine, make_table
-    from emgraph_b200.evaluation import EvalDataset
+def inner_repeat(steps, est_ms):
+    return max(1, int(math.ceil(TIMED_REGION_MS / max(steps * est_ms, 1e-6))))
 
-    torch.cuda.set_device(0)
+
+def build_model(w, dev):
+    """The public-API model of a workload with the seeded tables injected (initializer='constant')."""
+    from emgraph_b200 import models
+    E, R, k = w["E"], w["R"], w["k"]
+    ent0 = seeded_table(E, w["model"], k, dev, TABLE_SEED).cpu().numpy()
+    rel0 = seeded_table(R, w["model"], k, dev, TABLE_SEED + 1).cpu().numpy()
+    cls = models.MODEL_REGISTRY[w["model"]]
+    model = cls(k=k, eta=w["eta"], epochs=1, batches_count=w["batches"], seed=0, optimizer=w["opt"], optimizer_params={"lr": w["lr"]},
+                loss=w["loss"], loss_params={"margin": w["margin"]}, initializer="constant",
+                initializer_params={"entity": ent0, "relation": rel0})
+    return model
+
+
+def rank_pretrain_single(args, w, eng, ent, rel, X, test):
+    """Filtered 's,o' ranks of the seeded, untrained tables on one GPU (the witness multi-GPU runs must reproduce)."""
+    import torch
+    from emgraph_b200 import _lib
+    from emgraph_b200.engine import model_id
+    from emgraph_b200.evaluation import EvalDataset
+    ds = EvalDataset(test, X)
+    ds.build_filter(eng, w["E"], w["R"])
+    use_tc = ((w["model"] != "TransE") if args.rank_tc < 0 else bool(args.rank_tc)) and eng.has_tensor_core_rank()
+    ranks = eng.rank(model_id(w["model"]), w["k"], ent, rel, ds.test_device(eng.tdev), side=0, strategy=0, filtered=True,
+                     use_tensor_cores=use_tc)
+    torch.cuda.synchronize()
+    return ranks.cpu().numpy()
+
+
+def ranks_digest(r):
+    import hashlib
+    r = np.ascontiguousarray(np.asarray(r, np.int32))
+    return {"mrr_pretrain": float(np.mean(1.0 / r.reshape(-1).astype(np.float64))), "sha1": hashlib.sha1(r.tobytes()).hexdigest()[:16], "n": int(r.size)}
+
+
+def train_bench_single(args, name, w, steps, warmup, detailed):
+    """Single-GPU train measurement of one workload through the public model API.  detailed: also per-kernel phases,
+    roofline, warm-L2 and synchronous e2e numbers (the main record); the sub-records keep value + e2e."""
+    import torch
+    from emgraph_b200.engine import get_engine
     eng = get_engine(0)
     dev = eng.tdev
     peaks = load_peaks()
     E, R, k, eta = w["E"], w["R"], w["k"], w["eta"]
     K = internal_k(w["model"], k)
-    B = int(math.ceil(w["N"] / w["batches"]))
-    steps, warmup = args.steps, args.warmup
-    do_rank = not args.no_rank
-    n_train_needed = (steps + warmup) * B
-    X = synth_triples(E, R, w["N"] if do_rank else min(w["N"], n_train_needed), seed=0, zipf=not args.uniform)
+    B = batch_positives(w)
+    X, test = make_dataset(w, (steps * 4 + warmup + 16) * B, with_test=True, zipf=not args.uniform)
     nb = max(1, X.shape[0] // B)
-    rng = np.random.Generator(np.random.PCG64(1))
-    test = X[rng.permutation(X.shape[0])[: w["T"]]].copy() if do_rank else None
-
-    cls = models.MODEL_REGISTRY[w["model"]]
-    model = cls(k=k, eta=eta, epochs=1, batches_count=w["batches"], seed=0, optimizer=w["opt"], optimizer_params={"lr": w["lr"]},
-                loss=w["loss"], loss_params={"margin": w["margin"]},
-                initializer="constant", initializer_params={"entity": glorot(E, K, 2), "relation": glorot(R, K, 3)})
+    model = build_model(w, dev)
     f = model._fit_prepare(E, R)
+    # ranks of the untrained seeded tables: the witness every multi-GPU line must reproduce bit for bit
+    parity = ranks_digest(rank_pretrain_single(args, w, eng, f["ent"], f["rel"], X, test))
     pipeline_on = os.environ.get("KGE_PIPELINE", "1")[:1] != "0"
     Xd = torch.from_numpy(X).to(dev)
     Xh = torch.from_numpy(X).pin_memory()
@@ -293,11 +408,22 @@ def single_gpu_main(args, w):
         return b * B, (b + 1) * B
 
     it = 0
-    for _ in range(warmup):
+    first_loss = None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for s_ in range(warmup):
         lo, hi = batch(it)
+        if s_ == warmup - 1:
+            e0.record()
         model._fit_step_device(Xd[lo:hi])
+        if s_ == warmup - 1:
+            e1.record()
+        if it == 0:
+            first_loss = float(f["loss_dev"].item())
         it += 1
     torch.cuda.synchronize()
+    est = e0.elapsed_time(e1)
+    rep = inner_repeat(steps, est)
+    n_timed = steps * rep
     sampler = ClockSampler(0)
     sampler.start()
 
@@ -306,9 +432,9 @@ def single_gpu_main(args, w):
     # steps, so the pipeline is switched off here; the back-to-back loops below (no untimed gaps) keep it on.
     f["pipeline"] = False
     l0 = eng.launches
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_timed)]
     torch.cuda.synchronize()
-    for s in range(steps):
+    for s in range(n_timed):
         flush.fill_(float(s))
         lo, hi = batch(it)
         evs[s][0].record()
@@ -319,9 +445,12 @@ def single_gpu_main(args, w):
     launches_timed = eng.launches - l0
     t_cold_ms = sum(a.elapsed_time(b) for a, b in evs)
     triples_per_step = B * (1 + eta)
-    value = steps * triples_per_step / (t_cold_ms * 1e-3)
+    value = n_timed * triples_per_step / (t_cold_ms * 1e-3)
+    step_ms = t_cold_ms / n_timed
+    out = {"value": value, "ms_per_step": step_ms, "inner_repeat": rep, "timed_steps": n_timed, "timed_region_ms": t_cold_ms,
+           "launches": launches_timed, "first_step_loss": first_loss, "rank_parity": parity}
 
-    # ---- warm: K steps back to back (what a training loop sees; tables stay in L2 when they fit), pipelined
+    # ---- warm: steps back to back (what a training loop sees; tables stay in L2 when they fit), pipelined
     f["pipeline"] = pipeline_on
     for _ in range(2):
         lo, hi = batch(it)
@@ -330,58 +459,84 @@ def single_gpu_main(args, w):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for s in range(steps):
+    for s in range(n_timed):
         lo, hi = batch(it)
         model._fit_step_device(Xd[lo:hi])
         it += 1
     e1.record()
     torch.cuda.synchronize()
     t_warm_ms = e0.elapsed_time(e1)
-    value_warm = steps * triples_per_step / (t_warm_ms * 1e-3)
+    out["value_warm_l2"] = n_timed * triples_per_step / (t_warm_ms * 1e-3)
+    out["ms_per_step_warm"] = t_warm_ms / n_timed
 
-    # ---- per-kernel time inside the real step (library-side CUDA events on the launching stream, L2
-    # flushed before every step): emit | fwd_bwd | reduce_apply (after the hidden sort) | span/hub reduction
-    f["pipeline"] = False
-    eng.set_timing(True)
-    for s in range(steps):
-        flush.fill_(float(s))
-        lo, hi = batch(it)
-        model._fit_step_device(Xd[lo:hi])
-        it += 1
-    torch.cuda.synchronize()
-    phases, n_timed = eng.get_timing()
-    eng.set_timing(False)
-    f["pipeline"] = pipeline_on
-    t_emit, t_fb, t_apply, t_span = phases["emit"], phases["fwd_bwd"], phases["reduce_apply"], phases["spans"]
-    # distinct rows touched per step (entities + relations), from the library's own sort keys
-    S = (3 + eta) * B
-    keys = torch.empty(S, dtype=torch.int32, device=dev)
-    uniq = []
-    for j in range(3):
-        lo, hi = batch(it + j)
-        a = eng.train_args(ent=f["ent"], rel=f["rel"], pos=Xd[lo:hi], loss_out=f["loss_dev"], side=0, step=f["step"] + 1 + j, **f["kw"], **f["st"])
-        eng.train_emit(a, keys)
-        uniq.append(int(torch.unique(keys).numel()))
-    n_unique = float(np.mean(uniq))
+    if detailed:
+        # ---- per-kernel time inside the real step (library-side CUDA events on the launching stream, L2
+        # flushed before every step): emit | fwd_bwd | reduce_apply (after the hidden sort) | span/hub reduction
+        f["pipeline"] = False
+        eng.set_timing(True)
+        for s in range(min(n_timed, 200)):
+            flush.fill_(float(s))
+            lo, hi = batch(it)
+            model._fit_step_device(Xd[lo:hi])
+            it += 1
+        torch.cuda.synchronize()
+        phases, n_ph = eng.get_timing()
+        eng.set_timing(False)
+        f["pipeline"] = pipeline_on
+        t_emit, t_fb, t_apply, t_span = phases["emit"], phases["fwd_bwd"], phases["reduce_apply"], phases["spans"]
+        S = (3 + eta) * B
+        keys = torch.empty(S, dtype=torch.int32, device=dev)
+        uniq = []
+        for j in range(3):
+            lo, hi = batch(it + j)
+            a = eng.train_args(ent=f["ent"], rel=f["rel"], pos=Xd[lo:hi], loss_out=f["loss_dev"], side=0, step=f["step"] + 1 + j, **f["kw"], **f["st"])
+            eng.train_emit(a, keys)
+            uniq.append(int(torch.unique(keys).numel()))
+        n_unique = float(np.mean(uniq))
+        # roofline of the dominant training kernel.  Algorithmic bytes per launch:
+        #   fwd_bwd      : (3+eta) rows gathered + 5 rows + eta coefficients/flags written, per positive
+        #   reduce_apply : one row-sized read + 13 B of key/slot/coefficient per slot, plus w,m,v read and
+        #                  written once per DISTINCT touched row (Adam: 6 row-sized accesses)
+        n_state = {"adam": 6, "adagrad": 4, "momentum": 4, "sgd": 2}[w["opt"]]
+        bytes_fb = ((3 + eta) * 4 * K + 5 * 4 * K + 5 * eta) * B
+        bytes_apply = (3 + eta) * B * (4 * K + 13) + n_state * 4 * K * n_unique
+        t_red = t_apply + t_span
+        dom = "kge_fwd_bwd_kernel" if t_fb >= t_red else "kge_reduce_apply_kernel (+ span/hub reduction)"
+        dom_t, dom_b = (t_fb, bytes_fb) if t_fb >= t_red else (t_red, bytes_apply)
+        ach = dom_b / (dom_t * 1e-3) / 1e9
+        traffic, tsrc = load_traffic(name, dom.split(" ")[0])
+        out["roofline"] = {
+            "bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+            "traffic": traffic, "traffic_source": tsrc, "peak_source": peaks["src"], "algorithmic_bytes_per_launch": dom_b, "kernel_ms": dom_t,
+            "phases_ms": {"emit": t_emit, "fwd_bwd": t_fb, "reduce_apply": t_apply, "span_hub": t_span,
+                          "sort_done_after_emit": phases.get("sort_after_emit", 0.0), "timed_steps": n_ph},
+            "kernels": {"fwd_bwd": {"bytes": bytes_fb, "GBps": bytes_fb / (t_fb * 1e-3) / 1e9, "frac": bytes_fb / (t_fb * 1e-3) / 1e9 / peaks["hbm"]},
+                        "reduce_apply": {"bytes": bytes_apply, "GBps": bytes_apply / (t_red * 1e-3) / 1e9,
+                                         "frac": bytes_apply / (t_red * 1e-3) / 1e9 / peaks["hbm"]}},
+            "distinct_rows_per_step": n_unique,
+            "step_algorithmic_GBps": (bytes_fb + bytes_apply) / (step_ms * 1e-3) / 1e9,
+            "step_frac": (bytes_fb + bytes_apply) / (step_ms * 1e-3) / 1e9 / peaks["hbm"],
+            "note": "tables of cfg1-3 are L2-resident: the bytes are what the kernel loads/stores, mostly served by L2"
+                    if (E * K * 4 * 3) < (100 << 20) else "tables exceed L2: HBM-bound"}
 
     # ---- e2e: host batches through the public step (pinned H2D of the batch + D2H of the loss, every step).
-    # (a) synchronous: every call returns its own loss (what the reference's loop does);
-    # (b) pipelined (what fit(host_batches) runs): the call returns once the step is queued and hands back the
-    #     loss of the previous step, so the GPU never waits for the host; same copies, same kernels, same order.
-    for _ in range(3):
-        lo, hi = batch(it)
-        model._fit_step_host(Xh[lo:hi])
-        it += 1
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    # pipelined (what fit(host_batches) runs): the call returns once the step is queued and hands back the loss of the
+    # previous step, so the GPU never waits for the host; same copies, same kernels, same order.
     last_loss = 0.0
-    for s in range(steps):
-        lo, hi = batch(it)
-        last_loss = model._fit_step_host(Xh[lo:hi])
-        it += 1
-    torch.cuda.synchronize()
-    t_e2e_sync = time.perf_counter() - t0
-    assert math.isfinite(last_loss), "training diverged in the benchmark"
+    if detailed:
+        for _ in range(3):
+            lo, hi = batch(it)
+            model._fit_step_host(Xh[lo:hi])
+            it += 1
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(n_timed):
+            lo, hi = batch(it)
+            last_loss = model._fit_step_host(Xh[lo:hi])
+            it += 1
+        torch.cuda.synchronize()
+        t_e2e_sync = time.perf_counter() - t0
+        assert math.isfinite(last_loss), "training diverged in the benchmark"
     for _ in range(3):
         lo, hi = batch(it)
         model._fit_step_host_pipelined(Xh[lo:hi])
@@ -390,7 +545,7 @@ def single_gpu_main(args, w):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     n_losses = 0
-    for s in range(steps):
+    for s in range(n_timed):
         lo, hi = batch(it)
         lv = model._fit_step_host_pipelined(Xh[lo:hi])
         if lv is not None:
@@ -401,63 +556,54 @@ def single_gpu_main(args, w):
     n_losses += 1
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
-    e2e_value = steps * triples_per_step / t_e2e
-    assert math.isfinite(last_loss) and n_losses == steps, "training diverged in the benchmark / a loss was not read back"
-    clocks = sampler.stop()
+    assert math.isfinite(last_loss) and n_losses == n_timed, "training diverged in the benchmark / a loss was not read back"
+    out["clocks"] = sampler.stop()
+    out["e2e"] = {"value": n_timed * triples_per_step / t_e2e, "unit": "triples/s", "h2d_bytes_per_step": B * 12, "d2h_bytes_per_step": 4,
+                  "ms_per_step": 1e3 * t_e2e / n_timed,
+                  "api": "EmbeddingModel._fit_step_host_pipelined -> kge_train_step_host_async / kge_train_host_wait (the loss of step t "
+                         "is read while step t+1 runs; every step copies its batch in and its loss out)"}
+    if detailed:
+        out["e2e"]["synchronous"] = {"value": n_timed * triples_per_step / t_e2e_sync, "ms_per_step": 1e3 * t_e2e_sync / n_timed,
+                                     "api": "EmbeddingModel._fit_step_host -> kge_train_step_host (returns its own loss)"}
+    out["_ctx"] = (eng, model, f, X, test)
+    return out
 
-    # roofline of the dominant training kernel.  Algorithmic bytes per launch:
-    #   fwd_bwd      : (3+eta) rows gathered + 5 rows + eta coefficients/flags written, per positive
-    #   reduce_apply : one row-sized read + 13 B of key/slot/coefficient per slot, plus w,m,v read and
-    #                  written once per DISTINCT touched row (Adam: 6 row-sized accesses)
-    n_state = {"adam": 6, "adagrad": 4, "momentum": 4, "sgd": 2}[w["opt"]]
-    bytes_fb = ((3 + eta) * 4 * K + 5 * 4 * K + 5 * eta) * B
-    bytes_apply = (3 + eta) * B * (4 * K + 13) + n_state * 4 * K * n_unique
-    bytes_survey = 36 * K * (3 + eta) * B  # SURVEY 8(d) per-positive figure (no duplicate-row reuse), for reference
-    t_red = t_apply + t_span
-    dom = "kge_fwd_bwd_kernel" if t_fb >= t_red else "kge_reduce_apply_kernel (+ span/hub reduction)"
-    dom_t, dom_b = (t_fb, bytes_fb) if t_fb >= t_red else (t_red, bytes_apply)
-    ach = dom_b / (dom_t * 1e-3) / 1e9
-    step_ms = t_cold_ms / steps
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                "traffic": load_traffic(args.workload, dom.split(" ")[0]), "traffic_source": "ncu --set full capture, profiles/traffic_r01.json",
-                "peak_source": peaks["src"], "algorithmic_bytes_per_launch": dom_b, "kernel_ms": dom_t,
-                "phases_ms": {"emit": t_emit, "fwd_bwd": t_fb, "reduce_apply": t_apply, "span_hub": t_span,
-                              "sort_done_after_emit": phases.get("sort_after_emit", 0.0), "timed_steps": n_timed},
-                "kernels": {"fwd_bwd": {"bytes": bytes_fb, "GBps": bytes_fb / (t_fb * 1e-3) / 1e9, "frac": bytes_fb / (t_fb * 1e-3) / 1e9 / peaks["hbm"]},
-                            "reduce_apply": {"bytes": bytes_apply, "GBps": bytes_apply / (t_red * 1e-3) / 1e9,
-                                             "frac": bytes_apply / (t_red * 1e-3) / 1e9 / peaks["hbm"]}},
-                "distinct_rows_per_step": n_unique,
-                "step_algorithmic_GBps": (bytes_fb + bytes_apply) / (step_ms * 1e-3) / 1e9,
-                "step_frac": (bytes_fb + bytes_apply) / (step_ms * 1e-3) / 1e9 / peaks["hbm"],
-                "step_survey_accounting_GBps": bytes_survey / (step_ms * 1e-3) / 1e9,
-                "note": "tables of cfg1-3 are L2-resident: the bytes are what the kernel loads/stores, mostly served by L2"
-                        if (E * K * 4 * 3) < (100 << 20) else "tables exceed L2: HBM-bound"}
 
+def single_gpu_main(args, w):
+    import torch
+    torch.cuda.set_device(0)
+    steps, warmup = args.steps, args.warmup
+    do_rank = not args.no_rank
+    r = train_bench_single(args, args.workload, w, steps, warmup, detailed=True)
+    eng, model, f, X, test = r.pop("_ctx")
+    peaks = load_peaks()
+    pipeline_on = os.environ.get("KGE_PIPELINE", "1")[:1] != "0"
+    cfg = config_for(args, args.workload, w, 1)
     line = {
-        "metric": TRAIN_METRIC, "value": value, "unit": "triples/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
-        "ms_per_step": t_cold_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "batch_positives": B, "eta": eta, "E": E, "R": R, "K": K,
-                   "entity_popularity": "uniform" if args.uniform else "zipf(1.0)", "optimizer": "stateful sparse " + w["opt"],
-                   "l2": "flushed before every timed step (%d MiB write)" % (L2_FLUSH_BYTES >> 20), "parallelism": "1 GPU",
-                   "step_pipelining": ("value: off (in-order steps, every step's work inside its own timed window); value_warm_l2 and "
-                                       "e2e: corruption generation + sort of step t+1 overlap step t") if pipeline_on else "off"},
-        "value_warm_l2": value_warm, "ms_per_step_warm": t_warm_ms / steps,
-        "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": B * 12, "d2h_bytes_per_step": 4,
-                "ms_per_step": 1e3 * t_e2e / steps,
-                "api": "EmbeddingModel._fit_step_host_pipelined -> kge_train_step_host_async / kge_train_host_wait (the loss of step t "
-                       "is read while step t+1 runs; every step copies its batch in and its loss out)",
-                "synchronous": {"value": steps * triples_per_step / t_e2e_sync, "ms_per_step": 1e3 * t_e2e_sync / steps,
-                                "api": "EmbeddingModel._fit_step_host -> kge_train_step_host (returns its own loss)"}},
-        "gpu_launches": launches_timed, "clocks": clocks, "roofline": roofline,
+        "metric": TRAIN_METRIC, "value": r["value"], "unit": "triples/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": cfg,
+        "measurement": {"inner_repeat": r["inner_repeat"], "timed_steps": r["timed_steps"], "timed_region_ms": r["timed_region_ms"],
+                        "step_pipelining": ("value: off (in-order steps, every step's work inside its own timed window); value_warm_l2 and "
+                                            "e2e: corruption generation + sort of step t+1 overlap step t") if pipeline_on else "off",
+                        "optimizer": "stateful sparse " + w["opt"]},
+        "value_warm_l2": r["value_warm_l2"], "ms_per_step_warm": r["ms_per_step_warm"],
+        "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": r["roofline"],
+        "rank_parity": dict(r["rank_parity"], equal_to_single_gpu=True, note="this IS the single-GPU run: the digest every N must print"),
+        "first_step_loss": r["first_step_loss"],
     }
-
-    # ---- ranking half of the metric
     if do_rank:
         line["rank"] = bench_rank(args, w, eng, model, f, X, test, peaks)
-
+    del model, f
+    torch.cuda.empty_cache()
+    if not args.no_sub:
+        if args.workload != "cfg5":
+            line["cfg5"] = sub_record_single(args, "cfg5", max(10, steps // 2), warmup)
+        line["others"] = {nm: sub_record_single(args, nm, max(10, steps // 2), warmup, brief=True)
+                          for nm in ("cfg1", "cfg2", "cfg4") if nm != args.workload}
     # ---- CPU baseline (reference-equivalent op graph on the host cores), bounded sample
     if not args.no_cpu:
+        B = batch_positives(w)
         tr, rk, cores = cpu_arm(w, X[: min(X.shape[0], 40 * B)], test if do_rank else X[:8], X if do_rank else None, steps=12, warmup=1,
                                 budget_s=15.0, rank_budget_s=12.0, do_rank=do_rank)
         line["cpu_baseline"] = {"value": tr["value"], "unit": "triples/s", "cores": cores, "kind": "port", "sample": tr["sample"]}
@@ -467,58 +613,119 @@ def single_gpu_main(args, w):
     return 0
 
 
-def multi_gpu_main(args, w, rank, world):
-    """Row-sharded table over `world` GPUs.  Weak scaling for training: every
-    rank takes its own batch of B positives per step; ranking shards the entity sweep (fixed T)."""
+def sub_record_single(args, name, steps, warmup, brief=False):
+    """Train measurement of another BASELINE config on this GPU (same protocol as the main record)."""
+    import torch
+    w = dict(WORKLOADS[name])
+    try:
+        r = train_bench_single(args, name, w, steps, warmup, detailed=False)
+    except Exception as e:  # the main record must survive a failing sub-record
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+    r.pop("_ctx")
+    torch.cuda.empty_cache()
+    rec = {"workload": "%s: %s" % (name, w["desc"]), "metric": TRAIN_METRIC, "value": r["value"], "unit": "triples/s", "ms_per_step": r["ms_per_step"],
+           "e2e": {"value": r["e2e"]["value"], "ms_per_step": r["e2e"]["ms_per_step"], "h2d_bytes_per_step": r["e2e"]["h2d_bytes_per_step"],
+                   "d2h_bytes_per_step": 4}, "value_warm_l2": r["value_warm_l2"], "timed_steps": r["timed_steps"], "n_gpus": 1,
+           "batch_positives_per_gpu": batch_positives(w)}
+    if not brief:
+        rec.update(rank_parity=dict(r["rank_parity"], equal_to_single_gpu=True), first_step_loss=r["first_step_loss"], scaling="weak",
+                   nvlink_bytes_per_gpu_per_step=0, phases_ms=None)
+    return rec
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-GPU: one process per GPU, tables column-sharded, the global batch on every GPU
+# ------------------------------------------------------------------------------------------------
+def sharded_record(args, name, w, rank, world, steps, warmup, detailed):
+    """Train measurement of one workload on `world` GPUs (weak scaling: B positives per GPU and step) + the
+    correctness witnesses: pre-training ranks and first-step loss against a single-GPU run of the same seeded tables
+    and the same global batch, computed on rank 0 inside this run."""
     import torch
     import torch.distributed as dist
     from emgraph_b200 import _lib
-    from emgraph_b200.distributed import ShardedKGE, batch_slice
+    from emgraph_b200 import distributed as D
+    from emgraph_b200.engine import model_id
     from emgraph_b200.evaluation import EvalDataset
-
     local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    peaks = load_peaks()
+    dev = torch.device("cuda", local)
     E, R, k, eta = w["E"], w["R"], w["k"], w["eta"]
     K = internal_k(w["model"], k)
-    B = int(math.ceil(w["N"] / w["batches"]))
-    steps, warmup = args.steps, args.warmup
-    do_rank = not args.no_rank
-    need = (steps * 2 + warmup + 8) * B * world
-    X = synth_triples(E, R, w["N"] if do_rank else min(w["N"], need), seed=0, zipf=not args.uniform)
-    sk = ShardedKGE(w["model"], k, eta, w["loss"], w["opt"], E, R, B, lr=w["lr"], margin=w["margin"], seed=0, device=local)
-    eng, dev = sk.eng, sk.eng.tdev
-    g = torch.Generator(device=dev).manual_seed(100 + rank)
-    lim_e, lim_r = math.sqrt(6.0 / (E + K)), math.sqrt(6.0 / (R + K))
-    sk.ent.tensor.uniform_(-lim_e, lim_e, generator=g)
-    sk.rel.copy_(torch.from_numpy(glorot(R, K, 3)).to(dev))
-    dist.barrier()
+    B = batch_positives(w)
+    n = B * world
+    X, test = make_dataset(w, (steps * 4 + warmup + 16) * n, with_test=True, zipf=not args.uniform)
+    kc = D.dim_width(k, world)
+    c0, c1 = D.dim_range(k, world, rank)
+    ent_slice = seeded_table(E, w["model"], k, dev, TABLE_SEED, c0, c1, pad_to=kc)
+    rel_slice = seeded_table(R, w["model"], k, dev, TABLE_SEED + 1, c0, c1, pad_to=kc)
+    sk = D.ShardedKGE(w["model"], k, eta, w["loss"], w["opt"], E, R, B, lr=w["lr"], margin=w["margin"], seed=0, device=local,
+                      chunks=args.chunks, ent_slice=ent_slice, rel_slice=rel_slice)
+    eng = sk.eng
     Xd = torch.from_numpy(X).to(dev)
     Xh = torch.from_numpy(X).pin_memory()
+    nb = max(1, X.shape[0] // n)
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    use_tc = ((w["model"] != "TransE") if args.rank_tc < 0 else bool(args.rank_tc)) and eng.has_tensor_core_rank()
+
+    def gbatch(i):
+        b = i % nb
+        return b * n, (b + 1) * n
+
+    # ---- witnesses.  Rank 0 holds the whole seeded table for a moment and runs the single-GPU kernels on it.
+    ds = EvalDataset(test, X)
+    ds.build_filter(eng, E, R)
+    test_d = ds.test_device(dev)
+    ranks_sh = sk.rank(test_d, side=0, strategy=0, filtered=True, use_tensor_cores=use_tc).cpu().numpy()
+    full_ent = sk._gather_cols(sk.ent)
+    full_rel = sk._gather_cols(sk.rel)
+    single = {}
+    if rank == 0:
+        r1 = eng.rank(model_id(w["model"]), k, full_ent, full_rel, test_d, side=0, strategy=0, filtered=True, use_tensor_cores=use_tc).cpu().numpy()
+        single["ranks_equal"] = bool(np.array_equal(r1, ranks_sh))
+        single["digest"] = ranks_digest(r1)
+        lo, hi = gbatch(0)
+        loss1 = torch.zeros(1, device=dev)
+        a = eng.train_args(model=model_id(w["model"]), loss=_lib.LOSS_IDS[w["loss"]], opt=_lib.OPT_IDS[w["opt"]], k=k, eta=eta, ent=full_ent,
+                           rel=full_rel, pos=Xd[lo:hi].contiguous(), loss_out=loss1, flags=_lib.F_NO_UPDATE, margin=w["margin"], lr=w["lr"],
+                           seed=0, step=1)
+        eng.train_step(a)
+        single["first_step_loss"] = float(loss1.item())
+    del full_ent, full_rel
+    torch.cuda.empty_cache()
+    dist.barrier()
+
     it = 0
-
-    def my_batch(i):
-        return batch_slice(X.shape[0], world, rank, i, B)
-
-    for _ in range(warmup):
-        lo, hi = my_batch(it)
-        sk.train_step(Xd[lo:hi])
+    first_loss = None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for s_ in range(warmup):
+        lo, hi = gbatch(it)
+        if s_ == warmup - 1:
+            e0.record()
+        sk.train_step(Xd[lo:hi], pos_is_global=True)
+        if s_ == warmup - 1:
+            e1.record()
+        if it == 0:
+            first_loss = float(sk.loss_dev.item())
         it += 1
     torch.cuda.synchronize()
+    est = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    rep = inner_repeat(steps, float(est.item()))
+    n_timed = steps * rep
     dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
+
+    # ---- value: L2 flushed before every step, in-order steps (no prologue hiding in the untimed flush), max over ranks
+    sk.pipeline = False
     l0 = eng.launches
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_timed)]
     torch.cuda.synchronize()
     dist.barrier()
-    for s in range(steps):
+    for s in range(n_timed):
         flush.fill_(float(s))
-        lo, hi = my_batch(it)
+        lo, hi = gbatch(it)
         evs[s][0].record()
-        sk.train_step(Xd[lo:hi])
+        sk.train_step(Xd[lo:hi], pos_is_global=True)
         evs[s][1].record()
         it += 1
     torch.cuda.synchronize()
@@ -527,38 +734,73 @@ def multi_gpu_main(args, w, rank, world):
     t_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev)
     dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     t_ms = float(t_ms.item())
-    triples_per_step = world * B * (1 + eta)
-    value = steps * triples_per_step / (t_ms * 1e-3)
+    triples_per_step = n * (1 + eta)
+    out = {"value": n_timed * triples_per_step / (t_ms * 1e-3), "ms_per_step": t_ms / n_timed, "inner_repeat": rep, "timed_steps": n_timed,
+           "timed_region_ms": t_ms, "launches": launches}
 
-    # e2e: every step the rank's batch comes from pinned host memory and the global loss is read back
-    stage = torch.empty((B, 3), dtype=torch.int32, device=dev)
+    # ---- warm: back to back, pipelined (emit + sort of step t+1 beside step t), one event pair, max over ranks
+    sk.pipeline = True
     for _ in range(2):
-        lo, hi = my_batch(it)
-        stage.copy_(Xh[lo:hi], non_blocking=True)
-        float(sk.train_step(stage).item())
+        lo, hi = gbatch(it)
+        sk.train_step(Xd[lo:hi], pos_is_global=True)
         it += 1
     torch.cuda.synchronize()
     dist.barrier()
-    t0 = time.perf_counter()
-    for s in range(steps):
-        lo, hi = my_batch(it)
-        stage.copy_(Xh[lo:hi], non_blocking=True)
-        last = float(sk.train_step(stage).item())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(n_timed):
+        lo, hi = gbatch(it)
+        sk.train_step(Xd[lo:hi], pos_is_global=True)
         it += 1
+    e1.record()
+    torch.cuda.synchronize()
+    tw = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    out["value_warm_l2"] = n_timed * triples_per_step / (float(tw.item()) * 1e-3)
+    out["ms_per_step_warm"] = float(tw.item()) / n_timed
+
+    # ---- e2e: every rank copies ITS batch from pinned host memory every step, the global loss is read back every step
+    # (one step late: the loss of step t is read while step t+1 runs)
+    def my_batch(i):
+        lo, _ = gbatch(i)
+        return lo + rank * B, lo + (rank + 1) * B
+
+    for _ in range(3):
+        lo, hi = my_batch(it)
+        sk.train_step_host(Xh[lo:hi])
+        it += 1
+    sk.host_flush()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    n_losses, last = 0, 0.0
+    for s in range(n_timed):
+        lo, hi = my_batch(it)
+        lv = sk.train_step_host(Xh[lo:hi])
+        if lv is not None:
+            last = lv
+            n_losses += 1
+        it += 1
+    last = sk.host_flush()
+    n_losses += 1
     torch.cuda.synchronize()
     dist.barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     t_e2e = float(t_e2e.item())
-    assert math.isfinite(last), "training diverged in the benchmark"
-    clocks = sampler.stop()
+    assert math.isfinite(last) and n_losses == n_timed, "training diverged in the benchmark / a loss was not read back"
+    out["clocks"] = sampler.stop()
+    out["e2e"] = {"value": n_timed * triples_per_step / t_e2e, "unit": "triples/s", "h2d_bytes_per_step": B * 12 * world,
+                  "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * t_e2e / n_timed,
+                  "api": "ShardedKGE.train_step_host (every rank copies its own batch in, NCCL all-gather of the batches, loss read back one step late)"}
 
-    # per-phase time inside the real step (CUDA events on the launching stream, L2 flushed, max over ranks)
+    # ---- per-phase time inside the real step (CUDA events on the launching stream, L2 flushed, max over ranks)
+    sk.pipeline = False
     sk.timing = True
-    for s in range(min(steps, 10)):
+    for s in range(min(n_timed, 20)):
         flush.fill_(float(s))
-        lo, hi = my_batch(it)
-        sk.train_step(Xd[lo:hi])
+        lo, hi = gbatch(it)
+        sk.train_step(Xd[lo:hi], pos_is_global=True)
         it += 1
     ph = sk.phase_times()
     sk.timing = False
@@ -566,50 +808,94 @@ def multi_gpu_main(args, w, rank, world):
     pt = torch.tensor([ph[k_] for k_ in names], device=dev)
     dist.all_reduce(pt, op=dist.ReduceOp.MAX)
     ph = {k_: float(v) for k_, v in zip(names, pt.tolist())}
-    # roofline of the exchange: rows pushed to the other ranks cross NVLink once ((world-1)/world of the
-    # entity slots), plus the all-gathered [Qo|Qs|coef|keep] tails
-    nv_bytes = (2 + eta) * 4 * K * B * (world - 1) / world
-    t_push = ph.get("push", 0.0) + ph.get("push_barrier", 0.0)
-    roofline = {"bound": "nvlink", "kernel": "kge_push_rows_kernel (owner-side row push, peer stores)",
-                "achieved": nv_bytes / (max(t_push, 1e-6) * 1e-3) / 1e9,
-                "peak": 770.0, "unit": "GB/s per direction per GPU (measured peer copy, B200_PROFILING.md)",
-                "frac": nv_bytes / (max(t_push, 1e-6) * 1e-3) / 1e9 / 770.0, "traffic": None, "kernel_ms": t_push,
-                "algorithmic_bytes_per_launch": nv_bytes, "phases_ms_max_over_ranks": ph,
-                "tails_allgather_bytes": (world - 1) * sk.tail_stride * 4}
+    out["phases_ms_max_over_ranks"] = ph
+    payload = 4 * (1 + eta) * n
+    out["nvlink_bytes_per_gpu_per_step"] = int(2 * (world - 1) / world * payload)
+    out["allreduce_payload_bytes"] = payload
+    # witnesses
+    flags = torch.tensor([1.0 if single.get("ranks_equal", False) else 0.0, single.get("first_step_loss", 0.0)], device=dev, dtype=torch.float64)
+    dist.broadcast(flags, 0)
+    l_single = float(flags[1].item())
+    out["rank_parity"] = dict(ranks_digest(ranks_sh), equal_to_single_gpu=bool(flags[0].item() == 1.0),
+                              how="rank 0 gathered the seeded tables and ran the single-GPU sweep on the same test set in this run")
+    out["first_step_loss"] = first_loss
+    out["first_step_loss_single_gpu"] = l_single
+    out["first_step_loss_rel_err"] = abs(first_loss - l_single) / max(abs(l_single), 1e-30)
+    assert out["first_step_loss_rel_err"] < 1e-5, "sharded first-step loss %r != single-GPU loss %r on the concatenated batch" % (first_loss, l_single)
+    assert out["rank_parity"]["equal_to_single_gpu"], "sharded pre-training ranks differ from the single-GPU ranks"
 
+    if detailed:
+        # per-GPU algorithmic HBM bytes of the step: both phase kernels gather (3+eta) row slices per
+        # positive of the GLOBAL batch, the reduction reads one slice per slot and w, m, v of every distinct touched row
+        Kc = sk.Kc
+        S = (3 + eta) * n
+        keys = torch.empty(S, dtype=torch.int32, device=dev)
+        lo, hi = gbatch(it)
+        a = sk.make_args(Xd[lo:hi], step=sk.step + 1)
+        eng.train_emit(a, keys)
+        n_unique = int(torch.unique(keys).numel())
+        n_state = {"adam": 6, "adagrad": 4, "momentum": 4, "sgd": 2}[w["opt"]]
+        b_part = ((3 + eta) * 4 * Kc + 4 * (1 + eta) + 5 * eta) * n
+        b_bwd = ((3 + eta) * 4 * Kc + 5 * 4 * Kc + 4 * (1 + eta) + 10 * eta) * n
+        b_apply = S * (4 * Kc + 13) + n_state * 4 * Kc * n_unique
+        peaks = load_peaks()
+        step_ms = out["ms_per_step"]
+        t_apply = ph.get("reduce_apply", step_ms)
+        out["roofline"] = {"bound": "hbm", "kernel": "kge_reduce_apply_group_kernel (+ span/hub reduction) on the column slice" if Kc <= 64
+                           else "kge_reduce_apply_kernel (+ span/hub reduction) on the column slice",
+                           "achieved": b_apply / (t_apply * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s per GPU",
+                           "frac": b_apply / (t_apply * 1e-3) / 1e9 / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
+                           "algorithmic_bytes_per_launch": b_apply, "kernel_ms": t_apply, "distinct_rows_per_step": n_unique,
+                           "bytes_per_gpu": {"partial": b_part, "backward": b_bwd, "reduce_apply": b_apply},
+                           "step_algorithmic_GBps_per_gpu": (b_part + b_bwd + b_apply) / (step_ms * 1e-3) / 1e9,
+                           "step_frac": (b_part + b_bwd + b_apply) / (step_ms * 1e-3) / 1e9 / peaks["hbm"],
+                           "nvlink": {"bytes_per_gpu_per_step": out["nvlink_bytes_per_gpu_per_step"], "peak_GBps": 770.0,
+                                      "time_at_peak_ms": out["nvlink_bytes_per_gpu_per_step"] / 770e9 * 1e3}}
+    out["_ctx"] = (sk, ds, X, test, use_tc)
+    return out
+
+
+def multi_gpu_main(args, w, rank, world):
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    steps, warmup = args.steps, args.warmup
+    do_rank = not args.no_rank
+    r = sharded_record(args, args.workload, w, rank, world, steps, warmup, detailed=True)
+    sk, ds, X, test, use_tc = r.pop("_ctx")
+    eng = sk.eng
+    E, R, k, eta = w["E"], w["R"], w["k"], w["eta"]
+    K = internal_k(w["model"], k)
     line = {
-        "metric": TRAIN_METRIC, "value": value, "unit": "triples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "batch_positives_per_gpu": B, "global_batch": B * world, "eta": eta,
-                   "E": E, "R": R, "K": K, "entity_popularity": "uniform" if args.uniform else "zipf(1.0)",
-                   "optimizer": "stateful sparse " + w["opt"], "l2": "flushed before every timed step (%d MiB write)" % (L2_FLUSH_BYTES >> 20),
-                   "parallelism": "dp%d, entity table + optimizer state row-sharded, owner-push row exchange over peer memory" % world},
-        "e2e": {"value": steps * triples_per_step / t_e2e, "unit": "triples/s", "h2d_bytes_per_step": B * 12 * world,
-                "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * t_e2e / steps, "api": "ShardedKGE.train_step (host batch, loss read back)"},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "metric": TRAIN_METRIC, "value": r["value"], "unit": "triples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_for(args, args.workload, w, world),
+        "measurement": {"inner_repeat": r["inner_repeat"], "timed_steps": r["timed_steps"], "timed_region_ms": r["timed_region_ms"],
+                        "chunks": args.chunks, "optimizer": "stateful sparse " + w["opt"],
+                        "step_pipelining": "value: off (in-order steps); value_warm_l2: corruption generation + sort of step t+1 overlap step t"},
+        "value_warm_l2": r["value_warm_l2"], "ms_per_step_warm": r["ms_per_step_warm"], "e2e": r["e2e"],
+        "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": r["roofline"], "rank_parity": r["rank_parity"],
+        "first_step_loss": r["first_step_loss"], "first_step_loss_single_gpu": r["first_step_loss_single_gpu"],
+        "phases_ms_max_over_ranks": r["phases_ms_max_over_ranks"], "nvlink_bytes_per_gpu_per_step": r["nvlink_bytes_per_gpu_per_step"],
     }
 
     if do_rank:
         T = w["T"]
-        rng = np.random.Generator(np.random.PCG64(1))
-        test = X[rng.permutation(X.shape[0])[:T]].copy()
-        ds = EvalDataset(test, X)
-        t0 = time.perf_counter()
-        ds.build_filter(eng, E, R)
-        torch.cuda.synchronize()
-        t_filter = time.perf_counter() - t0
-        use_tc = ((w["model"] != "TransE") if args.rank_tc < 0 else bool(args.rank_tc)) and eng.has_tensor_core_rank()
+        flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+        t_filter = 0.0
         test_d = ds.test_device(dev)
         test_h = ds.test_host_pinned()
         for _ in range(2):
             ranks = sk.rank(test_d, side=0, strategy=0, filtered=True, use_tensor_cores=use_tc)
         torch.cuda.synchronize()
         dist.barrier()
-        n = max(1, args.rank_steps)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        nr = max(1, args.rank_steps)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nr)]
         l0 = eng.launches
-        for s in range(n):
+        for s in range(nr):
             flush.fill_(float(s))
             evs[s][0].record()
             ranks = sk.rank(test_d, side=0, strategy=0, filtered=True, use_tensor_cores=use_tc)
@@ -617,27 +903,29 @@ def multi_gpu_main(args, w, rank, world):
         torch.cuda.synchronize()
         dist.barrier()
         r_launches = (eng.launches - l0) * world
-        tr = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / n], device=dev)
+        tr = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / nr], device=dev)
         dist.all_reduce(tr, op=dist.ReduceOp.MAX)
         tr = float(tr.item())
         stage_t = torch.empty((T, 3), dtype=torch.int32, device=dev)
         out_h = torch.empty((T, 2), dtype=torch.int32).pin_memory()
         dist.barrier()
         t0 = time.perf_counter()
-        for s in range(n):
+        for s in range(nr):
             stage_t.copy_(test_h, non_blocking=True)
             out_h.copy_(sk.rank(stage_t, side=0, strategy=0, filtered=True, use_tensor_cores=use_tc))
             torch.cuda.synchronize()
         dist.barrier()
-        te = torch.tensor([(time.perf_counter() - t0) / n], device=dev)
+        te = torch.tensor([(time.perf_counter() - t0) / nr], device=dev)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         te = float(te.item())
         rk = out_h.numpy()
         assert rk.min() >= 1
         flops = 4.0 * E * K * T
-        peak = peaks["bf16"] / 2.0 * world
-        line["rank"] = {"metric": RANK_METRIC, "value": T / (tr * 1e-3), "unit": "test triples/s", "ms_per_step": tr, "steps": n, "T": T,
-                        "scaling": "strong (entity sweep sharded by row range, counts all-reduced)", "corrupt_side": "s,o",
+        tf32 = measure_tf32_peak(dev) if use_tc else None
+        peak = (tf32 if tf32 else 148 * 128 * 2 * 1.965e9 / 1e12) * world
+        line["rank"] = {"metric": RANK_METRIC, "value": T / (tr * 1e-3), "unit": "test triples/s", "ms_per_step": tr, "steps": nr, "T": T,
+                        "scaling": "strong (the trained column slices are transposed once into row-range shards -- cached, outside the timed "
+                                   "sweep -- every GPU sweeps its rows, counts all-reduced)", "corrupt_side": "s,o",
                         "filter_triples": int(X.shape[0]), "filter_build_ms": 1e3 * t_filter, "tensor_cores": bool(use_tc),
                         "mrr": float(np.mean(1.0 / rk.reshape(-1))),
                         "e2e": {"value": T / te, "unit": "test triples/s", "h2d_bytes_per_step": T * 12 * world, "d2h_bytes_per_step": T * 8 * world,
@@ -645,7 +933,23 @@ def multi_gpu_main(args, w, rank, world):
                         "gpu_launches": r_launches,
                         "roofline": {"bound": "tensor" if use_tc else "fp32-alu", "achieved": flops / (tr * 1e-3) / 1e12, "peak": peak,
                                      "unit": "TFLOP/s (logical; x3 TF32 MMAs issued), whole job", "frac": flops / (tr * 1e-3) / 1e12 / peak,
+                                     "peak_source": "cuBLAS TF32 GEMM 8192^3 measured in this run x %d GPUs" % world if use_tc else "fp32 FMA issue rate",
                                      "traffic": None, "kernel_ms": tr}}
+    del sk, ds
+    torch.cuda.empty_cache()
+    if not args.no_sub and args.workload != "cfg5":
+        w5 = dict(WORKLOADS["cfg5"])
+        try:
+            r5 = sharded_record(args, "cfg5", w5, rank, world, max(10, steps // 2), warmup, detailed=True)
+            r5.pop("_ctx")
+            line["cfg5"] = {"workload": "cfg5: %s" % w5["desc"], "metric": TRAIN_METRIC, "unit": "triples/s", "n_gpus": world, "scaling": "weak",
+                            "batch_positives_per_gpu": batch_positives(w5),
+                            **{k_: r5[k_] for k_ in ("value", "ms_per_step", "value_warm_l2", "ms_per_step_warm", "timed_steps", "rank_parity",
+                                                     "first_step_loss", "first_step_loss_single_gpu", "phases_ms_max_over_ranks",
+                                                     "nvlink_bytes_per_gpu_per_step", "roofline")},
+                            "e2e": {k_: r5["e2e"][k_] for k_ in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}}
+        except Exception as e:
+            line["cfg5"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     dist.barrier()
@@ -656,7 +960,6 @@ def multi_gpu_main(args, w, rank, world):
 def bench_rank(args, w, eng, model, f, X, test, peaks):
     """Filtered 's,o' ranking of T test triples against all E entities; filter = all synthetic triples."""
     import torch
-    from emgraph_b200 import _lib
     from emgraph_b200.evaluation import EvalDataset
     dev = eng.tdev
     E, R, k = w["E"], w["R"], w["k"]
@@ -678,12 +981,17 @@ def bench_rank(args, w, eng, model, f, X, test, peaks):
     test_d = ds.test_device(dev)
     mid = model._model_id()
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
-    n = max(1, args.rank_steps)
     counts = torch.empty((T, 2, 4), dtype=torch.int32, device=dev)
-    for _ in range(2):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(2):
+        if i == 1:
+            e0.record()
         eng.rank_counts(mid, k, ent, rel, test_d, side=0, filtered=True, use_tensor_cores=use_tc, counts=counts)
         eng.rank_finalize(counts, side=0, strategy=0, filtered=True)
+        if i == 1:
+            e1.record()
     torch.cuda.synchronize()
+    n = max(1, args.rank_steps) * inner_repeat(max(1, args.rank_steps), e0.elapsed_time(e1))
     l0 = eng.launches
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n)]
     for s in range(n):
@@ -717,11 +1025,14 @@ def bench_rank(args, w, eng, model, f, X, test, peaks):
         roof = {"bound": "fp32-alu", "achieved": ach, "peak": peak, "unit": "T lane-instr/s (FADD sub + FADD |.| accumulate per element)",
                 "frac": ach / peak, "traffic": None, "peak_source": "148 SMs x 128 fp32 lanes x 1.965 GHz (max SM clock)"}
     elif use_tc:
-        # 3xTF32: three tensor-core MMAs per logical MAC; TF32 dense peak = 1/2 of the measured bf16 peak
-        peak = peaks["bf16"] / 2.0
+        # three tensor-core MMAs per logical MAC (hi*hi + hi*lo + lo*hi); the denominator is the dense TF32 rate of this GPU
+        # measured in this run (cuBLAS fp32 GEMM with TF32 tensor cores, same recipe as MEASURED_PEAKS.json's bf16)
+        peak = measure_tf32_peak(dev)
         ach = flops / (t_sweep_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (logical fp32-accurate flops; x3 TF32 MMAs issued)",
-                "frac": ach / peak, "frac_issued_3x": 3 * ach / peak, "traffic": load_traffic(args.workload, "kge_rank_tc_kernel"), "peak_source": peaks["src"] + " bf16/2"}
+        traffic, tsrc = load_traffic(args.workload, "kge_rank_tc_kernel")
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s (logical fp32-accurate flops; x3 tensor-core MMAs issued)",
+                "frac": ach / peak, "frac_issued_3x": 3 * ach / peak, "traffic": traffic, "traffic_source": tsrc,
+                "peak_source": "cuBLAS TF32 GEMM 8192^3, best of 10, measured in this run (bf16 peak / 2 would be %.0f)" % (peaks["bf16"] / 2.0)}
     else:
         peak = 148 * 128 * 2 * 1.965e9 / 1e12
         ach = flops / (t_sweep_ms * 1e-3) / 1e12

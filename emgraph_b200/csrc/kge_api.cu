@@ -117,7 +117,7 @@ __device__ __forceinline__ float score_triple_warp(int model, int k, int K, cons
 }
 
 __global__ void kge_score_kernel(int model, int k, TableView ent, const float* __restrict__ rel,
-                                 const int32_t* __restrict__ triples, int64_t n, float* __restrict__ out) {
+                                 const int32_t* __restrict__ triples, int64_t n, float* __restrict__ out, int nl) {
     const int lane = threadIdx.x & 31;
     const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= n) return;
@@ -126,12 +126,18 @@ __global__ void kge_score_kernel(int model, int k, TableView ent, const float* _
     const float* p = rel + (size_t)triples[3 * t + 1] * K;
     const float* o = table_row(ent, triples[3 * t + 2]);
     float f = score_triple_warp(model, k, K, s, p, o, lane);
-    if (lane == 0) out[t] = f;
+    if (lane == 0) out[t] = apply_nl(nl, f);
 }
 
 extern "C" int kge_score(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
                          const int32_t* triples, int64_t n, float* out, void* stream) {
+    return kge_predict(ctx, model, k, ent, rel, R, triples, n, KGE_NL_LINEAR, out, stream);
+}
+
+extern "C" int kge_predict(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
+                           const int32_t* triples, int64_t n, int non_linearity, float* out, void* stream) {
     KGE_REQUIRE(ctx != nullptr, "kge_score: null ctx");
+    KGE_REQUIRE(non_linearity >= KGE_NL_LINEAR && non_linearity <= KGE_NL_SOFTPLUS, "Invalid non-linearity");
     KGE_REQUIRE(model >= KGE_TRANSE_L1 && model <= KGE_HOLE, "kge_score: unknown model %d", model);
     KGE_REQUIRE(ent != nullptr && rel != nullptr && out != nullptr, "kge_score: null tensor");
     KGE_REQUIRE(ent->K == model_row_width(model, k), "kge_score: table width %d != internal_k %d", ent->K,
@@ -141,7 +147,7 @@ extern "C" int kge_score(kge_ctx* ctx, int model, int k, const kge_table* ent, c
     KGE_REQUIRE(triples != nullptr, "kge_score: null triples");
     const int warps = 8;
     kge_score_kernel<<<(unsigned)((n + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
-        model, k, make_view(*ent), rel, triples, n, out);
+        model, k, make_view(*ent), rel, triples, n, out, non_linearity);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

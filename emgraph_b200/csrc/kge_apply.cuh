@@ -42,7 +42,10 @@ struct ApplyParams {
     int reg_p;
     float reg_lambda_ent, reg_lambda_rel;
     uint32_t* touched;
+    int prefetch;  // 1: L2-prefetch the optimizer rows of a chunk before walking its runs
 };
+
+__device__ __forceinline__ bool prefetch_on(const ApplyParams& P) { return P.prefetch != 0; }
 
 __device__ __forceinline__ float reg_grad1(float w, int p, float lam) {
     if (p == 2) return 2.f * lam * w;
@@ -127,6 +130,13 @@ __device__ __forceinline__ void ldg_vec(float (&d)[V], const float* p) {
     }
 }
 
+// L2 prefetch of one 128-byte line (no register, no dependency): used to put the optimizer rows of a whole chunk of
+// sorted slots in flight before the runs are walked one after the other
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// prefetch w (and m, v when the optimizer reads them) of row `key` -- K floats each
+__device__ __forceinline__ void prefetch_row_state(const ApplyParams& P, int32_t key, bool need_m, bool need_v);
+
 // contribution of one slot to V columns of the gradient; rc = current value of the row being updated.
 // Plain gradient rows (mode 0) carry c = 1, so the trilinear models need no branch at all.
 template <int V, int TMODE>
@@ -189,4 +199,15 @@ __device__ __forceinline__ void reg_add(const ApplyParams& P, bool is_rel, float
 }
 __device__ __forceinline__ void mark_touched(const ApplyParams& P, int32_t key) {
     if (P.touched != nullptr) atomicOr(P.touched + (key >> 5), 1u << (key & 31));
+}
+
+__device__ __forceinline__ void prefetch_row_state(const ApplyParams& P, int32_t key, bool need_m, bool need_v) {
+    const RowPtrs r = resolve_row(P, key);
+    if (!r.owned) return;
+    const int K = P.ent.K;
+    for (int off = 0; off < K; off += 32) {
+        prefetch_l2(r.w + off);
+        if (need_m && r.m != nullptr) prefetch_l2(r.m + off);
+        if (need_v && r.v != nullptr) prefetch_l2(r.v + off);
+    }
 }

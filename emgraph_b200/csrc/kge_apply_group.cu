@@ -55,6 +55,12 @@ __global__ void __launch_bounds__(KGE_RAG_THREADS) kge_reduce_apply_group_kernel
     const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
     const int cc = min(lg * V, K - V);  // lanes past the end of the row read a valid duplicate and never store
     const bool col_ok = lg * V < K;
+    // The runs of a chunk are walked one after the other and each needs its row's w, m, v from HBM: put all of them in
+    // flight now (one L2 prefetch per 128-byte line, issued by the lane that holds the run head), so that the walk below
+    // finds them in L2 instead of paying one DRAM round trip per run
+    if (!no_update && prefetch_on(P))
+        for (int t = lg; t < cnt; t += GS)
+            if ((heads >> t) & 1u) prefetch_row_state(P, skey[gib][t], need_m, need_v);
 
     while (heads) {
         const int a = __ffs(heads) - 1;

@@ -140,6 +140,9 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
     const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
     const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
     const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
+    // the optimizer rows of every run that starts in this chunk go in flight now (L2 prefetch by the lane that holds the
+    // run head): the runs are walked one after the other below, and each would otherwise pay its own DRAM round trip
+    if (head && !no_update && prefetch_on(P)) prefetch_row_state(P, key, need_m, need_v);
 
     while (heads) {
         const int a = __ffs(heads) - 1;
@@ -1063,6 +1066,14 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
     P.reg_lambda_ent = a->reg_lambda_ent;
     P.reg_lambda_rel = a->reg_lambda_rel;
     P.touched = nullptr;
+    {   // KGE_APPLY_PREFETCH=0 switches the chunk-wide L2 prefetch of the optimizer rows off (A/B)
+        static int pf = -1;
+        if (pf < 0) {
+            const char* e = getenv("KGE_APPLY_PREFETCH");
+            pf = (e != nullptr && e[0] == '0') ? 0 : 1;
+        }
+        P.prefetch = pf;
+    }
     const bool reg = a->reg_p > 0 && (a->reg_lambda_ent != 0.f || a->reg_lambda_rel != 0.f);
     if (!reg) P.reg_p = 0;
     if (reg) {

@@ -385,7 +385,7 @@ class ShardedKGE:
 
     def __init__(self, model, k, eta, loss, optimizer, E, R, n_per_rank, *, lr=5e-4, margin=1.0, norm=1, seed=0,
                  init_ent=None, init_rel=None, device=None, chunks=2, alpha=0.5, non_linearity="linear", side="s,o",
-                 optimizer_params=None, pipeline=True, group=None):
+                 optimizer_params=None, pipeline=True, group=None, ent_slice=None, rel_slice=None):
         self.group = group
         assert dist.is_initialized(), "init torch.distributed first"
         self.rank_id, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -406,8 +406,10 @@ class ShardedKGE:
             full = full_or_fn() if callable(full_or_fn) else full_or_fn
             return torch.from_numpy(np.ascontiguousarray(slice_columns(full, model, self.k, self.world, self.rank_id), dtype=np.float32)).to(dev)
 
-        self.ent = local(init_ent, self.E)
-        self.rel = local(init_rel, self.R)
+        # ent_slice / rel_slice: this rank's [rows, Kc] slices already on the device (large tables are drawn per rank)
+        self.ent = local(init_ent, self.E) if ent_slice is None else ent_slice.to(dev).contiguous()
+        self.rel = local(init_rel, self.R) if rel_slice is None else rel_slice.to(dev).contiguous()
+        assert tuple(self.ent.shape) == (self.E, self.Kc) and tuple(self.rel.shape) == (self.R, self.Kc)
         opt = _lib.OPT_IDS[optimizer]
         self.state = {}
         if opt == 0:
@@ -500,6 +502,38 @@ class ShardedKGE:
         n = max(1, len(self._marks))
         self._marks = []
         return {k: v / n for k, v in acc.items()}
+
+    def train_step_host(self, pos_host):
+        """The step fed the way the reference feeds it (models/EmbeddingModel.py:1329-1337, :1421): this rank's batch comes
+        from (pinned) host memory and the batch loss goes back to the host -- one step late, so that the GPU always has the
+        next step queued: returns the loss of the step submitted one call earlier (None on the first call);
+        host_flush() returns the last one.  Every step copies its batch in and its loss out."""
+        assert (not pos_host.is_cuda) and pos_host.dtype == torch.int32 and pos_host.shape[0] == self.n_local
+        dev = self.eng.tdev
+        if not hasattr(self, "_hb"):
+            self._hb = dict(stage=[torch.empty((self.n_local, 3), dtype=torch.int32, device=dev) for _ in range(2)],
+                            ring=torch.zeros(4, dtype=torch.float32).pin_memory(),
+                            ev=[torch.cuda.Event() for _ in range(4)], pending=None, tick=0)
+        hb = self._hb
+        i, st = hb["tick"] % 4, hb["stage"][hb["tick"] % 2]
+        hb["tick"] += 1
+        st.copy_(pos_host, non_blocking=True)
+        self.train_step(st)
+        hb["ring"][i:i + 1].copy_(self.loss_dev, non_blocking=True)
+        hb["ev"][i].record()
+        prev, hb["pending"] = hb["pending"], i
+        if prev is None:
+            return None
+        hb["ev"][prev].synchronize()
+        return float(hb["ring"][prev])
+
+    def host_flush(self):
+        hb = getattr(self, "_hb", None)
+        if hb is None or hb["pending"] is None:
+            return None
+        prev, hb["pending"] = hb["pending"], None
+        hb["ev"][prev].synchronize()
+        return float(hb["ring"][prev])
 
     # ---------------------------------------------------------------- parameters
     def _gather_cols(self, t):

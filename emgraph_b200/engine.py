@@ -121,14 +121,15 @@ class Engine:
         return int(self.lib.kge_ctx_workspace_bytes(self._h))
 
     # ---------------------------------------------------------------- scoring
-    def score(self, model: int, k: int, ent, rel, triples):
-        """ent: tensor [E,K] or KgeTable; returns fp32 CUDA tensor [n]."""
+    def score(self, model: int, k: int, ent, rel, triples, non_linearity: int = 0):
+        """ent: tensor [E,K] or KgeTable; returns fp32 CUDA tensor [n] (nl(score) when non_linearity != 0)."""
         tb = ent if isinstance(ent, KgeTable) else make_table(ent)
         _chk_f32(rel, "rel")
         _chk_i32(triples, "triples")
         n = triples.shape[0]
         out = torch.empty(n, dtype=torch.float32, device=self.tdev)
-        check(self.lib.kge_score(self._h, model, k, C.byref(tb), _ptr(rel), rel.shape[0], _ptr(triples), n, _ptr(out), _stream()))
+        check(self.lib.kge_predict(self._h, model, k, C.byref(tb), _ptr(rel), rel.shape[0], _ptr(triples), n, int(non_linearity),
+                                   _ptr(out), _stream()))
         self.launches += 1 if n else 0
         return out
 

@@ -857,7 +857,15 @@ class EmbeddingModel:
         Xi = X.astype(np.int32) if from_idx else to_idx(X, self._ent_index, self._rel_index)
         eng = get_engine(self.engine_params.get("device"))
         ent, rel = self._device_params()
-        out = eng.score(self._model_id(), self.k, ent, rel, to_dev_i32(Xi, eng.tdev))
+        if from_idx and Xi.size:
+            # the reference's gather raises on an id outside the tables (tf.nn.embedding_lookup, models/EmbeddingModel.py:504);
+            # the kernel does not range-check, so the ids the user hands in are validated here
+            E, R = int(ent.shape[0]), int(rel.shape[0])
+            if Xi.min() < 0 or Xi[:, 0].max() >= E or Xi[:, 2].max() >= E or Xi[:, 1].max() >= R:
+                raise ValueError("predict(from_idx=True): ids outside the fitted tables (entities 0..%d, relations 0..%d)" % (E - 1, R - 1))
+        # the non-linearity is applied to the returned scores as the reference does (models/EmbeddingModel.py:2135-2147; its
+        # tanh branch reads a non-existent attribute and raises -- the intended tanh(score) is returned here)
+        out = eng.score(self._model_id(), self.k, ent, rel, to_dev_i32(Xi, eng.tdev), non_linearity=self._non_linearity())
         return out.cpu().numpy()
 
     # ---- get_embeddings (models/EmbeddingModel.py:455-488)

@@ -154,6 +154,10 @@ int64_t kge_ctx_workspace_bytes(kge_ctx* ctx);
 /* EmbeddingModel.predict / _lookup_embeddings + _fn  (models/EmbeddingModel.py:2101-2147, :490-533) */
 int kge_score(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
               const int32_t* triples, int64_t n, float* out, void* stream);
+/* the same with embedding_model_params['non_linearity'] applied to the scores, as EmbeddingModel.predict returns them
+ * (models/EmbeddingModel.py:2135-2147; KGE_NL_*).  Ids are not range-checked: the caller validates 0 <= s,o < E, 0 <= p < R. */
+int kge_predict(kge_ctx* ctx, int model, int k, const kge_table* ent, const float* rel, int64_t R,
+                const int32_t* triples, int64_t n, int non_linearity, float* out, void* stream);
 
 /* Whole step on one GPU (n_shards == 1): corruption generation -> fused score/loss/backward ->
  * duplicate-row segmented reduction -> sparse row-wise optimizer. */

@@ -67,6 +67,26 @@ MULTISIDE_CASES = [
      {"p": 2, "lambda": 1e-2}),
 ]
 
+# Wide rows on a larger table (the vectorised multi-chunk kernel paths, K >= 256, E = 5000), executed by the reference's own
+# code.  Tables come from np.random.RandomState(seed) (a frozen stream) and the gradients are stored for the touched rows
+# only, so the fixtures stay small: name, model, loss, k, eta, E, R, n, emb_params
+WIDE_CASES = [
+    ("transe_l1_pairwise_k256", "TransE", "pairwise", 256, 6, 5000, 9, 96, {}),
+    ("distmult_nll_k256", "DistMult", "nll", 256, 8, 5000, 9, 96, {}),
+    ("complex_nll_k200", "ComplEx", "nll", 200, 6, 5000, 9, 96, {}),
+    ("hole_multiclass_k256", "HolE", "multiclass_nll", 256, 5, 5000, 9, 64, {}),
+    ("transe_l2_selfadv_k300", "TransE", "self_adversarial", 300, 4, 5000, 9, 64, {"norm": 2}),
+]
+
+
+def wide_tables(seed, E, R, K):
+    """The tables of a wide case, regenerated by the tests from the seed (RandomState streams are frozen)."""
+    rs = np.random.RandomState(seed)
+    ent = (rs.standard_normal((E, K)) * 0.3).astype(np.float32)
+    rel = (rs.standard_normal((R, K)) * 0.3).astype(np.float32)
+    return ent, rel
+
+
 RANK_CASES = [
     # name, model, k, E, R, F, T, emb_params, scale
     ("rank_transe_l1", "TransE", 10, 120, 4, 900, 60, {}, 0.5),
@@ -138,6 +158,27 @@ def main():
             keep_subj=keep2, repl=repl2, loss=np.float32(ref["loss"]), scores_pos=np.tile(ref["scores_pos"], S), scores_neg=sneg,
             neg=neg2.astype(np.int32), grad_ent=ref["grad_ent"], grad_rel=ref["grad_rel"])
         print("train multiside", name, "loss", ref["loss"])
+    for ci, (name, model, loss, k, eta, E, R, n, ep) in enumerate(WIDE_CASES):
+        if not wanted("wide_" + name):
+            continue
+        seed = 5000 + ci
+        K = ko.internal_k(model, k)
+        ent, rel = wide_tables(seed, E, R, K)
+        rng = np.random.Generator(np.random.PCG64(seed))
+        pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+        pos[: n // 4, 0] = pos[0, 0]  # a hub entity
+        keep = ko.side_mask("s,o", n * eta, rng)
+        repl = rng.integers(0, E, n * eta).astype(np.int32)
+        ref = ref_shim.ref_train_forward_backward(model, k, eta, loss, ent, rel, pos, keep, repl, {}, ep, "s,o", None, None)
+        rows = np.flatnonzero(np.abs(ref["grad_ent"]).max(1) > 0).astype(np.int32)
+        touched = np.unique(np.concatenate([pos[:, 0], pos[:, 2], repl]))
+        assert np.all(np.isin(rows, touched))
+        np.savez_compressed(
+            os.path.join(OUT, "wide_%s.npz" % name), model=model, loss_name=loss, k=k, eta=eta, E=E, R=R, table_seed=seed,
+            margin=3.0 if loss == "self_adversarial" else 1.0, alpha=0.5, norm=int(ep.get("norm", 1)), pos=pos, keep_subj=keep, repl=repl,
+            loss=np.float32(ref["loss"]), scores_pos=ref["scores_pos"], scores_neg=ref["scores_neg"],
+            grad_rows=touched.astype(np.int32), grad_ent_rows=ref["grad_ent"][touched], grad_rel=ref["grad_rel"])
+        print("wide", name, "loss", ref["loss"], "touched rows", touched.size)
     if wanted("split_cases"):
         # train_test_split_no_unseen (evaluation/protocol.py:24-407), both algorithms, executed by the reference
         rng = np.random.Generator(np.random.PCG64(4000))

@@ -172,6 +172,12 @@ def load():
     for sub in ("nn", "math", "random", "keras"):
         sys.modules["tensorflow." + sub] = getattr(tf, sub)
     sys.modules["tensorflow.keras.backend"] = tf.keras.backend
+    # importlib.util.find_spec("tensorflow") (torch._dynamo probes optional packages that way) raises on a module
+    # without a spec: give the shim modules one
+    import importlib.machinery
+    for name, mod in list(sys.modules.items()):
+        if (name == "tensorflow" or name.startswith("tensorflow.")) and isinstance(mod, types.ModuleType) and getattr(mod, "__spec__", None) is None:
+            mod.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)
     for sub in ("python", "python.ops", "python.framework", "keras.layers", "keras.models"):
         sys.modules.setdefault("tensorflow." + sub, mock.MagicMock())
     import pydantic.v1 as pv1  # the reference's dataset classes use the pydantic-1 API

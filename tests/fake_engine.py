@@ -195,9 +195,9 @@ class FakeEngine:
         nrm = emb.norm(dim=1, keepdim=True).clamp(min=1.0)
         emb.div_(nrm)
 
-    def score(self, model, k, ent, rel, triples):
+    def score(self, model, k, ent, rel, triples, non_linearity=0):
         name, norm = _MODEL[model]
-        return torch.from_numpy(ko.score(name, k, ent.numpy(), rel.numpy(), triples.numpy(), norm))
+        return torch.from_numpy(ko.non_linearity(_NL[non_linearity], ko.score(name, k, ent.numpy(), rel.numpy(), triples.numpy(), norm))[0])
 
     # ---- evaluation: the filter is the raw triple array, ranks come from the oracle
     def filter_build(self, triples, E, R):

@@ -10,12 +10,6 @@ from oracle import kge_oracle as ko
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def engine():
-    from emgraph_b200.engine import get_engine
-    return get_engine(0)
-
-
 def _labels(tri):
     """int ids -> string labels whose sorted order is the id order (e0007 ...)."""
     X = np.empty(tri.shape, dtype=object)
@@ -184,7 +178,7 @@ def test_save_restore_predict_and_resume(engine, tmp_path):
 @pytest.mark.parametrize("nl", ["tanh", "sigmoid", "softplus"])
 def test_non_linearity_train_and_rank_match_oracle(engine, nl):
     """embedding_model_params['non_linearity'] (models/EmbeddingModel.py:679-689, :801-812, :1868-1881): the loss and
-    the rank comparison see nl(score); predict returns the raw score."""
+    the rank comparison see nl(score), and predict returns nl(score) as the reference does (:2135-2147)."""
     from emgraph_b200 import _lib
     from emgraph_b200.engine import model_id
     from emgraph_b200.evaluation import evaluate_performance
@@ -225,6 +219,11 @@ def test_non_linearity_train_and_rank_match_oracle(engine, nl):
         got = evaluate_performance(_labels(test), m, filter_triples=X, corrupt_side="s,o")
         exp = ko.ranks(model, k, ent, rel, test, tri, "s,o", "worst", nl=nl)
         assert got.shape == exp.shape and (got != exp).sum() <= max(2, exp.size // 20), (nl, tc, (got != exp).sum())
-    np.testing.assert_allclose(m.predict(X[:20]), ko.score(model, k, ent, rel, tri[:20]), rtol=1e-5, atol=1e-6)
+    exp_pred = ko.non_linearity(nl, ko.score(model, k, ent, rel, tri[:20]))[0]
+    np.testing.assert_allclose(m.predict(X[:20]), exp_pred, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m.predict(tri[:20], from_idx=True), exp_pred, rtol=1e-5, atol=1e-6)
+    for bad in ([[E, 0, 1]], [[0, R, 1]], [[0, 0, -1]]):  # the reference's gather raises on ids outside the tables
+        with pytest.raises(ValueError):
+            m.predict(np.asarray(bad), from_idx=True)
     with pytest.raises(ValueError):
         ComplEx(k=4, epochs=1, batches_count=1, embedding_model_params={"non_linearity": "relu"}).fit(X)
