@@ -419,8 +419,8 @@ class ShardedKGE:
             self.state = dict(ent_m=torch.full_like(self.ent, 0.1), rel_m=torch.full_like(self.rel, 0.1))
         elif opt == 2:
             self.state = dict(ent_m=torch.zeros_like(self.ent), rel_m=torch.zeros_like(self.rel))
-        self.bounds = chunk_bounds(self.n, chunks)
-        self.sums = [torch.zeros((1 + self.eta) * (hi - lo), dtype=torch.float32, device=dev) for lo, hi in self.bounds]
+        self.chunks = int(chunks)
+        self.sums_flat = torch.zeros((1 + self.eta) * self.n, dtype=torch.float32, device=dev)  # chunk c at (1+eta)*lo_c
         self.pos_all = torch.empty((self.n, 3), dtype=torch.int32, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step = 0
@@ -461,7 +461,10 @@ class ShardedKGE:
         the global batch.  Returns the device scalar holding the batch loss (identical on every rank)."""
         eng = self.eng
         pos_all = pos_local if pos_is_global else self.gather_batch(pos_local)
-        assert pos_all.shape[0] == self.n
+        n = pos_all.shape[0]
+        assert 0 < n <= self.n, "global batch of %d positives; this model was sized for %d" % (n, self.n)
+        bounds = chunk_bounds(n, self.chunks)
+        sums = [self.sums_flat[(1 + self.eta) * lo:(1 + self.eta) * hi] for lo, hi in bounds]
         self.step += 1
         # the side-stream prologue may only read batches that were resident before the previous step was submitted
         pipe = self.pipeline and pos_is_global and repl is None and keep_subj is None
@@ -476,15 +479,15 @@ class ShardedKGE:
 
         mark("start")
         works = []
-        for c, (lo, hi) in enumerate(self.bounds):
-            eng.train_partial(a, self.sums[c], lo, hi)
+        for c, (lo, hi) in enumerate(bounds):
+            eng.train_partial(a, sums[c], lo, hi)
             mark("partial%d" % c)
-            works.append(dist.all_reduce(self.sums[c], group=self.group, async_op=True) if self.world > 1 else None)
-        for c, (lo, hi) in enumerate(self.bounds):
+            works.append(dist.all_reduce(sums[c], group=self.group, async_op=True) if self.world > 1 else None)
+        for c, (lo, hi) in enumerate(bounds):
             if works[c] is not None:
                 works[c].wait()
             mark("allreduce%d" % c)
-            eng.train_backward(a, self.sums[c], lo, hi)
+            eng.train_backward(a, sums[c], lo, hi)
             mark("backward%d" % c)
         eng.train_reduce(a)
         mark("reduce_apply")
@@ -549,6 +552,10 @@ class ShardedKGE:
         full = self._gather_cols(self.rel)
         return full if device else full.cpu().numpy()
 
+    def gather_state(self, name):
+        """Full-model optimizer-state table `name` (ent_m / ent_v / rel_m / rel_v) on every rank, as a CPU tensor."""
+        return self._gather_cols(self.state[name]).cpu()
+
     def row_shard(self):
         """[rps, K] full-width rows [row_begin,row_end) of the CURRENT parameters (zero rows past the end): the
         column slices are transposed into row-range shards by one all-to-all; cached until the next step."""
@@ -585,3 +592,78 @@ class ShardedKGE:
     def rank(self, test_dev, *, side=0, strategy=0, filtered=False, use_tensor_cores=False, non_linearity=0):
         counts = self.rank_counts(test_dev, side=side, filtered=filtered, use_tensor_cores=use_tensor_cores, non_linearity=non_linearity)
         return self.eng.rank_finalize(counts, side=side, strategy=strategy, filtered=filtered)
+
+
+# ------------------------------------------------------------------------------------------------
+# fit(engine_params={"n_gpus": N}) from a plain process: one worker per GPU
+# ------------------------------------------------------------------------------------------------
+def _free_port():
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _spawn_worker(rank, world, port, cls_name, hyper, resume, Xi_path, E, R, out_path, backend):
+    import os
+    import pickle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    try:
+        from . import models
+        hyper = dict(hyper)
+        ep = dict(hyper.get("engine_params") or {})
+        if backend == "nccl":
+            ep["device"] = rank
+        hyper["engine_params"] = ep
+        m = getattr(models, cls_name)(**hyper)
+        if resume is not None:
+            m.trained_model_params = [resume["ent"], resume["rel"]]
+            m._opt_state = {k: torch.from_numpy(v) for k, v in resume["state"].items()}
+            m._opt_step = int(resume["step"])
+            m._resume = True
+            m.is_fitted = True
+        m._fit_sharded_spmd(np.load(Xi_path), E, R)
+        if rank == 0:
+            with open(out_path, "wb") as fw:
+                pickle.dump(dict(ent=m.trained_model_params[0], rel=m.trained_model_params[1], step=m._opt_step, loss_history=m.loss_history,
+                                 state={k: v.numpy() for k, v in m._opt_state.items()}), fw, protocol=pickle.HIGHEST_PROTOCOL)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def spawn_fit(model, Xi, E, R, n_gpus, backend="nccl"):
+    """Run model._fit_sharded_spmd on `n_gpus` freshly spawned workers; returns dict(ent, rel, state, step, loss_history)."""
+    import os
+    import pickle
+    import tempfile
+    import torch.multiprocessing as mp
+    if backend == "nccl" and torch.cuda.device_count() < n_gpus:
+        raise _lib.KgeError("engine_params['n_gpus']=%d but only %d CUDA devices are visible" % (n_gpus, torch.cuda.device_count()))
+    resume = None
+    if getattr(model, "_resume", False):
+        st = getattr(model, "_opt_state", None) or {}
+        resume = dict(ent=np.asarray(model.trained_model_params[0]), rel=np.asarray(model.trained_model_params[1]), step=int(getattr(model, "_opt_step", 0)),
+                      state={k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in st.items()})
+    with tempfile.TemporaryDirectory(prefix="kge_fit_") as d:
+        xi_path, out_path = os.path.join(d, "xi.npy"), os.path.join(d, "out.pkl")
+        np.save(xi_path, np.ascontiguousarray(Xi, dtype=np.int32))
+        ctx = mp.get_context("spawn")
+        port = _free_port()
+        procs = [ctx.Process(target=_spawn_worker, args=(r, n_gpus, port, model.__class__.__name__, dict(model.all_params, engine_params=dict(model.engine_params)), resume, xi_path, E, R,
+                                                         out_path, backend)) for r in range(n_gpus)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join()
+        bad = [p.exitcode for p in procs if p.exitcode != 0]
+        if bad or not os.path.exists(out_path):
+            raise _lib.KgeError("multi-GPU fit failed (worker exit codes %r)" % ([p.exitcode for p in procs],))
+        with open(out_path, "rb") as fr:
+            return pickle.load(fr)

@@ -751,7 +751,117 @@ class EmbeddingModel:
         f["eng"].train_host_wait(prev[0])
         return float(f["loss_ring"][prev[1]])
 
+    # ---- multi-GPU fit: engine_params={"n_gpus": N}.  The tables and the optimizer state are split by column range over
+    # N GPUs of one node (emgraph_b200/distributed.py:ShardedKGE) and every step runs the SAME global batch, corruption
+    # stream and update as the single-GPU fit, so the trained parameters agree to rounding.  Two ways in:
+    #   * the script runs under torchrun (torch.distributed initialised, world size == N): every rank calls fit() with the
+    #     same arguments (SPMD) and ends up with the same model object
+    #   * a plain `python script.py`: fit() spawns N worker processes (one per GPU, NCCL over 127.0.0.1), hands them the
+    #     model's hyper-parameters and the id triples, and takes back the trained tables and the optimizer state
+    # Replaces the reference's host-paged "large graph" training (models/EmbeddingModel.py:645-666, :1251-1281), which is
+    # single-process and SGD-only.
+    def _sharded_unsupported(self, early_stopping):
+        f = []
+        if early_stopping:
+            f.append("early_stopping")
+        if len(self._train_sides()) > 1:
+            f.append("a list-valued corrupt_side")
+        if self.embedding_model_params.get("negative_corruption_entities", DEFAULT_CORRUPTION_ENTITIES) != "all":
+            f.append("negative_corruption_entities")
+        if self._reg.get("reg_p", 0):
+            f.append("the LP regulariser")
+        if self.embedding_model_params.get("normalize_ent_emb", False):
+            f.append("normalize_ent_emb")
+        if self.engine_params.get("host_batches", False) or self.engine_params.get("reset_state", False):
+            f.append("host_batches / reset_state")
+        if f:
+            raise NotImplementedError("engine_params['n_gpus'] > 1 does not support: " + ", ".join(f))
+
+    def _fit_sharded_spmd(self, Xi, E, R):
+        """Every rank of an initialised process group runs this with the same arguments."""
+        import torch.distributed as dist
+        from .distributed import ShardedKGE, slice_columns
+        self._reseed_if_refit()
+        K = self.internal_k
+        resume = bool(getattr(self, "_resume", False))
+        if resume:
+            ent0 = np.ascontiguousarray(self.trained_model_params[0], dtype=np.float32)
+            rel0 = np.ascontiguousarray(self.trained_model_params[1], dtype=np.float32)
+            if ent0.shape != (E, K) or rel0.shape != (R, K):
+                raise ValueError("resume: parameter shapes {} / {} do not fit this model".format(ent0.shape, rel0.shape))
+        else:
+            ent0, rel0 = self._init_table(E, K, "entity"), self._init_table(R, K, "relation")  # same seed on every rank
+        N = Xi.shape[0]
+        batch_size = int(np.ceil(N / self.batches_count))
+        world = dist.get_world_size()
+        norm = int(self.embedding_model_params.get("norm", DEFAULT_NORM_TRANSE)) if self.name == "TransE" else 1
+        sk = ShardedKGE(self.name, self.k, self.eta, self.loss, self.optimizer, E, R, -(-batch_size // world), norm=norm,
+                        margin=float(self.loss_params.get("margin", DEFAULT_MARGIN_ADVERSARIAL if self.loss == "self_adversarial" else DEFAULT_MARGIN)),
+                        alpha=float(self.loss_params.get("alpha", DEFAULT_ALPHA_ADVERSARIAL)), seed=int(self.seed), init_ent=ent0, init_rel=rel0,
+                        device=self.engine_params.get("device"), chunks=int(self.engine_params.get("chunks", 2)),
+                        non_linearity=self.embedding_model_params.get("non_linearity", "linear"), side=self._train_sides()[0],
+                        optimizer_params=self.optimizer_params, pipeline=bool(self.engine_params.get("pipeline", True)))
+        del ent0, rel0
+        if resume:
+            saved = getattr(self, "_opt_state", None) or {}
+            if set(saved) == set(sk.state):
+                for nm, t in sk.state.items():  # the full-model state (merged at restore) -> this rank's columns
+                    full = saved[nm].detach().cpu().numpy() if isinstance(saved[nm], torch.Tensor) else np.asarray(saved[nm])
+                    t.copy_(torch.from_numpy(slice_columns(full, self.name, self.k, sk.world, sk.rank_id)).to(t.device))
+            sk.step = int(getattr(self, "_opt_step", 0))
+        dev = sk.eng.tdev
+        Xd = to_dev_i32(Xi, dev)
+        torch.cuda.synchronize(dev) if dev.type == "cuda" else None
+        loss_steps = torch.zeros(self.batches_count, dtype=torch.float32, device=dev)
+        sched = SGDSchedule(self.optimizer_params, self.batches_count) if self.optimizer == "sgd" else None
+        denom = batch_size * (self.eta if self.loss in TILED_POSITIVE_LOSSES else 1) * self.batches_count
+        self.loss_history = []
+        for epoch in range(1, self.epochs + 1):
+            loss_steps.zero_()
+            for b in range(self.batches_count):
+                lo, hi = b * batch_size, min(N, (b + 1) * batch_size)
+                if hi <= lo:
+                    continue
+                if sched is not None:
+                    sk.kw["lr"] = float(sched(b + 1, epoch))
+                loss_steps[b:b + 1].copy_(sk.train_step(Xd[lo:hi], pos_is_global=True))
+            el = float(loss_steps.double().sum().item())
+            if not np.isfinite(el):  # models/EmbeddingModel.py:1422-1427
+                raise ValueError("Loss is {}. Please change the hyperparameters.".format(el))
+            self.loss_history.append(el / denom)
+            if self.verbose and sk.rank_id == 0:
+                print("Average Loss: {:10f} -- epoch {}/{}".format(self.loss_history[-1], epoch, self.epochs))
+        self._sharded = sk
+        self._best_params = None
+        self._dev = None
+        self._opt_step = sk.step
+        # the whole model on every rank (host): predict / get_embeddings / save_model work as after a single-GPU fit;
+        # the optimizer state stays sharded (save_model writes one file per rank)
+        self.trained_model_params = [sk.gather_entities(), sk.gather_relations()]
+        self._opt_state = {nm: sk.gather_state(nm) for nm in sk.state}
+        self.is_fitted = True
+
+    def _fit_sharded(self, Xi, E, R, n_gpus, early_stopping):
+        import torch.distributed as dist
+        self._sharded_unsupported(early_stopping)
+        if dist.is_available() and dist.is_initialized():
+            if dist.get_world_size() != n_gpus:
+                raise ValueError("engine_params['n_gpus']={} but the process group has {} ranks".format(n_gpus, dist.get_world_size()))
+            return self._fit_sharded_spmd(Xi, E, R)
+        from .distributed import spawn_fit
+        out = spawn_fit(self, Xi, E, R, n_gpus)
+        self.trained_model_params = [out["ent"], out["rel"]]
+        self._opt_state = {nm: torch.from_numpy(v) for nm, v in out["state"].items()}
+        self._opt_step = int(out["step"])
+        self.loss_history = list(out["loss_history"])
+        self._dev = None
+        self._best_params = None
+        self.is_fitted = True
+
     def _fit_idx(self, Xi, E, R, early_stopping=False):
+        n_gpus = int(self.engine_params.get("n_gpus", 1))
+        if n_gpus > 1:
+            return self._fit_sharded(Xi, E, R, n_gpus, early_stopping)
         f = self._fit_prepare(E, R)
         self._best_params = None
         self.early_stopping_history = []

@@ -26,14 +26,49 @@ def save_model(model, model_name_path=None, protocol=pickle.HIGHEST_PROTOCOL, sa
         "is_calibrated": model.is_calibrated,
     }
     model.get_embedding_model_params(obj)
-    if save_optimizer_state and getattr(model, "_opt_state", None):
-        obj["b200_optimizer_state"] = {k: v.detach().cpu().numpy() for k, v in model._opt_state.items()}
-        obj["b200_optimizer_step"] = int(getattr(model, "_opt_step", 0))
     if model_name_path is None:
         model_name_path = DEFAULT_MODEL_NAMES.format(strftime("%Y_%m_%d-%H_%M_%S", gmtime()))
-    with open(model_name_path, "wb") as fw:
-        pickle.dump(obj, fw, protocol=protocol)
+    sk = getattr(model, "_sharded", None)
+    sharded = save_optimizer_state and sk is not None and _dist_ranks() > 1
+    if sharded:
+        # a model trained under torchrun: every rank writes the optimizer state of ITS column slice next to the main file
+        # (<path>.opt.<rank>-of-<world>.npz); rank 0 writes the reference-format pickle with the whole parameter tables
+        np.savez(shard_path(model_name_path, sk.rank_id, sk.world), step=int(sk.step), world=sk.world, rank=sk.rank_id, k=sk.k,
+                 model=sk.model, **{nm: t.detach().cpu().numpy() for nm, t in sk.state.items()})
+        obj["b200_optimizer_shards"] = int(sk.world)
+        obj["b200_optimizer_step"] = int(sk.step)
+    elif save_optimizer_state and getattr(model, "_opt_state", None):
+        obj["b200_optimizer_state"] = {k: v.detach().cpu().numpy() for k, v in model._opt_state.items()}
+        obj["b200_optimizer_step"] = int(getattr(model, "_opt_step", 0))
+    if not sharded or sk.rank_id == 0:
+        with open(model_name_path, "wb") as fw:
+            pickle.dump(obj, fw, protocol=protocol)
+    if sharded:
+        import torch.distributed as dist
+        dist.barrier()
     return model_name_path
+
+
+def _dist_ranks():
+    try:
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    except Exception:
+        return 1
+
+
+def shard_path(model_name_path, rank, world):
+    return "{}.opt.{}-of-{}.npz".format(model_name_path, rank, world)
+
+
+def load_optimizer_shards(model_name_path, world):
+    """Merge the per-rank optimizer-state files of a column-sharded model into full-model tables (any later fit --
+    one GPU or a different number of GPUs -- slices them again)."""
+    from .distributed import merge_columns
+    parts = [np.load(shard_path(model_name_path, r, world)) for r in range(world)]
+    model, k = str(parts[0]["model"]), int(parts[0]["k"])
+    names = [nm for nm in parts[0].files if nm in ("ent_m", "ent_v", "rel_m", "rel_v")]
+    return {nm: merge_columns([p[nm] for p in parts], model, k) for nm in names}, int(parts[0]["step"])
 
 
 def restore_model(model_name_path=None):
@@ -54,6 +89,11 @@ def restore_model(model_name_path=None):
         model.rel_to_idx = restored_obj["rel_to_idx"]
         model.is_calibrated = restored_obj.get("is_calibrated", False)
         model.restore_model_params(restored_obj)
+        if restored_obj.get("b200_optimizer_shards"):
+            import torch
+            st, step = load_optimizer_shards(model_name_path, int(restored_obj["b200_optimizer_shards"]))
+            model._opt_state = {k_: torch.from_numpy(np.ascontiguousarray(v)) for k_, v in st.items()}
+            model._opt_step = step
     except pickle.UnpicklingError as e:
         raise Exception("Error unpickling model {} : {}.".format(model_name_path, e))
     except (IOError, FileNotFoundError):

@@ -276,3 +276,65 @@ def test_gloo_world2_sharded_driver_matches_single_process_oracle(model, loss, k
         b, e = res[r]["range"]
         np.testing.assert_array_equal(res[r]["rows"][:e - b], res[0]["ent"][b:e])  # the transposed shard holds whole rows
         np.testing.assert_array_equal(res[r]["ranks"], exp)
+
+
+# ------------------------------------------------------------------------------------------------
+# fit(engine_params={"n_gpus": 2}) under an initialised process group + the sharded optimizer-state checkpoint
+# ------------------------------------------------------------------------------------------------
+def _fit_worker(rank, world, port, tmp, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_engine import FakeEngine
+        from emgraph_b200 import models, utils
+        fake = FakeEngine()
+        D.get_engine = lambda device=None: fake
+        models.get_engine = lambda device=None: fake
+        from toy_graph import TOY_QUERY, TOY_X
+        kw = dict(k=10, eta=2, batches_count=2, seed=555, optimizer="adam", optimizer_params={"lr": 0.05}, loss="nll",
+                  engine_params={"n_gpus": world})
+        m = models.ComplEx(epochs=4, **kw)
+        m.fit(TOY_X)
+        y4 = m.predict(TOY_QUERY)
+        # 2 + 2 epochs through the sharded checkpoint == 4 epochs
+        a = models.ComplEx(epochs=2, **kw)
+        a.fit(TOY_X)
+        path = os.path.join(tmp, "m.pkl")
+        utils.save_model(a, path, save_optimizer_state=True)
+        shard_files = sorted(f for f in os.listdir(tmp) if ".opt." in f)
+        b = utils.restore_model(path)
+        np.testing.assert_array_equal(b._opt_state["ent_v"].numpy(), a._opt_state["ent_v"].numpy())  # merged shards == gathered state
+        b.engine_params = {"n_gpus": world, "resume": True}
+        b.fit(TOY_X)
+        q.put((rank, dict(ent=m.trained_model_params[0], rel=m.trained_model_params[1], y4=y4, y22=b.predict(TOY_QUERY),
+                          ent22=b.trained_model_params[0], losses=m.loss_history, shard_files=shard_files, step=b._opt_step)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_gloo_world2_fit_n_gpus_equals_the_fit_emulation_and_resumes_from_sharded_state(tmp_path):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + ((os.getpid() * 13) % 2000)
+    procs = [ctx.Process(target=_fit_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=250) for _ in procs)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    from toy_graph import TOY_QUERY, TOY_X
+    r2i, e2i = ko.create_mappings(TOY_X)
+    Xi = ko.to_idx(TOY_X, e2i, r2i)
+    ent, rel, losses = ko.fit_emulation("ComplEx", 10, 2, 4, 2, 555, "nll", "adam", 0.05, Xi, len(e2i), len(r2i))
+    y = ko.score("ComplEx", 10, ent, rel, ko.to_idx(TOY_QUERY, e2i, r2i))
+    for r in range(world):
+        np.testing.assert_allclose(res[r]["ent"], ent, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(res[r]["y4"], y, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(res[r]["y22"], res[r]["y4"], rtol=1e-5, atol=1e-6)  # resumed == uninterrupted
+        np.testing.assert_allclose(res[r]["ent22"], res[r]["ent"], rtol=1e-5, atol=1e-6)
+        assert res[r]["step"] == 8 and res[r]["shard_files"] == ["m.pkl.opt.0-of-2.npz", "m.pkl.opt.1-of-2.npz"]
+    np.testing.assert_array_equal(res[0]["ent"], res[1]["ent"])

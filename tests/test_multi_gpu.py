@@ -141,3 +141,36 @@ def test_sharded_step_and_ranking_match_oracle(world, model, loss, k, exchange, 
     for key in ("ranks_tc0", "ranks_tc1"):
         if key in res:
             assert res[key].shape == exp.shape and (res[key] != exp).sum() <= 2, key
+
+
+@pytest.mark.parametrize("model,opt", [("ComplEx", "adam"), ("TransE", "adagrad")])
+def test_fit_n_gpus_equals_single_gpu_fit_and_resumes(model, opt, tmp_path):
+    """fit(engine_params={'n_gpus': 2}) from a plain process (spawns one worker per GPU) trains the model the single-GPU
+    fit trains -- same batches, same corruption stream, same updates -- and 2 + 2 epochs through save / restore /
+    resume equal 4 epochs (reference API: models/EmbeddingModel.py:1113, utils/model_utils.py:63-87, :139-154)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from emgraph_b200 import models, utils
+    from toy_graph import TOY_QUERY
+    rng = np.random.default_rng(4)
+    tri = ko.synthetic_triples(60, 4, 500, seed=2)
+    X = np.stack([np.char.add("e", tri[:, 0].astype(str)), np.char.add("r", tri[:, 1].astype(str)), np.char.add("e", tri[:, 2].astype(str))], 1)
+    kw = dict(k=12, eta=4, batches_count=3, seed=9, optimizer=opt, optimizer_params={"lr": 0.02}, loss="nll")
+    cls = getattr(models, model)
+    m1 = cls(epochs=4, **kw).fit(X)
+    m2 = cls(epochs=4, engine_params={"n_gpus": 2}, **kw).fit(X)
+    np.testing.assert_allclose(m2.trained_model_params[0], m1.trained_model_params[0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(m2.predict(X[:40]), m1.predict(X[:40]), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(m2.loss_history, m1.loss_history, rtol=1e-5)
+    a = cls(epochs=2, engine_params={"n_gpus": 2}, **kw).fit(X)
+    path = str(tmp_path / "m.pkl")
+    utils.save_model(a, path, save_optimizer_state=True)
+    b = utils.restore_model(path)
+    b.engine_params = {"n_gpus": 2, "resume": True}
+    b.fit(X)
+    np.testing.assert_allclose(b.trained_model_params[0], m2.trained_model_params[0], rtol=1e-5, atol=1e-6)
+    # a model trained on 2 GPUs evaluates like the single-GPU one
+    from emgraph_b200.evaluation import evaluate_performance
+    r1 = evaluate_performance(X[:30], m1, filter_triples=X, corrupt_side="s,o")
+    r2 = evaluate_performance(X[:30], m2, filter_triples=X, corrupt_side="s,o")
+    assert (r1 != r2).sum() <= 2
