@@ -69,6 +69,7 @@ extern "C" int kge_ctx_destroy(kge_ctx* c) {
     for (cudaEvent_t e : {c->ev_fork, c->ev_sorted, c->ev_fwd, c->ev_loss})
         if (e) cudaEventDestroy(e);
     if (c->side) cudaStreamDestroy(c->side);
+    if (c->lstream) cudaStreamDestroy(c->lstream);
     delete c;
     return 0;
 }

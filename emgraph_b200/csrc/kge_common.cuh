@@ -96,6 +96,7 @@ struct kge_ctx {
     // owner-side slot selection (kge_train_select): count travels to the host behind an event
     // side stream of the single-GPU step (sort + loss reduction beside the forward/backward kernel)
     cudaStream_t  side = nullptr;
+    cudaStream_t  lstream = nullptr;  // loss reduction of a PIPELINED step: keeps the side stream free for the next prologue
     cudaEvent_t   ev_fork = nullptr, ev_sorted = nullptr, ev_fwd = nullptr, ev_loss = nullptr;
     // optional per-phase timing of kge_train_step (bench instrumentation): emit | fwd_bwd | reduce | spans
     bool          timing = false, tpending = false;

@@ -96,6 +96,18 @@ __device__ __forceinline__ void row_select(Row<4, NCH, CPLX>& d, bool first, con
 }
 
 #define KGE_DIM_THREADS 256
+// The candidate rows of a positive are fetched in rounds of U; a round costs two dependent memory round trips (ids,
+// then rows), and ncu showed both phase kernels waiting on exactly that (long-scoreboard stalls, DRAM 40 % busy).  The
+// lanes therefore load the ids of the round KGE_DIM_PF rounds ahead at the top of a round and, at its end, put those
+// rows in flight with L2 prefetches (no registers held, no dependency): when their round comes the row loads hit L2.
+// The footprint -- resident groups x U x KGE_DIM_PF rows -- stays a fraction of L2.
+#define KGE_DIM_PF 2
+__device__ __forceinline__ void dim_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// prefetch the K floats of a row slice: one 128-byte line per 32 floats, lines dealt over the lanes of the group
+template <int GS>
+__device__ __forceinline__ void dim_prefetch_row(const float* row, int K, int lg_rot) {
+    for (int off = lg_rot * 32; off < K; off += GS * 32) dim_prefetch_l2(row + off);
+}
 
 // ---------------------------------------------------------------------------------------------- phase 1
 template <int MODEL, int GS, int NCH, int U>
@@ -130,11 +142,12 @@ __global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_partial_kernel(DimPar
     float* out = P.sums + nc + il;
     for (int j0 = 0; j0 < eta; j0 += U) {
         // one id / side load per group serves U negatives
-        int my_idx = 0, my_keep = 0;
+        int my_idx = 0, my_keep = 0, pf_idx = -1;
         if (lg < U) {
             const int64_t q = (int64_t)min(j0 + lg, eta - 1) * n + i;
             my_idx = P.repl[q];
             my_keep = P.keep[q];
+            if (j0 + KGE_DIM_PF * U + lg < eta) pf_idx = P.repl[(int64_t)(j0 + KGE_DIM_PF * U + lg) * n + i];
         }
         R r[U];
         bool kp[U];
@@ -158,12 +171,21 @@ __global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_partial_kernel(DimPar
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (valid && j0 + u < eta && lg == u) out[(int64_t)(j0 + u) * nc] = pv[u];
+        if (pf_idx >= 0) dim_prefetch_row<1>(P.ent + (size_t)pf_idx * K, K, 0);
     }
 }
 
 // ---------------------------------------------------------------------------------------------- phase 2
+// resident CTAs the compiler is asked to allow (register cap): the row registers grow with NCH and the complex halves
+template <int MODEL, int NCH>
+struct DimOcc {
+    static constexpr int regs = NCH * 4 * (MODEL == 3 ? 2 : 1);
+    static constexpr int bwd = regs <= 4 ? 4 : (regs <= 8 ? 3 : (regs <= 16 ? 2 : 1));
+    static constexpr int fwd = regs <= 8 ? 5 : (regs <= 16 ? 3 : 2);
+};
+
 template <int MODEL, int GS, int NCH, int U>
-__global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_backward_kernel(DimParams P) {
+__global__ void __launch_bounds__(KGE_DIM_THREADS, (DimOcc<MODEL, NCH>::bwd)) kge_dim_backward_kernel(DimParams P) {
     using A = Algebra<MODEL, 4, NCH>;
     using R = typename A::R;
     constexpr bool TRANSE = A::TRANSE;
@@ -230,7 +252,7 @@ __global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_backward_kernel(DimPa
     uint8_t* keep_out = gbuf_keep(P.gbuf, eta, n, K);
     for (int j0 = 0; j0 < eta; j0 += U) {
         // lane lg < U owns negative j0+lg of this round: id, side, total -> dL/dscore, coefficient, loss term
-        int my_idx = 0, my_keep = 0;
+        int my_idx = 0, my_keep = 0, pf_idx = -1;
         float my_w = 0.f, my_sn = 0.f;
         if (lg < U) {
             const int j = min(j0 + lg, eta - 1);
@@ -238,6 +260,7 @@ __global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_backward_kernel(DimPa
             const int64_t q = (int64_t)j * n + i;
             my_idx = P.repl[q];
             my_keep = P.keep[q];
+            if (j0 + KGE_DIM_PF * U + lg < eta) pf_idx = P.repl[(int64_t)(j0 + KGE_DIM_PF * U + lg) * n + i];
             const float sn = A::finish(tot[(int64_t)j * nc], scale);
             const float st = apply_nl(nl, sn);
             const float dn = apply_nl_grad(nl, sn);
@@ -310,6 +333,7 @@ __global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_backward_kernel(DimPa
                 }
             }
         }
+        if (pf_idx >= 0) dim_prefetch_row<1>(P.ent + (size_t)pf_idx * K, K, 0);
     }
     loss_acc = group_sum<GS>(loss_acc);
     wsum = group_sum<GS>(wsum);

@@ -1,15 +1,19 @@
-// tcgen05 3xTF32 ranking sweep for sm_100a (DistMult / ComplEx / HolE).
+// tcgen05 split-precision ranking sweep for sm_100a (DistMult / ComplEx / HolE).
 //
 // S[m,e] = sum_k Q[m,k] * Ent[e,k]  with Q the folded queries of the test triples is a
-// dense [2T,K] x [K,E] contraction.  fp32 accuracy is kept with the 3xTF32 split: every operand is
-// pre-split into hi = top 19 bits and lo = x - hi (exact), and each k-step issues
-//     D += Qhi*Ehi ; D += Qhi*Elo ; D += Qlo*Ehi           (fp32 accumulate in TMEM)
+// dense [2T,K] x [K,E] contraction.  fp32 accuracy is kept with a three-term split: every operand x is scaled by a
+// power of two (one per operand, from its largest magnitude, so that the low halves stay in the normal fp16 range)
+// and written as hi = fp16(x), lo = fp16(x - hi) -- 11 + 11 significant bits, what 3xTF32 carries -- and each
+// k-step issues
+//     D += Qlo*Ehi ; D += Qhi*Elo ; D += Qhi*Ehi           (kind::f16, fp32 accumulate in TMEM)
+// at twice the tensor-pipe rate of kind::tf32 and half the operand bytes; the epilogue multiplies by the exact
+// inverse of the two scales.  KGE_RANK_TF32=1 selects the round-1 3xTF32 operands (A/B).
 //
 // One persistent CTA per SM, warp-specialised:
 //   warp 0      TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) of the 4 operand tiles of a k-block
-//                              (Qhi,Qlo: 128x32 fp32; Ehi,Elo: 256x32 fp32) into a 2-stage smem ring
-//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::tf32, M=128 N=256 K=8, 12 MMAs per stage,
-//                              accumulator = 128 lanes x 256 columns of TMEM, double buffered (512 cols)
+//                              (Qhi,Qlo: 128 rows x 128 bytes; Ehi,Elo: 256 rows x 128 bytes) into a 2-stage smem ring
+//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1, M=128 N=256, K=16 (f16) / 8 (tf32) per instruction, 12 MMAs per
+//                              stage, accumulator = 128 lanes x 256 columns of TMEM, double buffered (512 cols)
 //   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 -> each thread owns ONE query row and 32 candidate
 //                              scores; x1e5 int truncation (F7), compare with the positive's quantised
 //                              score, filter bitmask from the sorted known-triple list, popcount into the
@@ -20,12 +24,13 @@
 // rank) and :1989-2033 (perform_comparision) for the trilinear models.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 
 #include "kge_common.cuh"
 
 #define TC_BM 128
 #define TC_BN 256
-#define TC_BK 32   // fp32 elements per k-block = 128 bytes = one SWIZZLE_128B row
+#define TC_BK 32   // 4-byte slots per k-block = 128 bytes = one SWIZZLE_128B row (32 tf32 or 64 fp16 elements)
 #define TC_STAGES 2
 #define TC_A_BYTES (TC_BM * TC_BK * 4)   // 16 KB
 #define TC_B_BYTES (TC_BN * TC_BK * 4)   // 32 KB
@@ -47,13 +52,23 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
+template <bool F16>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (F16) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -86,6 +101,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 with A = B = F16 (format code 0), D = F32
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // ------------------------------------------------------------------------------------------------
 // operand preparation: hi/lo split into zero-padded [2*rows_pad, Kp] (rows [0,rows_pad) hi, then lo)
@@ -103,7 +122,41 @@ __global__ void kge_tf32_split_kernel(const float* __restrict__ src, int64_t row
     }
 }
 
+// largest magnitude of an operand, as the bit pattern of a non-negative float (orders like an unsigned int)
+__global__ void kge_absmax_kernel(const float* __restrict__ src, int64_t n, uint32_t* __restrict__ out) {
+    float m = 0.f;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(src[t]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+// power of two that brings the operand's largest magnitude into [2^13, 2^14): the low halves of elements down to
+// 2^-17 of the maximum are then normal fp16 numbers; smaller elements lose low-half bits that are below 2^-38 of the
+// largest product and cannot move a score.  1.0 for an all-zero operand.
+__device__ __forceinline__ float split_scale(uint32_t absmax_bits) {
+    if (absmax_bits == 0u) return 1.f;
+    const int e = (int)((absmax_bits >> 23) & 0xffu) - 127;  // max in [2^e, 2^(e+1))
+    return __uint_as_float((uint32_t)(127 + 13 - e) << 23);
+}
+
+// fp16 hi/lo split into zero-padded [2*rows_pad, Kp] halves (rows [0,rows_pad) hi, then lo)
+__global__ void kge_f16_split_kernel(const float* __restrict__ src, int64_t rows, int K, int Kp, int64_t rows_pad,
+                                     const uint32_t* __restrict__ absmax, __half* __restrict__ dst) {
+    const int64_t total = rows_pad * (int64_t)Kp;
+    const float sc = split_scale(*absmax);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / Kp;
+        const int c = (int)(t - r * Kp);
+        const float x = ((r < rows && c < K) ? src[r * (int64_t)K + c] : 0.f) * sc;  // exact: power of two
+        const __half hi = __float2half_rn(x);
+        dst[t] = hi;
+        dst[total + t] = __float2half_rn(x - __half2float(hi));
+    }
+}
+
 struct TcParams {
+    const uint32_t* absmax;  // [2]: bit patterns of max|Q|, max|Ent| (fp16 split: the epilogue undoes the two scales)
     int k_blocks;
     int64_t M;        // query rows handled (after side selection)
     int64_t Mp, Np;   // padded row counts of the split operands
@@ -121,6 +174,7 @@ struct TcParams {
     int nl;  // KGE_NL_*: non-linearity applied to the scores before the quantisation
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE, TcParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -176,10 +230,11 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* st = smem + (size_t)stage * TC_STAGE_BYTES;
                         mbar_expect_tx(&full[stage], TC_STAGE_BYTES);
-                        tma_load_2d(st, &tmQ, kb * TC_BK, m0, &full[stage]);
-                        tma_load_2d(st + TC_A_BYTES, &tmQ, kb * TC_BK, (int)P.Mp + m0, &full[stage]);
-                        tma_load_2d(st + 2 * TC_A_BYTES, &tmE, kb * TC_BK, n0, &full[stage]);
-                        tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmE, kb * TC_BK, (int)P.Np + n0, &full[stage]);
+                        constexpr int KB_ELEMS = F16 ? 64 : 32;  // elements per 128-byte k-block (TMA coordinates count elements)
+                        tma_load_2d(st, &tmQ, kb * KB_ELEMS, m0, &full[stage]);
+                        tma_load_2d(st + TC_A_BYTES, &tmQ, kb * KB_ELEMS, (int)P.Mp + m0, &full[stage]);
+                        tma_load_2d(st + 2 * TC_A_BYTES, &tmE, kb * KB_ELEMS, n0, &full[stage]);
+                        tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmE, kb * KB_ELEMS, (int)P.Np + n0, &full[stage]);
                         if (++stage == TC_STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -190,7 +245,7 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+            constexpr uint32_t idesc = F16 ? make_idesc_f16(TC_BM, TC_BN) : make_idesc_tf32(TC_BM, TC_BN);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t tile_it = 0;
@@ -212,10 +267,10 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         const uint64_t b_lo = make_sw128_desc(sa + 2 * TC_A_BYTES + TC_B_BYTES);
 #pragma unroll
                         for (int j = 0; j < TC_BK / 8; ++j) {
-                            const uint64_t off = (uint64_t)(j * 32 >> 4);  // 8 tf32 = 32 bytes along K
-                            tc_mma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, (kb | j) != 0);
-                            tc_mma_tf32(d_tmem, a_hi + off, b_lo + off, idesc, 1);
-                            tc_mma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1);
+                            const uint64_t off = (uint64_t)(j * 32 >> 4);  // one MMA = 32 bytes along K: 8 tf32 or 16 fp16
+                            tc_mma<F16>(d_tmem, a_lo + off, b_hi + off, idesc, (kb | j) != 0);
+                            tc_mma<F16>(d_tmem, a_hi + off, b_lo + off, idesc, 1);
+                            tc_mma<F16>(d_tmem, a_hi + off, b_hi + off, idesc, 1);
                         }
                         tc_commit(&empty[stage]);  // smem stage reusable once these MMAs retire
                         if (++stage == TC_STAGES) {
@@ -231,6 +286,9 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
         const int quarter = warp & 3;
         const int row_in_tile = quarter * 32 + lane;
+        // fp16 split: the accumulator holds the score times the two operand scales (powers of two: the product of their
+        // inverses is exact, and so is the multiplication unless the score is subnormal)
+        const float unscale = F16 ? 1.f / (split_scale(P.absmax[0]) * split_scale(P.absmax[1])) : 1.f;
         uint32_t tile_it = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int mt = u / P.nsplit, sp = u - mt * P.nsplit;
@@ -285,14 +343,14 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     if (P.nl == KGE_NL_LINEAR) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const int q = quantise_score(__uint_as_float(v[i]));
+                            const int q = quantise_score(F16 ? __uint_as_float(v[i]) * unscale : __uint_as_float(v[i]));
                             gtm |= (q > pq ? 1u : 0u) << i;
                             eqm |= (q == pq ? 1u : 0u) << i;
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const int q = quantise_score(apply_nl(P.nl, __uint_as_float(v[i])));
+                            const int q = quantise_score(apply_nl(P.nl, F16 ? __uint_as_float(v[i]) * unscale : __uint_as_float(v[i])));
                             gtm |= (q > pq ? 1u : 0u) << i;
                             eqm |= (q == pq ? 1u : 0u) << i;
                         }
@@ -340,15 +398,17 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_tensormap_encoder() {
     return fn;
 }
 
-// 2-D row-major fp32 [rows, Kp] with a (32 x box_rows) box and the 128-byte swizzle
-static int make_tmap(CUtensorMap* tm, const float* base, int64_t rows, int Kp, int box_rows) {
+// 2-D row-major [rows, Kp] (fp32, or fp16 when f16) with a (128 bytes x box_rows) box and the 128-byte swizzle
+static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int Kp, int box_rows, bool f16) {
     auto enc = get_tensormap_encoder();
     KGE_REQUIRE(enc != nullptr, "kge_rank_counts: cuTensorMapEncodeTiled unavailable in this driver");
+    const size_t esz = f16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)Kp * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     KGE_REQUIRE(r == CUDA_SUCCESS, "kge_rank_counts: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
@@ -368,28 +428,47 @@ int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ
         q_row0 = T;
         M = T;
     }
-    const int Kp = ((K + TC_BK - 1) / TC_BK) * TC_BK;
+    static int use_tf32 = -1;  // KGE_RANK_TF32=1: the round-1 3xTF32 operands (A/B)
+    if (use_tf32 < 0) {
+        const char* e = getenv("KGE_RANK_TF32");
+        use_tf32 = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    const bool f16 = use_tf32 == 0;
+    const int kb_elems = f16 ? 64 : 32;  // elements per 128-byte k-block
+    const size_t esz = f16 ? 2 : 4;
+    const int Kp = ((K + kb_elems - 1) / kb_elems) * kb_elems;
     const int64_t Mp = ((M + TC_BM - 1) / TC_BM) * TC_BM;
     const int64_t Np = ((n_local + TC_BN - 1) / TC_BN) * TC_BN;
     KGE_REQUIRE(2 * Mp < (int64_t)INT32_MAX && 2 * Np < (int64_t)INT32_MAX, "kge_rank_counts: operand too large for the TMA coordinates");
-    if (ctx->q_hi.reserve((size_t)2 * Mp * Kp * sizeof(float))) return -2;
-    if (ctx->e_hi.reserve((size_t)2 * Np * Kp * sizeof(float))) return -2;
+    if (ctx->q_hi.reserve((size_t)2 * Mp * Kp * esz)) return -2;
+    if (ctx->e_hi.reserve((size_t)2 * Np * Kp * esz)) return -2;
+    if (ctx->q_lo.reserve(2 * sizeof(uint32_t))) return -2;  // the two absmax words
+    uint32_t* absmax = ctx->q_lo.as<uint32_t>();
     {
         int threads = 256;
         int64_t tot = Mp * Kp;
         int blocks = (int)std::min<int64_t>((tot + threads - 1) / threads, (int64_t)ctx->sm_count * 32);
-        kge_tf32_split_kernel<<<blocks, threads, 0, st>>>(q + (size_t)q_row0 * K, M, K, Kp, Mp, ctx->q_hi.as<float>());
-        tot = Np * Kp;
-        blocks = (int)std::min<int64_t>((tot + threads - 1) / threads, (int64_t)ctx->sm_count * 32);
-        kge_tf32_split_kernel<<<blocks, threads, 0, st>>>(ent_local, n_local, K, Kp, Np, ctx->e_hi.as<float>());
+        int64_t tot_e = Np * Kp;
+        int blocks_e = (int)std::min<int64_t>((tot_e + threads - 1) / threads, (int64_t)ctx->sm_count * 32);
+        if (f16) {
+            KGE_CUDA_CHECK(cudaMemsetAsync(absmax, 0, 2 * sizeof(uint32_t), st));
+            kge_absmax_kernel<<<std::min(blocks, ctx->sm_count * 8), threads, 0, st>>>(q + (size_t)q_row0 * K, M * (int64_t)K, absmax);
+            kge_absmax_kernel<<<std::min(blocks_e, ctx->sm_count * 8), threads, 0, st>>>(ent_local, n_local * (int64_t)K, absmax + 1);
+            kge_f16_split_kernel<<<blocks, threads, 0, st>>>(q + (size_t)q_row0 * K, M, K, Kp, Mp, absmax, ctx->q_hi.as<__half>());
+            kge_f16_split_kernel<<<blocks_e, threads, 0, st>>>(ent_local, n_local, K, Kp, Np, absmax + 1, ctx->e_hi.as<__half>());
+        } else {
+            kge_tf32_split_kernel<<<blocks, threads, 0, st>>>(q + (size_t)q_row0 * K, M, K, Kp, Mp, ctx->q_hi.as<float>());
+            kge_tf32_split_kernel<<<blocks_e, threads, 0, st>>>(ent_local, n_local, K, Kp, Np, ctx->e_hi.as<float>());
+        }
         KGE_CUDA_CHECK(cudaGetLastError());
     }
     CUtensorMap tmQ, tmE;
-    if (int rc = make_tmap(&tmQ, ctx->q_hi.as<float>(), 2 * Mp, Kp, TC_BM)) return rc;
-    if (int rc = make_tmap(&tmE, ctx->e_hi.as<float>(), 2 * Np, Kp, TC_BN)) return rc;
+    if (int rc = make_tmap(&tmQ, ctx->q_hi.p, 2 * Mp, Kp, TC_BM, f16)) return rc;
+    if (int rc = make_tmap(&tmE, ctx->e_hi.p, 2 * Np, Kp, TC_BN, f16)) return rc;
 
     TcParams P;
-    P.k_blocks = Kp / TC_BK;
+    P.k_blocks = Kp / kb_elems;
+    P.absmax = absmax;
     P.M = M;
     P.Mp = Mp;
     P.Np = Np;
@@ -415,10 +494,12 @@ int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ
     const int grid = std::min(n_units, ctx->sm_count);
     static bool attr_set = false;
     if (!attr_set) {
-        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_set = true;
     }
-    kge_rank_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmQ, tmE, P);
+    if (f16) kge_rank_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmQ, tmE, P);
+    else kge_rank_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmQ, tmE, P);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -140,10 +140,6 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
     const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
     const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
     const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
-    // the optimizer rows of every run that starts in this chunk go in flight now (L2 prefetch by the lane that holds the
-    // run head): the runs are walked one after the other below, and each would otherwise pay its own DRAM round trip
-    if (head && !no_update && prefetch_on(P)) prefetch_row_state(P, key, need_m, need_v);
-
     while (heads) {
         const int a = __ffs(heads) - 1;
         heads &= heads - 1;
@@ -1066,7 +1062,9 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
     P.reg_lambda_ent = a->reg_lambda_ent;
     P.reg_lambda_rel = a->reg_lambda_rel;
     P.touched = nullptr;
-    {   // KGE_APPLY_PREFETCH=0 switches the chunk-wide L2 prefetch of the optimizer rows off (A/B)
+    {   // KGE_APPLY_PREFETCH=0 switches the short-distance L2 prefetch of the narrow-row reduction off (A/B).  Measured on
+        // B200 (profiles/r02_b_summary.md): prefetching the optimizer rows of a whole 16-slot chunk thrashes L2 (DRAM reads
+        // double, cfg5 reduce_apply 0.70 -> 0.86 ms), so only the group kernel prefetches, and only two slots ahead
         static int pf = -1;
         if (pf < 0) {
             const char* e = getenv("KGE_APPLY_PREFETCH");
@@ -1134,6 +1132,7 @@ static int ensure_side_stream(kge_ctx* ctx) {
     int prio_lo = 0, prio_hi = 0;
     KGE_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     KGE_CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_hi));
+    KGE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->lstream, cudaStreamNonBlocking));
     KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming));
     KGE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fwd, cudaEventDisableTiming));
@@ -1346,7 +1345,9 @@ static int pipeline_main(kge_ctx* ctx, const kge_train_args* a, cudaStream_t st,
     const int K = a->ent.K;
     const int64_t S = (int64_t)(3 + a->eta) * a->n_pos;
     if (wait_inside) KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_pro_emit[sid], 0));
-    if (int rc = fwd_bwd_impl(ctx, a, ctx->grad_rows.as<float>(), st, ctx->side)) return rc;
+    // the loss reduction goes to its own stream: on the side stream it would sit behind ev_fwd(t) and hold back the
+    // prologue (emit + sort) of step t+1, which is queued on that in-order stream
+    if (int rc = fwd_bwd_impl(ctx, a, ctx->grad_rows.as<float>(), st, ctx->lstream)) return rc;
     kge_table g;
     memset(&g, 0, sizeof(g));
     g.shard[0] = ctx->grad_rows.as<float>();

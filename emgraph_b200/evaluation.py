@@ -109,16 +109,19 @@ def evaluate_performance(X, model, filter_triples=None, verbose=False, filter_un
             raise ValueError("X must be either a numpy array or an EmgraphBaseDatasetAdaptor.")
         filt_idx = None
         if filter_triples is not None:
-            if isinstance(filter_triples, np.ndarray):
+            if isinstance(X, EvalDataset):
+                # a prepared dataset brings its own filter; filter_triples only switches it on (evaluation/protocol.py:905-915)
+                if not isinstance(filter_triples, bool):
+                    raise Exception("Expected a boolean type")
+                if filter_triples is True:
+                    if X.filter_idx is None:
+                        raise Exception("Filtered evaluation requested but the dataset holds no filter triples")
+                    model.set_filter_for_eval()
+            elif isinstance(filter_triples, np.ndarray):
                 if filter_unseen:
                     filter_triples = filter_unseen_entities(filter_triples, model, verbose=verbose)
                 filt_idx = to_idx(filter_triples, model._ent_index, model._rel_index)
                 model.set_filter_for_eval()
-            elif isinstance(X, EvalDataset):
-                if not isinstance(filter_triples, bool):
-                    raise Exception("Expected a boolean type")
-                if filter_triples is True:
-                    model.set_filter_for_eval()
             else:
                 raise Exception("Invalid datatype for filter. Expected a numpy array or preset data in the adapter.")
         if dataset_handle is None:
