@@ -42,7 +42,8 @@ struct ApplyParams {
     int reg_p;
     float reg_lambda_ent, reg_lambda_rel;
     uint32_t* touched;
-    int prefetch;  // 1: L2-prefetch the optimizer rows of a chunk before walking its runs
+    int prefetch;       // 1: short-distance L2 prefetch of the optimizer rows ahead of the walk (narrow-row kernel)
+    int prefetch_wide;  // 1: the same, one run ahead, in the warp-per-chunk kernel
 };
 
 __device__ __forceinline__ bool prefetch_on(const ApplyParams& P) { return P.prefetch != 0; }

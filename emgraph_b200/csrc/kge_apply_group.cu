@@ -5,13 +5,20 @@
 // row only 8 of its 32 lanes would carry data.  Here a GROUP of GS lanes (8 or 16) owns a chunk, so a warp
 // walks 32/GS chunks at once and every load instruction fetches 32/GS rows.
 //
-// The groups of a warp hold runs of different lengths, so walking "run by run" makes them diverge and the warp
-// issues every instruction once per group (measured: 78 warp-instructions per slot, IPC-bound at 51 % of HBM).
-// The walk is therefore SLOT-synchronous: in step u every group handles slot u of its chunk -- add the slot's row
-// to the running sum; if the slot is the head of a run, fetch the row's w, m, v first; if it is the tail, apply the
-// optimizer (or park the partial sum of a run that crosses chunks).  Most runs of a large sparse batch are one or two
-// slots long, so nearly every step does all three things in every group and the warp stays converged.  The rows of
-// the slots two steps ahead are put in flight with L2 prefetches (short distance: the footprint stays far below L2).
+// Two measured facts shape the kernel (ncu, profiles/r02_c_summary.md): (1) walking a chunk "run by run" makes the
+// groups of a warp diverge -- runs differ in length -- and the warp issues every instruction once per group; (2) the
+// per-slot control work (slot decoding with 64-bit divisions, run bookkeeping, row addressing), done redundantly by
+// every lane, cost 130 warp-instructions per slot against 1 load + 4 FMAs of useful work: the kernel was
+// instruction-bound at 42 % of HBM.  So:
+//   * a lane-PARALLEL prologue writes one 16-byte descriptor per slot into shared memory: source row, coefficient, key and
+//     the flags {head, tail, process, complete, span head, partial index} -- every decision of the run rule is a function
+//     of the slot's key and of six chunk-level scalars, so each lane decides its own slots independently;
+//   * the walk is SLOT-synchronous: in step u every group reads descriptor u (one 128-bit shared load) and does what its
+//     flags say -- fetch the row's w, m, v at a run head, add the slot's row, apply the optimizer (or park the partial
+//     sum of a run that crosses chunks) at a tail.  Most runs of a large sparse batch are one or two slots long, so nearly
+//     every step does all three in every group and the warp stays converged;
+//   * the optimizer rows of the run heads KGE_RAG_PF slots ahead are put in flight with L2 prefetches (short distance:
+//     the footprint stays far below L2 -- prefetching a whole chunk thrashes it, measured).
 //
 // Chunk ids, the rule that decides which chunk finishes a run, the per-chunk partial rows of long runs and the
 // span/hub kernel that finishes them are exactly those of the warp-per-chunk kernel, so the two are interchangeable
@@ -19,29 +26,67 @@
 #include "kge_apply.cuh"
 
 #define KGE_RAG_THREADS 128
-#define KGE_RAG_PF 2  // prefetch distance in slots
+#define KGE_RAG_PF 3  // prefetch distance in slots
+
+#define RAG_HEAD 1u
+#define RAG_TAIL 2u
+#define RAG_PROCESS 4u
+#define RAG_COMPLETE 8u
+#define RAG_SPAN 16u
+#define RAG_OPEN_START 32u
+#define RAG_MODE1 64u  // replacement row of a negative: F(c, Q, r) for the TransE models
+
+struct __align__(16) RagDesc {
+    uint32_t src;   // source row of the slot's contribution: float offset / 4 from the gradient buffer's base
+    float c;
+    int32_t key;
+    uint32_t flags;
+};
+
+// slot -> (source row offset in floats, coefficient, mode) with 32-bit arithmetic (one gradient buffer: n_ranks == 1)
+__device__ __forceinline__ void rag_decode(const GradView& G, uint32_t t, uint32_t n, uint32_t& src_off, float& c, uint32_t& mode1) {
+    const uint32_t K = (uint32_t)G.K, eta_n = (uint32_t)G.eta * n;
+    c = 1.f;
+    mode1 = 0u;
+    if (t < 2u * n) {
+        src_off = t * K;
+    } else if (t < 2u * n + eta_n) {
+        const uint32_t q = t - 2u * n, i = q % n;
+        const float* coef = gbuf_coef(G.base[0], n, G.K);
+        const uint8_t* keep = gbuf_keep(G.base[0], G.eta, n, G.K);
+        c = coef[q];
+        src_off = ((keep[q] ? 3u : 4u) * n + i) * K;
+        mode1 = RAG_MODE1;
+    } else {
+        src_off = (2u * n + (t - 2u * n - eta_n)) * K;
+    }
+}
 
 template <int GS, int TMODE>
 __global__ void __launch_bounds__(KGE_RAG_THREADS) kge_reduce_apply_group_kernel(ApplyParams P) {
     constexpr int V = 4;
     constexpr int GPB = KGE_RAG_THREADS / GS;  // chunks per CTA
-    __shared__ SlotMeta meta[GPB][2 * KGE_CH];
+    __shared__ RagDesc desc[GPB][2 * KGE_CH];
     __shared__ int32_t skey[GPB][2 * KGE_CH + 1];
     const int lane = threadIdx.x & 31, lg = lane & (GS - 1), gib = threadIdx.x / GS;
-    const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << (lane & ~(GS - 1)));
     const int64_t w = (int64_t)blockIdx.x * GPB + gib;
     const int64_t b0 = w * KGE_CH;
     const bool live = b0 < P.n_keys;  // surplus groups of the last CTA idle through the (warp-uniform) loop
     const int cnt = live ? (int)min((int64_t)KGE_CH, P.n_keys - b0) : 0;
     const int K = P.ent.K;
+    const uint32_t n32 = (uint32_t)P.G.n;
 
-    // own chunk in [0,16), the next chunk in [16,32) (candidates for a spill-over run)
-    for (int t = lg; t < 2 * KGE_CH; t += GS) {
+    // ---- keys of the own chunk [0,16) and of the next one [16,32) (candidates for a spill-over run)
+    uint32_t my_slot[2 * KGE_CH / GS];
+#pragma unroll
+    for (int i = 0; i < 2 * KGE_CH / GS; ++i) {
+        const int t = lg + GS * i;
         int32_t key = -2;
+        my_slot[i] = 0;
         if (live && b0 + t < P.n_keys) {
             const uint64_t kv = P.ks[b0 + t];
             key = (int32_t)(kv >> 32);
-            meta[gib][t] = decode_slot(P.G, (int32_t)(kv & 0xffffffffu));
+            my_slot[i] = (uint32_t)(kv & 0xffffffffu);
         }
         skey[gib][t] = key;
     }
@@ -50,17 +95,52 @@ __global__ void __launch_bounds__(KGE_RAG_THREADS) kge_reduce_apply_group_kernel
     const int32_t key_prev2 = (live && b0 > KGE_CH) ? (int32_t)(P.ks[b0 - KGE_CH - 1] >> 32) : -1;
     const int32_t key_next2 = (live && b0 + 2 * KGE_CH < P.n_keys) ? (int32_t)(P.ks[b0 + 2 * KGE_CH] >> 32) : -1;
     __syncwarp();
+    // ---- chunk-level scalars of the run rule
+    const int32_t key_first = skey[gib][0];
     const int32_t key_next = skey[gib][KGE_CH];  // -2 when there is no next chunk
     const int32_t key_last = cnt > 0 ? skey[gib][cnt - 1] : -4;
-    // the last run of the chunk: where it starts, and how far it reaches into the next chunk
-    int last_a = cnt - 1;
-    while (last_a > 0 && skey[gib][last_a - 1] == key_last) --last_a;
-    int ext = 0;
+    int ext = 0;  // slots at the front of the next chunk that continue this chunk's last run
     while (ext < KGE_CH && skey[gib][KGE_CH + ext] == key_last && key_last >= 0) ++ext;
+    const bool first_open = key_first == key_prev;                       // the first run continues a run of chunk w-1
+    const bool last_is_first = key_last == key_first;                    // one run covers the whole chunk
+    const bool last_open_start = last_is_first && first_open;
+    const bool last_reaches_next = cnt == KGE_CH && key_last == key_next;
     // a run that starts here and ends inside the next chunk is finished here (same rule as the warp-per-chunk kernel)
-    const bool last_open_start = (last_a == 0) && (key_last == key_prev);
-    const bool last_spills = cnt == KGE_CH && key_last == key_next && !last_open_start && key_next2 != key_last;
+    const bool last_spills = last_reaches_next && !last_open_start && key_next2 != key_last;
     const int lim = last_spills ? cnt + ext : cnt;
+
+    // ---- lane-parallel descriptors: every decision is a function of the slot's key and the scalars above
+#pragma unroll
+    for (int i = 0; i < 2 * KGE_CH / GS; ++i) {
+        const int t = lg + GS * i;
+        if (t >= lim) continue;
+        const int32_t key = skey[gib][t];
+        uint32_t src, mode1;
+        float c;
+        rag_decode(P.G, my_slot[i], n32, src, c, mode1);
+        const bool head = (t == 0) || (key != skey[gib][t - 1]);
+        const bool tail = (t + 1 == lim) || (skey[gib][t + 1] != key);
+        const bool open_start = first_open && key == key_first;
+        const bool open_end = last_reaches_next && !last_spills && key == key_last;
+        const bool is_rel = key >= P.E;
+        const bool owned = is_rel || ((int64_t)key >= P.row_begin && (int64_t)key < P.row_end);
+        const bool process = owned && !(open_start && !open_end && key_prev2 != key);  // else the head's group (chunk w-1) reduces it
+        const bool complete = !open_start && !open_end;
+        uint32_t f = mode1;
+        f |= head ? RAG_HEAD : 0u;
+        f |= tail ? RAG_TAIL : 0u;
+        f |= process ? RAG_PROCESS : 0u;
+        f |= complete ? RAG_COMPLETE : 0u;
+        f |= (head && process && !open_start && open_end) ? RAG_SPAN : 0u;
+        f |= open_start ? RAG_OPEN_START : 0u;
+        RagDesc d;
+        d.src = src >> 2;
+        d.c = c;
+        d.key = key;
+        d.flags = f;
+        desc[gib][t] = d;
+    }
+    __syncwarp();
 
     const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
     const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
@@ -69,71 +149,71 @@ __global__ void __launch_bounds__(KGE_RAG_THREADS) kge_reduce_apply_group_kernel
     const int cc = min(lg * V, K - V);  // lanes past the end of the row read a valid duplicate and never store
     const bool col_ok = lg * V < K;
     const bool pf = prefetch_on(P) && !no_update;
+    const float* gbase = P.G.base[0];
+    // table bases of this lane's prefetch duty (lane 0: w, lane 1: m, lane 2: v)
+    const int n_lines = (K + 31) / 32;
 
-    // per-run state (group-uniform)
     float g[V], rc[V], mv[V], vv[V];
-    bool process = false, complete = false, open_start = false;
-    RowPtrs r;
-    r.w = r.m = r.v = nullptr;
-    r.is_rel = false;
-    r.owned = false;
-    r.row = 0;
+    float *pw = nullptr, *pm = nullptr, *pv = nullptr;
 #pragma unroll
     for (int x = 0; x < V; ++x) g[x] = rc[x] = mv[x] = vv[x] = 0.f;
 
     for (int u = 0; __any_sync(0xffffffffu, u < lim); ++u) {
         if (u >= lim) continue;
-        const int32_t key = skey[gib][u];
-        const bool head = (u == 0) || (key != skey[gib][u - 1]);
-        const bool tail = (u + 1 == lim) || (skey[gib][u + 1] != key);
-        if (pf && u + KGE_RAG_PF < lim) {
-            // rows needed KGE_RAG_PF slots from now: the slot's gradient row and, at a run head, the row's optimizer state
-            const int un = u + KGE_RAG_PF;
-            const int32_t kn = skey[gib][un];
-            if (lg == 0) prefetch_l2(meta[gib][un].row);
-            if (kn != skey[gib][un - 1] && lg == 1) prefetch_row_state(P, kn, need_m, need_v);
-        }
-        if (head) {
-            // the run [u, b): b = next head, or the end of the chunk (+ the spill-over of the last run)
-            const bool is_last = (u >= last_a);
-            open_start = (u == 0) && (key == key_prev);
-            bool open_end = is_last && cnt == KGE_CH && key == key_next && !last_spills;
-            r = resolve_row(P, key);
-            process = r.owned && !(open_start && !open_end && key_prev2 != key);  // else the head's group (chunk w-1) reduces it
-            complete = !open_start && !open_end;
-            if (process && !open_start && open_end && lg == 0) P.span_list[atomicAdd(P.span_count, 1)] = (int32_t)w;
-            if (process && complete && lg == 0) mark_touched(P, key);
-#pragma unroll
-            for (int x = 0; x < V; ++x) g[x] = rc[x] = mv[x] = vv[x] = 0.f;
-            if (process) {
-                if (complete || TMODE != 0) ldg_vec<V>(rc, r.w + cc);
-                if (complete && need_m) ldg_vec<V>(mv, r.m + cc);
-                if (complete && need_v) ldg_vec<V>(vv, r.v + cc);
+        const RagDesc d = desc[gib][u];
+        const uint32_t f = d.flags;
+        if (pf && u + KGE_RAG_PF < lim && lg < 3 * n_lines) {
+            // optimizer row of a run head KGE_RAG_PF slots ahead -> L2 (lane = tensor * n_lines + line)
+            const RagDesc dn = desc[gib][u + KGE_RAG_PF];
+            if ((dn.flags & (RAG_HEAD | RAG_PROCESS | RAG_COMPLETE)) == (RAG_HEAD | RAG_PROCESS | RAG_COMPLETE)) {
+                const int tsel = lg / n_lines, line = lg - tsel * n_lines;
+                const bool rel = dn.key >= P.E;
+                const int64_t row = rel ? dn.key - P.E : dn.key;
+                const float* base = tsel == 0 ? (rel ? P.rel : P.ent.shard[0]) : (tsel == 1 ? (rel ? P.rel_m : P.ent_m.shard[0]) : (rel ? P.rel_v : P.ent_v.shard[0]));
+                if (tsel == 0 || (tsel == 1 && need_m) || (tsel == 2 && need_v)) prefetch_l2(base + row * K + line * 32);
             }
         }
-        if (process) {
-            float v0[V];
-            const SlotMeta m0 = meta[gib][u];
-            ldg_vec<V>(v0, m0.row + cc);
-            add_slot<V, TMODE>(g, v0, m0.c, m0.mode, rc);
+        if (f & RAG_HEAD) {
+#pragma unroll
+            for (int x = 0; x < V; ++x) g[x] = rc[x] = mv[x] = vv[x] = 0.f;
+            if (f & RAG_PROCESS) {
+                const bool rel = d.key >= P.E;
+                const int64_t off = (int64_t)(rel ? d.key - P.E : d.key) * K + cc;
+                pw = (rel ? P.rel : P.ent.shard[0]) + off;
+                pm = (rel ? P.rel_m : P.ent_m.shard[0]) + off;
+                pv = (rel ? P.rel_v : P.ent_v.shard[0]) + off;
+                const bool complete = (f & RAG_COMPLETE) != 0;
+                if (complete || TMODE != 0) ldg_vec<V>(rc, pw);
+                if (complete && need_m) ldg_vec<V>(mv, pm);
+                if (complete && need_v) ldg_vec<V>(vv, pv);
+                if (lg == 0) {
+                    if (f & RAG_SPAN) P.span_list[atomicAdd(P.span_count, 1)] = (int32_t)w;
+                    if (complete) mark_touched(P, d.key);
+                }
+            }
         }
-        if (tail && process && col_ok) {
-            if (!complete) {
-                st_vec<V>(P.partial + ((size_t)(2 * w + (open_start ? 0 : 1))) * K + cc, g);
-            } else {
-                float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
-                reg_add<V>(P, r.is_rel, g, rc);
-                if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + cc, g);
-                if (!no_update) {
-                    opt_math<V>(P, reset, g, rc, mv, vv);
-                    if (r.m && P.opt != KGE_OPT_SGD) st_vec<V>(r.m + cc, mv);
-                    if (r.v && P.opt == KGE_OPT_ADAM) st_vec<V>(r.v + cc, vv);
-                    st_vec<V>(r.w + cc, rc);
+        if (f & RAG_PROCESS) {
+            float v0[V];
+            ldg_vec<V>(v0, gbase + ((size_t)d.src << 2) + cc);
+            add_slot<V, TMODE>(g, v0, d.c, (f & RAG_MODE1) ? 1 : 0, rc);
+            if ((f & RAG_TAIL) && col_ok) {
+                if (!(f & RAG_COMPLETE)) {
+                    st_vec<V>(P.partial + ((size_t)(2 * w + ((f & RAG_OPEN_START) ? 0 : 1))) * K + cc, g);
+                } else {
+                    const bool rel = d.key >= P.E;
+                    float* dbg = rel ? P.dbg_grad_rel : P.dbg_grad_ent;
+                    reg_add<V>(P, rel, g, rc);
+                    if (dbg != nullptr) st_vec<V>(dbg + (size_t)(rel ? d.key - P.E : d.key) * K + cc, g);
+                    if (!no_update) {
+                        opt_math<V>(P, reset, g, rc, mv, vv);
+                        if (P.opt != KGE_OPT_SGD && (rel ? P.rel_m != nullptr : P.has_m)) st_vec<V>(pm, mv);
+                        if (P.opt == KGE_OPT_ADAM && (rel ? P.rel_v != nullptr : P.has_v)) st_vec<V>(pv, vv);
+                        st_vec<V>(pw, rc);
+                    }
                 }
             }
         }
     }
-    (void)gmask;
 }
 
 template <int GS>
@@ -148,9 +228,15 @@ static int launch_group(const ApplyParams& P, int tmode, cudaStream_t st) {
     return 0;
 }
 
-// level 1 of the reduction for K % 4 == 0, K <= 64; the caller zeroes span_count first and launches the span kernel after
-int kge_launch_apply_group(const ApplyParams& P, int tmode, cudaStream_t st) {
+// can this launch take the narrow-row kernel?  one local gradient buffer, one local table shard, 32-bit slot arithmetic
+bool kge_apply_group_ok(const ApplyParams& P) {
     const int K = P.ent.K;
-    KGE_REQUIRE(K % 4 == 0 && K <= 64, "kge_launch_apply_group: K=%d", K);
-    return K <= 32 ? launch_group<8>(P, tmode, st) : launch_group<16>(P, tmode, st);
+    return K % 4 == 0 && K <= 64 && P.G.n_ranks == 1 && P.ent.n_shards == 1 && P.G.S < ((int64_t)1 << 31) &&
+           5 * P.G.n * (int64_t)K < ((int64_t)1 << 32);
+}
+
+// level 1 of the reduction; the caller zeroes span_count first and launches the span kernel after
+int kge_launch_apply_group(const ApplyParams& P, int tmode, cudaStream_t st) {
+    KGE_REQUIRE(kge_apply_group_ok(P), "kge_launch_apply_group: unsupported shape (K=%d)", P.ent.K);
+    return P.ent.K <= 32 ? launch_group<8>(P, tmode, st) : launch_group<16>(P, tmode, st);
 }

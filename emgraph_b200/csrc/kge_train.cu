@@ -91,6 +91,7 @@ __global__ void kge_loss_reduce_kernel(const float* __restrict__ part, int64_t n
 #include "kge_dim.cuh"
 
 int kge_launch_apply_group(const ApplyParams& P, int tmode, cudaStream_t st);  // kge_apply_group.cu
+bool kge_apply_group_ok(const ApplyParams& P);
 
 
 // Level 1: one warp per chunk of KGE_CH sorted slots.  NCA > 0: lanes own ALL their column vectors of
@@ -140,11 +141,28 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
     const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
     const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
     const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
+    const bool pf = prefetch_on(P) && !no_update && P.prefetch_wide;
     while (heads) {
         const int a = __ffs(heads) - 1;
         heads &= heads - 1;
         int b = heads ? (__ffs(heads) - 1) : cnt;
         const int32_t skey = __shfl_sync(0xffffffffu, key, a);
+        if (pf) {
+            // the runs of a chunk are walked one after the other, each paying a memory round trip for its row's w, m, v:
+            // put the optimizer rows of the NEXT run in flight now (L2 prefetch, one 128-byte line per lane and tensor).  One
+            // run ahead only: prefetching the whole chunk thrashes L2 (measured, profiles/r02_b_summary.md)
+            const int a1 = heads ? (__ffs(heads) - 1) : -1;
+            const int32_t k1 = __shfl_sync(0xffffffffu, key, max(a1, 0));
+            if (a1 >= 0) {
+                const RowPtrs r1 = resolve_row(P, k1);
+                if (r1.owned)
+                    for (int off = lane * 32; off < K; off += 32 * 32) {
+                        prefetch_l2(r1.w + off);
+                        if (need_m && r1.m != nullptr) prefetch_l2(r1.m + off);
+                        if (need_v && r1.v != nullptr) prefetch_l2(r1.v + off);
+                    }
+            }
+        }
         const bool open_start = (a == 0) && (skey == key_prev);
         bool open_end = (b == cnt) && (skey == key_next);
         const RowPtrs r = resolve_row(P, skey);
@@ -756,6 +774,16 @@ static int fwd_bwd_impl(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, 
     P.loss_part = ctx->loss_part.as<float>();
     P.dbg_scores = a->dbg_scores;
     P.stage = a->stage;
+    {   // tables that do not fit L2 make the candidate gather an HBM random-row gather: prefetch behind the ring window.
+        // KGE_FWD_L2PF=0/1 forces it off/on (A/B); default: on when the entity table exceeds 64 MiB
+        static int force = -2;
+        if (force == -2) {
+            const char* e = getenv("KGE_FWD_L2PF");
+            force = e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
+        }
+        const bool big = (size_t)a->ent.rows * a->ent.K * sizeof(float) > ((size_t)64 << 20);
+        P.l2_prefetch = force >= 0 ? force : (big ? 1 : 0);
+    }
     int rc;
     switch (a->model) {
         case KGE_TRANSE_L1: rc = kge_launch_fwd_bwd_m0(P, ctx->sm_count, st); break;
@@ -959,7 +987,7 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
             const char* e = getenv("KGE_APPLY_GROUP");
             grp_on = (e != nullptr && e[0] == '0') ? 0 : 1;
         }
-        grouped = !staged && grp_on != 0 && P.ent.K <= 64;
+        grouped = !staged && grp_on != 0 && kge_apply_group_ok(P);
         if (grouped)
             if (int rc = kge_launch_apply_group(P, tmode, st)) return rc;
     }
@@ -1071,6 +1099,12 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
             pf = (e != nullptr && e[0] == '0') ? 0 : 1;
         }
         P.prefetch = pf;
+        static int pfw = -1;  // KGE_APPLY_PREFETCH_WIDE=1: one-run-ahead prefetch in the warp-per-chunk kernel too (A/B)
+        if (pfw < 0) {
+            const char* e = getenv("KGE_APPLY_PREFETCH_WIDE");
+            pfw = (e != nullptr && e[0] == '1') ? 1 : 0;
+        }
+        P.prefetch_wide = pfw;
     }
     const bool reg = a->reg_p > 0 && (a->reg_lambda_ent != 0.f || a->reg_lambda_rel != 0.f);
     if (!reg) P.reg_p = 0;

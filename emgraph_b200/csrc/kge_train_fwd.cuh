@@ -307,6 +307,7 @@ struct FwdBwdParams {
     float* loss_part;   // [n]
     float* dbg_scores;  // optional [n*(1+eta)]
     const float* stage; // optional local [(2+eta)*n][K]: entity row of slot t (subjects, objects, replacements)
+    int l2_prefetch;    // 1: L2-prefetch the candidate rows that do not fit the bulk-copy ring window yet
 };
 
 // entity row `idx` that sits in entity slot `slot` of this batch: from the staging copy when the
@@ -451,6 +452,14 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
             my_issued = !(lane < lim);
             consumed = 0;
             issue_window();
+            // rows behind the ring window: the bulk copies of at most 2^ns_log2 rows are in flight per warp, which leaves a
+            // random-row gather from HBM latency-bound (ncu r01: 62 % of the copy bandwidth on cfg5).  Their ids are known
+            // now, so they are sent towards L2 right away (one prefetch per 128-byte line, no register or smem held);
+            // the bulk copy that follows later finds them there.
+            if (P.l2_prefetch && lane < lim && !my_issued && P.stage == nullptr) {
+                const float* row = table_row(P.ent, my_idx);
+                for (int off = 0; off < K; off += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+            }
         }
     };
 
