@@ -157,27 +157,38 @@ __device__ __forceinline__ void add_slot(float (&g)[V], const float (&a)[V], flo
     }
 }
 
-// pure-register optimizer math on V columns; m/v are the row's state (ignored when not needed)
-template <int V>
-__device__ __forceinline__ void opt_math(const ApplyParams& P, bool reset, const float (&g)[V], float (&wv)[V], float (&mv)[V], float (&vv)[V]) {
-    if (P.opt == KGE_OPT_ADAM) {
+// square root of the Adam / Adagrad denominators: one MUFU.SQRT (relative error <= 2^-22, far below the 1e-5 the optimizer
+// parity is held to) instead of sqrtf's refinement sequence -- the sparse optimizer runs once per touched row and column and
+// its instruction count is what bounds the narrow-row reduction
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// pure-register optimizer math on V columns, optimizer OPT fixed at compile time; m/v are the row's state (ignored when
+// not needed); lr_t is Adam's bias-corrected rate of this step
+template <int V, int OPT>
+__device__ __forceinline__ void opt_math_t(const ApplyParams& P, bool reset, float lr_t, const float (&g)[V], float (&wv)[V], float (&mv)[V],
+                                           float (&vv)[V]) {
+    if constexpr (OPT == KGE_OPT_ADAM) {
         // Keras Adam (beta1 .9, beta2 .999, eps 1e-7): var -= lr_t * m / (sqrt(v) + eps)
-        const float lr_t = P.dyn != nullptr ? P.dyn->lr_t : P.lr_t;
+        const float b1 = P.beta1, b2 = P.beta2, c1 = 1.f - P.beta1, c2 = 1.f - P.beta2;
 #pragma unroll
         for (int x = 0; x < V; ++x) {
             const float m0 = reset ? 0.f : mv[x], v0 = reset ? 0.f : vv[x];
-            mv[x] = P.beta1 * m0 + (1.f - P.beta1) * g[x];
-            vv[x] = P.beta2 * v0 + (1.f - P.beta2) * g[x] * g[x];
-            wv[x] = wv[x] - __fdividef(lr_t * mv[x], sqrtf(vv[x]) + P.eps);
+            mv[x] = b1 * m0 + c1 * g[x];
+            vv[x] = b2 * v0 + c2 * g[x] * g[x];
+            wv[x] = wv[x] - __fdividef(lr_t * mv[x], fast_sqrt(vv[x]) + P.eps);
         }
-    } else if (P.opt == KGE_OPT_ADAGRAD) {
+    } else if constexpr (OPT == KGE_OPT_ADAGRAD) {
         // Keras Adagrad: accumulator starts at 0.1; var -= lr * g / (sqrt(acc) + eps)
 #pragma unroll
         for (int x = 0; x < V; ++x) {
             mv[x] = (reset ? 0.1f : mv[x]) + g[x] * g[x];
-            wv[x] = wv[x] - __fdividef(P.lr * g[x], sqrtf(mv[x]) + P.eps);
+            wv[x] = wv[x] - __fdividef(P.lr * g[x], fast_sqrt(mv[x]) + P.eps);
         }
-    } else if (P.opt == KGE_OPT_MOMENTUM) {
+    } else if constexpr (OPT == KGE_OPT_MOMENTUM) {
         // Keras SGD momentum: vel = mu*vel - lr*g ; var += vel
 #pragma unroll
         for (int x = 0; x < V; ++x) {
@@ -188,6 +199,15 @@ __device__ __forceinline__ void opt_math(const ApplyParams& P, bool reset, const
 #pragma unroll
         for (int x = 0; x < V; ++x) wv[x] = wv[x] - P.lr * g[x];
     }
+}
+
+// the same with the optimizer chosen at run time (one formula: every reduction kernel produces the same bits)
+template <int V>
+__device__ __forceinline__ void opt_math(const ApplyParams& P, bool reset, const float (&g)[V], float (&wv)[V], float (&mv)[V], float (&vv)[V]) {
+    if (P.opt == KGE_OPT_ADAM) opt_math_t<V, KGE_OPT_ADAM>(P, reset, P.dyn != nullptr ? P.dyn->lr_t : P.lr_t, g, wv, mv, vv);
+    else if (P.opt == KGE_OPT_ADAGRAD) opt_math_t<V, KGE_OPT_ADAGRAD>(P, reset, 0.f, g, wv, mv, vv);
+    else if (P.opt == KGE_OPT_MOMENTUM) opt_math_t<V, KGE_OPT_MOMENTUM>(P, reset, 0.f, g, wv, mv, vv);
+    else opt_math_t<V, KGE_OPT_SGD>(P, reset, 0.f, g, wv, mv, vv);
 }
 
 // gradient of the LP penalty on V columns of a row whose current values are w

@@ -62,7 +62,7 @@ __device__ __forceinline__ void rag_decode(const GradView& G, uint32_t t, uint32
     }
 }
 
-template <int GS, int TMODE>
+template <int GS, int TMODE, int OPT>
 __global__ void __launch_bounds__(KGE_RAG_THREADS) kge_reduce_apply_group_kernel(ApplyParams P) {
     constexpr int V = 4;
     constexpr int GPB = KGE_RAG_THREADS / GS;  // chunks per CTA
@@ -144,88 +144,112 @@ __global__ void __launch_bounds__(KGE_RAG_THREADS) kge_reduce_apply_group_kernel
 
     const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
     const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
-    const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
-    const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
+    const bool need_m = !no_update && !reset && OPT != KGE_OPT_SGD;
+    const bool need_v = !no_update && !reset && OPT == KGE_OPT_ADAM;
+    const float lr_t = P.dyn != nullptr ? P.dyn->lr_t : P.lr_t;
     const int cc = min(lg * V, K - V);  // lanes past the end of the row read a valid duplicate and never store
     const bool col_ok = lg * V < K;
-    const bool pf = prefetch_on(P) && !no_update;
+    const bool pf = prefetch_on(P) && !no_update;  // off unless KGE_APPLY_PREFETCH=1: measured no gain on B200
     const float* gbase = P.G.base[0];
     // table bases of this lane's prefetch duty (lane 0: w, lane 1: m, lane 2: v)
     const int n_lines = (K + 31) / 32;
 
     float g[V], rc[V], mv[V], vv[V];
-    float *pw = nullptr, *pm = nullptr, *pv = nullptr;
 #pragma unroll
     for (int x = 0; x < V; ++x) g[x] = rc[x] = mv[x] = vv[x] = 0.f;
+    const int32_t E32 = (int32_t)P.E;
+    float* const ent_w = P.ent.shard[0];
+    float* const ent_m = P.ent_m.shard[0];
+    float* const ent_v = P.ent_v.shard[0];
+    const bool st_m_ent = OPT != KGE_OPT_SGD && P.has_m, st_m_rel = OPT != KGE_OPT_SGD && P.rel_m != nullptr;
+    const bool st_v_ent = OPT == KGE_OPT_ADAM && P.has_v, st_v_rel = OPT == KGE_OPT_ADAM && P.rel_v != nullptr;
 
+    // The body is written branch-free (selects and predicated loads / stores; the optimizer math runs every step on copies):
+    // the groups of a warp are at different points of their runs, and every divergent branch would be issued once per group.
     for (int u = 0; __any_sync(0xffffffffu, u < lim); ++u) {
         if (u >= lim) continue;
         const RagDesc d = desc[gib][u];
         const uint32_t f = d.flags;
+        const bool head = (f & RAG_HEAD) != 0, proc = (f & RAG_PROCESS) != 0, comp = (f & RAG_COMPLETE) != 0, tail = (f & RAG_TAIL) != 0;
+        const bool rel = d.key >= E32;
+        const size_t off = (size_t)(uint32_t)(rel ? d.key - E32 : d.key) * (uint32_t)K + cc;
+        float* const pw = (rel ? P.rel : ent_w) + off;
+        float* const pm = (rel ? P.rel_m : ent_m) + off;
+        float* const pv = (rel ? P.rel_v : ent_v) + off;
         if (pf && u + KGE_RAG_PF < lim && lg < 3 * n_lines) {
             // optimizer row of a run head KGE_RAG_PF slots ahead -> L2 (lane = tensor * n_lines + line)
             const RagDesc dn = desc[gib][u + KGE_RAG_PF];
             if ((dn.flags & (RAG_HEAD | RAG_PROCESS | RAG_COMPLETE)) == (RAG_HEAD | RAG_PROCESS | RAG_COMPLETE)) {
                 const int tsel = lg / n_lines, line = lg - tsel * n_lines;
-                const bool rel = dn.key >= P.E;
-                const int64_t row = rel ? dn.key - P.E : dn.key;
-                const float* base = tsel == 0 ? (rel ? P.rel : P.ent.shard[0]) : (tsel == 1 ? (rel ? P.rel_m : P.ent_m.shard[0]) : (rel ? P.rel_v : P.ent_v.shard[0]));
+                const bool reln = dn.key >= E32;
+                const int64_t row = reln ? dn.key - E32 : dn.key;
+                const float* base = tsel == 0 ? (reln ? P.rel : ent_w) : (tsel == 1 ? (reln ? P.rel_m : ent_m) : (reln ? P.rel_v : ent_v));
                 if (tsel == 0 || (tsel == 1 && need_m) || (tsel == 2 && need_v)) prefetch_l2(base + row * K + line * 32);
             }
         }
-        if (f & RAG_HEAD) {
+        // ---- run head: fresh sum; the row's w, m, v (predicated loads; the registers keep the previous run's values otherwise)
 #pragma unroll
-            for (int x = 0; x < V; ++x) g[x] = rc[x] = mv[x] = vv[x] = 0.f;
-            if (f & RAG_PROCESS) {
-                const bool rel = d.key >= P.E;
-                const int64_t off = (int64_t)(rel ? d.key - P.E : d.key) * K + cc;
-                pw = (rel ? P.rel : P.ent.shard[0]) + off;
-                pm = (rel ? P.rel_m : P.ent_m.shard[0]) + off;
-                pv = (rel ? P.rel_v : P.ent_v.shard[0]) + off;
-                const bool complete = (f & RAG_COMPLETE) != 0;
-                if (complete || TMODE != 0) ldg_vec<V>(rc, pw);
-                if (complete && need_m) ldg_vec<V>(mv, pm);
-                if (complete && need_v) ldg_vec<V>(vv, pv);
-                if (lg == 0) {
-                    if (f & RAG_SPAN) P.span_list[atomicAdd(P.span_count, 1)] = (int32_t)w;
-                    if (complete) mark_touched(P, d.key);
-                }
+        for (int x = 0; x < V; ++x) g[x] = head ? 0.f : g[x];
+        const bool hp = head && proc;
+        if (hp && (comp || TMODE != 0)) ldg_vec<V>(rc, pw);
+        if (hp && comp && need_m) ldg_vec<V>(mv, pm);
+        if (hp && comp && need_v) ldg_vec<V>(vv, pv);
+        if (hp && lg == 0 && ((f & RAG_SPAN) != 0 || (comp && P.touched != nullptr))) {  // rare
+            if (f & RAG_SPAN) P.span_list[atomicAdd(P.span_count, 1)] = (int32_t)w;
+            if (comp) mark_touched(P, d.key);
+        }
+        // ---- the slot's contribution
+        float v0[V];
+#pragma unroll
+        for (int x = 0; x < V; ++x) v0[x] = 0.f;
+        if (proc) ldg_vec<V>(v0, gbase + ((size_t)d.src << 2) + cc);
+        add_slot<V, TMODE>(g, v0, d.c, (f & RAG_MODE1) ? 1 : 0, rc);
+        // ---- run tail: optimizer on copies (computed every step, stored at a complete tail), or the partial sum parked
+        const bool tp = tail && proc && col_ok;
+        if (tp && !comp) st_vec<V>(P.partial + ((size_t)(2 * w + ((f & RAG_OPEN_START) ? 0 : 1))) * K + cc, g);
+        float gg[V], w2[V], m2[V], v2[V];
+#pragma unroll
+        for (int x = 0; x < V; ++x) {
+            gg[x] = g[x];
+            w2[x] = rc[x];
+            m2[x] = mv[x];
+            v2[x] = vv[x];
+        }
+        if (P.reg_p > 0 || P.dbg_grad_ent != nullptr || P.dbg_grad_rel != nullptr) {  // LP regulariser / parity tests: uniform, normally false
+            if (tp && comp) {
+                float* dbg = rel ? P.dbg_grad_rel : P.dbg_grad_ent;
+                reg_add<V>(P, rel, gg, rc);
+                if (dbg != nullptr) st_vec<V>(dbg + (size_t)(rel ? d.key - E32 : d.key) * K + cc, gg);
             }
         }
-        if (f & RAG_PROCESS) {
-            float v0[V];
-            ldg_vec<V>(v0, gbase + ((size_t)d.src << 2) + cc);
-            add_slot<V, TMODE>(g, v0, d.c, (f & RAG_MODE1) ? 1 : 0, rc);
-            if ((f & RAG_TAIL) && col_ok) {
-                if (!(f & RAG_COMPLETE)) {
-                    st_vec<V>(P.partial + ((size_t)(2 * w + ((f & RAG_OPEN_START) ? 0 : 1))) * K + cc, g);
-                } else {
-                    const bool rel = d.key >= P.E;
-                    float* dbg = rel ? P.dbg_grad_rel : P.dbg_grad_ent;
-                    reg_add<V>(P, rel, g, rc);
-                    if (dbg != nullptr) st_vec<V>(dbg + (size_t)(rel ? d.key - P.E : d.key) * K + cc, g);
-                    if (!no_update) {
-                        opt_math<V>(P, reset, g, rc, mv, vv);
-                        if (P.opt != KGE_OPT_SGD && (rel ? P.rel_m != nullptr : P.has_m)) st_vec<V>(pm, mv);
-                        if (P.opt == KGE_OPT_ADAM && (rel ? P.rel_v != nullptr : P.has_v)) st_vec<V>(pv, vv);
-                        st_vec<V>(pw, rc);
-                    }
-                }
-            }
-        }
+        opt_math_t<V, OPT>(P, reset, lr_t, gg, w2, m2, v2);
+        const bool st = tp && comp && !no_update;
+        if (st && (rel ? st_m_rel : st_m_ent)) st_vec<V>(pm, m2);
+        if (st && (rel ? st_v_rel : st_v_ent)) st_vec<V>(pv, v2);
+        if (st) st_vec<V>(pw, w2);
     }
+}
+
+template <int GS, int TMODE>
+static int launch_group_opt(const ApplyParams& P, cudaStream_t st) {
+    constexpr int GPB = KGE_RAG_THREADS / GS;
+    const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
+    dim3 grid((unsigned)((n_chunks + GPB - 1) / GPB)), block(KGE_RAG_THREADS);
+    switch (P.opt) {
+        case KGE_OPT_ADAM: kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_ADAM><<<grid, block, 0, st>>>(P); break;
+        case KGE_OPT_ADAGRAD: kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_ADAGRAD><<<grid, block, 0, st>>>(P); break;
+        case KGE_OPT_MOMENTUM: kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_MOMENTUM><<<grid, block, 0, st>>>(P); break;
+        default: kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_SGD><<<grid, block, 0, st>>>(P); break;
+    }
+    KGE_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 template <int GS>
 static int launch_group(const ApplyParams& P, int tmode, cudaStream_t st) {
-    constexpr int GPB = KGE_RAG_THREADS / GS;
-    const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
-    dim3 grid((unsigned)((n_chunks + GPB - 1) / GPB)), block(KGE_RAG_THREADS);
-    if (tmode == 0) kge_reduce_apply_group_kernel<GS, 0><<<grid, block, 0, st>>>(P);
-    else if (tmode == 1) kge_reduce_apply_group_kernel<GS, 1><<<grid, block, 0, st>>>(P);
-    else kge_reduce_apply_group_kernel<GS, 2><<<grid, block, 0, st>>>(P);
-    KGE_CUDA_CHECK(cudaGetLastError());
-    return 0;
+    if (tmode == 0) return launch_group_opt<GS, 0>(P, st);
+    if (tmode == 1) return launch_group_opt<GS, 1>(P, st);
+    return launch_group_opt<GS, 2>(P, st);
 }
 
 // can this launch take the narrow-row kernel?  one local gradient buffer, one local table shard, 32-bit slot arithmetic

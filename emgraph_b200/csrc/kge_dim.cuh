@@ -101,7 +101,7 @@ __device__ __forceinline__ void row_select(Row<4, NCH, CPLX>& d, bool first, con
 // lanes therefore load the ids of the round KGE_DIM_PF rounds ahead at the top of a round and, at its end, put those
 // rows in flight with L2 prefetches (no registers held, no dependency): when their round comes the row loads hit L2.
 // The footprint -- resident groups x U x KGE_DIM_PF rows -- stays a fraction of L2.
-#define KGE_DIM_PF 2
+#define KGE_DIM_PF 1000  // rounds of look-ahead; 1000 = off: measured slower on B200 (partial 198 -> 213 us, backward 213 -> 227 us)
 __device__ __forceinline__ void dim_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // prefetch the K floats of a row slice: one 128-byte line per 32 floats, lines dealt over the lanes of the group
 template <int GS>

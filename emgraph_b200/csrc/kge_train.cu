@@ -774,15 +774,16 @@ static int fwd_bwd_impl(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, 
     P.loss_part = ctx->loss_part.as<float>();
     P.dbg_scores = a->dbg_scores;
     P.stage = a->stage;
-    {   // tables that do not fit L2 make the candidate gather an HBM random-row gather: prefetch behind the ring window.
-        // KGE_FWD_L2PF=0/1 forces it off/on (A/B); default: on when the entity table exceeds 64 MiB
+    {   // tables that do not fit L2 make the candidate gather an HBM random-row gather: optional prefetch behind the ring
+        // window, KGE_FWD_L2PF=1 (A/B knob)
         static int force = -2;
         if (force == -2) {
             const char* e = getenv("KGE_FWD_L2PF");
             force = e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
         }
         const bool big = (size_t)a->ent.rows * a->ent.K * sizeof(float) > ((size_t)64 << 20);
-        P.l2_prefetch = force >= 0 ? force : (big ? 1 : 0);
+        (void)big;
+        P.l2_prefetch = force > 0 ? 1 : 0;  // measured slower on cfg5 (fwd_bwd 0.210 -> 0.251 ms): off unless forced
     }
     int rc;
     switch (a->model) {
@@ -1090,13 +1091,14 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
     P.reg_lambda_ent = a->reg_lambda_ent;
     P.reg_lambda_rel = a->reg_lambda_rel;
     P.touched = nullptr;
-    {   // KGE_APPLY_PREFETCH=0 switches the short-distance L2 prefetch of the narrow-row reduction off (A/B).  Measured on
-        // B200 (profiles/r02_b_summary.md): prefetching the optimizer rows of a whole 16-slot chunk thrashes L2 (DRAM reads
-        // double, cfg5 reduce_apply 0.70 -> 0.86 ms), so only the group kernel prefetches, and only two slots ahead
+    {   // KGE_APPLY_PREFETCH=1 switches the short-distance L2 prefetch of the narrow-row reduction on (A/B knob, off by default).
+        // Measured on B200 (profiles/r02_summary.md): prefetching the optimizer rows of a whole 16-slot chunk thrashes L2 (DRAM
+        // reads double, cfg5 reduce_apply 0.70 -> 0.86 ms) and a 2-3 slot look-ahead changes nothing: these kernels are bound by
+        // the DRAM request rate of random 128-byte rows and by instruction issue, not by exposed latency
         static int pf = -1;
         if (pf < 0) {
             const char* e = getenv("KGE_APPLY_PREFETCH");
-            pf = (e != nullptr && e[0] == '0') ? 0 : 1;
+            pf = (e != nullptr && e[0] == '1') ? 1 : 0;
         }
         P.prefetch = pf;
         static int pfw = -1;  // KGE_APPLY_PREFETCH_WIDE=1: one-run-ahead prefetch in the warp-per-chunk kernel too (A/B)
