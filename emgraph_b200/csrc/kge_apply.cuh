@@ -66,9 +66,17 @@ struct SlotMeta {
     int mode;  // 0: add row ; 1: replacement row of a negative, F(c, Q, r)
 };
 
-__device__ __forceinline__ SlotMeta decode_slot(const GradView& G, int32_t slot) {
+// Low word of a sort entry: slot id in bits [0,30); bit 31 = "the side of this negative travels with the entry", bit 30 =
+// that side (1: subject kept -> query Qo).  kge_emit_kernel knows the side when it writes the entry, so the reduction does
+// not have to fetch one byte per negative from a 32-byte DRAM sector in sorted (= random) order.  Entries made elsewhere
+// (owner-side selection of the row-sharded path) leave both bits clear and the side is read from the gradient buffer.
+#define KGE_SLOT_MASK 0x3fffffffu
+#define KGE_SLOT_HAS_SIDE 0x80000000u
+#define KGE_SLOT_SIDE 0x40000000u
+
+__device__ __forceinline__ SlotMeta decode_slot(const GradView& G, uint32_t word) {
     int rr = 0;
-    int64_t t = slot;
+    int64_t t = (int64_t)(word & KGE_SLOT_MASK);
     if (G.n_ranks > 1) {
         rr = (int)(t / G.S);
         t -= (int64_t)rr * G.S;
@@ -87,7 +95,8 @@ __device__ __forceinline__ SlotMeta decode_slot(const GradView& G, int32_t slot)
         const float* coef = gbuf_coef(tbase, n, G.K);
         const uint8_t* keep = gbuf_keep(tbase, G.eta, n, G.K);
         m.c = coef[q];
-        m.row = tbase + ((keep[q] ? 3 : 4) * n + i) * G.K;
+        const bool kept = (word & KGE_SLOT_HAS_SIDE) ? (word & KGE_SLOT_SIDE) != 0 : keep[q] != 0;
+        m.row = tbase + ((kept ? 3 : 4) * n + i) * G.K;
         m.mode = 1;
     } else {
         m.row = base + (2 * n + (t - 2 * n - (int64_t)G.eta * n)) * G.K;
@@ -137,6 +146,15 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 // prefetch w (and m, v when the optimizer reads them) of row `key` -- K floats each
 __device__ __forceinline__ void prefetch_row_state(const ApplyParams& P, int32_t key, bool need_m, bool need_v);
+
+// streaming variants for data touched once per step (the optimizer rows): evict-first in L1 and L2, so that the rows that
+// ARE reused within the step -- queries, coefficients, sort entries -- stay cached
+__device__ __forceinline__ void ldg_vec4_cs(float (&d)[4], const float* p) {
+    asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]) : "l"(p));
+}
+__device__ __forceinline__ void stg_vec4_cs(float* p, const float (&d)[4]) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(d[0]), "f"(d[1]), "f"(d[2]), "f"(d[3]) : "memory");
+}
 
 // contribution of one slot to V columns of the gradient; rc = current value of the row being updated.
 // Plain gradient rows (mode 0) carry c = 1, so the trilinear models need no branch at all.

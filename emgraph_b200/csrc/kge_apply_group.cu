@@ -44,8 +44,8 @@ struct __align__(16) RagDesc {
 };
 
 // slot -> (source row offset in floats, coefficient, mode) with 32-bit arithmetic (one gradient buffer: n_ranks == 1)
-__device__ __forceinline__ void rag_decode(const GradView& G, uint32_t t, uint32_t n, uint32_t& src_off, float& c, uint32_t& mode1) {
-    const uint32_t K = (uint32_t)G.K, eta_n = (uint32_t)G.eta * n;
+__device__ __forceinline__ void rag_decode(const GradView& G, uint32_t word, uint32_t n, uint32_t& src_off, float& c, uint32_t& mode1) {
+    const uint32_t K = (uint32_t)G.K, eta_n = (uint32_t)G.eta * n, t = word & KGE_SLOT_MASK;
     c = 1.f;
     mode1 = 0u;
     if (t < 2u * n) {
@@ -55,7 +55,8 @@ __device__ __forceinline__ void rag_decode(const GradView& G, uint32_t t, uint32
         const float* coef = gbuf_coef(G.base[0], n, G.K);
         const uint8_t* keep = gbuf_keep(G.base[0], G.eta, n, G.K);
         c = coef[q];
-        src_off = ((keep[q] ? 3u : 4u) * n + i) * K;
+        const bool kept = (word & KGE_SLOT_HAS_SIDE) ? (word & KGE_SLOT_SIDE) != 0 : keep[q] != 0;
+        src_off = ((kept ? 3u : 4u) * n + i) * K;
         mode1 = RAG_MODE1;
     } else {
         src_off = (2u * n + (t - 2u * n - eta_n)) * K;
@@ -191,9 +192,9 @@ __global__ void __launch_bounds__(KGE_RAG_THREADS) kge_reduce_apply_group_kernel
 #pragma unroll
         for (int x = 0; x < V; ++x) g[x] = head ? 0.f : g[x];
         const bool hp = head && proc;
-        if (hp && (comp || TMODE != 0)) ldg_vec<V>(rc, pw);
-        if (hp && comp && need_m) ldg_vec<V>(mv, pm);
-        if (hp && comp && need_v) ldg_vec<V>(vv, pv);
+        if (hp && (comp || TMODE != 0)) ldg_vec4_cs(rc, pw);  // touched once per step: streaming (evict-first)
+        if (hp && comp && need_m) ldg_vec4_cs(mv, pm);
+        if (hp && comp && need_v) ldg_vec4_cs(vv, pv);
         if (hp && lg == 0 && ((f & RAG_SPAN) != 0 || (comp && P.touched != nullptr))) {  // rare
             if (f & RAG_SPAN) P.span_list[atomicAdd(P.span_count, 1)] = (int32_t)w;
             if (comp) mark_touched(P, d.key);
@@ -224,9 +225,9 @@ __global__ void __launch_bounds__(KGE_RAG_THREADS) kge_reduce_apply_group_kernel
         }
         opt_math_t<V, OPT>(P, reset, lr_t, gg, w2, m2, v2);
         const bool st = tp && comp && !no_update;
-        if (st && (rel ? st_m_rel : st_m_ent)) st_vec<V>(pm, m2);
-        if (st && (rel ? st_v_rel : st_v_ent)) st_vec<V>(pv, v2);
-        if (st) st_vec<V>(pw, w2);
+        if (st && (rel ? st_m_rel : st_m_ent)) stg_vec4_cs(pm, m2);
+        if (st && (rel ? st_v_rel : st_v_ent)) stg_vec4_cs(pv, v2);
+        if (st) stg_vec4_cs(pw, w2);
     }
 }
 

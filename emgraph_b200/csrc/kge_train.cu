@@ -18,6 +18,7 @@
 #include <cub/device/device_select.cuh>
 
 #include "kge_train_fwd.cuh"
+#include "kge_apply.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // slot layout for one batch of n positives (S = (3+eta)*n slots)
@@ -37,6 +38,7 @@ __global__ void kge_emit_kernel(const int32_t* __restrict__ pos, int64_t n, int 
     if (dyn != nullptr) step = dyn->step;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < S; t += (int64_t)gridDim.x * blockDim.x) {
         int32_t key;
+        uint32_t side_bits = 0;  // negatives: the corrupted side rides in the sort entry (kge_apply.cuh: KGE_SLOT_*)
         if (t < n) {
             key = pos[3 * t + 0];
         } else if (t < 2 * n) {
@@ -65,29 +67,45 @@ __global__ void kge_emit_kernel(const int32_t* __restrict__ pos, int64_t n, int 
             repl_out[q] = r;
             keep_out[q] = ks;
             key = r;
+            side_bits = KGE_SLOT_HAS_SIDE | (ks ? KGE_SLOT_SIDE : 0u);
         } else {
             key = (int32_t)E + pos[3 * (t - 2 * n - (int64_t)eta * n) + 1];
         }
         if (keys != nullptr) keys[t] = key;
-        if (packed != nullptr) packed[t] = ((uint64_t)(uint32_t)key << 32) | (uint64_t)(uint32_t)t;
+        if (packed != nullptr) packed[t] = ((uint64_t)(uint32_t)key << 32) | (uint64_t)((uint32_t)t | side_bits);
     }
 }
 
-// deterministic fixed-order reduction of the per-positive loss terms
-__global__ void kge_loss_reduce_kernel(const float* __restrict__ part, int64_t n, float* __restrict__ out) {
-    __shared__ double sm[1024];
+// deterministic fixed-order reduction of the per-positive loss terms: CTA b sums terms b, b+G, ... in double, the last CTA
+// to finish (ticket counter) adds the G partial sums in index order -- one launch, the same bits every time
+#define KGE_LOSS_CTAS 64
+__global__ void __launch_bounds__(256) kge_loss_reduce_kernel(const float* __restrict__ part, int64_t n, float* __restrict__ out,
+                                                              double* __restrict__ scratch, unsigned int* __restrict__ ticket) {
+    __shared__ double sm[256];
+    __shared__ bool last;
     double acc = 0.0;
-    for (int64_t t = threadIdx.x; t < n; t += blockDim.x) acc += (double)part[t];
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) acc += (double)part[t];
     sm[threadIdx.x] = acc;
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = (float)sm[0];
+    if (threadIdx.x == 0) {
+        scratch[blockIdx.x] = sm[0];
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double tot = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) tot += ((volatile double*)scratch)[b];
+        out[0] = (float)tot;
+        *ticket = 0u;  // ready for the next launch
+    }
 }
 
-#include "kge_apply.cuh"
 #include "kge_dim.cuh"
 
 int kge_launch_apply_group(const ApplyParams& P, int tmode, cudaStream_t st);  // kge_apply_group.cu
@@ -119,7 +137,7 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
     if (b0 + lane < P.n_keys) {
         const uint64_t kv = P.ks[b0 + lane];
         key = (int32_t)(kv >> 32);
-        meta[wib][lane] = decode_slot(P.G, (int32_t)(kv & 0xffffffffu));
+        meta[wib][lane] = decode_slot(P.G, (uint32_t)(kv & 0xffffffffu));
     }
     int32_t key_prev = -1, key_prev2 = -1, key_next2 = -1;
     if (lane == 0 && b0 > 0) key_prev = (int32_t)(P.ks[b0 - 1] >> 32);
@@ -332,7 +350,7 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_staged_ker
     if (b0 + lane < P.n_keys) {
         const uint64_t kv = P.ks[b0 + lane];
         key = (int32_t)(kv >> 32);
-        meta[wib][lane] = decode_slot(P.G, (int32_t)(kv & 0xffffffffu));
+        meta[wib][lane] = decode_slot(P.G, (uint32_t)(kv & 0xffffffffu));
     }
     int32_t key_prev = -1, key_prev2 = -1, key_next2 = -1;
     if (lane == 0 && b0 > 0) key_prev = (int32_t)(P.ks[b0 - 1] >> 32);
@@ -719,6 +737,10 @@ static int ensure_train_ws(kge_ctx* ctx, const kge_train_args* a) {
     if (ctx->repl.reserve((size_t)a->eta * n * sizeof(int32_t))) return -2;
     if (ctx->keep.reserve((size_t)a->eta * n)) return -2;
     if (ctx->loss_part.reserve((size_t)(n + 1) * sizeof(float))) return -2;
+    if (ctx->loss_scr.cap == 0) {  // partial sums + ticket counter of kge_loss_reduce_kernel; the ticket starts at 0
+        if (ctx->loss_scr.reserve((KGE_LOSS_CTAS + 2) * sizeof(double))) return -2;
+        KGE_CUDA_CHECK(cudaMemset(ctx->loss_scr.p, 0, (KGE_LOSS_CTAS + 2) * sizeof(double)));
+    }
     return 0;
 }
 
@@ -799,7 +821,8 @@ static int fwd_bwd_impl(kge_ctx* ctx, const kge_train_args* a, float* grad_buf, 
         KGE_CUDA_CHECK(cudaStreamWaitEvent(side, ctx->ev_fwd, 0));
         ls = side;
     }
-    kge_loss_reduce_kernel<<<1, 1024, 0, ls>>>(ctx->loss_part.as<float>(), a->n_pos, a->loss_out);
+    kge_loss_reduce_kernel<<<KGE_LOSS_CTAS, 256, 0, ls>>>(ctx->loss_part.as<float>(), a->n_pos, a->loss_out, ctx->loss_scr.as<double>(),
+                                                         reinterpret_cast<unsigned int*>(ctx->loss_scr.as<double>() + KGE_LOSS_CTAS));
     KGE_CUDA_CHECK(cudaGetLastError());
     if (side != nullptr) KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_loss, side));
     return 0;
@@ -1015,7 +1038,7 @@ static int launch_apply(const ApplyParams& P, int tmode, int sm_count, cudaStrea
 
 // packed_in: n_items (key << 32 | global slot) entries, unsorted; sorted by key (stable) into ctx->ks_sorted
 static int sort_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* packed_in, int64_t n_items, cudaStream_t st) {
-    KGE_REQUIRE(n_items < (int64_t)INT32_MAX, "kge_train_apply: too many slots");
+    KGE_REQUIRE(n_items <= (int64_t)KGE_SLOT_MASK, "kge_train_apply: too many slots");
     if (n_items == 0) return 0;
     const int K = a->ent.K;
     const int64_t n_chunks = (n_items + KGE_CH - 1) / KGE_CH;
@@ -1672,7 +1695,8 @@ extern "C" int kge_train_reduce(kge_ctx* ctx, const kge_train_args* a, void* str
     }
     KGE_REQUIRE(a->ent.n_shards == 1, "kge_train_reduce: a->ent must be the local column slice");
     const int64_t S = (int64_t)(3 + a->eta) * a->n_pos;
-    kge_loss_reduce_kernel<<<1, 1024, 0, st>>>(ctx->loss_part.as<float>(), a->n_pos, a->loss_out);
+    kge_loss_reduce_kernel<<<KGE_LOSS_CTAS, 256, 0, st>>>(ctx->loss_part.as<float>(), a->n_pos, a->loss_out, ctx->loss_scr.as<double>(),
+                                                         reinterpret_cast<unsigned int*>(ctx->loss_scr.as<double>() + KGE_LOSS_CTAS));
     KGE_CUDA_CHECK(cudaGetLastError());
     kge_table g;
     memset(&g, 0, sizeof(g));

@@ -463,7 +463,8 @@ class ShardedKGE:
         pos_all = pos_local if pos_is_global else self.gather_batch(pos_local)
         n = pos_all.shape[0]
         assert 0 < n <= self.n, "global batch of %d positives; this model was sized for %d" % (n, self.n)
-        bounds = chunk_bounds(n, self.chunks)
+        # small batches: the all-reduce payload is a few hundred KB and latency-bound -- cutting it up only adds launches
+        bounds = chunk_bounds(n, self.chunks if n * (1 + self.eta) * 4 >= (2 << 20) else 1)
         sums = [self.sums_flat[(1 + self.eta) * lo:(1 + self.eta) * hi] for lo, hi in bounds]
         self.step += 1
         # the side-stream prologue may only read batches that were resident before the previous step was submitted

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, session E (1 GPU): branch-free group reduction
-O=gpurun_out; mkdir -p $O; T=r2e
+O=gpurun_out; mkdir -p $O; T=r2g
 ( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > $O/${T}_pytest_all.log
 for W in 8 4 2; do
   timeout 300 python tools/dim_probe.py --workload cfg5 --world $W --steps 15 > $O/${T}_probe_cfg5_w$W.json 2> $O/${T}_probe_cfg5_w$W.err
