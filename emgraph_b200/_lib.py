@@ -77,6 +77,7 @@ SYMBOLS = {
     "kge_train_fwd_bwd": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P]),
     "kge_train_apply": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _L, C.POINTER(KgeTable), _L, _L, _P]),
     "kge_train_partial": (_I, [_P, C.POINTER(KgeTrainArgs), _L, _L, _P, _P]),
+    "kge_train_partial_sorted": (_I, [_P, C.POINTER(KgeTrainArgs), _I, _P, _P]),
     "kge_train_backward": (_I, [_P, C.POINTER(KgeTrainArgs), _L, _L, _P, _P]),
     "kge_train_reduce": (_I, [_P, C.POINTER(KgeTrainArgs), _P]),
     "kge_train_step_host": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P, _P]),

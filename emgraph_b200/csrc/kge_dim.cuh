@@ -374,6 +374,117 @@ __global__ void __launch_bounds__(KGE_DIM_THREADS, (DimOcc<MODEL, NCH>::bwd)) kg
     }
 }
 
+// ---------------------------------------------------------------------------------------------- phase 1, sorted order
+// The candidate gather of kge_dim_partial_kernel reads 128-byte row slices in RANDOM order, and HBM delivers those at ~40 %
+// of its copy bandwidth (request-rate bound: ncu, profiles/r02_summary.md).  The sort entries of the step list the same rows
+// in ascending row order, duplicates adjacent.  So phase 1 can run over the SORTED entries instead: every entity row is then
+// streamed once, in address order, and what is gathered at random is the 2n-row query table, which lives in L2:
+//   kge_dim_query_kernel           per positive: Qo, Qs -> the gradient buffer's query rows; the positive's own partial sum
+//   kge_dim_sorted_partial_kernel  per sort entry that is a negative (j,i): <Q_side(i), row(key)> -> sums
+// Layout of `sums`: chunk-major for n_chunks pieces of the positive range (distributed.py:chunk_bounds), so that the host
+// can all-reduce piece c while piece c+1 is still being consumed.
+struct DimChunks {
+    uint32_t base, extra;  // n = n_chunks*base + extra; the first `extra` chunks hold base+1 positives
+};
+__device__ __forceinline__ void dim_chunk_of(const DimChunks& C, uint32_t i, uint32_t& lo, uint32_t& nc) {
+    const uint32_t split = C.extra * (C.base + 1);
+    const uint32_t c = i < split ? i / (C.base + 1) : C.extra + (i - split) / C.base;
+    lo = c * C.base + min(c, C.extra);
+    nc = C.base + (c < C.extra ? 1u : 0u);
+}
+
+template <int MODEL, int GS, int NCH>
+__global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_query_kernel(DimParams P, DimChunks C, int eta1) {
+    using A = Algebra<MODEL, 4, NCH>;
+    using R = typename A::R;
+    const int lane = threadIdx.x & 31, lg = lane & (GS - 1);
+    const int64_t n = P.n;
+    const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GS;
+    const bool valid = grp < n;
+    const int64_t i = valid ? grp : n - 1;
+    const int K = P.K;
+    const int half = A::CPLX ? P.k : 0;
+    const int nvec = (A::CPLX ? P.k : K) / 4;
+    float msk[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) msk[c] = 1.f;
+    R s, p, o, Qo, Qs;
+    const int32_t si = P.pos[3 * i + 0], pi = P.pos[3 * i + 1], oi = P.pos[3 * i + 2];
+    grow_load<GS>(s, P.ent + (size_t)si * K, lg, nvec, half);
+    grow_load<GS>(p, P.rel + (size_t)pi * K, lg, nvec, half);
+    grow_load<GS>(o, P.ent + (size_t)oi * K, lg, nvec, half);
+    A::queries(s, p, o, Qo, Qs);
+    const float sp = group_sum<GS>(A::partial(Qo, o, msk));
+    if (!valid) return;
+    grow_store<GS>(P.gbuf + (size_t)(3 * n + i) * K, Qo, lg, nvec, half);
+    grow_store<GS>(P.gbuf + (size_t)(4 * n + i) * K, Qs, lg, nvec, half);
+    if (lg == 0) {
+        uint32_t lo, nc;
+        dim_chunk_of(C, (uint32_t)i, lo, nc);
+        P.sums[(size_t)eta1 * lo + ((uint32_t)i - lo)] = sp;
+    }
+}
+
+template <int MODEL, int GS, int NCH, int U>
+__global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_sorted_partial_kernel(DimParams P, DimChunks C, const uint64_t* __restrict__ ks,
+                                                                                 int64_t n_keys, int eta1) {
+    using A = Algebra<MODEL, 4, NCH>;
+    using R = typename A::R;
+    const int lane = threadIdx.x & 31, lg = lane & (GS - 1);
+    const uint32_t n = (uint32_t)P.n, eta_n = (uint32_t)P.eta * n;
+    const int K = P.K;
+    const int half = A::CPLX ? P.k : 0;
+    const int nvec = (A::CPLX ? P.k : K) / 4;
+    float msk[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) msk[c] = 1.f;
+    // a group takes U consecutive sort entries (neighbours often name the same row: the second load hits L1)
+    const int64_t x0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GS) * U;
+    R r[U], Q[U];
+    uint32_t off[U];
+    bool neg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t x = x0 + u;
+        neg[u] = false;
+        off[u] = 0;
+        uint64_t kv = 0;
+        if (x < n_keys) kv = ks[x];
+        const uint32_t word = (uint32_t)(kv & 0xffffffffu), t = word & 0x3fffffffu;
+        const uint32_t key = (uint32_t)(kv >> 32);
+        const bool is_neg = x < n_keys && t >= 2u * n && t < 2u * n + eta_n;
+        uint32_t i = 0, j = 0;
+        if (is_neg) {
+            const uint32_t q = t - 2u * n;
+            j = q / n;
+            i = q - j * n;
+        }
+        // the side rides in the sort entry (bit 31 set by kge_emit_kernel); entries without it read the side array
+        const bool kept = (word & 0x80000000u) ? (word & 0x40000000u) != 0 : (is_neg ? P.keep[(size_t)j * n + i] != 0 : false);
+        neg[u] = is_neg;
+        if (is_neg) {
+            uint32_t lo, nc;
+            dim_chunk_of(C, i, lo, nc);
+            off[u] = (uint32_t)eta1 * lo + nc + j * nc + (i - lo);
+            grow_load<GS>(r[u], P.ent + (size_t)key * K, lg, nvec, half);
+            grow_load<GS>(Q[u], P.gbuf + (size_t)((kept ? 3u : 4u) * n + i) * K, lg, nvec, half);
+        } else {
+            row_zero(r[u]);
+            row_zero(Q[u]);
+        }
+    }
+    float pv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) pv[u] = A::partial(Q[u], r[u], msk);
+#pragma unroll
+    for (int o2 = GS / 2; o2 > 0; o2 >>= 1)
+#pragma unroll
+        for (int u = 0; u < U; ++u) pv[u] += __shfl_xor_sync(0xffffffffu, pv[u], o2);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (neg[u] && lg == (u & (GS - 1))) P.sums[off[u]] = pv[u];
+}
+
 // ---------------------------------------------------------------------------------------------- launch
 template <int MODEL, int GS, int NCH, int U>
 static int launch_dim_one(int phase, const DimParams& P, cudaStream_t st) {
@@ -384,6 +495,36 @@ static int launch_dim_one(int phase, const DimParams& P, cudaStream_t st) {
     else kge_dim_backward_kernel<MODEL, GS, NCH, U><<<grid, block, 0, st>>>(P);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+// phase 3: queries + positives' sums; phase 4: sorted-order partial sums of the negatives
+template <int MODEL, int GS, int NCH, int U>
+static int launch_dim_sorted_one(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st) {
+    const int eta1 = P.eta + 1;
+    if (phase == 3) {
+        const int gpb = KGE_DIM_THREADS / GS;
+        kge_dim_query_kernel<MODEL, GS, NCH><<<(unsigned)((P.n + gpb - 1) / gpb), KGE_DIM_THREADS, 0, st>>>(P, C, eta1);
+    } else {
+        const int64_t epb = (int64_t)(KGE_DIM_THREADS / GS) * U;  // entries per CTA
+        kge_dim_sorted_partial_kernel<MODEL, GS, NCH, U><<<(unsigned)((n_keys + epb - 1) / epb), KGE_DIM_THREADS, 0, st>>>(P, C, ks, n_keys, eta1);
+    }
+    KGE_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+template <int MODEL>
+static int launch_dim_sorted_model(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st) {
+    constexpr bool Cx = (MODEL == 3);
+    const int width = Cx ? P.k : P.K;
+    KGE_REQUIRE(width % 4 == 0 && P.K % 4 == 0, "kge_train (dimension-sharded): the local slice needs a multiple of 4 columns per half, got %d", width);
+    const int nvec = width / 4;
+    if (nvec <= 8) return launch_dim_sorted_one<MODEL, 8, 1, (Cx ? 2 : 4)>(phase, P, C, ks, n_keys, st);
+    if (nvec <= 16) return launch_dim_sorted_one<MODEL, 16, 1, (Cx ? 2 : 4)>(phase, P, C, ks, n_keys, st);
+    if (nvec <= 32) return launch_dim_sorted_one<MODEL, 32, 1, (Cx ? 2 : 4)>(phase, P, C, ks, n_keys, st);
+    if (nvec <= 64) return launch_dim_sorted_one<MODEL, 32, 2, (Cx ? 1 : 2)>(phase, P, C, ks, n_keys, st);
+    if (nvec <= 128) return launch_dim_sorted_one<MODEL, 32, 4, 1>(phase, P, C, ks, n_keys, st);
+    kge_set_error("kge_train (dimension-sharded): local slice of %d columns per half is too wide (max 512)", width);
+    return -1;
 }
 
 // group size / chunks per lane from the vectors per half of the local slice
@@ -403,6 +544,10 @@ static int launch_dim_model(int phase, const DimParams& P, cudaStream_t st) {
 }
 
 // one translation unit per model (parallel compilation): kge_dim_m{0,1,2,3}.cu
+int kge_launch_dim_sorted_m0(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
+int kge_launch_dim_sorted_m1(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
+int kge_launch_dim_sorted_m2(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
+int kge_launch_dim_sorted_m3(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
 int kge_launch_dim_m0(int phase, const DimParams& P, cudaStream_t st);
 int kge_launch_dim_m1(int phase, const DimParams& P, cudaStream_t st);
 int kge_launch_dim_m2(int phase, const DimParams& P, cudaStream_t st);

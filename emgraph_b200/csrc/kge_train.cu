@@ -1675,6 +1675,48 @@ extern "C" int kge_train_partial(kge_ctx* ctx, const kge_train_args* a, int64_t 
     return launch_dim(1, a, P, st);
 }
 
+// phase 1 of the whole batch with the entity rows streamed in sorted order (kge_dim.cuh); sums in the chunk-major layout
+extern "C" int kge_train_partial_sorted(kge_ctx* ctx, const kge_train_args* a, int n_chunks, float* sums, void* stream) {
+    KGE_REQUIRE(ctx != nullptr, "kge_train_partial_sorted: null ctx");
+    if (int rc = validate_train(a)) return rc;
+    if (a->n_pos == 0) return 0;
+    KGE_REQUIRE(n_chunks >= 1 && n_chunks <= a->n_pos, "kge_train_partial_sorted: bad chunk count %d", n_chunks);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t S = (int64_t)(3 + a->eta) * a->n_pos;
+    KGE_REQUIRE(S <= (int64_t)KGE_SLOT_MASK && (int64_t)(1 + a->eta) * a->n_pos < ((int64_t)1 << 32), "kge_train_partial_sorted: batch too large");
+    if (int rc = ensure_side_stream(ctx)) return rc;
+    ctx->dim_pipelined = (a->flags & KGE_F_PIPELINE) != 0 && pipeline_enabled();
+    if (ctx->dim_pipelined) {
+        if (int rc = pipeline_prologue(ctx, a, nullptr)) return rc;
+        KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_pro_emit[ctx->set_id], 0));
+    } else {
+        if (ctx->ks_in.reserve((size_t)S * 8)) return -2;
+        if (ctx->grad_rows.reserve((size_t)gbuf_floats(a->eta, a->n_pos, a->ent.K) * sizeof(float))) return -2;
+        KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_sorted, 0));
+        if (int rc = emit_impl(ctx, a, nullptr, ctx->ks_in.as<uint64_t>(), st, nullptr)) return rc;
+        KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, st));
+        KGE_CUDA_CHECK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        if (int rc = sort_impl(ctx, a, ctx->ks_in.as<uint64_t>(), S, ctx->side)) return rc;
+        KGE_CUDA_CHECK(cudaEventRecord(ctx->ev_sorted, ctx->side));
+    }
+    DimParams P;
+    if (int rc = dim_params(ctx, a, 0, a->n_pos, sums, P)) return rc;
+    DimChunks C;
+    C.base = (uint32_t)(a->n_pos / n_chunks);
+    C.extra = (uint32_t)(a->n_pos % n_chunks);
+    auto go = [&](int phase) -> int {
+        switch (a->model) {
+            case KGE_TRANSE_L1: return kge_launch_dim_sorted_m0(phase, P, C, ctx->ks_sorted.as<uint64_t>(), S, st);
+            case KGE_TRANSE_L2: return kge_launch_dim_sorted_m1(phase, P, C, ctx->ks_sorted.as<uint64_t>(), S, st);
+            case KGE_DISTMULT: return kge_launch_dim_sorted_m2(phase, P, C, ctx->ks_sorted.as<uint64_t>(), S, st);
+            default: return kge_launch_dim_sorted_m3(phase, P, C, ctx->ks_sorted.as<uint64_t>(), S, st);
+        }
+    };
+    if (int rc = go(3)) return rc;  // queries + positives: independent of the sort
+    KGE_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->dim_pipelined ? ctx->ev_pro_sorted[ctx->set_id] : ctx->ev_sorted, 0));
+    return go(4);
+}
+
 extern "C" int kge_train_backward(kge_ctx* ctx, const kge_train_args* a, int64_t i_begin, int64_t i_end, const float* sums, void* stream) {
     KGE_REQUIRE(ctx != nullptr, "kge_train_backward: null ctx");
     if (int rc = validate_train(a)) return rc;

@@ -385,7 +385,7 @@ class ShardedKGE:
 
     def __init__(self, model, k, eta, loss, optimizer, E, R, n_per_rank, *, lr=5e-4, margin=1.0, norm=1, seed=0,
                  init_ent=None, init_rel=None, device=None, chunks=2, alpha=0.5, non_linearity="linear", side="s,o",
-                 optimizer_params=None, pipeline=True, group=None, ent_slice=None, rel_slice=None):
+                 optimizer_params=None, pipeline=True, group=None, ent_slice=None, rel_slice=None, sorted_partial=None):
         self.group = group
         assert dist.is_initialized(), "init torch.distributed first"
         self.rank_id, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -420,6 +420,10 @@ class ShardedKGE:
         elif opt == 2:
             self.state = dict(ent_m=torch.zeros_like(self.ent), rel_m=torch.zeros_like(self.rel))
         self.chunks = int(chunks)
+        # phase 1 over the SORTED slot list (every entity row streamed once, in address order) instead of one random gather
+        # per scored triple: pays when the row slices are narrow (random 128-byte reads run at ~40 % of HBM's copy rate on
+        # B200) and the batch is dense in the table; None = decide from the slice width
+        self.sorted_partial = (self.Kc <= 64) if sorted_partial is None else bool(sorted_partial)
         self.sums_flat = torch.zeros((1 + self.eta) * self.n, dtype=torch.float32, device=dev)  # chunk c at (1+eta)*lo_c
         self.pos_all = torch.empty((self.n, 3), dtype=torch.int32, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -480,10 +484,15 @@ class ShardedKGE:
 
         mark("start")
         works = []
-        for c, (lo, hi) in enumerate(bounds):
-            eng.train_partial(a, sums[c], lo, hi)
-            mark("partial%d" % c)
-            works.append(dist.all_reduce(sums[c], group=self.group, async_op=True) if self.world > 1 else None)
+        if self.sorted_partial:
+            eng.train_partial_sorted(a, self.sums_flat, len(bounds))
+            mark("partial_sorted")
+            works = [dist.all_reduce(t, group=self.group, async_op=True) if self.world > 1 else None for t in sums]
+        else:
+            for c, (lo, hi) in enumerate(bounds):
+                eng.train_partial(a, sums[c], lo, hi)
+                mark("partial%d" % c)
+                works.append(dist.all_reduce(sums[c], group=self.group, async_op=True) if self.world > 1 else None)
         for c, (lo, hi) in enumerate(bounds):
             if works[c] is not None:
                 works[c].wait()

@@ -289,6 +289,14 @@ class Engine:
         check(self.lib.kge_train_partial(self._h, C.byref(a), i_begin, i_end, _ptr(sums), _stream()))
         self.launches += 1 + ((1 + self.launches_per_step(a.ent.rows + a.R) - 5) if i_begin == 0 else 0)
 
+    def train_partial_sorted(self, a: KgeTrainArgs, sums, n_chunks: int = 1):
+        """Phase 1 of the whole batch, entity rows streamed in sorted order; `sums` ((1+eta)*n_pos floats) holds the pieces of
+        n_chunks consecutive positive ranges back to back (include/kge_b200.h)."""
+        _chk_f32(sums, "sums")
+        assert sums.numel() >= (1 + a.eta) * a.n_pos
+        check(self.lib.kge_train_partial_sorted(self._h, C.byref(a), int(n_chunks), _ptr(sums), _stream()))
+        self.launches += 2 + (1 + self.launches_per_step(a.ent.rows + a.R) - 5)
+
     def train_backward(self, a: KgeTrainArgs, sums, i_begin: int = 0, i_end: int | None = None):
         _chk_f32(sums, "sums")
         i_end = a.n_pos if i_end is None else i_end

@@ -210,6 +210,12 @@ int kge_train_select(kge_ctx* ctx, const kge_train_args* a, const int32_t* keys_
  * a->ent.n_shards == 1, a->k = columns per half of the slice (a multiple of 4), a->k_model = the model's k.
  * Replaces the reference's host-paged "large graph" mode (models/EmbeddingModel.py:645-666, :1070-1097, :1251-1281). */
 int kge_train_partial(kge_ctx* ctx, const kge_train_args* a, int64_t i_begin, int64_t i_end, float* sums, void* stream);
+/* kge_train_partial for the whole batch at once with the entity rows streamed in SORTED order (each row once, in address
+ * order, instead of (3+eta) random 4*Kc-byte reads per positive).  `sums` takes the pieces of n_chunks consecutive positive
+ * ranges back to back -- piece c covers positives [lo_c, lo_c + nc_c) with nc_c = n_pos / n_chunks (+1 for the first
+ * n_pos % n_chunks pieces) and starts at float (1+eta)*lo_c, laid out as kge_train_partial lays out one range -- so that the
+ * caller can all-reduce piece c and hand it to kge_train_backward(lo_c, lo_c + nc_c) while later pieces are in flight. */
+int kge_train_partial_sorted(kge_ctx* ctx, const kge_train_args* a, int n_chunks, float* sums, void* stream);
 int kge_train_backward(kge_ctx* ctx, const kge_train_args* a, int64_t i_begin, int64_t i_end, const float* sums, void* stream);
 int kge_train_reduce(kge_ctx* ctx, const kge_train_args* a, void* stream);
 

@@ -119,6 +119,18 @@ class FakeEngine:
         sums[:out.size].copy_(torch.from_numpy(out))
         self.launches += 1
 
+    def train_partial_sorted(self, a, sums, n_chunks=1):
+        """kge_train_partial_sorted: every piece of the chunk-major layout, computed piece by piece (the order in which the
+        rows are read does not change the sums)."""
+        n, eta = a.pos.shape[0], a.eta
+        chunks = max(1, min(int(n_chunks), n))
+        base, extra = divmod(n, chunks)
+        lo = 0
+        for c in range(chunks):
+            hi = lo + base + (1 if c < extra else 0)
+            self.train_partial(a, sums[(1 + eta) * lo:(1 + eta) * hi], lo, hi)
+            lo = hi
+
     def train_backward(self, a, sums, i_begin=0, i_end=None):
         i_end = a.pos.shape[0] if i_end is None else i_end
         self._dim["totals"][(i_begin, i_end)] = sums.numpy()[:(1 + a.eta) * (i_end - i_begin)].copy()

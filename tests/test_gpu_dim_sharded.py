@@ -25,7 +25,7 @@ def _close(a, b, rtol=1e-5):
 
 
 def virtual_step(engine, model, k, W, loss, eta, ent, rel, pos, keep=None, repl=None, *, norm=1, opt="adam", lr=1e-3, margin=1.0,
-                 flags=0, state=None, step=1, chunks=1, nl=0, seed=0, alpha=0.5):
+                 flags=0, state=None, step=1, chunks=1, nl=0, seed=0, alpha=0.5, sorted_partial=False):
     """One optimisation step of a model split over W virtual ranks; returns merged tables / gradients / scores."""
     from emgraph_b200 import _lib
     from emgraph_b200 import distributed as D
@@ -49,13 +49,20 @@ def virtual_step(engine, model, k, W, loss, eta, ent, rel, pos, keep=None, repl=
                               ent=e, rel=rl, pos=pos_d, loss_out=out["loss"], flags=flags, margin=margin, alpha=alpha, lr=lr, step=step,
                               seed=seed, repl=repl_d, keep_subj=keep_d, dbg_scores=out["scores"], dbg_grad_ent=out["g_ent"],
                               dbg_grad_rel=out["g_rel"], non_linearity=nl, **st)
-        sums = [torch.zeros((1 + eta) * (hi - lo), device="cuda") for lo, hi in bounds]
-        ranks.append(dict(a=a, ent=e, rel=rl, st=st, out=out, sums=sums))
+        flat = torch.zeros((1 + eta) * n, device="cuda")
+        sums = [flat[(1 + eta) * lo:(1 + eta) * hi] for lo, hi in bounds]
+        ranks.append(dict(a=a, ent=e, rel=rl, st=st, out=out, sums=sums, flat=flat))
     # phase 1 on every rank, then the "all-reduce" (fixed rank order), then phase 2 + reduction rank by rank (the ctx-owned
     # corruption / key buffers hold the same values for every rank: same batch, seed and step)
+    def phase1(rk):
+        if sorted_partial:  # the whole batch at once, entity rows streamed in sorted order, same chunk-major layout
+            engine.train_partial_sorted(rk["a"], rk["flat"], len(bounds))
+        else:
+            for c, (lo, hi) in enumerate(bounds):
+                engine.train_partial(rk["a"], rk["sums"][c], lo, hi)
+
     for rk in ranks:
-        for c, (lo, hi) in enumerate(bounds):
-            engine.train_partial(rk["a"], rk["sums"][c], lo, hi)
+        phase1(rk)
     totals = []
     for c in range(len(bounds)):
         t = ranks[0]["sums"][c].clone()
@@ -63,8 +70,7 @@ def virtual_step(engine, model, k, W, loss, eta, ent, rel, pos, keep=None, repl=
             t += rk["sums"][c]
         totals.append(t)
     for rk in ranks:
-        for c, (lo, hi) in enumerate(bounds):
-            engine.train_partial(rk["a"], rk["sums"][c], lo, hi)  # re-establish this rank's step (emit + sort)
+        phase1(rk)  # re-establish this rank's step (emit + sort)
         for c, (lo, hi) in enumerate(bounds):
             engine.train_backward(rk["a"], totals[c], lo, hi)
         engine.train_reduce(rk["a"])
@@ -87,8 +93,9 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("sorted_partial", [False, True], ids=["gather", "sorted"])
 @pytest.mark.parametrize("model,loss,k,eta,W,norm", CASES)
-def test_dim_sharded_step_vs_oracle(engine, model, loss, k, eta, W, norm):
+def test_dim_sharded_step_vs_oracle(engine, model, loss, k, eta, W, norm, sorted_partial):
     """scores, loss, summed row gradients of the merged slices against the oracle on the whole model (supplied corruptions)."""
     from emgraph_b200 import _lib
     rng = np.random.default_rng(31)
@@ -102,7 +109,7 @@ def test_dim_sharded_step_vs_oracle(engine, model, loss, k, eta, W, norm):
     repl = rng.integers(0, E, n * eta).astype(np.int32)
     margin = 5.0 if model == "DistMult" else 1.0
     r = virtual_step(engine, model, k, W, loss, eta, ent, rel, pos, keep, repl, norm=norm, margin=margin, flags=_lib.F_NO_UPDATE,
-                     chunks=3 if W == 4 else 1)
+                     chunks=3 if W == 4 else 1, sorted_partial=sorted_partial)
     o = ko.train_step(model, k, loss, eta, ent, rel, pos, keep, repl, margin=margin, norm=norm, dtype=np.float64)
     _close(r["scores"][:n], o["scores_pos"])
     _close(r["scores"][n:], o["scores_neg"])
@@ -139,7 +146,8 @@ def test_dim_sharded_three_stateful_steps(engine, model, k, W, opt):
         pos[: n // 3, 0] = 7  # a hub entity: runs that span several chunks of the reduction
         keep = rng.integers(0, 2, n * eta).astype(np.uint8)
         repl = rng.integers(0, E, n * eta).astype(np.int32)
-        r = virtual_step(engine, model, k, W, "nll", eta, ent, rel, pos, keep, repl, opt=opt, lr=5e-3, state=st or None, step=step, chunks=2)
+        r = virtual_step(engine, model, k, W, "nll", eta, ent, rel, pos, keep, repl, opt=opt, lr=5e-3, state=st or None, step=step, chunks=2,
+                         sorted_partial=(W >= 4))
         o = ko.train_step(model, k, "nll", eta, e_o, r_o, pos, keep, repl, opt=opt, lr=5e-3, state=o_state, step=step)
         ent, rel = r["ent"], r["rel"]
         st = r.get("state", {})

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=1)
     ap.add_argument("--pipeline", type=int, default=0)
     ap.add_argument("--uniform", action="store_true")
+    ap.add_argument("--sorted", type=int, default=0, help="1: phase 1 over the sorted slot list")
     args = ap.parse_args()
     w = bench.WORKLOADS[args.workload]
     W = args.world
@@ -52,7 +53,8 @@ def main():
     st = dict(ent_m=torch.zeros_like(ent), ent_v=torch.zeros_like(ent), rel_m=torch.zeros_like(rel), rel_v=torch.zeros_like(rel))
     loss = torch.zeros(1, device=dev)
     bounds = D.chunk_bounds(n, args.chunks)
-    sums = [torch.zeros((1 + eta) * (hi - lo), device=dev) for lo, hi in bounds]
+    sums_flat = torch.zeros((1 + eta) * n, device=dev)
+    sums = [sums_flat[(1 + eta) * lo:(1 + eta) * hi] for lo, hi in bounds]
     flush = torch.empty(bench.L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
     kw = dict(model=model_id(w["model"]), loss=_lib.LOSS_IDS[w["loss"]], opt=0, k=kc, k_model=k, eta=eta, margin=w["margin"], lr=w["lr"], seed=0)
     names = ["emit+partial", "allreduce_standin", "backward", "reduce_apply"]
@@ -65,8 +67,11 @@ def main():
         flush.fill_(float(s))
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
-        for c, (lo, hi) in enumerate(bounds):
-            eng.train_partial(a, sums[c], lo, hi)
+        if args.sorted:
+            eng.train_partial_sorted(a, sums_flat, len(bounds))
+        else:
+            for c, (lo, hi) in enumerate(bounds):
+                eng.train_partial(a, sums[c], lo, hi)
         ev[1].record()
         for t in sums:
             t.mul_(float(W))  # stand-in for the sum over ranks (every rank would hold comparable partial sums)
@@ -82,7 +87,7 @@ def main():
                 acc[nm] += ev[i].elapsed_time(ev[i + 1])
             total += ev[0].elapsed_time(ev[4])
     steps = args.steps
-    out = {"workload": args.workload, "world": W, "global_batch": n, "Kc": Kc, "chunks": args.chunks, "pipeline": args.pipeline,
+    out = {"workload": args.workload, "world": W, "global_batch": n, "Kc": Kc, "chunks": args.chunks, "pipeline": args.pipeline, "sorted": args.sorted,
            "ms_per_step": total / steps, "phases_ms": {nm: v / steps for nm, v in acc.items()}, "loss": float(loss.item()),
            "triples_per_s_job": n * (1 + eta) / (total / steps * 1e-3)}
     print(json.dumps(out), flush=True)
