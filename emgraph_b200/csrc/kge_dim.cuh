@@ -394,7 +394,7 @@ __device__ __forceinline__ void dim_chunk_of(const DimChunks& C, uint32_t i, uin
 }
 
 template <int MODEL, int GS, int NCH>
-__global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_query_kernel(DimParams P, DimChunks C, int eta1) {
+__global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_query_kernel(DimParams P, DimChunks C, int eta1, uint2* __restrict__ pos_off) {
     using A = Algebra<MODEL, 4, NCH>;
     using R = typename A::R;
     const int lane = threadIdx.x & 31, lg = lane & (GS - 1);
@@ -421,13 +421,17 @@ __global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_query_kernel(DimParam
     if (lg == 0) {
         uint32_t lo, nc;
         dim_chunk_of(C, (uint32_t)i, lo, nc);
-        P.sums[(size_t)eta1 * lo + ((uint32_t)i - lo)] = sp;
+        const uint32_t o0 = (uint32_t)eta1 * lo + ((uint32_t)i - lo);
+        P.sums[o0] = sp;
+        // where the sums of this positive's negatives go: negative j at pos_off[i].x + (1 + j) * pos_off[i].y -- looked up
+        // by the sorted kernel (two cached loads instead of two integer divisions per sort entry)
+        pos_off[i] = make_uint2(o0, nc);
     }
 }
 
 template <int MODEL, int GS, int NCH, int U>
-__global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_sorted_partial_kernel(DimParams P, DimChunks C, const uint64_t* __restrict__ ks,
-                                                                                 int64_t n_keys, int eta1) {
+__global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_sorted_partial_kernel(DimParams P, const uint2* __restrict__ pos_off,
+                                                                                 const uint64_t* __restrict__ ks, int64_t n_keys) {
     using A = Algebra<MODEL, 4, NCH>;
     using R = typename A::R;
     const int lane = threadIdx.x & 31, lg = lane & (GS - 1);
@@ -463,9 +467,8 @@ __global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_sorted_partial_kernel
         const bool kept = (word & 0x80000000u) ? (word & 0x40000000u) != 0 : (is_neg ? P.keep[(size_t)j * n + i] != 0 : false);
         neg[u] = is_neg;
         if (is_neg) {
-            uint32_t lo, nc;
-            dim_chunk_of(C, i, lo, nc);
-            off[u] = (uint32_t)eta1 * lo + nc + j * nc + (i - lo);
+            const uint2 po = pos_off[i];
+            off[u] = po.x + (1u + j) * po.y;
             grow_load<GS>(r[u], P.ent + (size_t)key * K, lg, nvec, half);
             grow_load<GS>(Q[u], P.gbuf + (size_t)((kept ? 3u : 4u) * n + i) * K, lg, nvec, half);
         } else {
@@ -499,30 +502,32 @@ static int launch_dim_one(int phase, const DimParams& P, cudaStream_t st) {
 
 // phase 3: queries + positives' sums; phase 4: sorted-order partial sums of the negatives
 template <int MODEL, int GS, int NCH, int U>
-static int launch_dim_sorted_one(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st) {
+static int launch_dim_sorted_one(int phase, const DimParams& P, const DimChunks& C, uint2* pos_off, const uint64_t* ks, int64_t n_keys,
+                                 cudaStream_t st) {
     const int eta1 = P.eta + 1;
     if (phase == 3) {
         const int gpb = KGE_DIM_THREADS / GS;
-        kge_dim_query_kernel<MODEL, GS, NCH><<<(unsigned)((P.n + gpb - 1) / gpb), KGE_DIM_THREADS, 0, st>>>(P, C, eta1);
+        kge_dim_query_kernel<MODEL, GS, NCH><<<(unsigned)((P.n + gpb - 1) / gpb), KGE_DIM_THREADS, 0, st>>>(P, C, eta1, pos_off);
     } else {
         const int64_t epb = (int64_t)(KGE_DIM_THREADS / GS) * U;  // entries per CTA
-        kge_dim_sorted_partial_kernel<MODEL, GS, NCH, U><<<(unsigned)((n_keys + epb - 1) / epb), KGE_DIM_THREADS, 0, st>>>(P, C, ks, n_keys, eta1);
+        kge_dim_sorted_partial_kernel<MODEL, GS, NCH, U><<<(unsigned)((n_keys + epb - 1) / epb), KGE_DIM_THREADS, 0, st>>>(P, pos_off, ks, n_keys);
     }
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
 template <int MODEL>
-static int launch_dim_sorted_model(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st) {
+static int launch_dim_sorted_model(int phase, const DimParams& P, const DimChunks& C, uint2* pos_off, const uint64_t* ks, int64_t n_keys,
+                                   cudaStream_t st) {
     constexpr bool Cx = (MODEL == 3);
     const int width = Cx ? P.k : P.K;
     KGE_REQUIRE(width % 4 == 0 && P.K % 4 == 0, "kge_train (dimension-sharded): the local slice needs a multiple of 4 columns per half, got %d", width);
     const int nvec = width / 4;
-    if (nvec <= 8) return launch_dim_sorted_one<MODEL, 8, 1, (Cx ? 2 : 4)>(phase, P, C, ks, n_keys, st);
-    if (nvec <= 16) return launch_dim_sorted_one<MODEL, 16, 1, (Cx ? 2 : 4)>(phase, P, C, ks, n_keys, st);
-    if (nvec <= 32) return launch_dim_sorted_one<MODEL, 32, 1, (Cx ? 2 : 4)>(phase, P, C, ks, n_keys, st);
-    if (nvec <= 64) return launch_dim_sorted_one<MODEL, 32, 2, (Cx ? 1 : 2)>(phase, P, C, ks, n_keys, st);
-    if (nvec <= 128) return launch_dim_sorted_one<MODEL, 32, 4, 1>(phase, P, C, ks, n_keys, st);
+    if (nvec <= 8) return launch_dim_sorted_one<MODEL, 8, 1, (Cx ? 2 : 4)>(phase, P, C, pos_off, ks, n_keys, st);
+    if (nvec <= 16) return launch_dim_sorted_one<MODEL, 16, 1, (Cx ? 2 : 4)>(phase, P, C, pos_off, ks, n_keys, st);
+    if (nvec <= 32) return launch_dim_sorted_one<MODEL, 32, 1, (Cx ? 2 : 4)>(phase, P, C, pos_off, ks, n_keys, st);
+    if (nvec <= 64) return launch_dim_sorted_one<MODEL, 32, 2, (Cx ? 1 : 2)>(phase, P, C, pos_off, ks, n_keys, st);
+    if (nvec <= 128) return launch_dim_sorted_one<MODEL, 32, 4, 1>(phase, P, C, pos_off, ks, n_keys, st);
     kge_set_error("kge_train (dimension-sharded): local slice of %d columns per half is too wide (max 512)", width);
     return -1;
 }
@@ -544,10 +549,10 @@ static int launch_dim_model(int phase, const DimParams& P, cudaStream_t st) {
 }
 
 // one translation unit per model (parallel compilation): kge_dim_m{0,1,2,3}.cu
-int kge_launch_dim_sorted_m0(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
-int kge_launch_dim_sorted_m1(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
-int kge_launch_dim_sorted_m2(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
-int kge_launch_dim_sorted_m3(int phase, const DimParams& P, const DimChunks& C, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
+int kge_launch_dim_sorted_m0(int phase, const DimParams& P, const DimChunks& C, uint2* pos_off, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
+int kge_launch_dim_sorted_m1(int phase, const DimParams& P, const DimChunks& C, uint2* pos_off, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
+int kge_launch_dim_sorted_m2(int phase, const DimParams& P, const DimChunks& C, uint2* pos_off, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
+int kge_launch_dim_sorted_m3(int phase, const DimParams& P, const DimChunks& C, uint2* pos_off, const uint64_t* ks, int64_t n_keys, cudaStream_t st);
 int kge_launch_dim_m0(int phase, const DimParams& P, cudaStream_t st);
 int kge_launch_dim_m1(int phase, const DimParams& P, cudaStream_t st);
 int kge_launch_dim_m2(int phase, const DimParams& P, cudaStream_t st);

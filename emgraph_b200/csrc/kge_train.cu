@@ -1704,12 +1704,14 @@ extern "C" int kge_train_partial_sorted(kge_ctx* ctx, const kge_train_args* a, i
     DimChunks C;
     C.base = (uint32_t)(a->n_pos / n_chunks);
     C.extra = (uint32_t)(a->n_pos % n_chunks);
+    if (ctx->pos_off.reserve((size_t)a->n_pos * sizeof(uint2))) return -2;
+    uint2* po = ctx->pos_off.as<uint2>();
     auto go = [&](int phase) -> int {
         switch (a->model) {
-            case KGE_TRANSE_L1: return kge_launch_dim_sorted_m0(phase, P, C, ctx->ks_sorted.as<uint64_t>(), S, st);
-            case KGE_TRANSE_L2: return kge_launch_dim_sorted_m1(phase, P, C, ctx->ks_sorted.as<uint64_t>(), S, st);
-            case KGE_DISTMULT: return kge_launch_dim_sorted_m2(phase, P, C, ctx->ks_sorted.as<uint64_t>(), S, st);
-            default: return kge_launch_dim_sorted_m3(phase, P, C, ctx->ks_sorted.as<uint64_t>(), S, st);
+            case KGE_TRANSE_L1: return kge_launch_dim_sorted_m0(phase, P, C, po, ctx->ks_sorted.as<uint64_t>(), S, st);
+            case KGE_TRANSE_L2: return kge_launch_dim_sorted_m1(phase, P, C, po, ctx->ks_sorted.as<uint64_t>(), S, st);
+            case KGE_DISTMULT: return kge_launch_dim_sorted_m2(phase, P, C, po, ctx->ks_sorted.as<uint64_t>(), S, st);
+            default: return kge_launch_dim_sorted_m3(phase, P, C, po, ctx->ks_sorted.as<uint64_t>(), S, st);
         }
     };
     if (int rc = go(3)) return rc;  // queries + positives: independent of the sort
