@@ -236,12 +236,28 @@ static int launch_group_opt(const ApplyParams& P, cudaStream_t st) {
     constexpr int GPB = KGE_RAG_THREADS / GS;
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
     dim3 grid((unsigned)((n_chunks + GPB - 1) / GPB)), block(KGE_RAG_THREADS);
-    switch (P.opt) {
-        case KGE_OPT_ADAM: kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_ADAM><<<grid, block, 0, st>>>(P); break;
-        case KGE_OPT_ADAGRAD: kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_ADAGRAD><<<grid, block, 0, st>>>(P); break;
-        case KGE_OPT_MOMENTUM: kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_MOMENTUM><<<grid, block, 0, st>>>(P); break;
-        default: kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_SGD><<<grid, block, 0, st>>>(P); break;
+    // KGE_APPLY_MAXCTAS=m (A/B knob): at most m resident CTAs per SM (unused dynamic shared memory does the limiting), so that
+    // the sort of the NEXT step, which a pipelined caller runs beside this kernel, finds room on every SM
+    static long pad = -1;
+    if (pad < 0) {
+        const char* e = getenv("KGE_APPLY_MAXCTAS");
+        const int m = (e != nullptr && e[0] >= '1' && e[0] <= '9') ? (e[0] - '0') : 0;
+        pad = m > 0 ? (long)(233472 / m - 1024 - 12 * 1024) : 0;
     }
+    const size_t dsm = pad > 0 ? (size_t)pad : 0;
+    auto launch = [&](auto kern) -> int {
+        if (dsm > 36 * 1024) KGE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+        kern<<<grid, block, dsm, st>>>(P);
+        return 0;
+    };
+    int rc;
+    switch (P.opt) {
+        case KGE_OPT_ADAM: rc = launch(kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_ADAM>); break;
+        case KGE_OPT_ADAGRAD: rc = launch(kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_ADAGRAD>); break;
+        case KGE_OPT_MOMENTUM: rc = launch(kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_MOMENTUM>); break;
+        default: rc = launch(kge_reduce_apply_group_kernel<GS, TMODE, KGE_OPT_SGD>); break;
+    }
+    if (rc) return rc;
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -489,13 +489,35 @@ __global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_sorted_partial_kernel
 }
 
 // ---------------------------------------------------------------------------------------------- launch
+// KGE_DIM_MAXCTAS=m (A/B knob): at most m resident CTAs of a phase kernel per SM -- an unused dynamic shared-memory
+// request does the limiting -- so that the CTAs of the radix sort, which runs beside these kernels on the side stream, find
+// registers and shared memory on every SM instead of waiting for whole waves of the phase kernel to drain.  0 = no limit.
+static inline size_t dim_pad_smem() {
+    static long v = -1;
+    if (v < 0) {
+        const char* e = getenv("KGE_DIM_MAXCTAS");
+        const int m = (e != nullptr && e[0] >= '1' && e[0] <= '8') ? (e[0] - '0') : 0;
+        v = m > 0 ? (long)(233472 / m - 1024) : 0;
+    }
+    return (size_t)v;
+}
+
 template <int MODEL, int GS, int NCH, int U>
 static int launch_dim_one(int phase, const DimParams& P, cudaStream_t st) {
     const int64_t nc = P.i1 - P.i0;
     const int gpb = KGE_DIM_THREADS / GS;
     dim3 grid((unsigned)((nc + gpb - 1) / gpb)), block(KGE_DIM_THREADS);
-    if (phase == 1) kge_dim_partial_kernel<MODEL, GS, NCH, U><<<grid, block, 0, st>>>(P);
-    else kge_dim_backward_kernel<MODEL, GS, NCH, U><<<grid, block, 0, st>>>(P);
+    const size_t pad = dim_pad_smem();
+    if (pad > 48 * 1024) {
+        static bool set = false;
+        if (!set) {
+            KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_dim_partial_kernel<MODEL, GS, NCH, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+            KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_dim_backward_kernel<MODEL, GS, NCH, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+            set = true;
+        }
+    }
+    if (phase == 1) kge_dim_partial_kernel<MODEL, GS, NCH, U><<<grid, block, pad, st>>>(P);
+    else kge_dim_backward_kernel<MODEL, GS, NCH, U><<<grid, block, pad, st>>>(P);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

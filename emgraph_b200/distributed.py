@@ -421,9 +421,10 @@ class ShardedKGE:
             self.state = dict(ent_m=torch.zeros_like(self.ent), rel_m=torch.zeros_like(self.rel))
         self.chunks = int(chunks)
         # phase 1 over the SORTED slot list (every entity row streamed once, in address order) instead of one random gather
-        # per scored triple: pays when the row slices are narrow (random 128-byte reads run at ~40 % of HBM's copy rate on
-        # B200) and the batch is dense in the table; None = decide from the slice width
-        self.sorted_partial = (self.Kc <= 64) if sorted_partial is None else bool(sorted_partial)
+        # per scored triple (kge_train_partial_sorted): an alternative for narrow slices and batches dense in the table.
+        # Measured on B200 (profiles/r02_summary.md): at cfg5 / 8 ranks the sorted kernel takes 250 us against 198 us for the
+        # random gather -- the query gather then misses L2 half of the time -- so it is OFF unless asked for.
+        self.sorted_partial = False if sorted_partial is None else bool(sorted_partial)
         self.sums_flat = torch.zeros((1 + self.eta) * self.n, dtype=torch.float32, device=dev)  # chunk c at (1+eta)*lo_c
         self.pos_all = torch.empty((self.n, 3), dtype=torch.int32, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
