@@ -860,7 +860,10 @@ def multi_gpu_main(args, w, rank, world):
     import torch.distributed as dist
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # NCCL's kernels on a high-priority stream: the all-reduce of one piece of the partial scores must get SM slots while the
+    # phase kernel of the next piece is filling the machine
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     dev = torch.device("cuda", local)
     steps, warmup = args.steps, args.warmup
     do_rank = not args.no_rank

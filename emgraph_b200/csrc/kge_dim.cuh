@@ -109,9 +109,17 @@ __device__ __forceinline__ void dim_prefetch_row(const float* row, int K, int lg
     for (int off = lg_rot * 32; off < K; off += GS * 32) dim_prefetch_l2(row + off);
 }
 
+// resident CTAs the compiler is asked to allow (register cap): the row registers grow with NCH and the complex halves
+template <int MODEL, int NCH>
+struct DimOcc {
+    static constexpr int regs = NCH * 4 * (MODEL == 3 ? 2 : 1);
+    static constexpr int bwd = regs <= 4 ? 4 : (regs <= 8 ? 3 : (regs <= 16 ? 2 : 1));
+    static constexpr int fwd = regs <= 4 ? 6 : (regs <= 8 ? 5 : (regs <= 16 ? 3 : 2));
+};
+
 // ---------------------------------------------------------------------------------------------- phase 1
 template <int MODEL, int GS, int NCH, int U>
-__global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_partial_kernel(DimParams P) {
+__global__ void __launch_bounds__(KGE_DIM_THREADS, (DimOcc<MODEL, NCH>::fwd)) kge_dim_partial_kernel(DimParams P) {
     using A = Algebra<MODEL, 4, NCH>;
     using R = typename A::R;
     static_assert(U <= GS, "the lanes of a group fetch the ids of one round of U negatives");
@@ -176,14 +184,6 @@ __global__ void __launch_bounds__(KGE_DIM_THREADS) kge_dim_partial_kernel(DimPar
 }
 
 // ---------------------------------------------------------------------------------------------- phase 2
-// resident CTAs the compiler is asked to allow (register cap): the row registers grow with NCH and the complex halves
-template <int MODEL, int NCH>
-struct DimOcc {
-    static constexpr int regs = NCH * 4 * (MODEL == 3 ? 2 : 1);
-    static constexpr int bwd = regs <= 4 ? 4 : (regs <= 8 ? 3 : (regs <= 16 ? 2 : 1));
-    static constexpr int fwd = regs <= 8 ? 5 : (regs <= 16 ? 3 : 2);
-};
-
 template <int MODEL, int GS, int NCH, int U>
 __global__ void __launch_bounds__(KGE_DIM_THREADS, (DimOcc<MODEL, NCH>::bwd)) kge_dim_backward_kernel(DimParams P) {
     using A = Algebra<MODEL, 4, NCH>;

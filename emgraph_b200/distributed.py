@@ -622,7 +622,8 @@ def _spawn_worker(rank, world, port, cls_name, hyper, resume, Xi_path, E, R, out
     os.environ["MASTER_PORT"] = str(port)
     if backend == "nccl":
         torch.cuda.set_device(rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                                pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True))
     else:
         dist.init_process_group(backend, rank=rank, world_size=world)
     try:
