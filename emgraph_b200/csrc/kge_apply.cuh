@@ -34,6 +34,7 @@ struct ApplyParams {
     int32_t* span_list;    // chunk ids that start a run crossing chunk borders (unordered)
     int32_t* hub_list;     // the subset whose run covers more than KGE_SPAN_WARP_MAX chunks
     int32_t* span_count;   // [2]: {#span heads, #hubs}, zeroed before the reduce kernel
+    int span_use_hubs;     // 1: kge_span_warp_kernel runs first and leaves only hub_list to kge_span_apply_kernel
     float* dbg_grad_ent;
     float* dbg_grad_rel;
     // LP regulariser (regularizers/lp.py:81-113): lambda * sum |w|^p over the WHOLE tables, so every row has

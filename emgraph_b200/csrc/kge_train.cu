@@ -556,13 +556,15 @@ __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(App
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int K = P.ent.K;
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
-    const int n_heads = P.span_count[0];
+    // with the warp-per-run pass in front (dense batches) only the hubs it set aside are left for the CTAs
+    const int n_heads = P.span_use_hubs ? P.span_count[1] : P.span_count[0];
+    const int32_t* heads_list = P.span_use_hubs ? P.hub_list : P.span_list;
     const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
     const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
     const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
     const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
     for (int h = blockIdx.x; h < n_heads; h += gridDim.x) {
-        const int64_t w = P.span_list[h];
+        const int64_t w = heads_list[h];
         const int32_t key = (int32_t)(P.ks[w * KGE_CH + KGE_CH - 1] >> 32);
         const RowPtrs r = resolve_row(P, key);
         if (threadIdx.x == 0) mark_touched(P, key);
@@ -634,6 +636,70 @@ __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(App
             }
         }
         __syncthreads();
+    }
+}
+
+// Level 2 for DENSE batches (many more slots than rows: every row's run crosses chunk borders, so there are thousands of
+// span heads, each with a handful of partial rows): one WARP per run instead of one 1024-thread CTA.  The warp adds the
+// run's partial rows in chunk order (fixed order => reproducible) and applies the optimizer; runs with more than
+// KGE_SPAN_WARP_MAX partial rows (the hubs) are put on hub_list for kge_span_apply_kernel.
+#define KGE_SPAN_WARP_MAX 64
+template <int V>
+__global__ void __launch_bounds__(256) kge_span_warp_kernel(ApplyParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int K = P.ent.K;
+    const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
+    const int n_heads = P.span_count[0];
+    const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
+    const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
+    const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
+    const bool need_v = !no_update && !reset && P.opt == KGE_OPT_ADAM;
+    for (int64_t h = warp; h < n_heads; h += nwarps) {
+        const int64_t w = P.span_list[h];
+        const int32_t key = (int32_t)(P.ks[w * KGE_CH + KGE_CH - 1] >> 32);
+        const int64_t last = span_last_chunk(P, w, key, n_chunks, lane);
+        const int64_t n_ent = last - w + 1;
+        if (n_ent > KGE_SPAN_WARP_MAX) {
+            if (lane == 0) P.hub_list[atomicAdd(P.span_count + 1, 1)] = (int32_t)w;
+            continue;
+        }
+        const RowPtrs r = resolve_row(P, key);
+        if (lane == 0) mark_touched(P, key);
+        float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
+        for (int c0 = lane * V; c0 < K; c0 += 32 * V) {
+            float g[V], rc[V], mv[V], vv[V];
+#pragma unroll
+            for (int x = 0; x < V; ++x) g[x] = mv[x] = vv[x] = 0.f;
+            ld_vec<V>(rc, r.w + c0);
+            if (need_m) ld_vec<V>(mv, r.m + c0);
+            if (need_v) ld_vec<V>(vv, r.v + c0);
+            int64_t e = 0;
+            for (; e + 2 <= n_ent; e += 2) {
+                float t0[V], t1[V];
+                ld_vec<V>(t0, span_entry(P, w, e, K) + c0);
+                ld_vec<V>(t1, span_entry(P, w, e + 1, K) + c0);
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[x] += t0[x];
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[x] += t1[x];
+            }
+            if (e < n_ent) {
+                float t0[V];
+                ld_vec<V>(t0, span_entry(P, w, e, K) + c0);
+#pragma unroll
+                for (int x = 0; x < V; ++x) g[x] += t0[x];
+            }
+            reg_add<V>(P, r.is_rel, g, rc);
+            if (dbg != nullptr) st_vec<V>(dbg + (size_t)r.row * K + c0, g);
+            if (!no_update) {
+                opt_math<V>(P, reset, g, rc, mv, vv);
+                if (r.m && P.opt != KGE_OPT_SGD) st_vec<V>(r.m + c0, mv);
+                if (r.v && P.opt == KGE_OPT_ADAM) st_vec<V>(r.v + c0, vv);
+                st_vec<V>(r.w + c0, rc);
+            }
+        }
     }
 }
 
@@ -1021,6 +1087,10 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
     else kge_reduce_apply_kernel<V, 2, NCA><<<grid, block, 0, st>>>(P);
     KGE_CUDA_CHECK(cudaGetLastError());
     if (mid != nullptr) KGE_CUDA_CHECK(cudaEventRecord(mid, st));
+    if (P.span_use_hubs) {  // dense batch: a warp per run first, the CTAs take the hubs it sets aside
+        kge_span_warp_kernel<V><<<sm_count * 8, 256, 0, st>>>(P);
+        KGE_CUDA_CHECK(cudaGetLastError());
+    }
     return span_warps(P.ent.K) == 32 ? launch_span<V, 32>(P, sm_count, st) : launch_span<V, 8>(P, sm_count, st);
 }
 
@@ -1108,6 +1178,9 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
         P.span_list = ctx->span_head.as<int32_t>() + 2;
         P.hub_list = P.span_list + n_chunks;
     }
+    // dense batch (on average >= 8 slots per table row): most runs cross chunk borders -> thousands of short spans
+    P.span_use_hubs = (n_items >= 8 * (E + a->R)) ? 1 : 0;
+    if (const char* e = getenv("KGE_SPAN_WARP")) P.span_use_hubs = (e[0] == '1') ? 1 : 0;
     P.dbg_grad_ent = a->dbg_grad_ent;
     P.dbg_grad_rel = a->dbg_grad_rel;
     P.reg_p = a->reg_p;

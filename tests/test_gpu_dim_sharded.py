@@ -207,3 +207,30 @@ def test_group_reduction_equals_warp_reduction(engine, K, monkeypatch):
     big = np.abs(o["grad_ent"]) > 1e-3
     np.testing.assert_allclose(r["ent"][big], o["ent_new"][big], rtol=1e-5, atol=1e-6)
     np.testing.assert_array_equal(r["ent"][~o["touched_ent"]], ent[~o["touched_ent"]])
+
+
+@pytest.mark.parametrize("K,opt", [(32, "adam"), (56, "adagrad"), (200, "adam")])
+def test_dense_batch_spans_warp_per_run_and_hubs(engine, K, opt):
+    """Many more slots than rows (the regime of a small table on many GPUs): nearly every run crosses chunk borders.  The
+    warp-per-run span pass finishes the short spans, a hub entity with > 64 chunks of slots goes through hub_list to the
+    CTA kernel; gradients and updated rows against the oracle."""
+    rng = np.random.default_rng(100 + K)
+    model, E, R, eta, n = "DistMult", 60, 3, 4, 3000
+    ent = (rng.normal(size=(E, K)) * 0.3).astype(np.float32)
+    rel = (rng.normal(size=(R, K)) * 0.3).astype(np.float32)
+    pos = np.stack([rng.integers(0, E, n), rng.integers(0, R, n), rng.integers(0, E, n)], 1).astype(np.int32)
+    pos[:1500, 0] = 5  # 1500+ slots of one key: ~100 chunks
+    keep = rng.integers(0, 2, n * eta).astype(np.uint8)
+    repl = rng.integers(0, E, n * eta).astype(np.int32)
+    if opt == "adam":
+        st = dict(ent_m=np.zeros_like(ent), ent_v=np.zeros_like(ent), rel_m=np.zeros_like(rel), rel_v=np.zeros_like(rel))
+        o_state = ((np.zeros_like(ent), np.zeros_like(ent)), (np.zeros_like(rel), np.zeros_like(rel)))
+    else:
+        st = dict(ent_m=np.full_like(ent, 0.1), rel_m=np.full_like(rel, 0.1))
+        o_state = ((np.full_like(ent, 0.1),), (np.full_like(rel, 0.1),))
+    r = virtual_step(engine, model, K, 1, "nll", eta, ent, rel, pos, keep, repl, opt=opt, lr=1e-2, state=st, step=1)
+    o = ko.train_step(model, K, "nll", eta, ent, rel, pos, keep, repl, opt=opt, lr=1e-2, step=1, state=o_state)
+    _close(r["g_ent"], o["grad_ent"], rtol=2e-5)
+    _close(r["g_rel"], o["grad_rel"], rtol=2e-5)
+    big = np.abs(o["grad_ent"]) > 1e-3
+    np.testing.assert_allclose(r["ent"][big], o["ent_new"][big], rtol=1e-5, atol=1e-6)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, session K (1 GPU): higher occupancy targets (partial 6 CTAs, group reduction 10 CTAs)
-O=gpurun_out; mkdir -p $O; T=r2k
+O=gpurun_out; mkdir -p $O; T=r2l
 ( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 ) > $O/${T}_pytest_all.log
 run() { name=$1; shift; env "$@" timeout 300 python tools/dim_probe.py --workload $WL --world $W --steps 15 $EXTRA > $O/${T}_probe_$name.json 2> $O/${T}_probe_$name.err; }
 WL=cfg5; W=8; EXTRA=""; run w8 X=1
