@@ -469,7 +469,7 @@ class ShardedKGE:
         n = pos_all.shape[0]
         assert 0 < n <= self.n, "global batch of %d positives; this model was sized for %d" % (n, self.n)
         # small batches: the all-reduce payload is a few hundred KB and latency-bound -- cutting it up only adds launches
-        bounds = chunk_bounds(n, self.chunks if n * (1 + self.eta) * 4 >= (2 << 20) else 1)
+        bounds = chunk_bounds(n, self.chunks if n * (1 + self.eta) * 4 >= (256 << 10) else 1)
         sums = [self.sums_flat[(1 + self.eta) * lo:(1 + self.eta) * hi] for lo, hi in bounds]
         self.step += 1
         # the side-stream prologue may only read batches that were resident before the previous step was submitted
