@@ -125,8 +125,10 @@ def batch_positives(w):
 
 
 def make_dataset(w, need_train, with_test, zipf=True):
-    """(X, test): the first min(N, need_train) synthetic triples of the shape + T test triples sampled from them."""
-    n = w["N"] if with_test and w["N"] <= 2_000_000 else min(w["N"], max(need_train, w["T"] * 8 if with_test else 0))
+    """(X, test): synthetic triples of the shape + T test triples sampled from them.  The size does NOT depend on the number
+    of GPUs or steps (the whole set up to 4 M triples, batches wrap around), so that the test set, the filter and with them
+    the rank_parity digest are the same at every N."""
+    n = min(w["N"], 4_000_000) if with_test else min(w["N"], need_train)
     X = synth_triples(w["E"], w["R"], n, seed=0, zipf=zipf)
     test = None
     if with_test:

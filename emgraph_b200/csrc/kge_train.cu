@@ -122,11 +122,16 @@ bool kge_apply_group_ok(const ApplyParams& P);
 // and the span kernels.  Every chunk evaluates the same predicate from the sorted keys alone:
 //   head side : the run is long  <=>  the first key of chunk w+2 still equals the run's key
 //   tail side : the run's head lies in chunk w-1  <=>  the last key of chunk w-2 differs
-template <int V, int TMODE, int NCA>
+// CS > 1: CS warps share a chunk, each owning a contiguous 1/CS of the columns (same keys, same decisions, half the
+// registers): a batch that is only a few waves of warps deep -- cfg3: 6 100 chunks -- is a chain of ~10 dependent memory
+// round trips per warp, and twice the resident warps is what shortens it.
+template <int V, int TMODE, int NCA, int CS>
 __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(ApplyParams P) {
     __shared__ SlotMeta meta[KGE_RA_WARPS][2 * KGE_CH];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t w = (int64_t)blockIdx.x * KGE_RA_WARPS + wib;
+    const int64_t wg = (int64_t)blockIdx.x * KGE_RA_WARPS + wib;
+    const int64_t w = wg / CS;
+    const int part_id = (int)(wg - w * CS);  // which 1/CS of the columns this warp owns
     const int64_t b0 = w * KGE_CH;
     if (b0 >= P.n_keys) return;
     const int cnt = (int)min((int64_t)KGE_CH, P.n_keys - b0);
@@ -190,19 +195,22 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
             b = cnt + ext;  // the run ends inside the next chunk: finish it here
             open_end = false;
         }
-        if (!open_start && open_end && lane == 0) P.span_list[atomicAdd(P.span_count, 1)] = (int32_t)w;
+        if (!open_start && open_end && lane == 0 && part_id == 0) P.span_list[atomicAdd(P.span_count, 1)] = (int32_t)w;
         const bool complete = !open_start && !open_end;
-        if (complete && lane == 0) mark_touched(P, skey);
+        if (complete && lane == 0 && part_id == 0) mark_touched(P, skey);
         float* part = P.partial + ((size_t)(2 * w + (open_start ? 0 : 1))) * K;
         float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
         if constexpr (NCA > 0) {
-            // lanes past the end of the row read a clamped (valid, duplicate) vector and never store:
-            // no divergence inside the load/accumulate loops
+            // lanes past the end of the row (of this warp's share of it) read a clamped (valid, duplicate) vector and
+            // never store: no divergence inside the load/accumulate loops
             float g[NCA][V], rc[NCA][V], mv[NCA][V], vv[NCA][V];
             int cc[NCA];
+            const int nvec_row = K / V;
+            const int cps = (nvec_row + CS - 1) / CS;                  // vectors per column share
+            const int v_lo = part_id * cps, v_hi = min(v_lo + cps, nvec_row);  // this warp's vectors [v_lo, v_hi)
 #pragma unroll
             for (int i = 0; i < NCA; ++i) {
-                cc[i] = min((lane + 32 * i) * V, K - V);
+                cc[i] = min(v_lo + lane + 32 * i, v_hi - 1) * V;
 #pragma unroll
                 for (int x = 0; x < V; ++x) g[i][x] = rc[i][x] = mv[i][x] = vv[i][x] = 0.f;
             }
@@ -241,8 +249,9 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
             }
 #pragma unroll
             for (int i = 0; i < NCA; ++i) {
-                const int c0 = (lane + 32 * i) * V;
-                if (c0 >= K) continue;
+                const int vi = v_lo + lane + 32 * i;
+                const int c0 = vi * V;
+                if (vi >= v_hi) continue;
                 if (!complete) {
                     st_vec<V>(part + c0, g[i]);
                     continue;
@@ -256,6 +265,7 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_kernel(App
                 st_vec<V>(r.w + c0, rc[i]);
             }
         } else {
+            static_assert(NCA > 0 || CS == 1, "the generic column loop is not split");
             for (int c0 = lane * V; c0 < K; c0 += 32 * V) {
                 float g[V], rc[V], mv[V], vv[V];
 #pragma unroll
@@ -1081,10 +1091,28 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
         if (grouped)
             if (int rc = kge_launch_apply_group(P, tmode, st)) return rc;
     }
+    // a shallow grid (a few waves of warps) is latency-bound: two warps per chunk, half the columns each.  KGE_APPLY_SPLIT=0/1
+    // forces it off / on (A/B)
+    bool split = false;
+    if constexpr (V == 4 && NCA >= 2) {
+        static int force = -2;
+        if (force == -2) {
+            const char* e = getenv("KGE_APPLY_SPLIT");
+            force = e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
+        }
+        split = force >= 0 ? force != 0 : n_chunks < (int64_t)sm_count * 16 * 8;
+    }
     if (staged || grouped) {
-    } else if (tmode == 0) kge_reduce_apply_kernel<V, 0, NCA><<<grid, block, 0, st>>>(P);
-    else if (tmode == 1) kge_reduce_apply_kernel<V, 1, NCA><<<grid, block, 0, st>>>(P);
-    else kge_reduce_apply_kernel<V, 2, NCA><<<grid, block, 0, st>>>(P);
+    } else if (split) {
+        if constexpr (V == 4 && NCA >= 2) {
+            dim3 grid2((unsigned)((2 * n_chunks + KGE_RA_WARPS - 1) / KGE_RA_WARPS));
+            if (tmode == 0) kge_reduce_apply_kernel<V, 0, NCA / 2, 2><<<grid2, block, 0, st>>>(P);
+            else if (tmode == 1) kge_reduce_apply_kernel<V, 1, NCA / 2, 2><<<grid2, block, 0, st>>>(P);
+            else kge_reduce_apply_kernel<V, 2, NCA / 2, 2><<<grid2, block, 0, st>>>(P);
+        }
+    } else if (tmode == 0) kge_reduce_apply_kernel<V, 0, NCA, 1><<<grid, block, 0, st>>>(P);
+    else if (tmode == 1) kge_reduce_apply_kernel<V, 1, NCA, 1><<<grid, block, 0, st>>>(P);
+    else kge_reduce_apply_kernel<V, 2, NCA, 1><<<grid, block, 0, st>>>(P);
     KGE_CUDA_CHECK(cudaGetLastError());
     if (mid != nullptr) KGE_CUDA_CHECK(cudaEventRecord(mid, st));
     if (P.span_use_hubs) {  // dense batch: a warp per run first, the CTAs take the hubs it sets aside
