@@ -80,6 +80,7 @@ SYMBOLS = {
     "kge_train_partial_sorted": (_I, [_P, C.POINTER(KgeTrainArgs), _I, _P, _P]),
     "kge_train_backward": (_I, [_P, C.POINTER(KgeTrainArgs), _L, _L, _P, _P]),
     "kge_train_reduce": (_I, [_P, C.POINTER(KgeTrainArgs), _P]),
+    "kge_allreduce_p2p": (_I, [_P, C.POINTER(KgeTable), C.POINTER(KgeTable), C.POINTER(KgeTable), _I, _L, _L, C.c_uint32, _P]),
     "kge_train_step_host": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P, _P]),
     "kge_train_step_host_async": (_I, [_P, C.POINTER(KgeTrainArgs), _P, _P, _P, C.POINTER(_I)]),
     "kge_train_host_wait": (_I, [_P, _I]),

@@ -83,7 +83,7 @@ struct kge_ctx {
     int sm_count = 148;
     // training workspace
     KgeBuf sort_tmp;
-    KgeBuf loss_scr, pos_off;
+    KgeBuf loss_scr, pos_off, p2p_counter;
     KgeBuf repl, keep, grad_rows, loss_part, neg_scores, partial, span_head, reg_partial, touched;
     KgeBuf ks_in, ks_sel, ks_sorted, sel_flags, sel_count;
     // second set of the per-step corruption / sort-key buffers {repl, keep, ks_in, ks_sorted}: a pipelined step

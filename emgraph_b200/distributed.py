@@ -16,6 +16,7 @@ Replaces the reference's host-paged "large graph" mode (models/EmbeddingModel.py
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -385,7 +386,8 @@ class ShardedKGE:
 
     def __init__(self, model, k, eta, loss, optimizer, E, R, n_per_rank, *, lr=5e-4, margin=1.0, norm=1, seed=0,
                  init_ent=None, init_rel=None, device=None, chunks=2, alpha=0.5, non_linearity="linear", side="s,o",
-                 optimizer_params=None, pipeline=True, group=None, ent_slice=None, rel_slice=None, sorted_partial=None):
+                 optimizer_params=None, pipeline=True, group=None, ent_slice=None, rel_slice=None, sorted_partial=None,
+                 p2p_allreduce=None):
         self.group = group
         assert dist.is_initialized(), "init torch.distributed first"
         self.rank_id, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -425,7 +427,28 @@ class ShardedKGE:
         # Measured on B200 (profiles/r02_summary.md): at cfg5 / 8 ranks the sorted kernel takes 250 us against 198 us for the
         # random gather -- the query gather then misses L2 half of the time -- so it is OFF unless asked for.
         self.sorted_partial = False if sorted_partial is None else bool(sorted_partial)
-        self.sums_flat = torch.zeros((1 + self.eta) * self.n, dtype=torch.float32, device=dev)  # chunk c at (1+eta)*lo_c
+        n_sums = ((1 + self.eta) * self.n + 7) // 4 * 4
+        # the sum over the ranks: by default the library's own all-reduce over peer memory (kge_allreduce_p2p: P2P loads and
+        # stores through CUDA-IPC mappings, flags in peer memory) when the ranks are CUDA devices of one node; NCCL otherwise
+        # (p2p_allreduce=False, KGE_P2P_ALLREDUCE=0, or a CPU process group in the tests)
+        if p2p_allreduce is None:
+            p2p_allreduce = os.environ.get("KGE_P2P_ALLREDUCE", "1")[:1] != "0"
+        self.p2p = bool(p2p_allreduce) and self.world > 1 and dev.type == "cuda" and hasattr(eng, "allreduce_p2p")
+        if self.p2p:
+            self._sums_pb = PeerBuffer(eng, (n_sums,))
+            self._tot_pb = PeerBuffer(eng, (n_sums,))
+            self._flag_pb = PeerBuffer(eng, (64,), dtype=torch.int32)
+            for b in (self._sums_pb, self._tot_pb, self._flag_pb):
+                b.tensor.zero_()
+            torch.cuda.synchronize(dev)
+            exchange_peers(eng, [self._sums_pb, self._tot_pb, self._flag_pb], self.rank_id, self.world)
+            self.sums_flat, self.totals_flat = self._sums_pb.tensor, self._tot_pb.tensor
+            self._p2p_tables = tuple(make_table(b.peers, rows=n_sums * self.world, rows_per_shard=n_sums, K=1)
+                                     for b in (self._sums_pb, self._tot_pb, self._flag_pb))
+            self._p2p_seq = 0
+        else:
+            self.sums_flat = torch.zeros(n_sums, dtype=torch.float32, device=dev)  # chunk c at (1+eta)*lo_c
+            self.totals_flat = self.sums_flat  # NCCL reduces in place
         self.pos_all = torch.empty((self.n, 3), dtype=torch.int32, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step = 0
@@ -470,7 +493,9 @@ class ShardedKGE:
         assert 0 < n <= self.n, "global batch of %d positives; this model was sized for %d" % (n, self.n)
         # small batches: the all-reduce payload is a few hundred KB and latency-bound -- cutting it up only adds launches
         bounds = chunk_bounds(n, self.chunks if n * (1 + self.eta) * 4 >= (256 << 10) else 1)
-        sums = [self.sums_flat[(1 + self.eta) * lo:(1 + self.eta) * hi] for lo, hi in bounds]
+        e1 = 1 + self.eta
+        sums = [self.sums_flat[e1 * lo:e1 * hi] for lo, hi in bounds]
+        totals = [self.totals_flat[e1 * lo:e1 * hi] for lo, hi in bounds]
         self.step += 1
         # the side-stream prologue may only read batches that were resident before the previous step was submitted
         pipe = self.pipeline and pos_is_global and repl is None and keep_subj is None
@@ -484,21 +509,37 @@ class ShardedKGE:
                 marks.append((name, ev))
 
         mark("start")
+        def reduce_piece(c):
+            """sum of piece c over the ranks: in-stream over peer memory, or an asynchronous NCCL all-reduce"""
+            if self.world == 1:
+                return None
+            if self.p2p:
+                lo, hi = bounds[c]
+                off = e1 * lo // 4 * 4  # the kernel works on 16-byte vectors: the range is rounded outwards (the few
+                end = (e1 * hi + 3) // 4 * 4  # neighbouring floats it also sums are rewritten by their own piece)
+                self._p2p_seq += 1
+                eng.allreduce_p2p(*self._p2p_tables, self.rank_id, off, end - off, self._p2p_seq)
+                return None
+            return dist.all_reduce(sums[c], group=self.group, async_op=True)
+
         works = []
         if self.sorted_partial:
             eng.train_partial_sorted(a, self.sums_flat, len(bounds))
             mark("partial_sorted")
-            works = [dist.all_reduce(t, group=self.group, async_op=True) if self.world > 1 else None for t in sums]
+            works = [reduce_piece(c) for c in range(len(bounds))]
         else:
             for c, (lo, hi) in enumerate(bounds):
                 eng.train_partial(a, sums[c], lo, hi)
                 mark("partial%d" % c)
-                works.append(dist.all_reduce(sums[c], group=self.group, async_op=True) if self.world > 1 else None)
+                works.append(reduce_piece(c))
+                if self.p2p:
+                    mark("allreduce%d" % c)
         for c, (lo, hi) in enumerate(bounds):
             if works[c] is not None:
                 works[c].wait()
-            mark("allreduce%d" % c)
-            eng.train_backward(a, sums[c], lo, hi)
+            if not self.p2p:
+                mark("allreduce%d" % c)
+            eng.train_backward(a, totals[c], lo, hi)
             mark("backward%d" % c)
         eng.train_reduce(a)
         mark("reduce_apply")

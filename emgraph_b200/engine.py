@@ -307,6 +307,13 @@ class Engine:
         check(self.lib.kge_train_reduce(self._h, C.byref(a), _stream()))
         self.launches += 3
 
+    def allreduce_p2p(self, sums: KgeTable, totals: KgeTable, flags: KgeTable, rank: int, off: int, length: int, seq: int):
+        """Sum floats [off, off+length) of every rank's partial-sum buffer over peer memory into every rank's totals buffer
+        (include/kge_b200.h: kge_allreduce_p2p); collective: every rank calls it with the same range and seq."""
+        check(self.lib.kge_allreduce_p2p(self._h, C.byref(sums), C.byref(totals), C.byref(flags), int(rank), int(off), int(length),
+                                         int(seq) & 0xFFFFFFFF, _stream()))
+        self.launches += 1
+
     def normalize_rows(self, emb):
         _chk_f32(emb, "emb")
         check(self.lib.kge_normalize_rows(self._h, _ptr(emb), emb.shape[0], emb.shape[1], _stream()))

@@ -219,6 +219,14 @@ int kge_train_partial_sorted(kge_ctx* ctx, const kge_train_args* a, int n_chunks
 int kge_train_backward(kge_ctx* ctx, const kge_train_args* a, int64_t i_begin, int64_t i_end, const float* sums, void* stream);
 int kge_train_reduce(kge_ctx* ctx, const kge_train_args* a, void* stream);
 
+/* The all-reduce(sum) of the step above over peer memory instead of NCCL: floats [off, off+len) of every rank's `sums` buffer
+ * are summed in rank order and the totals written into every rank's `totals` buffer.  sums / totals / flags: shard[p] = rank p's
+ * buffer (own memory or a CUDA-IPC mapping, kge_ipc_open); flags: 16 uint32 words per rank, zeroed once before the first call;
+ * seq: a number that grows with every call (the same on every rank).  Every rank must call it with the same range and seq; the
+ * kernel returns (on the stream) when this rank's totals are complete.  off and len are multiples of 4. */
+int kge_allreduce_p2p(kge_ctx* ctx, const kge_table* sums, const kge_table* totals, const kge_table* flags, int rank,
+                      int64_t off, int64_t len, uint32_t seq, void* stream);
+
 /* Host-buffer form of kge_train_step: what a reference-side caller binds.  The reference feeds every
  * batch from host numpy through tf.data (models/EmbeddingModel.py:1329-1337, :1044-1111) and reads
  * the batch loss back with .numpy() (:1421).  pos_host [n_pos,3] int32 (pinned for an async copy) is
