@@ -446,6 +446,9 @@ class ShardedKGE:
             self._p2p_tables = tuple(make_table(b.peers, rows=n_sums * self.world, rows_per_shard=n_sums, K=1)
                                      for b in (self._sums_pb, self._tot_pb, self._flag_pb))
             self._p2p_seq = 0
+            # the exchange of piece c runs on its own (high-priority) stream beside the phase kernel of piece c+1
+            self._ar_stream = torch.cuda.Stream(device=dev, priority=-1)
+            self._ar_events = []
         else:
             self.sums_flat = torch.zeros(n_sums, dtype=torch.float32, device=dev)  # chunk c at (1+eta)*lo_c
             self.totals_flat = self.sums_flat  # NCCL reduces in place
@@ -518,8 +521,16 @@ class ShardedKGE:
                 off = e1 * lo // 4 * 4  # the kernel works on 16-byte vectors: the range is rounded outwards (the few
                 end = (e1 * hi + 3) // 4 * 4  # neighbouring floats it also sums are rewritten by their own piece)
                 self._p2p_seq += 1
-                eng.allreduce_p2p(*self._p2p_tables, self.rank_id, off, end - off, self._p2p_seq)
-                return None
+                while len(self._ar_events) <= 2 * c + 1:
+                    self._ar_events.append(torch.cuda.Event())
+                ready, done = self._ar_events[2 * c], self._ar_events[2 * c + 1]
+                main = torch.cuda.current_stream()
+                ready.record(main)
+                with torch.cuda.stream(self._ar_stream):
+                    self._ar_stream.wait_event(ready)
+                    eng.allreduce_p2p(*self._p2p_tables, self.rank_id, off, end - off, self._p2p_seq)
+                    done.record(self._ar_stream)
+                return done
             return dist.all_reduce(sums[c], group=self.group, async_op=True)
 
         works = []
@@ -532,13 +543,13 @@ class ShardedKGE:
                 eng.train_partial(a, sums[c], lo, hi)
                 mark("partial%d" % c)
                 works.append(reduce_piece(c))
-                if self.p2p:
-                    mark("allreduce%d" % c)
         for c, (lo, hi) in enumerate(bounds):
             if works[c] is not None:
-                works[c].wait()
-            if not self.p2p:
-                mark("allreduce%d" % c)
+                if self.p2p:
+                    torch.cuda.current_stream().wait_event(works[c])
+                else:
+                    works[c].wait()
+            mark("allreduce%d" % c)
             eng.train_backward(a, totals[c], lo, hi)
             mark("backward%d" % c)
         eng.train_reduce(a)
