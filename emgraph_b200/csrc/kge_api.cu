@@ -1,5 +1,6 @@
 // Context, error reporting, scoring (predict) and IPC helpers of the C ABI (include/kge_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -269,8 +270,16 @@ extern "C" int kge_allreduce_p2p(kge_ctx* ctx, const kge_table* sums, const kge_
     A.off = off;
     A.len = len;
     A.seq = seq;
+    // a SMALL grid: the CTAs poll peer flags while they wait for the slowest rank, and the kernel runs beside the phase kernel
+    // of the next piece -- 296 CTAs cost that kernel 50 % (measured on 8 GPUs); 16 CTAs of 256 threads keep ~1 MB of peer
+    // loads in flight, enough for the link.  KGE_P2P_CTAS overrides (A/B).
+    static int max_ctas = -1;
+    if (max_ctas < 0) {
+        const char* e = getenv("KGE_P2P_CTAS");
+        max_ctas = (e != nullptr && atoi(e) > 0) ? atoi(e) : 16;
+    }
     const int64_t per = (len / 4 + W - 1) / W;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((per + 255) / 256, 2 * (int64_t)ctx->sm_count));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((per + 255) / 256, (int64_t)max_ctas));
     kge_allreduce_p2p_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(A);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
