@@ -428,11 +428,12 @@ class ShardedKGE:
         # random gather -- the query gather then misses L2 half of the time -- so it is OFF unless asked for.
         self.sorted_partial = False if sorted_partial is None else bool(sorted_partial)
         n_sums = ((1 + self.eta) * self.n + 7) // 4 * 4
-        # the sum over the ranks: by default the library's own all-reduce over peer memory (kge_allreduce_p2p: P2P loads and
-        # stores through CUDA-IPC mappings, flags in peer memory) when the ranks are CUDA devices of one node; NCCL otherwise
-        # (p2p_allreduce=False, KGE_P2P_ALLREDUCE=0, or a CPU process group in the tests)
+        # the sum over the ranks: NCCL's all-reduce by default; p2p_allreduce=True / KGE_P2P_ALLREDUCE=1 selects the library's own
+        # exchange over peer memory (kge_allreduce_p2p: P2P loads and stores through CUDA-IPC mappings, flags in peer memory).
+        # Measured on 8 x B200 (profiles/r02_summary.md): NCCL (in-switch reduction) moves the 10.7 MB pieces of cfg5 faster than
+        # a plain pull/push kernel of a size that does not disturb the phase kernels, so it stays the default
         if p2p_allreduce is None:
-            p2p_allreduce = os.environ.get("KGE_P2P_ALLREDUCE", "1")[:1] != "0"
+            p2p_allreduce = os.environ.get("KGE_P2P_ALLREDUCE", "0")[:1] == "1"
         self.p2p = bool(p2p_allreduce) and self.world > 1 and dev.type == "cuda" and hasattr(eng, "allreduce_p2p")
         if self.p2p:
             self._sums_pb = PeerBuffer(eng, (n_sums,))
