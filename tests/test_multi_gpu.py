@@ -26,8 +26,11 @@ def _worker(rank, world, port, cfg, q):
         model, loss, k, eta, E, R, n = cfg["model"], cfg["loss"], cfg["k"], cfg["eta"], cfg["E"], cfg["R"], cfg["n"]
         ent, rel = cfg["ent"], cfg["rel"]
         out = {}
-        if cfg["exchange"] == "dim":
-            sk = ShardedKGE(model, k, eta, loss, "adam", E, R, n, lr=1e-2, seed=77, init_ent=ent, init_rel=rel, device=rank, chunks=cfg["chunks"])
+        if cfg["exchange"] in ("dim", "dim_p2p"):
+            # "dim_p2p": the sum over the ranks through the library's peer-memory all-reduce instead of NCCL
+            sk = ShardedKGE(model, k, eta, loss, "adam", E, R, n, lr=1e-2, seed=77, init_ent=ent, init_rel=rel, device=rank, chunks=cfg["chunks"],
+                            p2p_allreduce=cfg["exchange"] == "dim_p2p")
+            assert sk.p2p == (cfg["exchange"] == "dim_p2p")
             dev = sk.eng.tdev
             N = n * world
             P = np.concatenate(cfg["pos"], 0)
@@ -97,7 +100,7 @@ def _global_corruptions(world, n, eta, repl, keep):
     (2, "ComplEx", "nll", 12, "dim", 2), (2, "TransE", "pairwise", 16, "dim", 1), (2, "DistMult", "multiclass_nll", 8, "dim", 3),
     (2, "HolE", "self_adversarial", 10, "dim", 2), (4, "DistMult", "nll", 64, "dim", 2), (8, "ComplEx", "nll", 100, "dim", 2),
     (8, "DistMult", "nll", 256, "dim", 2), (8, "TransE", "multiclass_nll", 20, "dim", 1),
-    (2, "ComplEx", "nll", 12, "push", 1),
+    (2, "ComplEx", "nll", 12, "push", 1), (2, "DistMult", "nll", 20, "dim_p2p", 2), (8, "ComplEx", "multiclass_nll", 24, "dim_p2p", 2),
 ])
 def test_sharded_step_and_ranking_match_oracle(world, model, loss, k, exchange, chunks):
     if torch.cuda.device_count() < world:
@@ -124,7 +127,7 @@ def test_sharded_step_and_ranking_match_oracle(world, model, loss, k, exchange, 
     touched = o["touched_ent"].copy()
     big = np.abs(o["grad_ent"]) > 1e-3  # first Adam step ~ lr*sign(g): ill-conditioned where |g| ~ eps
     e_exp, r_exp = o["ent_new"], o["rel_new"]
-    if exchange == "dim":
+    if exchange.startswith("dim"):
         repl2, keep2 = ko.draw_corruptions(77, 2, P.shape[0], eta, E, "s,o")
         o2 = ko.train_step(model, k, loss, eta, o["ent_new"], o["rel_new"], P, keep2, repl2, opt="adam", lr=1e-2,
                            state=(o["state_ent"], o["state_rel"]), step=2)
@@ -135,7 +138,7 @@ def test_sharded_step_and_ranking_match_oracle(world, model, loss, k, exchange, 
     np.testing.assert_array_equal(res["ent"][~touched], ent[~touched])
     np.testing.assert_allclose(res["ent"][big], e_exp[big], rtol=1e-4, atol=2e-6)
     bigr = np.abs(o["grad_rel"]) > 1e-3
-    if exchange != "dim":
+    if not exchange.startswith("dim"):
         np.testing.assert_allclose(res["rel"][bigr], r_exp[bigr], rtol=1e-5, atol=1e-6)
     exp = ko.ranks(model, k, res["ent"], res["rel"], test, filt, "s,o", "worst")
     for key in ("ranks_tc0", "ranks_tc1"):
