@@ -1093,22 +1093,31 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
     }
     // a shallow grid (a few waves of warps) is latency-bound: two warps per chunk, half the columns each.  KGE_APPLY_SPLIT=0/1
     // forces it off / on (A/B)
-    bool split = false;
+    int split = 0;  // warps per chunk: 0/1 = one; 2 or 4 = that many, each with 1/2 or 1/4 of the columns
     if constexpr (V == 4 && NCA >= 2) {
         static int force = -2;
         if (force == -2) {
             const char* e = getenv("KGE_APPLY_SPLIT");
-            force = e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
+            force = e == nullptr ? -1 : atoi(e);
         }
-        split = force >= 0 ? force != 0 : n_chunks < (int64_t)sm_count * 16 * 8;
+        split = force >= 0 ? force : (n_chunks < (int64_t)sm_count * 16 * 8 ? 2 : 0);
+        if (split == 4 && NCA < 4) split = 2;
+        if (split == 1) split = 0;
     }
     if (staged || grouped) {
-    } else if (split) {
+    } else if (split == 2) {
         if constexpr (V == 4 && NCA >= 2) {
             dim3 grid2((unsigned)((2 * n_chunks + KGE_RA_WARPS - 1) / KGE_RA_WARPS));
             if (tmode == 0) kge_reduce_apply_kernel<V, 0, NCA / 2, 2><<<grid2, block, 0, st>>>(P);
             else if (tmode == 1) kge_reduce_apply_kernel<V, 1, NCA / 2, 2><<<grid2, block, 0, st>>>(P);
             else kge_reduce_apply_kernel<V, 2, NCA / 2, 2><<<grid2, block, 0, st>>>(P);
+        }
+    } else if (split == 4) {
+        if constexpr (V == 4 && NCA >= 4) {
+            dim3 grid4((unsigned)((4 * n_chunks + KGE_RA_WARPS - 1) / KGE_RA_WARPS));
+            if (tmode == 0) kge_reduce_apply_kernel<V, 0, NCA / 4, 4><<<grid4, block, 0, st>>>(P);
+            else if (tmode == 1) kge_reduce_apply_kernel<V, 1, NCA / 4, 4><<<grid4, block, 0, st>>>(P);
+            else kge_reduce_apply_kernel<V, 2, NCA / 4, 4><<<grid4, block, 0, st>>>(P);
         }
     } else if (tmode == 0) kge_reduce_apply_kernel<V, 0, NCA, 1><<<grid, block, 0, st>>>(P);
     else if (tmode == 1) kge_reduce_apply_kernel<V, 1, NCA, 1><<<grid, block, 0, st>>>(P);

@@ -833,13 +833,16 @@ __global__ void __launch_bounds__(128, (FwdOcc<MODEL, V, NCH, PIPE>::value)) kge
     }
 }
 
-static inline int fwd_bwd_max_ctas() {
+// resident CTAs of the staged kernel per SM.  3 leaves room on every SM for the CTAs of the radix sort that runs beside it --
+// right when the sort is the longer of the two (cfg1-3: ~60 us against 30-53 us); a large batch (cfg5: sort 120 us against
+// 210 us) is better served by a fourth CTA (measured: fwd_bwd 0.211 -> 0.191 ms).  KGE_FWD_MAXCTAS overrides (A/B).
+static inline int fwd_bwd_max_ctas(int64_t n_slots) {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("KGE_FWD_MAXCTAS");
-        v = (e != nullptr && e[0] >= '1' && e[0] <= '8') ? (e[0] - '0') : 3;
+        v = (e != nullptr && e[0] >= '1' && e[0] <= '8') ? (e[0] - '0') : 0;
     }
-    return v;
+    return v > 0 ? v : (n_slots >= 400000 ? 4 : 3);
 }
 
 // ring slots per warp (log2) of the PIPE variant: 16 when four 4-warp CTAs still fit one SM, else 8
@@ -869,7 +872,7 @@ static int launch_fwd_bwd_split(int split, bool pipe, const FwdBwdParams& P, cud
         if (pp_) {
             // leave room on every SM for the CTAs of the radix sort that runs beside this kernel on the
             // side stream: at most `m` resident CTAs of this kernel (KGE_FWD_MAXCTAS, default 3)
-            const int m = fwd_bwd_max_ctas();
+            const int m = fwd_bwd_max_ctas((int64_t)(3 + P.eta) * P.n);
             const size_t floor_bytes = 233472 / (size_t)(m + 1) - 1024 + 16;
             if (smem < floor_bytes) smem = floor_bytes;
         }
