@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(256) kge_loss_reduce_kernel(const float* __res
 
 int kge_launch_apply_group(const ApplyParams& P, int tmode, cudaStream_t st);  // kge_apply_group.cu
 bool kge_apply_group_ok(const ApplyParams& P);
+int kge_launch_apply_wide(const ApplyParams& P, int tmode, cudaStream_t st);  // kge_apply_wide.cu
+bool kge_apply_wide_ok(const ApplyParams& P);
 
 
 // Level 1: one warp per chunk of KGE_CH sorted slots.  NCA > 0: lanes own ALL their column vectors of
@@ -1091,8 +1093,22 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
         if (grouped)
             if (int rc = kge_launch_apply_group(P, tmode, st)) return rc;
     }
-    // a shallow grid (a few waves of warps) is latency-bound: two warps per chunk, half the columns each.  KGE_APPLY_SPLIT=0/1
-    // forces it off / on (A/B)
+    // wide rows on one local buffer: the load-list kernel (kge_apply_wide.cu).  KGE_APPLY_WIDE=0: off, 1: always, default:
+    // shallow grids only (a batch that is a few waves of warps deep is latency-bound; a deep one already runs at DRAM speed)
+    bool wide = false;
+    if constexpr (V == 4 && NCA > 0) {
+        static int wide_on = -2;
+        if (wide_on == -2) {
+            const char* e = getenv("KGE_APPLY_WIDE");
+            wide_on = e == nullptr ? -1 : atoi(e);
+        }
+        const bool want = wide_on >= 0 ? wide_on != 0 : n_chunks < (int64_t)sm_count * 16 * 8;
+        wide = !staged && !grouped && want && kge_apply_wide_ok(P);
+        if (wide)
+            if (int rc = kge_launch_apply_wide(P, tmode, st)) return rc;
+    }
+    // the warp-per-chunk kernel on a shallow grid: two (four) warps per chunk, half (a quarter of) the columns each.
+    // KGE_APPLY_SPLIT=0/2/4 forces it (A/B)
     int split = 0;  // warps per chunk: 0/1 = one; 2 or 4 = that many, each with 1/2 or 1/4 of the columns
     if constexpr (V == 4 && NCA >= 2) {
         static int force = -2;
@@ -1104,7 +1120,7 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
         if (split == 4 && NCA < 4) split = 2;
         if (split == 1) split = 0;
     }
-    if (staged || grouped) {
+    if (staged || grouped || wide) {
     } else if (split == 2) {
         if constexpr (V == 4 && NCA >= 2) {
             dim3 grid2((unsigned)((2 * n_chunks + KGE_RA_WARPS - 1) / KGE_RA_WARPS));
