@@ -593,27 +593,58 @@ __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(App
         }
         const int64_t last = span_last_chunk(P, w, key, n_chunks, lane);
         const int64_t n_ent = last - w + 1;
-        for (int c0 = lane * V; c0 < K; c0 += 32 * V) {
-            float g[V];
+        // The top hub of a Zipf graph owns ~10 % of all slots -- hundreds of partial rows -- and its CTA's chain of loads IS
+        // the duration of this kernel.  The warps form a grid of nrg row groups x ncg column groups (a lane owns one vector
+        // of its column group), so a warp keeps 8 partial rows in flight instead of walking the row's column groups one
+        // after the other with 2: ~10 dependent round trips for a 600-chunk hub at K = 400 instead of ~40.
+        const int ncg = (K + 32 * V - 1) / (32 * V);
+        int nrg = KGE_SPAN_WARPS;  // rows of sred in use
+        if (ncg <= KGE_SPAN_WARPS) {
+            nrg = KGE_SPAN_WARPS / ncg;
+            const int cg = wib % ncg, rg = wib / ncg;
+            const int c0 = (cg * 32 + lane) * V;
+            if (rg < nrg && c0 < K) {
+                float g[V];
 #pragma unroll
-            for (int x = 0; x < V; ++x) g[x] = 0.f;
-            int64_t e = wib;
-            for (; e + KGE_SPAN_WARPS < n_ent; e += 2 * KGE_SPAN_WARPS) {
-                float t0[V], t1[V];
-                ld_vec<V>(t0, span_entry(P, w, e, K) + c0);
-                ld_vec<V>(t1, span_entry(P, w, e + KGE_SPAN_WARPS, K) + c0);
+                for (int x = 0; x < V; ++x) g[x] = 0.f;
+                for (int64_t e = rg; e < n_ent; e += 8 * (int64_t)nrg) {
+                    float t[8][V];
 #pragma unroll
-                for (int x = 0; x < V; ++x) g[x] += t0[x];
+                    for (int q = 0; q < 8; ++q) {
 #pragma unroll
-                for (int x = 0; x < V; ++x) g[x] += t1[x];
+                        for (int x = 0; x < V; ++x) t[q][x] = 0.f;
+                        if (e + (int64_t)q * nrg < n_ent) ld_vec<V>(t[q], span_entry(P, w, e + (int64_t)q * nrg, K) + c0);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+#pragma unroll
+                        for (int x = 0; x < V; ++x) g[x] += t[q][x];
+                }
+                st_vec<V>(sred + (size_t)rg * K + c0, g);
             }
-            if (e < n_ent) {
-                float t0[V];
-                ld_vec<V>(t0, span_entry(P, w, e, K) + c0);
+        } else {
+            for (int c0 = lane * V; c0 < K; c0 += 32 * V) {
+                float g[V];
 #pragma unroll
-                for (int x = 0; x < V; ++x) g[x] += t0[x];
+                for (int x = 0; x < V; ++x) g[x] = 0.f;
+                int64_t e = wib;
+                for (; e + KGE_SPAN_WARPS < n_ent; e += 2 * KGE_SPAN_WARPS) {
+                    float t0[V], t1[V];
+                    ld_vec<V>(t0, span_entry(P, w, e, K) + c0);
+                    ld_vec<V>(t1, span_entry(P, w, e + KGE_SPAN_WARPS, K) + c0);
+#pragma unroll
+                    for (int x = 0; x < V; ++x) g[x] += t0[x];
+#pragma unroll
+                    for (int x = 0; x < V; ++x) g[x] += t1[x];
+                }
+                if (e < n_ent) {
+                    float t0[V];
+                    ld_vec<V>(t0, span_entry(P, w, e, K) + c0);
+#pragma unroll
+                    for (int x = 0; x < V; ++x) g[x] += t0[x];
+                }
+                st_vec<V>(sred + (size_t)wib * K + c0, g);
             }
-            st_vec<V>(sred + (size_t)wib * K + c0, g);
         }
         __syncthreads();
         float* dbg = r.is_rel ? P.dbg_grad_rel : P.dbg_grad_ent;
@@ -631,8 +662,7 @@ __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(App
                 if (need_m) ld_vec<V>(mv, r.m + c0);
                 if (need_v) ld_vec<V>(vv, r.v + c0);
             }
-#pragma unroll
-            for (int j = 0; j < KGE_SPAN_WARPS; ++j) {
+            for (int j = 0; j < nrg; ++j) {
                 float t0[V];
                 ld_vec<V>(t0, sred + (size_t)j * K + c0);
 #pragma unroll
@@ -1093,8 +1123,10 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
         if (grouped)
             if (int rc = kge_launch_apply_group(P, tmode, st)) return rc;
     }
-    // wide rows on one local buffer: the load-list kernel (kge_apply_wide.cu).  KGE_APPLY_WIDE=0: off, 1: always, default:
-    // shallow grids only (a batch that is a few waves of warps deep is latency-bound; a deep one already runs at DRAM speed)
+    // wide rows on one local buffer: the load-list kernel (kge_apply_wide.cu), KGE_APPLY_WIDE=1.  Off by default: measured on
+    // B200 (profiles/r02_summary.md, session r2w) it shortens the dependent chain of a chunk from ~10 to ~3 memory round trips
+    // and still takes 63 us against 55 us on cfg3 -- both kernels move the same 13 M L2 sectors, ~60 % of the measured L2
+    // sector rate, and that, not latency, is what bounds the reduction of a dense batch
     bool wide = false;
     if constexpr (V == 4 && NCA > 0) {
         static int wide_on = -2;
@@ -1102,7 +1134,7 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
             const char* e = getenv("KGE_APPLY_WIDE");
             wide_on = e == nullptr ? -1 : atoi(e);
         }
-        const bool want = wide_on >= 0 ? wide_on != 0 : n_chunks < (int64_t)sm_count * 16 * 8;
+        const bool want = wide_on > 0;
         wide = !staged && !grouped && want && kge_apply_wide_ok(P);
         if (wide)
             if (int rc = kge_launch_apply_wide(P, tmode, st)) return rc;

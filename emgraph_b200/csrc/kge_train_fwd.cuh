@@ -931,6 +931,14 @@ static int launch_fwd_bwd_model(const FwdBwdParams& P, int sm_count, cudaStream_
     const int64_t want = (int64_t)sm_count * 24;
     if (P.n < want && P.eta >= 8) split = 2;
     if (P.n * 2 < want && P.eta >= 16) split = 4;
+    {
+        static int force = -2;  // KGE_FWD_SPLIT=1|2|4 overrides (A/B)
+        if (force == -2) {
+            const char* e = getenv("KGE_FWD_SPLIT");
+            force = e == nullptr ? -1 : atoi(e);
+        }
+        if (force == 1 || force == 2 || force == 4) split = force;
+    }
     if (width % 4 == 0) {
         int nvec = width / 4;
         // staged (bulk-copy) rows need 16-byte row pitch and local memory
