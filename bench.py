@@ -482,10 +482,13 @@ def train_bench_single(args, name, w, steps, warmup, detailed):
             model._fit_step_device(Xd[lo:hi])
             it += 1
         torch.cuda.synchronize()
-        phases, n_ph = eng.get_timing()
+        phases, n_ph = eng.get_timing_ex()
         eng.set_timing(False)
         f["pipeline"] = pipeline_on
+        # reduce_apply = the level-1 reduction kernel alone, from its launch point on the stream (an event recorded behind
+        # the wait for the side-stream sort) to its end; the wait itself is reported as sort_wait
         t_emit, t_fb, t_apply, t_span = phases["emit"], phases["fwd_bwd"], phases["reduce_apply"], phases["spans"]
+        t_wait = phases["sort_wait"]
         S = (3 + eta) * B
         keys = torch.empty(S, dtype=torch.int32, device=dev)
         uniq = []
@@ -510,7 +513,7 @@ def train_bench_single(args, name, w, steps, warmup, detailed):
         out["roofline"] = {
             "bound": "hbm", "kernel": dom, "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
             "traffic": traffic, "traffic_source": tsrc, "peak_source": peaks["src"], "algorithmic_bytes_per_launch": dom_b, "kernel_ms": dom_t,
-            "phases_ms": {"emit": t_emit, "fwd_bwd": t_fb, "reduce_apply": t_apply, "span_hub": t_span,
+            "phases_ms": {"emit": t_emit, "fwd_bwd": t_fb, "sort_wait": t_wait, "reduce_apply": t_apply, "span_hub": t_span,
                           "sort_done_after_emit": phases.get("sort_after_emit", 0.0), "timed_steps": n_ph},
             "kernels": {"fwd_bwd": {"bytes": bytes_fb, "GBps": bytes_fb / (t_fb * 1e-3) / 1e9, "frac": bytes_fb / (t_fb * 1e-3) / 1e9 / peaks["hbm"]},
                         "reduce_apply": {"bytes": bytes_apply, "GBps": bytes_apply / (t_red * 1e-3) / 1e9,

@@ -70,6 +70,8 @@ SYMBOLS = {
     "kge_ctx_workspace_bytes": (_L, [_P]),
     "kge_ctx_set_timing": (_I, [_P, _I]),
     "kge_ctx_get_timing": (_I, [_P, C.POINTER(C.c_float), C.POINTER(_I)]),
+    "kge_ctx_get_timing_ex": (_I, [_P, C.POINTER(C.c_float), _I, C.POINTER(_I)]),
+    "kge_sort_entries": (_I, [_P, _P, _L, _L, _I, _P, _P]),
     "kge_score": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _P, _P]),
     "kge_predict": (_I, [_P, _I, _I, C.POINTER(KgeTable), _P, _L, _P, _L, _I, _P, _P]),
     "kge_train_step": (_I, [_P, C.POINTER(KgeTrainArgs), _P]),

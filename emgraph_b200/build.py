@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkge_b200.so")
 SOURCES = ["kge_api.cu", "kge_train.cu", "kge_train_fwd_m0.cu", "kge_train_fwd_m1.cu", "kge_train_fwd_m2.cu",
-           "kge_train_fwd_m3.cu", "kge_dim_m0.cu", "kge_dim_m1.cu", "kge_dim_m2.cu", "kge_dim_m3.cu", "kge_apply_group.cu", "kge_apply_wide.cu",
+           "kge_train_fwd_m3.cu", "kge_dim_m0.cu", "kge_dim_m1.cu", "kge_dim_m2.cu", "kge_dim_m3.cu", "kge_apply_group.cu", "kge_apply_wide.cu", "kge_sort_small.cu",
            "kge_rank.cu", "kge_rank_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

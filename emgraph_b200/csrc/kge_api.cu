@@ -45,7 +45,7 @@ extern "C" int kge_ctx_destroy(kge_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     KgeBuf* bufs[] = {&c->sort_tmp, &c->repl, &c->keep,
-                      &c->grad_rows, &c->loss_part, &c->loss_scr, &c->pos_off, &c->p2p_counter, &c->neg_scores, &c->partial, &c->span_head, &c->ks_in, &c->ks_sel, &c->ks_sorted, &c->sel_flags, &c->sel_count, &c->h_pos, &c->h_loss, &c->h_test, &c->h_counts, &c->h_ranks, &c->q_fold, &c->q_hi, &c->q_lo, &c->e_hi, &c->e_lo,
+                      &c->grad_rows, &c->loss_part, &c->loss_scr, &c->pos_off, &c->p2p_counter, &c->ss_hist, &c->ss_aux, &c->neg_scores, &c->partial, &c->span_head, &c->ks_in, &c->ks_sel, &c->ks_sorted, &c->sel_flags, &c->sel_count, &c->h_pos, &c->h_loss, &c->h_test, &c->h_counts, &c->h_ranks, &c->q_fold, &c->q_hi, &c->q_lo, &c->e_hi, &c->e_lo,
                       &c->pos_q, &c->excl_lo, &c->excl_hi, &c->f_sp_comp, &c->f_po_comp, &c->f_sp_ent, &c->f_po_ent,
                       &c->f_tmp, &c->f_tmp2, &c->f_count};
     for (KgeBuf* b : bufs) b->release();
@@ -71,6 +71,8 @@ extern "C" int kge_ctx_destroy(kge_ctx* c) {
     if (c->ev_count) cudaEventDestroy(c->ev_count);
     for (cudaEvent_t e : {c->ev_fork, c->ev_sorted, c->ev_fwd, c->ev_loss})
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->tev)
+        if (e) cudaEventDestroy(e);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->lstream) cudaStreamDestroy(c->lstream);
     delete c;
@@ -80,7 +82,7 @@ extern "C" int kge_ctx_destroy(kge_ctx* c) {
 extern "C" int64_t kge_ctx_workspace_bytes(kge_ctx* c) {
     if (!c) return 0;
     KgeBuf* bufs[] = {&c->sort_tmp, &c->repl, &c->keep,
-                      &c->grad_rows, &c->loss_part, &c->loss_scr, &c->pos_off, &c->p2p_counter, &c->neg_scores, &c->partial, &c->span_head, &c->ks_in, &c->ks_sel, &c->ks_sorted, &c->sel_flags, &c->sel_count, &c->h_pos, &c->h_loss, &c->h_test, &c->h_counts, &c->h_ranks, &c->q_fold, &c->q_hi, &c->q_lo, &c->e_hi, &c->e_lo,
+                      &c->grad_rows, &c->loss_part, &c->loss_scr, &c->pos_off, &c->p2p_counter, &c->ss_hist, &c->ss_aux, &c->neg_scores, &c->partial, &c->span_head, &c->ks_in, &c->ks_sel, &c->ks_sorted, &c->sel_flags, &c->sel_count, &c->h_pos, &c->h_loss, &c->h_test, &c->h_counts, &c->h_ranks, &c->q_fold, &c->q_hi, &c->q_lo, &c->e_hi, &c->e_lo,
                       &c->pos_q, &c->excl_lo, &c->excl_hi, &c->f_sp_comp, &c->f_po_comp, &c->f_sp_ent, &c->f_po_ent,
                       &c->f_tmp, &c->f_tmp2, &c->f_count};
     int64_t tot = (int64_t)c->h_pos2[0].cap + (int64_t)c->h_pos2[1].cap;

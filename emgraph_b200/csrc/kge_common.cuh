@@ -84,6 +84,7 @@ struct kge_ctx {
     // training workspace
     KgeBuf sort_tmp;
     KgeBuf loss_scr, pos_off, p2p_counter;
+    KgeBuf ss_hist, ss_aux;  // kge_sort_small.cu: segment x key count matrix (all-zero between sorts), key / CTA offsets + ticket
     KgeBuf repl, keep, grad_rows, loss_part, neg_scores, partial, span_head, reg_partial, touched;
     KgeBuf ks_in, ks_sel, ks_sorted, sel_flags, sel_count;
     // second set of the per-step corruption / sort-key buffers {repl, keep, ks_in, ks_sorted}: a pipelined step
@@ -101,8 +102,8 @@ struct kge_ctx {
     cudaEvent_t   ev_fork = nullptr, ev_sorted = nullptr, ev_fwd = nullptr, ev_loss = nullptr;
     // optional per-phase timing of kge_train_step (bench instrumentation): emit | fwd_bwd | reduce | spans
     bool          timing = false, tpending = false;
-    cudaEvent_t   tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    double        tacc[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t   tev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double        tacc[6] = {0, 0, 0, 0, 0, 0};
     int           tcount = 0;
     int*          h_count = nullptr;
     cudaEvent_t   ev_count = nullptr;

@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(256) kge_loss_reduce_kernel(const float* __res
 
 int kge_launch_apply_group(const ApplyParams& P, int tmode, cudaStream_t st);  // kge_apply_group.cu
 bool kge_apply_group_ok(const ApplyParams& P);
+bool kge_small_sort_ok(int64_t n_items, int64_t n_keys);  // kge_sort_small.cu
+int kge_small_sort(kge_ctx* ctx, const uint64_t* in, int64_t n_items, int64_t n_keys, uint64_t* out, cudaStream_t st);
 int kge_launch_apply_wide(const ApplyParams& P, int tmode, cudaStream_t st);  // kge_apply_wide.cu
 bool kge_apply_wide_ok(const ApplyParams& P);
 
@@ -1090,10 +1092,11 @@ static int launch_span(const ApplyParams& P, int sm_count, cudaStream_t st) {
 }
 
 template <int V, int NCA>
-static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st, cudaEvent_t mid) {
+static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st, cudaEvent_t mid, cudaEvent_t pre) {
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
     dim3 grid((unsigned)((n_chunks + KGE_RA_WARPS - 1) / KGE_RA_WARPS)), block(KGE_RA_WARPS * 32);
     KGE_CUDA_CHECK(cudaMemsetAsync(P.span_count, 0, 2 * sizeof(int32_t), st));
+    if (pre != nullptr) KGE_CUDA_CHECK(cudaEventRecord(pre, st));  // bench instrumentation: the level-1 kernel starts here
     bool staged = false;
     if constexpr (V == 4 && NCA > 0) {
         // staged rows need local buffers (bulk copies of peer memory are not used) and 16-byte rows
@@ -1148,7 +1151,10 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
             const char* e = getenv("KGE_APPLY_SPLIT");
             force = e == nullptr ? -1 : atoi(e);
         }
-        split = force >= 0 ? force : (n_chunks < (int64_t)sm_count * 16 * 8 ? 2 : 0);
+        // measured (profiles/r02_summary.md, sessions r2z / r2v): cfg3 (6 100 chunks) 87 -> 65 -> 62 us with 1 -> 2 -> 4 warps per
+        // chunk, cfg4 (21 000 chunks) 268 -> 255 us with 4; a deep grid of narrower rows (cfg5, 43 000 chunks) already runs at
+        // DRAM speed with one warp per chunk
+        split = force >= 0 ? force : (n_chunks < (int64_t)sm_count * 256 ? (NCA >= 4 ? 4 : 2) : 0);
         if (split == 4 && NCA < 4) split = 2;
         if (split == 1) split = 0;
     }
@@ -1179,16 +1185,16 @@ static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaS
     return span_warps(P.ent.K) == 32 ? launch_span<V, 32>(P, sm_count, st) : launch_span<V, 8>(P, sm_count, st);
 }
 
-static int launch_apply(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st, cudaEvent_t mid) {
+static int launch_apply(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st, cudaEvent_t mid, cudaEvent_t pre = nullptr) {
     const int K = P.ent.K;
     KGE_REQUIRE((size_t)span_warps(K) * K * sizeof(float) <= 200 * 1024, "kge_train: embedding size %d too large for the span reduction", K);
     if (K % 4 == 0) {
-        if (K <= 128) return launch_apply_nca<4, 1>(P, tmode, sm_count, st, mid);
-        if (K <= 256) return launch_apply_nca<4, 2>(P, tmode, sm_count, st, mid);
-        if (K <= 512) return launch_apply_nca<4, 4>(P, tmode, sm_count, st, mid);
-        return launch_apply_nca<4, 0>(P, tmode, sm_count, st, mid);
+        if (K <= 128) return launch_apply_nca<4, 1>(P, tmode, sm_count, st, mid, pre);
+        if (K <= 256) return launch_apply_nca<4, 2>(P, tmode, sm_count, st, mid, pre);
+        if (K <= 512) return launch_apply_nca<4, 4>(P, tmode, sm_count, st, mid, pre);
+        return launch_apply_nca<4, 0>(P, tmode, sm_count, st, mid, pre);
     }
-    return launch_apply_nca<1, 0>(P, tmode, sm_count, st, mid);
+    return launch_apply_nca<1, 0>(P, tmode, sm_count, st, mid, pre);
 }
 
 // packed_in: n_items (key << 32 | global slot) entries, unsorted; sorted by key (stable) into ctx->ks_sorted
@@ -1201,6 +1207,9 @@ static int sort_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* pack
     if (ctx->partial.reserve((size_t)2 * n_chunks * K * sizeof(float))) return -2;
     if (ctx->span_head.reserve((size_t)(2 * n_chunks + 2) * sizeof(int32_t))) return -2;
     int64_t E = a->ent.rows;
+    // small batch over a small key range: one-pass stable counting sort with CTAs small enough to run beside the
+    // forward/backward kernel (kge_sort_small.cu); same output, bit for bit
+    if (kge_small_sort_ok(n_items, E + a->R)) return kge_small_sort(ctx, packed_in, n_items, E + a->R, ctx->ks_sorted.as<uint64_t>(), st);
     int end_bit = 1;
     while (((int64_t)1 << end_bit) < E + a->R) ++end_bit;
     size_t tmp_bytes = 0;
@@ -1320,7 +1329,7 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
             KGE_REQUIRE(P.has_m && a->rel_m, "kge_train: optimizer state missing");
     }
     const int tmode = a->model == KGE_TRANSE_L1 ? 1 : (a->model == KGE_TRANSE_L2 ? 2 : 0);
-    if (int rc = launch_apply(P, tmode, ctx->sm_count, st, ctx->timing ? ctx->tev[3] : nullptr)) return rc;
+    if (int rc = launch_apply(P, tmode, ctx->sm_count, st, ctx->timing ? ctx->tev[3] : nullptr, ctx->timing ? ctx->tev[6] : nullptr)) return rc;
     if (reg) {
         if (K % 4 == 0) kge_reg_dense_kernel<4><<<ctx->sm_count * 8, 256, 0, st>>>(P);
         else kge_reg_dense_kernel<1><<<ctx->sm_count * 8, 256, 0, st>>>(P);
@@ -1433,6 +1442,10 @@ static void timing_collect(kge_ctx* ctx) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->tev[1], ctx->tev[5]) == cudaSuccess) ctx->tacc[4] += ms;
     }
+    {   // end of fwd_bwd -> launch of the level-1 reduction kernel: the wait for the sort (+ two memsets)
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->tev[2], ctx->tev[6]) == cudaSuccess) ctx->tacc[5] += ms;
+    }
     ctx->tcount += 1;
     ctx->tpending = false;
 }
@@ -1440,10 +1453,10 @@ static void timing_collect(kge_ctx* ctx) {
 extern "C" int kge_ctx_set_timing(kge_ctx* ctx, int on) {
     KGE_REQUIRE(ctx != nullptr, "kge_ctx_set_timing: null ctx");
     if (on && ctx->tev[0] == nullptr)
-        for (int i = 0; i < 6; ++i) KGE_CUDA_CHECK(cudaEventCreate(&ctx->tev[i]));
+        for (int i = 0; i < 7; ++i) KGE_CUDA_CHECK(cudaEventCreate(&ctx->tev[i]));
     timing_collect(ctx);
     ctx->timing = on != 0;
-    for (int i = 0; i < 5; ++i) ctx->tacc[i] = 0;
+    for (int i = 0; i < 6; ++i) ctx->tacc[i] = 0;
     ctx->tcount = 0;
     return 0;
 }
@@ -1452,6 +1465,43 @@ extern "C" int kge_ctx_get_timing(kge_ctx* ctx, float* ms_out5, int* steps_out) 
     KGE_REQUIRE(ctx != nullptr && ms_out5 != nullptr, "kge_ctx_get_timing: null argument");
     timing_collect(ctx);
     for (int i = 0; i < 5; ++i) ms_out5[i] = ctx->tcount ? (float)(ctx->tacc[i] / ctx->tcount) : 0.f;
+    if (steps_out) *steps_out = ctx->tcount;
+    return 0;
+}
+
+// test hook: the sort of the (key << 32 | slot) entries alone.  algo 0: cub::DeviceRadixSort on the key bits (stable); 1: the
+// counting sort of kge_sort_small.cu (fails when the size is outside its range)
+extern "C" int kge_sort_entries(kge_ctx* ctx, const uint64_t* in, int64_t n, int64_t n_keys, int algo, uint64_t* out, void* stream) {
+    KGE_REQUIRE(ctx != nullptr && in != nullptr && out != nullptr && n >= 0 && n_keys > 0, "kge_sort_entries: bad argument");
+    KGE_REQUIRE(n <= (int64_t)KGE_SLOT_MASK, "kge_sort_entries: too many entries");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (algo == 1) {
+        KGE_REQUIRE(kge_small_sort_ok(n, n_keys), "kge_sort_entries: %lld entries / %lld keys is outside the counting sort's range",
+                    (long long)n, (long long)n_keys);
+        return kge_small_sort(ctx, in, n, n_keys, out, st);
+    }
+    int end_bit = 1;
+    while (((int64_t)1 << end_bit) < n_keys) ++end_bit;
+    size_t tmp_bytes = 0;
+    KGE_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, in, out, (int)n, 32, 32 + end_bit, st));
+    if (ctx->sort_tmp.reserve(tmp_bytes)) return -2;
+    KGE_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, tmp_bytes, in, out, (int)n, 32, 32 + end_bit, st));
+    return 0;
+}
+
+// the same with the wait for the sort split off: {emit, fwd_bwd, sort wait, level-1 reduction kernel, span/hub reduction,
+// end of the sort measured from the end of emit}
+extern "C" int kge_ctx_get_timing_ex(kge_ctx* ctx, float* ms_out, int n_out, int* steps_out) {
+    KGE_REQUIRE(ctx != nullptr && ms_out != nullptr && n_out >= 6, "kge_ctx_get_timing_ex: need room for 6 phases");
+    timing_collect(ctx);
+    const double n = ctx->tcount ? (double)ctx->tcount : 1.0;
+    ms_out[0] = (float)(ctx->tacc[0] / n);
+    ms_out[1] = (float)(ctx->tacc[1] / n);
+    ms_out[2] = (float)(ctx->tacc[5] / n);
+    ms_out[3] = (float)((ctx->tacc[2] - ctx->tacc[5]) / n);
+    ms_out[4] = (float)(ctx->tacc[3] / n);
+    ms_out[5] = (float)(ctx->tacc[4] / n);
     if (steps_out) *steps_out = ctx->tcount;
     return 0;
 }

@@ -117,6 +117,21 @@ class Engine:
         check(self.lib.kge_ctx_get_timing(self._h, out, C.byref(n)))
         return dict(zip(("emit", "fwd_bwd", "reduce_apply", "spans", "sort_after_emit"), [float(x) for x in out])), int(n.value)
 
+    def get_timing_ex(self):
+        """like get_timing with the wait for the sort split off the level-1 reduction kernel"""
+        out = (C.c_float * 6)()
+        n = C.c_int()
+        check(self.lib.kge_ctx_get_timing_ex(self._h, out, 6, C.byref(n)))
+        return dict(zip(("emit", "fwd_bwd", "sort_wait", "reduce_apply", "spans", "sort_after_emit"), [float(x) for x in out])), int(n.value)
+
+    def sort_entries(self, entries, n_keys: int, algo: int = 0):
+        """test hook: entries = int64 CUDA tensor of (key << 32 | slot); returns them sorted by key, equal keys in input order"""
+        assert entries.is_cuda and entries.dtype == torch.int64 and entries.is_contiguous()
+        out = torch.empty_like(entries)
+        check(self.lib.kge_sort_entries(self._h, entries.data_ptr(), entries.numel(), int(n_keys), int(algo), out.data_ptr(), _stream()))
+        self.launches += 3
+        return out
+
     def workspace_bytes(self) -> int:
         return int(self.lib.kge_ctx_workspace_bytes(self._h))
 

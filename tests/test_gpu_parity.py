@@ -541,3 +541,48 @@ def test_tc_ranks_vs_fp32_sweep_and_oracle(engine, model, k, E, T):
     so_f = _rank_gpu(engine, model, k, ent, rel, test, filt, "s,o", "worst", tc=True)
     so_u = _rank_gpu(engine, model, k, ent, rel, test, None, "s,o", "worst", tc=True)
     assert np.all(so_f <= so_u) and so_f.min() >= 1 and so_u.min() >= 2 and so_u.max() <= E + 1
+
+
+# ------------------------------------------------------------------ the sort in front of the segmented reduction
+def _entries(rng, n, n_keys, zipf):
+    if zipf:
+        w = 1.0 / np.arange(1, n_keys + 1) ** 1.1
+        keys = rng.choice(n_keys, size=n, p=w / w.sum())
+    else:
+        keys = rng.integers(0, n_keys, n)
+    slots = np.arange(n, dtype=np.int64) | (rng.integers(0, 4, n).astype(np.int64) << 30)  # slot id + the two side bits
+    return (keys.astype(np.int64) << 32) | slots
+
+
+@pytest.mark.parametrize("n,n_keys,zipf", [(1, 1, False), (31, 7, False), (512, 100, True), (513, 100, True), (97796, 14778, True),
+                                           (97796, 14778, False), (55276, 14778, True), (262144, 2000, True), (40000, 32768, False),
+                                           (5000, 1, False)])
+def test_counting_sort_equals_stable_radix_sort(engine, n, n_keys, zipf):
+    """kge_sort_small.cu (one-pass counting sort of small batches over small key ranges) against cub's stable radix sort and
+    against a stable host sort: equal keys keep their input order, bit for bit.  Run twice: its count matrix must be left
+    all-zero for the next sort."""
+    rng = np.random.default_rng(n + n_keys)
+    for rep in range(2):
+        e = _entries(rng, n, n_keys, zipf)
+        d = torch.from_numpy(e).cuda()
+        want = e[np.argsort(e >> 32, kind="stable")]
+        got_radix = engine.sort_entries(d, n_keys, algo=0).cpu().numpy()
+        got_count = engine.sort_entries(d, n_keys, algo=1).cpu().numpy()
+        np.testing.assert_array_equal(got_radix, want)
+        np.testing.assert_array_equal(got_count, want)
+
+
+def test_counting_sort_sizes_in_sequence_and_out_of_range(engine):
+    """different shapes through the same context (the count matrix is re-laid-out, still all-zero), then a size outside the
+    counting sort's range: refused loudly by the hook, routed to the radix sort by the train step."""
+    rng = np.random.default_rng(5)
+    for n, n_keys in [(3000, 900), (70000, 14000), (100, 32768), (262144, 1500), (3000, 900)]:
+        e = _entries(rng, n, n_keys, True)
+        got = engine.sort_entries(torch.from_numpy(e).cuda(), n_keys, algo=1).cpu().numpy()
+        np.testing.assert_array_equal(got, e[np.argsort(e >> 32, kind="stable")])
+    e = _entries(rng, 1000, 40000, False)
+    from emgraph_b200._lib import KgeError
+    with pytest.raises(KgeError):
+        engine.sort_entries(torch.from_numpy(e).cuda(), 40000, algo=1)
+    got = engine.sort_entries(torch.from_numpy(e).cuda(), 40000, algo=0).cpu().numpy()
+    np.testing.assert_array_equal(got, e[np.argsort(e >> 32, kind="stable")])

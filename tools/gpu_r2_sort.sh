@@ -1,0 +1,26 @@
+#!/bin/bash
+# round 2: counting sort for small batches (kge_sort_small.cu) -- its tests first (short timeout: new synchronisation
+# code), the GPU suite, A/B lines against the radix sort, launch list.  usage: gpu_r2_sort.sh TAG
+T=${1:-r2u}; O=gpurun_out; mkdir -p $O
+( timeout 180 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "counting_sort" 2>&1 | tail -15 ) > $O/${T}_pytest_sort.log
+tail -4 $O/${T}_pytest_sort.log
+if ! grep -q " passed" $O/${T}_pytest_sort.log || grep -q "failed\|error" $O/${T}_pytest_sort.log; then echo "SORT TESTS FAILED"; cat $O/${T}_pytest_sort.log; exit 1; fi
+( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > $O/${T}_pytest.log
+tail -3 $O/${T}_pytest.log
+for wl in cfg3 cfg1 cfg2 cfg4; do
+  for kv in "KGE_SMALL_SORT=0" "KGE_SMALL_SORT=1" "KGE_SMALL_SORT=1 KGE_FWD_MAXCTAS=4"; do
+    tag=$(echo $kv | tr ' =' '__')
+    env $kv timeout 200 python bench.py --workload $wl --steps 20 --warmup 5 --no-cpu --no-rank --no-sub > $O/${T}_ab_${wl}_${tag}.json 2> $O/${T}_ab_${wl}_${tag}.err
+  done
+done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches.csv \
+  python bench.py --steps 3 --warmup 3 --no-cpu --no-rank --no-sub > $O/${T}_ncu_bench.log 2>&1
+python - <<PY
+import glob, json
+for f in sorted(glob.glob("$O/${T}_ab_*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print("%-52s flushed %.4f warm %.4f e2e %.4f" % (f.split("/")[-1], d["ms_per_step"], d["ms_per_step_warm"], d["e2e"]["ms_per_step"]), {k: round(v, 4) for k, v in d["roofline"]["phases_ms"].items()}, round(d["roofline"]["frac"], 3))
+    except Exception as e:
+        print(f, "ERR", e, open(f.replace(".json", ".err")).read()[-400:])
+PY
