@@ -181,10 +181,11 @@ int kge_small_sort(kge_ctx* ctx, const uint64_t* in, int64_t n_items, int64_t n_
     if (ctx->ss_aux.reserve(aux_bytes)) return -2;
     if (ctx->ss_aux.p != a_before) KGE_CUDA_CHECK(cudaMemsetAsync(ctx->ss_aux.p, 0, ctx->ss_aux.cap, st));
     uint32_t* H = ctx->ss_hist.as<uint32_t>();
-    uint32_t* key_first = ctx->ss_aux.as<uint32_t>();
+    // the ticket sits at a FIXED place (word 0): every sort leaves it zero, and the arrays behind it move with the key count
+    unsigned int* ticket = ctx->ss_aux.as<unsigned int>();
+    uint32_t* key_first = ctx->ss_aux.as<uint32_t>() + 32;
     uint32_t* cta_first = key_first + nk;
     uint32_t* cta_total = cta_first + n_ctas_scan;
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(cta_total + n_ctas_scan);
     const int warps_per_cta = 8;
     const unsigned seg_ctas = (unsigned)((n_segs + warps_per_cta - 1) / warps_per_cta);
     kge_ss_count_kernel<<<seg_ctas, warps_per_cta * 32, 0, st>>>(in, n, nk, H);
