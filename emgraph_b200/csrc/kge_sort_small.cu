@@ -13,12 +13,15 @@
 //   1. count    a warp owns a SEGMENT of KGE_SS_SEG consecutive entries (input order = slot order); H[segment][key] += 1
 //               (fire-and-forget reductions; H is a dense uint32 matrix, <= 16 MB, all-zero between sorts)
 //   2. scan     per key, the exclusive prefix of its counts over the segments (written back in place where the count is
-//               non-zero) and the key's total; totals are scanned inside the CTA (128 keys) and the CTA sums by the last
+//               non-zero) and the key's total; totals are scanned inside the CTA (32 keys) and the CTA sums by the last
 //               CTA to finish (ticket), giving every key its first output position
 //   3. scatter  each warp walks its segment again, 32 entries at a time: lanes with equal keys find each other with
-//               match.any, the lowest one takes `count` positions from H[segment][key] (atomic fetch-add), lane rank
-//               inside the group keeps the input order: position = first(key) + prefix(segment, key) + rank.  The
-//               warp then zeroes the H entries it touched, so H is all-zero again without a memset.
+//               match.any, the lowest one looks up how many entries of the key the segment has shown so far in a per-warp
+//               shared-memory table (open addressing; no memory round trip between two steps), lane rank inside the group
+//               keeps the input order: position = first(key) + prefix(segment, key) + seen(key) + rank.  Every load of the
+//               walk is issued before it starts.  The warp then zeroes the H entries it touched, so H is all-zero again
+//               without a memset.
+// The three kernels are chains of ~2, ~3 and ~3 dependent memory round trips.
 // Equal keys keep their input order (segment order, then order inside the segment): the output is bit-identical to the
 // stable radix sort, and everything downstream (summation order of the reduction) is unchanged.
 #include "kge_common.cuh"
@@ -27,8 +30,8 @@
 #define KGE_SS_MAX_KEYS 32768
 #define KGE_SS_MAX_ITEMS (1 << 18)
 #define KGE_SS_MAX_H_BYTES ((size_t)16 << 20)
-#define KGE_SS_SCAN_KEYS 128    // keys per CTA of the scan kernel
-#define KGE_SS_SCAN_GROUPS 4    // segment groups per CTA of the scan kernel
+#define KGE_SS_SCAN_KEYS 32     // keys per CTA of the scan kernel
+#define KGE_SS_SCAN_GROUPS 8    // segment groups per CTA of the scan kernel
 
 __global__ void __launch_bounds__(256) kge_ss_count_kernel(const uint64_t* __restrict__ in, int n, int n_keys, uint32_t* __restrict__ H) {
     const int lane = threadIdx.x & 31;
@@ -43,12 +46,13 @@ __global__ void __launch_bounds__(256) kge_ss_count_kernel(const uint64_t* __res
     }
 }
 
-// grid = ceil(n_keys / 128) CTAs of 512 threads: thread (g, kk) sums segment group g of key kk
+// grid = ceil(n_keys / 32) CTAs of 256 threads: warp g of a CTA sums segment group g (of 8) for the CTA's 32 keys, lane =
+// key.  All of a thread's loads are independent (a few batches of 16 in flight); the second walk over the same addresses,
+// which writes the prefixes, is served by L1.
 __global__ void __launch_bounds__(KGE_SS_SCAN_KEYS * KGE_SS_SCAN_GROUPS)
 kge_ss_scan_kernel(uint32_t* __restrict__ H, int n_segs, int n_keys, uint32_t* __restrict__ key_first, uint32_t* __restrict__ cta_first,
                    uint32_t* __restrict__ cta_total, unsigned int* __restrict__ ticket) {
     __shared__ uint32_t part[KGE_SS_SCAN_GROUPS][KGE_SS_SCAN_KEYS];
-    __shared__ uint32_t wsum[KGE_SS_SCAN_KEYS / 32];
     __shared__ bool last;
     const int kk = threadIdx.x % KGE_SS_SCAN_KEYS, g = threadIdx.x / KGE_SS_SCAN_KEYS;
     const int key = blockIdx.x * KGE_SS_SCAN_KEYS + kk;
@@ -56,7 +60,7 @@ kge_ss_scan_kernel(uint32_t* __restrict__ H, int n_segs, int n_keys, uint32_t* _
     const int s0 = min(g * per, n_segs), s1 = min(s0 + per, n_segs);
     uint32_t sum = 0;
     if (key < n_keys) {
-#pragma unroll 8
+#pragma unroll 16
         for (int s = s0; s < s1; ++s) sum += H[(size_t)s * n_keys + key];
     }
     part[g][kk] = sum;
@@ -65,40 +69,37 @@ kge_ss_scan_kernel(uint32_t* __restrict__ H, int n_segs, int n_keys, uint32_t* _
     uint32_t run = 0;
     for (int q = 0; q < g; ++q) run += part[q][kk];
     if (key < n_keys && sum != 0) {
-#pragma unroll 8
+#pragma unroll 16
         for (int s = s0; s < s1; ++s) {
             const uint32_t c = H[(size_t)s * n_keys + key];
             if (c != 0) H[(size_t)s * n_keys + key] = run;
             run += c;
         }
     }
-    // first output position of every key: scan of the totals inside the CTA; the CTA's own offset is added by the scatter
+    // first output position of every key: scan of the totals of the CTA's 32 keys (warp 0); the CTA's own offset is added
+    // by the scatter
+    last = false;
+    __syncthreads();
     if (g == 0) {
         uint32_t tot = 0;
 #pragma unroll
         for (int q = 0; q < KGE_SS_SCAN_GROUPS; ++q) tot += part[q][kk];
-        const int lane = kk & 31, wid = kk >> 5;
         uint32_t incl = tot;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += up;
+            if (kk >= d) incl += up;
         }
-        if (lane == 31) wsum[wid] = incl;
-        // only the first KGE_SS_SCAN_KEYS threads (whole warps) are in this branch: a named barrier over them
-        asm volatile("bar.sync 1, %0;" ::"n"(KGE_SS_SCAN_KEYS));
-        uint32_t off = 0;
-        for (int q = 0; q < wid; ++q) off += wsum[q];
-        if (key < n_keys) key_first[key] = off + incl - tot;
+        if (key < n_keys) key_first[key] = incl - tot;
         if (kk == KGE_SS_SCAN_KEYS - 1) {
-            cta_total[blockIdx.x] = off + incl;
+            cta_total[blockIdx.x] = incl;
             __threadfence();
             last = atomicAdd(ticket, 1u) == gridDim.x - 1;
         }
     }
     __syncthreads();
     if (last && threadIdx.x < 32) {
-        // the last CTA to finish: exclusive scan of the CTA totals (<= 256 of them), one warp
+        // the last CTA to finish: exclusive scan of the CTA totals (<= 1024 of them), one warp
         __threadfence();
         const int lane = threadIdx.x;
         uint32_t carry = 0;
@@ -118,38 +119,70 @@ kge_ss_scan_kernel(uint32_t* __restrict__ H, int n_segs, int n_keys, uint32_t* _
     }
 }
 
-__global__ void __launch_bounds__(256) kge_ss_scatter_kernel(const uint64_t* __restrict__ in, int n, int n_keys, uint32_t* __restrict__ H,
+// per-warp table of (key + 1) << 16 | count for the keys of one segment: open addressing, linear probing; only the lowest
+// lane of every group of equal keys touches it, groups of one step hold different keys
+#define KGE_SS_TBL 1024
+__device__ __forceinline__ uint32_t ss_take(uint32_t* tbl, uint32_t key, uint32_t cnt) {
+    const uint32_t tag = (key + 1u) << 16;
+    uint32_t h = (key * 0x9E3779B1u) >> 22;  // 10 bits
+    for (;;) {
+        uint32_t cur = tbl[h];
+        if (cur == 0u) cur = atomicCAS(tbl + h, 0u, tag), cur = cur == 0u ? tag : cur;
+        if ((cur & 0xffff0000u) == tag) break;
+        h = (h + 1u) & (KGE_SS_TBL - 1u);
+    }
+    return atomicAdd(tbl + h, cnt) & 0xffffu;  // entries of this key seen in earlier steps of the segment (<= 512)
+}
+
+#define KGE_SS_SCATTER_WARPS 4  // 128 threads x 80 registers, 16 KB of tables: fits beside three forward/backward CTAs
+__global__ void __launch_bounds__(KGE_SS_SCATTER_WARPS * 32) kge_ss_scatter_kernel(const uint64_t* __restrict__ in, int n, int n_keys, uint32_t* __restrict__ H,
                                                              const uint32_t* __restrict__ key_first, const uint32_t* __restrict__ cta_first,
                                                              uint64_t* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t tbl_all[KGE_SS_SCATTER_WARPS][KGE_SS_TBL];
+    constexpr int NIT = KGE_SS_SEG / 32;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int seg = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int base = seg * KGE_SS_SEG;
-    if (base >= n) return;  // whole warps leave together
+    if (base >= n) return;  // whole warps leave together; no CTA-wide barrier below
+    uint32_t* tbl = tbl_all[wib];
+#pragma unroll
+    for (int i = 0; i < KGE_SS_TBL / 32; ++i) tbl[lane + 32 * i] = 0u;
     uint32_t* row = H + (size_t)seg * n_keys;
     const unsigned lt = (1u << lane) - 1u;
-    uint64_t e_next = base + lane < n ? in[base + lane] : 0ull;
-    for (int it = 0; it < KGE_SS_SEG / 32; ++it) {
+    // everything that comes from memory is independent of the ranks: all of it in flight before the walk
+    uint64_t e[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int idx = base + it * 32 + lane;
+        e[it] = idx < n ? in[idx] : 0ull;
+    }
+    uint32_t pos[NIT];  // first position of the key + entries of the key in earlier segments
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int idx = base + it * 32 + lane;
+        const uint32_t key = (uint32_t)(e[it] >> 32);
+        pos[it] = idx < n ? cta_first[key / KGE_SS_SCAN_KEYS] + key_first[key] + row[key] : 0u;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
         const int idx = base + it * 32 + lane;
         const bool valid = idx < n;
-        const uint64_t e = e_next;
-        const int idx_n = idx + 32;
-        e_next = (it + 1 < KGE_SS_SEG / 32 && idx_n < n) ? in[idx_n] : 0ull;  // next group's entries: independent of the counters
-        const uint32_t key = (uint32_t)(e >> 32);
+        const uint32_t key = (uint32_t)(e[it] >> 32);
         // lanes past the end get keys of their own, so they never join a group
         const unsigned peers = __match_any_sync(0xffffffffu, valid ? key : (0x80000000u | (uint32_t)lane));
         const int leader = __ffs(peers) - 1;
-        const uint32_t rank = (uint32_t)__popc(peers & lt);
-        uint32_t first = 0, taken = 0;
-        if (valid) first = cta_first[key / KGE_SS_SCAN_KEYS] + key_first[key];
-        if (valid && lane == leader) taken = atomicAdd(row + key, (uint32_t)__popc(peers));
+        uint32_t taken = 0;
+        if (valid && lane == leader) taken = ss_take(tbl, key, (uint32_t)__popc(peers));
         taken = __shfl_sync(0xffffffffu, taken, leader);
-        if (valid) out[first + taken + rank] = e;
+        if (valid) out[pos[it] + taken + (uint32_t)__popc(peers & lt)] = e[it];
+        __syncwarp();  // the table updates of this step are visible to the next one
     }
-    // leave H all-zero: the entries this segment touched (plain stores behind the atomics of the same warp)
-    __syncwarp();
-    for (int it = 0; it < KGE_SS_SEG / 32; ++it) {
+    // leave H all-zero: the entries this segment touched (every read of them is behind us)
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
         const int idx = base + it * 32 + lane;
-        if (idx < n) row[(uint32_t)(in[idx] >> 32)] = 0u;
+        if (idx < n) row[(uint32_t)(e[it] >> 32)] = 0u;
     }
 }
 
@@ -190,7 +223,8 @@ int kge_small_sort(kge_ctx* ctx, const uint64_t* in, int64_t n_items, int64_t n_
     const unsigned seg_ctas = (unsigned)((n_segs + warps_per_cta - 1) / warps_per_cta);
     kge_ss_count_kernel<<<seg_ctas, warps_per_cta * 32, 0, st>>>(in, n, nk, H);
     kge_ss_scan_kernel<<<n_ctas_scan, KGE_SS_SCAN_KEYS * KGE_SS_SCAN_GROUPS, 0, st>>>(H, n_segs, nk, key_first, cta_first, cta_total, ticket);
-    kge_ss_scatter_kernel<<<seg_ctas, warps_per_cta * 32, 0, st>>>(in, n, nk, H, key_first, cta_first, out);
+    kge_ss_scatter_kernel<<<(unsigned)((n_segs + KGE_SS_SCATTER_WARPS - 1) / KGE_SS_SCATTER_WARPS), KGE_SS_SCATTER_WARPS * 32, 0, st>>>(
+        in, n, nk, H, key_first, cta_first, out);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
