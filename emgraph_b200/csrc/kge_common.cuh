@@ -84,7 +84,7 @@ struct kge_ctx {
     // training workspace
     KgeBuf sort_tmp;
     KgeBuf loss_scr, pos_off, p2p_counter;
-    KgeBuf ss_hist, ss_aux;  // kge_sort_small.cu: segment x key count matrix (all-zero between sorts), key / CTA offsets + ticket
+    KgeBuf ss_hist, ss_aux;  // kge_sort_small.cu: pass-1 output; grid barrier words + per-tile digit histograms
     KgeBuf repl, keep, grad_rows, loss_part, neg_scores, partial, span_head, reg_partial, touched;
     KgeBuf ks_in, ks_sel, ks_sorted, sel_flags, sel_count;
     // second set of the per-step corruption / sort-key buffers {repl, keep, ks_in, ks_sorted}: a pipelined step

@@ -1207,7 +1207,7 @@ static int sort_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* pack
     if (ctx->partial.reserve((size_t)2 * n_chunks * K * sizeof(float))) return -2;
     if (ctx->span_head.reserve((size_t)(2 * n_chunks + 2) * sizeof(int32_t))) return -2;
     int64_t E = a->ent.rows;
-    // small batch over a small key range: one-pass stable counting sort with CTAs small enough to run beside the
+    // small batch over a small key range: single-launch stable radix sort with CTAs small enough to run beside the
     // forward/backward kernel (kge_sort_small.cu); same output, bit for bit
     if (kge_small_sort_ok(n_items, E + a->R)) return kge_small_sort(ctx, packed_in, n_items, E + a->R, ctx->ks_sorted.as<uint64_t>(), st);
     int end_bit = 1;
@@ -1470,14 +1470,14 @@ extern "C" int kge_ctx_get_timing(kge_ctx* ctx, float* ms_out5, int* steps_out) 
 }
 
 // test hook: the sort of the (key << 32 | slot) entries alone.  algo 0: cub::DeviceRadixSort on the key bits (stable); 1: the
-// counting sort of kge_sort_small.cu (fails when the size is outside its range)
+// single-launch sort of kge_sort_small.cu (fails when the size is outside its range)
 extern "C" int kge_sort_entries(kge_ctx* ctx, const uint64_t* in, int64_t n, int64_t n_keys, int algo, uint64_t* out, void* stream) {
     KGE_REQUIRE(ctx != nullptr && in != nullptr && out != nullptr && n >= 0 && n_keys > 0, "kge_sort_entries: bad argument");
     KGE_REQUIRE(n <= (int64_t)KGE_SLOT_MASK, "kge_sort_entries: too many entries");
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (algo == 1) {
-        KGE_REQUIRE(kge_small_sort_ok(n, n_keys), "kge_sort_entries: %lld entries / %lld keys is outside the counting sort's range",
+        KGE_REQUIRE(kge_small_sort_ok(n, n_keys), "kge_sort_entries: %lld entries / %lld keys is outside the small sort's range",
                     (long long)n, (long long)n_keys);
         return kge_small_sort(ctx, in, n, n_keys, out, st);
     }

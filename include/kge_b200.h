@@ -152,8 +152,8 @@ int kge_ctx_get_timing(kge_ctx* ctx, float* ms_out5, int* steps_out);
  * level-1 reduction kernel alone, span/hub reduction, end of the sort measured from the end of emit} */
 int kge_ctx_get_timing_ex(kge_ctx* ctx, float* ms_out, int n_out, int* steps_out);
 /* Test hook: stable sort of n (key << 32 | slot) entries by key (every key < n_keys), the order the segmented reduction
- * walks.  algo 0: radix sort on the key bits; 1: the one-pass counting sort used for small batches over small key ranges
- * (csrc/kge_sort_small.cu; error when the size is outside its range).  Both give the same output. */
+ * walks.  algo 0: radix sort on the key bits; 1: the single-launch two-pass radix sort used for small batches over small key
+ * ranges (csrc/kge_sort_small.cu; error when the size is outside its range).  Both give the same output. */
 int kge_sort_entries(kge_ctx* ctx, const uint64_t* in, int64_t n, int64_t n_keys, int algo, uint64_t* out, void* stream);
 /* bytes of device workspace currently held by the ctx */
 int64_t kge_ctx_workspace_bytes(kge_ctx* ctx);

@@ -556,11 +556,11 @@ def _entries(rng, n, n_keys, zipf):
 
 @pytest.mark.parametrize("n,n_keys,zipf", [(1, 1, False), (31, 7, False), (512, 100, True), (513, 100, True), (97796, 14778, True),
                                            (97796, 14778, False), (55276, 14778, True), (262144, 2000, True), (40000, 32768, False),
-                                           (5000, 1, False)])
+                                           (5000, 1, False), (2048, 65536, False), (2049, 300, True), (200000, 65536, True)])
 def test_counting_sort_equals_stable_radix_sort(engine, n, n_keys, zipf):
-    """kge_sort_small.cu (one-pass counting sort of small batches over small key ranges) against cub's stable radix sort and
-    against a stable host sort: equal keys keep their input order, bit for bit.  Run twice: its count matrix must be left
-    all-zero for the next sort."""
+    """kge_sort_small.cu (single-launch two-pass radix sort of small batches over small key ranges) against cub's stable
+    radix sort and against a stable host sort: equal keys keep their input order, bit for bit.  Run twice: its grid barrier
+    must be left ready for the next launch."""
     rng = np.random.default_rng(n + n_keys)
     for rep in range(2):
         e = _entries(rng, n, n_keys, zipf)
@@ -573,16 +573,18 @@ def test_counting_sort_equals_stable_radix_sort(engine, n, n_keys, zipf):
 
 
 def test_counting_sort_sizes_in_sequence_and_out_of_range(engine):
-    """different shapes through the same context (the count matrix is re-laid-out, still all-zero), then a size outside the
-    counting sort's range: refused loudly by the hook, routed to the radix sort by the train step."""
+    """different shapes through the same context (different grids on the same barrier words), then a size outside the
+    small sort's range: refused loudly by the hook, routed to the radix sort by the train step."""
     rng = np.random.default_rng(5)
     for n, n_keys in [(3000, 900), (70000, 14000), (100, 32768), (262144, 1500), (3000, 900)]:
         e = _entries(rng, n, n_keys, True)
         got = engine.sort_entries(torch.from_numpy(e).cuda(), n_keys, algo=1).cpu().numpy()
         np.testing.assert_array_equal(got, e[np.argsort(e >> 32, kind="stable")])
-    e = _entries(rng, 1000, 40000, False)
+    e = _entries(rng, 1000, 70000, False)
     from emgraph_b200._lib import KgeError
     with pytest.raises(KgeError):
-        engine.sort_entries(torch.from_numpy(e).cuda(), 40000, algo=1)
-    got = engine.sort_entries(torch.from_numpy(e).cuda(), 40000, algo=0).cpu().numpy()
+        engine.sort_entries(torch.from_numpy(e).cuda(), 70000, algo=1)
+    with pytest.raises(KgeError):
+        engine.sort_entries(torch.from_numpy(_entries(rng, 300000, 900, True)).cuda(), 900, algo=1)
+    got = engine.sort_entries(torch.from_numpy(e).cuda(), 70000, algo=0).cpu().numpy()
     np.testing.assert_array_equal(got, e[np.argsort(e >> 32, kind="stable")])
