@@ -16,9 +16,9 @@
 //   rank     warp w walks its 256 consecutive entries 32 at a time; lanes with equal digits find each other with match.any,
 //            the lowest one bumps the warp's private counter of that digit, lane rank inside the group keeps the input
 //            order.  The counters of the 8 warps are then scanned per digit (warp order = input order) and their sums
-//            published as the tile's digit histogram G[digit][tile].
+//            published as the tile's digit histogram G[tile][digit].
 //   barrier  every tile's histogram is visible.
-//   place    thread d adds up G[d][tiles before mine] and G[d][all tiles], the totals are scanned over the digits inside the
+//   place    thread d adds up G[tiles before mine][d] and G[all tiles][d], the totals are scanned over the digits inside the
 //            CTA: first position of (digit, tile).  Each entry goes to first(digit, tile) + entries of the digit in earlier
 //            warps + its rank in the warp.
 // Equal digits keep their input order in both passes, so equal keys keep their input order: the output is bit-identical
@@ -33,26 +33,25 @@
 #define KGE_SS_MAX_TILES 128
 #define KGE_SS_MAX_KEYS 65536
 
-// grid-wide barrier for CTAs that are all resident (<= 128 small CTAs on 148 SMs): arrival counter + generation word.
-// Self-resetting, so the two words stay {0, g} between launches; gen_seen is the generation this CTA read before it arrived.
-__device__ __forceinline__ void ss_grid_barrier(unsigned int* bar, unsigned int& gen_seen) {
+// grid-wide barrier for CTAs that are all resident (<= 128 small CTAs on 148 SMs).  bar[0] counts arrivals and never goes
+// back; bar[1] holds the value it had when this launch began (the last arrival of a launch's final barrier stores it for
+// the next launch).  Barrier k of a launch is complete when the counter reaches base + k * gridDim.x: an arrival is one
+// fire-and-forget reduction, a waiter sees the last one a single L2 round trip later.
+__device__ __forceinline__ void ss_grid_barrier(unsigned int* bar, unsigned int target, bool final_one) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned int arrived = atomicAdd(bar, 1u);
-        if (arrived == gridDim.x - 1) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
+        if (final_one) {
+            if (atomicAdd(bar, 1u) + 1u == target) bar[1] = target;
         } else {
-            unsigned long long spins = 0;
-            while (((volatile unsigned int*)bar)[1] == gen_seen) {
-                if (++spins > (1ull << 28)) __trap();  // seconds: a CTA of this grid never ran -- fail loudly instead of hanging
-            }
+            atomicAdd(bar, 1u);
+        }
+        unsigned long long spins = 0;
+        while ((int)(((volatile unsigned int*)bar)[0] - target) < 0) {
+            if (++spins > (1ull << 28)) __trap();  // seconds: a CTA of this grid never ran -- fail loudly instead of hanging
         }
         __threadfence();
     }
-    gen_seen += 1;
     __syncthreads();
 }
 
@@ -62,8 +61,8 @@ __device__ __forceinline__ uint64_t ss_ldcg(const uint64_t* p) {
 
 // one pass: entries of this tile from src (stable) to dst by digit (key >> shift) & 255
 __device__ __forceinline__ void ss_pass(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, int n, int shift, bool src_is_input,
-                                        uint32_t* __restrict__ G, unsigned int* bar, unsigned int& gen_seen, uint32_t (*cntw)[256],
-                                        uint32_t* first, uint32_t* wsum) {
+                                        uint32_t* __restrict__ G, unsigned int* bar, unsigned int target, bool final_one,
+                                        uint32_t (*cntw)[256], uint32_t* first, uint32_t* wsum) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n_tiles = gridDim.x, tile = blockIdx.x;
     const int base = tile * KGE_SS_TILE + w * KGE_SS_PER_WARP;
@@ -105,17 +104,16 @@ __device__ __forceinline__ void ss_pass(const uint64_t* __restrict__ src, uint64
             cntw[q][d] = run;
             run += c;
         }
-        __stcg(G + (size_t)d * n_tiles + tile, run);
+        __stcg(G + (size_t)tile * 256 + d, run);  // G[tile][digit]: written and read 128 bytes per warp
     }
-    ss_grid_barrier(bar, gen_seen);
+    ss_grid_barrier(bar, target, final_one);
     // ---- place: first output position of (digit, this tile)
     {
         const int d = threadIdx.x;
         uint32_t below = 0, total = 0;
-        const uint32_t* row = G + (size_t)d * n_tiles;
-#pragma unroll 8
+#pragma unroll 16
         for (int t = 0; t < n_tiles; ++t) {
-            const uint32_t c = __ldcg(row + t);
+            const uint32_t c = __ldcg(G + (size_t)t * 256 + d);
             total += c;
             below += t < tile ? c : 0u;
         }
@@ -149,13 +147,13 @@ __global__ void __launch_bounds__(KGE_SS_THREADS, 4) kge_small_sort_kernel(const
     __shared__ uint32_t cntw[KGE_SS_WARPS][256];
     __shared__ uint32_t first[256];
     __shared__ uint32_t wsum[KGE_SS_WARPS];
-    __shared__ unsigned int gen0;
-    if (threadIdx.x == 0) gen0 = ((volatile unsigned int*)bar)[1];  // no barrier of this launch can complete before this CTA arrives
+    __shared__ unsigned int base0;
+    if (threadIdx.x == 0) base0 = ((volatile unsigned int*)bar)[1];  // stable until this launch's final barrier completes
     __syncthreads();
-    unsigned int gen_seen = gen0;
-    ss_pass(in, tmp, n, 32, true, G, bar, gen_seen, cntw, first, wsum);
-    ss_grid_barrier(bar, gen_seen);  // every tile's entries are in tmp
-    ss_pass(tmp, out, n, 40, false, G + (size_t)256 * gridDim.x, bar, gen_seen, cntw, first, wsum);
+    const unsigned int base = base0, nt = gridDim.x;
+    ss_pass(in, tmp, n, 32, true, G, bar, base + nt, false, cntw, first, wsum);
+    ss_grid_barrier(bar, base + 2u * nt, false);  // every tile's entries are in tmp
+    ss_pass(tmp, out, n, 40, false, G + (size_t)256 * nt, bar, base + 3u * nt, true, cntw, first, wsum);
 }
 
 bool kge_small_sort_ok(int64_t n_items, int64_t n_keys) {
@@ -174,7 +172,7 @@ int kge_small_sort(kge_ctx* ctx, const uint64_t* in, int64_t n_items, int64_t n_
     KGE_REQUIRE(in != out, "kge_small_sort: in-place sort is not supported");
     const int n = (int)n_items;
     const int n_tiles = (n + KGE_SS_TILE - 1) / KGE_SS_TILE;
-    // aux: [0,2) barrier {count, generation} (zeroed once, self-resetting) | 64 words in: G[2 passes][256][n_tiles]
+    // aux: [0,2) barrier {arrivals, value at launch} (zeroed once) | 64 words in: G[2 passes][n_tiles][256]
     const size_t aux_bytes = (64 + (size_t)2 * 256 * KGE_SS_MAX_TILES) * sizeof(uint32_t);
     const void* a_before = ctx->ss_aux.p;
     if (ctx->ss_aux.reserve(aux_bytes)) return -2;

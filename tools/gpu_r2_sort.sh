@@ -8,14 +8,14 @@ if ! grep -q " passed" $O/${T}_pytest_sort.log || grep -q "failed\|error" $O/${T
 ( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > $O/${T}_pytest.log
 tail -3 $O/${T}_pytest.log
 for wl in cfg3 cfg1 cfg2; do
-  for kv in "KGE_SMALL_SORT=0" "KGE_SMALL_SORT=1" "KGE_SMALL_SORT=1 KGE_FWD_MAXCTAS=4"; do
+  for kv in "KGE_SMALL_SORT=0" "KGE_SMALL_SORT=1"; do
     tag=$(echo $kv | tr ' =' '__')
     env $kv timeout 200 python bench.py --workload $wl --steps 20 --warmup 5 --no-cpu --no-rank --no-sub > $O/${T}_ab_${wl}_${tag}.json 2> $O/${T}_ab_${wl}_${tag}.err
   done
 done
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'kge_ss|RadixSort|kge_emit|kge_fwd_bwd|kge_reduce|kge_span|kge_loss' -c 300 --csv --log-file $O/${T}_launches.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'kge_small_sort|RadixSort|kge_emit|kge_fwd_bwd|kge_reduce|kge_span|kge_loss' -c 300 --csv --log-file $O/${T}_launches.csv \
   python bench.py --steps 3 --warmup 3 --no-cpu --no-rank --no-sub > $O/${T}_ncu_bench.log 2>&1
-KGE_SMALL_SORT=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'kge_ss|RadixSort|kge_emit|kge_fwd_bwd|kge_reduce|kge_span|kge_loss' -c 300 --csv --log-file $O/${T}_launches_radix.csv \
+KGE_SMALL_SORT=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'kge_small_sort|RadixSort|kge_emit|kge_fwd_bwd|kge_reduce|kge_span|kge_loss' -c 300 --csv --log-file $O/${T}_launches_radix.csv \
   python bench.py --steps 3 --warmup 3 --no-cpu --no-rank --no-sub > $O/${T}_ncu_bench_radix.log 2>&1
 python - <<PY
 import glob, json
