@@ -33,7 +33,8 @@ struct ApplyParams {
     float* partial;        // [2*n_chunks][K]
     int32_t* span_list;    // chunk ids that start a run crossing chunk borders (unordered)
     int32_t* hub_list;     // the subset whose run covers more than KGE_SPAN_WARP_MAX chunks
-    int32_t* span_count;   // [2]: {#span heads, #hubs}, zeroed before the reduce kernel
+    int32_t* span_count;   // [2]: {#span heads, #hubs}: zero when the level-1 kernel starts (kge_span_apply_kernel re-zeroes them)
+    int32_t* span_ticket;  // CTAs of kge_span_apply_kernel that have read the counters
     int span_use_hubs;     // 1: kge_span_warp_kernel runs first and leaves only hub_list to kge_span_apply_kernel
     float* dbg_grad_ent;
     float* dbg_grad_rel;

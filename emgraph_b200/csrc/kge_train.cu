@@ -534,21 +534,27 @@ __global__ void __launch_bounds__(KGE_RA_WARPS * 32) kge_reduce_apply_staged_ker
     }
 }
 
-// last chunk whose first slot still carries `key` (32 chunks probed per round)
+// last chunk whose first slot still carries `key`.  Round 1 probes the next 32 chunks (nearly every span ends there); a hub
+// that goes on is finished by a 32-ary search over the rest of the sorted list -- "chunk c starts with key" is monotone in
+// c -- so the top hub of a Zipf graph (600 chunks at cfg3) costs 4 dependent loads instead of 19 (measured: this chain
+// was most of kge_span_apply_kernel's duration).
 __device__ __forceinline__ int64_t span_last_chunk(const ApplyParams& P, int64_t w, int32_t key, int64_t n_chunks, int lane) {
-    int64_t last = w;
-    for (;;) {
-        const int64_t c = last + 1 + lane;
+    {
+        const int64_t c = w + 1 + lane;
         const bool same = c < n_chunks && (int32_t)(P.ks[c * KGE_CH] >> 32) == key;
         const unsigned mk = __ballot_sync(0xffffffffu, same);
-        if (mk == 0xffffffffu) {
-            last += 32;
-            continue;
-        }
-        last += __ffs(~mk) - 1;
-        break;
+        if (mk != 0xffffffffu) return w + (__ffs(~mk) - 1);
     }
-    return last;
+    int64_t lo = w + 32, hi = n_chunks;  // chunk lo starts with key, chunk hi does not (or does not exist)
+    while (hi - lo > 1) {
+        const int64_t d = (hi - lo + 31) / 32;
+        const int64_t c = lo + (int64_t)(lane + 1) * d;
+        const bool same = c < hi && (int32_t)(P.ks[c * KGE_CH] >> 32) == key;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, same));  // a prefix of the lanes
+        lo += (int64_t)cnt * d;
+        hi = min(hi, lo + d);
+    }
+    return lo;
 }
 
 __device__ __forceinline__ const float* span_entry(const ApplyParams& P, int64_t w, int64_t e, int K) {
@@ -571,8 +577,16 @@ __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(App
     const int K = P.ent.K;
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
     // with the warp-per-run pass in front (dense batches) only the hubs it set aside are left for the CTAs
-    const int n_heads = P.span_use_hubs ? P.span_count[1] : P.span_count[0];
+    const int n_heads = ((volatile int32_t*)P.span_count)[P.span_use_hubs ? 1 : 0];  // read exactly once
     const int32_t* heads_list = P.span_use_hubs ? P.hub_list : P.span_list;
+    // This kernel is the last reader of the two counters: the last CTA to have read them zeroes them for the next step's
+    // reduction (a memset in front of the level-1 kernel was 2-3 us of every step's critical path)
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(P.span_ticket, 1) == (int)gridDim.x - 1) {
+        P.span_count[0] = 0;
+        P.span_count[1] = 0;
+        *P.span_ticket = 0;
+    }
     const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
     const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
     const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
@@ -1095,7 +1109,7 @@ template <int V, int NCA>
 static int launch_apply_nca(const ApplyParams& P, int tmode, int sm_count, cudaStream_t st, cudaEvent_t mid, cudaEvent_t pre) {
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
     dim3 grid((unsigned)((n_chunks + KGE_RA_WARPS - 1) / KGE_RA_WARPS)), block(KGE_RA_WARPS * 32);
-    KGE_CUDA_CHECK(cudaMemsetAsync(P.span_count, 0, 2 * sizeof(int32_t), st));
+    // P.span_count is zero here: zeroed when the buffer was allocated, and again by every kge_span_apply_kernel
     if (pre != nullptr) KGE_CUDA_CHECK(cudaEventRecord(pre, st));  // bench instrumentation: the level-1 kernel starts here
     bool staged = false;
     if constexpr (V == 4 && NCA > 0) {
@@ -1205,7 +1219,12 @@ static int sort_impl(kge_ctx* ctx, const kge_train_args* a, const uint64_t* pack
     const int64_t n_chunks = (n_items + KGE_CH - 1) / KGE_CH;
     if (ctx->ks_sorted.reserve((size_t)n_items * 8)) return -2;
     if (ctx->partial.reserve((size_t)2 * n_chunks * K * sizeof(float))) return -2;
-    if (ctx->span_head.reserve((size_t)(2 * n_chunks + 2) * sizeof(int32_t))) return -2;
+    {   // header {span heads, hubs, ticket, pad} + the two lists; the header is zeroed once per allocation (kge_span_apply_kernel
+        // leaves it zero) on the stream the sort runs on, which the reduction waits for
+        const void* before = ctx->span_head.p;
+        if (ctx->span_head.reserve((size_t)(2 * n_chunks + 4) * sizeof(int32_t))) return -2;
+        if (ctx->span_head.p != before) KGE_CUDA_CHECK(cudaMemsetAsync(ctx->span_head.p, 0, 4 * sizeof(int32_t), st));
+    }
     int64_t E = a->ent.rows;
     // small batch over a small key range: single-launch stable radix sort with CTAs small enough to run beside the
     // forward/backward kernel (kge_sort_small.cu); same output, bit for bit
@@ -1269,7 +1288,8 @@ static int reduce_impl(kge_ctx* ctx, const kge_train_args* a, int64_t n_items, c
     {
         const int64_t n_chunks = (n_items + KGE_CH - 1) / KGE_CH;
         P.span_count = ctx->span_head.as<int32_t>();
-        P.span_list = ctx->span_head.as<int32_t>() + 2;
+        P.span_ticket = ctx->span_head.as<int32_t>() + 2;
+        P.span_list = ctx->span_head.as<int32_t>() + 4;
         P.hub_list = P.span_list + n_chunks;
     }
     // dense batch (on average >= 8 slots per table row): most runs cross chunk borders -> thousands of short spans
