@@ -577,16 +577,18 @@ __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(App
     const int K = P.ent.K;
     const int64_t n_chunks = (P.n_keys + KGE_CH - 1) / KGE_CH;
     // with the warp-per-run pass in front (dense batches) only the hubs it set aside are left for the CTAs
-    const int n_heads = ((volatile int32_t*)P.span_count)[P.span_use_hubs ? 1 : 0];  // read exactly once
-    const int32_t* heads_list = P.span_use_hubs ? P.hub_list : P.span_list;
-    // This kernel is the last reader of the two counters: the last CTA to have read them zeroes them for the next step's
-    // reduction (a memset in front of the level-1 kernel was 2-3 us of every step's critical path)
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(P.span_ticket, 1) == (int)gridDim.x - 1) {
-        P.span_count[0] = 0;
-        P.span_count[1] = 0;
-        *P.span_ticket = 0;
+    // This kernel is the last reader of the two counters: the CTA that draws the last ticket -- every other CTA has read
+    // them by then -- zeroes them for the next step's reduction (a memset in front of the level-1 kernel was 2-3 us of
+    // every step's critical path).  The ticket's value is only looked at when the CTA is done: nobody waits for it here.
+    __shared__ int s_heads;
+    int ticket = 0;
+    if (threadIdx.x == 0) {
+        s_heads = ((volatile int32_t*)P.span_count)[P.span_use_hubs ? 1 : 0];
+        ticket = atomicAdd(P.span_ticket, 1);
     }
+    __syncthreads();
+    const int n_heads = s_heads;
+    const int32_t* heads_list = P.span_use_hubs ? P.hub_list : P.span_list;
     const bool reset = (P.flags & KGE_F_RESET_STATE) != 0;
     const bool no_update = (P.flags & KGE_F_NO_UPDATE) != 0;
     const bool need_m = !no_update && !reset && P.opt != KGE_OPT_SGD;
@@ -694,6 +696,11 @@ __global__ void __launch_bounds__(KGE_SPAN_WARPS * 32) kge_span_apply_kernel(App
             }
         }
         __syncthreads();
+    }
+    if (threadIdx.x == 0 && ticket == (int)gridDim.x - 1) {
+        P.span_count[0] = 0;
+        P.span_count[1] = 0;
+        *P.span_ticket = 0;
     }
 }
 
