@@ -4,7 +4,7 @@
 T=${1:-r2y}; O=gpurun_out; mkdir -p $O; S=/tmp/ncu_$T; mkdir -p $S
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 500 > $O/${T}_clocks.csv &
 SMI=$!
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'kge_fwd_bwd|kge_reduce_apply|kge_span' -s 12 -c 6 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'kge_fwd_bwd|kge_reduce_apply|kge_span|kge_small_sort' -s 16 -c 8 \
   -o $S/prof python bench.py --steps 3 --warmup 3 --no-cpu --no-rank --no-sub > $O/${T}_ncu_full.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'kge_rank_tc_kernel' -s 1 -c 1 \
   -o $S/prof_rank python bench.py --steps 3 --warmup 3 --no-cpu --no-sub --rank-steps 1 > $O/${T}_ncu_fullr.log 2>&1
@@ -15,15 +15,15 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'kge
 for n in prof prof_rank prof_cfg5 prof_dim; do
   ncu -i $S/$n.ncu-rep --page raw --csv > $O/${T}_${n}_raw.csv 2>/dev/null
 done
-ncu -i $S/prof.ncu-rep --page source --csv -k regex:'kge_reduce_apply_kernel' > $O/${T}_prof_reduce_source.csv 2>/dev/null
-ncu -i $S/prof.ncu-rep --page source --csv -k regex:'kge_fwd_bwd' > $O/${T}_prof_fwd_source.csv 2>/dev/null
+ncu -i $S/prof.ncu-rep --page source --csv -k regex:'kge_small_sort' > $O/${T}_prof_sort_source.csv 2>/dev/null
 python tools/ncu_traffic.py $T $O/traffic_session.json cfg3=$S/prof.ncu-rep cfg3=$S/prof_rank.ncu-rep cfg5=$S/prof_cfg5.ncu-rep cfg5w8=$S/prof_dim.ncu-rep > $O/${T}_traffic.log 2>&1
 cp $O/traffic_session.json $O/${T}_traffic.json
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/${T}_bench_default.json 2> $O/${T}_bench_default.err
 timeout 400 python bench.py --impl reference --steps 4 --warmup 1 > $O/${T}_bench_ref.json 2> $O/${T}_bench_ref.err
 kill $SMI
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/${T}_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'kge_|RadixSort|DeviceSelect' -c 400 --csv --log-file $O/${T}_launches.csv \
   python bench.py --steps 3 --warmup 3 --no-cpu --rank-steps 1 --no-sub > $O/${T}_ncu_bench.log 2>&1
+( timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 ) > $O/${T}_smoke.log; cat $O/${T}_smoke.log
 ls -la $O | tail -20; du -sh $O
 python - <<PY
 import json
