@@ -156,13 +156,29 @@ __global__ void __launch_bounds__(KGE_SS_THREADS, 4) kge_small_sort_kernel(const
     ss_pass(tmp, out, n, 40, false, G + (size_t)256 * nt, bar, base + 3u * nt, true, cntw, first, wsum);
 }
 
+// The grid barriers need every CTA of the launch resident at the same time: the grid is capped by what the device can hold
+// (148 SMs x 4 CTAs on a full B200 -- far above KGE_SS_MAX_TILES -- but a partitioned device may be much smaller)
+static int ss_max_resident_ctas() {
+    static int v = -1;
+    if (v < 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kge_small_sort_kernel, KGE_SS_THREADS, 0) != cudaSuccess)
+            v = 0;
+        else
+            v = sms * per_sm;
+    }
+    return v;
+}
+
 bool kge_small_sort_ok(int64_t n_items, int64_t n_keys) {
     static int on = -1;  // KGE_SMALL_SORT=0 keeps the radix sort (A/B)
     if (on < 0) {
         const char* e = getenv("KGE_SMALL_SORT");
         on = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
-    return on && n_items > 0 && n_items <= (int64_t)KGE_SS_MAX_TILES * KGE_SS_TILE && n_keys > 0 && n_keys <= KGE_SS_MAX_KEYS;
+    if (!on || n_items <= 0 || n_items > (int64_t)KGE_SS_MAX_TILES * KGE_SS_TILE || n_keys <= 0 || n_keys > KGE_SS_MAX_KEYS) return false;
+    return (n_items + KGE_SS_TILE - 1) / KGE_SS_TILE <= (int64_t)ss_max_resident_ctas();
 }
 
 // in: n_items entries, every key (high word) < n_keys <= 65536; out: the same entries ordered by key, equal keys in input order
