@@ -19,7 +19,8 @@
 int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ, int64_t T, const float* ent_local,
                       int64_t row_begin, int64_t row_end, const int32_t* test, const int32_t* pos_q,
                       const int32_t* excl_lo, const int32_t* excl_hi, const int32_t* sp_ent, const int32_t* po_ent,
-                      int side_mask, int32_t* counts, cudaStream_t st);
+                      int side_mask, int32_t* counts, const uint32_t* q_absmax, cudaStream_t st);
+bool kge_rank_tc_f16();
 
 // ------------------------------------------------------------------------------------------------
 // filter index
@@ -129,6 +130,8 @@ struct PrepParams {
     int32_t* pos_q;   // [T] quantised positive score
     int32_t* excl_lo; // [2T]
     int32_t* excl_hi; // [2T]
+    uint32_t* q_absmax;  // optional: bit pattern of the largest |q| over the swept sides (the fp16 split's operand scale)
+    int amax_mask;       // bit 0: object-sweep queries count, bit 1: subject-sweep queries
 };
 
 __global__ void kge_rank_prepare_kernel(PrepParams P) {
@@ -143,10 +146,13 @@ __global__ void kge_rank_prepare_kernel(PrepParams P) {
     float* qo = P.q + (size_t)t * K;
     float* qs = P.q + (size_t)(P.T + t) * K;
     float acc = 0.f;
+    float mo = 0.f, ms = 0.f;  // largest |qo|, |qs| of this lane
     const float hs = model == KGE_HOLE ? 2.0f / (float)k : 1.0f;
+    // the loads of four column steps are issued before their stores (the rows are read-only here); the sum keeps its order
     if (model == KGE_TRANSE_L1 || model == KGE_TRANSE_L2) {
+#pragma unroll 4
         for (int c = lane; c < K; c += 32) {
-            float sv = s[c], pv = p[c], ov = o[c];
+            float sv = __ldg(s + c), pv = __ldg(p + c), ov = __ldg(o + c);
             qo[c] = sv + pv;   // S_o[e] = -|| (s+p) - e ||
             qs[c] = ov - pv;   // S_s[e] = -|| e - (o-p) ||
             float u = sv + pv - ov;
@@ -155,25 +161,40 @@ __global__ void kge_rank_prepare_kernel(PrepParams P) {
         acc = warp_sum(acc);
         acc = model == KGE_TRANSE_L1 ? -acc : -sqrtf(acc);
     } else if (model == KGE_DISTMULT) {
+#pragma unroll 4
         for (int c = lane; c < K; c += 32) {
-            float sv = s[c], pv = p[c], ov = o[c];
-            qo[c] = sv * pv;
-            qs[c] = pv * ov;
+            float sv = __ldg(s + c), pv = __ldg(p + c), ov = __ldg(o + c);
+            const float a = sv * pv, b = pv * ov;
+            qo[c] = a;
+            qs[c] = b;
+            mo = fmaxf(mo, fabsf(a));
+            ms = fmaxf(ms, fabsf(b));
             acc = fmaf(sv * pv, ov, acc);
         }
         acc = warp_sum(acc);
     } else {
+#pragma unroll 2
         for (int c = lane; c < k; c += 32) {
-            float sr = s[c], si2 = s[c + k], pr = p[c], pim = p[c + k], orr = o[c], oim = o[c + k];
+            float sr = __ldg(s + c), si2 = __ldg(s + c + k), pr = __ldg(p + c), pim = __ldg(p + c + k), orr = __ldg(o + c),
+                  oim = __ldg(o + c + k);
             float a = pr * sr - pim * si2, b = pr * si2 + pim * sr;
-            qo[c] = hs * a;
-            qo[c + k] = hs * b;
-            qs[c] = hs * (pr * orr + pim * oim);
-            qs[c + k] = hs * (pr * oim - pim * orr);
+            const float q0 = hs * a, q1 = hs * b, q2 = hs * (pr * orr + pim * oim), q3 = hs * (pr * oim - pim * orr);
+            qo[c] = q0;
+            qo[c + k] = q1;
+            qs[c] = q2;
+            qs[c + k] = q3;
+            mo = fmaxf(mo, fmaxf(fabsf(q0), fabsf(q1)));
+            ms = fmaxf(ms, fmaxf(fabsf(q2), fabsf(q3)));
             acc = fmaf(a, orr, acc);
             acc = fmaf(b, oim, acc);
         }
         acc = hs * warp_sum(acc);
+    }
+    if (P.q_absmax != nullptr) {
+        float m = fmaxf((P.amax_mask & 1) ? mo : 0.f, (P.amax_mask & 2) ? ms : 0.f);
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
+        if (lane == 0 && m > 0.f) atomicMax(P.q_absmax, __float_as_uint(m));
     }
     if (lane == 0) P.pos_q[t] = quantise_score(apply_nl(P.nl, acc));
     if (lane < 2) {
@@ -761,6 +782,15 @@ static int rank_counts_impl(kge_ctx* ctx, int model, int k, const kge_table* ent
     pp.pos_q = ctx->pos_q.as<int32_t>();
     pp.excl_lo = ctx->excl_lo.as<int32_t>();
     pp.excl_hi = ctx->excl_hi.as<int32_t>();
+    pp.q_absmax = nullptr;
+    pp.amax_mask = side == KGE_RANK_O ? 1 : (side == KGE_RANK_S ? 2 : 3);
+    const bool tc_path = use_tensor_cores && !(model == KGE_TRANSE_L1 || model == KGE_TRANSE_L2);
+    if (tc_path && kge_rank_tc_f16() && row_end > row_begin) {
+        // the fp16 split scales the queries by a power of two taken from their largest magnitude: found here, while they are written
+        if (ctx->q_lo.reserve(2 * sizeof(uint32_t))) return -2;
+        KGE_CUDA_CHECK(cudaMemsetAsync(ctx->q_lo.p, 0, 2 * sizeof(uint32_t), st));
+        pp.q_absmax = ctx->q_lo.as<uint32_t>();
+    }
     {
         const int warps = 8;
         kge_rank_prepare_kernel<<<(unsigned)((T + warps - 1) / warps), warps * 32, 0, st>>>(pp);
@@ -776,7 +806,7 @@ static int rank_counts_impl(kge_ctx* ctx, int model, int k, const kge_table* ent
         KGE_REQUIRE(trilinear, "kge_rank_counts: the tensor-core sweep covers DistMult/ComplEx/HolE; TransE uses the fp32 sweep");
         int side_mask = side == KGE_RANK_O ? 1 : (side == KGE_RANK_S ? 2 : 3);
         return kge_rank_sweep_tc(ctx, model, K, pp.q, 2 * T, T, ent_local, row_begin, row_end, test, pp.pos_q, pp.excl_lo,
-                                 pp.excl_hi, ctx->f_sp_ent.as<int32_t>(), ctx->f_po_ent.as<int32_t>(), side_mask, counts, st);
+                                 pp.excl_hi, ctx->f_sp_ent.as<int32_t>(), ctx->f_po_ent.as<int32_t>(), side_mask, counts, pp.q_absmax, st);
     }
     SweepParams sp;
     sp.model = model;

@@ -10,15 +10,17 @@
 // inverse of the two scales.  KGE_RANK_TF32=1 selects the round-1 3xTF32 operands (A/B).
 //
 // One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) of the 4 operand tiles of a k-block
-//                              (Qhi,Qlo: 128 rows x 128 bytes; Ehi,Elo: 256 rows x 128 bytes) into a 2-stage smem ring
-//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1, M=128 N=256, K=16 (f16) / 8 (tf32) per instruction, 12 MMAs per
-//                              stage, accumulator = 128 lanes x 256 columns of TMEM, double buffered (512 cols)
+//   warp 0      TMA producer : cp.async.bulk.tensor (swizzled) of the 4 operand tiles of a k-block (Qhi,Qlo: 128 rows,
+//                              Ehi,Elo: 256 rows, one swizzle row wide) into a smem ring of 2 x 96 KB or 4 x 48 KB (TcCfg)
+//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1, M=128 N=256, K=16 (f16) / 8 (tf32) per instruction, 3 MMAs per
+//                              k-step, accumulator = 128 lanes x 256 columns of TMEM, double buffered (512 cols).  The
+//                              k-steps that lie wholly in the zero padding behind K are not issued (K = 400: 25 of 28).
 //   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 -> each thread owns ONE query row and 32 candidate
 //                              scores; x1e5 int truncation (F7), compare with the positive's quantised
 //                              score, filter bitmask from the sorted known-triple list, popcount into the
 //                              four per-row counters.  The [T,2E] score matrix never leaves the SM.
-// The epilogue of tile i overlaps the MMAs of tile i+1.
+// The epilogue of tile i overlaps the MMAs of tile i+1.  Work split: the (query tile, entity tile) pairs in query-major
+// order, cut into one contiguous range per CTA (ranges differ by at most one tile).
 //
 // Replaces reference models/EmbeddingModel.py:1856-1866 (score all corruptions), :1942-1986 (filter +
 // rank) and :1989-2033 (perform_comparision) for the trilinear models.
@@ -30,13 +32,24 @@
 
 #define TC_BM 128
 #define TC_BN 256
-#define TC_BK 32   // 4-byte slots per k-block = 128 bytes = one SWIZZLE_128B row (32 tf32 or 64 fp16 elements)
-#define TC_STAGES 2
-#define TC_A_BYTES (TC_BM * TC_BK * 4)   // 16 KB
-#define TC_B_BYTES (TC_BN * TC_BK * 4)   // 32 KB
-#define TC_STAGE_BYTES (2 * TC_A_BYTES + 2 * TC_B_BYTES)  // 96 KB
-#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 #define TC_THREADS 192
+
+// The k-block of a pipeline stage is one swizzle row wide: SWB = 128 bytes (64 fp16 / 32 tf32 columns, 4 MMA k-steps, 96 KB
+// per stage, 2 stages) or 64 bytes (32 fp16 columns, 2 k-steps, 48 KB per stage, 4 stages: three loads in flight behind the
+// block the tensor pipe is working on, which hides the TMA latency of the short last block of a K that is not a multiple
+// of the block width).
+#ifndef KGE_RANK_SW_DEFAULT
+#define KGE_RANK_SW_DEFAULT 128
+#endif
+template <int SWB>
+struct TcCfg {
+    static constexpr int STAGES = SWB == 128 ? 2 : 4;
+    static constexpr int KSTEPS = SWB / 32;                   // one MMA covers 32 bytes along K: 16 fp16 or 8 tf32
+    static constexpr int A_BYTES = TC_BM * SWB;               // 16 KB / 8 KB
+    static constexpr int B_BYTES = TC_BN * SWB;               // 32 KB / 16 KB
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -84,15 +97,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start address >> 4,
-// LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B) >> 4, version 1, layout 2.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+// K-major swizzled shared-memory matrix descriptor (sm_100 UMMA) of a tile whose rows are one swizzle row (SWB bytes) wide:
+// start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 8 rows x SWB bytes >> 4, version 1, layout type 2
+// (SWIZZLE_128B) or 4 (SWIZZLE_64B).
+template <int SWB>
+__device__ __forceinline__ uint64_t make_sw_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((8 * SWB) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(SWB == 128 ? 2 : 4) << 61;
     return d;
 }
 
@@ -122,10 +137,22 @@ __global__ void kge_tf32_split_kernel(const float* __restrict__ src, int64_t row
     }
 }
 
-// largest magnitude of an operand, as the bit pattern of a non-negative float (orders like an unsigned int)
+// largest magnitude of an operand, as the bit pattern of a non-negative float (orders like an unsigned int).
+// VEC: 16-byte loads (n a multiple of 4, src 16-byte aligned)
+template <bool VEC>
 __global__ void kge_absmax_kernel(const float* __restrict__ src, int64_t n, uint32_t* __restrict__ out) {
     float m = 0.f;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(src[t]));
+    if constexpr (VEC) {
+        const float4* __restrict__ s4 = reinterpret_cast<const float4*>(src);
+        const int64_t n4 = n >> 2;
+#pragma unroll 4
+        for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+            const float4 x = __ldg(s4 + t);
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+        }
+    } else {
+        for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(src[t]));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
@@ -140,24 +167,53 @@ __device__ __forceinline__ float split_scale(uint32_t absmax_bits) {
     return __uint_as_float((uint32_t)(127 + 13 - e) << 23);
 }
 
-// fp16 hi/lo split into zero-padded [2*rows_pad, Kp] halves (rows [0,rows_pad) hi, then lo)
+// fp16 hi/lo split into zero-padded [2*rows_pad, Kp] halves (rows [0,rows_pad) hi, then lo).  One thread per 8 consecutive
+// columns of a row (Kp is a multiple of 64): two 16-byte loads when VEC (K a multiple of 4, src 16-byte aligned), one
+// 16-byte store into each half.
+template <bool VEC>
 __global__ void kge_f16_split_kernel(const float* __restrict__ src, int64_t rows, int K, int Kp, int64_t rows_pad,
                                      const uint32_t* __restrict__ absmax, __half* __restrict__ dst) {
-    const int64_t total = rows_pad * (int64_t)Kp;
+    const int c8n = Kp >> 3;
+    const int64_t total8 = rows_pad * (int64_t)c8n;
     const float sc = split_scale(*absmax);
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = t / Kp;
-        const int c = (int)(t - r * Kp);
-        const float x = ((r < rows && c < K) ? src[r * (int64_t)K + c] : 0.f) * sc;  // exact: power of two
-        const __half hi = __float2half_rn(x);
-        dst[t] = hi;
-        dst[total + t] = __float2half_rn(x - __half2float(hi));
+    uint4* __restrict__ d_hi = reinterpret_cast<uint4*>(dst);
+    uint4* __restrict__ d_lo = reinterpret_cast<uint4*>(dst + rows_pad * (int64_t)Kp);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total8; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / c8n;
+        const int c = (int)(t - r * c8n) << 3;
+        float x[8];
+        if (r < rows && c < K) {
+            const float* __restrict__ row = src + r * (int64_t)K + c;
+            if (VEC && c + 8 <= K) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(row)), b = __ldg(reinterpret_cast<const float4*>(row) + 1);
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+                x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = c + i < K ? row[i] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = 0.f;
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float x0 = x[2 * i] * sc, x1 = x[2 * i + 1] * sc;  // exact: power of two
+            const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+            const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+            h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        d_hi[t] = make_uint4(h[0], h[1], h[2], h[3]);
+        d_lo[t] = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
 struct TcParams {
     const uint32_t* absmax;  // [2]: bit patterns of max|Q|, max|Ent| (fp16 split: the epilogue undoes the two scales)
     int k_blocks;
+    int tail_mmas;    // MMA k-steps of the LAST k-block that hold real columns (the rest of the block is zero padding: skipped)
     int64_t M;        // query rows handled (after side selection)
     int64_t Mp, Np;   // padded row counts of the split operands
     int64_t T;
@@ -170,14 +226,16 @@ struct TcParams {
     const int32_t* sp_ent;
     const int32_t* po_ent;
     int32_t* counts;
-    int n_m_tiles, n_n_tiles, nsplit;
+    int n_m_tiles, n_n_tiles;
     int nl;  // KGE_NL_*: non-linearity applied to the scores before the quantisation
 };
 
-template <bool F16>
+template <bool F16, int SWB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE, TcParams P) {
     extern __shared__ uint8_t smem_raw[];
+    using C = TcCfg<SWB>;
+    constexpr int TC_STAGES = C::STAGES, TC_STAGE_BYTES = C::STAGE_BYTES, TC_A_BYTES = C::A_BYTES, TC_B_BYTES = C::B_BYTES;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* full = bars;                    // [TC_STAGES]
@@ -213,33 +271,36 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_units = P.n_m_tiles * P.nsplit;
-    const int tiles_per_split = (P.n_n_tiles + P.nsplit - 1) / P.nsplit;
+    // work split: the (query tile, entity tile) pairs in query-major order, one contiguous range per CTA -- the CTAs differ
+    // by at most one tile; a range crosses a query-tile boundary a few times at most, where the epilogue flushes its row
+    const int64_t n_tiles = (int64_t)P.n_m_tiles * P.n_n_tiles;
+    const int64_t tile0 = n_tiles * blockIdx.x / gridDim.x, tile1 = n_tiles * (blockIdx.x + 1) / gridDim.x;
+    const int mt_first = (int)(tile0 / P.n_n_tiles), nt_first = (int)(tile0 - (int64_t)mt_first * P.n_n_tiles);
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const int mt = u / P.nsplit, sp = u - mt * P.nsplit;
-                const int nt0 = sp * tiles_per_split, nt1 = min(P.n_n_tiles, nt0 + tiles_per_split);
-                const int m0 = mt * TC_BM;
-                for (int nt = nt0; nt < nt1; ++nt) {
-                    const int n0 = nt * TC_BN;
-                    for (int kb = 0; kb < P.k_blocks; ++kb) {
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* st = smem + (size_t)stage * TC_STAGE_BYTES;
-                        mbar_expect_tx(&full[stage], TC_STAGE_BYTES);
-                        constexpr int KB_ELEMS = F16 ? 64 : 32;  // elements per 128-byte k-block (TMA coordinates count elements)
-                        tma_load_2d(st, &tmQ, kb * KB_ELEMS, m0, &full[stage]);
-                        tma_load_2d(st + TC_A_BYTES, &tmQ, kb * KB_ELEMS, (int)P.Mp + m0, &full[stage]);
-                        tma_load_2d(st + 2 * TC_A_BYTES, &tmE, kb * KB_ELEMS, n0, &full[stage]);
-                        tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmE, kb * KB_ELEMS, (int)P.Np + n0, &full[stage]);
-                        if (++stage == TC_STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+            int mt = mt_first, nt = nt_first;
+            for (int64_t tile = tile0; tile < tile1; ++tile) {
+                const int m0 = mt * TC_BM, n0 = nt * TC_BN;
+                for (int kb = 0; kb < P.k_blocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* st = smem + (size_t)stage * TC_STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], TC_STAGE_BYTES);
+                    constexpr int KB_ELEMS = SWB / (F16 ? 2 : 4);  // columns per k-block (TMA coordinates count elements)
+                    tma_load_2d(st, &tmQ, kb * KB_ELEMS, m0, &full[stage]);
+                    tma_load_2d(st + TC_A_BYTES, &tmQ, kb * KB_ELEMS, (int)P.Mp + m0, &full[stage]);
+                    tma_load_2d(st + 2 * TC_A_BYTES, &tmE, kb * KB_ELEMS, n0, &full[stage]);
+                    tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmE, kb * KB_ELEMS, (int)P.Np + n0, &full[stage]);
+                    if (++stage == TC_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
                     }
+                }
+                if (++nt == P.n_n_tiles) {
+                    nt = 0;
+                    ++mt;
                 }
             }
         }
@@ -249,37 +310,37 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             uint32_t tile_it = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const int mt = u / P.nsplit, sp = u - mt * P.nsplit;
-                const int nt0 = sp * tiles_per_split, nt1 = min(P.n_n_tiles, nt0 + tiles_per_split);
-                for (int nt = nt0; nt < nt1; ++nt, ++tile_it) {
-                    const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
-                    mbar_wait(&tempty[as], aphase ^ 1);
+            for (int64_t tile = tile0; tile < tile1; ++tile, ++tile_it) {
+                const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
+                mbar_wait(&tempty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * TC_BN;
+                for (int kb = 0; kb < P.k_blocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + as * TC_BN;
-                    for (int kb = 0; kb < P.k_blocks; ++kb) {
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + (size_t)stage * TC_STAGE_BYTES);
-                        const uint64_t a_hi = make_sw128_desc(sa);
-                        const uint64_t a_lo = make_sw128_desc(sa + TC_A_BYTES);
-                        const uint64_t b_hi = make_sw128_desc(sa + 2 * TC_A_BYTES);
-                        const uint64_t b_lo = make_sw128_desc(sa + 2 * TC_A_BYTES + TC_B_BYTES);
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * TC_STAGE_BYTES);
+                    const uint64_t a_hi = make_sw_desc<SWB>(sa);
+                    const uint64_t a_lo = make_sw_desc<SWB>(sa + TC_A_BYTES);
+                    const uint64_t b_hi = make_sw_desc<SWB>(sa + 2 * TC_A_BYTES);
+                    const uint64_t b_lo = make_sw_desc<SWB>(sa + 2 * TC_A_BYTES + TC_B_BYTES);
+                    // the zero-padded columns behind K add exact zeros: their k-steps are not issued
+                    const int nj = kb + 1 == P.k_blocks ? P.tail_mmas : C::KSTEPS;
 #pragma unroll
-                        for (int j = 0; j < TC_BK / 8; ++j) {
+                    for (int j = 0; j < C::KSTEPS; ++j) {
+                        if (j < nj) {
                             const uint64_t off = (uint64_t)(j * 32 >> 4);  // one MMA = 32 bytes along K: 8 tf32 or 16 fp16
                             tc_mma<F16>(d_tmem, a_lo + off, b_hi + off, idesc, (kb | j) != 0);
                             tc_mma<F16>(d_tmem, a_hi + off, b_lo + off, idesc, 1);
                             tc_mma<F16>(d_tmem, a_hi + off, b_hi + off, idesc, 1);
                         }
-                        tc_commit(&empty[stage]);  // smem stage reusable once these MMAs retire
-                        if (++stage == TC_STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
                     }
-                    tc_commit(&tfull[as]);  // accumulator complete
+                    tc_commit(&empty[stage]);  // smem stage reusable once these MMAs retire
+                    if (++stage == TC_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
+                tc_commit(&tfull[as]);  // accumulator complete
             }
         }
     } else {
@@ -290,35 +351,41 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // inverses is exact, and so is the multiplication unless the score is subnormal)
         const float unscale = F16 ? 1.f / (split_scale(P.absmax[0]) * split_scale(P.absmax[1])) : 1.f;
         uint32_t tile_it = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const int mt = u / P.nsplit, sp = u - mt * P.nsplit;
-            const int nt0 = sp * tiles_per_split, nt1 = min(P.n_n_tiles, nt0 + tiles_per_split);
-            const int64_t m = (int64_t)mt * TC_BM + row_in_tile;
-            const bool row_ok = m < P.M;
-            int32_t pq = 0, self = -1, cur = 0, hi = 0;
-            const int32_t* list = nullptr;
-            int64_t tt = 0;
-            int side = 0;
-            const int64_t e_first = P.row_begin + (int64_t)nt0 * TC_BN;
-            if (row_ok) {
-                const int64_t r = P.q_row0 + m;
-                side = r >= P.T ? 1 : 0;
-                tt = r - (int64_t)side * P.T;
-                self = side == 0 ? P.test[3 * tt + 2] : P.test[3 * tt + 0];
-                pq = P.pos_q[tt];
-                list = side == 0 ? P.sp_ent : P.po_ent;
-                int32_t a = P.excl_lo[r], b = P.excl_hi[r];
-                hi = b;
-                while (a < b) {  // first known entity >= first candidate of this unit
-                    int32_t mid = (a + b) >> 1;
-                    if ((int64_t)list[mid] < e_first) a = mid + 1;
-                    else b = mid;
+        int mt = mt_first, nt = nt_first;
+        bool fresh = true;  // a new query tile starts: this thread's row state is set up before its first entity tile
+        bool row_ok = false;
+        int32_t pq = 0, self = -1, cur = 0, hi = 0;
+        const int32_t* list = nullptr;
+        int64_t tt = 0, next_f = (int64_t)1 << 40;
+        int side = 0;
+        int c_gt = 0, c_eq = 0, c_gtf = 0, c_eqf = 0;
+        for (int64_t tile = tile0; tile < tile1; ++tile, ++tile_it) {
+            if (fresh) {
+                fresh = false;
+                const int64_t m = (int64_t)mt * TC_BM + row_in_tile;
+                row_ok = m < P.M;
+                pq = 0; self = -1; cur = 0; hi = 0;
+                c_gt = c_eq = c_gtf = c_eqf = 0;
+                if (row_ok) {
+                    const int64_t e_first = P.row_begin + (int64_t)nt * TC_BN;
+                    const int64_t r = P.q_row0 + m;
+                    side = r >= P.T ? 1 : 0;
+                    tt = r - (int64_t)side * P.T;
+                    self = side == 0 ? P.test[3 * tt + 2] : P.test[3 * tt + 0];
+                    pq = P.pos_q[tt];
+                    list = side == 0 ? P.sp_ent : P.po_ent;
+                    int32_t a = P.excl_lo[r], b = P.excl_hi[r];
+                    hi = b;
+                    while (a < b) {  // first known entity >= first candidate of this range
+                        int32_t mid = (a + b) >> 1;
+                        if ((int64_t)list[mid] < e_first) a = mid + 1;
+                        else b = mid;
+                    }
+                    cur = a;
                 }
-                cur = a;
+                next_f = (cur < hi) ? (int64_t)list[cur] : (int64_t)1 << 40;
             }
-            int64_t next_f = (cur < hi) ? (int64_t)list[cur] : (int64_t)1 << 40;
-            int c_gt = 0, c_eq = 0, c_gtf = 0, c_eqf = 0;
-            for (int nt = nt0; nt < nt1; ++nt, ++tile_it) {
+            {
                 const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
                 mbar_wait(&tfull[as], aphase);
                 tc_fence_after();
@@ -366,7 +433,12 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
             }
-            if (row_ok) {
+            if (++nt == P.n_n_tiles) {
+                nt = 0;
+                ++mt;
+                fresh = true;
+            }
+            if ((fresh || tile + 1 == tile1) && row_ok) {  // last entity tile of this row in this CTA's range
                 int32_t* dst = P.counts + (tt * 2 + side) * 4;
                 if (c_gt) atomicAdd(dst + 0, c_gt);
                 if (c_eq) atomicAdd(dst + 1, c_eq);
@@ -398,26 +470,46 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_tensormap_encoder() {
     return fn;
 }
 
-// 2-D row-major [rows, Kp] (fp32, or fp16 when f16) with a (128 bytes x box_rows) box and the 128-byte swizzle
-static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int Kp, int box_rows, bool f16) {
+// 2-D row-major [rows, Kp] (fp32, or fp16 when f16) with a (swb bytes x box_rows) box and the swb-byte swizzle (128 or 64)
+static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int Kp, int box_rows, bool f16, int swb) {
     auto enc = get_tensormap_encoder();
     KGE_REQUIRE(enc != nullptr, "kge_rank_counts: cuTensorMapEncodeTiled unavailable in this driver");
     const size_t esz = f16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)Kp * esz};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(swb / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     KGE_REQUIRE(r == CUDA_SUCCESS, "kge_rank_counts: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
+}
+
+// KGE_RANK_SW=128|64: width in bytes of a pipeline stage's k-block (TcCfg); the 3xTF32 A/B path keeps 128
+static int rank_tc_swb() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KGE_RANK_SW");
+        v = (e != nullptr && atoi(e) == 64) ? 64 : ((e != nullptr && atoi(e) == 128) ? 128 : KGE_RANK_SW_DEFAULT);
+    }
+    return v;
+}
+
+// KGE_RANK_TF32=1: the round-1 3xTF32 operands (A/B); default: the fp16 split
+bool kge_rank_tc_f16() {
+    static int use_tf32 = -1;
+    if (use_tf32 < 0) {
+        const char* e = getenv("KGE_RANK_TF32");
+        use_tf32 = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return use_tf32 == 0;
 }
 
 int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ, int64_t T, const float* ent_local,
                       int64_t row_begin, int64_t row_end, const int32_t* test, const int32_t* pos_q,
                       const int32_t* excl_lo, const int32_t* excl_hi, const int32_t* sp_ent, const int32_t* po_ent,
-                      int side_mask, int32_t* counts, cudaStream_t st) {
+                      int side_mask, int32_t* counts, const uint32_t* q_absmax, cudaStream_t st) {
     (void)model;
     (void)NQ;
     const int64_t n_local = row_end - row_begin;
@@ -428,14 +520,10 @@ int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ
         q_row0 = T;
         M = T;
     }
-    static int use_tf32 = -1;  // KGE_RANK_TF32=1: the round-1 3xTF32 operands (A/B)
-    if (use_tf32 < 0) {
-        const char* e = getenv("KGE_RANK_TF32");
-        use_tf32 = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
-    const bool f16 = use_tf32 == 0;
-    const int kb_elems = f16 ? 64 : 32;  // elements per 128-byte k-block
+    const bool f16 = kge_rank_tc_f16();
     const size_t esz = f16 ? 2 : 4;
+    const int swb = f16 ? rank_tc_swb() : 128;
+    const int kb_elems = swb / (int)esz;  // columns per k-block: 64 / 32 fp16, 32 tf32
     const int Kp = ((K + kb_elems - 1) / kb_elems) * kb_elems;
     const int64_t Mp = ((M + TC_BM - 1) / TC_BM) * TC_BM;
     const int64_t Np = ((n_local + TC_BN - 1) / TC_BN) * TC_BN;
@@ -446,28 +534,50 @@ int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ
     uint32_t* absmax = ctx->q_lo.as<uint32_t>();
     {
         int threads = 256;
-        int64_t tot = Mp * Kp;
-        int blocks = (int)std::min<int64_t>((tot + threads - 1) / threads, (int64_t)ctx->sm_count * 32);
-        int64_t tot_e = Np * Kp;
-        int blocks_e = (int)std::min<int64_t>((tot_e + threads - 1) / threads, (int64_t)ctx->sm_count * 32);
+        const float* q0 = q + (size_t)q_row0 * K;
         if (f16) {
-            KGE_CUDA_CHECK(cudaMemsetAsync(absmax, 0, 2 * sizeof(uint32_t), st));
-            kge_absmax_kernel<<<std::min(blocks, ctx->sm_count * 8), threads, 0, st>>>(q + (size_t)q_row0 * K, M * (int64_t)K, absmax);
-            kge_absmax_kernel<<<std::min(blocks_e, ctx->sm_count * 8), threads, 0, st>>>(ent_local, n_local * (int64_t)K, absmax + 1);
-            kge_f16_split_kernel<<<blocks, threads, 0, st>>>(q + (size_t)q_row0 * K, M, K, Kp, Mp, absmax, ctx->q_hi.as<__half>());
-            kge_f16_split_kernel<<<blocks_e, threads, 0, st>>>(ent_local, n_local, K, Kp, Np, absmax + 1, ctx->e_hi.as<__half>());
+            // [0]: max|Q| -- already there when the caller folded the queries with q_absmax (same buffer); [1]: max|Ent|
+            const bool vq = (K & 3) == 0 && ((uintptr_t)q0 & 15) == 0, ve = (K & 3) == 0 && ((uintptr_t)ent_local & 15) == 0;
+            const int64_t nq = M * (int64_t)K, ne = n_local * (int64_t)K;
+            const int64_t cap = (int64_t)ctx->sm_count * 8;
+            if (q_absmax == nullptr) {
+                KGE_CUDA_CHECK(cudaMemsetAsync(absmax, 0, 2 * sizeof(uint32_t), st));
+                const int bq = (int)std::max<int64_t>(1, std::min(((vq ? nq >> 2 : nq) + threads * 4 - 1) / (threads * 4), cap));
+                if (vq) kge_absmax_kernel<true><<<bq, threads, 0, st>>>(q0, nq, absmax);
+                else kge_absmax_kernel<false><<<bq, threads, 0, st>>>(q0, nq, absmax);
+            } else {
+                KGE_REQUIRE(q_absmax == absmax, "kge_rank_sweep_tc: the query maximum must sit in the context's scale buffer");
+            }
+            const int be = (int)std::max<int64_t>(1, std::min(((ve ? ne >> 2 : ne) + threads * 4 - 1) / (threads * 4), cap));
+            if (ve) kge_absmax_kernel<true><<<be, threads, 0, st>>>(ent_local, ne, absmax + 1);
+            else kge_absmax_kernel<false><<<be, threads, 0, st>>>(ent_local, ne, absmax + 1);
+            const int64_t tq8 = Mp * (int64_t)(Kp >> 3), te8 = Np * (int64_t)(Kp >> 3);
+            const int bsq = (int)std::min<int64_t>((tq8 + threads - 1) / threads, (int64_t)ctx->sm_count * 32);
+            const int bse = (int)std::min<int64_t>((te8 + threads - 1) / threads, (int64_t)ctx->sm_count * 32);
+            if (vq) kge_f16_split_kernel<true><<<bsq, threads, 0, st>>>(q0, M, K, Kp, Mp, absmax, ctx->q_hi.as<__half>());
+            else kge_f16_split_kernel<false><<<bsq, threads, 0, st>>>(q0, M, K, Kp, Mp, absmax, ctx->q_hi.as<__half>());
+            if (ve) kge_f16_split_kernel<true><<<bse, threads, 0, st>>>(ent_local, n_local, K, Kp, Np, absmax + 1, ctx->e_hi.as<__half>());
+            else kge_f16_split_kernel<false><<<bse, threads, 0, st>>>(ent_local, n_local, K, Kp, Np, absmax + 1, ctx->e_hi.as<__half>());
         } else {
-            kge_tf32_split_kernel<<<blocks, threads, 0, st>>>(q + (size_t)q_row0 * K, M, K, Kp, Mp, ctx->q_hi.as<float>());
+            int64_t tot = Mp * Kp;
+            int blocks = (int)std::min<int64_t>((tot + threads - 1) / threads, (int64_t)ctx->sm_count * 32);
+            int64_t tot_e = Np * Kp;
+            int blocks_e = (int)std::min<int64_t>((tot_e + threads - 1) / threads, (int64_t)ctx->sm_count * 32);
+            kge_tf32_split_kernel<<<blocks, threads, 0, st>>>(q0, M, K, Kp, Mp, ctx->q_hi.as<float>());
             kge_tf32_split_kernel<<<blocks_e, threads, 0, st>>>(ent_local, n_local, K, Kp, Np, ctx->e_hi.as<float>());
         }
         KGE_CUDA_CHECK(cudaGetLastError());
     }
     CUtensorMap tmQ, tmE;
-    if (int rc = make_tmap(&tmQ, ctx->q_hi.p, 2 * Mp, Kp, TC_BM, f16)) return rc;
-    if (int rc = make_tmap(&tmE, ctx->e_hi.p, 2 * Np, Kp, TC_BN, f16)) return rc;
+    if (int rc = make_tmap(&tmQ, ctx->q_hi.p, 2 * Mp, Kp, TC_BM, f16, swb)) return rc;
+    if (int rc = make_tmap(&tmE, ctx->e_hi.p, 2 * Np, Kp, TC_BN, f16, swb)) return rc;
 
     TcParams P;
     P.k_blocks = Kp / kb_elems;
+    {
+        const int mma_k = 32 / (int)esz;  // columns per MMA k-step: 16 fp16 or 8 tf32
+        P.tail_mmas = (K - (P.k_blocks - 1) * kb_elems + mma_k - 1) / mma_k;
+    }
     P.absmax = absmax;
     P.M = M;
     P.Mp = Mp;
@@ -485,21 +595,18 @@ int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ
     P.counts = counts;
     P.n_m_tiles = (int)(Mp / TC_BM);
     P.n_n_tiles = (int)(Np / TC_BN);
-    // enough work units for ~12 rounds over the SMs, each unit at least 2 entity tiles when possible
-    int nsplit = (int)std::max<int64_t>(1, ((int64_t)ctx->sm_count * 12 + P.n_m_tiles - 1) / P.n_m_tiles);
-    nsplit = std::min(nsplit, std::max(1, P.n_n_tiles / 2));
-    P.nsplit = nsplit;
     P.nl = ctx->rank_nl;
-    const int n_units = P.n_m_tiles * nsplit;
-    const int grid = std::min(n_units, ctx->sm_count);
+    const int grid = (int)std::min<int64_t>((int64_t)P.n_m_tiles * P.n_n_tiles, (int64_t)ctx->sm_count);
     static bool attr_set = false;
     if (!attr_set) {
-        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
+        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES));
+        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
         attr_set = true;
     }
-    if (f16) kge_rank_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmQ, tmE, P);
-    else kge_rank_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tmQ, tmE, P);
+    if (!f16) kge_rank_tc_kernel<false, 128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(tmQ, tmE, P);
+    else if (swb == 128) kge_rank_tc_kernel<true, 128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(tmQ, tmE, P);
+    else kge_rank_tc_kernel<true, 64><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(tmQ, tmE, P);
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
