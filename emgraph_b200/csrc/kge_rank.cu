@@ -194,7 +194,9 @@ __global__ void kge_rank_prepare_kernel(PrepParams P) {
         float m = fmaxf((P.amax_mask & 1) ? mo : 0.f, (P.amax_mask & 2) ? ms : 0.f);
 #pragma unroll
         for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o2));
-        if (lane == 0 && m > 0.f) atomicMax(P.q_absmax, __float_as_uint(m));
+        // the running maximum settles after a few warps: most warps see that theirs is not larger and skip the atomic
+        // (a stale read only costs an atomic that changes nothing)
+        if (lane == 0 && m > 0.f && __float_as_uint(m) > *(volatile uint32_t*)P.q_absmax) atomicMax(P.q_absmax, __float_as_uint(m));
     }
     if (lane == 0) P.pos_q[t] = quantise_score(apply_nl(P.nl, acc));
     if (lane < 2) {

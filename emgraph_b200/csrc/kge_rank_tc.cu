@@ -15,8 +15,10 @@
 //   warp 1      MMA issuer   : tcgen05.mma.cta_group::1, M=128 N=256, K=16 (f16) / 8 (tf32) per instruction, 3 MMAs per
 //                              k-step, accumulator = 128 lanes x 256 columns of TMEM, double buffered (512 cols).  The
 //                              k-steps that lie wholly in the zero padding behind K are not issued (K = 400: 25 of 28).
-//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 -> each thread owns ONE query row and 32 candidate
-//                              scores; x1e5 int truncation (F7), compare with the positive's quantised
+//   warps 2..9  epilogue     : two warps per TMEM lane quarter, each owning half of the tile's columns (with one warp per
+//                              scheduler the epilogue of a tile took longer than its MMAs: ~3.5 K dependent instructions
+//                              at 0.3 IPC, measured r2ra); tcgen05.ld 32x32b.x32 -> each thread owns ONE query row and 32
+//                              candidate scores; x1e5 int truncation (F7), compare with the positive's quantised
 //                              score, filter bitmask from the sorted known-triple list, popcount into the
 //                              four per-row counters.  The [T,2E] score matrix never leaves the SM.
 // The epilogue of tile i overlaps the MMAs of tile i+1.  Work split: the (query tile, entity tile) pairs in query-major
@@ -32,14 +34,16 @@
 
 #define TC_BM 128
 #define TC_BN 256
-#define TC_THREADS 192
+// epilogue warps EW: 8 = two per TMEM lane quarter, each owning half of the tile's columns (default); 4 = one per quarter
+// (KGE_RANK_EW=4, the round-2 kernel, kept for A/B)
+#define TC_THREADS_MAX (64 + 32 * 8)
 
 // The k-block of a pipeline stage is one swizzle row wide: SWB = 128 bytes (64 fp16 / 32 tf32 columns, 4 MMA k-steps, 96 KB
 // per stage, 2 stages) or 64 bytes (32 fp16 columns, 2 k-steps, 48 KB per stage, 4 stages: three loads in flight behind the
 // block the tensor pipe is working on, which hides the TMA latency of the short last block of a K that is not a multiple
 // of the block width).
 #ifndef KGE_RANK_SW_DEFAULT
-#define KGE_RANK_SW_DEFAULT 128
+#define KGE_RANK_SW_DEFAULT 64
 #endif
 template <int SWB>
 struct TcCfg {
@@ -155,7 +159,7 @@ __global__ void kge_absmax_kernel(const float* __restrict__ src, int64_t n, uint
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0 && m > 0.f && __float_as_uint(m) > *(volatile uint32_t*)out) atomicMax(out, __float_as_uint(m));
 }
 
 // power of two that brings the operand's largest magnitude into [2^13, 2^14): the low halves of elements down to
@@ -230,8 +234,8 @@ struct TcParams {
     int nl;  // KGE_NL_*: non-linearity applied to the scores before the quantisation
 };
 
-template <bool F16, int SWB>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool F16, int SWB, int TC_EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * TC_EPI_WARPS, 1)
 kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE, TcParams P) {
     extern __shared__ uint8_t smem_raw[];
     using C = TcCfg<SWB>;
@@ -258,7 +262,7 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&tfull[b], 1);
-                mbar_init(&tempty[b], 4);  // one arrive per epilogue warp
+                mbar_init(&tempty[b], TC_EPI_WARPS);  // one arrive per epilogue warp
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -347,6 +351,9 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
         const int quarter = warp & 3;
         const int row_in_tile = quarter * 32 + lane;
+        // the warps of one quarter split the tile's columns: this warp owns 32-column chunks [c_begin, c_end) of every tile
+        constexpr int CHUNKS = TC_BN / 32, PER_WARP = CHUNKS / (TC_EPI_WARPS / 4);
+        const int c_begin = ((warp - 2) >> 2) * PER_WARP, c_end = c_begin + PER_WARP;
         // fp16 split: the accumulator holds the score times the two operand scales (powers of two: the product of their
         // inverses is exact, and so is the multiplication unless the score is subnormal)
         const float unscale = F16 ? 1.f / (split_scale(P.absmax[0]) * split_scale(P.absmax[1])) : 1.f;
@@ -367,7 +374,7 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 pq = 0; self = -1; cur = 0; hi = 0;
                 c_gt = c_eq = c_gtf = c_eqf = 0;
                 if (row_ok) {
-                    const int64_t e_first = P.row_begin + (int64_t)nt * TC_BN;
+                    const int64_t e_first = P.row_begin + (int64_t)nt * TC_BN + c_begin * 32;
                     const int64_t r = P.q_row0 + m;
                     side = r >= P.T ? 1 : 0;
                     tt = r - (int64_t)side * P.T;
@@ -391,7 +398,7 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * TC_BN;
 #pragma unroll 1
-                for (int c = 0; c < TC_BN / 32; ++c) {
+                for (int c = c_begin; c < c_end; ++c) {
                     uint32_t v[32];
                     tc_ld32(taddr + c * 32, v);
                     tc_wait_ld();
@@ -597,16 +604,23 @@ int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ
     P.n_n_tiles = (int)(Np / TC_BN);
     P.nl = ctx->rank_nl;
     const int grid = (int)std::min<int64_t>((int64_t)P.n_m_tiles * P.n_n_tiles, (int64_t)ctx->sm_count);
-    static bool attr_set = false;
-    if (!attr_set) {
-        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
-        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES));
-        KGE_CUDA_CHECK(cudaFuncSetAttribute(kge_rank_tc_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
-        attr_set = true;
+    static int ew = -1;  // KGE_RANK_EW=4|8 epilogue warps
+    if (ew < 0) {
+        const char* e = getenv("KGE_RANK_EW");
+        ew = (e != nullptr && atoi(e) == 4) ? 4 : 8;
     }
-    if (!f16) kge_rank_tc_kernel<false, 128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(tmQ, tmE, P);
-    else if (swb == 128) kge_rank_tc_kernel<true, 128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(tmQ, tmE, P);
-    else kge_rank_tc_kernel<true, 64><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, st>>>(tmQ, tmE, P);
+    auto go = [&](auto kern, int smem, int threads) -> int {
+        KGE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, threads, smem, st>>>(tmQ, tmE, P);
+        return 0;
+    };
+    int rc;
+    if (!f16) rc = go(kge_rank_tc_kernel<false, 128, 8>, TcCfg<128>::SMEM_BYTES, 64 + 32 * 8);
+    else if (swb == 128) rc = ew == 4 ? go(kge_rank_tc_kernel<true, 128, 4>, TcCfg<128>::SMEM_BYTES, 64 + 32 * 4)
+                                      : go(kge_rank_tc_kernel<true, 128, 8>, TcCfg<128>::SMEM_BYTES, 64 + 32 * 8);
+    else rc = ew == 4 ? go(kge_rank_tc_kernel<true, 64, 4>, TcCfg<64>::SMEM_BYTES, 64 + 32 * 4)
+                      : go(kge_rank_tc_kernel<true, 64, 8>, TcCfg<64>::SMEM_BYTES, 64 + 32 * 8);
+    if (rc) return rc;
     KGE_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
