@@ -1002,6 +1002,10 @@ def bench_rank(args, w, eng, model, f, X, test, peaks):
     n = max(1, args.rank_steps) * inner_repeat(max(1, args.rank_steps), e0.elapsed_time(e1))
     l0 = eng.launches
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n)]
+    # the tensor-core sweep runs into the board's power cap (sw_power_cap, SM clock ~1.55 GHz): the ranking record carries
+    # the clocks and reasons of ITS timed region, the top-level "clocks" are those of the training steps
+    rank_sampler = ClockSampler(dev.index or 0)
+    rank_sampler.start()
     for s in range(n):
         flush.fill_(float(s))
         evs[s][0].record()
@@ -1010,6 +1014,7 @@ def bench_rank(args, w, eng, model, f, X, test, peaks):
         ranks = eng.rank_finalize(counts, side=0, strategy=0, filtered=True)
         evs[s][2].record()
     torch.cuda.synchronize()
+    rank_clocks = rank_sampler.stop()
     launches = eng.launches - l0
     t_ms = sum(e[0].elapsed_time(e[2]) for e in evs) / n
     t_sweep_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / n
@@ -1052,7 +1057,7 @@ def bench_rank(args, w, eng, model, f, X, test, peaks):
             "corrupt_side": "s,o", "filter_triples": int(X.shape[0]), "filter_build_ms": 1e3 * t_filter, "tensor_cores": bool(use_tc),
             "mrr": mrr, "e2e": {"value": T / t_e2e, "unit": "test triples/s", "h2d_bytes_per_step": T * 12, "d2h_bytes_per_step": T * 8,
                                 "api": "EmbeddingModel.get_ranks -> kge_rank_host"},
-            "gpu_launches": launches, "roofline": roof}
+            "gpu_launches": launches, "roofline": roof, "clocks": rank_clocks}
 
 
 if __name__ == "__main__":
