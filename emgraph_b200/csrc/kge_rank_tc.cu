@@ -42,6 +42,9 @@
 // per stage, 2 stages) or 64 bytes (32 fp16 columns, 2 k-steps, 48 KB per stage, 4 stages: three loads in flight behind the
 // block the tensor pipe is working on, which hides the TMA latency of the short last block of a K that is not a multiple
 // of the block width).
+#ifndef KGE_RANK_GROUP_DEFAULT
+#define KGE_RANK_GROUP_DEFAULT 1
+#endif
 #ifndef KGE_RANK_SW_DEFAULT
 #define KGE_RANK_SW_DEFAULT 64
 #endif
@@ -231,6 +234,7 @@ struct TcParams {
     const int32_t* po_ent;
     int32_t* counts;
     int n_m_tiles, n_n_tiles;
+    int group;  // CTAs that share a tile range (1: every CTA has its own)
     int nl;  // KGE_NL_*: non-linearity applied to the scores before the quantisation
 };
 
@@ -277,8 +281,12 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     // work split: the (query tile, entity tile) pairs in query-major order, one contiguous range per CTA -- the CTAs differ
     // by at most one tile; a range crosses a query-tile boundary a few times at most, where the epilogue flushes its row
+    // P.group = G > 1 (KGE_RANK_GROUP): G neighbouring CTAs share a range and take its tiles in turn (CTA j: first + j, + G, ...),
+    // so that at any time they work on the same query tile and on adjacent entity tiles
     const int64_t n_tiles = (int64_t)P.n_m_tiles * P.n_n_tiles;
-    const int64_t tile0 = n_tiles * blockIdx.x / gridDim.x, tile1 = n_tiles * (blockIdx.x + 1) / gridDim.x;
+    const int tstep = P.group;
+    const int64_t n_groups = gridDim.x / tstep, gi = blockIdx.x / tstep;
+    const int64_t tile0 = n_tiles * gi / n_groups + (blockIdx.x - gi * tstep), tile1 = n_tiles * (gi + 1) / n_groups;
     const int mt_first = (int)(tile0 / P.n_n_tiles), nt_first = (int)(tile0 - (int64_t)mt_first * P.n_n_tiles);
 
     if (warp == 0) {
@@ -286,7 +294,7 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             int mt = mt_first, nt = nt_first;
-            for (int64_t tile = tile0; tile < tile1; ++tile) {
+            for (int64_t tile = tile0; tile < tile1; tile += tstep) {
                 const int m0 = mt * TC_BM, n0 = nt * TC_BN;
                 for (int kb = 0; kb < P.k_blocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -302,8 +310,9 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         phase ^= 1;
                     }
                 }
-                if (++nt == P.n_n_tiles) {
-                    nt = 0;
+                nt += tstep;
+                while (nt >= P.n_n_tiles) {
+                    nt -= P.n_n_tiles;
                     ++mt;
                 }
             }
@@ -314,7 +323,7 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             uint32_t tile_it = 0;
-            for (int64_t tile = tile0; tile < tile1; ++tile, ++tile_it) {
+            for (int64_t tile = tile0; tile < tile1; tile += tstep, ++tile_it) {
                 const uint32_t as = tile_it & 1, aphase = (tile_it >> 1) & 1;
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
@@ -366,7 +375,7 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         int64_t tt = 0, next_f = (int64_t)1 << 40;
         int side = 0;
         int c_gt = 0, c_eq = 0, c_gtf = 0, c_eqf = 0;
-        for (int64_t tile = tile0; tile < tile1; ++tile, ++tile_it) {
+        for (int64_t tile = tile0; tile < tile1; tile += tstep, ++tile_it) {
             if (fresh) {
                 fresh = false;
                 const int64_t m = (int64_t)mt * TC_BM + row_in_tile;
@@ -440,12 +449,13 @@ kge_rank_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
             }
-            if (++nt == P.n_n_tiles) {
-                nt = 0;
+            nt += tstep;
+            while (nt >= P.n_n_tiles) {
+                nt -= P.n_n_tiles;
                 ++mt;
                 fresh = true;
             }
-            if ((fresh || tile + 1 == tile1) && row_ok) {  // last entity tile of this row in this CTA's range
+            if ((fresh || tile + tstep >= tile1) && row_ok) {  // last entity tile of this row in this CTA's share
                 int32_t* dst = P.counts + (tt * 2 + side) * 4;
                 if (c_gt) atomicAdd(dst + 0, c_gt);
                 if (c_eq) atomicAdd(dst + 1, c_eq);
@@ -604,6 +614,13 @@ int kge_rank_sweep_tc(kge_ctx* ctx, int model, int K, const float* q, int64_t NQ
     P.n_n_tiles = (int)(Np / TC_BN);
     P.nl = ctx->rank_nl;
     const int grid = (int)std::min<int64_t>((int64_t)P.n_m_tiles * P.n_n_tiles, (int64_t)ctx->sm_count);
+    static int group = -1;  // KGE_RANK_GROUP=1|2|4
+    if (group < 0) {
+        const char* e = getenv("KGE_RANK_GROUP");
+        const int g = e != nullptr ? atoi(e) : KGE_RANK_GROUP_DEFAULT;
+        group = (g == 2 || g == 4) ? g : 1;
+    }
+    P.group = grid % group == 0 ? group : 1;
     static int ew = -1;  // KGE_RANK_EW=4|8 epilogue warps
     if (ew < 0) {
         const char* e = getenv("KGE_RANK_EW");
