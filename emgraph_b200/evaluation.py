@@ -68,7 +68,12 @@ class EvalDataset:
 def filter_unseen_entities(X, model, verbose=False):
     """evaluation/protocol.py:1014-1041: drop triples whose subject or object the model never saw."""
     X = np.asarray(X)
-    keep = model._ent_index.contains(X[:, 0]) & model._ent_index.contains(X[:, 2])
+    index = getattr(model, "_ent_index", None)
+    if index is not None:
+        keep = index.contains(X[:, 0]) & index.contains(X[:, 2])
+    else:  # anything that carries an ent_to_idx dictionary (the reference's own test passes a namedtuple)
+        known = np.array(list(model.ent_to_idx.keys()))
+        keep = np.isin(X[:, 0], known) & np.isin(X[:, 2], known)
     n_removed = int(X.shape[0] - keep.sum())
     if n_removed > 0:
         if verbose:
